@@ -1,0 +1,248 @@
+"""CPU ORACLE — test infrastructure, NOT product code.
+
+ctypes wrapper over oracle/liborb_oracle.so (built from oracle/orb_oracle.c by `make -C oracle`).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this package; pointslot_b200 never does.
+
+Parity status: "parity unpinned" by the reference (no tests, un-vendored OpenCV); the primitives are
+pinned against OpenCV 4.13.0 (tests/test_oracle_cv2.py, tests/golden/).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "liborb_oracle.so"
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+     ("octave", "<i4"), ("class_id", "<i4")]
+)
+assert KEYPOINT_DTYPE.itemsize == 28
+
+
+def build(force: bool = False) -> Path:
+    """Compile the C restatement (gcc, seconds)."""
+    src = _HERE / "orb_oracle.c"
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+        subprocess.check_call(["make", "-C", str(_HERE), "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            build()
+        L = C.CDLL(str(_LIB_PATH))
+        vp, ip, fp, u8p = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_void_p
+        L.orc_create.restype = vp
+        L.orc_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_destroy.argtypes = [vp]
+        for name in ("orc_scale_factors", "orc_inv_scale_factors", "orc_level_sigma2", "orc_inv_level_sigma2"):
+            getattr(L, name).restype = fp
+            getattr(L, name).argtypes = [vp]
+        for name in ("orc_features_per_level", "orc_umax"):
+            getattr(L, name).restype = ip
+            getattr(L, name).argtypes = [vp]
+        L.orc_extract.restype = C.c_int
+        L.orc_extract.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_ssize_t, vp, u8p, C.c_int, ip]
+        L.orc_level_size.argtypes = [vp, C.c_int, ip, ip]
+        L.orc_level_ptr.restype = vp
+        L.orc_level_ptr.argtypes = [vp, C.c_int]
+        L.orc_blurred_ptr.restype = vp
+        L.orc_blurred_ptr.argtypes = [vp, C.c_int]
+        L.orc_level_candidates.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+        L.orc_level_keypoints.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
+        L.orc_level_tie_sensitive.argtypes = [vp, C.c_int]
+        L.orc_stereo_match.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_float, C.c_float,
+                                       vp, vp, vp, vp, vp]
+        L.orc_hamming256.argtypes = [vp, vp]
+        L.orc_resize_linear_u8.argtypes = [vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_int, C.c_int, C.c_ssize_t]
+        L.orc_resize_linear_u8.restype = None
+        L.orc_fast9_16.argtypes = [vp, C.c_int, C.c_int, C.c_ssize_t, C.c_int, C.c_int, vp, vp, vp]
+        L.orc_gaussian7x7_s2.argtypes = [vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_ssize_t]
+        L.orc_gaussian7x7_s2.restype = None
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_cv_round.argtypes = [C.c_double]
+        L.orc_distribute_octtree.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, vp, vp, vp, ip]
+        _lib = L
+    return _lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---------------------------------------------------------------------------------------------
+# primitives (for the known-answer tests)
+# ---------------------------------------------------------------------------------------------
+def resize_linear(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_ptr(src), src.shape[1], src.shape[0], src.strides[0], _ptr(dst), dw, dh, dw)
+    return dst
+
+
+def fast9_16(img: np.ndarray, threshold: int):
+    """-> (x, y, response) int arrays, raster order (cv::FAST with nonmaxSuppression=true)."""
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    h, w = img.shape
+    cap = ((w + 1) // 2) * ((h + 1) // 2) + 1
+    x = np.empty(cap, np.int32); y = np.empty(cap, np.int32); r = np.empty(cap, np.int32)
+    n = lib().orc_fast9_16(_ptr(img), w, h, img.strides[0], threshold, cap, _ptr(x), _ptr(y), _ptr(r))
+    return x[:n].copy(), y[:n].copy(), r[:n].copy()
+
+
+def gaussian7x7(img: np.ndarray) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    lib().orc_gaussian7x7_s2(_ptr(img), img.shape[1], img.shape[0], img.strides[0], _ptr(out), out.strides[0])
+    return out
+
+
+def fast_atan2(y: float, x: float) -> float:
+    return float(lib().orc_fast_atan2(float(y), float(x)))
+
+
+def cv_round(v: float) -> int:
+    return int(lib().orc_cv_round(float(v)))
+
+
+def hamming256(a: np.ndarray, b: np.ndarray) -> int:
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    assert a.size == 32 and b.size == 32
+    return int(lib().orc_hamming256(_ptr(a), _ptr(b)))
+
+
+def distribute_octtree(x, y, resp, min_x, max_x, min_y, max_y, n_features):
+    """-> (x, y, resp, tie_sensitive) of the retained keys in list order."""
+    x = np.ascontiguousarray(x, np.int32); y = np.ascontiguousarray(y, np.int32)
+    resp = np.ascontiguousarray(resp, np.int32)
+    cap = max(len(x), 1) + 8
+    ox = np.empty(cap, np.int32); oy = np.empty(cap, np.int32); orr = np.empty(cap, np.int32)
+    tie = C.c_int(0)
+    n = lib().orc_distribute_octtree(_ptr(x), _ptr(y), _ptr(resp), len(x), min_x, max_x, min_y, max_y,
+                                     n_features, cap, _ptr(ox), _ptr(oy), _ptr(orr), C.byref(tie))
+    return ox[:n].copy(), oy[:n].copy(), orr[:n].copy(), bool(tie.value)
+
+
+# ---------------------------------------------------------------------------------------------
+# the extractor / stereo matcher
+# ---------------------------------------------------------------------------------------------
+class OracleExtractor:
+    """Restatement of ORB_SLAM2::ORBextractor (reference include/ORBextractor.h:45-111)."""
+
+    def __init__(self, nfeatures: int, scale_factor: float, nlevels: int, ini_th: int, min_th: int):
+        self._h = lib().orc_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        if not self._h:
+            raise ValueError("bad extractor parameters")
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self.cap = nfeatures + 16 * nlevels + 64
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_destroy(self._h)
+            self._h = None
+
+    def _f(self, fn, n=None):
+        p = getattr(lib(), fn)(self._h)
+        return np.ctypeslib.as_array(p, shape=(n or self.nlevels,)).copy()
+
+    @property
+    def scale_factors(self): return self._f("orc_scale_factors")
+    @property
+    def inv_scale_factors(self): return self._f("orc_inv_scale_factors")
+    @property
+    def level_sigma2(self): return self._f("orc_level_sigma2")
+    @property
+    def inv_level_sigma2(self): return self._f("orc_inv_level_sigma2")
+    @property
+    def features_per_level(self): return self._f("orc_features_per_level")
+    @property
+    def umax(self): return self._f("orc_umax", 16)
+
+    def extract(self, img: np.ndarray):
+        """-> (keypoints structured array [n], descriptors uint8 [n,32])"""
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        cap = self.cap
+        while True:
+            kps = np.zeros(cap, KEYPOINT_DTYPE)
+            desc = np.zeros((cap, 32), np.uint8)
+            n = C.c_int(0)
+            rc = lib().orc_extract(self._h, _ptr(img), img.shape[1], img.shape[0], img.strides[0],
+                                   _ptr(kps), _ptr(desc), cap, C.byref(n))
+            if rc == -1:
+                cap = n.value + 8
+                continue
+            if rc != 0:
+                raise RuntimeError(f"orc_extract failed rc={rc}")
+            return kps[: n.value].copy(), desc[: n.value].copy()
+
+    def level_size(self, level: int):
+        w, h = C.c_int(0), C.c_int(0)
+        lib().orc_level_size(self._h, level, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def _img(self, fn, level):
+        w, h = self.level_size(level)
+        p = getattr(lib(), fn)(self._h, level)
+        if not p:
+            return None
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(h, w)).copy()
+
+    def level(self, level: int): return self._img("orc_level_ptr", level)
+    def blurred(self, level: int): return self._img("orc_blurred_ptr", level)
+
+    def level_candidates(self, level: int):
+        cap = 1 << 16
+        while True:
+            x = np.empty(cap, np.int32); y = np.empty(cap, np.int32); r = np.empty(cap, np.int32)
+            n = lib().orc_level_candidates(self._h, level, cap, _ptr(x), _ptr(y), _ptr(r))
+            if n <= cap:
+                return x[:n].copy(), y[:n].copy(), r[:n].copy()
+            cap = n
+
+    def level_keypoints(self, level: int):
+        cap = 1 << 16
+        x = np.empty(cap, np.int32); y = np.empty(cap, np.int32); r = np.empty(cap, np.int32)
+        a = np.empty(cap, np.float32)
+        n = lib().orc_level_keypoints(self._h, level, cap, _ptr(x), _ptr(y), _ptr(r), _ptr(a))
+        return x[:n].copy(), y[:n].copy(), r[:n].copy(), a[:n].copy()
+
+    def tie_sensitive(self, level: int) -> bool:
+        return bool(lib().orc_level_tie_sensitive(self._h, level))
+
+
+def stereo_match(eL: OracleExtractor, eR: OracleExtractor, kL, dL, kR, dR, bf: float, maxD: float, debug=False):
+    """Frame::ComputeStereoMatches on the pyramids currently held by eL / eR."""
+    kL = np.ascontiguousarray(kL, KEYPOINT_DTYPE); kR = np.ascontiguousarray(kR, KEYPOINT_DTYPE)
+    dL = np.ascontiguousarray(dL, np.uint8); dR = np.ascontiguousarray(dR, np.uint8)
+    nL, nR = len(kL), len(kR)
+    ur = np.empty(max(nL, 1), np.float32); dp = np.empty(max(nL, 1), np.float32)
+    bd = np.empty(max(nL, 1), np.int32); bi = np.empty(max(nL, 1), np.int32); bs = np.empty(max(nL, 1), np.int32)
+    rc = lib().orc_stereo_match(eL._h, eR._h, _ptr(kL), nL, _ptr(dL), _ptr(kR), nR, _ptr(dR),
+                                C.c_float(bf), C.c_float(maxD), _ptr(ur), _ptr(dp), _ptr(bd), _ptr(bi), _ptr(bs))
+    if rc != 0:
+        raise RuntimeError(f"orc_stereo_match rc={rc}")
+    if debug:
+        return ur[:nL], dp[:nL], bd[:nL], bi[:nL], bs[:nL]
+    return ur[:nL], dp[:nL]
+
+
+def stereo_pair(params, imL, imR, bf, maxD):
+    """Whole unit of work: extract both views + stereo match (reference Frame.cc:144-173)."""
+    eL = OracleExtractor(*params); eR = OracleExtractor(*params)
+    kL, dL = eL.extract(imL); kR, dR = eR.extract(imR)
+    ur, dp = stereo_match(eL, eR, kL, dL, kR, dR, bf, maxD)
+    return kL, dL, kR, dR, ur, dp

@@ -1,0 +1,883 @@
+/*
+ * orb_oracle.c — CPU ORACLE (test infrastructure, NOT product code).  See orb_oracle.h.
+ *
+ * Plain C11, no dependencies.  Build with -ffp-contract=off: every float expression below
+ * must round once per operation (DESIGN.md parity rule 3, "no FMA").
+ *
+ * Each function cites the reference lines it restates (paths under /root/reference).
+ */
+#include "orb_oracle.h"
+
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define PATCH_SIZE 31      /* ORBextractor.cc:72 */
+#define HALF_PATCH_SIZE 15 /* ORBextractor.cc:73 */
+#define EDGE_THRESHOLD 19  /* ORBextractor.cc:74 */
+#define MAX_LEVELS 32
+
+static const int8_t k_pattern[1024] = {
+#include "../include/pslot_orb_pattern.inc"
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* OpenCV scalar helpers                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+
+/* cvRound: round-half-to-even of a double (SSE2 cvtsd2si under the default rounding mode). */
+int orc_cv_round(double v) { return (int)lrint(v); }
+
+/* cv::fastAtan2 (OpenCV 4.13 core/mathfuncs_core: atanImpl<float>), degrees in [0,360).
+ * float32, one rounding per operation.  Called at ORBextractor.cc:103. */
+float orc_fast_atan2(float y, float x)
+{
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * scale;
+    const float p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale;
+    const float p7 = -0.04432655554792128f * scale;
+    const float eps = (float)2.2204460492503131e-16; /* (float)DBL_EPSILON */
+    float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + eps);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + eps);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* cv::resize(..., INTER_LINEAR) for CV_8UC1 (called at ORBextractor.cc:1120)                 */
+/* fixed point: 11-bit coefficients, horizontal pass in int32, vertical pass as in             */
+/* OpenCV's VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>.                          */
+/* ------------------------------------------------------------------------------------------ */
+static void resize_axis_table(int n_dst, int n_src, int *idx0, int *idx1, int16_t *c0, int16_t *c1)
+{
+    double scale = 1.0 / ((double)n_dst / (double)n_src);
+    for (int d = 0; d < n_dst; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= n_src - 1) { s = n_src - 1; f = 0.f; }
+        idx0[d] = s;
+        idx1[d] = s + 1 < n_src ? s + 1 : n_src - 1;
+        c0[d] = (int16_t)orc_cv_round((double)((1.f - f) * 2048.f));
+        c1[d] = (int16_t)orc_cv_round((double)(f * 2048.f));
+    }
+}
+
+void orc_resize_linear_u8(const uint8_t *src, int sw, int sh, ptrdiff_t spitch,
+                          uint8_t *dst, int dw, int dh, ptrdiff_t dpitch)
+{
+    int *x0 = malloc(sizeof(int) * (size_t)dw), *x1 = malloc(sizeof(int) * (size_t)dw);
+    int *y0 = malloc(sizeof(int) * (size_t)dh), *y1 = malloc(sizeof(int) * (size_t)dh);
+    int16_t *cx0 = malloc(2 * (size_t)dw), *cx1 = malloc(2 * (size_t)dw);
+    int16_t *cy0 = malloc(2 * (size_t)dh), *cy1 = malloc(2 * (size_t)dh);
+    int32_t *h0 = malloc(sizeof(int32_t) * (size_t)dw), *h1 = malloc(sizeof(int32_t) * (size_t)dw);
+    resize_axis_table(dw, sw, x0, x1, cx0, cx1);
+    resize_axis_table(dh, sh, y0, y1, cy0, cy1);
+    for (int dy = 0; dy < dh; ++dy) {
+        const uint8_t *r0 = src + (ptrdiff_t)y0[dy] * spitch;
+        const uint8_t *r1 = src + (ptrdiff_t)y1[dy] * spitch;
+        for (int dx = 0; dx < dw; ++dx) {
+            h0[dx] = r0[x0[dx]] * cx0[dx] + r0[x1[dx]] * cx1[dx];
+            h1[dx] = r1[x0[dx]] * cx0[dx] + r1[x1[dx]] * cx1[dx];
+        }
+        int b0 = cy0[dy], b1 = cy1[dy];
+        uint8_t *o = dst + (ptrdiff_t)dy * dpitch;
+        for (int dx = 0; dx < dw; ++dx) {
+            int v = (((b0 * (h0[dx] >> 4)) >> 16) + ((b1 * (h1[dx] >> 4)) >> 16) + 2) >> 2;
+            o[dx] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+    }
+    free(x0); free(x1); free(y0); free(y1); free(cx0); free(cx1); free(cy0); free(cy1); free(h0); free(h1);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* cv::FAST(img, kps, threshold, nonmaxSuppression=true), TYPE_9_16 (ORBextractor.cc:809,814)  */
+/* ------------------------------------------------------------------------------------------ */
+static const int k_ring_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+static const int k_ring_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+
+/* raw corner score: max over the 16 arcs of 9 contiguous ring pixels of min(d) resp. min(-d),
+ * minus 1 (OpenCV cornerScore<16>); pixel is a corner at threshold t  <=>  score >= t. */
+static inline int fast_raw_score(const uint8_t *p, const ptrdiff_t *off)
+{
+    int d[25];
+    int v = p[0];
+    for (int k = 0; k < 16; ++k) d[k] = v - p[off[k]];
+    for (int k = 16; k < 25; ++k) d[k] = d[k - 16];
+    int best_hi = INT_MIN, best_lo = INT_MIN;
+    for (int k = 0; k < 16; ++k) {
+        int mn = d[k], mx = d[k];
+        for (int j = 1; j < 9; ++j) {
+            if (d[k + j] < mn) mn = d[k + j];
+            if (d[k + j] > mx) mx = d[k + j];
+        }
+        if (mn > best_hi) best_hi = mn;
+        if (-mx > best_lo) best_lo = -mx;
+    }
+    return (best_hi > best_lo ? best_hi : best_lo) - 1;
+}
+
+/* scratch must hold w*h bytes */
+static int fast9_16_impl(const uint8_t *img, int w, int h, ptrdiff_t pitch, int threshold,
+                         uint8_t *score, int cap, int *ox, int *oy, int *oresp)
+{
+    if (w < 7 || h < 7) return 0;
+    ptrdiff_t off[16];
+    for (int k = 0; k < 16; ++k) off[k] = (ptrdiff_t)k_ring_dy[k] * pitch + k_ring_dx[k];
+    memset(score, 0, (size_t)w * (size_t)h);
+    const int t = threshold;
+    for (int y = 3; y < h - 3; ++y) {
+        const uint8_t *row = img + (ptrdiff_t)y * pitch;
+        uint8_t *srow = score + (size_t)y * (size_t)w;
+        for (int x = 3; x < w - 3; ++x) {
+            const uint8_t *p = row + x;
+            int v = p[0];
+            /* every arc of 9 contains one pixel of each diametral pair: cheap rejection */
+            int a0 = v - p[off[0]], a8 = v - p[off[8]];
+            int hi = (a0 > t) | (a8 > t), lo = (a0 < -t) | (a8 < -t);
+            if (!(hi | lo)) continue;
+            int a4 = v - p[off[4]], a12 = v - p[off[12]];
+            hi &= (a4 > t) | (a12 > t);
+            lo &= (a4 < -t) | (a12 < -t);
+            if (!(hi | lo)) continue;
+            int s = fast_raw_score(p, off);
+            if (s >= t) srow[x] = (uint8_t)s;
+        }
+    }
+    int n = 0;
+    for (int y = 3; y < h - 3; ++y) {
+        const uint8_t *c = score + (size_t)y * (size_t)w;
+        const uint8_t *u = c - w, *d = c + w;
+        for (int x = 3; x < w - 3; ++x) {
+            int s = c[x];
+            if (!s) continue;
+            if (s > u[x - 1] && s > u[x] && s > u[x + 1] && s > c[x - 1] && s > c[x + 1] &&
+                s > d[x - 1] && s > d[x] && s > d[x + 1]) {
+                if (n < cap) { ox[n] = x; oy[n] = y; oresp[n] = s; }
+                ++n;
+            }
+        }
+    }
+    return n;
+}
+
+int orc_fast9_16(const uint8_t *img, int w, int h, ptrdiff_t pitch, int threshold,
+                 int cap, int *x, int *y, int *resp)
+{
+    uint8_t *score = malloc((size_t)(w > 0 ? w : 1) * (size_t)(h > 0 ? h : 1));
+    int n = fast9_16_impl(img, w, h, pitch, threshold, score, cap, x, y, resp);
+    free(score);
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* cv::GaussianBlur(src, dst, Size(7,7), 2, 2, BORDER_REFLECT_101) on a continuous CV_8U Mat   */
+/* (ORBextractor.cc:1085-1086): fixed-point separable kernel [18 34 48 56 48 34 18]/256,       */
+/* single rounding at the end.                                                                 */
+/* ------------------------------------------------------------------------------------------ */
+static inline int reflect101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i;
+        else i = 2 * (n - 1) - i;
+    }
+    return i;
+}
+
+void orc_gaussian7x7_s2(const uint8_t *src, int w, int h, ptrdiff_t spitch, uint8_t *dst, ptrdiff_t dpitch)
+{
+    static const int kw[7] = {18, 34, 48, 56, 48, 34, 18};
+    int32_t *hbuf = malloc(sizeof(int32_t) * (size_t)w * (size_t)h);
+    for (int y = 0; y < h; ++y) {
+        const uint8_t *r = src + (ptrdiff_t)y * spitch;
+        int32_t *o = hbuf + (size_t)y * (size_t)w;
+        for (int x = 0; x < w; ++x) {
+            int acc = 0;
+            if (x >= 3 && x < w - 3) {
+                for (int k = 0; k < 7; ++k) acc += kw[k] * r[x + k - 3];
+            } else {
+                for (int k = 0; k < 7; ++k) acc += kw[k] * r[reflect101(x + k - 3, w)];
+            }
+            o[x] = acc;
+        }
+    }
+    for (int y = 0; y < h; ++y) {
+        const int32_t *rows[7];
+        for (int k = 0; k < 7; ++k) rows[k] = hbuf + (size_t)reflect101(y + k - 3, h) * (size_t)w;
+        uint8_t *o = dst + (ptrdiff_t)y * dpitch;
+        for (int x = 0; x < w; ++x) {
+            int acc = 0;
+            for (int k = 0; k < 7; ++k) acc += kw[k] * rows[k][x];
+            o[x] = (uint8_t)((acc + 32768) >> 16);
+        }
+    }
+    free(hbuf);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* ORBmatcher::DescriptorDistance (ORBmatcher.cc:2704-2720)                                    */
+/* ------------------------------------------------------------------------------------------ */
+int orc_hamming256(const void *a, const void *b)
+{
+    uint32_t pa[8], pb[8];
+    memcpy(pa, a, 32);
+    memcpy(pb, b, 32);
+    int dist = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t v = pa[i] ^ pb[i];
+        v = v - ((v >> 1) & 0x55555555u);
+        v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u);
+        dist += (int)((((v + (v >> 4)) & 0xF0F0F0Fu) * 0x1010101u) >> 24);
+    }
+    return dist;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* DistributeOctTree (ORBextractor.cc:539-763) + ExtractorNode::DivideNode (:481-537)          */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct qnode {
+    int ulx, uly, urx, ury, blx, bly, brx, bry; /* UL, UR, BL, BR corners */
+    int *keys;                                  /* indices into the candidate arrays, insertion order */
+    int nkeys;
+    int nomore;
+    long seq; /* creation sequence number: the canonical stand-in for the heap address (rule C.1) */
+    struct qnode *prev, *next;
+} qnode;
+
+typedef struct { qnode *head, *tail; int size; long next_seq; } qlist;
+
+static qnode *qnode_new(int reserve)
+{
+    qnode *n = calloc(1, sizeof(qnode));
+    n->keys = malloc(sizeof(int) * (size_t)(reserve > 0 ? reserve : 1));
+    return n;
+}
+static void qnode_free(qnode *n) { free(n->keys); free(n); }
+static void qlist_push_front(qlist *l, qnode *n)
+{
+    n->seq = l->next_seq++;
+    n->prev = NULL; n->next = l->head;
+    if (l->head) l->head->prev = n; else l->tail = n;
+    l->head = n; l->size++;
+}
+static void qlist_push_back(qlist *l, qnode *n)
+{
+    n->seq = l->next_seq++;
+    n->next = NULL; n->prev = l->tail;
+    if (l->tail) l->tail->next = n; else l->head = n;
+    l->tail = n; l->size++;
+}
+static qnode *qlist_erase(qlist *l, qnode *n) /* returns the following node */
+{
+    qnode *nx = n->next;
+    if (n->prev) n->prev->next = n->next; else l->head = n->next;
+    if (n->next) n->next->prev = n->prev; else l->tail = n->prev;
+    l->size--;
+    qnode_free(n);
+    return nx;
+}
+
+/* DivideNode (:481-537).  x,y are the candidate coordinate arrays. */
+static void divide_node(const qnode *p, const int *kx, const int *ky, qnode *c[4])
+{
+    const int halfX = (int)ceilf((float)(p->urx - p->ulx) / 2);
+    const int halfY = (int)ceilf((float)(p->bry - p->uly) / 2);
+    for (int i = 0; i < 4; ++i) c[i] = qnode_new(p->nkeys);
+    qnode *n1 = c[0], *n2 = c[1], *n3 = c[2], *n4 = c[3];
+    n1->ulx = p->ulx; n1->uly = p->uly;
+    n1->urx = p->ulx + halfX; n1->ury = p->uly;
+    n1->blx = p->ulx; n1->bly = p->uly + halfY;
+    n1->brx = p->ulx + halfX; n1->bry = p->uly + halfY;
+
+    n2->ulx = n1->urx; n2->uly = n1->ury;
+    n2->urx = p->urx; n2->ury = p->ury;
+    n2->blx = n1->brx; n2->bly = n1->bry;
+    n2->brx = p->urx; n2->bry = p->uly + halfY;
+
+    n3->ulx = n1->blx; n3->uly = n1->bly;
+    n3->urx = n1->brx; n3->ury = n1->bry;
+    n3->blx = p->blx; n3->bly = p->bly;
+    n3->brx = n1->brx; n3->bry = p->bly;
+
+    n4->ulx = n3->urx; n4->uly = n3->ury;
+    n4->urx = n2->brx; n4->ury = n2->bry;
+    n4->blx = n3->brx; n4->bly = n3->bry;
+    n4->brx = p->brx; n4->bry = p->bry;
+
+    for (int i = 0; i < p->nkeys; ++i) {
+        int k = p->keys[i];
+        qnode *dst;
+        if (kx[k] < n1->urx) dst = (ky[k] < n1->bry) ? n1 : n3;
+        else dst = (ky[k] < n1->bry) ? n2 : n4;
+        dst->keys[dst->nkeys++] = k;
+    }
+    for (int i = 0; i < 4; ++i)
+        if (c[i]->nkeys == 1) c[i]->nomore = 1;
+}
+
+typedef struct { int size; long seq; qnode *node; } qsized;
+static int qsized_cmp(const void *a, const void *b)
+{
+    const qsized *pa = a, *pb = b;
+    if (pa->size != pb->size) return pa->size < pb->size ? -1 : 1;
+    if (pa->seq != pb->seq) return pa->seq < pb->seq ? -1 : 1; /* rule C.1: later-created sorts last */
+    return 0;
+}
+
+/* push the non-empty children in order n1..n4, recording expandable ones; frees empty ones */
+static void push_children(qlist *l, qnode *c[4], qsized **v, int *nv, int *capv, int *n_to_expand)
+{
+    for (int i = 0; i < 4; ++i) {
+        if (c[i]->nkeys > 0) {
+            qlist_push_front(l, c[i]);
+            if (c[i]->nkeys > 1) {
+                if (n_to_expand) (*n_to_expand)++;
+                if (*nv == *capv) { *capv = *capv * 2 + 16; *v = realloc(*v, sizeof(qsized) * (size_t)*capv); }
+                (*v)[*nv].size = c[i]->nkeys; (*v)[*nv].seq = c[i]->seq; (*v)[*nv].node = c[i];
+                (*nv)++;
+            }
+        } else {
+            qnode_free(c[i]);
+        }
+    }
+}
+
+int orc_distribute_octtree(const int *x, const int *y, const int *resp, int n,
+                           int minX, int maxX, int minY, int maxY, int N,
+                           int cap, int *ox, int *oy, int *oresp, int *tie_sensitive)
+{
+    if (tie_sensitive) *tie_sensitive = 0;
+    /* :543-545 */
+    const int nIni = (int)roundf((float)(maxX - minX) / (float)(maxY - minY));
+    const float hX = (float)(maxX - minX) / (float)nIni;
+    if (nIni <= 0) return 0; /* reference divides by zero here; such shapes are rejected upstream */
+
+    qlist L = {0};
+    qnode **roots = malloc(sizeof(qnode *) * (size_t)nIni);
+    for (int i = 0; i < nIni; ++i) { /* :550-563 */
+        qnode *ni = qnode_new(n);
+        ni->ulx = (int)(hX * (float)i); ni->uly = 0;
+        ni->urx = (int)(hX * (float)(i + 1)); ni->ury = 0;
+        ni->blx = ni->ulx; ni->bly = maxY - minY;
+        ni->brx = ni->urx; ni->bry = maxY - minY;
+        qlist_push_back(&L, ni);
+        roots[i] = ni;
+    }
+    /* push_back'ed roots must order front->back as 0..nIni-1 while every later push_front lands
+       before them; seq is only used for sorting ties among *children*, so the root values are moot */
+    for (int i = 0; i < n; ++i) { /* :566-570 */
+        int r = (int)((float)x[i] / hX);
+        if (r >= nIni) r = nIni - 1; /* cannot happen for in-window keys; guards the oracle only */
+        roots[r]->keys[roots[r]->nkeys++] = i;
+    }
+    free(roots);
+    for (qnode *it = L.head; it;) { /* :572-585 */
+        if (it->nkeys == 1) { it->nomore = 1; it = it->next; }
+        else if (it->nkeys == 0) it = qlist_erase(&L, it);
+        else it = it->next;
+    }
+
+    int finish = 0;
+    qsized *V = NULL; int nV = 0, capV = 0;
+    while (!finish) { /* :594 */
+        int prevSize = L.size;
+        int nToExpand = 0;
+        nV = 0;
+        /* coarse pass (:600-665): visit only the nodes present at the start of the pass */
+        qnode *it = L.head;
+        while (it) {
+            if (it->nomore) { it = it->next; continue; }
+            qnode *c[4];
+            divide_node(it, x, y, c);
+            push_children(&L, c, &V, &nV, &capV, &nToExpand);
+            it = qlist_erase(&L, it);
+        }
+        if (L.size >= N || L.size == prevSize) { /* :669 */
+            finish = 1;
+        } else if (L.size + nToExpand * 3 > N) { /* :673 */
+            while (!finish) {
+                prevSize = L.size;
+                int nP = nV;
+                qsized *P = malloc(sizeof(qsized) * (size_t)(nP > 0 ? nP : 1));
+                memcpy(P, V, sizeof(qsized) * (size_t)nP);
+                nV = 0;
+                qsort(P, (size_t)nP, sizeof(qsized), qsized_cmp); /* :684 */
+                for (int j = nP - 1; j >= 0; --j) {
+                    qnode *c[4];
+                    divide_node(P[j].node, x, y, c);
+                    push_children(&L, c, &V, &nV, &capV, NULL);
+                    qlist_erase(&L, P[j].node);
+                    if (L.size >= N) { /* :731 */
+                        if (tie_sensitive && j > 0 && P[j - 1].size == P[j].size) *tie_sensitive = 1;
+                        break;
+                    }
+                }
+                free(P);
+                if (L.size >= N || L.size == prevSize) finish = 1; /* :735 */
+            }
+        }
+    }
+    free(V);
+
+    /* :741-760 keep the first maximum-response key of each node, list order */
+    int no = 0;
+    for (qnode *it = L.head; it;) {
+        int best = it->keys[0];
+        for (int k = 1; k < it->nkeys; ++k)
+            if ((float)resp[it->keys[k]] > (float)resp[best]) best = it->keys[k];
+        if (no < cap) { ox[no] = x[best]; oy[no] = y[best]; oresp[no] = resp[best]; }
+        ++no;
+        qnode *nx = it->next;
+        qnode_free(it);
+        it = nx;
+    }
+    return no;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* ORBextractor                                                                                */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int w, h;
+    uint8_t *img;     /* borderless level image, pitch = w (the 19-px frame of :1113-1128 is never read) */
+    uint8_t *blurred; /* GaussianBlur of img, NULL if the level has no keypoints */
+    int ncand, capcand;
+    int *cx, *cy, *cresp;
+    int nkp, capkp;
+    int *kx, *ky, *kresp;
+    float *kangle;
+    int tie_sensitive;
+} orc_level;
+
+struct orc_extractor {
+    int nfeatures, nlevels, ini_th, min_th;
+    double scale_factor;
+    float sf[MAX_LEVELS], inv_sf[MAX_LEVELS], sigma2[MAX_LEVELS], inv_sigma2[MAX_LEVELS];
+    int per_level[MAX_LEVELS];
+    int umax[HALF_PATCH_SIZE + 1];
+    orc_level lv[MAX_LEVELS];
+};
+
+orc_extractor *orc_create(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th)
+{
+    if (nlevels < 1 || nlevels > MAX_LEVELS || nfeatures < 1) return NULL;
+    orc_extractor *e = calloc(1, sizeof(*e));
+    e->nfeatures = nfeatures; e->nlevels = nlevels; e->ini_th = ini_th; e->min_th = min_th;
+    e->scale_factor = (double)scale_factor; /* ORBextractor.h:98 double member, float argument */
+    /* :415-431 */
+    e->sf[0] = 1.0f; e->sigma2[0] = 1.0f;
+    for (int i = 1; i < nlevels; ++i) {
+        e->sf[i] = (float)((double)e->sf[i - 1] * e->scale_factor);
+        e->sigma2[i] = e->sf[i] * e->sf[i];
+    }
+    for (int i = 0; i < nlevels; ++i) {
+        e->inv_sf[i] = 1.0f / e->sf[i];
+        e->inv_sigma2[i] = 1.0f / e->sigma2[i];
+    }
+    /* :435-446 */
+    float factor = (float)(1.0 / e->scale_factor);
+    float nDesired = (float)nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; ++l) {
+        e->per_level[l] = orc_cv_round((double)nDesired);
+        sum += e->per_level[l];
+        nDesired *= factor;
+    }
+    e->per_level[nlevels - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
+    /* :454-469 */
+    int v, v0;
+    int vmax = (int)floor((double)(HALF_PATCH_SIZE * sqrtf(2.f) / 2 + 1));
+    int vmin = (int)ceil((double)(HALF_PATCH_SIZE * sqrtf(2.f) / 2));
+    const double hp2 = HALF_PATCH_SIZE * HALF_PATCH_SIZE;
+    for (v = 0; v <= vmax; ++v) e->umax[v] = orc_cv_round(sqrt(hp2 - v * v));
+    for (v = HALF_PATCH_SIZE, v0 = 0; v >= vmin; --v) {
+        while (e->umax[v0] == e->umax[v0 + 1]) ++v0;
+        e->umax[v] = v0;
+        ++v0;
+    }
+    return e;
+}
+
+static void level_release(orc_level *L)
+{
+    free(L->img); free(L->blurred);
+    free(L->cx); free(L->cy); free(L->cresp);
+    free(L->kx); free(L->ky); free(L->kresp); free(L->kangle);
+    memset(L, 0, sizeof(*L));
+}
+
+void orc_destroy(orc_extractor *e)
+{
+    if (!e) return;
+    for (int l = 0; l < e->nlevels; ++l) level_release(&e->lv[l]);
+    free(e);
+}
+
+const float *orc_scale_factors(const orc_extractor *e) { return e->sf; }
+const float *orc_inv_scale_factors(const orc_extractor *e) { return e->inv_sf; }
+const float *orc_level_sigma2(const orc_extractor *e) { return e->sigma2; }
+const float *orc_inv_level_sigma2(const orc_extractor *e) { return e->inv_sigma2; }
+const int *orc_features_per_level(const orc_extractor *e) { return e->per_level; }
+const int *orc_umax(const orc_extractor *e) { return e->umax; }
+
+/* ComputePyramid (:1107-1132) */
+static void compute_pyramid(orc_extractor *e, const uint8_t *img, int w, int h, ptrdiff_t pitch)
+{
+    for (int l = 0; l < e->nlevels; ++l) {
+        orc_level *L = &e->lv[l];
+        float scale = e->inv_sf[l];
+        int lw = orc_cv_round((double)((float)w * scale));
+        int lh = orc_cv_round((double)((float)h * scale));
+        free(L->img); free(L->blurred); L->blurred = NULL;
+        L->w = lw; L->h = lh;
+        L->img = malloc((size_t)(lw > 0 ? lw : 1) * (size_t)(lh > 0 ? lh : 1));
+        if (l == 0) {
+            for (int y = 0; y < lh; ++y) memcpy(L->img + (size_t)y * (size_t)lw, img + (ptrdiff_t)y * pitch, (size_t)lw);
+        } else {
+            orc_level *P = &e->lv[l - 1];
+            orc_resize_linear_u8(P->img, P->w, P->h, P->w, L->img, lw, lh, lw);
+        }
+    }
+}
+
+static void cand_push(orc_level *L, int x, int y, int r)
+{
+    if (L->ncand == L->capcand) {
+        L->capcand = L->capcand * 2 + 1024;
+        L->cx = realloc(L->cx, sizeof(int) * (size_t)L->capcand);
+        L->cy = realloc(L->cy, sizeof(int) * (size_t)L->capcand);
+        L->cresp = realloc(L->cresp, sizeof(int) * (size_t)L->capcand);
+    }
+    L->cx[L->ncand] = x; L->cy[L->ncand] = y; L->cresp[L->ncand] = r; L->ncand++;
+}
+
+/* IC_Angle (:77-104) */
+static float ic_angle(const uint8_t *img, int pitch, int px, int py, const int *umax)
+{
+    int m_01 = 0, m_10 = 0;
+    const uint8_t *center = img + (ptrdiff_t)py * pitch + px;
+    for (int u = -HALF_PATCH_SIZE; u <= HALF_PATCH_SIZE; ++u) m_10 += u * center[u];
+    for (int v = 1; v <= HALF_PATCH_SIZE; ++v) {
+        int v_sum = 0;
+        int d = umax[v];
+        for (int u = -d; u <= d; ++u) {
+            int val_plus = center[u + v * pitch], val_minus = center[u - v * pitch];
+            v_sum += (val_plus - val_minus);
+            m_10 += u * (val_plus + val_minus);
+        }
+        m_01 += v * v_sum;
+    }
+    return orc_fast_atan2((float)m_01, (float)m_10);
+}
+
+/* ComputeKeyPointsOctTree (:765-853) */
+static int compute_keypoints_octtree(orc_extractor *e)
+{
+    const float W = 30;
+    uint8_t *score = NULL; size_t score_cap = 0;
+    int *fx = NULL, *fy = NULL, *fr = NULL; int fcap = 0;
+    for (int level = 0; level < e->nlevels; ++level) {
+        orc_level *L = &e->lv[level];
+        L->ncand = 0; L->nkp = 0; L->tie_sensitive = 0;
+        const int minBorderX = EDGE_THRESHOLD - 3;
+        const int minBorderY = minBorderX;
+        const int maxBorderX = L->w - EDGE_THRESHOLD + 3;
+        const int maxBorderY = L->h - EDGE_THRESHOLD + 3;
+        const float width = (float)(maxBorderX - minBorderX);
+        const float height = (float)(maxBorderY - minBorderY);
+        const int nCols = (int)(width / W);
+        const int nRows = (int)(height / W);
+        if (nCols < 1 || nRows < 1) { free(score); free(fx); free(fy); free(fr); return -2; } /* reference: /0 */
+        const int wCell = (int)ceilf(width / (float)nCols);
+        const int hCell = (int)ceilf(height / (float)nRows);
+
+        for (int i = 0; i < nRows; ++i) {
+            const float iniY = (float)(minBorderY + i * hCell);
+            float maxY = iniY + (float)hCell + 6;
+            if (iniY >= (float)(maxBorderY - 3)) continue;
+            if (maxY > (float)maxBorderY) maxY = (float)maxBorderY;
+            for (int j = 0; j < nCols; ++j) {
+                const float iniX = (float)(minBorderX + j * wCell);
+                float maxX = iniX + (float)wCell + 6;
+                if (iniX >= (float)(maxBorderX - 3)) continue; /* :803 (upstream has -6) */
+                if (maxX > (float)maxBorderX) maxX = (float)maxBorderX;
+                /* rowRange(iniY,maxY).colRange(iniX,maxX): float -> int truncation */
+                int y0 = (int)iniY, y1 = (int)maxY, x0 = (int)iniX, x1 = (int)maxX;
+                int cw = x1 - x0, ch = y1 - y0;
+                if ((size_t)cw * (size_t)ch > score_cap) { score_cap = (size_t)cw * (size_t)ch; score = realloc(score, score_cap); }
+                int maxk = ((cw + 1) / 2) * ((ch + 1) / 2) + 1;
+                if (maxk > fcap) { fcap = maxk; fx = realloc(fx, sizeof(int) * (size_t)fcap); fy = realloc(fy, sizeof(int) * (size_t)fcap); fr = realloc(fr, sizeof(int) * (size_t)fcap); }
+                const uint8_t *sub = L->img + (ptrdiff_t)y0 * L->w + x0;
+                int nk = fast9_16_impl(sub, cw, ch, L->w, e->ini_th, score, fcap, fx, fy, fr);
+                if (nk == 0) nk = fast9_16_impl(sub, cw, ch, L->w, e->min_th, score, fcap, fx, fy, fr);
+                for (int k = 0; k < nk; ++k) cand_push(L, fx[k] + j * wCell, fy[k] + i * hCell, fr[k]);
+            }
+        }
+
+        int capk = e->per_level[level] + 8;
+        if (capk < L->ncand + 1) capk = L->ncand + 1; /* list can never exceed the candidate count */
+        if (capk > L->capkp) {
+            L->capkp = capk;
+            L->kx = realloc(L->kx, sizeof(int) * (size_t)capk);
+            L->ky = realloc(L->ky, sizeof(int) * (size_t)capk);
+            L->kresp = realloc(L->kresp, sizeof(int) * (size_t)capk);
+            L->kangle = realloc(L->kangle, sizeof(float) * (size_t)capk);
+        }
+        L->nkp = orc_distribute_octtree(L->cx, L->cy, L->cresp, L->ncand, minBorderX, maxBorderX,
+                                        minBorderY, maxBorderY, e->per_level[level],
+                                        L->capkp, L->kx, L->ky, L->kresp, &L->tie_sensitive);
+        for (int i = 0; i < L->nkp; ++i) { /* :837-847 */
+            L->kx[i] += minBorderX;
+            L->ky[i] += minBorderY;
+        }
+    }
+    free(score); free(fx); free(fy); free(fr);
+    for (int level = 0; level < e->nlevels; ++level) { /* :850-852 */
+        orc_level *L = &e->lv[level];
+        for (int i = 0; i < L->nkp; ++i) L->kangle[i] = ic_angle(L->img, L->w, L->kx[i], L->ky[i], e->umax);
+    }
+    return 0;
+}
+
+/* computeOrbDescriptor (:107-147) */
+static void compute_orb_descriptor(const uint8_t *img, int step, int px, int py, float kp_angle, uint8_t *desc)
+{
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    float angle = kp_angle * factorPI;
+    /* rule: cos/sin evaluated in double, rounded to float (DESIGN.md parity rule 3) */
+    float a = (float)cos((double)angle), b = (float)sin((double)angle);
+    const uint8_t *center = img + (ptrdiff_t)py * step + px;
+    const int8_t *pat = k_pattern;
+    for (int i = 0; i < 32; ++i, pat += 32) {
+        int val = 0;
+        for (int t = 0; t < 8; ++t) {
+            const int8_t *q = pat + 4 * t;
+            float x0 = (float)q[0], y0 = (float)q[1], x1 = (float)q[2], y1 = (float)q[3];
+            int t0 = center[orc_cv_round((double)(x0 * b + y0 * a)) * step + orc_cv_round((double)(x0 * a - y0 * b))];
+            int t1 = center[orc_cv_round((double)(x1 * b + y1 * a)) * step + orc_cv_round((double)(x1 * a - y1 * b))];
+            val |= (t0 < t1) << t;
+        }
+        desc[i] = (uint8_t)val;
+    }
+}
+
+int orc_extract(orc_extractor *e, const uint8_t *img, int w, int h, ptrdiff_t pitch,
+                orc_keypoint *kps, uint8_t *desc32, int cap, int *n)
+{
+    *n = 0;
+    if (!img || w <= 0 || h <= 0) return 0; /* :1046-1047 */
+    compute_pyramid(e, img, w, h, pitch);
+    int rc = compute_keypoints_octtree(e);
+    if (rc) return rc;
+    int total = 0;
+    for (int l = 0; l < e->nlevels; ++l) total += e->lv[l].nkp;
+    *n = total;
+    if (total > cap) return -1;
+    int offset = 0;
+    for (int l = 0; l < e->nlevels; ++l) { /* :1075-1104 */
+        orc_level *L = &e->lv[l];
+        if (L->nkp == 0) continue;
+        L->blurred = malloc((size_t)L->w * (size_t)L->h);
+        orc_gaussian7x7_s2(L->img, L->w, L->h, L->w, L->blurred, L->w);
+        const int scaledPatchSize = (int)((float)PATCH_SIZE * e->sf[l]); /* :834 */
+        for (int i = 0; i < L->nkp; ++i) {
+            orc_keypoint *k = &kps[offset + i];
+            compute_orb_descriptor(L->blurred, L->w, L->kx[i], L->ky[i], L->kangle[i], desc32 + 32 * (size_t)(offset + i));
+            k->x = (float)L->kx[i]; k->y = (float)L->ky[i];
+            if (l != 0) { k->x *= e->sf[l]; k->y *= e->sf[l]; } /* :1095-1101 */
+            k->size = (float)scaledPatchSize;
+            k->angle = L->kangle[i];
+            k->response = (float)L->kresp[i];
+            k->octave = l;
+            k->class_id = -1;
+        }
+        offset += L->nkp;
+    }
+    return 0;
+}
+
+int orc_level_size(const orc_extractor *e, int level, int *w, int *h)
+{
+    if (level < 0 || level >= e->nlevels) return -1;
+    *w = e->lv[level].w; *h = e->lv[level].h;
+    return 0;
+}
+const uint8_t *orc_level_ptr(const orc_extractor *e, int level) { return e->lv[level].img; }
+const uint8_t *orc_blurred_ptr(const orc_extractor *e, int level) { return e->lv[level].blurred; }
+int orc_level_candidates(const orc_extractor *e, int level, int cap, int *x, int *y, int *resp)
+{
+    const orc_level *L = &e->lv[level];
+    for (int i = 0; i < L->ncand && i < cap; ++i) { x[i] = L->cx[i]; y[i] = L->cy[i]; resp[i] = L->cresp[i]; }
+    return L->ncand;
+}
+int orc_level_keypoints(const orc_extractor *e, int level, int cap, int *x, int *y, int *resp, float *angle)
+{
+    const orc_level *L = &e->lv[level];
+    for (int i = 0; i < L->nkp && i < cap; ++i) { x[i] = L->kx[i]; y[i] = L->ky[i]; resp[i] = L->kresp[i]; angle[i] = L->kangle[i]; }
+    return L->nkp;
+}
+int orc_level_tie_sensitive(const orc_extractor *e, int level) { return e->lv[level].tie_sensitive; }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Frame::ComputeStereoMatches (Frame.cc:2142-2316)                                            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { int dist, idx; } dist_idx;
+static int dist_idx_cmp(const void *a, const void *b)
+{
+    const dist_idx *pa = a, *pb = b;
+    if (pa->dist != pb->dist) return pa->dist < pb->dist ? -1 : 1;
+    if (pa->idx != pb->idx) return pa->idx < pb->idx ? -1 : 1;
+    return 0;
+}
+
+int orc_stereo_match(const orc_extractor *eL, const orc_extractor *eR,
+                     const orc_keypoint *kL, int nL, const uint8_t *dL,
+                     const orc_keypoint *kR, int nR, const uint8_t *dR,
+                     float bf, float maxD, float *uright, float *depth,
+                     int *best_dist_out, int *best_idx_out, int *best_sad_out)
+{
+    const int TH_HIGH = 100, TH_LOW = 50; /* ORBmatcher.cc:58-62 */
+    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+    for (int i = 0; i < nL; ++i) {
+        uright[i] = -1.0f; depth[i] = -1.0f;
+        if (best_dist_out) best_dist_out[i] = TH_HIGH;
+        if (best_idx_out) best_idx_out[i] = -1;
+        if (best_sad_out) best_sad_out[i] = -1;
+    }
+    if (nL == 0) return 0;
+    const int nRows = eL->lv[0].h;
+    /* row table (:2152-2169) */
+    int *rcount = calloc((size_t)nRows + 1, sizeof(int));
+    for (int pass = 0; pass < 1; ++pass)
+        for (int iR = 0; iR < nR; ++iR) {
+            const float kpY = kR[iR].y;
+            const float r = 2.0f * eL->sf[kR[iR].octave];
+            const int maxr = (int)ceilf(kpY + r);
+            const int minr = (int)floorf(kpY - r);
+            for (int yi = minr; yi <= maxr; ++yi)
+                if (yi >= 0 && yi < nRows) rcount[yi]++;
+        }
+    int *rstart = malloc(sizeof(int) * ((size_t)nRows + 1));
+    int tot = 0;
+    for (int i = 0; i < nRows; ++i) { rstart[i] = tot; tot += rcount[i]; rcount[i] = 0; }
+    rstart[nRows] = tot;
+    int *rlist = malloc(sizeof(int) * (size_t)(tot > 0 ? tot : 1));
+    for (int iR = 0; iR < nR; ++iR) {
+        const float kpY = kR[iR].y;
+        const float r = 2.0f * eL->sf[kR[iR].octave];
+        const int maxr = (int)ceilf(kpY + r);
+        const int minr = (int)floorf(kpY - r);
+        for (int yi = minr; yi <= maxr; ++yi)
+            if (yi >= 0 && yi < nRows) rlist[rstart[yi] + rcount[yi]++] = iR;
+    }
+
+    const float minD = 0;
+    dist_idx *vDistIdx = malloc(sizeof(dist_idx) * (size_t)nL);
+    int nDist = 0;
+
+    for (int iL = 0; iL < nL; ++iL) { /* :2180 */
+        const orc_keypoint *kpL = &kL[iL];
+        const int levelL = kpL->octave;
+        const float vL = kpL->y, uL = kpL->x;
+        const int row = (int)vL;
+        if (row < 0 || row >= nRows) continue;
+        const int nc = rcount[row];
+        if (nc == 0) continue;
+        const int *cands = rlist + rstart[row];
+        const float minU = uL - maxD;
+        const float maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = TH_HIGH;
+        int bestIdxR = 0;
+        const uint8_t *dl = dL + 32 * (size_t)iL;
+        for (int iC = 0; iC < nc; ++iC) {
+            const int iR = cands[iC];
+            const orc_keypoint *kpR = &kR[iR];
+            if (kpR->octave < levelL - 1 || kpR->octave > levelL + 1) continue;
+            const float uR = kpR->x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = orc_hamming256(dl, dR + 32 * (size_t)iR);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (best_dist_out) best_dist_out[iL] = bestDist;
+        if (best_idx_out && bestDist < TH_HIGH) best_idx_out[iL] = bestIdxR;
+
+        if (bestDist < thOrbDist) { /* :2228 */
+            const float uR0 = kR[bestIdxR].x;
+            const float scaleFactor = eL->inv_sf[kpL->octave];
+            const float scaleduL = roundf(kpL->x * scaleFactor);
+            const float scaledvL = roundf(kpL->y * scaleFactor);
+            const float scaleduR0 = roundf(uR0 * scaleFactor);
+            const int w = 5;
+            const orc_level *PL = &eL->lv[kpL->octave], *PR = &eR->lv[kpL->octave];
+            const int ly0 = (int)(scaledvL - w), lx0 = (int)(scaleduL - w);
+            int bestSAD = INT_MAX;
+            int bestincR = 0;
+            const int Lh = 5;
+            float vDists[11];
+            const float iniu = scaleduR0 + Lh - w;
+            const float endu = scaleduR0 + Lh + w + 1;
+            if (iniu < 0 || endu >= (float)PR->w) continue;
+            const int cl = PL->img[(size_t)(ly0 + w) * (size_t)PL->w + (size_t)(lx0 + w)];
+            for (int incR = -Lh; incR <= Lh; ++incR) {
+                const int rx0 = (int)(scaleduR0 + (float)incR - w);
+                const int cr = PR->img[(size_t)(ly0 + w) * (size_t)PR->w + (size_t)(rx0 + w)];
+                /* cv::norm(IL,IR,NORM_L1) of the centre-subtracted float patches: integer-exact */
+                int acc = 0;
+                for (int yy = 0; yy < 2 * w + 1; ++yy) {
+                    const uint8_t *pl = PL->img + (size_t)(ly0 + yy) * (size_t)PL->w + lx0;
+                    const uint8_t *pr = PR->img + (size_t)(ly0 + yy) * (size_t)PR->w + rx0;
+                    for (int xx = 0; xx < 2 * w + 1; ++xx) acc += abs((pl[xx] - cl) - (pr[xx] - cr));
+                }
+                float dist = (float)acc;
+                if (dist < (float)bestSAD) { bestSAD = (int)dist; bestincR = incR; }
+                vDists[Lh + incR] = dist;
+            }
+            if (bestincR == -Lh || bestincR == Lh) continue;
+            const float dist1 = vDists[Lh + bestincR - 1];
+            const float dist2 = vDists[Lh + bestincR];
+            const float dist3 = vDists[Lh + bestincR + 1];
+            const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+            if (deltaR < -1 || deltaR > 1) continue;
+            float bestuR = eL->sf[kpL->octave] * ((float)scaleduR0 + (float)bestincR + deltaR);
+            float disparity = (uL - bestuR);
+            if (disparity >= minD && disparity < maxD) {
+                if (disparity <= 0) {
+                    disparity = (float)0.01;
+                    bestuR = (float)((double)uL - 0.01);
+                }
+                depth[iL] = bf / disparity;
+                uright[iL] = bestuR;
+                if (best_sad_out) best_sad_out[iL] = bestSAD;
+                vDistIdx[nDist].dist = bestSAD; vDistIdx[nDist].idx = iL; nDist++;
+            }
+        }
+    }
+    if (nDist > 0) { /* :2302-2315 (empty -> no-op, rule C.4) */
+        qsort(vDistIdx, (size_t)nDist, sizeof(dist_idx), dist_idx_cmp);
+        const float median = (float)vDistIdx[nDist / 2].dist;
+        const float thDist = 1.5f * 1.4f * median;
+        for (int i = nDist - 1; i >= 0; --i) {
+            if ((float)vDistIdx[i].dist < thDist) break;
+            uright[vDistIdx[i].idx] = -1;
+            depth[vDistIdx[i].idx] = -1;
+        }
+    }
+    free(vDistIdx); free(rlist); free(rstart); free(rcount);
+    return 0;
+}

@@ -1,0 +1,92 @@
+/*
+ * orb_oracle.h — CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain-C restatement of PointSLOT's per-frame stereo ORB front end, used only by tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs as the checker
+ * and the timed CPU baseline.  The shipped library (libpslot_orb.so) never links or calls it.
+ *
+ * PARITY STATUS: "parity unpinned" by the reference — it ships no tests or golden vectors
+ *  and its OpenCV is un-vendored.  The primitives restated here (resize
+ * INTER_LINEAR, FAST 9-16 + NMS, GaussianBlur 7x7 s=2, fastAtan2, cvRound) are pinned instead
+ * against OpenCV 4.13.0 through cv2 in tests/test_oracle_cv2.py and the fixtures under
+ * tests/golden/.  Explicit rules replace the reference's two UB / address-dependent spots
+ * (DESIGN.md "Parity rules"): quadtree ties -> later-created node first; maxD explicit.
+ *
+ * Reference files restated (paths under /root/reference):
+ *   src/ORBextractor.cc:77-147, 410-853, 1034-1132   include/ORBextractor.h
+ *   src/Frame.cc:2142-2316                           src/ORBmatcher.cc:2704-2720
+ */
+#ifndef ORB_ORACLE_H
+#define ORB_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* layout-identical to cv::KeyPoint (28 bytes) */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} orc_keypoint;
+
+typedef struct orc_extractor orc_extractor;
+
+orc_extractor *orc_create(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th);
+void orc_destroy(orc_extractor *e);
+
+/* tables computed by the constructor (ORBextractor.cc:410-470) */
+const float *orc_scale_factors(const orc_extractor *e);
+const float *orc_inv_scale_factors(const orc_extractor *e);
+const float *orc_level_sigma2(const orc_extractor *e);
+const float *orc_inv_level_sigma2(const orc_extractor *e);
+const int *orc_features_per_level(const orc_extractor *e);
+const int *orc_umax(const orc_extractor *e);
+
+/* ORBextractor::operator() (ORBextractor.cc:1043-1105). Returns 0, or -1 if cap is too small
+ * (n is still set to the required count).  Empty image (w<=0||h<=0) -> n=0, return 0. */
+int orc_extract(orc_extractor *e, const uint8_t *img, int w, int h, ptrdiff_t pitch,
+                orc_keypoint *kps, uint8_t *desc32, int cap, int *n);
+
+/* stage intermediates of the most recent orc_extract */
+int orc_level_size(const orc_extractor *e, int level, int *w, int *h);
+const uint8_t *orc_level_ptr(const orc_extractor *e, int level);   /* borderless, pitch = w */
+const uint8_t *orc_blurred_ptr(const orc_extractor *e, int level); /* NULL if level had no keypoints */
+/* FAST candidates handed to DistributeOctTree, window-relative coords, reference order */
+int orc_level_candidates(const orc_extractor *e, int level, int cap, int *x, int *y, int *resp);
+/* keypoints after DistributeOctTree + border offset, level coordinates, list order */
+int orc_level_keypoints(const orc_extractor *e, int level, int cap, int *x, int *y, int *resp, float *angle);
+/* 1 if the fine phase of DistributeOctTree stopped inside a run of equal-size nodes (tie-sensitive) */
+int orc_level_tie_sensitive(const orc_extractor *e, int level);
+
+/* Frame::ComputeStereoMatches (Frame.cc:2142-2316) on the pyramids held by eL / eR.
+ * uright/depth: nL floats (-1 = no match).  Optional debug arrays (may be NULL), nL entries:
+ *   best_dist (Hamming of the chosen candidate, 100 if none), best_idx (right index or -1),
+ *   best_sad (SAD of accepted matches before outlier rejection, -1 otherwise). */
+int orc_stereo_match(const orc_extractor *eL, const orc_extractor *eR,
+                     const orc_keypoint *kL, int nL, const uint8_t *dL,
+                     const orc_keypoint *kR, int nR, const uint8_t *dR,
+                     float bf, float maxD, float *uright, float *depth,
+                     int *best_dist, int *best_idx, int *best_sad);
+
+/* ORBmatcher::DescriptorDistance (ORBmatcher.cc:2704-2720) */
+int orc_hamming256(const void *a, const void *b);
+
+/* restated OpenCV primitives, exported for the known-answer tests */
+void orc_resize_linear_u8(const uint8_t *src, int sw, int sh, ptrdiff_t spitch,
+                          uint8_t *dst, int dw, int dh, ptrdiff_t dpitch);
+int orc_fast9_16(const uint8_t *img, int w, int h, ptrdiff_t pitch, int threshold,
+                 int cap, int *x, int *y, int *resp);
+void orc_gaussian7x7_s2(const uint8_t *src, int w, int h, ptrdiff_t spitch, uint8_t *dst, ptrdiff_t dpitch);
+float orc_fast_atan2(float y, float x);
+int orc_cv_round(double v);
+/* DistributeOctTree alone (ORBextractor.cc:539-763); in/out arrays of n / cap ints */
+int orc_distribute_octtree(const int *x, const int *y, const int *resp, int n,
+                           int minX, int maxX, int minY, int maxY, int N,
+                           int cap, int *ox, int *oy, int *oresp, int *tie_sensitive);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,46 @@
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def golden_names():
+    return sorted(p.stem for p in GOLDEN.glob("*.npz"))
+
+
+def load_golden(name):
+    """-> dict with params, left/right images (stored or regenerated + sha-checked), expected outputs."""
+    import hashlib
+
+    g = dict(np.load(GOLDEN / f"{name}.npz", allow_pickle=False))
+    if "left" not in g:
+        from pointslot_b200.synth import synth_pair
+
+        W, H, seed = (int(v) for v in g["src"])
+        L, R = synth_pair(W, H, seed)
+        if hashlib.sha256(L.tobytes()).hexdigest() != str(g["sha_left"]) or \
+           hashlib.sha256(R.tobytes()).hexdigest() != str(g["sha_right"]):
+            pytest.skip(f"{name}: synthetic input differs on this host's cv2/numpy build (inputs not stored)")
+        g["left"], g["right"] = L, R
+    p = g["params"]
+    g["params_t"] = (int(p[0]), float(p[1]), int(p[2]), int(p[3]), int(p[4]))
+    return g
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    import oracle
+
+    oracle.build()
+    return oracle
