@@ -1,0 +1,166 @@
+/*
+ * pslot_orb.h — C ABI of libpslot_orb.so: PointSLOT's per-frame stereo ORB front end on B200.
+ *
+ * The reference (pkzhou/PointSLOT) has no FFI layer; its boundary for this path is the C++ class
+ * surface that Tracking / Frame compile against.  Each entry point below names the reference
+ * interface it replaces (paths under /root/reference).  The C++ drop-in classes that keep the
+ * reference signatures verbatim and forward here live in pointslot_b200/cpp/ (see INTEGRATION.md).
+ *
+ * Conventions: every function returns 0 on success and a negative pslot_status on failure, never
+ * throws, and leaves a thread-local message retrievable with pslot_last_error().  Plain pointers and
+ * sizes only.  There is no CPU fallback: without a CUDA device every compute call fails with
+ * PSLOT_ERR_CUDA.  Contexts are not re-entrant; distinct contexts may be used from distinct host
+ * threads concurrently (each owns a CUDA stream), as Frame.cc:161-164 does with its two extractors.
+ */
+#ifndef PSLOT_ORB_H
+#define PSLOT_ORB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSLOT_ABI_VERSION 1
+
+typedef enum pslot_status {
+    PSLOT_OK = 0,
+    PSLOT_ERR_ARG = -1,      /* bad argument (null pointer, non-positive size, unsupported parameter) */
+    PSLOT_ERR_CAPACITY = -2, /* caller's output capacity too small; *n holds the required count */
+    PSLOT_ERR_CUDA = -3,     /* CUDA runtime / driver error (no device, launch failure, OOM) */
+    PSLOT_ERR_SHAPE = -4,    /* image too small for the pyramid (coarsest level needs >= 62 x 62 px) */
+    PSLOT_ERR_STATE = -5     /* call sequence error (e.g. stereo before extraction) */
+} pslot_status;
+
+/* Layout-identical to cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id. */
+typedef struct pslot_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} pslot_keypoint;
+
+typedef struct pslot_orb pslot_orb;     /* one extractor == one ORB_SLAM2::ORBextractor object */
+typedef struct pslot_batch pslot_batch; /* throughput context: batches of independent stereo pairs */
+
+const char *pslot_last_error(void);
+int pslot_abi_version(void);
+/* Number of visible CUDA devices, or a negative pslot_status. */
+int pslot_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Extractor — replaces class ORBextractor (include/ORBextractor.h:45-111, src/ORBextractor.cc).
+ * --------------------------------------------------------------------------------------------- */
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * (ORBextractor.cc:410-470).  device = CUDA ordinal. */
+int pslot_orb_create(pslot_orb **ctx, int nfeatures, float scale_factor, int nlevels,
+                     int ini_th_fast, int min_th_fast, int device);
+void pslot_orb_destroy(pslot_orb *ctx);
+
+/* GetLevels / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares (ORBextractor.h:63-83) and mnFeaturesPerLevel (:103).
+ * Each non-null array receives nlevels entries. */
+int pslot_orb_levels(const pslot_orb *ctx);
+int pslot_orb_tables(const pslot_orb *ctx, float *scale, float *inv_scale, float *sigma2,
+                     float *inv_sigma2, int32_t *features_per_level);
+/* Upper bound on the number of keypoints one image can yield (the reference overshoots nfeatures by
+ * up to 3 per level, ORBextractor.cc:669-737): size kps / desc32 with this. */
+int pslot_orb_max_keypoints(const pslot_orb *ctx);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors); the mask is ignored there too
+ * (ORBextractor.cc:1043-1105).  img: CV_8UC1, h rows of w bytes, row stride `pitch` bytes (host
+ * memory).  Writes *n keypoints (level-ascending, quadtree list order inside a level) and *n x 32
+ * descriptor bytes.  Synchronous.  Empty image (w<=0 || h<=0 || !img): *n = 0, returns PSLOT_OK and
+ * leaves kps/desc32 untouched (:1046-1047). */
+int pslot_orb_extract(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch,
+                      pslot_keypoint *kps, uint8_t *desc32, int cap, int *n);
+
+/* Backing store of the public member std::vector<cv::Mat> mvImagePyramid (ORBextractor.h:85,
+ * filled by ComputePyramid, ORBextractor.cc:1107-1132).  Copies level `level` of the most recent
+ * extraction to host memory (dst may be NULL to query the size only).  The 19-px replicated frame of
+ * the reference is not materialised: no consumer reads it. */
+int pslot_orb_level(pslot_orb *ctx, int level, uint8_t *dst, ptrdiff_t pitch, int *w, int *h);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stereo matcher — replaces Frame::ComputeStereoMatches (src/Frame.cc:2142-2316).  Also covers
+ * Frame::ComputeObjStereoMatches (Frame.cc:2318-2503), which is the same routine on the object
+ * keypoint subset, because the keypoint/descriptor sets are explicit arguments.
+ *
+ * Reads the un-blurred pyramids of the most recent extraction held by ctx_l / ctx_r (the reference
+ * reads mpORBextractorLeft/Right->mvImagePyramid, Frame.cc:2238,2256).  bf = mbf.  max_d replaces
+ * the reference's `mbf/mb` with `mb` uninitialised at that point (Frame.cc:2172-2174 vs :197):
+ * pass mbf/(mbf/fx) for the intended behaviour, INFINITY for "mb == 0".
+ * u_right / depth receive n_l floats each (-1 = no match), i.e. mvuRight / mvDepth.
+ * --------------------------------------------------------------------------------------------- */
+int pslot_stereo_match(pslot_orb *ctx_l, pslot_orb *ctx_r,
+                       const pslot_keypoint *kps_l, int n_l, const uint8_t *desc_l,
+                       const pslot_keypoint *kps_r, int n_r, const uint8_t *desc_r,
+                       float bf, float max_d, float *u_right, float *depth);
+
+/* static int ORBmatcher::DescriptorDistance(const cv::Mat&, const cv::Mat&) (ORBmatcher.cc:2704-2720):
+ * Hamming distance of two 32-byte descriptors.  Host-side (one popcount pair is not device work);
+ * the device matcher uses the same definition inside the stereo kernel. */
+int pslot_hamming256(const void *a, const void *b);
+
+/* ---------------------------------------------------------------------------------------------
+ * Throughput API — independent stereo pairs of one geometry, processed `max_pairs` at a time on one
+ * GPU stream: both extractions (Frame.cc:161-164) + ComputeStereoMatches (:173) per pair, with no
+ * host round trip in between.  This is the data-parallel form of the Frame stereo constructor path
+ * used for batch / multi-GPU processing; pairs never interact.
+ * --------------------------------------------------------------------------------------------- */
+/* stream: a cudaStream_t to run on (e.g. torch.cuda.Stream().cuda_stream), or NULL to create one. */
+int pslot_batch_create(pslot_batch **b, int nfeatures, float scale_factor, int nlevels,
+                       int ini_th_fast, int min_th_fast, int width, int height, int max_pairs,
+                       int device, void *stream);
+void pslot_batch_destroy(pslot_batch *b);
+int pslot_batch_max_keypoints(const pslot_batch *b); /* per-image capacity K of the output arrays */
+void *pslot_batch_stream(const pslot_batch *b);      /* the cudaStream_t all work is enqueued on */
+
+/* Host-memory outputs of one batch; image i of view v owns rows [ (v*npairs+i)*K, ... +K ).
+ *   counts  [2*npairs]          keypoints per image (left images first, then right images)
+ *   kps     [2*npairs*K]        pslot_keypoint
+ *   desc    [2*npairs*K*32]     descriptors
+ *   u_right [npairs*K], depth [npairs*K]   per LEFT keypoint, -1 = none
+ * Pointers may be pageable or pinned (pinned makes the copies asynchronous). */
+typedef struct pslot_batch_out {
+    int32_t *counts;
+    pslot_keypoint *kps;
+    uint8_t *desc;
+    float *u_right;
+    float *depth;
+} pslot_batch_out;
+
+/* Enqueue one batch: left / right point to npairs images each (image stride `image_stride` bytes,
+ * row stride `pitch` bytes), in HOST memory when host_input != 0, else in DEVICE memory.  With
+ * out == NULL the results stay on the device (kernel-only timing).  Asynchronous with respect to
+ * the host; call pslot_batch_wait before reading `out` or reusing the input buffers. */
+int pslot_batch_submit(pslot_batch *b, const uint8_t *left, const uint8_t *right, ptrdiff_t pitch,
+                       ptrdiff_t image_stride, int npairs, int host_input, float bf, float max_d,
+                       const pslot_batch_out *out);
+int pslot_batch_wait(pslot_batch *b);
+/* Number of kernels pslot_batch_submit launches per call (for launch accounting). */
+int pslot_batch_kernel_launches(const pslot_batch *b);
+/* Device pointers of the last batch's results (same layout as pslot_batch_out), valid until the next
+ * submit; for callers that keep the features on the GPU. */
+int pslot_batch_device_out(const pslot_batch *b, pslot_batch_out *dev);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage accessors for the parity tests (not needed by a drop-in caller).
+ * --------------------------------------------------------------------------------------------- */
+/* FAST candidates handed to the quadtree for `level` of the last pslot_orb_extract: window-relative
+ * x, y and the FAST response, in the reference's order (cells row-major, raster inside a cell;
+ * ORBextractor.cc:789-829). */
+int pslot_orb_debug_candidates(pslot_orb *ctx, int level, int cap, int32_t *x, int32_t *y,
+                               int32_t *resp, int *n);
+/* Keypoints of `level` after DistributeOctTree + border offset (level coordinates, list order;
+ * ORBextractor.cc:831-847) with their IC_Angle orientation (:850-852). */
+int pslot_orb_debug_level_keypoints(pslot_orb *ctx, int level, int cap, int32_t *x, int32_t *y,
+                                    int32_t *resp, float *angle, int *n);
+/* Per-left-keypoint intermediates of the last pslot_stereo_match: best Hamming distance (100 = none),
+ * index of the chosen right keypoint (-1 = none), SAD of accepted matches before the median test (-1). */
+int pslot_stereo_debug(pslot_orb *ctx_l, int n_l, int32_t *best_dist, int32_t *best_idx, int32_t *best_sad);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSLOT_ORB_H */

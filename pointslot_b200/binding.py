@@ -1,0 +1,269 @@
+"""ctypes binding of include/pslot_orb.h — the host-side mirror used by tests and bench.py.
+
+Mirrors the reference's interface for this path (ORBextractor / Frame stereo constructor):
+  OrbExtractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)   ~ ORBextractor.h:45-111
+  OrbExtractor.extract(image) -> (keypoints, descriptors)               ~ operator() (ORBextractor.cc:1043)
+  stereo_match(extL, extR, kL, dL, kR, dR, bf, maxD) -> (uRight, depth) ~ Frame::ComputeStereoMatches
+  StereoBatch: many independent pairs per call on one GPU stream.
+There is no fallback: if libpslot_orb.so is missing or no CUDA device exists, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpslot_orb.so"
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+     ("octave", "<i4"), ("class_id", "<i4")]
+)
+
+# every symbol include/pslot_orb.h declares (tests check the .so exports exactly these)
+ABI_SYMBOLS = [
+    "pslot_last_error", "pslot_abi_version", "pslot_device_count",
+    "pslot_orb_create", "pslot_orb_destroy", "pslot_orb_levels", "pslot_orb_tables", "pslot_orb_max_keypoints",
+    "pslot_orb_extract", "pslot_orb_level", "pslot_stereo_match", "pslot_hamming256",
+    "pslot_batch_create", "pslot_batch_destroy", "pslot_batch_max_keypoints", "pslot_batch_stream",
+    "pslot_batch_submit", "pslot_batch_wait", "pslot_batch_kernel_launches", "pslot_batch_device_out",
+    "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug",
+]
+
+
+class PslotError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pslot error {code}: {msg}")
+        self.code = code
+
+
+class BatchOut(C.Structure):
+    _fields_ = [("counts", C.c_void_p), ("kps", C.c_void_p), ("desc", C.c_void_p),
+                ("u_right", C.c_void_p), ("depth", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libpslot_orb.so (raises if it has not been built — there is no CPU path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -m pointslot_b200.build` (needs nvcc). "
+                           "pointslot_b200 has no CPU fallback.")
+    L = C.CDLL(str(LIB_PATH))
+    vp, ip = C.c_void_p, C.POINTER(C.c_int)
+    L.pslot_last_error.restype = C.c_char_p
+    L.pslot_orb_create.argtypes = [C.POINTER(vp), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.pslot_orb_destroy.argtypes = [vp]
+    L.pslot_orb_destroy.restype = None
+    L.pslot_orb_levels.argtypes = [vp]
+    L.pslot_orb_tables.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.pslot_orb_max_keypoints.argtypes = [vp]
+    L.pslot_orb_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_ssize_t, vp, vp, C.c_int, ip]
+    L.pslot_orb_level.argtypes = [vp, C.c_int, vp, C.c_ssize_t, ip, ip]
+    L.pslot_stereo_match.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_float, C.c_float, vp, vp]
+    L.pslot_hamming256.argtypes = [vp, vp]
+    L.pslot_batch_create.argtypes = [C.POINTER(vp), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, vp]
+    L.pslot_batch_destroy.argtypes = [vp]
+    L.pslot_batch_destroy.restype = None
+    L.pslot_batch_max_keypoints.argtypes = [vp]
+    L.pslot_batch_stream.argtypes = [vp]
+    L.pslot_batch_stream.restype = vp
+    L.pslot_batch_submit.argtypes = [vp, vp, vp, C.c_ssize_t, C.c_ssize_t, C.c_int, C.c_int, C.c_float, C.c_float,
+                                     C.POINTER(BatchOut)]
+    L.pslot_batch_wait.argtypes = [vp]
+    L.pslot_batch_kernel_launches.argtypes = [vp]
+    L.pslot_batch_device_out.argtypes = [vp, C.POINTER(BatchOut)]
+    L.pslot_orb_debug_candidates.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, ip]
+    L.pslot_orb_debug_level_keypoints.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, ip]
+    L.pslot_stereo_debug.argtypes = [vp, C.c_int, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc < 0:
+        raise PslotError(rc, lib().pslot_last_error().decode(errors="replace"))
+    return rc
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count() -> int:
+    return _check(lib().pslot_device_count())
+
+
+def hamming256(a, b) -> int:
+    """ORBmatcher::DescriptorDistance (reference src/ORBmatcher.cc:2704-2720)."""
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    assert a.size == 32 and b.size == 32
+    return lib().pslot_hamming256(_p(a), _p(b))
+
+
+def max_disparity(bf: float, fx: float) -> float:
+    """The value the reference intends for maxD: mb = mbf/fx, maxD = mbf/mb in float32."""
+    mb = np.float32(bf) / np.float32(fx)
+    return float(np.float32(bf) / mb)
+
+
+class OrbExtractor:
+    """Drop-in mirror of ORB_SLAM2::ORBextractor over the C ABI."""
+
+    def __init__(self, nfeatures: int, scale_factor: float, nlevels: int, ini_th: int, min_th: int, device: int = 0):
+        h = C.c_void_p()
+        _check(lib().pslot_orb_create(C.byref(h), nfeatures, scale_factor, nlevels, ini_th, min_th, device))
+        self._h = h
+        self.nlevels = nlevels
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pslot_orb_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def tables(self):
+        n = self.nlevels
+        out = [np.zeros(n, np.float32) for _ in range(4)] + [np.zeros(n, np.int32)]
+        _check(lib().pslot_orb_tables(self._h, *[_p(a) for a in out]))
+        return dict(zip(("scale", "inv_scale", "sigma2", "inv_sigma2", "features_per_level"), out))
+
+    def extract(self, img: np.ndarray):
+        """-> (keypoints [n] KEYPOINT_DTYPE, descriptors [n,32] uint8)"""
+        assert img.dtype == np.uint8 and img.ndim == 2 and (img.size == 0 or img.strides[1] == 1)
+        cap = _check(lib().pslot_orb_max_keypoints(self._h))
+        h, w = img.shape
+        for _ in range(2):
+            kps = np.zeros(cap, KEYPOINT_DTYPE)
+            desc = np.zeros((cap, 32), np.uint8)
+            n = C.c_int(0)
+            rc = lib().pslot_orb_extract(self._h, _p(img), w, h, img.strides[0] if img.size else 0, _p(kps), _p(desc),
+                                         cap, C.byref(n))
+            if rc == -2:  # PSLOT_ERR_CAPACITY
+                cap = n.value
+                continue
+            _check(rc)
+            return kps[: n.value].copy(), desc[: n.value].copy()
+        raise PslotError(-2, "capacity retry failed")
+
+    def level(self, level: int) -> np.ndarray:
+        """mvImagePyramid[level] of the last extraction (borderless)."""
+        w, h = C.c_int(0), C.c_int(0)
+        _check(lib().pslot_orb_level(self._h, level, None, 0, C.byref(w), C.byref(h)))
+        out = np.empty((h.value, w.value), np.uint8)
+        _check(lib().pslot_orb_level(self._h, level, _p(out), out.strides[0], C.byref(w), C.byref(h)))
+        return out
+
+    def debug_candidates(self, level: int):
+        cap = 1 << 18
+        x = np.empty(cap, np.int32); y = np.empty(cap, np.int32); r = np.empty(cap, np.int32)
+        n = C.c_int(0)
+        _check(lib().pslot_orb_debug_candidates(self._h, level, cap, _p(x), _p(y), _p(r), C.byref(n)))
+        return x[: n.value].copy(), y[: n.value].copy(), r[: n.value].copy()
+
+    def debug_level_keypoints(self, level: int):
+        cap = 1 << 16
+        x = np.empty(cap, np.int32); y = np.empty(cap, np.int32); r = np.empty(cap, np.int32)
+        a = np.empty(cap, np.float32)
+        n = C.c_int(0)
+        _check(lib().pslot_orb_debug_level_keypoints(self._h, level, cap, _p(x), _p(y), _p(r), _p(a), C.byref(n)))
+        return x[: n.value].copy(), y[: n.value].copy(), r[: n.value].copy(), a[: n.value].copy()
+
+
+def stereo_match(ext_l: OrbExtractor, ext_r: OrbExtractor, kL, dL, kR, dR, bf: float, max_d: float, debug=False):
+    """Frame::ComputeStereoMatches (reference src/Frame.cc:2142-2316) -> (mvuRight, mvDepth)."""
+    kL = np.ascontiguousarray(kL, KEYPOINT_DTYPE); kR = np.ascontiguousarray(kR, KEYPOINT_DTYPE)
+    dL = np.ascontiguousarray(dL, np.uint8); dR = np.ascontiguousarray(dR, np.uint8)
+    nL, nR = len(kL), len(kR)
+    ur = np.full(max(nL, 1), -1, np.float32); dp = np.full(max(nL, 1), -1, np.float32)
+    _check(lib().pslot_stereo_match(ext_l._h, ext_r._h, _p(kL), nL, _p(dL), _p(kR), nR, _p(dR),
+                                    C.c_float(bf), C.c_float(max_d), _p(ur), _p(dp)))
+    if debug:
+        bd = np.zeros(max(nL, 1), np.int32); bi = np.zeros(max(nL, 1), np.int32); bs = np.zeros(max(nL, 1), np.int32)
+        if nL:
+            _check(lib().pslot_stereo_debug(ext_l._h, nL, _p(bd), _p(bi), _p(bs)))
+        return ur[:nL], dp[:nL], bd[:nL], bi[:nL], bs[:nL]
+    return ur[:nL], dp[:nL]
+
+
+class StereoBatch:
+    """Throughput context: up to max_pairs independent stereo pairs per submit on one GPU stream."""
+
+    def __init__(self, params, width: int, height: int, max_pairs: int, device: int = 0, stream: int = 0):
+        h = C.c_void_p()
+        nf, sf, nl, it, mt = params
+        _check(lib().pslot_batch_create(C.byref(h), nf, sf, nl, it, mt, width, height, max_pairs, device,
+                                        C.c_void_p(stream) if stream else None))
+        self._h = h
+        self.W, self.H, self.max_pairs = width, height, max_pairs
+        self.K = _check(lib().pslot_batch_max_keypoints(h))
+        self.kernel_launches = _check(lib().pslot_batch_kernel_launches(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pslot_batch_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def stream(self) -> int:
+        return lib().pslot_batch_stream(self._h) or 0
+
+    def alloc_out(self, npairs: int, pinned: bool = False):
+        """Host output arrays in the layout pslot_batch_out documents."""
+        K = self.K
+        shapes = dict(counts=((2 * npairs,), np.int32), kps=((2 * npairs, K), KEYPOINT_DTYPE),
+                      desc=((2 * npairs, K, 32), np.uint8), u_right=((npairs, K), np.float32),
+                      depth=((npairs, K), np.float32))
+        out = {}
+        for k, (shp, dt) in shapes.items():
+            if pinned:
+                import torch
+                nbytes = int(np.prod(shp)) * np.dtype(dt).itemsize
+                t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+                out["_t_" + k] = t
+                out[k] = t.numpy().view(dt).reshape(shp)
+            else:
+                out[k] = np.zeros(shp, dt)
+        return out
+
+    def submit_ptr(self, left_ptr: int, right_ptr: int, pitch: int, image_stride: int, npairs: int, host_input: bool,
+                   bf: float, max_d: float, out=None):
+        bo = None
+        if out is not None:
+            bo = BatchOut(*(out[k].ctypes.data for k in ("counts", "kps", "desc", "u_right", "depth")))
+        _check(lib().pslot_batch_submit(self._h, C.c_void_p(left_ptr), C.c_void_p(right_ptr), pitch, image_stride,
+                                        npairs, 1 if host_input else 0, C.c_float(bf), C.c_float(max_d),
+                                        C.byref(bo) if bo is not None else None))
+
+    def submit(self, left: np.ndarray, right: np.ndarray, bf: float, max_d: float, out=None):
+        """left/right: uint8 [npairs, H, W] host arrays (C-contiguous rows)."""
+        assert left.dtype == np.uint8 and left.shape == right.shape and left.ndim == 3
+        assert left.strides[2] == 1 and right.strides == left.strides
+        self.submit_ptr(left.ctypes.data, right.ctypes.data, left.strides[1], left.strides[0], left.shape[0], True,
+                        bf, max_d, out)
+
+    def wait(self):
+        _check(lib().pslot_batch_wait(self._h))
+
+    def run(self, left, right, bf, max_d):
+        """Synchronous convenience: -> list of per-pair dicts (kL, dL, kR, dR, u_right, depth)."""
+        n = left.shape[0]
+        out = self.alloc_out(n)
+        self.submit(left, right, bf, max_d, out)
+        self.wait()
+        res = []
+        for i in range(n):
+            nl, nr = int(out["counts"][i]), int(out["counts"][n + i])
+            res.append(dict(kL=out["kps"][i, :nl].copy(), dL=out["desc"][i, :nl].copy(),
+                            kR=out["kps"][n + i, :nr].copy(), dR=out["desc"][n + i, :nr].copy(),
+                            u_right=out["u_right"][i, :nl].copy(), depth=out["depth"][i, :nl].copy()))
+        return res

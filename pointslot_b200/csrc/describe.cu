@@ -1,0 +1,221 @@
+// describe.cu — K4+K5+K6 fused: IC_Angle orientation (reference src/ORBextractor.cc:77-104, 472-479),
+// GaussianBlur 7x7 sigma 2 (:1085-1086) and the steered-BRIEF descriptor (:107-147, 1034-1041), plus
+// the output assembly (:834-847, 1095-1103).  One warp per keypoint.
+//
+// The reference blurs every whole level and then gathers 512 samples per keypoint.  Here each warp
+// stages the 43x43 raw patch around its keypoint in shared memory once (37x37 blurred support,
+// radius 18 = max |rotated pattern coordinate|, plus the 3-px blur halo), and derives from it
+//   * the intensity-centroid moments over the radius-15 disc (integer, exact) -> fastAtan2 angle,
+//   * the separable fixed-point blur [18 34 48 56 48 34 18]/256 with one final rounding
+//     (v + 2^15) >> 16, BORDER_REFLECT_101 applied at the true image edge while staging,
+//   * the 256 pattern tests; lane i produces descriptor byte i.
+// No blurred level is ever written to or read from global memory.
+//
+// Float islands follow DESIGN.md parity rule 3: single-rounded __f*_rn ops (no FMA), cos/sin in
+// double then rounded to float, cvRound = round-half-even.
+//
+// Bound: shared memory (≈8.5 k shared accesses per keypoint); algorithmic global bytes per keypoint
+// = 1849 (patch) + 4 (lkp) + 28 + 32 (outputs).
+#include "pslot_internal.h"
+
+namespace {
+
+constexpr int DW = 4;           // warps (keypoints) per CTA
+constexpr int PR = 21;          // raw patch radius
+constexpr int PD = 2 * PR + 1;  // 43
+constexpr int RS = 44;          // raw row stride (bytes): 11 words, odd -> conflict-free row-parallel access
+constexpr int BR = 18;          // blurred patch radius
+constexpr int BD = 2 * BR + 1;  // 37
+constexpr int HS = 38;          // h-pass row stride (u16): 19 words, odd
+constexpr int BS = 40;          // blurred row stride (bytes)
+
+__constant__ int8_t c_pattern[1024] = {
+#include "../../include/pslot_orb_pattern.inc"
+};
+// umax[v]: half-width of the radius-15 disc at row v (ORBextractor.cc:454-469)
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+struct WarpSmem {
+    uint8_t raw[PD * RS];
+    uint16_t hp[PD * HS];
+    uint8_t blur[BD * BS];
+};
+
+__device__ __forceinline__ int reflect101(int i, int n)
+{
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+// cv::fastAtan2 (OpenCV 4.13 atanImpl<float>), degrees; float32, one rounding per operation.
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    const float eps = (float)2.2204460492503131e-16;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(DW * 32)
+k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
+           const uint32_t *__restrict__ lkp, const int *__restrict__ lkp_count,
+           pslot_keypoint *__restrict__ out_kps, uint8_t *__restrict__ out_desc, int *__restrict__ out_count)
+{
+    __shared__ __align__(16) WarpSmem sm[DW];
+    __shared__ uint32_t s_pat[256]; // [t][lane]: test 8*lane + t, bytes x0,y0,x1,y1
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slot = blockIdx.y;
+    for (int i = tid; i < 256; i += DW * 32) {
+        const int t = i >> 5, ln = i & 31;
+        const int8_t *p = c_pattern + 4 * (8 * ln + t);
+        s_pat[i] = (uint32_t)(uint8_t)p[0] | ((uint32_t)(uint8_t)p[1] << 8) | ((uint32_t)(uint8_t)p[2] << 16) |
+                   ((uint32_t)(uint8_t)p[3] << 24);
+    }
+    __syncthreads();
+
+    // which keypoint: global index over the per-level capacity segments
+    int idx = blockIdx.x * DW + warp;
+    if (idx >= g.lkp_per_slot) return;
+    int l = 0;
+    while (l + 1 < g.nlevels && idx >= g.lv[l + 1].kp_base) ++l;
+    const LevelGeom &L = g.lv[l];
+    const int i = idx - L.kp_base;
+    const int *cnt = lkp_count + (size_t)slot * g.nlevels;
+    int out_base = 0, total = 0;
+    for (int k = 0; k < g.nlevels; ++k) {
+        const int c = cnt[k];
+        if (k < l) out_base += c;
+        total += c;
+    }
+    if (idx == 0 && lane == 0) out_count[slot] = total;
+    if (i >= cnt[l]) return;
+
+    const uint32_t kp = lkp[(size_t)slot * g.lkp_per_slot + idx];
+    const int kx = pslot_px(kp), ky = pslot_py(kp), kr = pslot_pr(kp);
+    const uint8_t *img = pyr.lv[l] + (size_t)slot * pyr.slot_stride[l];
+    WarpSmem &S = sm[warp];
+
+    // ---- stage the 43x43 raw patch (reflect-101 at the image edge) ------------------------------
+    const int x0 = kx - PR, y0 = ky - PR;
+    const bool interior = x0 >= 0 && y0 >= 0 && x0 + PD <= L.w && y0 + PD <= L.h;
+    if (interior) {
+        for (int e = lane; e < PD * PD; e += 32) {
+            const int r = e / PD, c = e - r * PD;
+            S.raw[r * RS + c] = __ldg(img + (size_t)(y0 + r) * L.pitch + x0 + c);
+        }
+    } else {
+        for (int e = lane; e < PD * PD; e += 32) {
+            const int r = e / PD, c = e - r * PD;
+            S.raw[r * RS + c] = __ldg(img + (size_t)reflect101(y0 + r, L.h) * L.pitch + reflect101(x0 + c, L.w));
+        }
+    }
+    __syncwarp();
+
+    // ---- IC_Angle: lane r owns disc row v = r - 15 -------------------------------------------------
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int v = lane - PSLOT_HALF_PATCH;
+        const int d = c_umax[v < 0 ? -v : v];
+        const uint8_t *row = S.raw + (PR + v) * RS + PR;
+        int sum = 0;
+        for (int u = -d; u <= d; ++u) {
+            const int val = row[u];
+            m10 += u * val;
+            sum += val;
+        }
+        m01 = v * sum;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- horizontal blur pass: lane = patch row, sliding 7-tap window -------------------------------
+    for (int r = lane; r < PD; r += 32) {
+        const uint8_t *row = S.raw + r * RS;
+        uint16_t *hrow = S.hp + r * HS;
+        int a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3], a4 = row[4], a5 = row[5];
+        for (int c = 0; c < BD; ++c) {
+            const int a6 = row[c + 6];
+            hrow[c] = (uint16_t)(18 * (a0 + a6) + 34 * (a1 + a5) + 48 * (a2 + a4) + 56 * a3);
+            a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = a5; a5 = a6;
+        }
+    }
+    __syncwarp();
+    // ---- vertical pass: lane = patch column ---------------------------------------------------------
+    for (int c = lane; c < BD; c += 32) {
+        const uint16_t *col = S.hp + c;
+        int a0 = col[0], a1 = col[HS], a2 = col[2 * HS], a3 = col[3 * HS], a4 = col[4 * HS], a5 = col[5 * HS];
+        for (int r = 0; r < BD; ++r) {
+            const int a6 = col[(r + 6) * HS];
+            const int v = 18 * (a0 + a6) + 34 * (a1 + a5) + 48 * (a2 + a4) + 56 * a3;
+            S.blur[r * BS + c] = (uint8_t)((v + 32768) >> 16);
+            a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = a5; a5 = a6;
+        }
+    }
+    __syncwarp();
+
+    // ---- steered BRIEF: lane -> descriptor byte (:107-147) ------------------------------------------
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
+    const float ang = __fmul_rn(angle, factorPI);
+    double sd, cd;
+    sincos((double)ang, &sd, &cd);
+    const float a = (float)cd, b = (float)sd;
+    const uint8_t *center = S.blur + BR * BS + BR;
+    int val = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const uint32_t p = s_pat[t * 32 + lane];
+        const float px0 = (float)(int8_t)(p & 0xFF), py0 = (float)(int8_t)((p >> 8) & 0xFF);
+        const float px1 = (float)(int8_t)((p >> 16) & 0xFF), py1 = (float)(int8_t)(p >> 24);
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(px0, b), __fmul_rn(py0, a)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(px0, a), __fmul_rn(py0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(px1, b), __fmul_rn(py1, a)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(px1, a), __fmul_rn(py1, b)));
+        const int t0 = center[r0 * BS + c0], t1 = center[r1 * BS + c1];
+        val |= (t0 < t1) << t;
+    }
+    const size_t o = (size_t)slot * g.kp_cap_total + out_base + i;
+    out_desc[o * 32 + lane] = (uint8_t)val;
+
+    // ---- keypoint record (:834-847, 1095-1103) ------------------------------------------------------
+    if (lane == 0) {
+        pslot_keypoint k;
+        k.x = (float)kx; k.y = (float)ky;
+        if (l != 0) { k.x = __fmul_rn(k.x, L.scale); k.y = __fmul_rn(k.y, L.scale); }
+        k.size = (float)L.patch_size;
+        k.angle = angle;
+        k.response = (float)kr;
+        k.octave = l;
+        k.class_id = -1;
+        out_kps[o] = k;
+    }
+}
+
+} // namespace
+
+int launch_describe(const Geom &g, const PyrPtrs &pyr, const uint32_t *lkp, const int *lkp_count,
+                    pslot_keypoint *out_kps, uint8_t *out_desc, int *out_count, int nslots, cudaStream_t st)
+{
+    dim3 grid((g.lkp_per_slot + DW - 1) / DW, nslots);
+    k_describe<<<grid, DW * 32, 0, st>>>(g, pyr, lkp, lkp_count, out_kps, out_desc, out_count);
+    return 1;
+}

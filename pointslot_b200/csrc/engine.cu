@@ -1,0 +1,669 @@
+// engine.cu — host side of libpslot_orb.so: geometry tables, device buffers, launch sequencing and the
+// C ABI of include/pslot_orb.h.  No CPU compute path exists here: every result comes from the kernels
+// in pyramid.cu / fast.cu / quadtree.cu / describe.cu / stereo.cu.
+//
+// Host float code below reproduces the reference constructor arithmetic (src/ORBextractor.cc:410-470,
+// 1107-1132, 765-787, 543-545); build with -ffp-contract=off so no expression is fused.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "pslot_internal.h"
+
+namespace {
+
+thread_local char t_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(PSLOT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                        \
+    } while (0)
+
+inline int cv_round(double v) { return (int)lrint(v); } // cvRound: half-to-even
+
+struct Tables {
+    float sf[PSLOT_MAX_LEVELS], inv_sf[PSLOT_MAX_LEVELS], sigma2[PSLOT_MAX_LEVELS], inv_sigma2[PSLOT_MAX_LEVELS];
+    int per_level[PSLOT_MAX_LEVELS];
+};
+
+struct Params {
+    int nfeatures;
+    float scale_factor;
+    int nlevels, ini_th, min_th;
+};
+
+// ORBextractor::ORBextractor (ORBextractor.cc:410-446)
+void make_tables(const Params &p, Tables &t)
+{
+    const double scaleFactor = (double)p.scale_factor; // ORBextractor.h:98: double member
+    t.sf[0] = 1.0f;
+    t.sigma2[0] = 1.0f;
+    for (int i = 1; i < p.nlevels; ++i) {
+        t.sf[i] = (float)((double)t.sf[i - 1] * scaleFactor);
+        t.sigma2[i] = t.sf[i] * t.sf[i];
+    }
+    for (int i = 0; i < p.nlevels; ++i) {
+        t.inv_sf[i] = 1.0f / t.sf[i];
+        t.inv_sigma2[i] = 1.0f / t.sigma2[i];
+    }
+    const float factor = (float)(1.0 / scaleFactor);
+    float nDesired = (float)p.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)p.nlevels));
+    int sum = 0;
+    for (int l = 0; l < p.nlevels - 1; ++l) {
+        t.per_level[l] = cv_round((double)nDesired);
+        sum += t.per_level[l];
+        nDesired *= factor;
+    }
+    t.per_level[p.nlevels - 1] = std::max(p.nfeatures - sum, 0);
+}
+
+// taps of cv::resize INTER_LINEAR for one axis (OpenCV resize.cpp, 8-bit path)
+void resize_taps(int n_dst, int n_src, ResizeTap *out, int padded)
+{
+    const double scale = 1.0 / ((double)n_dst / (double)n_src);
+    for (int d = 0; d < n_dst; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= n_src - 1) { s = n_src - 1; f = 0.f; }
+        out[d].s0 = (uint16_t)s;
+        out[d].s1 = (uint16_t)std::min(s + 1, n_src - 1);
+        out[d].c0 = (int16_t)cv_round((double)((1.f - f) * 2048.f));
+        out[d].c1 = (int16_t)cv_round((double)(f * 2048.f));
+    }
+    for (int d = n_dst; d < padded; ++d) out[d] = out[n_dst - 1];
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Engine {
+    Params p{};
+    Tables t{};
+    int device = 0;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+
+    int W = 0, H = 0, S = 0; // configured geometry / slot capacity
+    Geom g{};
+    PyrPtrs pyr{};
+    bool has_pyramid = false;
+
+    uint8_t *d_pyr = nullptr;
+    ResizeTap *d_taps = nullptr;
+    int *d_cell_count = nullptr, *d_cell_prefix = nullptr;
+    uint32_t *d_cell_cand = nullptr, *d_qt_keys = nullptr;
+    uint16_t *d_qt_nodes = nullptr;
+    uint32_t *d_lkp = nullptr;
+    int *d_lkp_count = nullptr, *d_err = nullptr;
+    // outputs: one block [counts | kps | desc] so a whole batch comes back in few copies
+    unsigned char *d_out = nullptr;
+    size_t out_bytes = 0, off_kps = 0, off_desc = 0;
+    int *d_out_count = nullptr;
+    pslot_keypoint *d_out_kps = nullptr;
+    uint8_t *d_out_desc = nullptr;
+    // stereo results, [S/2 (>=1)][K]
+    float *d_uright = nullptr, *d_depth = nullptr;
+    int *d_best_dist = nullptr, *d_best_idx = nullptr, *d_sad = nullptr;
+
+    ~Engine() { release(); if (own_stream && st) cudaStreamDestroy(st); }
+
+    void release()
+    {
+        cudaFree(d_pyr); cudaFree(d_taps); cudaFree(d_cell_count); cudaFree(d_cell_prefix);
+        cudaFree(d_cell_cand); cudaFree(d_qt_keys); cudaFree(d_qt_nodes); cudaFree(d_lkp);
+        cudaFree(d_lkp_count); cudaFree(d_err); cudaFree(d_out);
+        cudaFree(d_uright); cudaFree(d_depth); cudaFree(d_best_dist); cudaFree(d_best_idx); cudaFree(d_sad);
+        d_pyr = nullptr; d_taps = nullptr; d_cell_count = d_cell_prefix = nullptr; d_cell_cand = d_qt_keys = nullptr;
+        d_qt_nodes = nullptr; d_lkp = nullptr; d_lkp_count = d_err = nullptr; d_out = nullptr;
+        d_uright = d_depth = nullptr; d_best_dist = d_best_idx = d_sad = nullptr;
+        W = H = S = 0; has_pyramid = false;
+    }
+
+    int init(const Params &pp, int dev, void *stream)
+    {
+        if (pp.nlevels < 1 || pp.nlevels > PSLOT_MAX_LEVELS) return fail(PSLOT_ERR_ARG, "nlevels must be in [1,%d]", PSLOT_MAX_LEVELS);
+        if (pp.nfeatures < 1 || pp.nfeatures > 30000) return fail(PSLOT_ERR_ARG, "nfeatures must be in [1,30000]");
+        if (!(pp.scale_factor > 1.0f)) return fail(PSLOT_ERR_ARG, "scaleFactor must be > 1");
+        if (pp.min_th < 1 || pp.ini_th < pp.min_th || pp.ini_th > 254)
+            return fail(PSLOT_ERR_ARG, "need 1 <= minThFAST <= iniThFAST <= 254");
+        p = pp;
+        device = dev;
+        make_tables(p, t);
+        int ndev = 0;
+        CU(cudaGetDeviceCount(&ndev));
+        if (dev < 0 || dev >= ndev) return fail(PSLOT_ERR_CUDA, "CUDA device %d not available (%d visible)", dev, ndev);
+        CU(cudaSetDevice(dev));
+        if (stream) { st = (cudaStream_t)stream; own_stream = false; }
+        else { CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); own_stream = true; }
+        return PSLOT_OK;
+    }
+
+    // Geometry of every level for a w x h image (ORBextractor.cc:1111-1112, 773-787, 543-545).
+    int make_geom(int w, int h, Geom &G, std::vector<ResizeTap> &taps) const
+    {
+        if (w > 4096 || h > 4096) return fail(PSLOT_ERR_SHAPE, "image %dx%d exceeds 4096 px", w, h);
+        memset(&G, 0, sizeof(G));
+        G.nlevels = p.nlevels; G.ini_th = p.ini_th; G.min_th = p.min_th;
+        int cells = 0, cand = 0, lkp = 0, maxcap = 0;
+        taps.clear();
+        for (int l = 0; l < p.nlevels; ++l) {
+            LevelGeom &L = G.lv[l];
+            L.w = cv_round((double)((float)w * t.inv_sf[l]));
+            L.h = cv_round((double)((float)h * t.inv_sf[l]));
+            L.pitch = (int)align_up((size_t)std::max(L.w, 1), 128);
+            L.max_bx = L.w - PSLOT_EDGE + 3;
+            L.max_by = L.h - PSLOT_EDGE + 3;
+            const float width = (float)(L.max_bx - PSLOT_MINB), height = (float)(L.max_by - PSLOT_MINB);
+            L.n_cols = (int)(width / 30.f);
+            L.n_rows = (int)(height / 30.f);
+            if (L.n_cols < 1 || L.n_rows < 1)
+                return fail(PSLOT_ERR_SHAPE, "level %d of a %dx%d image is %dx%d: below the 62x62 minimum", l, w, h, L.w, L.h);
+            L.w_cell = (int)ceilf(width / (float)L.n_cols);
+            L.h_cell = (int)ceilf(height / (float)L.n_rows);
+            if (L.w_cell > 59 || L.h_cell > 59) return fail(PSLOT_ERR_SHAPE, "cell %dx%d too large", L.w_cell, L.h_cell);
+            L.cell_base = cells;
+            cells += L.n_cols * L.n_rows;
+            L.cand_stride = ((L.w_cell + 1) / 2) * ((L.h_cell + 1) / 2);
+            L.cand_base = cand;
+            cand += L.n_cols * L.n_rows * L.cand_stride;
+            L.quota = t.per_level[l];
+            const int wd = L.max_bx - PSLOT_MINB, hd = L.max_by - PSLOT_MINB;
+            L.n_ini = (int)roundf((float)wd / (float)hd);
+            if (L.n_ini < 1) return fail(PSLOT_ERR_SHAPE, "level %d aspect ratio gives no quadtree root", l);
+            L.hx = (float)wd / (float)L.n_ini;
+            L.kp_cap = std::max(L.quota + 3, 4 * L.n_ini) + 1;
+            L.kp_base = lkp;
+            lkp += L.kp_cap;
+            maxcap = std::max(maxcap, L.kp_cap);
+            L.scale = t.sf[l];
+            L.inv_scale = t.inv_sf[l];
+            L.patch_size = (int)(31.f * t.sf[l]);
+            if (l > 0) {
+                const LevelGeom &P = G.lv[l - 1];
+                const int px = (int)align_up((size_t)L.w, 4), py = (int)align_up((size_t)L.h, 4);
+                L.tab_x = (int)taps.size();
+                taps.resize(taps.size() + px);
+                resize_taps(L.w, P.w, taps.data() + L.tab_x, px);
+                L.tab_y = (int)taps.size();
+                taps.resize(taps.size() + py);
+                resize_taps(L.h, P.h, taps.data() + L.tab_y, py);
+            }
+        }
+        G.cells_per_slot = cells; G.cand_per_slot = cand; G.lkp_per_slot = lkp; G.kp_cap_total = lkp;
+        G.max_level_cap = maxcap;
+        int key_cap = 0;
+        if (quadtree_smem_bytes(G, &key_cap) > 200 * 1024)
+            return fail(PSLOT_ERR_ARG, "nfeatures too large for the on-chip quadtree tables");
+        return PSLOT_OK;
+    }
+
+    int configure(int w, int h, int nslots)
+    {
+        if (w == W && h == H && nslots <= S) return PSLOT_OK;
+        CU(cudaSetDevice(device));
+        Geom G;
+        std::vector<ResizeTap> taps;
+        int rc = make_geom(w, h, G, taps);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(st));
+        release();
+        g = G;
+        size_t off = 0;
+        size_t lvoff[PSLOT_MAX_LEVELS];
+        for (int l = 0; l < g.nlevels; ++l) {
+            lvoff[l] = off;
+            pyr.slot_stride[l] = (unsigned long long)g.lv[l].pitch * g.lv[l].h;
+            off += align_up((size_t)pyr.slot_stride[l] * nslots, 256);
+        }
+        CU(cudaMalloc(&d_pyr, off + 256));
+        for (int l = 0; l < g.nlevels; ++l) pyr.lv[l] = d_pyr + lvoff[l];
+        CU(cudaMalloc(&d_taps, sizeof(ResizeTap) * std::max<size_t>(taps.size(), 4)));
+        if (!taps.empty()) CU(cudaMemcpy(d_taps, taps.data(), sizeof(ResizeTap) * taps.size(), cudaMemcpyHostToDevice));
+        const size_t ns = (size_t)nslots;
+        CU(cudaMalloc(&d_cell_count, 4 * ns * g.cells_per_slot));
+        CU(cudaMalloc(&d_cell_prefix, 4 * ns * g.cells_per_slot));
+        CU(cudaMalloc(&d_cell_cand, 4 * ns * g.cand_per_slot));
+        CU(cudaMalloc(&d_qt_keys, 4 * ns * g.cand_per_slot));
+        CU(cudaMalloc(&d_qt_nodes, 2 * ns * g.cand_per_slot));
+        CU(cudaMalloc(&d_lkp, 4 * ns * g.lkp_per_slot));
+        CU(cudaMalloc(&d_lkp_count, 4 * ns * g.nlevels));
+        CU(cudaMalloc(&d_err, 4));
+        CU(cudaMemset(d_err, 0, 4));
+        const size_t K = (size_t)g.kp_cap_total;
+        off_kps = align_up(4 * ns, 256);
+        off_desc = off_kps + align_up(sizeof(pslot_keypoint) * ns * K, 256);
+        out_bytes = off_desc + align_up(32 * ns * K, 256);
+        CU(cudaMalloc(&d_out, out_bytes));
+        CU(cudaMemset(d_out, 0, out_bytes));
+        d_out_count = (int *)d_out;
+        d_out_kps = (pslot_keypoint *)(d_out + off_kps);
+        d_out_desc = (uint8_t *)(d_out + off_desc);
+        const size_t np = std::max<size_t>(ns / 2, 1);
+        CU(cudaMalloc(&d_uright, 4 * np * K)); CU(cudaMalloc(&d_depth, 4 * np * K));
+        CU(cudaMalloc(&d_best_dist, 4 * np * K)); CU(cudaMalloc(&d_best_idx, 4 * np * K)); CU(cudaMalloc(&d_sad, 4 * np * K));
+        W = w; H = h; S = nslots;
+        return PSLOT_OK;
+    }
+
+    // K1..K6 on slots [0, nslots); level 0 must already be in place.  Returns kernels launched (>0) or <0.
+    int run_extract(int nslots)
+    {
+        int n = 0;
+        n += launch_pyramid(g, pyr, d_taps, nslots, st);
+        n += launch_fast(g, pyr, d_cell_count, d_cell_cand, nslots, st);
+        n += launch_quadtree(g, d_cell_count, d_cell_cand, d_cell_prefix, d_qt_keys, d_qt_nodes, d_lkp, d_lkp_count,
+                             d_err, nslots, st);
+        n += launch_describe(g, pyr, d_lkp, d_lkp_count, d_out_kps, d_out_desc, d_out_count, nslots, st);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+        has_pyramid = true;
+        return n;
+    }
+};
+
+int check_err_flag(Engine &E)
+{
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, E.d_err, 4, cudaMemcpyDeviceToHost, E.st));
+    CU(cudaStreamSynchronize(E.st));
+    if (flag) {
+        cudaMemsetAsync(E.d_err, 0, 4, E.st);
+        return fail(PSLOT_ERR_CUDA, "quadtree node table overflow (internal capacity bound violated)");
+    }
+    return PSLOT_OK;
+}
+
+} // namespace
+
+// -------------------------------------------------------------------------------------------------
+struct pslot_orb {
+    Engine E;
+    // device scratch for host-provided feature sets (pslot_stereo_match)
+    pslot_keypoint *d_kl = nullptr, *d_kr = nullptr;
+    uint8_t *d_dl = nullptr, *d_dr = nullptr;
+    int *d_n = nullptr;
+    float *d_ur = nullptr, *d_dp = nullptr;
+    int *d_bd = nullptr, *d_bi = nullptr, *d_sd = nullptr;
+    int st_cap = 0;
+    int last_nl = 0;
+    unsigned char *h_stage = nullptr; // pinned mirror of E.d_out
+    size_t h_stage_bytes = 0;
+
+    ~pslot_orb()
+    {
+        free_stereo();
+        if (h_stage) cudaFreeHost(h_stage);
+    }
+    void free_stereo()
+    {
+        cudaFree(d_kl); cudaFree(d_kr); cudaFree(d_dl); cudaFree(d_dr); cudaFree(d_n);
+        cudaFree(d_ur); cudaFree(d_dp); cudaFree(d_bd); cudaFree(d_bi); cudaFree(d_sd);
+        d_kl = d_kr = nullptr; d_dl = d_dr = nullptr; d_n = nullptr; d_ur = d_dp = nullptr; d_bd = d_bi = d_sd = nullptr;
+        st_cap = 0;
+    }
+};
+
+struct pslot_batch {
+    Engine E;
+    int max_pairs = 0;
+    int last_pairs = 0;
+    int launches = 0;
+};
+
+extern "C" {
+
+const char *pslot_last_error(void) { return t_err; }
+int pslot_abi_version(void) { return PSLOT_ABI_VERSION; }
+
+int pslot_device_count(void)
+{
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    return n;
+}
+
+int pslot_hamming256(const void *a, const void *b)
+{
+    uint64_t x[4], y[4];
+    memcpy(x, a, 32);
+    memcpy(y, b, 32);
+    int d = 0;
+    for (int i = 0; i < 4; ++i) d += __builtin_popcountll(x[i] ^ y[i]);
+    return d;
+}
+
+int pslot_orb_create(pslot_orb **ctx, int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int device)
+{
+    if (!ctx) return fail(PSLOT_ERR_ARG, "ctx is null");
+    *ctx = nullptr;
+    pslot_orb *c = new (std::nothrow) pslot_orb();
+    if (!c) return fail(PSLOT_ERR_ARG, "out of host memory");
+    Params p{nfeatures, scale_factor, nlevels, ini_th, min_th};
+    int rc = c->E.init(p, device, nullptr);
+    if (rc) { delete c; return rc; }
+    *ctx = c;
+    return PSLOT_OK;
+}
+
+void pslot_orb_destroy(pslot_orb *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->E.device);
+    if (ctx->E.st) cudaStreamSynchronize(ctx->E.st);
+    delete ctx;
+}
+
+int pslot_orb_levels(const pslot_orb *ctx) { return ctx ? ctx->E.p.nlevels : fail(PSLOT_ERR_ARG, "ctx is null"); }
+
+int pslot_orb_tables(const pslot_orb *ctx, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2, int32_t *per_level)
+{
+    if (!ctx) return fail(PSLOT_ERR_ARG, "ctx is null");
+    const Tables &t = ctx->E.t;
+    for (int i = 0; i < ctx->E.p.nlevels; ++i) {
+        if (scale) scale[i] = t.sf[i];
+        if (inv_scale) inv_scale[i] = t.inv_sf[i];
+        if (sigma2) sigma2[i] = t.sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = t.inv_sigma2[i];
+        if (per_level) per_level[i] = t.per_level[i];
+    }
+    return PSLOT_OK;
+}
+
+static int max_keypoints(const Engine &E)
+{
+    // sum over levels of max(quota+3, 4*nIni)+1; nIni depends on the image aspect, bound it generously
+    int k = 0;
+    for (int l = 0; l < E.p.nlevels; ++l) k += std::max(E.t.per_level[l] + 3, 64) + 1;
+    return k;
+}
+
+int pslot_orb_max_keypoints(const pslot_orb *ctx)
+{
+    if (!ctx) return fail(PSLOT_ERR_ARG, "ctx is null");
+    return ctx->E.W ? ctx->E.g.kp_cap_total : max_keypoints(ctx->E);
+}
+
+int pslot_orb_extract(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, pslot_keypoint *kps,
+                      uint8_t *desc32, int cap, int *n)
+{
+    if (!ctx || !n) return fail(PSLOT_ERR_ARG, "ctx / n is null");
+    *n = 0;
+    if (!img || w <= 0 || h <= 0) return PSLOT_OK; // ORBextractor.cc:1046-1047
+    if (pitch < w) return fail(PSLOT_ERR_ARG, "pitch < width");
+    Engine &E = ctx->E;
+    CU(cudaSetDevice(E.device));
+    int rc = E.configure(w, h, 1);
+    if (rc) return rc;
+    if (ctx->h_stage_bytes < E.out_bytes) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr;
+        CU(cudaHostAlloc((void **)&ctx->h_stage, E.out_bytes, cudaHostAllocDefault));
+        ctx->h_stage_bytes = E.out_bytes;
+    }
+    CU(cudaMemcpy2DAsync(E.pyr.lv[0], E.g.lv[0].pitch, img, pitch, w, h, cudaMemcpyHostToDevice, E.st));
+    rc = E.run_extract(1);
+    if (rc < 0) return rc;
+    CU(cudaMemcpyAsync(ctx->h_stage, E.d_out, E.out_bytes, cudaMemcpyDeviceToHost, E.st));
+    rc = check_err_flag(E); // synchronises the stream
+    if (rc) return rc;
+    const int count = *(const int *)ctx->h_stage;
+    *n = count;
+    if (count > cap) return fail(PSLOT_ERR_CAPACITY, "need room for %d keypoints, caller gave %d", count, cap);
+    if (count > 0) {
+        if (!kps || !desc32) return fail(PSLOT_ERR_ARG, "kps / desc32 is null");
+        memcpy(kps, ctx->h_stage + E.off_kps, sizeof(pslot_keypoint) * (size_t)count);
+        memcpy(desc32, ctx->h_stage + E.off_desc, 32 * (size_t)count);
+    }
+    return PSLOT_OK;
+}
+
+int pslot_orb_level(pslot_orb *ctx, int level, uint8_t *dst, ptrdiff_t pitch, int *w, int *h)
+{
+    if (!ctx) return fail(PSLOT_ERR_ARG, "ctx is null");
+    Engine &E = ctx->E;
+    if (!E.has_pyramid) return fail(PSLOT_ERR_STATE, "no image has been extracted yet");
+    if (level < 0 || level >= E.p.nlevels) return fail(PSLOT_ERR_ARG, "level out of range");
+    const LevelGeom &L = E.g.lv[level];
+    if (w) *w = L.w;
+    if (h) *h = L.h;
+    if (!dst) return PSLOT_OK;
+    if (pitch < L.w) return fail(PSLOT_ERR_ARG, "pitch < level width");
+    CU(cudaSetDevice(E.device));
+    CU(cudaMemcpy2DAsync(dst, pitch, E.pyr.lv[level], L.pitch, L.w, L.h, cudaMemcpyDeviceToHost, E.st));
+    CU(cudaStreamSynchronize(E.st));
+    return PSLOT_OK;
+}
+
+int pslot_stereo_match(pslot_orb *cl, pslot_orb *cr, const pslot_keypoint *kps_l, int n_l, const uint8_t *desc_l,
+                       const pslot_keypoint *kps_r, int n_r, const uint8_t *desc_r, float bf, float max_d,
+                       float *u_right, float *depth)
+{
+    if (!cl || !cr) return fail(PSLOT_ERR_ARG, "ctx is null");
+    if (n_l < 0 || n_r < 0) return fail(PSLOT_ERR_ARG, "negative count");
+    if (n_l == 0) return PSLOT_OK;
+    if (!kps_l || !desc_l || !u_right || !depth || (n_r > 0 && (!kps_r || !desc_r))) return fail(PSLOT_ERR_ARG, "null array");
+    Engine &L = cl->E, &R = cr->E;
+    if (!L.has_pyramid || !R.has_pyramid) return fail(PSLOT_ERR_STATE, "both extractors must have processed an image");
+    if (L.W != R.W || L.H != R.H || L.p.nlevels != R.p.nlevels || L.device != R.device)
+        return fail(PSLOT_ERR_STATE, "left / right extractors differ in geometry or device");
+    if (n_r > 16000 || n_l > (1 << 24)) return fail(PSLOT_ERR_ARG, "too many keypoints");
+    for (int i = 0; i < n_l; ++i)
+        if (kps_l[i].octave < 0 || kps_l[i].octave >= L.p.nlevels) return fail(PSLOT_ERR_ARG, "left keypoint %d: octave out of range", i);
+    CU(cudaSetDevice(L.device));
+    const int need = std::max(std::max(n_l, n_r), 1);
+    if (need > cl->st_cap) {
+        cl->free_stereo();
+        const size_t c = (size_t)need + 256;
+        CU(cudaMalloc(&cl->d_kl, sizeof(pslot_keypoint) * c)); CU(cudaMalloc(&cl->d_kr, sizeof(pslot_keypoint) * c));
+        CU(cudaMalloc(&cl->d_dl, 32 * c)); CU(cudaMalloc(&cl->d_dr, 32 * c));
+        CU(cudaMalloc(&cl->d_n, 8));
+        CU(cudaMalloc(&cl->d_ur, 4 * c)); CU(cudaMalloc(&cl->d_dp, 4 * c));
+        CU(cudaMalloc(&cl->d_bd, 4 * c)); CU(cudaMalloc(&cl->d_bi, 4 * c)); CU(cudaMalloc(&cl->d_sd, 4 * c));
+        cl->st_cap = (int)c;
+    }
+    cudaStream_t st = L.st;
+    CU(cudaStreamSynchronize(R.st)); // the right pyramid must be complete (extract is synchronous anyway)
+    const int counts[2] = {n_l, n_r};
+    CU(cudaMemcpyAsync(cl->d_n, counts, 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(cl->d_kl, kps_l, sizeof(pslot_keypoint) * (size_t)n_l, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(cl->d_dl, desc_l, 32 * (size_t)n_l, cudaMemcpyHostToDevice, st));
+    if (n_r) {
+        CU(cudaMemcpyAsync(cl->d_kr, kps_r, sizeof(pslot_keypoint) * (size_t)n_r, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(cl->d_dr, desc_r, 32 * (size_t)n_r, cudaMemcpyHostToDevice, st));
+    }
+    StereoArgs a{};
+    a.kps_l = cl->d_kl; a.kps_r = cl->d_kr; a.desc_l = cl->d_dl; a.desc_r = cl->d_dr;
+    a.n_l = cl->d_n; a.n_r = cl->d_n + 1;
+    a.K = cl->st_cap;
+    a.pyr_l = L.pyr; a.pyr_r = R.pyr;
+    a.bf = bf; a.max_d = max_d;
+    a.u_right = cl->d_ur; a.depth = cl->d_dp; a.best_dist = cl->d_bd; a.best_idx = cl->d_bi; a.sad = cl->d_sd;
+    // the grid is sized from K; shrink it to the actual left count
+    StereoArgs launch_args = a;
+    launch_args.K = cl->st_cap;
+    launch_stereo(L.g, launch_args, 1, std::max(n_r, 1), st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "stereo launch failed: %s", cudaGetErrorString(e));
+    CU(cudaMemcpyAsync(u_right, cl->d_ur, 4 * (size_t)n_l, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(depth, cl->d_dp, 4 * (size_t)n_l, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cl->last_nl = n_l;
+    return PSLOT_OK;
+}
+
+int pslot_stereo_debug(pslot_orb *cl, int n_l, int32_t *best_dist, int32_t *best_idx, int32_t *best_sad)
+{
+    if (!cl) return fail(PSLOT_ERR_ARG, "ctx is null");
+    if (n_l > cl->last_nl) return fail(PSLOT_ERR_STATE, "no stereo result of that size");
+    CU(cudaSetDevice(cl->E.device));
+    if (best_dist) CU(cudaMemcpy(best_dist, cl->d_bd, 4 * (size_t)n_l, cudaMemcpyDeviceToHost));
+    if (best_idx) CU(cudaMemcpy(best_idx, cl->d_bi, 4 * (size_t)n_l, cudaMemcpyDeviceToHost));
+    if (best_sad) CU(cudaMemcpy(best_sad, cl->d_sd, 4 * (size_t)n_l, cudaMemcpyDeviceToHost));
+    return PSLOT_OK;
+}
+
+int pslot_orb_debug_candidates(pslot_orb *ctx, int level, int cap, int32_t *x, int32_t *y, int32_t *resp, int *n)
+{
+    if (!ctx || !n) return fail(PSLOT_ERR_ARG, "null argument");
+    Engine &E = ctx->E;
+    if (!E.has_pyramid) return fail(PSLOT_ERR_STATE, "no image has been extracted yet");
+    if (level < 0 || level >= E.p.nlevels) return fail(PSLOT_ERR_ARG, "level out of range");
+    const LevelGeom &L = E.g.lv[level];
+    const int ncells = L.n_cols * L.n_rows;
+    std::vector<int> cnt(ncells);
+    std::vector<uint32_t> cand((size_t)ncells * L.cand_stride);
+    CU(cudaSetDevice(E.device));
+    CU(cudaMemcpy(cnt.data(), E.d_cell_count + L.cell_base, 4 * (size_t)ncells, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(cand.data(), E.d_cell_cand + L.cand_base, 4 * cand.size(), cudaMemcpyDeviceToHost));
+    int k = 0;
+    for (int c = 0; c < ncells; ++c)
+        for (int i = 0; i < cnt[c]; ++i, ++k)
+            if (k < cap) {
+                const uint32_t p = cand[(size_t)c * L.cand_stride + i];
+                x[k] = pslot_px(p); y[k] = pslot_py(p); resp[k] = pslot_pr(p);
+            }
+    *n = k;
+    return k > cap ? fail(PSLOT_ERR_CAPACITY, "need room for %d candidates", k) : PSLOT_OK;
+}
+
+int pslot_orb_debug_level_keypoints(pslot_orb *ctx, int level, int cap, int32_t *x, int32_t *y, int32_t *resp,
+                                    float *angle, int *n)
+{
+    if (!ctx || !n) return fail(PSLOT_ERR_ARG, "null argument");
+    Engine &E = ctx->E;
+    if (!E.has_pyramid) return fail(PSLOT_ERR_STATE, "no image has been extracted yet");
+    if (level < 0 || level >= E.p.nlevels) return fail(PSLOT_ERR_ARG, "level out of range");
+    const LevelGeom &L = E.g.lv[level];
+    std::vector<int> cnt(E.p.nlevels);
+    std::vector<uint32_t> kp(L.kp_cap);
+    CU(cudaSetDevice(E.device));
+    CU(cudaMemcpy(cnt.data(), E.d_lkp_count, 4 * (size_t)E.p.nlevels, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(kp.data(), E.d_lkp + L.kp_base, 4 * (size_t)L.kp_cap, cudaMemcpyDeviceToHost));
+    int base = 0;
+    for (int l = 0; l < level; ++l) base += cnt[l];
+    const int c = cnt[level];
+    std::vector<pslot_keypoint> out(std::max(c, 1));
+    if (c) CU(cudaMemcpy(out.data(), E.d_out_kps + base, sizeof(pslot_keypoint) * (size_t)c, cudaMemcpyDeviceToHost));
+    *n = c;
+    if (c > cap) return fail(PSLOT_ERR_CAPACITY, "need room for %d keypoints", c);
+    for (int i = 0; i < c; ++i) {
+        x[i] = pslot_px(kp[i]); y[i] = pslot_py(kp[i]); resp[i] = pslot_pr(kp[i]);
+        if (angle) angle[i] = out[i].angle;
+    }
+    return PSLOT_OK;
+}
+
+// ---- throughput API -------------------------------------------------------------------------------
+int pslot_batch_create(pslot_batch **b, int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th,
+                       int width, int height, int max_pairs, int device, void *stream)
+{
+    if (!b) return fail(PSLOT_ERR_ARG, "b is null");
+    *b = nullptr;
+    if (max_pairs < 1 || max_pairs > 16384) return fail(PSLOT_ERR_ARG, "max_pairs must be in [1,16384]");
+    if (width <= 0 || height <= 0) return fail(PSLOT_ERR_ARG, "bad image size");
+    pslot_batch *c = new (std::nothrow) pslot_batch();
+    if (!c) return fail(PSLOT_ERR_ARG, "out of host memory");
+    Params p{nfeatures, scale_factor, nlevels, ini_th, min_th};
+    int rc = c->E.init(p, device, stream);
+    if (!rc) rc = c->E.configure(width, height, 2 * max_pairs);
+    if (rc) { delete c; return rc; }
+    c->max_pairs = max_pairs;
+    *b = c;
+    return PSLOT_OK;
+}
+
+void pslot_batch_destroy(pslot_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->E.device);
+    if (b->E.st) cudaStreamSynchronize(b->E.st);
+    delete b;
+}
+
+int pslot_batch_max_keypoints(const pslot_batch *b) { return b ? b->E.g.kp_cap_total : fail(PSLOT_ERR_ARG, "b is null"); }
+void *pslot_batch_stream(const pslot_batch *b) { return b ? (void *)b->E.st : nullptr; }
+int pslot_batch_kernel_launches(const pslot_batch *b) { return b ? b->E.p.nlevels - 1 + 3 + 2 : fail(PSLOT_ERR_ARG, "b is null"); }
+
+int pslot_batch_submit(pslot_batch *b, const uint8_t *left, const uint8_t *right, ptrdiff_t pitch, ptrdiff_t image_stride,
+                       int npairs, int host_input, float bf, float max_d, const pslot_batch_out *out)
+{
+    if (!b || !left || !right) return fail(PSLOT_ERR_ARG, "null argument");
+    if (npairs < 1 || npairs > b->max_pairs) return fail(PSLOT_ERR_ARG, "npairs must be in [1,%d]", b->max_pairs);
+    Engine &E = b->E;
+    if (pitch < E.W || image_stride < pitch * E.H) return fail(PSLOT_ERR_ARG, "bad pitch / image stride");
+    CU(cudaSetDevice(E.device));
+    const cudaMemcpyKind kind = host_input ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const LevelGeom &L0 = E.g.lv[0];
+    const uint8_t *views[2] = {left, right};
+    for (int v = 0; v < 2; ++v) {
+        uint8_t *dst = E.pyr.lv[0] + (size_t)v * npairs * E.pyr.slot_stride[0];
+        if (image_stride == pitch * E.H) {
+            CU(cudaMemcpy2DAsync(dst, L0.pitch, views[v], pitch, E.W, (size_t)E.H * npairs, kind, E.st));
+        } else {
+            for (int i = 0; i < npairs; ++i)
+                CU(cudaMemcpy2DAsync(dst + (size_t)i * E.pyr.slot_stride[0], L0.pitch, views[v] + (size_t)i * image_stride,
+                                     pitch, E.W, E.H, kind, E.st));
+        }
+    }
+    int rc = E.run_extract(2 * npairs);
+    if (rc < 0) return rc;
+    const int K = E.g.kp_cap_total;
+    StereoArgs a{};
+    a.kps_l = E.d_out_kps; a.kps_r = E.d_out_kps + (size_t)npairs * K;
+    a.desc_l = E.d_out_desc; a.desc_r = E.d_out_desc + (size_t)npairs * K * 32;
+    a.n_l = E.d_out_count; a.n_r = E.d_out_count + npairs;
+    a.K = K;
+    a.pyr_l = E.pyr; a.pyr_r = E.pyr;
+    for (int l = 0; l < E.g.nlevels; ++l) a.pyr_r.lv[l] = E.pyr.lv[l] + (size_t)npairs * E.pyr.slot_stride[l];
+    a.bf = bf; a.max_d = max_d;
+    a.u_right = E.d_uright; a.depth = E.d_depth; a.best_dist = E.d_best_dist; a.best_idx = E.d_best_idx; a.sad = E.d_sad;
+    rc += launch_stereo(E.g, a, npairs, K, E.st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "stereo launch failed: %s", cudaGetErrorString(e));
+    b->launches = rc;
+    b->last_pairs = npairs;
+    if (out) {
+        const size_t ni = 2 * (size_t)npairs;
+        if (out->counts) CU(cudaMemcpyAsync(out->counts, E.d_out_count, 4 * ni, cudaMemcpyDeviceToHost, E.st));
+        if (out->kps) CU(cudaMemcpyAsync(out->kps, E.d_out_kps, sizeof(pslot_keypoint) * ni * K, cudaMemcpyDeviceToHost, E.st));
+        if (out->desc) CU(cudaMemcpyAsync(out->desc, E.d_out_desc, 32 * ni * K, cudaMemcpyDeviceToHost, E.st));
+        if (out->u_right) CU(cudaMemcpyAsync(out->u_right, E.d_uright, 4 * (size_t)npairs * K, cudaMemcpyDeviceToHost, E.st));
+        if (out->depth) CU(cudaMemcpyAsync(out->depth, E.d_depth, 4 * (size_t)npairs * K, cudaMemcpyDeviceToHost, E.st));
+    }
+    return PSLOT_OK;
+}
+
+int pslot_batch_wait(pslot_batch *b)
+{
+    if (!b) return fail(PSLOT_ERR_ARG, "b is null");
+    CU(cudaSetDevice(b->E.device));
+    return check_err_flag(b->E);
+}
+
+int pslot_batch_device_out(const pslot_batch *b, pslot_batch_out *dev)
+{
+    if (!b || !dev) return fail(PSLOT_ERR_ARG, "null argument");
+    dev->counts = b->E.d_out_count; dev->kps = b->E.d_out_kps; dev->desc = b->E.d_out_desc;
+    dev->u_right = b->E.d_uright; dev->depth = b->E.d_depth;
+    return PSLOT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,86 @@
+// pslot_internal.h — geometry tables and kernel launchers shared by the .cu files of libpslot_orb.so.
+//
+// Device data layout (all per "slot" = one image of a batch; a single extractor is a 1-slot engine):
+//   pyramid     level-major: level l is one array [S][h_l][pitch_l] of u8 (pitch_l % 128 == 0), so the
+//               level-0 upload of a whole batch is one 2-D copy and a (x, y, slot) tensor map per level
+//               can address every tile.  No 19-px border is stored (never read).
+//   cell_count  [S][cells]  FAST survivors per 30-px cell (all levels concatenated)
+//   cell_cand   [S][cand_per_slot] u32  per-cell slots of packed candidates (x:12 | y:12 | resp:8,
+//               window-relative coordinates), raster order inside a cell
+//   lkp         [S][lkp_per_slot] u32   per-level keypoints chosen by the quadtree (level image coords)
+//   lkp_count   [S][nlevels]
+//   out_*       final keypoints / descriptors / counts, level-ascending
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/pslot_orb.h"
+
+#define PSLOT_MAX_LEVELS 16
+#define PSLOT_EDGE 19       // EDGE_THRESHOLD, ORBextractor.cc:74
+#define PSLOT_MINB 16       // minBorderX/Y = EDGE_THRESHOLD-3, ORBextractor.cc:773-774
+#define PSLOT_HALF_PATCH 15 // HALF_PATCH_SIZE, ORBextractor.cc:73
+
+struct LevelGeom {
+    int w, h, pitch;                    // level image (ORBextractor.cc:1111-1112)
+    int max_bx, max_by;                 // maxBorderX/Y = dim - 16 (:775-776)
+    int n_cols, n_rows, w_cell, h_cell; // FAST cell grid (:784-787)
+    int cell_base;                      // first cell of this level inside a slot
+    int cand_stride;                    // candidate slots per cell (upper bound of strict 3x3 maxima)
+    int cand_base;                      // u32 offset of this level's candidate slots inside a slot
+    int quota;                          // mnFeaturesPerLevel[level] (:435-446)
+    int kp_base, kp_cap;                // this level's segment of the lkp buffer
+    int n_ini;                          // quadtree roots (:543)
+    float hx;                           // root width (:545)
+    float scale, inv_scale;             // mvScaleFactor / mvInvScaleFactor (:421,429)
+    int patch_size;                     // (int)(31 * scale) (:834)
+    int tab_x, tab_y;                   // offsets into the resize tap table
+};
+
+struct Geom {
+    int nlevels, ini_th, min_th;
+    int cells_per_slot, cand_per_slot, lkp_per_slot, kp_cap_total;
+    int max_level_cap; // max kp_cap over levels (sizes the quadtree node tables)
+    LevelGeom lv[PSLOT_MAX_LEVELS];
+};
+
+struct PyrPtrs {
+    uint8_t *lv[PSLOT_MAX_LEVELS];            // base of [S][h][pitch]
+    unsigned long long slot_stride[PSLOT_MAX_LEVELS]; // h * pitch
+};
+
+// one bilinear tap of cv::resize INTER_LINEAR (8-bit): source indices and 11-bit coefficients
+struct ResizeTap {
+    uint16_t s0, s1;
+    int16_t c0, c1;
+};
+
+// packed candidate / level keypoint
+__host__ __device__ inline uint32_t pslot_pack(int x, int y, int r) { return ((uint32_t)y << 20) | ((uint32_t)x << 8) | (uint32_t)r; }
+__host__ __device__ inline int pslot_px(uint32_t p) { return (int)((p >> 8) & 0xFFFu); }
+__host__ __device__ inline int pslot_py(uint32_t p) { return (int)(p >> 20); }
+__host__ __device__ inline int pslot_pr(uint32_t p) { return (int)(p & 0xFFu); }
+
+struct StereoArgs {
+    // left / right feature sets: per pair p, keypoints at kps + slot*K
+    const pslot_keypoint *kps_l, *kps_r;
+    const uint8_t *desc_l, *desc_r;
+    const int *n_l, *n_r; // per-pair counts
+    int K;                // row stride (keypoints) between pairs
+    PyrPtrs pyr_l, pyr_r; // pyramids; pair p is slot p of each
+    float bf, max_d;
+    float *u_right, *depth;          // [pairs][K]
+    int *best_dist, *best_idx, *sad; // [pairs][K]
+};
+
+// ---- launchers (each enqueues on `st`; returns the number of kernels launched) -----------------
+int launch_pyramid(const Geom &g, const PyrPtrs &pyr, const ResizeTap *taps, int nslots, cudaStream_t st);
+int launch_fast(const Geom &g, const PyrPtrs &pyr, int *cell_count, uint32_t *cell_cand, int nslots, cudaStream_t st);
+int launch_quadtree(const Geom &g, const int *cell_count, const uint32_t *cell_cand, int *cell_prefix,
+                    uint32_t *qt_keys, uint16_t *qt_nodes, uint32_t *lkp, int *lkp_count, int *err_flag,
+                    int nslots, cudaStream_t st);
+int launch_describe(const Geom &g, const PyrPtrs &pyr, const uint32_t *lkp, const int *lkp_count,
+                    pslot_keypoint *out_kps, uint8_t *out_desc, int *out_count, int nslots, cudaStream_t st);
+int launch_stereo(const Geom &g, const StereoArgs &a, int npairs, int max_n_r, cudaStream_t st);
+size_t quadtree_smem_bytes(const Geom &g, int *key_cap);

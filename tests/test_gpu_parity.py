@@ -1,0 +1,135 @@
+"""GPU parity tests (run with -m gpu on the B200 box): CUDA path through the C ABI vs the oracle and
+the golden vectors.  Bar (north_star): keypoints / octaves / angles / descriptors bit-exact; matched
+pair set identical; sub-pixel uRight within 1e-3 px (TOL_PX below; in practice bit-equal)."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+TOL_PX = 1e-3  # north_star: "stereo depth must fall within 1e-3 px of the reference's sub-pixel disparity"
+
+
+@pytest.fixture(scope="module")
+def B():
+    from pointslot_b200 import binding
+    assert binding.device_count() > 0
+    return binding
+
+
+def _assert_stereo(ur, dp, ur_ref, dp_ref):
+    assert np.array_equal(ur >= 0, ur_ref >= 0), "matched-pair set differs"
+    m = ur_ref >= 0
+    assert np.all(np.abs(ur[m] - ur_ref[m]) <= TOL_PX)
+    rel = np.abs(dp[m] - dp_ref[m]) / np.maximum(np.abs(dp_ref[m]), 1e-9)
+    assert np.all(rel <= 1e-5)
+    assert np.all(ur[~m] == -1) and np.all(dp[~m] == -1)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_end_to_end(name, B):
+    g = load_golden(name)
+    eL, eR = B.OrbExtractor(*g["params_t"]), B.OrbExtractor(*g["params_t"])
+    kL, dL = eL.extract(g["left"]); kR, dR = eR.extract(g["right"])
+    assert kL.tobytes() == g["kL"].tobytes() and kR.tobytes() == g["kR"].tobytes()
+    assert np.array_equal(dL, g["dL"]) and np.array_equal(dR, g["dR"])
+    ur, dp = B.stereo_match(eL, eR, kL, dL, kR, dR, float(g["bf"]), float(g["maxD"]))
+    _assert_stereo(ur, dp, g["uright"], g["depth"])
+
+
+@pytest.mark.parametrize("name", ["odd_synth_s5_500", "kitti_natural_2000"])
+def test_stage_parity(name, B, oracle_mod):
+    """pyramid -> FAST candidates -> quadtree keypoints -> angles, each against the oracle."""
+    g = load_golden(name)
+    o = oracle_mod.OracleExtractor(*g["params_t"]); o.extract(g["left"])
+    e = B.OrbExtractor(*g["params_t"]); e.extract(g["left"])
+    for l in range(o.nlevels):
+        assert np.array_equal(e.level(l), o.level(l)), f"pyramid level {l}"
+        for a, b in zip(e.debug_candidates(l), o.level_candidates(l)):
+            assert np.array_equal(a, b), f"candidates level {l}"
+        for a, b in zip(e.debug_level_keypoints(l), o.level_keypoints(l)):
+            assert np.array_equal(a, b), f"keypoints level {l}"
+
+
+@pytest.mark.parametrize("shape,params", [((375, 1242), (1000, 1.2, 8, 20, 5)), ((480, 752), (1200, 1.2, 8, 20, 7)),
+                                         ((376, 1241), (2000, 1.2, 8, 20, 7)), ((300, 400), (800, 1.3, 6, 15, 5))])
+def test_random_seeds_vs_oracle(shape, params, B, oracle_mod):
+    from pointslot_b200.synth import synth_pair
+    H, W = shape
+    bf, fx = 384.38148, 721.5377
+    maxD = B.max_disparity(bf, fx)
+    eL, eR = B.OrbExtractor(*params), B.OrbExtractor(*params)
+    oL, oR = oracle_mod.OracleExtractor(*params), oracle_mod.OracleExtractor(*params)
+    for seed in (100, 101, 102):
+        L, R = synth_pair(W, H, seed)
+        kL, dL = eL.extract(L); kR, dR = eR.extract(R)
+        okL, odL = oL.extract(L); okR, odR = oR.extract(R)
+        assert kL.tobytes() == okL.tobytes() and kR.tobytes() == okR.tobytes()
+        assert np.array_equal(dL, odL) and np.array_equal(dR, odR)
+        ur, dp = B.stereo_match(eL, eR, kL, dL, kR, dR, bf, maxD)
+        our, odp = oracle_mod.stereo_match(oL, oR, okL, odL, okR, odR, bf, maxD)
+        _assert_stereo(ur, dp, our, odp)
+        ur2, dp2 = B.stereo_match(eL, eR, kL, dL, kR, dR, bf, float("inf"))  # the reference's mb == 0 case
+        our2, odp2 = oracle_mod.stereo_match(oL, oR, okL, odL, okR, odR, bf, float("inf"))
+        _assert_stereo(ur2, dp2, our2, odp2)
+
+
+def test_batch_equals_single_and_oracle(B, oracle_mod):
+    from pointslot_b200.synth import synth_batch
+    params = (1000, 1.2, 8, 20, 5)
+    W, H, n = 1242, 375, 6
+    bf, fx = 384.38148, 721.5377
+    maxD = B.max_disparity(bf, fx)
+    Ls, Rs = synth_batch(W, H, range(40, 40 + n))
+    sb = B.StereoBatch(params, W, H, 8)
+    res = sb.run(Ls, Rs, bf, maxD)
+    res_again = sb.run(Ls[:3], Rs[:3], bf, maxD)  # smaller batch through the same context
+    oL, oR = oracle_mod.OracleExtractor(*params), oracle_mod.OracleExtractor(*params)
+    for i in range(n):
+        okL, odL = oL.extract(Ls[i]); okR, odR = oR.extract(Rs[i])
+        our, odp = oracle_mod.stereo_match(oL, oR, okL, odL, okR, odR, bf, maxD)
+        r = res[i]
+        assert r["kL"].tobytes() == okL.tobytes() and r["kR"].tobytes() == okR.tobytes()
+        assert np.array_equal(r["dL"], odL) and np.array_equal(r["dR"], odR)
+        _assert_stereo(r["u_right"], r["depth"], our, odp)
+        if i < 3:
+            for k in r:
+                assert r[k].tobytes() == res_again[i][k].tobytes()
+
+
+def test_edge_cases(B, oracle_mod):
+    e = B.OrbExtractor(500, 1.2, 8, 20, 7)
+    k, d = e.extract(np.zeros((0, 0), np.uint8))  # empty image: reference returns without touching outputs
+    assert len(k) == 0
+    k, d = e.extract(np.full((400, 600), 77, np.uint8))  # featureless
+    assert len(k) == 0 and d.shape == (0, 32)
+    ur, dp = B.stereo_match(e, e, k, d, k, d, 40.0, 300.0)
+    assert len(ur) == 0
+    with pytest.raises(B.PslotError) as ei:
+        e.extract(np.zeros((120, 160), np.uint8))  # coarsest level < 62 px: reference divides by zero
+    assert ei.value.code == -4
+    # non-contiguous rows (honour `pitch`)
+    from pointslot_b200.synth import synth_pair
+    L, _ = synth_pair(500, 320, 9)
+    big = np.zeros((320, 640), np.uint8); big[:, :500] = L
+    k1, d1 = e.extract(L); k2, d2 = e.extract(big[:, :500])
+    assert k1.tobytes() == k2.tobytes() and np.array_equal(d1, d2)
+    o = oracle_mod.OracleExtractor(500, 1.2, 8, 20, 7)
+    ok, od = o.extract(L)
+    assert k1.tobytes() == ok.tobytes() and np.array_equal(d1, od)
+    # capacity error reports the needed count
+    import ctypes as C
+    n = C.c_int(0)
+    kp = np.zeros(4, B.KEYPOINT_DTYPE); ds = np.zeros((4, 32), np.uint8)
+    rc = B.lib().pslot_orb_extract(e._h, L.ctypes.data_as(C.c_void_p), 500, 320, 500, kp.ctypes.data_as(C.c_void_p),
+                                   ds.ctypes.data_as(C.c_void_p), 4, C.byref(n))
+    assert rc == -2 and n.value == len(k1)
+
+
+def test_noise_image_many_candidates(B, oracle_mod):
+    """Uniform noise: FAST fires almost everywhere -> stresses cell capacity, quadtree spill, ties."""
+    img = np.random.default_rng(5).integers(0, 256, (240, 320), dtype=np.uint8)
+    params = (1500, 1.2, 4, 20, 7)
+    e = B.OrbExtractor(*params); o = oracle_mod.OracleExtractor(*params)
+    k, d = e.extract(img); ok, od = o.extract(img)
+    assert k.tobytes() == ok.tobytes() and np.array_equal(d, od)
