@@ -144,6 +144,18 @@ int pslot_batch_kernel_launches(const pslot_batch *b);
  * submit; for callers that keep the features on the GPU. */
 int pslot_batch_device_out(const pslot_batch *b, pslot_batch_out *dev);
 
+/* Per-stage device timing of a submit (CUDA events on the batch stream, recorded only when enabled).
+ * Stages: 0 ingest copy (H2D or D2D), 1 pyramid (nlevels-1 launches), 2 FAST cells, 3 quadtree,
+ * 4 orientation+blur+descriptor, 5 stereo match, 6 stereo reject, 7 result copy (D2H).
+ * pslot_batch_stage_times is valid after pslot_batch_wait; ms receives PSLOT_NUM_STAGES floats. */
+#define PSLOT_NUM_STAGES 8
+int pslot_batch_set_profiling(pslot_batch *b, int enable);
+int pslot_batch_stage_times(pslot_batch *b, float *ms);
+/* Work counters of the last batch (read back after pslot_batch_wait; not on the timed path):
+ * stats[0] FAST candidates over all images, [1] keypoints over all images, [2] left keypoints that
+ * reached the SAD refinement (best Hamming < 75), [3] stereo matches that survived the median test. */
+int pslot_batch_stats(pslot_batch *b, int64_t stats[4]);
+
 /* ---------------------------------------------------------------------------------------------
  * Stage accessors for the parity tests (not needed by a drop-in caller).
  * --------------------------------------------------------------------------------------------- */

@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "pslot_orb_extract", "pslot_orb_level", "pslot_stereo_match", "pslot_hamming256",
     "pslot_batch_create", "pslot_batch_destroy", "pslot_batch_max_keypoints", "pslot_batch_stream",
     "pslot_batch_submit", "pslot_batch_wait", "pslot_batch_kernel_launches", "pslot_batch_device_out",
+    "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug",
 ]
 
@@ -79,6 +80,9 @@ def lib():
     L.pslot_batch_wait.argtypes = [vp]
     L.pslot_batch_kernel_launches.argtypes = [vp]
     L.pslot_batch_device_out.argtypes = [vp, C.POINTER(BatchOut)]
+    L.pslot_batch_set_profiling.argtypes = [vp, C.c_int]
+    L.pslot_batch_stage_times.argtypes = [vp, vp]
+    L.pslot_batch_stats.argtypes = [vp, vp]
     L.pslot_orb_debug_candidates.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, ip]
     L.pslot_orb_debug_level_keypoints.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, ip]
     L.pslot_stereo_debug.argtypes = [vp, C.c_int, vp, vp, vp]
@@ -253,6 +257,22 @@ class StereoBatch:
 
     def wait(self):
         _check(lib().pslot_batch_wait(self._h))
+
+    STAGES = ("ingest_copy", "pyramid", "fast", "quadtree", "describe", "stereo_match", "stereo_reject", "result_copy")
+
+    def set_profiling(self, enable: bool):
+        _check(lib().pslot_batch_set_profiling(self._h, 1 if enable else 0))
+
+    def stats(self) -> dict:
+        """Work counters of the last batch (candidates, keypoints, SAD evaluations, final matches)."""
+        st = np.zeros(4, np.int64)
+        _check(lib().pslot_batch_stats(self._h, _p(st)))
+        return dict(zip(("candidates", "keypoints", "sad_evals", "matches"), (int(v) for v in st)))
+
+    def stage_times_ms(self) -> np.ndarray:
+        ms = np.zeros(len(self.STAGES), np.float32)
+        _check(lib().pslot_batch_stage_times(self._h, _p(ms)))
+        return ms
 
     def run(self, left, right, bf, max_d):
         """Synchronous convenience: -> list of per-pair dicts (kL, dL, kR, dR, u_right, depth)."""

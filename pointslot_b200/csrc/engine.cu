@@ -264,14 +264,19 @@ struct Engine {
     }
 
     // K1..K6 on slots [0, nslots); level 0 must already be in place.  Returns kernels launched (>0) or <0.
-    int run_extract(int nslots)
+    int run_extract(int nslots, cudaEvent_t *ev = nullptr)
     {
         int n = 0;
+        if (ev) cudaEventRecord(ev[1], st);
         n += launch_pyramid(g, pyr, d_taps, nslots, st);
+        if (ev) cudaEventRecord(ev[2], st);
         n += launch_fast(g, pyr, d_cell_count, d_cell_cand, nslots, st);
+        if (ev) cudaEventRecord(ev[3], st);
         n += launch_quadtree(g, d_cell_count, d_cell_cand, d_cell_prefix, d_qt_keys, d_qt_nodes, d_lkp, d_lkp_count,
                              d_err, nslots, st);
+        if (ev) cudaEventRecord(ev[4], st);
         n += launch_describe(g, pyr, d_lkp, d_lkp_count, d_out_kps, d_out_desc, d_out_count, nslots, st);
+        if (ev) cudaEventRecord(ev[5], st);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
         has_pyramid = true;
@@ -326,6 +331,13 @@ struct pslot_batch {
     int max_pairs = 0;
     int last_pairs = 0;
     int launches = 0;
+    bool profiling = false, profiled = false;
+    cudaEvent_t ev[PSLOT_NUM_STAGES + 1] = {};
+    ~pslot_batch()
+    {
+        for (auto &e : ev)
+            if (e) cudaEventDestroy(e);
+    }
 };
 
 extern "C" {
@@ -612,6 +624,8 @@ int pslot_batch_submit(pslot_batch *b, const uint8_t *left, const uint8_t *right
     CU(cudaSetDevice(E.device));
     const cudaMemcpyKind kind = host_input ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     const LevelGeom &L0 = E.g.lv[0];
+    cudaEvent_t *ev = b->profiling ? b->ev : nullptr;
+    if (ev) cudaEventRecord(ev[0], E.st);
     const uint8_t *views[2] = {left, right};
     for (int v = 0; v < 2; ++v) {
         uint8_t *dst = E.pyr.lv[0] + (size_t)v * npairs * E.pyr.slot_stride[0];
@@ -623,7 +637,7 @@ int pslot_batch_submit(pslot_batch *b, const uint8_t *left, const uint8_t *right
                                      pitch, E.W, E.H, kind, E.st));
         }
     }
-    int rc = E.run_extract(2 * npairs);
+    int rc = E.run_extract(2 * npairs, ev);
     if (rc < 0) return rc;
     const int K = E.g.kp_cap_total;
     StereoArgs a{};
@@ -635,7 +649,8 @@ int pslot_batch_submit(pslot_batch *b, const uint8_t *left, const uint8_t *right
     for (int l = 0; l < E.g.nlevels; ++l) a.pyr_r.lv[l] = E.pyr.lv[l] + (size_t)npairs * E.pyr.slot_stride[l];
     a.bf = bf; a.max_d = max_d;
     a.u_right = E.d_uright; a.depth = E.d_depth; a.best_dist = E.d_best_dist; a.best_idx = E.d_best_idx; a.sad = E.d_sad;
-    rc += launch_stereo(E.g, a, npairs, K, E.st);
+    rc += launch_stereo(E.g, a, npairs, K, E.st, ev ? ev[6] : nullptr);
+    if (ev) cudaEventRecord(ev[7], E.st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "stereo launch failed: %s", cudaGetErrorString(e));
     b->launches = rc;
@@ -648,6 +663,8 @@ int pslot_batch_submit(pslot_batch *b, const uint8_t *left, const uint8_t *right
         if (out->u_right) CU(cudaMemcpyAsync(out->u_right, E.d_uright, 4 * (size_t)npairs * K, cudaMemcpyDeviceToHost, E.st));
         if (out->depth) CU(cudaMemcpyAsync(out->depth, E.d_depth, 4 * (size_t)npairs * K, cudaMemcpyDeviceToHost, E.st));
     }
+    if (ev) cudaEventRecord(ev[8], E.st);
+    b->profiled = ev != nullptr;
     return PSLOT_OK;
 }
 
@@ -656,6 +673,54 @@ int pslot_batch_wait(pslot_batch *b)
     if (!b) return fail(PSLOT_ERR_ARG, "b is null");
     CU(cudaSetDevice(b->E.device));
     return check_err_flag(b->E);
+}
+
+int pslot_batch_set_profiling(pslot_batch *b, int enable)
+{
+    if (!b) return fail(PSLOT_ERR_ARG, "b is null");
+    CU(cudaSetDevice(b->E.device));
+    if (enable)
+        for (auto &e : b->ev)
+            if (!e) CU(cudaEventCreate(&e));
+    b->profiling = enable != 0;
+    b->profiled = false;
+    return PSLOT_OK;
+}
+
+int pslot_batch_stage_times(pslot_batch *b, float *ms)
+{
+    if (!b || !ms) return fail(PSLOT_ERR_ARG, "null argument");
+    if (!b->profiled) return fail(PSLOT_ERR_STATE, "no profiled submit to report");
+    CU(cudaSetDevice(b->E.device));
+    CU(cudaEventSynchronize(b->ev[PSLOT_NUM_STAGES]));
+    for (int i = 0; i < PSLOT_NUM_STAGES; ++i) CU(cudaEventElapsedTime(&ms[i], b->ev[i], b->ev[i + 1]));
+    return PSLOT_OK;
+}
+
+int pslot_batch_stats(pslot_batch *b, int64_t stats[4])
+{
+    if (!b || !stats) return fail(PSLOT_ERR_ARG, "null argument");
+    Engine &E = b->E;
+    const int np = b->last_pairs;
+    if (np <= 0) return fail(PSLOT_ERR_STATE, "no batch has been submitted");
+    CU(cudaSetDevice(E.device));
+    CU(cudaStreamSynchronize(E.st));
+    const size_t K = (size_t)E.g.kp_cap_total;
+    std::vector<int> cells((size_t)2 * np * E.g.cells_per_slot), counts((size_t)2 * np), bd((size_t)np * K);
+    std::vector<float> ur((size_t)np * K);
+    CU(cudaMemcpy(cells.data(), E.d_cell_count, 4 * cells.size(), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(counts.data(), E.d_out_count, 4 * counts.size(), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(bd.data(), E.d_best_dist, 4 * bd.size(), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ur.data(), E.d_uright, 4 * ur.size(), cudaMemcpyDeviceToHost));
+    stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    for (int v : cells) stats[0] += v;
+    for (int v : counts) stats[1] += v;
+    for (int p = 0; p < np; ++p)
+        for (int i = 0; i < counts[p]; ++i) {
+            stats[2] += bd[p * K + i] < 75;
+            stats[3] += ur[p * K + i] >= 0.f;
+        }
+    return PSLOT_OK;
 }
 
 int pslot_batch_device_out(const pslot_batch *b, pslot_batch_out *dev)

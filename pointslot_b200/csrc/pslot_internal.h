@@ -82,5 +82,6 @@ int launch_quadtree(const Geom &g, const int *cell_count, const uint32_t *cell_c
                     int nslots, cudaStream_t st);
 int launch_describe(const Geom &g, const PyrPtrs &pyr, const uint32_t *lkp, const int *lkp_count,
                     pslot_keypoint *out_kps, uint8_t *out_desc, int *out_count, int nslots, cudaStream_t st);
-int launch_stereo(const Geom &g, const StereoArgs &a, int npairs, int max_n_r, cudaStream_t st);
+int launch_stereo(const Geom &g, const StereoArgs &a, int npairs, int max_n_r, cudaStream_t st,
+                  cudaEvent_t between = nullptr);
 size_t quadtree_smem_bytes(const Geom &g, int *key_cap);

@@ -242,12 +242,13 @@ k_stereo_reject(const __grid_constant__ StereoArgs a)
 
 } // namespace
 
-int launch_stereo(const Geom &g, const StereoArgs &a, int npairs, int max_n_r, cudaStream_t st)
+int launch_stereo(const Geom &g, const StereoArgs &a, int npairs, int max_n_r, cudaStream_t st, cudaEvent_t between)
 {
     const size_t smem = sizeof(RightKey) * (size_t)max_n_r;
     cudaFuncSetAttribute(k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((a.K + SW * 4 - 1) / (SW * 4), npairs);
     k_stereo_match<<<grid, SW * 32, smem, st>>>(g, a, max_n_r);
+    if (between) cudaEventRecord(between, st);
     k_stereo_reject<<<npairs, 256, 0, st>>>(a);
     return 2;
 }
