@@ -4,18 +4,22 @@
 //
 // The reference blurs every whole level and then gathers 512 samples per keypoint.  Here each warp
 // stages the 43x43 raw patch around its keypoint in shared memory once (37x37 blurred support,
-// radius 18 = max |rotated pattern coordinate|, plus the 3-px blur halo), and derives from it
+// radius 18 = max |rotated pattern coordinate|, plus the 3-px blur halo) with aligned 32-bit loads,
+// and derives from it
 //   * the intensity-centroid moments over the radius-15 disc (integer, exact) -> fastAtan2 angle,
-//   * the separable fixed-point blur [18 34 48 56 48 34 18]/256 with one final rounding
-//     (v + 2^15) >> 16, BORDER_REFLECT_101 applied at the true image edge while staging,
-//   * the 256 pattern tests; lane i produces descriptor byte i.
-// No blurred level is ever written to or read from global memory.
+//   * the horizontal half of the separable fixed-point blur [18 34 48 56 48 34 18]/256 for all 43 rows,
+//     two rows per lane packed 16x2 in one 32-bit register (each half stays <= 65280, so plain 32-bit
+//     multiply-adds never carry across the halves),
+//   * the vertical half only at the 512 sampled positions, fused into the pattern tests with the single
+//     final rounding (v + 2^15) >> 16; lane i produces descriptor byte i.
+// BORDER_REFLECT_101 is applied at the true image edge while staging.  No blurred level is ever written
+// to or read from global memory.
 //
 // Float islands follow DESIGN.md parity rule 3: single-rounded __f*_rn ops (no FMA), cos/sin in
 // double then rounded to float, cvRound = round-half-even.
 //
-// Bound: shared memory (≈8.5 k shared accesses per keypoint); algorithmic global bytes per keypoint
-// = 1849 (patch) + 4 (lkp) + 28 + 32 (outputs).
+// Bound: shared memory / integer ALU; algorithmic global bytes per keypoint = 1849 (patch) + 4 (lkp)
+// + 28 + 32 (outputs).
 #include "pslot_internal.h"
 
 namespace {
@@ -23,11 +27,12 @@ namespace {
 constexpr int DW = 4;           // warps (keypoints) per CTA
 constexpr int PR = 21;          // raw patch radius
 constexpr int PD = 2 * PR + 1;  // 43
-constexpr int RS = 44;          // raw row stride (bytes): 11 words, odd -> conflict-free row-parallel access
-constexpr int BR = 18;          // blurred patch radius
+constexpr int RW = 13;          // raw row stride in words (52 bytes): odd -> conflict-free row-parallel access
+constexpr int RS = RW * 4;
+constexpr int NW = 12;          // aligned words fetched per patch row (covers 43 bytes at any alignment)
+constexpr int BR = 18;          // blurred support radius
 constexpr int BD = 2 * BR + 1;  // 37
 constexpr int HS = 38;          // h-pass row stride (u16): 19 words, odd
-constexpr int BS = 40;          // blurred row stride (bytes)
 
 __constant__ int8_t c_pattern[1024] = {
 #include "../../include/pslot_orb_pattern.inc"
@@ -36,9 +41,8 @@ __constant__ int8_t c_pattern[1024] = {
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
 struct WarpSmem {
-    uint8_t raw[PD * RS];
-    uint16_t hp[PD * HS];
-    uint8_t blur[BD * BS];
+    uint32_t raw[PD * RW];  // patch bytes, row stride 52; column c of the patch is byte c + shift
+    uint16_t hp[PD * HS];   // horizontal pass, [patch row][blurred column]
 };
 
 __device__ __forceinline__ int reflect101(int i, int n)
@@ -110,19 +114,24 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
     const int kx = pslot_px(kp), ky = pslot_py(kp), kr = pslot_pr(kp);
     const uint8_t *img = pyr.lv[l] + (size_t)slot * pyr.slot_stride[l];
     WarpSmem &S = sm[warp];
+    uint8_t *rawb = reinterpret_cast<uint8_t *>(S.raw);
 
-    // ---- stage the 43x43 raw patch (reflect-101 at the image edge) ------------------------------
+    // ---- stage the 43x43 raw patch ------------------------------------------------------------------
     const int x0 = kx - PR, y0 = ky - PR;
-    const bool interior = x0 >= 0 && y0 >= 0 && x0 + PD <= L.w && y0 + PD <= L.h;
-    if (interior) {
-        for (int e = lane; e < PD * PD; e += 32) {
-            const int r = e / PD, c = e - r * PD;
-            S.raw[r * RS + c] = __ldg(img + (size_t)(y0 + r) * L.pitch + x0 + c);
+    int shift; // patch column c lives at byte c + shift of its shared row
+    if (x0 >= 0 && y0 >= 0 && x0 + PD <= L.w && y0 + PD <= L.h) {
+        // rows are 4-byte aligned in global memory (pitch % 128 == 0): fetch 12 aligned words per row
+        shift = x0 & 3;
+        const uint8_t *src = img + (size_t)y0 * L.pitch + (x0 - shift);
+        for (int e = lane; e < PD * NW; e += 32) {
+            const int r = e / NW, wc = e - r * NW;
+            S.raw[r * RW + wc] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)r * L.pitch) + wc);
         }
-    } else {
+    } else { // within 21 px of the image edge: BORDER_REFLECT_101, byte by byte
+        shift = 0;
         for (int e = lane; e < PD * PD; e += 32) {
             const int r = e / PD, c = e - r * PD;
-            S.raw[r * RS + c] = __ldg(img + (size_t)reflect101(y0 + r, L.h) * L.pitch + reflect101(x0 + c, L.w));
+            rawb[r * RS + c] = __ldg(img + (size_t)reflect101(y0 + r, L.h) * L.pitch + reflect101(x0 + c, L.w));
         }
     }
     __syncwarp();
@@ -132,7 +141,7 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
     if (lane < 31) {
         const int v = lane - PSLOT_HALF_PATCH;
         const int d = c_umax[v < 0 ? -v : v];
-        const uint8_t *row = S.raw + (PR + v) * RS + PR;
+        const uint8_t *row = rawb + (PR + v) * RS + PR + shift;
         int sum = 0;
         for (int u = -d; u <= d; ++u) {
             const int val = row[u];
@@ -148,49 +157,44 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // ---- horizontal blur pass: lane = patch row, sliding 7-tap window -------------------------------
-    for (int r = lane; r < PD; r += 32) {
-        const uint8_t *row = S.raw + r * RS;
-        uint16_t *hrow = S.hp + r * HS;
-        int a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3], a4 = row[4], a5 = row[5];
+    // ---- horizontal blur pass: lane owns rows (lane, lane + 22), packed 16x2 --------------------------
+    if (lane < 22) {
+        const int ra = lane, rb = min(lane + 22, PD - 1);
+        const uint8_t *pa = rawb + ra * RS + shift, *pb = rawb + rb * RS + shift;
+        uint16_t *ha = S.hp + ra * HS, *hb = S.hp + rb * HS;
+        uint32_t q[PD];
+#pragma unroll
+        for (int c = 0; c < PD; ++c) q[c] = (uint32_t)pa[c] | ((uint32_t)pb[c] << 16);
+#pragma unroll
         for (int c = 0; c < BD; ++c) {
-            const int a6 = row[c + 6];
-            hrow[c] = (uint16_t)(18 * (a0 + a6) + 34 * (a1 + a5) + 48 * (a2 + a4) + 56 * a3);
-            a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = a5; a5 = a6;
-        }
-    }
-    __syncwarp();
-    // ---- vertical pass: lane = patch column ---------------------------------------------------------
-    for (int c = lane; c < BD; c += 32) {
-        const uint16_t *col = S.hp + c;
-        int a0 = col[0], a1 = col[HS], a2 = col[2 * HS], a3 = col[3 * HS], a4 = col[4 * HS], a5 = col[5 * HS];
-        for (int r = 0; r < BD; ++r) {
-            const int a6 = col[(r + 6) * HS];
-            const int v = 18 * (a0 + a6) + 34 * (a1 + a5) + 48 * (a2 + a4) + 56 * a3;
-            S.blur[r * BS + c] = (uint8_t)((v + 32768) >> 16);
-            a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = a5; a5 = a6;
+            const uint32_t h = 18u * (q[c] + q[c + 6]) + 34u * (q[c + 1] + q[c + 5]) + 48u * (q[c + 2] + q[c + 4]) + 56u * q[c + 3];
+            ha[c] = (uint16_t)(h & 0xFFFFu);
+            hb[c] = (uint16_t)(h >> 16);
         }
     }
     __syncwarp();
 
-    // ---- steered BRIEF: lane -> descriptor byte (:107-147) ------------------------------------------
+    // ---- steered BRIEF with the vertical blur pass at the sampled positions (:107-147) ---------------
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
     const float ang = __fmul_rn(angle, factorPI);
     double sd, cd;
     sincos((double)ang, &sd, &cd);
     const float a = (float)cd, b = (float)sd;
-    const uint8_t *center = S.blur + BR * BS + BR;
+    const uint16_t *hc = S.hp + BR; // hp[r + 18 - 3 + j][c + 18]: rows r+15 .. r+21 for blurred row r (relative to centre)
+    auto sample = [&](float px, float py) -> int {
+        const int r = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+        const int c = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+        const uint16_t *p = hc + (r + BR) * HS + c; // top tap: patch row (r + 21) - 3
+        const int v = 18 * ((int)p[0] + (int)p[6 * HS]) + 34 * ((int)p[HS] + (int)p[5 * HS]) +
+                      48 * ((int)p[2 * HS] + (int)p[4 * HS]) + 56 * (int)p[3 * HS];
+        return (v + 32768) >> 16;
+    };
     int val = 0;
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
         const uint32_t p = s_pat[t * 32 + lane];
-        const float px0 = (float)(int8_t)(p & 0xFF), py0 = (float)(int8_t)((p >> 8) & 0xFF);
-        const float px1 = (float)(int8_t)((p >> 16) & 0xFF), py1 = (float)(int8_t)(p >> 24);
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(px0, b), __fmul_rn(py0, a)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(px0, a), __fmul_rn(py0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(px1, b), __fmul_rn(py1, a)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(px1, a), __fmul_rn(py1, b)));
-        const int t0 = center[r0 * BS + c0], t1 = center[r1 * BS + c1];
+        const int t0 = sample((float)(int8_t)(p & 0xFF), (float)(int8_t)((p >> 8) & 0xFF));
+        const int t1 = sample((float)(int8_t)((p >> 16) & 0xFF), (float)(int8_t)(p >> 24));
         val |= (t0 < t1) << t;
     }
     const size_t o = (size_t)slot * g.kp_cap_total + out_base + i;

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "pslot_internal.h"
+#include "tma.cuh"
 
 namespace {
 
@@ -104,6 +105,7 @@ struct Engine {
     int W = 0, H = 0, S = 0; // configured geometry / slot capacity
     Geom g{};
     PyrPtrs pyr{};
+    TmapSet maps{};
     bool has_pyramid = false;
 
     uint8_t *d_pyr = nullptr;
@@ -179,6 +181,8 @@ struct Engine {
             L.w_cell = (int)ceilf(width / (float)L.n_cols);
             L.h_cell = (int)ceilf(height / (float)L.n_rows);
             if (L.w_cell > 59 || L.h_cell > 59) return fail(PSLOT_ERR_SHAPE, "cell %dx%d too large", L.w_cell, L.h_cell);
+            L.box_w = (int)align_up((size_t)L.w_cell + 30, 16);
+            L.box_h = L.h_cell + 6;
             L.cell_base = cells;
             cells += L.n_cols * L.n_rows;
             L.cand_stride = ((L.w_cell + 1) / 2) * ((L.h_cell + 1) / 2);
@@ -215,6 +219,35 @@ struct Engine {
         return PSLOT_OK;
     }
 
+    // One (x, y, slot) u8 tensor map per pyramid level; box = the FAST cell tile.  Out-of-image box
+    // elements are zero-filled by the TMA unit.
+    int make_tensor_maps(int nslots)
+    {
+        typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = nullptr;
+        if (!encode) {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+            if (!fn || q != cudaDriverEntryPointSuccess) return fail(PSLOT_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+            encode = (EncodeFn)fn;
+        }
+        for (int l = 0; l < g.nlevels; ++l) {
+            const LevelGeom &L = g.lv[l];
+            const cuuint64_t dims[3] = {(cuuint64_t)L.w, (cuuint64_t)L.h, (cuuint64_t)nslots};
+            const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)pyr.slot_stride[l]};
+            const cuuint32_t box[3] = {(cuuint32_t)L.box_w, (cuuint32_t)L.box_h, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = encode(&maps.lv[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pyr.lv[l], dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(PSLOT_ERR_CUDA, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, (int)r);
+        }
+        return PSLOT_OK;
+    }
+
     int configure(int w, int h, int nslots)
     {
         if (w == W && h == H && nslots <= S) return PSLOT_OK;
@@ -235,6 +268,8 @@ struct Engine {
         }
         CU(cudaMalloc(&d_pyr, off + 256));
         for (int l = 0; l < g.nlevels; ++l) pyr.lv[l] = d_pyr + lvoff[l];
+        rc = make_tensor_maps(nslots);
+        if (rc) return rc;
         CU(cudaMalloc(&d_taps, sizeof(ResizeTap) * std::max<size_t>(taps.size(), 4)));
         if (!taps.empty()) CU(cudaMemcpy(d_taps, taps.data(), sizeof(ResizeTap) * taps.size(), cudaMemcpyHostToDevice));
         const size_t ns = (size_t)nslots;
@@ -270,7 +305,7 @@ struct Engine {
         if (ev) cudaEventRecord(ev[1], st);
         n += launch_pyramid(g, pyr, d_taps, nslots, st);
         if (ev) cudaEventRecord(ev[2], st);
-        n += launch_fast(g, pyr, d_cell_count, d_cell_cand, nslots, st);
+        n += launch_fast(g, maps, d_cell_count, d_cell_cand, nslots, st);
         if (ev) cudaEventRecord(ev[3], st);
         n += launch_quadtree(g, d_cell_count, d_cell_cand, d_cell_prefix, d_qt_keys, d_qt_nodes, d_lkp, d_lkp_count,
                              d_err, nslots, st);
@@ -333,10 +368,12 @@ struct pslot_batch {
     int launches = 0;
     bool profiling = false, profiled = false;
     cudaEvent_t ev[PSLOT_NUM_STAGES + 1] = {};
+    uint8_t *d_stage = nullptr; // tightly packed landing zone for host images (one linear H2D per view)
     ~pslot_batch()
     {
         for (auto &e : ev)
             if (e) cudaEventDestroy(e);
+        cudaFree(d_stage);
     }
 };
 
@@ -629,7 +666,14 @@ int pslot_batch_submit(pslot_batch *b, const uint8_t *left, const uint8_t *right
     const uint8_t *views[2] = {left, right};
     for (int v = 0; v < 2; ++v) {
         uint8_t *dst = E.pyr.lv[0] + (size_t)v * npairs * E.pyr.slot_stride[0];
-        if (image_stride == pitch * E.H) {
+        if (host_input && pitch == E.W && image_stride == pitch * E.H && pitch != L0.pitch) {
+            // PCIe at full rate: one linear copy, then an on-device 2-D copy into the padded level-0 rows
+            const size_t bytes = (size_t)E.W * E.H * npairs;
+            if (!b->d_stage) CU(cudaMalloc(&b->d_stage, 2 * (size_t)E.W * E.H * b->max_pairs));
+            uint8_t *stg = b->d_stage + (size_t)v * E.W * E.H * b->max_pairs;
+            CU(cudaMemcpyAsync(stg, views[v], bytes, cudaMemcpyHostToDevice, E.st));
+            CU(cudaMemcpy2DAsync(dst, L0.pitch, stg, E.W, E.W, (size_t)E.H * npairs, cudaMemcpyDeviceToDevice, E.st));
+        } else if (image_stride == pitch * E.H) {
             CU(cudaMemcpy2DAsync(dst, L0.pitch, views[v], pitch, E.W, (size_t)E.H * npairs, kind, E.st));
         } else {
             for (int i = 0; i < npairs; ++i)

@@ -36,6 +36,7 @@ struct LevelGeom {
     float scale, inv_scale;             // mvScaleFactor / mvInvScaleFactor (:421,429)
     int patch_size;                     // (int)(31 * scale) (:834)
     int tab_x, tab_y;                   // offsets into the resize tap table
+    int box_w, box_h;                   // TMA box of one FAST cell tile: align16(wCell + 30) x (hCell + 6)
 };
 
 struct Geom {
@@ -76,7 +77,8 @@ struct StereoArgs {
 
 // ---- launchers (each enqueues on `st`; returns the number of kernels launched) -----------------
 int launch_pyramid(const Geom &g, const PyrPtrs &pyr, const ResizeTap *taps, int nslots, cudaStream_t st);
-int launch_fast(const Geom &g, const PyrPtrs &pyr, int *cell_count, uint32_t *cell_cand, int nslots, cudaStream_t st);
+struct TmapSet;
+int launch_fast(const Geom &g, const TmapSet &maps, int *cell_count, uint32_t *cell_cand, int nslots, cudaStream_t st);
 int launch_quadtree(const Geom &g, const int *cell_count, const uint32_t *cell_cand, int *cell_prefix,
                     uint32_t *qt_keys, uint16_t *qt_nodes, uint32_t *lkp, int *lkp_count, int *err_flag,
                     int nslots, cudaStream_t st);

@@ -7,44 +7,57 @@
 // Integer-only, hence bit-exact.  Levels are chained (each from the previous one, :1120), so a batch
 // needs nlevels-1 dependent launches; each launch covers every slot of the batch.
 //
-// Bound: HBM/L2 streaming.  Algorithmic bytes per launch = S * (P_{l-1} + P_l).
+// Mapping: a warp covers 32 consecutive output columns (so one load instruction touches ~38 consecutive
+// source bytes = one or two 32-byte sectors) and each thread walks RROWS consecutive output rows,
+// re-using the horizontally interpolated source row shared by neighbouring output rows (scale 1.2:
+// consecutive output rows share a source row 4 times out of 5).
+//
+// Bound: L1/LSU wavefronts on byte loads (gather at a non-integer stride); algorithmic HBM bytes per
+// launch = S * (P_{l-1} + P_l).
 #include "pslot_internal.h"
 
 namespace {
 
-constexpr int RX = 64; // threads along x, 4 output pixels each
-constexpr int RY = 4;
+constexpr int RX = 128;   // threads per CTA = output columns per CTA
+constexpr int RROWS = 8;  // output rows per thread
 
-__global__ void __launch_bounds__(RX *RY)
+__global__ void __launch_bounds__(RX)
 k_resize_level(const uint8_t *__restrict__ src, int spitch, unsigned long long sstride,
                uint8_t *__restrict__ dst, int dw, int dh, int dpitch, unsigned long long dstride,
                const ResizeTap *__restrict__ xt, const ResizeTap *__restrict__ yt)
 {
-    const int dx0 = (blockIdx.x * RX + threadIdx.x) * 4;
-    const int dy = blockIdx.y * RY + threadIdx.y;
-    if (dx0 >= dw || dy >= dh) return;
+    const int dx = blockIdx.x * RX + threadIdx.x;
+    if (dx >= dw) return;
+    const int dy0 = blockIdx.y * RROWS;
     const uint8_t *s = src + (size_t)blockIdx.z * sstride;
-    uint8_t *d = dst + (size_t)blockIdx.z * dstride;
-    const ResizeTap ty = yt[dy];
-    const uint8_t *r0 = s + (size_t)ty.s0 * spitch;
-    const uint8_t *r1 = s + (size_t)ty.s1 * spitch;
-    // the tap table is padded to a multiple of 4 entries, so a 2 x 16-byte vector read is in bounds
-    const uint4 ta = __ldg(reinterpret_cast<const uint4 *>(xt + dx0));
-    const uint4 tb = __ldg(reinterpret_cast<const uint4 *>(xt + dx0 + 2));
-    const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-    uint32_t out = 0;
+    uint8_t *d = dst + (size_t)blockIdx.z * dstride + dx;
+    const ResizeTap tx = xt[dx];
+    const int x0 = tx.s0, x1 = tx.s1, cx0 = tx.c0, cx1 = tx.c1;
+    int cached_row = -1, cached_h = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int s0 = (int)(tw[2 * k] & 0xFFFFu), s1 = (int)(tw[2 * k] >> 16);
-        const int c0 = (int)(short)(tw[2 * k + 1] & 0xFFFFu), c1 = (int)(short)(tw[2 * k + 1] >> 16);
-        const int h0 = (int)__ldg(r0 + s0) * c0 + (int)__ldg(r0 + s1) * c1;
-        const int h1 = (int)__ldg(r1 + s0) * c0 + (int)__ldg(r1 + s1) * c1;
+    for (int r = 0; r < RROWS; ++r) {
+        const int dy = dy0 + r;
+        if (dy >= dh) break;
+        const ResizeTap ty = yt[dy];
+        int h0, h1;
+        if (ty.s0 == cached_row) {
+            h0 = cached_h;
+        } else {
+            const uint8_t *p = s + (size_t)ty.s0 * spitch;
+            h0 = (int)__ldg(p + x0) * cx0 + (int)__ldg(p + x1) * cx1;
+        }
+        if (ty.s1 == ty.s0) {
+            h1 = h0;
+        } else {
+            const uint8_t *p = s + (size_t)ty.s1 * spitch;
+            h1 = (int)__ldg(p + x0) * cx0 + (int)__ldg(p + x1) * cx1;
+        }
+        cached_row = ty.s1;
+        cached_h = h1;
         int v = ((((int)ty.c0 * (h0 >> 4)) >> 16) + (((int)ty.c1 * (h1 >> 4)) >> 16) + 2) >> 2;
         v = min(max(v, 0), 255);
-        out |= (uint32_t)v << (8 * k);
+        d[(size_t)dy * dpitch] = (uint8_t)v;
     }
-    // pitch is a multiple of 128, so the word store is aligned; bytes past dw land in row padding
-    *reinterpret_cast<uint32_t *>(d + (size_t)dy * dpitch + dx0) = out;
 }
 
 } // namespace
@@ -54,10 +67,9 @@ int launch_pyramid(const Geom &g, const PyrPtrs &pyr, const ResizeTap *taps, int
     int launches = 0;
     for (int l = 1; l < g.nlevels; ++l) {
         const LevelGeom &S = g.lv[l - 1], &D = g.lv[l];
-        dim3 block(RX, RY);
-        dim3 grid((D.w + RX * 4 - 1) / (RX * 4), (D.h + RY - 1) / RY, nslots);
-        k_resize_level<<<grid, block, 0, st>>>(pyr.lv[l - 1], S.pitch, pyr.slot_stride[l - 1], pyr.lv[l], D.w, D.h,
-                                               D.pitch, pyr.slot_stride[l], taps + D.tab_x, taps + D.tab_y);
+        dim3 grid((D.w + RX - 1) / RX, (D.h + RROWS - 1) / RROWS, nslots);
+        k_resize_level<<<grid, RX, 0, st>>>(pyr.lv[l - 1], S.pitch, pyr.slot_stride[l - 1], pyr.lv[l], D.w, D.h,
+                                            D.pitch, pyr.slot_stride[l], taps + D.tab_x, taps + D.tab_y);
         ++launches;
     }
     return launches;
