@@ -34,9 +34,24 @@ constexpr int BR = 18;          // blurred support radius
 constexpr int BD = 2 * BR + 1;  // 37
 constexpr int HS = 38;          // h-pass row stride (u16): 19 words, odd
 
-__constant__ int8_t c_pattern[1024] = {
+// pattern, re-laid out at compile time as [t][lane] words (test 8*lane + t; bytes x0,y0,x1,y1) so that a
+// warp reads one coalesced 128-byte line per test index
+struct PatTable { uint32_t w[256]; };
+constexpr PatTable make_pat()
+{
+    constexpr int8_t raw[1024] = {
 #include "../../include/pslot_orb_pattern.inc"
-};
+    };
+    PatTable t{};
+    for (int i = 0; i < 256; ++i) {
+        const int tt = i >> 5, ln = i & 31;
+        const int8_t *p = raw + 4 * (8 * ln + tt);
+        t.w[i] = (uint32_t)(uint8_t)p[0] | ((uint32_t)(uint8_t)p[1] << 8) | ((uint32_t)(uint8_t)p[2] << 16) |
+                 ((uint32_t)(uint8_t)p[3] << 24);
+    }
+    return t;
+}
+__device__ const PatTable g_pat = make_pat();
 // umax[v]: half-width of the radius-15 disc at row v (ORBextractor.cc:454-469)
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
@@ -81,17 +96,9 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
            pslot_keypoint *__restrict__ out_kps, uint8_t *__restrict__ out_desc, int *__restrict__ out_count)
 {
     __shared__ __align__(16) WarpSmem sm[DW];
-    __shared__ uint32_t s_pat[256]; // [t][lane]: test 8*lane + t, bytes x0,y0,x1,y1
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slot = blockIdx.y;
-    for (int i = tid; i < 256; i += DW * 32) {
-        const int t = i >> 5, ln = i & 31;
-        const int8_t *p = c_pattern + 4 * (8 * ln + t);
-        s_pat[i] = (uint32_t)(uint8_t)p[0] | ((uint32_t)(uint8_t)p[1] << 8) | ((uint32_t)(uint8_t)p[2] << 16) |
-                   ((uint32_t)(uint8_t)p[3] << 24);
-    }
-    __syncthreads();
 
     // which keypoint: global index over the per-level capacity segments
     int idx = blockIdx.x * DW + warp;
@@ -123,9 +130,20 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
         // rows are 4-byte aligned in global memory (pitch % 128 == 0): fetch 12 aligned words per row
         shift = x0 & 3;
         const uint8_t *src = img + (size_t)y0 * L.pitch + (x0 - shift);
-        for (int e = lane; e < PD * NW; e += 32) {
+        // all 17 loads of a lane are issued before the first store (memory-level parallelism)
+        constexpr int NLD = (PD * NW + 31) / 32;
+        uint32_t v[NLD];
+#pragma unroll
+        for (int k = 0; k < NLD; ++k) {
+            const int e = min(lane + 32 * k, PD * NW - 1);
             const int r = e / NW, wc = e - r * NW;
-            S.raw[r * RW + wc] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)r * L.pitch) + wc);
+            v[k] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)r * L.pitch) + wc);
+        }
+#pragma unroll
+        for (int k = 0; k < NLD; ++k) {
+            const int e = lane + 32 * k;
+            const int r = e / NW, wc = e - r * NW;
+            if (e < PD * NW) S.raw[r * RW + wc] = v[k];
         }
     } else { // within 21 px of the image edge: BORDER_REFLECT_101, byte by byte
         shift = 0;
@@ -192,7 +210,7 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
     int val = 0;
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-        const uint32_t p = s_pat[t * 32 + lane];
+        const uint32_t p = __ldg(&g_pat.w[t * 32 + lane]);
         const int t0 = sample((float)(int8_t)(p & 0xFF), (float)(int8_t)((p >> 8) & 0xFF));
         const int t1 = sample((float)(int8_t)((p >> 16) & 0xFF), (float)(int8_t)(p >> 24));
         val |= (t0 < t1) << t;

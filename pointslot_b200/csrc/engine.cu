@@ -143,7 +143,8 @@ struct Engine {
     {
         if (pp.nlevels < 1 || pp.nlevels > PSLOT_MAX_LEVELS) return fail(PSLOT_ERR_ARG, "nlevels must be in [1,%d]", PSLOT_MAX_LEVELS);
         if (pp.nfeatures < 1 || pp.nfeatures > 30000) return fail(PSLOT_ERR_ARG, "nfeatures must be in [1,30000]");
-        if (!(pp.scale_factor > 1.0f)) return fail(PSLOT_ERR_ARG, "scaleFactor must be > 1");
+        if (!(pp.scale_factor > 1.0f) || pp.scale_factor > 1.45f)
+            return fail(PSLOT_ERR_ARG, "scaleFactor must be in (1, 1.45] (the pyramid kernel stages <= 1.49 source px per output px)");
         if (pp.min_th < 1 || pp.ini_th < pp.min_th || pp.ini_th > 254)
             return fail(PSLOT_ERR_ARG, "need 1 <= minThFAST <= iniThFAST <= 254");
         p = pp;

@@ -1,6 +1,6 @@
 // fast.cu — K2: the per-cell FAST loop of ComputeKeyPointsOctTree (reference src/ORBextractor.cc:765-829).
 //
-// One CTA per 30-px cell.  The reference calls cv::FAST(cell, iniThFAST, nms=true) and, if that
+// One WARP per 30-px cell (4 cells per CTA, no block-level barrier anywhere).  The reference calls cv::FAST(cell, iniThFAST, nms=true) and, if that
 // returns nothing, cv::FAST(cell, minThFAST, true) (:809-816).  Restated:
 //   raw score R(p) = max over the 16 arcs of 9 ring pixels of min(v - p_k) resp. min(p_k - v), minus 1
 //                    (OpenCV cornerScore<16>); p is a corner at threshold t  <=>  R >= t;
@@ -14,7 +14,9 @@
 // 16x2-packed pairs: the ring bytes are gathered from 21 aligned shared-memory words with PRMT into
 // the HIGH byte of each 16-bit half (the low byte is don't-care: it cannot change which high byte wins
 // a min/max), and the 9-wide sliding min/max runs on the native 3-input VIMNMX3.U16x2 (80 per pair).
-// The survivors are compacted in raster order with warp scans.
+// The survivors of both thresholds are compacted in raster order in the same sweep with one packed warp
+// scan (iniTh list straight to global memory, minTh list to shared memory, copied out only if the
+// iniTh list is empty).
 //
 // Integer-only, hence bit-exact.  Bound: integer ALU (~60 instructions per pixel, VIMNMX3 dominated);
 // algorithmic global bytes per launch = S * (sum_l P_l + 8 * n_candidates).
@@ -23,9 +25,7 @@
 
 namespace {
 
-constexpr int FT = 256;      // threads per CTA
-constexpr int TILE_BYTES = 96 * 66; // largest TMA box: wCell, hCell <= 59 -> 96 x 65 bytes (+1 score row)
-constexpr int MAX_ITERS = 4; // ceil(59 rows * 16 groups / 256)
+constexpr int FW = 4;        // warps (= cells) per CTA
 // A TMA box must start on a 16-byte boundary of the global row, so the box starts at the aligned x below
 // (cell start - 1); the residual 0..15 byte offset is uniform per CTA: a whole-word part folded into the
 // shared-memory word index and a 0..3 byte part removed with one funnel shift per word.
@@ -86,18 +86,17 @@ __device__ __forceinline__ void arc_minmax(const uint32_t (&P)[16], uint32_t &M1
 
 __device__ __forceinline__ int raw_score(int v, int m1, int m2) { return max(v - m1, m2 - v) - 1; }
 
-__global__ void __launch_bounds__(FT)
+__global__ void __launch_bounds__(FW * 32)
 k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet maps,
-             int *__restrict__ cell_count, uint32_t *__restrict__ cell_cand)
+             int *__restrict__ cell_count, uint32_t *__restrict__ cell_cand, int warp_smem_bytes)
 {
-    __shared__ __align__(128) uint8_t tile[TILE_BYTES];
-    __shared__ __align__(16) uint8_t score[TILE_BYTES];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ int warp_tot[FT / 32];
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[FW];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
-    int cell = blockIdx.x;
+    int cell = blockIdx.x * FW + warp;
+    if (cell >= g.cells_per_slot) return;
     int l = 0;
     while (l + 1 < g.nlevels && cell >= g.lv[l + 1].cell_base) ++l;
     const LevelGeom &L = g.lv[l];
@@ -111,40 +110,44 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
     const int tw = maxX - iniX, th = maxY - iniY;
     const int iw = tw - 6, ih = th - 6; // pixels cv::FAST actually tests
     if (iniY >= L.max_by - 3 || iniX >= L.max_bx - 3 || iw <= 0 || ih <= 0) {
-        if (tid == 0) *count_out = 0;
+        if (lane == 0) *count_out = 0;
         return;
     }
 
-    // ---- stage the cell: one TMA box load (x, y, slot) -> dense shared tile, row stride = box width ----
+    // per-warp shared memory: [ TMA tile (box_w x box_h) | score map (same stride, box_h + 1 rows) ]
+    uint8_t *tile = smem + (size_t)warp * warp_smem_bytes;
     const int TS = L.box_w, TSW = TS >> 2;
+    uint8_t *score = tile + ((TS * L.box_h + 127) & ~127);
+    uint64_t *bar = &bars[warp];
+
+    // ---- stage the cell: one TMA box load (x, y, slot) -> dense shared tile, row stride = box width ----
     const int xa = (iniX - 1) & ~15;          // 16-byte aligned box origin
     const int sh0 = (iniX - 1) - xa;          // image column iniX-1+b lives at shared byte sh0 + b
     const int wsh = sh0 >> 2, bsh = (sh0 & 3) * 8;
-    if (tid == 0) {
-        tma::mbar_init(&bar, 1);
+    if (lane == 0) {
+        tma::mbar_init(bar, 1);
         tma::fence_barrier_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        tma::mbar_arrive_expect_tx(&bar, (uint32_t)(L.box_w * L.box_h));
-        tma::load_3d(tile, &maps.lv[l], &bar, xa, iniY, slot);
+        tma::mbar_arrive_expect_tx(bar, (uint32_t)(TS * L.box_h));
+        tma::load_3d(tile, &maps.lv[l], bar, xa, iniY, slot);
     }
     {
-        uint32_t *s4 = reinterpret_cast<uint32_t *>(score);
-        const int nwords = (th + 1) * TSW;
-        for (int i = tid; i < nwords; i += FT) s4[i] = 0;
+        uint4 *s16 = reinterpret_cast<uint4 *>(score);
+        const int n16 = ((th + 1) * TS) >> 4; // TS % 16 == 0
+        for (int i = lane; i < n16; i += 32) s16[i] = make_uint4(0, 0, 0, 0);
     }
-    tma::mbar_wait(&bar, 0);
-    __syncthreads();
+    __syncwarp();
+    tma::mbar_wait(bar, 0);
 
     // tasks: (interior row y, group of 4 pixels gx); G groups per row, G a power of two
     const int gshift = iw <= 32 ? 3 : 4;
     const int G = 1 << gshift;
     const int ntasks = ih << gshift;
-    const int tmin = g.min_th, tini = g.ini_th;
+    // thresholds as packed constants: (t - 1) in both 16-bit halves; SWAR bias for "some byte >= minTh"
+    const uint32_t tmin1 = (uint32_t)(g.min_th - 1) * 0x00010001u, tini1 = (uint32_t)(g.ini_th - 1) * 0x00010001u;
+    const uint32_t ge_bias = g.min_th <= 128 ? (uint32_t)(128 - g.min_th) * 0x01010101u : 0x7F7F7F7Fu;
 
     // ---- pass 1: dense exact scores ---------------------------------------------------------------
-    for (int t = tid; t < ntasks; t += FT) {
+    for (int t = lane; t < ntasks; t += 32) {
         const int y = t >> gshift, gx = t & (G - 1);
         if (4 * gx >= iw) continue;
         // window of the group: bytes -4..7 around its first pixel = shared bytes sh0 + 4*gx + (0..11) of each ring row
@@ -164,101 +167,112 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
         ring_pairs<1>(w, P);
         arc_minmax(P, m1b, m2b);
         const uint32_t c = w[3][1]; // the 4 centre pixels
-        int s0 = raw_score((int)(c & 0xFF), (int)((m1a >> 8) & 0xFF), (int)((m2a >> 8) & 0xFF));
-        int s1 = raw_score((int)((c >> 8) & 0xFF), (int)(m1a >> 24), (int)(m2a >> 24));
-        int s2 = raw_score((int)((c >> 16) & 0xFF), (int)((m1b >> 8) & 0xFF), (int)((m2b >> 8) & 0xFF));
-        int s3 = raw_score((int)(c >> 24), (int)(m1b >> 24), (int)(m2b >> 24));
-        const int x0 = 4 * gx;
-        s0 = (s0 >= tmin) ? s0 : 0;
-        s1 = (s1 >= tmin && x0 + 1 < iw) ? s1 : 0;
-        s2 = (s2 >= tmin && x0 + 2 < iw) ? s2 : 0;
-        s3 = (s3 >= tmin && x0 + 3 < iw) ? s3 : 0;
-        reinterpret_cast<uint32_t *>(score)[(y + 3) * TSW + gx + 1] =
-            (uint32_t)s0 | ((uint32_t)s1 << 8) | ((uint32_t)s2 << 16) | ((uint32_t)s3 << 24);
+        // clean (zero-extended) 16x2 operands: centre pairs, and the extrema moved down from the high bytes
+        const uint32_t v01 = __byte_perm(c, 0, 0x4140), v23 = __byte_perm(c, 0, 0x4342);
+        const uint32_t a01 = __byte_perm(m1a, 0, 0x4341), b01 = __byte_perm(m2a, 0, 0x4341);
+        const uint32_t a23 = __byte_perm(m1b, 0, 0x4341), b23 = __byte_perm(m2b, 0, 0x4341);
+        // R = max(v - M1, M2 - v) - 1 clamped at 0; thresholds are applied in pass 2
+        const uint32_t one = 0x00010001u;
+        const uint32_t r01 = __vimax_s16x2_relu(__vsub2(__vsub2(v01, a01), one), __vsub2(__vsub2(b01, v01), one));
+        const uint32_t r23 = __vimax_s16x2_relu(__vsub2(__vsub2(v23, a23), one), __vsub2(__vsub2(b23, v23), one));
+        uint32_t s4 = __byte_perm(r01, r23, 0x6420);
+        const int rem = iw - 4 * gx; // tested pixels left in this row (>= 1)
+        if (rem < 4) s4 &= (1u << (8 * rem)) - 1u;
+        // score map: tested pixel x lives at byte x + 4 of its row
+        reinterpret_cast<uint32_t *>(score)[(y + 3) * TSW + gx + 1] = s4;
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- pass 2: 3x3 strict-maximum test at both thresholds ------------------------------------------
-    // flag bits per task: [3:0] survivor at iniTh, [7:4] survivor at minTh
-    uint32_t flags[MAX_ITERS];
-    bool any_ini = false;
-#pragma unroll
-    for (int it = 0; it < MAX_ITERS; ++it) {
-        flags[it] = 0;
-        const int t = tid + it * FT;
+    // ---- pass 2: 3x3 strict maxima at both thresholds + raster-ordered compaction of both lists ----
+    uint32_t *out = cell_cand + (size_t)slot * g.cand_per_slot + L.cand_base + (size_t)cell * L.cand_stride;
+    uint32_t *min_list = reinterpret_cast<uint32_t *>(tile); // the raw tile is dead after pass 1
+    const int ox = iniX + 3 - PSLOT_MINB, oy = iniY + 3 - PSLOT_MINB; // window-relative (:820-825)
+    uint32_t totals = 0; // iniTh count | minTh count << 16
+    for (int base = 0; base < ntasks; base += 32) {
+        const int t = base + lane;
+        const int y = t >> gshift, gx = t & (G - 1);
+        uint32_t f_ini = 0, f_min = 0, s4 = 0;
         if (t < ntasks) {
-            const int y = t >> gshift, gx = t & (G - 1);
-            const int off = (y + 3) * TS + 4 * gx + 4;
-            const uint32_t s4 = *reinterpret_cast<const uint32_t *>(score + off);
-            if (s4) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int s = (int)((s4 >> (8 * i)) & 0xFF);
-                    if (s) {
-                        const uint8_t *p = score + off + i;
-                        int nmax = max(max((int)p[-TS - 1], (int)p[-TS]), max((int)p[-TS + 1], (int)p[-1]));
-                        nmax = max(max(nmax, (int)p[1]), max(max((int)p[TS - 1], (int)p[TS]), (int)p[TS + 1]));
-                        // at threshold t the neighbour map is (score >= t ? score : 0)
-                        const bool keep_min = s > nmax;
-                        const bool keep_ini = (s >= tini) && (s > (nmax >= tini ? nmax : 0));
-                        flags[it] |= (keep_ini ? 1u : 0u) << i;
-                        flags[it] |= (keep_min ? 16u : 0u) << i;
-                        any_ini |= keep_ini;
-                    }
-                }
+            const uint32_t *sw = reinterpret_cast<const uint32_t *>(score) + (y + 3) * TSW + gx + 1;
+            s4 = sw[0];
+            // any byte >= minTh?  (SWAR "hasmore"; a false positive only costs the test below)
+            if (((s4 + ge_bias) | s4) & 0x80808080u) {
+                // At threshold t the neighbour map is (R >= t ? R : 0) and the pixel needs R >= t, so
+                // "strictly above all 8 neighbours at threshold t" == (R >= t) && (R > max of the 8 raw R).
+                const uint32_t uL = sw[-TSW - 1], uM = sw[-TSW], uR = sw[-TSW + 1];
+                const uint32_t cL = sw[-1], cR = sw[1];
+                const uint32_t dL = sw[TSW - 1], dM = sw[TSW], dR = sw[TSW + 1];
+                // words holding, for each of the 4 pixels, its neighbour one column to the left / right
+                const uint32_t ul = __funnelshift_r(uL, uM, 24), ur = __funnelshift_r(uM, uR, 8);
+                const uint32_t cl = __funnelshift_r(cL, s4, 24), cr = __funnelshift_r(s4, cR, 8);
+                const uint32_t dl = __funnelshift_r(dL, dM, 24), dr = __funnelshift_r(dM, dR, 8);
+#define EV(x) __byte_perm((x), 0, 0x4240) /* bytes 0,2 -> 16x2 */
+#define OD(x) __byte_perm((x), 0, 0x4341) /* bytes 1,3 -> 16x2 */
+                uint32_t ne = __vimax3_u16x2(EV(ul), EV(uM), EV(ur));
+                ne = __vimax3_u16x2(ne, EV(cl), EV(cr));
+                ne = __vimax3_u16x2(ne, EV(dl), EV(dM));
+                ne = __vmaxu2(ne, EV(dr));
+                uint32_t no = __vimax3_u16x2(OD(ul), OD(uM), OD(ur));
+                no = __vimax3_u16x2(no, OD(cl), OD(cr));
+                no = __vimax3_u16x2(no, OD(dl), OD(dM));
+                no = __vmaxu2(no, OD(dr));
+                const uint32_t se = EV(s4), so = OD(s4);
+#undef EV
+#undef OD
+                // sign bit of each half: (nmax - R) < 0  <=>  R > nmax ;  (t - 1 - R) < 0  <=>  R >= t
+                const uint32_t gte = __vsub2(ne, se), gto = __vsub2(no, so);
+                const uint32_t me = gte & __vsub2(tmin1, se), mo = gto & __vsub2(tmin1, so);
+                const uint32_t ie = gte & __vsub2(tini1, se), io = gto & __vsub2(tini1, so);
+                // halves: e = pixels (0, 2), o = pixels (1, 3)  ->  4-bit flags
+                const uint32_t cm = ((me & 0x80008000u) >> 1) | (mo & 0x80008000u);
+                const uint32_t cf = ((ie & 0x80008000u) >> 1) | (io & 0x80008000u);
+                f_min = ((cm >> 14) & 3u) | ((cm >> 28) & 0xCu);
+                f_ini = ((cf >> 14) & 3u) | ((cf >> 28) & 0xCu);
             }
         }
-    }
-    const int use_ini = __syncthreads_or(any_ini);
-    const int fshift = use_ini ? 0 : 4;
-
-    // ---- pass 3: raster-ordered compaction ---------------------------------------------------------
-    uint32_t *out = cell_cand + (size_t)slot * g.cand_per_slot + L.cand_base + (size_t)cell * L.cand_stride;
-    const int ox = iniX + 3 - PSLOT_MINB, oy = iniY + 3 - PSLOT_MINB; // window-relative (:820-825)
-    int total = 0;
-#pragma unroll
-    for (int it = 0; it < MAX_ITERS; ++it) {
-        if (it * FT >= ntasks) break; // block-uniform
-        const uint32_t m = (flags[it] >> fshift) & 0xFu;
-        const int c = __popc(m);
-        int incl = c;
+        if (__ballot_sync(0xffffffffu, f_min != 0) == 0) continue; // nothing survives in these 32 groups (warp-uniform)
+        const uint32_t c = (uint32_t)__popc(f_ini) | ((uint32_t)__popc(f_min) << 16);
+        uint32_t incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        int before = 0, chunk = 0;
-#pragma unroll
-        for (int w = 0; w < FT / 32; ++w) {
-            const int v = warp_tot[w];
-            before += (w < warp) ? v : 0;
-            chunk += v;
+        const uint32_t excl = totals + incl - c;
+        int pi = (int)(excl & 0xFFFFu), pm = (int)(excl >> 16);
+        const uint32_t vbase = pslot_pack(4 * gx + ox, y + oy, 0);
+        for (uint32_t f = f_min; f; f &= f - 1) { // survivors of this group in x order (f_ini is a subset of f_min)
+            const int i = __ffs((int)f) - 1;
+            const uint32_t v = vbase + ((uint32_t)i << 8) + ((s4 >> (8 * i)) & 0xFFu);
+            if (f_ini & (1u << i)) { if (pi < L.cand_stride) out[pi] = v; ++pi; }
+            if (pm < L.cand_stride) min_list[pm] = v;
+            ++pm;
         }
-        if (m) {
-            const int t = tid + it * FT;
-            const int y = t >> gshift, gx = t & (G - 1);
-            const int off = (y + 3) * TS + 4 * gx + 4;
-            int pos = total + before + incl - c;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (m & (1u << i)) {
-                    if (pos < L.cand_stride) out[pos] = pslot_pack(4 * gx + i + ox, y + oy, score[off + i]);
-                    ++pos;
-                }
-        }
-        total += chunk;
-        __syncthreads();
+        totals += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (tid == 0) *count_out = min(total, L.cand_stride);
+    const int n_ini = (int)(totals & 0xFFFFu), n_min = (int)(totals >> 16);
+    int n = n_ini;
+    if (n_ini == 0) { // no corner at iniThFAST: the cell falls back to minThFAST (:812-816)
+        __syncwarp();
+        n = min(n_min, L.cand_stride);
+        for (int i = lane; i < n; i += 32) out[i] = min_list[i];
+    }
+    if (lane == 0) *count_out = min(n, L.cand_stride);
 }
 
 } // namespace
 
 int launch_fast(const Geom &g, const TmapSet &maps, int *cell_count, uint32_t *cell_cand, int nslots, cudaStream_t st)
 {
-    dim3 grid(g.cells_per_slot, nslots);
-    k_fast_cells<<<grid, FT, 0, st>>>(g, maps, cell_count, cell_cand);
+    int per_warp = 0;
+    for (int l = 0; l < g.nlevels; ++l) {
+        const int tile = (g.lv[l].box_w * g.lv[l].box_h + 127) & ~127;
+        const int score = (g.lv[l].box_w * (g.lv[l].box_h + 1) + 127) & ~127;
+        per_warp = per_warp > tile + score ? per_warp : tile + score;
+    }
+    const size_t smem = (size_t)per_warp * FW;
+    cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid((g.cells_per_slot + FW - 1) / FW, nslots);
+    k_fast_cells<<<grid, FW * 32, smem, st>>>(g, maps, cell_count, cell_cand, per_warp);
     return 1;
 }

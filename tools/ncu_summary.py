@@ -55,3 +55,21 @@ if "--source" in sys.argv:
     print(f"  total samples {tot:.0f}, warp instructions {toti:.0f}")
     for sm, ie, fn, ln, txt in sorted(agg, reverse=True)[:int(sys.argv[sys.argv.index("--source") + 1]) if sys.argv[-1].isdigit() else 25]:
         print(f"  {100*sm/tot:5.1f}% smp {100*ie/toti:5.1f}% inst  {fn}:{ln}: {txt}")
+if "--ops" in sys.argv:
+    import re
+    sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(sass)))
+    h = next(r for r in rows if "Instructions Executed" in r)
+    ii, si = h.index("Instructions Executed"), h.index("Source")
+    ops, tot = collections.Counter(), 0.0
+    for r in rows:
+        if len(r) != len(h) or r is h:
+            continue
+        try:
+            n = float(r[ii] or 0)
+        except ValueError:
+            continue
+        m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[si])
+        ops[m.group(2).split(".")[0] if m else "?"] += n
+        tot += n
+    print(f"  dynamic warp instructions {tot:.0f}; by opcode: " + "  ".join(f"{o}={100*n/tot:.1f}%" for o, n in ops.most_common(18)))
