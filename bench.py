@@ -202,6 +202,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
 
     from pointslot_b200 import binding as B
+    from pointslot_b200.shard import max_over_ranks, shard_range, sub_batches
     from pointslot_b200.synth import synth_batch_parallel
 
     torch.cuda.set_device(local_rank)
@@ -216,7 +217,8 @@ def run_ours(args, rank, world, local_rank):
     maxD = max_disparity()
     t_gen = time.time()
     procs = max(1, host_cores() // max(world, 1))
-    Ls, Rs = synth_batch_parallel(W, H, range(rank * P, rank * P + P), procs=min(procs, 64))
+    # weak scaling: the global batch is world * P pairs, rank r owns the contiguous block r (no collective)
+    Ls, Rs = synth_batch_parallel(W, H, shard_range(world * P, rank, world), procs=min(procs, 64))
     t_gen = time.time() - t_gen
 
     # pinned host copies (e2e) and device-resident copies (value)
@@ -238,9 +240,10 @@ def run_ours(args, rank, world, local_rank):
     stage_sum = np.zeros(len(B.StereoBatch.STAGES), np.float64)
     stage_n = [0]
 
+    subs = sub_batches(P, Bsz)
+
     def sub(i):
-        lo = i * Bsz
-        return lo, min(Bsz, P - lo)
+        return subs[i]
 
     def one_step(host: bool, collect: bool):
         pending = [False] * nctx
@@ -290,10 +293,7 @@ def run_ours(args, rank, world, local_rank):
         t1 = time.time()
         barrier()
         ms = start.elapsed_time(stop)
-        if dist is not None:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = max_over_ranks(ms, dist, "cuda")  # a multi-GPU number is the slowest rank's device time
         return ms, (t0, t1)
 
     sampler = ClockSampler(local_rank)

@@ -1,0 +1,79 @@
+// ORBextractor.h — drop-in replacement of PointSLOT's include/ORBextractor.h (reference lines 45-111).
+//
+// Same namespace, class name, constructor, operator() and getters as the reference, so Tracking.cc:385-388
+// (`new ORBextractor(nFeatures, fScaleFactor, nLevels, fIniThFAST, fMinThFAST)`) and Frame::ExtractORB
+// compile unchanged.  Every result comes from libpslot_orb.so (include/pslot_orb.h); nothing is computed
+// on the CPU here.
+//
+// Difference a maintainer must know about: the public member `mvImagePyramid`
+// (reference :85) is only filled on request.  The GPU stereo matcher reads the pyramid on the device, so
+// downloading 1.4 MB per image just to mirror the member would be wasted work.  Callers that read the
+// member on the host (Frame::ComputeObjStereoMatches in the reference) either call SyncImagePyramid()
+// first or construct the extractor with keepHostPyramid = true.
+#ifndef ORBEXTRACTOR_H
+#define ORBEXTRACTOR_H
+
+#include <list>
+#include <vector>
+
+#include "compat/opencv_min.h"
+
+struct pslot_orb;
+
+namespace ORB_SLAM2
+{
+
+class ORBextractor
+{
+public:
+    enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
+    // extension: CUDA device ordinal and whether operator() mirrors the pyramid into mvImagePyramid
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int device,
+                 bool keepHostPyramid);
+    ~ORBextractor();
+    ORBextractor(const ORBextractor &) = delete;
+    ORBextractor &operator=(const ORBextractor &) = delete;
+
+    // Compute the ORB features and descriptors on an image.  ORB are dispersed on the image using an
+    // octree.  Mask is ignored, exactly as in the reference (ORBextractor.h:58).
+    void operator()(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint> &keypoints,
+                    cv::OutputArray descriptors);
+
+    int inline GetLevels() { return nlevels; }
+    float inline GetScaleFactor() { return scaleFactor; }
+    std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }
+    std::vector<float> inline GetInverseScaleFactors() { return mvInvScaleFactor; }
+    std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
+    std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
+
+    std::vector<cv::Mat> mvImagePyramid;
+
+    // Download the pyramid of the last operator() into mvImagePyramid (borderless levels).
+    void SyncImagePyramid();
+    // The C-ABI context behind this object (used by Frame::ComputeStereoMatches).
+    pslot_orb *Handle() const { return mpCtx; }
+
+protected:
+    int nfeatures;
+    double scaleFactor;
+    int nlevels;
+    int iniThFAST;
+    int minThFAST;
+
+    std::vector<int> mnFeaturesPerLevel;
+
+    std::vector<float> mvScaleFactor;
+    std::vector<float> mvInvScaleFactor;
+    std::vector<float> mvLevelSigma2;
+    std::vector<float> mvInvLevelSigma2;
+
+    pslot_orb *mpCtx;
+    bool mbKeepHostPyramid;
+    std::vector<unsigned char> mvDescBuf;
+};
+
+} // namespace ORB_SLAM2
+
+#endif

@@ -1,0 +1,65 @@
+// test_shim.cc — exercises the drop-in classes exactly as Tracking::GrabImageStereo does
+// (reference src/Tracking.cc:385-388, 1045): two ORBextractor objects, one Frame per stereo pair.
+// usage: test_shim <in.bin> <out.bin>
+//   in : int32 W,H,nfeatures,nlevels,iniTh,minTh; float32 scaleFactor,bf,fx; then W*H left bytes, W*H right bytes
+//   out: int32 N, Nr; N keypoints (28 B), N*32 desc, Nr keypoints, Nr*32 desc, N float uRight, N float depth,
+//        int32 pyramid level-1 w,h + bytes (checks SyncImagePyramid), int32 DescriptorDistance(desc0, desc1)
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "Frame.h"
+#include "ORBmatcher.h"
+
+using namespace ORB_SLAM2;
+
+int main(int argc, char **argv)
+{
+    if (argc < 3) return 2;
+    FILE *f = std::fopen(argv[1], "rb");
+    if (!f) return 3;
+    int hdr[6];
+    float fl[3];
+    if (std::fread(hdr, 4, 6, f) != 6 || std::fread(fl, 4, 3, f) != 3) return 4;
+    const int W = hdr[0], H = hdr[1];
+    std::vector<unsigned char> L((size_t)W * H), R((size_t)W * H);
+    if (std::fread(L.data(), 1, L.size(), f) != L.size() || std::fread(R.data(), 1, R.size(), f) != R.size()) return 5;
+    std::fclose(f);
+
+    ORBextractor *left = new ORBextractor(hdr[2], fl[0], hdr[3], hdr[4], hdr[5]);
+    ORBextractor *right = new ORBextractor(hdr[2], fl[0], hdr[3], hdr[4], hdr[5]);
+    cv::Mat imL(H, W, CV_8UC1, L.data()), imR(H, W, CV_8UC1, R.data());
+    cv::Mat K(3, 3, CV_32F);
+    for (int i = 0; i < 9; ++i) K.at<float>(i / 3, i % 3) = 0.f;
+    K.at<float>(0, 0) = fl[2]; K.at<float>(1, 1) = fl[2]; K.at<float>(0, 2) = W / 2.f; K.at<float>(1, 2) = H / 2.f; K.at<float>(2, 2) = 1.f;
+    cv::Mat dist(4, 1, CV_32F);
+    for (int i = 0; i < 4; ++i) dist.at<float>(i) = 0.f;
+    const float bf = fl[1], thDepth = 35.f;
+
+    Frame frame;
+    for (int rep = 0; rep < 2; ++rep) // twice: contexts are reused frame after frame
+        frame = Frame(imL, imR, 0.1 * rep, left, right, nullptr, K, dist, bf, thDepth);
+
+    FILE *o = std::fopen(argv[2], "wb");
+    if (!o) return 6;
+    const int N = frame.N, Nr = (int)frame.mvKeysRight.size();
+    std::fwrite(&N, 4, 1, o); std::fwrite(&Nr, 4, 1, o);
+    std::fwrite(frame.mvKeys.data(), sizeof(cv::KeyPoint), N, o);
+    for (int i = 0; i < N; ++i) std::fwrite(frame.mDescriptors.ptr(i), 1, 32, o);
+    std::fwrite(frame.mvKeysRight.data(), sizeof(cv::KeyPoint), Nr, o);
+    for (int i = 0; i < Nr; ++i) std::fwrite(frame.mDescriptorsRight.ptr(i), 1, 32, o);
+    std::fwrite(frame.mvuRight.data(), 4, N, o);
+    std::fwrite(frame.mvDepth.data(), 4, N, o);
+    left->SyncImagePyramid();
+    const cv::Mat &p1 = left->mvImagePyramid[1];
+    std::fwrite(&p1.cols, 4, 1, o); std::fwrite(&p1.rows, 4, 1, o);
+    for (int r = 0; r < p1.rows; ++r) std::fwrite(p1.ptr(r), 1, p1.cols, o);
+    const int dd = N >= 2 ? ORBmatcher::DescriptorDistance(frame.mDescriptors.row(0), frame.mDescriptors.row(1)) : -1;
+    std::fwrite(&dd, 4, 1, o);
+    std::fclose(o);
+    std::printf("shim ok: N=%d Nr=%d matched=%d mb=%g\n", N, Nr,
+                (int)std::count_if(frame.mvuRight.begin(), frame.mvuRight.end(), [](float v) { return v >= 0; }), frame.mb);
+    delete left; delete right;
+    return 0;
+}
