@@ -237,8 +237,8 @@ def run_ours(args, rank, world, local_rank):
     for c in ctxs:
         c.set_profiling(True)
 
-    stage_sum = np.zeros(len(B.StereoBatch.STAGES), np.float64)
-    stage_n = [0]
+    stage_acc = {False: [np.zeros(len(B.StereoBatch.STAGES), np.float64), 0],
+                 True: [np.zeros(len(B.StereoBatch.STAGES), np.float64), 0]}  # keyed by host-input mode
 
     subs = sub_batches(P, Bsz)
 
@@ -253,7 +253,7 @@ def run_ours(args, rank, world, local_rank):
             if pending[c]:
                 ctx.wait()
                 if collect:
-                    stage_sum[:] += ctx.stage_times_ms(); stage_n[0] += 1
+                    stage_acc[host][0] += ctx.stage_times_ms(); stage_acc[host][1] += 1
             lo, n = sub(i)
             if host:
                 ctx.submit_ptr(hL.data_ptr() + lo * img_bytes, hR.data_ptr() + lo * img_bytes, W, img_bytes, n, True,
@@ -266,7 +266,7 @@ def run_ours(args, rank, world, local_rank):
             if pending[c]:
                 ctxs[c].wait()
                 if collect:
-                    stage_sum[:] += ctxs[c].stage_times_ms(); stage_n[0] += 1
+                    stage_acc[host][0] += ctxs[c].stage_times_ms(); stage_acc[host][1] += 1
 
     def barrier():
         torch.cuda.synchronize()
@@ -303,7 +303,7 @@ def run_ours(args, rank, world, local_rank):
     ms_dev, win1 = timed(host=False, collect=True)
     stats = ctxs[0].stats()  # work counters of one sub-batch (off the timed path)
     stats_pairs = sub(((nsub - 1) // nctx) * nctx)[1] if nctx > 0 else Bsz
-    ms_e2e, win2 = timed(host=True, collect=False)
+    ms_e2e, win2 = timed(host=True, collect=True)
     clocks = sampler.stop([win1, win2]) if rank == 0 else None
 
     # sanity: the e2e outputs of the last sub-batch on ctx 0 are real features
@@ -325,7 +325,8 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    stage_ms = stage_sum / max(stage_n[0], 1)  # average per submit (one sub-batch of Bsz pairs)
+    stage_ms = stage_acc[False][0] / max(stage_acc[False][1], 1)  # average per submit (one sub-batch of Bsz pairs)
+    e2e_stage_ms = stage_acc[True][0] / max(stage_acc[True][1], 1)
     # algorithmic bytes per PAIR of each stage (SURVEY.md §8d / DESIGN.md), from the measured counters
     from pointslot_b200.binding import lib as _lib  # noqa: F401
     sp = max(stats_pairs, 1)
@@ -385,7 +386,8 @@ def run_ours(args, rank, world, local_rank):
                    "keypoints_per_image": n_k, "fast_candidates_per_image": n_c, "sad_refinements_per_pair": N_m,
                    "matches_per_pair": stats["matches"] / sp, "synth_seconds": t_gen},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "stage_ms_per_submit": {n: float(v) for n, v in zip(B.StereoBatch.STAGES, e2e_stage_ms)}},
         "gpu_launches": launches_per_submit * nsub * args.steps * world,
         "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clocks,
     }
