@@ -208,6 +208,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # rank 0's stdout must carry exactly one JSON line (no NCCL version banner)
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -408,7 +409,7 @@ def level_sizes():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1000, help="pairs per step per GPU")

@@ -172,6 +172,11 @@ int pslot_orb_debug_level_keypoints(pslot_orb *ctx, int level, int cap, int32_t 
  * index of the chosen right keypoint (-1 = none), SAD of accepted matches before the median test (-1). */
 int pslot_stereo_debug(pslot_orb *ctx_l, int n_l, int32_t *best_dist, int32_t *best_idx, int32_t *best_sad);
 
+/* The descriptor steering coefficients a = (float)cos(angle*pi/180), b = (float)sin(...) exactly as the
+ * device computes them (ORBextractor.cc:112-113), for n host angles in degrees; lets a test sweep every
+ * float in [0, 360] against libm. */
+int pslot_debug_steer(int device, const float *angle_deg, int n, float *a, float *b);
+
 #ifdef __cplusplus
 }
 #endif

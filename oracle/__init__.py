@@ -74,6 +74,8 @@ def lib():
         L.orc_fast_atan2.restype = C.c_float
         L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
         L.orc_cv_round.argtypes = [C.c_double]
+        L.orc_steer_coeffs.argtypes = [vp, C.c_int, vp, vp]
+        L.orc_steer_coeffs.restype = None
         L.orc_distribute_octtree.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_int, vp, vp, vp, ip]
         _lib = L
@@ -117,6 +119,14 @@ def fast_atan2(y: float, x: float) -> float:
 
 def cv_round(v: float) -> int:
     return int(lib().orc_cv_round(float(v)))
+
+
+def steer_coeffs(angle_deg: np.ndarray):
+    """(a, b) of computeOrbDescriptor for float32 angles in degrees (libm cos/sin in double, rounded to float)."""
+    ang = np.ascontiguousarray(angle_deg, np.float32)
+    a = np.empty_like(ang); b = np.empty_like(ang)
+    lib().orc_steer_coeffs(_ptr(ang), ang.size, _ptr(a), _ptr(b))
+    return a, b
 
 
 def hamming256(a: np.ndarray, b: np.ndarray) -> int:

@@ -653,13 +653,25 @@ static int compute_keypoints_octtree(orc_extractor *e)
     return 0;
 }
 
-/* computeOrbDescriptor (:107-147) */
-static void compute_orb_descriptor(const uint8_t *img, int step, int px, int py, float kp_angle, uint8_t *desc)
+/* steering coefficients (:112-113); rule: cos/sin evaluated in double, rounded to float (DESIGN.md parity rule 3) */
+static inline void steer_coeffs(float kp_angle, float *a, float *b)
 {
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
     float angle = kp_angle * factorPI;
-    /* rule: cos/sin evaluated in double, rounded to float (DESIGN.md parity rule 3) */
-    float a = (float)cos((double)angle), b = (float)sin((double)angle);
+    *a = (float)cos((double)angle);
+    *b = (float)sin((double)angle);
+}
+
+void orc_steer_coeffs(const float *angle_deg, int n, float *a, float *b)
+{
+    for (int i = 0; i < n; ++i) steer_coeffs(angle_deg[i], &a[i], &b[i]);
+}
+
+/* computeOrbDescriptor (:107-147) */
+static void compute_orb_descriptor(const uint8_t *img, int step, int px, int py, float kp_angle, uint8_t *desc)
+{
+    float a, b;
+    steer_coeffs(kp_angle, &a, &b);
     const uint8_t *center = img + (ptrdiff_t)py * step + px;
     const int8_t *pat = k_pattern;
     for (int i = 0; i < 32; ++i, pat += 32) {

@@ -81,6 +81,8 @@ int orc_fast9_16(const uint8_t *img, int w, int h, ptrdiff_t pitch, int threshol
 void orc_gaussian7x7_s2(const uint8_t *src, int w, int h, ptrdiff_t spitch, uint8_t *dst, ptrdiff_t dpitch);
 float orc_fast_atan2(float y, float x);
 int orc_cv_round(double v);
+/* steering coefficients of computeOrbDescriptor (ORBextractor.cc:112-113) for n angles in degrees */
+void orc_steer_coeffs(const float *angle_deg, int n, float *a, float *b);
 /* DistributeOctTree alone (ORBextractor.cc:539-763); in/out arrays of n / cap ints */
 int orc_distribute_octtree(const int *x, const int *y, const int *resp, int n,
                            int minX, int maxX, int minY, int maxY, int N,

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "pslot_batch_create", "pslot_batch_destroy", "pslot_batch_max_keypoints", "pslot_batch_stream",
     "pslot_batch_submit", "pslot_batch_wait", "pslot_batch_kernel_launches", "pslot_batch_device_out",
     "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats",
-    "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug",
+    "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
 ]
 
 
@@ -86,6 +86,7 @@ def lib():
     L.pslot_orb_debug_candidates.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, ip]
     L.pslot_orb_debug_level_keypoints.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, ip]
     L.pslot_stereo_debug.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.pslot_debug_steer.argtypes = [C.c_int, vp, C.c_int, vp, vp]
     _lib = L
     return L
 
@@ -109,6 +110,14 @@ def hamming256(a, b) -> int:
     a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
     assert a.size == 32 and b.size == 32
     return lib().pslot_hamming256(_p(a), _p(b))
+
+
+def debug_steer(angle_deg: np.ndarray, device: int = 0):
+    """(a, b) = ((float)cos, (float)sin) of angle*pi/180 as the descriptor kernel computes them."""
+    ang = np.ascontiguousarray(angle_deg, np.float32)
+    a = np.empty_like(ang); b = np.empty_like(ang)
+    _check(lib().pslot_debug_steer(device, _p(ang), ang.size, _p(a), _p(b)))
+    return a, b
 
 
 def max_disparity(bf: float, fx: float) -> float:

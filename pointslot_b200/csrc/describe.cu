@@ -90,6 +90,23 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
+// a = (float)cos(angle*factorPI), b = (float)sin(...) with the trigonometry in double (parity rule 3)
+__device__ __forceinline__ void steer_coeffs(float angle_deg, float &a, float &b)
+{
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
+    const float ang = __fmul_rn(angle_deg, factorPI);
+    double sd, cd;
+    sincos((double)ang, &sd, &cd);
+    a = (float)cd;
+    b = (float)sd;
+}
+
+__global__ void k_debug_steer(const float *__restrict__ angle_deg, int n, float *__restrict__ a, float *__restrict__ b)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) steer_coeffs(angle_deg[i], a[i], b[i]);
+}
+
 __global__ void __launch_bounds__(DW * 32)
 k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
            const uint32_t *__restrict__ lkp, const int *__restrict__ lkp_count,
@@ -193,11 +210,8 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
     __syncwarp();
 
     // ---- steered BRIEF with the vertical blur pass at the sampled positions (:107-147) ---------------
-    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
-    const float ang = __fmul_rn(angle, factorPI);
-    double sd, cd;
-    sincos((double)ang, &sd, &cd);
-    const float a = (float)cd, b = (float)sd;
+    float a, b;
+    steer_coeffs(angle, a, b);
     const uint16_t *hc = S.hp + BR; // hp[r + 18 - 3 + j][c + 18]: rows r+15 .. r+21 for blurred row r (relative to centre)
     auto sample = [&](float px, float py) -> int {
         const int r = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
@@ -233,6 +247,11 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
 }
 
 } // namespace
+
+void launch_debug_steer(const float *angle_deg, int n, float *a, float *b, cudaStream_t st)
+{
+    k_debug_steer<<<(n + 255) / 256, 256, 0, st>>>(angle_deg, n, a, b);
+}
 
 int launch_describe(const Geom &g, const PyrPtrs &pyr, const uint32_t *lkp, const int *lkp_count,
                     pslot_keypoint *out_kps, uint8_t *out_desc, int *out_count, int nslots, cudaStream_t st)

@@ -268,6 +268,7 @@ struct Engine {
             off += align_up((size_t)pyr.slot_stride[l] * nslots, 256);
         }
         CU(cudaMalloc(&d_pyr, off + 256));
+        CU(cudaMemset(d_pyr, 0, off + 256)); // row padding is read (never used) by 16-byte loads: keep it defined
         for (int l = 0; l < g.nlevels; ++l) pyr.lv[l] = d_pyr + lvoff[l];
         rc = make_tensor_maps(nslots);
         if (rc) return rc;
@@ -618,6 +619,24 @@ int pslot_orb_debug_level_keypoints(pslot_orb *ctx, int level, int cap, int32_t 
         x[i] = pslot_px(kp[i]); y[i] = pslot_py(kp[i]); resp[i] = pslot_pr(kp[i]);
         if (angle) angle[i] = out[i].angle;
     }
+    return PSLOT_OK;
+}
+
+int pslot_debug_steer(int device, const float *angle_deg, int n, float *a, float *b)
+{
+    if (!angle_deg || !a || !b || n < 0) return fail(PSLOT_ERR_ARG, "bad argument");
+    if (n == 0) return PSLOT_OK;
+    CU(cudaSetDevice(device));
+    float *d = nullptr;
+    CU(cudaMalloc(&d, 12 * (size_t)n));
+    cudaError_t e = cudaMemcpy(d, angle_deg, 4 * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        launch_debug_steer(d, n, d + n, d + 2 * (size_t)n, 0);
+        e = cudaMemcpy(a, d + n, 4 * (size_t)n, cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(b, d + 2 * (size_t)n, 4 * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "pslot_debug_steer: %s", cudaGetErrorString(e));
     return PSLOT_OK;
 }
 

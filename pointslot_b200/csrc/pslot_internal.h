@@ -87,3 +87,4 @@ int launch_describe(const Geom &g, const PyrPtrs &pyr, const uint32_t *lkp, cons
 int launch_stereo(const Geom &g, const StereoArgs &a, int npairs, int max_n_r, cudaStream_t st,
                   cudaEvent_t between = nullptr);
 size_t quadtree_smem_bytes(const Geom &g, int *key_cap);
+void launch_debug_steer(const float *angle_deg, int n, float *a, float *b, cudaStream_t st);

@@ -133,3 +133,16 @@ def test_noise_image_many_candidates(B, oracle_mod):
     e = B.OrbExtractor(*params); o = oracle_mod.OracleExtractor(*params)
     k, d = e.extract(img); ok, od = o.extract(img)
     assert k.tobytes() == ok.tobytes() and np.array_equal(d, od)
+
+
+def test_steering_coefficients_vs_libm(B, oracle_mod):
+    """a=(float)cos, b=(float)sin of angle*pi/180 (double trig, rounded): every 509th float in [0,360] + specials.
+    (tools/steer_sweep.py runs all 1.14e9 angles; result recorded in profiles/.)"""
+    hi = int(np.float32(360.0).view(np.uint32)) + 1
+    bits = np.arange(0, hi, 509, dtype=np.uint32)
+    ang = np.concatenate([bits.view(np.float32), np.arange(0, 361, dtype=np.float32),
+                          np.float32([0.5, 44.99999, 45.0, 89.99999, 90.00001, 179.9999, 270.0001, 359.9999])])
+    ga, gb = B.debug_steer(ang)
+    oa, ob = oracle_mod.steer_coeffs(ang)
+    assert np.array_equal(ga.view(np.uint32), oa.view(np.uint32))
+    assert np.array_equal(gb.view(np.uint32), ob.view(np.uint32))
