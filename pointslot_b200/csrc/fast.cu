@@ -27,33 +27,32 @@ namespace {
 
 constexpr int FW = 4;        // warps (= cells) per CTA
 // A TMA box must start on a 16-byte boundary of the global row, so the box starts at the aligned x below
-// (cell start - 1); the residual 0..15 byte offset is uniform per CTA: a whole-word part folded into the
-// shared-memory word index and a 0..3 byte part removed with one funnel shift per word.
+// (cell start - 1); the residual 0..15 byte offset is uniform per warp: a whole-word part folded into the
+// shared-memory word index and a 0..3 byte part S that selects one of four specialisations of the scoring
+// loop, in which every ring byte pair is fetched by ONE PRMT with compile-time selectors.
 
-// window bytes: A = offsets -4..-1, B = 0..3, C = 4..7 relative to the group's first pixel.
-// Returns a 16x2 value whose high bytes are window[O0] (low half) and window[O0 + 1] (high half).
-template <int O0>
-__device__ __forceinline__ uint32_t pick(uint32_t A, uint32_t B, uint32_t C)
+// w[0..3]: four consecutive shared words of one ring row; the group's first pixel is byte 4 + S of them.
+// Returns a 16x2 value whose HIGH bytes are the pixels at offsets O0 and O0 + 1 from the group's first pixel
+// (low bytes repeat them: a 16-bit min/max is decided by the high byte first, so they are harmless).
+template <int S, int O0>
+__device__ __forceinline__ uint32_t pick(const uint32_t (&w)[4])
 {
-    static_assert(O0 >= -4 && O0 + 1 <= 7, "offset out of window");
-    if constexpr (O0 + 1 <= 3) {
-        constexpr int i0 = O0 + 4, i1 = O0 + 5;
-        return __byte_perm(A, B, i0 | (i0 << 4) | (i1 << 8) | (i1 << 12));
-    } else {
-        static_assert(O0 + 1 <= 3 || O0 >= 0, "pair straddles A and C");
-        constexpr int i0 = O0, i1 = O0 + 1;
-        return __byte_perm(B, C, i0 | (i0 << 4) | (i1 << 8) | (i1 << 12));
-    }
+    constexpr int i0 = 4 + S + O0, i1 = i0 + 1; // byte indices into the 16-byte row segment
+    static_assert(i0 >= 0 && i1 <= 15, "offset out of the staged segment");
+    constexpr int wa = i0 >> 2, wb = (wa < 3) ? wa + 1 : 3;
+    constexpr int b0 = i0 - 4 * wa, b1 = i1 - 4 * wa; // 0..3 -> first source, 4..7 -> second source
+    static_assert(b1 <= 4 && (b1 < 4 || wa < 3), "pair leaves the segment");
+    return __byte_perm(w[wa], w[wb], b0 | (b0 << 4) | (b1 << 8) | (b1 << 12));
 }
 
 // ring position k -> (dx, dy) (OpenCV FAST 9-16 pixel order), rows indexed dy + 3
 // k:  0      1      2      3      4      5       6       7       8       9        10       11       12      13      14      15
 //   (0,3)  (1,3)  (2,2)  (3,1)  (3,0)  (3,-1)  (2,-2)  (1,-3)  (0,-3)  (-1,-3)  (-2,-2)  (-3,-1)  (-3,0)  (-3,1)  (-2,2)  (-1,3)
-template <int J>
-__device__ __forceinline__ void ring_pairs(const uint32_t (&w)[7][3], uint32_t (&P)[16])
+template <int S, int J>
+__device__ __forceinline__ void ring_pairs(const uint32_t (&w)[7][4], uint32_t (&P)[16])
 {
     constexpr int o = 2 * J;
-#define PK(k, dx, dy) P[k] = pick<o + (dx)>(w[(dy) + 3][0], w[(dy) + 3][1], w[(dy) + 3][2])
+#define PK(k, dx, dy) P[k] = pick<S, o + (dx)>(w[(dy) + 3])
     PK(0, 0, 3);   PK(1, 1, 3);   PK(2, 2, 2);    PK(3, 3, 1);
     PK(4, 3, 0);   PK(5, 3, -1);  PK(6, 2, -2);   PK(7, 1, -3);
     PK(8, 0, -3);  PK(9, -1, -3); PK(10, -2, -2); PK(11, -3, -1);
@@ -61,7 +60,11 @@ __device__ __forceinline__ void ring_pairs(const uint32_t (&w)[7][3], uint32_t (
 #undef PK
 }
 
-// M1 = min over the 16 arcs of max(9 contiguous), M2 = max over arcs of min(9 contiguous); 16x2 lanes.
+// M1 = min over the 16 arcs of max(9 contiguous ring pixels), M2 = max over arcs of min(...); 16x2 lanes.
+// Every integer ALU instruction issues at one per two cycles per SM sub-partition on B200 (measured with ncu: the
+// kernel is pinned on that pipe), so the 3-input VIMNMX3 - two comparisons per issue slot - is the cheapest
+// form: 16 triples + 16 arcs (max3 of three triples) + 8 to reduce = 40 per side.  (A van Herk prefix/suffix
+// network needs 59 two-input operations and measured no faster.)
 __device__ __forceinline__ void arc_minmax(const uint32_t (&P)[16], uint32_t &M1, uint32_t &M2)
 {
     uint32_t a[16], b[16];
@@ -84,7 +87,46 @@ __device__ __forceinline__ void arc_minmax(const uint32_t (&P)[16], uint32_t &M1
     M2 = m2;
 }
 
-__device__ __forceinline__ int raw_score(int v, int m1, int m2) { return max(v - m1, m2 - v) - 1; }
+// pass 1 for one alignment S: dense exact scores of every 4-pixel group of the cell
+template <int S>
+__device__ __forceinline__ void score_pass(const uint32_t *tile32, uint32_t *score32, int TSW, int wsh, int lane,
+                                           int ntasks, int gshift, int iw)
+{
+    const int G1 = (1 << gshift) - 1;
+    for (int t = lane; t < ntasks; t += 32) {
+        const int y = t >> gshift, gx = t & G1;
+        if (4 * gx >= iw) continue;
+        // 16-byte segment of each ring row that contains bytes -4..7 around the group's first pixel
+        const uint32_t *base = tile32 + (y + 3) * TSW + gx + wsh;
+        uint32_t w[7][4];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            const uint32_t *p = base + (r - 3) * TSW;
+            w[r][0] = p[0]; w[r][1] = p[1]; w[r][2] = p[2]; w[r][3] = p[3];
+        }
+        uint32_t P[16];
+        uint32_t m1a, m2a, m1b, m2b;
+        ring_pairs<S, 0>(w, P);
+        arc_minmax(P, m1a, m2a);
+        ring_pairs<S, 1>(w, P);
+        arc_minmax(P, m1b, m2b);
+        // the 4 centre pixels as clean (zero-extended) 16x2 pairs, and the extrema moved down from the high bytes
+        constexpr int c0 = 4 + S, ca = c0 >> 2, cb = ca + 1; // centre bytes c0..c0+3 of row 3
+        const uint32_t cw = __byte_perm(w[3][ca], w[3][cb], (c0 & 3) | (((c0 & 3) + 1) << 4) | (((c0 & 3) + 2) << 8) | (((c0 & 3) + 3) << 12));
+        const uint32_t v01 = __byte_perm(cw, 0, 0x4140), v23 = __byte_perm(cw, 0, 0x4342);
+        const uint32_t a01 = __byte_perm(m1a, 0, 0x4341), b01 = __byte_perm(m2a, 0, 0x4341);
+        const uint32_t a23 = __byte_perm(m1b, 0, 0x4341), b23 = __byte_perm(m2b, 0, 0x4341);
+        // R = max(v - M1, M2 - v) - 1 clamped at 0; thresholds are applied in pass 2
+        const uint32_t one = 0x00010001u;
+        const uint32_t r01 = __vimax_s16x2_relu(__vsub2(__vsub2(v01, a01), one), __vsub2(__vsub2(b01, v01), one));
+        const uint32_t r23 = __vimax_s16x2_relu(__vsub2(__vsub2(v23, a23), one), __vsub2(__vsub2(b23, v23), one));
+        uint32_t s4 = __byte_perm(r01, r23, 0x6420);
+        const int rem = iw - 4 * gx; // tested pixels left in this row (>= 1)
+        if (rem < 4) s4 &= (1u << (8 * rem)) - 1u;
+        // score map: tested pixel x lives at byte x + 4 of its row
+        score32[(y + 3) * TSW + gx + 1] = s4;
+    }
+}
 
 __global__ void __launch_bounds__(FW * 32)
 k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet maps,
@@ -123,7 +165,7 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
     // ---- stage the cell: one TMA box load (x, y, slot) -> dense shared tile, row stride = box width ----
     const int xa = (iniX - 1) & ~15;          // 16-byte aligned box origin
     const int sh0 = (iniX - 1) - xa;          // image column iniX-1+b lives at shared byte sh0 + b
-    const int wsh = sh0 >> 2, bsh = (sh0 & 3) * 8;
+    const int wsh = sh0 >> 2;
     if (lane == 0) {
         tma::mbar_init(bar, 1);
         tma::fence_barrier_init();
@@ -146,40 +188,16 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
     const uint32_t tmin1 = (uint32_t)(g.min_th - 1) * 0x00010001u, tini1 = (uint32_t)(g.ini_th - 1) * 0x00010001u;
     const uint32_t ge_bias = g.min_th <= 128 ? (uint32_t)(128 - g.min_th) * 0x01010101u : 0x7F7F7F7Fu;
 
-    // ---- pass 1: dense exact scores ---------------------------------------------------------------
-    for (int t = lane; t < ntasks; t += 32) {
-        const int y = t >> gshift, gx = t & (G - 1);
-        if (4 * gx >= iw) continue;
-        // window of the group: bytes -4..7 around its first pixel = shared bytes sh0 + 4*gx + (0..11) of each ring row
-        const uint32_t *base = reinterpret_cast<const uint32_t *>(tile) + (y + 3) * TSW + gx + wsh;
-        uint32_t w[7][3];
-#pragma unroll
-        for (int r = 0; r < 7; ++r) {
-            const uint32_t *p = base + (r - 3) * TSW;
-            const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3];
-            w[r][0] = __funnelshift_r(w0, w1, bsh);
-            w[r][1] = __funnelshift_r(w1, w2, bsh);
-            w[r][2] = __funnelshift_r(w2, w3, bsh);
+    // ---- pass 1: dense exact scores (specialised on the warp-uniform byte alignment of the cell) ----
+    {
+        const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
+        uint32_t *score32 = reinterpret_cast<uint32_t *>(score);
+        switch (sh0 & 3) {
+        case 0: score_pass<0>(tile32, score32, TSW, wsh, lane, ntasks, gshift, iw); break;
+        case 1: score_pass<1>(tile32, score32, TSW, wsh, lane, ntasks, gshift, iw); break;
+        case 2: score_pass<2>(tile32, score32, TSW, wsh, lane, ntasks, gshift, iw); break;
+        default: score_pass<3>(tile32, score32, TSW, wsh, lane, ntasks, gshift, iw); break;
         }
-        uint32_t P[16], m1a, m2a, m1b, m2b;
-        ring_pairs<0>(w, P);
-        arc_minmax(P, m1a, m2a);
-        ring_pairs<1>(w, P);
-        arc_minmax(P, m1b, m2b);
-        const uint32_t c = w[3][1]; // the 4 centre pixels
-        // clean (zero-extended) 16x2 operands: centre pairs, and the extrema moved down from the high bytes
-        const uint32_t v01 = __byte_perm(c, 0, 0x4140), v23 = __byte_perm(c, 0, 0x4342);
-        const uint32_t a01 = __byte_perm(m1a, 0, 0x4341), b01 = __byte_perm(m2a, 0, 0x4341);
-        const uint32_t a23 = __byte_perm(m1b, 0, 0x4341), b23 = __byte_perm(m2b, 0, 0x4341);
-        // R = max(v - M1, M2 - v) - 1 clamped at 0; thresholds are applied in pass 2
-        const uint32_t one = 0x00010001u;
-        const uint32_t r01 = __vimax_s16x2_relu(__vsub2(__vsub2(v01, a01), one), __vsub2(__vsub2(b01, v01), one));
-        const uint32_t r23 = __vimax_s16x2_relu(__vsub2(__vsub2(v23, a23), one), __vsub2(__vsub2(b23, v23), one));
-        uint32_t s4 = __byte_perm(r01, r23, 0x6420);
-        const int rem = iw - 4 * gx; // tested pixels left in this row (>= 1)
-        if (rem < 4) s4 &= (1u << (8 * rem)) - 1u;
-        // score map: tested pixel x lives at byte x + 4 of its row
-        reinterpret_cast<uint32_t *>(score)[(y + 3) * TSW + gx + 1] = s4;
     }
     __syncwarp();
 

@@ -173,9 +173,12 @@ k_quadtree(const __grid_constant__ Geom g, const int *__restrict__ cell_count,
     }
     {
         const uint32_t *src = cell_cand + (size_t)slot * g.cand_per_slot + L.cand_base;
-        for (int c = warp; c < ncells; c += QT / 32) {
+        // one thread per cell: the (few) survivors of a cell sit in one or two sectors, so independent
+        // threads keep hundreds of loads in flight instead of one dependent chain per warp
+        for (int c = tid; c < ncells; c += QT) {
             const int n = cc[c], o = cp[c];
-            for (int k = lane; k < n; k += 32) keys[o + k] = src[(size_t)c * L.cand_stride + k];
+            const uint32_t *p = src + (size_t)c * L.cand_stride;
+            for (int k = 0; k < n; ++k) keys[o + k] = p[k];
         }
     }
 
@@ -409,12 +412,13 @@ size_t smem_for(int cap, int key_cap)
 size_t quadtree_smem_bytes(const Geom &g, int *key_cap)
 {
     const int cap = g.max_level_cap;
-    // keys that fit beside the node tables in ~96 KB (two CTAs per SM); larger levels spill to global
-    const size_t budget = 96 * 1024;
+    // room for 6144 keys beside the node tables (levels with more candidates spill their key arrays to
+    // global scratch), capped so that at least two CTAs fit per SM
+    const size_t budget = 100 * 1024;
     const size_t fixed = smem_for(cap, 0);
-    int kc = fixed + 6 * 1024 < budget ? (int)((budget - fixed) / 6) : 1024;
+    int kc = 6144;
+    if (fixed + 6 * (size_t)kc > budget) kc = fixed + 6 * 1024 < budget ? (int)((budget - fixed) / 6) : 1024;
     kc = kc & ~7;
-    if (kc > 16384) kc = 16384;
     *key_cap = kc;
     return smem_for(cap, kc);
 }
