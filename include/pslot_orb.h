@@ -75,6 +75,13 @@ int pslot_orb_max_keypoints(const pslot_orb *ctx);
 int pslot_orb_extract(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch,
                       pslot_keypoint *kps, uint8_t *desc32, int cap, int *n);
 
+/* Colour ingest: the cvtColor(RGB/BGR(A) -> GRAY) that Tracking::GrabImageStereo applies
+ * before building the Frame (src/Tracking.cc:1014-1039), fused with the upload.  img: interleaved 8-bit,
+ * channels = 3 or 4 (alpha ignored), rgb_order != 0 for RGB(A) (Camera.RGB: 1), 0 for BGR(A).  Arithmetic =
+ * OpenCV 4.13: Y = (R*9798 + G*19235 + B*3735 + 2^14) >> 15.  channels = 1 is pslot_orb_extract. */
+int pslot_orb_extract_color(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, int channels,
+                            int rgb_order, pslot_keypoint *kps, uint8_t *desc32, int cap, int *n);
+
 /* Backing store of the public member std::vector<cv::Mat> mvImagePyramid (ORBextractor.h:85,
  * filled by ComputePyramid, ORBextractor.cc:1107-1132).  Copies level `level` of the most recent
  * extraction to host memory (dst may be NULL to query the size only).  The 19-px replicated frame of
@@ -137,6 +144,10 @@ typedef struct pslot_batch_out {
 int pslot_batch_submit(pslot_batch *b, const uint8_t *left, const uint8_t *right, ptrdiff_t pitch,
                        ptrdiff_t image_stride, int npairs, int host_input, float bf, float max_d,
                        const pslot_batch_out *out);
+/* Same for interleaved colour frames in HOST memory (channels 3 or 4; see pslot_orb_extract_color). */
+int pslot_batch_submit_color(pslot_batch *b, const uint8_t *left, const uint8_t *right, ptrdiff_t pitch,
+                             ptrdiff_t image_stride, int npairs, int channels, int rgb_order, float bf,
+                             float max_d, const pslot_batch_out *out);
 int pslot_batch_wait(pslot_batch *b);
 /* Number of kernels pslot_batch_submit launches per call (for launch accounting). */
 int pslot_batch_kernel_launches(const pslot_batch *b);

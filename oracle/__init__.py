@@ -74,6 +74,8 @@ def lib():
         L.orc_fast_atan2.restype = C.c_float
         L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
         L.orc_cv_round.argtypes = [C.c_double]
+        L.orc_cvt_gray.argtypes = [vp, C.c_int, C.c_int, C.c_ssize_t, C.c_int, C.c_int, vp, C.c_ssize_t]
+        L.orc_cvt_gray.restype = None
         L.orc_steer_coeffs.argtypes = [vp, C.c_int, vp, vp]
         L.orc_steer_coeffs.restype = None
         L.orc_distribute_octtree.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -119,6 +121,15 @@ def fast_atan2(y: float, x: float) -> float:
 
 def cv_round(v: float) -> int:
     return int(lib().orc_cv_round(float(v)))
+
+
+def cvt_gray(img: np.ndarray, rgb: bool) -> np.ndarray:
+    """cv::cvtColor(..., RGB2GRAY / BGR2GRAY / RGBA2GRAY / BGRA2GRAY) of an interleaved uint8 [H,W,3|4] image."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, ch = img.shape
+    out = np.empty((h, w), np.uint8)
+    lib().orc_cvt_gray(_ptr(img), w, h, img.strides[0], ch, 1 if rgb else 0, _ptr(out), out.strides[0])
+    return out
 
 
 def steer_coeffs(angle_deg: np.ndarray):

@@ -55,6 +55,20 @@ float orc_fast_atan2(float y, float x)
     return a;
 }
 
+/* cv::cvtColor(src, dst, CV_RGB2GRAY / CV_BGR2GRAY / CV_RGBA2GRAY / CV_BGRA2GRAY) for CV_8U (Tracking.cc:1014-1039):
+ * OpenCV 4.13 RGB2Gray<uchar>, 15-bit fixed point, BT.601. */
+void orc_cvt_gray(const uint8_t *src, int w, int h, ptrdiff_t spitch, int channels, int rgb_order, uint8_t *dst, ptrdiff_t dpitch)
+{
+    for (int y = 0; y < h; ++y) {
+        const uint8_t *s = src + (ptrdiff_t)y * spitch;
+        uint8_t *d = dst + (ptrdiff_t)y * dpitch;
+        for (int x = 0; x < w; ++x, s += channels) {
+            const unsigned r = rgb_order ? s[0] : s[2], g = s[1], b = rgb_order ? s[2] : s[0];
+            d[x] = (uint8_t)((r * 9798u + g * 19235u + b * 3735u + (1u << 14)) >> 15);
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* cv::resize(..., INTER_LINEAR) for CV_8UC1 (called at ORBextractor.cc:1120)                 */
 /* fixed point: 11-bit coefficients, horizontal pass in int32, vertical pass as in             */

@@ -81,6 +81,8 @@ int orc_fast9_16(const uint8_t *img, int w, int h, ptrdiff_t pitch, int threshol
 void orc_gaussian7x7_s2(const uint8_t *src, int w, int h, ptrdiff_t spitch, uint8_t *dst, ptrdiff_t dpitch);
 float orc_fast_atan2(float y, float x);
 int orc_cv_round(double v);
+/* cv::cvtColor(RGB/BGR(A) -> GRAY) for 8-bit images as OpenCV 4.13 computes it (called at Tracking.cc:1014-1039) */
+void orc_cvt_gray(const uint8_t *src, int w, int h, ptrdiff_t spitch, int channels, int rgb_order, uint8_t *dst, ptrdiff_t dpitch);
 /* steering coefficients of computeOrbDescriptor (ORBextractor.cc:112-113) for n angles in degrees */
 void orc_steer_coeffs(const float *angle_deg, int n, float *a, float *b);
 /* DistributeOctTree alone (ORBextractor.cc:539-763); in/out arrays of n / cap ints */

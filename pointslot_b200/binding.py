@@ -25,9 +25,9 @@ KEYPOINT_DTYPE = np.dtype(
 ABI_SYMBOLS = [
     "pslot_last_error", "pslot_abi_version", "pslot_device_count",
     "pslot_orb_create", "pslot_orb_destroy", "pslot_orb_levels", "pslot_orb_tables", "pslot_orb_max_keypoints",
-    "pslot_orb_extract", "pslot_orb_level", "pslot_stereo_match", "pslot_hamming256",
+    "pslot_orb_extract", "pslot_orb_extract_color", "pslot_orb_level", "pslot_stereo_match", "pslot_hamming256",
     "pslot_batch_create", "pslot_batch_destroy", "pslot_batch_max_keypoints", "pslot_batch_stream",
-    "pslot_batch_submit", "pslot_batch_wait", "pslot_batch_kernel_launches", "pslot_batch_device_out",
+    "pslot_batch_submit", "pslot_batch_submit_color", "pslot_batch_wait", "pslot_batch_kernel_launches", "pslot_batch_device_out",
     "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
 ]
@@ -65,6 +65,7 @@ def lib():
     L.pslot_orb_tables.argtypes = [vp, vp, vp, vp, vp, vp]
     L.pslot_orb_max_keypoints.argtypes = [vp]
     L.pslot_orb_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_ssize_t, vp, vp, C.c_int, ip]
+    L.pslot_orb_extract_color.argtypes = [vp, vp, C.c_int, C.c_int, C.c_ssize_t, C.c_int, C.c_int, vp, vp, C.c_int, ip]
     L.pslot_orb_level.argtypes = [vp, C.c_int, vp, C.c_ssize_t, ip, ip]
     L.pslot_stereo_match.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_float, C.c_float, vp, vp]
     L.pslot_hamming256.argtypes = [vp, vp]
@@ -77,6 +78,8 @@ def lib():
     L.pslot_batch_stream.restype = vp
     L.pslot_batch_submit.argtypes = [vp, vp, vp, C.c_ssize_t, C.c_ssize_t, C.c_int, C.c_int, C.c_float, C.c_float,
                                      C.POINTER(BatchOut)]
+    L.pslot_batch_submit_color.argtypes = [vp, vp, vp, C.c_ssize_t, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_float,
+                                           C.c_float, C.POINTER(BatchOut)]
     L.pslot_batch_wait.argtypes = [vp]
     L.pslot_batch_kernel_launches.argtypes = [vp]
     L.pslot_batch_device_out.argtypes = [vp, C.POINTER(BatchOut)]
@@ -148,17 +151,24 @@ class OrbExtractor:
         _check(lib().pslot_orb_tables(self._h, *[_p(a) for a in out]))
         return dict(zip(("scale", "inv_scale", "sigma2", "inv_sigma2", "features_per_level"), out))
 
-    def extract(self, img: np.ndarray):
-        """-> (keypoints [n] KEYPOINT_DTYPE, descriptors [n,32] uint8)"""
-        assert img.dtype == np.uint8 and img.ndim == 2 and (img.size == 0 or img.strides[1] == 1)
+    def extract(self, img: np.ndarray, rgb: bool = False):
+        """-> (keypoints [n] KEYPOINT_DTYPE, descriptors [n,32] uint8).  img: gray [H,W], or interleaved colour
+        [H,W,3|4] (converted on the device like Tracking::GrabImageStereo's cvtColor; rgb=True for RGB(A) order)."""
+        assert img.dtype == np.uint8 and img.ndim in (2, 3)
+        channels = 1 if img.ndim == 2 else img.shape[2]
+        assert img.size == 0 or img.strides[-1] == 1 and (img.ndim == 2 or img.strides[1] == channels)
         cap = _check(lib().pslot_orb_max_keypoints(self._h))
-        h, w = img.shape
+        h, w = img.shape[:2]
         for _ in range(2):
             kps = np.zeros(cap, KEYPOINT_DTYPE)
             desc = np.zeros((cap, 32), np.uint8)
             n = C.c_int(0)
-            rc = lib().pslot_orb_extract(self._h, _p(img), w, h, img.strides[0] if img.size else 0, _p(kps), _p(desc),
-                                         cap, C.byref(n))
+            if channels == 1:
+                rc = lib().pslot_orb_extract(self._h, _p(img), w, h, img.strides[0] if img.size else 0, _p(kps),
+                                             _p(desc), cap, C.byref(n))
+            else:
+                rc = lib().pslot_orb_extract_color(self._h, _p(img), w, h, img.strides[0], channels, 1 if rgb else 0,
+                                                   _p(kps), _p(desc), cap, C.byref(n))
             if rc == -2:  # PSLOT_ERR_CAPACITY
                 cap = n.value
                 continue
@@ -256,6 +266,17 @@ class StereoBatch:
         _check(lib().pslot_batch_submit(self._h, C.c_void_p(left_ptr), C.c_void_p(right_ptr), pitch, image_stride,
                                         npairs, 1 if host_input else 0, C.c_float(bf), C.c_float(max_d),
                                         C.byref(bo) if bo is not None else None))
+
+    def submit_color(self, left: np.ndarray, right: np.ndarray, rgb: bool, bf: float, max_d: float, out=None):
+        """left/right: uint8 [npairs, H, W, 3|4] interleaved colour host arrays."""
+        assert left.dtype == np.uint8 and left.shape == right.shape and left.ndim == 4 and left.strides == right.strides
+        bo = None
+        if out is not None:
+            bo = BatchOut(*(out[k].ctypes.data for k in ("counts", "kps", "desc", "u_right", "depth")))
+        _check(lib().pslot_batch_submit_color(self._h, C.c_void_p(left.ctypes.data), C.c_void_p(right.ctypes.data),
+                                              left.strides[1], left.strides[0], left.shape[0], left.shape[3],
+                                              1 if rgb else 0, C.c_float(bf), C.c_float(max_d),
+                                              C.byref(bo) if bo is not None else None))
 
     def submit(self, left: np.ndarray, right: np.ndarray, bf: float, max_d: float, out=None):
         """left/right: uint8 [npairs, H, W] host arrays (C-contiguous rows)."""

@@ -348,10 +348,13 @@ struct pslot_orb {
     int last_nl = 0;
     unsigned char *h_stage = nullptr; // pinned mirror of E.d_out
     size_t h_stage_bytes = 0;
+    uint8_t *d_cstage = nullptr;      // tightly packed colour frame awaiting conversion
+    size_t cstage_bytes = 0;
 
     ~pslot_orb()
     {
         free_stereo();
+        cudaFree(d_cstage);
         if (h_stage) cudaFreeHost(h_stage);
     }
     void free_stereo()
@@ -371,11 +374,14 @@ struct pslot_batch {
     bool profiling = false, profiled = false;
     cudaEvent_t ev[PSLOT_NUM_STAGES + 1] = {};
     uint8_t *d_stage = nullptr; // tightly packed landing zone for host images (one linear H2D per view)
+    uint8_t *d_cstage = nullptr; // same for colour frames
+    size_t cstage_bytes = 0;
     ~pslot_batch()
     {
         for (auto &e : ev)
             if (e) cudaEventDestroy(e);
         cudaFree(d_stage);
+        cudaFree(d_cstage);
     }
 };
 
@@ -452,13 +458,14 @@ int pslot_orb_max_keypoints(const pslot_orb *ctx)
     return ctx->E.W ? ctx->E.g.kp_cap_total : max_keypoints(ctx->E);
 }
 
-int pslot_orb_extract(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, pslot_keypoint *kps,
-                      uint8_t *desc32, int cap, int *n)
+static int extract_impl(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, int channels, int rgb,
+                        pslot_keypoint *kps, uint8_t *desc32, int cap, int *n)
 {
     if (!ctx || !n) return fail(PSLOT_ERR_ARG, "ctx / n is null");
     *n = 0;
     if (!img || w <= 0 || h <= 0) return PSLOT_OK; // ORBextractor.cc:1046-1047
-    if (pitch < w) return fail(PSLOT_ERR_ARG, "pitch < width");
+    if (channels != 1 && channels != 3 && channels != 4) return fail(PSLOT_ERR_ARG, "channels must be 1, 3 or 4");
+    if (pitch < (ptrdiff_t)w * channels) return fail(PSLOT_ERR_ARG, "pitch < width * channels");
     Engine &E = ctx->E;
     CU(cudaSetDevice(E.device));
     int rc = E.configure(w, h, 1);
@@ -469,7 +476,21 @@ int pslot_orb_extract(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_
         CU(cudaHostAlloc((void **)&ctx->h_stage, E.out_bytes, cudaHostAllocDefault));
         ctx->h_stage_bytes = E.out_bytes;
     }
-    CU(cudaMemcpy2DAsync(E.pyr.lv[0], E.g.lv[0].pitch, img, pitch, w, h, cudaMemcpyHostToDevice, E.st));
+    if (channels == 1) {
+        CU(cudaMemcpy2DAsync(E.pyr.lv[0], E.g.lv[0].pitch, img, pitch, w, h, cudaMemcpyHostToDevice, E.st));
+    } else { // colour frame: upload once, convert on the device straight into level 0 (Tracking.cc:1014-1039)
+        const size_t need = (size_t)w * h * channels + 16;
+        if (ctx->cstage_bytes < need) {
+            cudaFree(ctx->d_cstage);
+            ctx->d_cstage = nullptr; ctx->cstage_bytes = 0;
+            CU(cudaMalloc(&ctx->d_cstage, need));
+            ctx->cstage_bytes = need;
+        }
+        CU(cudaMemcpy2DAsync(ctx->d_cstage, (size_t)w * channels, img, pitch, (size_t)w * channels, h,
+                             cudaMemcpyHostToDevice, E.st));
+        launch_gray_ingest(ctx->d_cstage, (size_t)w * h * channels, channels, rgb, E.pyr.lv[0], w, h, E.g.lv[0].pitch,
+                           E.pyr.slot_stride[0], 1, E.st);
+    }
     rc = E.run_extract(1);
     if (rc < 0) return rc;
     CU(cudaMemcpyAsync(ctx->h_stage, E.d_out, E.out_bytes, cudaMemcpyDeviceToHost, E.st));
@@ -484,6 +505,18 @@ int pslot_orb_extract(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_
         memcpy(desc32, ctx->h_stage + E.off_desc, 32 * (size_t)count);
     }
     return PSLOT_OK;
+}
+
+int pslot_orb_extract(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, pslot_keypoint *kps,
+                      uint8_t *desc32, int cap, int *n)
+{
+    return extract_impl(ctx, img, w, h, pitch, 1, 0, kps, desc32, cap, n);
+}
+
+int pslot_orb_extract_color(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, int channels,
+                            int rgb_order, pslot_keypoint *kps, uint8_t *desc32, int cap, int *n)
+{
+    return extract_impl(ctx, img, w, h, pitch, channels, rgb_order, kps, desc32, cap, n);
 }
 
 int pslot_orb_level(pslot_orb *ctx, int level, uint8_t *dst, ptrdiff_t pitch, int *w, int *h)
@@ -671,13 +704,16 @@ int pslot_batch_max_keypoints(const pslot_batch *b) { return b ? b->E.g.kp_cap_t
 void *pslot_batch_stream(const pslot_batch *b) { return b ? (void *)b->E.st : nullptr; }
 int pslot_batch_kernel_launches(const pslot_batch *b) { return b ? b->E.p.nlevels - 1 + 3 + 2 : fail(PSLOT_ERR_ARG, "b is null"); }
 
-int pslot_batch_submit(pslot_batch *b, const uint8_t *left, const uint8_t *right, ptrdiff_t pitch, ptrdiff_t image_stride,
-                       int npairs, int host_input, float bf, float max_d, const pslot_batch_out *out)
+static int batch_submit_impl(pslot_batch *b, const uint8_t *left, const uint8_t *right, ptrdiff_t pitch,
+                             ptrdiff_t image_stride, int npairs, int host_input, int channels, int rgb, float bf,
+                             float max_d, const pslot_batch_out *out)
 {
     if (!b || !left || !right) return fail(PSLOT_ERR_ARG, "null argument");
     if (npairs < 1 || npairs > b->max_pairs) return fail(PSLOT_ERR_ARG, "npairs must be in [1,%d]", b->max_pairs);
+    if (channels != 1 && channels != 3 && channels != 4) return fail(PSLOT_ERR_ARG, "channels must be 1, 3 or 4");
     Engine &E = b->E;
-    if (pitch < E.W || image_stride < pitch * E.H) return fail(PSLOT_ERR_ARG, "bad pitch / image stride");
+    if (pitch < (ptrdiff_t)E.W * channels || image_stride < pitch * E.H) return fail(PSLOT_ERR_ARG, "bad pitch / image stride");
+    if (channels != 1 && !host_input) return fail(PSLOT_ERR_ARG, "colour input must be host memory");
     CU(cudaSetDevice(E.device));
     const cudaMemcpyKind kind = host_input ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     const LevelGeom &L0 = E.g.lv[0];
@@ -686,7 +722,27 @@ int pslot_batch_submit(pslot_batch *b, const uint8_t *left, const uint8_t *right
     const uint8_t *views[2] = {left, right};
     for (int v = 0; v < 2; ++v) {
         uint8_t *dst = E.pyr.lv[0] + (size_t)v * npairs * E.pyr.slot_stride[0];
-        if (host_input && pitch == E.W && image_stride == pitch * E.H && pitch != L0.pitch) {
+        if (channels != 1) {
+            // colour frames: tight upload, then one conversion kernel per view writes level 0 directly
+            const size_t per_img = (size_t)E.W * E.H * channels;
+            const size_t view_bytes = align_up(per_img * b->max_pairs + 16, 256); // keeps each view word-aligned
+            const size_t need = 2 * view_bytes;
+            if (b->cstage_bytes < need) {
+                cudaFree(b->d_cstage);
+                b->d_cstage = nullptr; b->cstage_bytes = 0;
+                CU(cudaMalloc(&b->d_cstage, need));
+                b->cstage_bytes = need;
+            }
+            uint8_t *stg = b->d_cstage + (size_t)v * view_bytes;
+            if (pitch == (ptrdiff_t)E.W * channels && image_stride == pitch * E.H) {
+                CU(cudaMemcpyAsync(stg, views[v], per_img * npairs, cudaMemcpyHostToDevice, E.st));
+            } else {
+                for (int i = 0; i < npairs; ++i)
+                    CU(cudaMemcpy2DAsync(stg + (size_t)i * per_img, (size_t)E.W * channels, views[v] + (size_t)i * image_stride,
+                                         pitch, (size_t)E.W * channels, E.H, cudaMemcpyHostToDevice, E.st));
+            }
+            launch_gray_ingest(stg, per_img, channels, rgb, dst, E.W, E.H, L0.pitch, E.pyr.slot_stride[0], npairs, E.st);
+        } else if (host_input && pitch == E.W && image_stride == pitch * E.H && pitch != L0.pitch) {
             // PCIe at full rate: one linear copy, then an on-device 2-D copy into the padded level-0 rows
             const size_t bytes = (size_t)E.W * E.H * npairs;
             if (!b->d_stage) CU(cudaMalloc(&b->d_stage, 2 * (size_t)E.W * E.H * b->max_pairs));
@@ -730,6 +786,19 @@ int pslot_batch_submit(pslot_batch *b, const uint8_t *left, const uint8_t *right
     if (ev) cudaEventRecord(ev[8], E.st);
     b->profiled = ev != nullptr;
     return PSLOT_OK;
+}
+
+int pslot_batch_submit(pslot_batch *b, const uint8_t *left, const uint8_t *right, ptrdiff_t pitch, ptrdiff_t image_stride,
+                       int npairs, int host_input, float bf, float max_d, const pslot_batch_out *out)
+{
+    return batch_submit_impl(b, left, right, pitch, image_stride, npairs, host_input, 1, 0, bf, max_d, out);
+}
+
+int pslot_batch_submit_color(pslot_batch *b, const uint8_t *left, const uint8_t *right, ptrdiff_t pitch,
+                             ptrdiff_t image_stride, int npairs, int channels, int rgb_order, float bf, float max_d,
+                             const pslot_batch_out *out)
+{
+    return batch_submit_impl(b, left, right, pitch, image_stride, npairs, 1, channels, rgb_order, bf, max_d, out);
 }
 
 int pslot_batch_wait(pslot_batch *b)

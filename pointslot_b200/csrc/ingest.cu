@@ -1,0 +1,75 @@
+// ingest.cu — colour -> gray ingest: the cv::cvtColor(RGB/BGR(A) -> GRAY) calls that
+// Tracking::GrabImageStereo makes right before building the Frame (reference src/Tracking.cc:1014-1039),
+// moved onto the device so that colour KITTI frames (Camera.gray: 0) are uploaded once and converted
+// straight into pyramid level 0.
+//
+// Arithmetic = OpenCV 4.13 RGB2Gray<uchar>: Y = (R*9798 + G*19235 + B*3735 + 2^14) >> 15 (BT.601, 15-bit
+// fixed point; OpenCV 3.x used the 14-bit triple 4899/9617/1868, which differs in the last bit for ~0.25 %
+// of colours — the oracle pins the 4.13 behaviour exhaustively over all 2^24 colours against cv2).
+//
+// Mapping: one thread per 4 output pixels; the 12 / 16 source bytes are fetched as aligned 32-bit words of
+// the tightly packed staging image and re-aligned with funnel shifts.  Bound: HBM stream;
+// algorithmic bytes = S * (channels + 1) * P_0.
+#include "pslot_internal.h"
+
+namespace {
+
+__device__ __forceinline__ uint32_t gray_of(uint32_t c0, uint32_t c1, uint32_t c2, bool rgb)
+{
+    const uint32_t r = rgb ? c0 : c2, b = rgb ? c2 : c0;
+    return (r * 9798u + c1 * 19235u + b * 3735u + (1u << 14)) >> 15;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256)
+k_gray_ingest(const uint8_t *__restrict__ src, size_t src_image_stride, uint8_t *__restrict__ dst, int w, int h,
+              int dpitch, unsigned long long dstride, int rgb)
+{
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x; // group of 4 pixels
+    const int y = blockIdx.y;
+    const int x0 = gx * 4;
+    if (x0 >= w) return;
+    // tight layout: row pitch = w * CH, images back to back; `src` itself is 256-byte aligned (cudaMalloc),
+    // an image start need not be 4-byte aligned, so the word alignment is taken on the offset from `src`
+    const size_t off = (size_t)blockIdx.z * src_image_stride + ((size_t)y * w + x0) * CH;
+    const size_t a = off & ~(size_t)3;
+    const int sh = (int)(off - a) * 8;
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(src + a);
+    // words covering the 4 pixels; the staging buffer is padded by 16 bytes so the tail read is in bounds
+    uint32_t v[CH + 1];
+#pragma unroll
+    for (int i = 0; i <= CH; ++i) v[i] = __ldg(p + i);
+    uint32_t q[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) q[i] = __funnelshift_r(v[i], v[i + 1], sh);
+    uint32_t g[4];
+    if (CH == 3) { // bytes: p0 = q0[0..2], p1 = q0[3] q1[0..1], p2 = q1[2..3] q2[0], p3 = q2[1..3]
+        g[0] = gray_of(q[0] & 0xFF, (q[0] >> 8) & 0xFF, (q[0] >> 16) & 0xFF, rgb);
+        g[1] = gray_of(q[0] >> 24, q[1] & 0xFF, (q[1] >> 8) & 0xFF, rgb);
+        g[2] = gray_of((q[1] >> 16) & 0xFF, q[1] >> 24, q[2] & 0xFF, rgb);
+        g[3] = gray_of((q[2] >> 8) & 0xFF, (q[2] >> 16) & 0xFF, q[2] >> 24, rgb);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g[i] = gray_of(q[i] & 0xFF, (q[i] >> 8) & 0xFF, (q[i] >> 16) & 0xFF, rgb);
+    }
+    uint8_t *o = dst + (size_t)blockIdx.z * dstride + (size_t)y * dpitch + x0;
+    if (x0 + 3 < w) {
+        *reinterpret_cast<uint32_t *>(o) = g[0] | (g[1] << 8) | (g[2] << 16) | (g[3] << 24); // dpitch % 128 == 0
+    } else {
+        for (int i = 0; x0 + i < w; ++i) o[i] = (uint8_t)g[i];
+    }
+}
+
+} // namespace
+
+int launch_gray_ingest(const uint8_t *src, size_t src_image_stride, int channels, int rgb, uint8_t *dst, int w, int h,
+                       int dpitch, unsigned long long dstride, int nimages, cudaStream_t st)
+{
+    dim3 block(256);
+    dim3 grid(((w + 3) / 4 + 255) / 256, h, nimages);
+    if (channels == 3)
+        k_gray_ingest<3><<<grid, block, 0, st>>>(src, src_image_stride, dst, w, h, dpitch, dstride, rgb);
+    else
+        k_gray_ingest<4><<<grid, block, 0, st>>>(src, src_image_stride, dst, w, h, dpitch, dstride, rgb);
+    return 1;
+}

@@ -87,4 +87,6 @@ int launch_describe(const Geom &g, const PyrPtrs &pyr, const uint32_t *lkp, cons
 int launch_stereo(const Geom &g, const StereoArgs &a, int npairs, int max_n_r, cudaStream_t st,
                   cudaEvent_t between = nullptr);
 size_t quadtree_smem_bytes(const Geom &g, int *key_cap);
+int launch_gray_ingest(const uint8_t *src, size_t src_image_stride, int channels, int rgb, uint8_t *dst, int w, int h,
+                       int dpitch, unsigned long long dstride, int nimages, cudaStream_t st);
 void launch_debug_steer(const float *angle_deg, int n, float *a, float *b, cudaStream_t st);

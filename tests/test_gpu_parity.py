@@ -146,3 +146,48 @@ def test_steering_coefficients_vs_libm(B, oracle_mod):
     oa, ob = oracle_mod.steer_coeffs(ang)
     assert np.array_equal(ga.view(np.uint32), oa.view(np.uint32))
     assert np.array_equal(gb.view(np.uint32), ob.view(np.uint32))
+
+
+@pytest.mark.parametrize("channels,rgb", [(3, True), (3, False), (4, True), (4, False)])
+def test_color_ingest(channels, rgb, B, oracle_mod):
+    """cvtColor fused with the upload == oracle cvtColor followed by the gray path."""
+    rng = np.random.default_rng(channels * 2 + rgb)
+    from pointslot_b200.synth import synth_pair
+    W, H = 641, 361  # odd width: the last 4-pixel group is partial, image starts are not word aligned
+    base, _ = synth_pair(W, H, 31)
+    col = np.stack([np.clip(base.astype(np.int32) + rng.integers(-30, 31, base.shape), 0, 255).astype(np.uint8)
+                    for _ in range(channels)], axis=2)
+    gray = oracle_mod.cvt_gray(col, rgb)
+    params = (700, 1.2, 8, 20, 7)
+    e = B.OrbExtractor(*params)
+    k, d = e.extract(col, rgb=rgb)
+    assert np.array_equal(e.level(0), gray)
+    o = oracle_mod.OracleExtractor(*params)
+    ok, od = o.extract(gray)
+    assert k.tobytes() == ok.tobytes() and np.array_equal(d, od)
+    # batch path
+    sb = B.StereoBatch(params, W, H, 2)
+    out = sb.alloc_out(2)
+    cols = np.ascontiguousarray(np.stack([col, col[:, ::-1].copy()]))
+    sb.submit_color(cols, cols, rgb, 100.0, 300.0, out); sb.wait()
+    n0 = int(out["counts"][0])
+    assert out["kps"][0, :n0].tobytes() == ok.tobytes() and np.array_equal(out["desc"][0, :n0], od)
+    ok1, od1 = o.extract(oracle_mod.cvt_gray(cols[1], rgb))
+    n1 = int(out["counts"][1])
+    assert out["kps"][1, :n1].tobytes() == ok1.tobytes() and np.array_equal(out["desc"][1, :n1], od1)
+
+
+def test_object_subset_stereo(B, oracle_mod):
+    """SURVEY 8f-1: Frame::ComputeObjStereoMatches (Frame.cc:2318-2503) is ComputeStereoMatches on a keypoint
+    subset reading the same pyramids -> pslot_stereo_match with explicit feature sets covers it."""
+    g = load_golden("kitti_natural_2000")
+    eL, eR = B.OrbExtractor(*g["params_t"]), B.OrbExtractor(*g["params_t"])
+    oL, oR = oracle_mod.OracleExtractor(*g["params_t"]), oracle_mod.OracleExtractor(*g["params_t"])
+    kL, dL = eL.extract(g["left"]); kR, dR = eR.extract(g["right"])
+    oL.extract(g["left"]); oR.extract(g["right"])
+    rng = np.random.default_rng(4)
+    selL = np.sort(rng.choice(len(kL), 300, replace=False)); selR = np.sort(rng.choice(len(kR), 700, replace=False))
+    ur, dp = B.stereo_match(eL, eR, kL[selL], dL[selL], kR[selR], dR[selR], float(g["bf"]), float(g["maxD"]))
+    our, odp = oracle_mod.stereo_match(oL, oR, kL[selL], dL[selL], kR[selR], dR[selR], float(g["bf"]), float(g["maxD"]))
+    _assert_stereo(ur, dp, our, odp)
+    assert (ur >= 0).sum() > 20

@@ -78,3 +78,14 @@ def test_c_oracle_equals_cv2_path(oracle_mod):
         ur2, dp2 = stereo_match_cv2(cL, cR, kL2, dL2, kR2, dR2, 40.0, maxD)
         assert ur.tobytes() == ur2.tobytes() and dp.tobytes() == dp2.tobytes()
         assert (ur >= 0).sum() > 10
+
+
+def test_cvt_gray_exhaustive(oracle_mod):
+    """All 2^24 colours, both channel orders and the alpha variants, vs cv2.cvtColor (OpenCV 4.13 arithmetic)."""
+    v = np.arange(1 << 24, dtype=np.uint32)
+    img = np.stack([(v & 0xFF), (v >> 8) & 0xFF, (v >> 16) & 0xFF], axis=1).astype(np.uint8).reshape(4096, 4096, 3)
+    assert np.array_equal(oracle_mod.cvt_gray(img, True), cv2.cvtColor(img, cv2.COLOR_RGB2GRAY))
+    assert np.array_equal(oracle_mod.cvt_gray(img, False), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    img4 = np.concatenate([img[:512], np.full((512, 4096, 1), 200, np.uint8)], axis=2)
+    assert np.array_equal(oracle_mod.cvt_gray(img4, True), cv2.cvtColor(img4, cv2.COLOR_RGBA2GRAY))
+    assert np.array_equal(oracle_mod.cvt_gray(img4, False), cv2.cvtColor(img4, cv2.COLOR_BGRA2GRAY))
