@@ -154,7 +154,7 @@ def run_reference(args, rank):
     from pointslot_b200.synth import synth_batch_parallel
 
     cores = host_cores()
-    sample = max(2 * cores, 16)
+    sample = max(8 * cores, 64)  # ~0.3 s of work per step on all cores
     Ls, Rs = synth_batch_parallel(W, H, range(sample))
     import oracle as O
     O.build()
