@@ -120,6 +120,11 @@ int pslot_batch_create(pslot_batch **b, int nfeatures, float scale_factor, int n
                        int ini_th_fast, int min_th_fast, int width, int height, int max_pairs,
                        int device, void *stream);
 void pslot_batch_destroy(pslot_batch *b);
+/* Route the host->device uploads of this context through `stream` (a cudaStream_t shared by all the batch
+ * contexts of a GPU; NULL restores per-context uploads).  Concurrent uploads from several streams interleave on
+ * the DMA engine and lose ~35 % of the PCIe rate; one upload stream keeps every transfer at full rate while the
+ * contexts' own streams overlap the kernels.  Ordering is enforced with events inside pslot_batch_submit. */
+int pslot_batch_set_copy_stream(pslot_batch *b, void *stream);
 int pslot_batch_max_keypoints(const pslot_batch *b); /* per-image capacity K of the output arrays */
 void *pslot_batch_stream(const pslot_batch *b);      /* the cudaStream_t all work is enqueued on */
 

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "pslot_last_error", "pslot_abi_version", "pslot_device_count",
     "pslot_orb_create", "pslot_orb_destroy", "pslot_orb_levels", "pslot_orb_tables", "pslot_orb_max_keypoints",
     "pslot_orb_extract", "pslot_orb_extract_color", "pslot_orb_level", "pslot_stereo_match", "pslot_hamming256",
-    "pslot_batch_create", "pslot_batch_destroy", "pslot_batch_max_keypoints", "pslot_batch_stream",
+    "pslot_batch_create", "pslot_batch_destroy", "pslot_batch_set_copy_stream", "pslot_batch_max_keypoints", "pslot_batch_stream",
     "pslot_batch_submit", "pslot_batch_submit_color", "pslot_batch_wait", "pslot_batch_kernel_launches", "pslot_batch_device_out",
     "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
@@ -73,6 +73,7 @@ def lib():
                                      C.c_int, C.c_int, vp]
     L.pslot_batch_destroy.argtypes = [vp]
     L.pslot_batch_destroy.restype = None
+    L.pslot_batch_set_copy_stream.argtypes = [vp, vp]
     L.pslot_batch_max_keypoints.argtypes = [vp]
     L.pslot_batch_stream.argtypes = [vp]
     L.pslot_batch_stream.restype = vp
@@ -227,7 +228,6 @@ class StereoBatch:
         self._h = h
         self.W, self.H, self.max_pairs = width, height, max_pairs
         self.K = _check(lib().pslot_batch_max_keypoints(h))
-        self.kernel_launches = _check(lib().pslot_batch_kernel_launches(h))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -237,8 +237,17 @@ class StereoBatch:
     __del__ = close
 
     @property
+    def kernel_launches(self) -> int:
+        """Kernels launched by the most recent submit (before any submit: the count of the gray host path)."""
+        return _check(lib().pslot_batch_kernel_launches(self._h))
+
+    @property
     def stream(self) -> int:
         return lib().pslot_batch_stream(self._h) or 0
+
+    def set_copy_stream(self, stream: int):
+        """Share one upload stream between the batch contexts of a GPU (full-rate PCIe transfers)."""
+        _check(lib().pslot_batch_set_copy_stream(self._h, C.c_void_p(stream) if stream else None))
 
     def alloc_out(self, npairs: int, pinned: bool = False):
         """Host output arrays in the layout pslot_batch_out documents."""

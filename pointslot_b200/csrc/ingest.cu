@@ -20,10 +20,20 @@ __device__ __forceinline__ uint32_t gray_of(uint32_t c0, uint32_t c1, uint32_t c
     return (r * 9798u + c1 * 19235u + b * 3735u + (1u << 14)) >> 15;
 }
 
+// aligned 32-bit load that never touches a byte at or beyond `limit` (the end of the caller's buffer)
+__device__ __forceinline__ uint32_t load_word_safe(const uint8_t *src, size_t a, size_t limit)
+{
+    if (a + 4 <= limit) return __ldg(reinterpret_cast<const uint32_t *>(src + a));
+    uint32_t v = 0;
+    for (int i = 0; i < 4; ++i)
+        if (a + i < limit) v |= (uint32_t)__ldg(src + a + i) << (8 * i);
+    return v;
+}
+
 template <int CH>
 __global__ void __launch_bounds__(256)
-k_gray_ingest(const uint8_t *__restrict__ src, size_t src_image_stride, uint8_t *__restrict__ dst, int w, int h,
-              int dpitch, unsigned long long dstride, int rgb)
+k_gray_ingest(const uint8_t *__restrict__ src, size_t src_image_stride, size_t limit, uint8_t *__restrict__ dst, int w,
+              int h, int dpitch, unsigned long long dstride, int rgb)
 {
     const int gx = blockIdx.x * blockDim.x + threadIdx.x; // group of 4 pixels
     const int y = blockIdx.y;
@@ -34,11 +44,10 @@ k_gray_ingest(const uint8_t *__restrict__ src, size_t src_image_stride, uint8_t 
     const size_t off = (size_t)blockIdx.z * src_image_stride + ((size_t)y * w + x0) * CH;
     const size_t a = off & ~(size_t)3;
     const int sh = (int)(off - a) * 8;
-    const uint32_t *p = reinterpret_cast<const uint32_t *>(src + a);
-    // words covering the 4 pixels; the staging buffer is padded by 16 bytes so the tail read is in bounds
+    // words covering the 4 pixels (the word after the last needed byte is only touched if it exists)
     uint32_t v[CH + 1];
 #pragma unroll
-    for (int i = 0; i <= CH; ++i) v[i] = __ldg(p + i);
+    for (int i = 0; i <= CH; ++i) v[i] = load_word_safe(src, a + 4 * i, limit);
     uint32_t q[CH];
 #pragma unroll
     for (int i = 0; i < CH; ++i) q[i] = __funnelshift_r(v[i], v[i + 1], sh);
@@ -48,9 +57,12 @@ k_gray_ingest(const uint8_t *__restrict__ src, size_t src_image_stride, uint8_t 
         g[1] = gray_of(q[0] >> 24, q[1] & 0xFF, (q[1] >> 8) & 0xFF, rgb);
         g[2] = gray_of((q[1] >> 16) & 0xFF, q[1] >> 24, q[2] & 0xFF, rgb);
         g[3] = gray_of((q[2] >> 8) & 0xFF, (q[2] >> 16) & 0xFF, q[2] >> 24, rgb);
-    } else {
+    } else if (CH == 4) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) g[i] = gray_of(q[i] & 0xFF, (q[i] >> 8) & 0xFF, (q[i] >> 16) & 0xFF, rgb);
+    } else { // CH == 1: gray input, plain re-pitch of tightly packed rows into the padded level-0 rows
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g[i] = (q[0] >> (8 * i)) & 0xFF;
     }
     uint8_t *o = dst + (size_t)blockIdx.z * dstride + (size_t)y * dpitch + x0;
     if (x0 + 3 < w) {
@@ -67,9 +79,12 @@ int launch_gray_ingest(const uint8_t *src, size_t src_image_stride, int channels
 {
     dim3 block(256);
     dim3 grid(((w + 3) / 4 + 255) / 256, h, nimages);
-    if (channels == 3)
-        k_gray_ingest<3><<<grid, block, 0, st>>>(src, src_image_stride, dst, w, h, dpitch, dstride, rgb);
+    const size_t limit = (size_t)(nimages - 1) * src_image_stride + (size_t)w * h * channels; // end of the last image
+    if (channels == 1)
+        k_gray_ingest<1><<<grid, block, 0, st>>>(src, src_image_stride, limit, dst, w, h, dpitch, dstride, rgb);
+    else if (channels == 3)
+        k_gray_ingest<3><<<grid, block, 0, st>>>(src, src_image_stride, limit, dst, w, h, dpitch, dstride, rgb);
     else
-        k_gray_ingest<4><<<grid, block, 0, st>>>(src, src_image_stride, dst, w, h, dpitch, dstride, rgb);
+        k_gray_ingest<4><<<grid, block, 0, st>>>(src, src_image_stride, limit, dst, w, h, dpitch, dstride, rgb);
     return 1;
 }
