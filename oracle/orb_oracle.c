@@ -651,6 +651,12 @@ static int compute_keypoints_octtree(orc_extractor *e)
             L->kresp = realloc(L->kresp, sizeof(int) * (size_t)capk);
             L->kangle = realloc(L->kangle, sizeof(float) * (size_t)capk);
         }
+        /* :543 nIni = round(width / height): 0 for portrait levels narrower than half their height, where the
+           reference divides by zero and indexes an empty vector -> rejected like the too-small case above */
+        if ((int)roundf((float)(maxBorderX - minBorderX) / (float)(maxBorderY - minBorderY)) < 1) {
+            free(score); free(fx); free(fy); free(fr);
+            return -2;
+        }
         L->nkp = orc_distribute_octtree(L->cx, L->cy, L->cresp, L->ncand, minBorderX, maxBorderX,
                                         minBorderY, maxBorderY, e->per_level[level],
                                         L->capkp, L->kx, L->ky, L->kresp, &L->tie_sensitive);

@@ -205,16 +205,34 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
     uint32_t *out = cell_cand + (size_t)slot * g.cand_per_slot + L.cand_base + (size_t)cell * L.cand_stride;
     uint32_t *min_list = reinterpret_cast<uint32_t *>(tile); // the raw tile is dead after pass 1
     const int ox = iniX + 3 - PSLOT_MINB, oy = iniY + 3 - PSLOT_MINB; // window-relative (:820-825)
-    uint32_t totals = 0; // iniTh count | minTh count << 16
+    // pass 2a: list (raster order) the groups that hold at least one score >= minTh; typically a quarter of
+    // them, so the neighbourhood test below runs on dense warps instead of dragging idle lanes along
+    uint16_t *glist = reinterpret_cast<uint16_t *>(tile + 4 * L.cand_stride); // behind min_list, inside the dead tile
+    int nlist = 0;
     for (int base = 0; base < ntasks; base += 32) {
         const int t = base + lane;
+        bool hit = false;
+        if (t < ntasks) {
+            const uint32_t s4 = reinterpret_cast<const uint32_t *>(score)[((t >> gshift) + 3) * TSW + (t & (G - 1)) + 1];
+            hit = (((s4 + ge_bias) | s4) & 0x80808080u) != 0; // SWAR "some byte >= minTh" (false positives are harmless)
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) glist[nlist + __popc(m & ((1u << lane) - 1u))] = (uint16_t)t;
+        nlist += __popc(m);
+    }
+    __syncwarp();
+
+    // pass 2b: strict 3x3 maxima of the listed groups + compaction
+    uint32_t totals = 0; // iniTh count | minTh count << 16
+    for (int base = 0; base < nlist; base += 32) {
+        const int j = base + lane;
+        const int t = j < nlist ? (int)glist[j] : 0;
         const int y = t >> gshift, gx = t & (G - 1);
         uint32_t f_ini = 0, f_min = 0, s4 = 0;
-        if (t < ntasks) {
+        if (j < nlist) {
             const uint32_t *sw = reinterpret_cast<const uint32_t *>(score) + (y + 3) * TSW + gx + 1;
             s4 = sw[0];
-            // any byte >= minTh?  (SWAR "hasmore"; a false positive only costs the test below)
-            if (((s4 + ge_bias) | s4) & 0x80808080u) {
+            {
                 // At threshold t the neighbour map is (R >= t ? R : 0) and the pixel needs R >= t, so
                 // "strictly above all 8 neighbours at threshold t" == (R >= t) && (R > max of the 8 raw R).
                 const uint32_t uL = sw[-TSW - 1], uM = sw[-TSW], uR = sw[-TSW + 1];

@@ -51,7 +51,16 @@ def test_extract_matches_oracle(kind, h, w, seed, nfeatures, nlevels, scale, ini
     img = _image(kind, h, w, seed)
     e = B.OrbExtractor(*params)
     o = O.OracleExtractor(*params)
-    k, d = e.extract(img)
+    try:
+        k, d = e.extract(img)
+    except B.PslotError as err:
+        # shapes the reference itself cannot process (a level with < 1 cell per axis, or a portrait level whose
+        # width/height rounds to 0 quadtree roots: division by zero in ORBextractor.cc:543-545, 784-787)
+        assert err.code == -4
+        with pytest.raises(RuntimeError):
+            o.extract(img)
+        e.close()
+        return
     ok, od = o.extract(img)
     assert k.tobytes() == ok.tobytes(), (kind, h, w, seed, params, len(k), len(ok))
     assert np.array_equal(d, od)
