@@ -32,7 +32,7 @@ constexpr int RS = RW * 4;
 constexpr int NW = 12;          // aligned words fetched per patch row (covers 43 bytes at any alignment)
 constexpr int BR = 18;          // blurred support radius
 constexpr int BD = 2 * BR + 1;  // 37
-constexpr int HS = 38;          // h-pass row stride (u16): 19 words, odd
+constexpr int CS = 44;          // h-pass column stride (u16): the h-pass is stored column-major, [blurred column][patch row]
 
 // pattern, re-laid out at compile time as [t][lane] words (test 8*lane + t; bytes x0,y0,x1,y1) so that a
 // warp reads one coalesced 128-byte line per test index
@@ -57,7 +57,7 @@ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9
 
 struct WarpSmem {
     uint32_t raw[PD * RW];  // patch bytes, row stride 52; column c of the patch is byte c + shift
-    uint16_t hp[PD * HS];   // horizontal pass, [patch row][blurred column]
+    uint32_t hp[BD * CS / 2]; // horizontal pass as u16 [blurred column][patch row]: the 7 vertical taps of a sample are contiguous
 };
 
 __device__ __forceinline__ int reflect101(int i, int n)
@@ -196,15 +196,15 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
     if (lane < 22) {
         const int ra = lane, rb = min(lane + 22, PD - 1);
         const uint8_t *pa = rawb + ra * RS + shift, *pb = rawb + rb * RS + shift;
-        uint16_t *ha = S.hp + ra * HS, *hb = S.hp + rb * HS;
+        uint16_t *ha = reinterpret_cast<uint16_t *>(S.hp) + ra, *hb = reinterpret_cast<uint16_t *>(S.hp) + rb;
         uint32_t q[PD];
 #pragma unroll
         for (int c = 0; c < PD; ++c) q[c] = (uint32_t)pa[c] | ((uint32_t)pb[c] << 16);
 #pragma unroll
         for (int c = 0; c < BD; ++c) {
             const uint32_t h = 18u * (q[c] + q[c + 6]) + 34u * (q[c + 1] + q[c + 5]) + 48u * (q[c + 2] + q[c + 4]) + 56u * q[c + 3];
-            ha[c] = (uint16_t)(h & 0xFFFFu);
-            hb[c] = (uint16_t)(h >> 16);
+            ha[c * CS] = (uint16_t)(h & 0xFFFFu); // lanes write consecutive rows of one column: conflict-free
+            hb[c * CS] = (uint16_t)(h >> 16);
         }
     }
     __syncwarp();
@@ -212,13 +212,18 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
     // ---- steered BRIEF with the vertical blur pass at the sampled positions (:107-147) ---------------
     float a, b;
     steer_coeffs(angle, a, b);
-    const uint16_t *hc = S.hp + BR; // hp[r + 18 - 3 + j][c + 18]: rows r+15 .. r+21 for blurred row r (relative to centre)
     auto sample = [&](float px, float py) -> int {
         const int r = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
         const int c = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-        const uint16_t *p = hc + (r + BR) * HS + c; // top tap: patch row (r + 21) - 3
-        const int v = 18 * ((int)p[0] + (int)p[6 * HS]) + 34 * ((int)p[HS] + (int)p[5 * HS]) +
-                      48 * ((int)p[2 * HS] + (int)p[4 * HS]) + 56 * (int)p[3 * HS];
+        // taps = patch rows (r + 18) .. (r + 24) of blurred column c + 18: 7 contiguous u16, fetched as 4 words
+        const int base = (c + BR) * CS + (r + BR);
+        const uint32_t *w = S.hp + (base >> 1);
+        const int sh = (base & 1) * 16;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+        const uint32_t t01 = __funnelshift_r(w0, w1, sh), t23 = __funnelshift_r(w1, w2, sh);
+        const uint32_t t45 = __funnelshift_r(w2, w3, sh), t6x = __funnelshift_r(w3, w3, sh);
+        const int v = 18 * (int)((t01 & 0xFFFFu) + (t6x & 0xFFFFu)) + 34 * (int)((t01 >> 16) + (t45 >> 16)) +
+                      48 * (int)((t23 & 0xFFFFu) + (t45 & 0xFFFFu)) + 56 * (int)(t23 >> 16);
         return (v + 32768) >> 16;
     };
     int val = 0;

@@ -45,11 +45,14 @@ k_resize_level(const uint8_t *__restrict__ src, int spitch, unsigned long long s
     const int ya = (int)yt[dy0].s0, yb = (int)yt[dy1].s1;
     const int nvec = (xb - xa) / 16 + 1, nrow = yb - ya + 1;
     if (nvec * 16 > SRC_W || nrow > SRC_H) return; // unsupported ratio (scaleFactor is capped on the host)
-    for (int i = tid; i < nvec * nrow; i += TW * TY) {
-        const int r = i / nvec, v = i - r * nvec;
-        // rows are padded to a multiple of 128 bytes, so a 16-byte read never leaves the row
-        *reinterpret_cast<uint4 *>(s_src + r * SRC_W + v * 16) =
-            __ldg(reinterpret_cast<const uint4 *>(s + (size_t)(ya + r) * spitch + xa) + v);
+    {
+        // 16 threads per staged row (nvec <= 13); rows are padded to a multiple of 128 bytes, so a 16-byte read
+        // never leaves the row
+        const int v = tid & 15;
+        if (v < nvec)
+            for (int r = tid >> 4; r < nrow; r += (TW * TY) >> 4)
+                *reinterpret_cast<uint4 *>(s_src + r * SRC_W + v * 16) =
+                    __ldg(reinterpret_cast<const uint4 *>(s + (size_t)(ya + r) * spitch + xa) + v);
     }
     if (tid < TH) {
         const ResizeTap t = yt[min(dy0 + tid, dy1)];
