@@ -1,7 +1,8 @@
 // fast.cu — K2: the per-cell FAST loop of ComputeKeyPointsOctTree (reference src/ORBextractor.cc:765-829).
 //
-// One WARP per 30-px cell (4 cells per CTA, no block-level barrier anywhere).  The reference calls cv::FAST(cell, iniThFAST, nms=true) and, if that
-// returns nothing, cv::FAST(cell, minThFAST, true) (:809-816).  Restated:
+// One WARP per 30-px cell (4 cells per CTA, no block-level barrier anywhere).  The reference calls
+// cv::FAST(cell, iniThFAST, nms=true) and, if that returns nothing, cv::FAST(cell, minThFAST, true) (:809-816).
+// Restated:
 //   raw score R(p) = max over the 16 arcs of 9 ring pixels of min(v - p_k) resp. min(p_k - v), minus 1
 //                    (OpenCV cornerScore<16>); p is a corner at threshold t  <=>  R >= t;
 //   score map S_t = R where R >= t else 0, on the pixels >= 3 px inside the cell sub-image;
@@ -9,17 +10,22 @@
 //   the cell yields the iniTh survivors if there is at least one, else the minTh survivors;
 //   order: raster inside the cell.
 //
-// Scoring is dense and branch-free.  With M1 = min_k max(p_k..p_k+8) and M2 = max_k min(p_k..p_k+8)
-// over the raw ring pixels, R = max(v - M1, M2 - v) - 1.  Each thread scores 4 adjacent pixels as two
-// 16x2-packed pairs: the ring bytes are gathered from 21 aligned shared-memory words with PRMT into
-// the HIGH byte of each 16-bit half (the low byte is don't-care: it cannot change which high byte wins
-// a min/max), and the 9-wide sliding min/max runs on the native 3-input VIMNMX3.U16x2 (80 per pair).
-// The survivors of both thresholds are compacted in raster order in the same sweep with one packed warp
-// scan (iniTh list straight to global memory, minTh list to shared memory, copied out only if the
-// iniTh list is empty).
+// Stages per cell:
+//   0. one TMA box load (cp.async.bulk.tensor.3d, coordinates x, y, slot) brings the cell tile into shared memory;
+//   1. dense, branch-free scoring.  With M1 = min_k max(p_k..p_k+8) and M2 = max_k min(p_k..p_k+8) over the raw ring
+//      pixels, R = max(v - M1, M2 - v) - 1.  Each lane scores 4 adjacent pixels as two 16x2-packed pairs: one PRMT per
+//      ring operand puts the two pixels into the HIGH byte of each 16-bit half (the low byte cannot change which high
+//      byte wins a min/max), and the 9-wide sliding extrema run on the native 3-input VIMNMX3.U16x2 (80 per pair;
+//      measured on B200: 2- and 3-input integer min/max both issue every 2 cycles per SM sub-partition, so the
+//      3-input form - two comparisons per slot - is the cheapest network);
+//   2. the 4-pixel groups holding some R >= minTh are listed with a ballot sweep, and the strict 3x3 maximum test at
+//      both thresholds runs packed (16x2) on that dense list; the survivors of both thresholds are compacted in raster
+//      order by one packed warp scan (iniTh list straight to global memory, minTh list to shared memory, copied out
+//      only if the iniTh list is empty).
 //
-// Integer-only, hence bit-exact.  Bound: integer ALU (~60 instructions per pixel, VIMNMX3 dominated);
-// algorithmic global bytes per launch = S * (sum_l P_l + 8 * n_candidates).
+// Integer-only, hence bit-exact.  Bound: the integer ALU pipe (ncu: sm__throughput ~90 %, math_pipe_throttle +
+// not_selected stalls; DRAM traffic equals the algorithmic bytes); algorithmic global bytes per launch =
+// S * (sum_l P_l + 8 * n_candidates).
 #include "pslot_internal.h"
 #include "tma.cuh"
 
