@@ -50,19 +50,41 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, s
 
     cv::Mat image = _image.getMat();
     assert(image.type() == CV_8UC1);
+    Run(image.data, image.cols, image.rows, (long)image.step, 1, false, _keypoints, _descriptors);
+}
 
+void ORBextractor::ExtractFromColor(const cv::Mat &imColor, int channels, bool bRGB, std::vector<cv::KeyPoint> &_keypoints,
+                                    cv::OutputArray _descriptors)
+{
+    if (imColor.empty()) return;
+    // with the stand-in cv::Mat the caller describes an interleaved image as rows x (cols * channels) bytes
+#ifdef PSLOT_USE_OPENCV
+    const int w = imColor.cols;
+#else
+    const int w = imColor.cols / channels;
+#endif
+    Run(imColor.data, w, imColor.rows, (long)imColor.step, channels, bRGB, _keypoints, _descriptors);
+}
+
+void ORBextractor::Run(const unsigned char *data, int w, int h, long step, int channels, bool rgb,
+                       std::vector<cv::KeyPoint> &_keypoints, cv::OutputArray _descriptors)
+{
     const int cap = pslot_orb_max_keypoints(mpCtx);
     _keypoints.resize(cap);
     mvDescBuf.resize((size_t)cap * 32);
     int n = 0;
     static_assert(sizeof(cv::KeyPoint) == sizeof(pslot_keypoint), "cv::KeyPoint must be 28 bytes");
-    int rc = pslot_orb_extract(mpCtx, image.data, image.cols, image.rows, (ptrdiff_t)image.step,
-                               reinterpret_cast<pslot_keypoint *>(_keypoints.data()), mvDescBuf.data(), cap, &n);
+    auto call = [&](int capacity) {
+        pslot_keypoint *k = reinterpret_cast<pslot_keypoint *>(_keypoints.data());
+        return channels == 1 ? pslot_orb_extract(mpCtx, data, w, h, (ptrdiff_t)step, k, mvDescBuf.data(), capacity, &n)
+                             : pslot_orb_extract_color(mpCtx, data, w, h, (ptrdiff_t)step, channels, rgb ? 1 : 0, k,
+                                                       mvDescBuf.data(), capacity, &n);
+    };
+    int rc = call(cap);
     if (rc == PSLOT_ERR_CAPACITY) { // the capacity depends on the image aspect ratio; retry with the exact count
         _keypoints.resize(n);
         mvDescBuf.resize((size_t)n * 32);
-        rc = pslot_orb_extract(mpCtx, image.data, image.cols, image.rows, (ptrdiff_t)image.step,
-                               reinterpret_cast<pslot_keypoint *>(_keypoints.data()), mvDescBuf.data(), n, &n);
+        rc = call(n);
     }
     if (rc != PSLOT_OK) die("pslot_orb_extract");
     _keypoints.resize(n);

@@ -41,6 +41,12 @@ public:
     void operator()(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint> &keypoints,
                     cv::OutputArray descriptors);
 
+    // Extension: same as operator() for an interleaved 8-bit colour frame (3 or 4 channels); the
+    // cvtColor(RGB/BGR(A) -> GRAY) that Tracking::GrabImageStereo applies first (Tracking.cc:1014-1039) runs on the
+    // device, fused with the upload.  bRGB = Tracking's mbRGB (Camera.RGB).
+    void ExtractFromColor(const cv::Mat &imColor, int channels, bool bRGB, std::vector<cv::KeyPoint> &keypoints,
+                          cv::OutputArray descriptors);
+
     int inline GetLevels() { return nlevels; }
     float inline GetScaleFactor() { return scaleFactor; }
     std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }
@@ -68,6 +74,9 @@ protected:
     std::vector<float> mvInvScaleFactor;
     std::vector<float> mvLevelSigma2;
     std::vector<float> mvInvLevelSigma2;
+
+    void Run(const unsigned char *data, int w, int h, long step, int channels, bool rgb,
+             std::vector<cv::KeyPoint> &keypoints, cv::OutputArray descriptors);
 
     pslot_orb *mpCtx;
     bool mbKeepHostPyramid;
