@@ -229,14 +229,17 @@ struct Engine {
         typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        static EncodeFn encode = nullptr;
-        if (!encode) {
+        // resolved once through the runtime (no link-time dependency on libcuda); function-local static
+        // initialisation is thread-safe, and two extractor contexts may configure concurrently (Frame.cc:161-164)
+        static const EncodeFn encode = []() -> EncodeFn {
             void *fn = nullptr;
             cudaDriverEntryPointQueryResult q;
-            CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-            if (!fn || q != cudaDriverEntryPointSuccess) return fail(PSLOT_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
-            encode = (EncodeFn)fn;
-        }
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+                q != cudaDriverEntryPointSuccess)
+                return nullptr;
+            return (EncodeFn)fn;
+        }();
+        if (!encode) return fail(PSLOT_ERR_CUDA, "cuTensorMapEncodeTiled unavailable in this driver");
         for (int l = 0; l < g.nlevels; ++l) {
             const LevelGeom &L = g.lv[l];
             const cuuint64_t dims[3] = {(cuuint64_t)L.w, (cuuint64_t)L.h, (cuuint64_t)nslots};
@@ -585,14 +588,11 @@ int pslot_stereo_match(pslot_orb *cl, pslot_orb *cr, const pslot_keypoint *kps_l
     StereoArgs a{};
     a.kps_l = cl->d_kl; a.kps_r = cl->d_kr; a.desc_l = cl->d_dl; a.desc_r = cl->d_dr;
     a.n_l = cl->d_n; a.n_r = cl->d_n + 1;
-    a.K = cl->st_cap;
+    a.K = need; // one pair: the row stride is never used, and the grid (sized from K) covers exactly the left set
     a.pyr_l = L.pyr; a.pyr_r = R.pyr;
     a.bf = bf; a.max_d = max_d;
     a.u_right = cl->d_ur; a.depth = cl->d_dp; a.best_dist = cl->d_bd; a.best_idx = cl->d_bi; a.sad = cl->d_sd;
-    // the grid is sized from K; shrink it to the actual left count
-    StereoArgs launch_args = a;
-    launch_args.K = cl->st_cap;
-    launch_stereo(L.g, launch_args, 1, std::max(n_r, 1), st);
+    launch_stereo(L.g, a, 1, std::max(n_r, 1), st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "stereo launch failed: %s", cudaGetErrorString(e));
     CU(cudaMemcpyAsync(u_right, cl->d_ur, 4 * (size_t)n_l, cudaMemcpyDeviceToHost, st));

@@ -183,7 +183,7 @@ k_quadtree(const __grid_constant__ Geom g, const int *__restrict__ cell_count,
     }
 
     // ---- roots (:543-585) ------------------------------------------------------------------------
-    const int wd = L.max_bx - PSLOT_MINB, hd = L.max_by - PSLOT_MINB;
+    const int hd = L.max_by - PSLOT_MINB;
     const int nIni = L.n_ini;
     const float hX = L.hx;
     int cur = 0;
@@ -217,7 +217,6 @@ k_quadtree(const __grid_constant__ Geom g, const int *__restrict__ cell_count,
     __syncthreads();
     for (int i = tid; i < nkeys; i += QT) knode[i] = s.newpos[knode[i]];
     __syncthreads();
-    (void)wd;
 
     // ---- main loop (:594-739) --------------------------------------------------------------------
     bool fine = false;
@@ -429,11 +428,8 @@ int launch_quadtree(const Geom &g, const int *cell_count, const uint32_t *cell_c
 {
     int key_cap = 0;
     const size_t smem = quadtree_smem_bytes(g, &key_cap);
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    // per device and per function: set on every launch (cheap), contexts may live on different devices
+    cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(g.nlevels, nslots);
     k_quadtree<<<grid, QT, smem, st>>>(g, cell_count, cell_cand, cell_prefix, qt_keys, qt_nodes, lkp, lkp_count,
                                        err_flag, g.max_level_cap, key_cap);
