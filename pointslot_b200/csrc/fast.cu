@@ -45,10 +45,12 @@ __device__ __forceinline__ uint32_t pick(const uint32_t (&w)[4])
 {
     constexpr int i0 = 4 + S + O0, i1 = i0 + 1; // byte indices into the 16-byte row segment
     static_assert(i0 >= 0 && i1 <= 15, "offset out of the staged segment");
-    constexpr int wa = i0 >> 2, wb = (wa < 3) ? wa + 1 : 3;
-    constexpr int b0 = i0 - 4 * wa, b1 = i1 - 4 * wa; // 0..3 -> first source, 4..7 -> second source
-    static_assert(b1 <= 4 && (b1 < 4 || wa < 3), "pair leaves the segment");
-    return __byte_perm(w[wa], w[wb], b0 | (b0 << 4) | (b1 << 8) | (b1 << 12));
+    // Byte extraction on the FMA pipe: IDP.4A with a one-hot byte mask returns that byte zero-extended, and one
+    // IMAD packs the pair as p0 | p1 << 16 (clean 16x2).  The integer ALU pipe - the kernel's bottleneck - is left
+    // to the min/max network; PRMT would cost one ALU slot per operand.
+    const uint32_t p0 = __dp4a(w[i0 >> 2], 1u << (8 * (i0 & 3)), 0u);
+    const uint32_t p1 = __dp4a(w[i1 >> 2], 1u << (8 * (i1 & 3)), 0u);
+    return p1 * 65536u + p0;
 }
 
 // ring position k -> (dx, dy) (OpenCV FAST 9-16 pixel order), rows indexed dy + 3
@@ -116,12 +118,9 @@ __device__ __forceinline__ void score_pass(const uint32_t *tile32, uint32_t *sco
         arc_minmax(P, m1a, m2a);
         ring_pairs<S, 1>(w, P);
         arc_minmax(P, m1b, m2b);
-        // the 4 centre pixels as clean (zero-extended) 16x2 pairs, and the extrema moved down from the high bytes
-        constexpr int c0 = 4 + S, ca = c0 >> 2, cb = ca + 1; // centre bytes c0..c0+3 of row 3
-        const uint32_t cw = __byte_perm(w[3][ca], w[3][cb], (c0 & 3) | (((c0 & 3) + 1) << 4) | (((c0 & 3) + 2) << 8) | (((c0 & 3) + 3) << 12));
-        const uint32_t v01 = __byte_perm(cw, 0, 0x4140), v23 = __byte_perm(cw, 0, 0x4342);
-        const uint32_t a01 = __byte_perm(m1a, 0, 0x4341), b01 = __byte_perm(m2a, 0, 0x4341);
-        const uint32_t a23 = __byte_perm(m1b, 0, 0x4341), b23 = __byte_perm(m2b, 0, 0x4341);
+        // the 4 centre pixels as clean (zero-extended) 16x2 pairs (the extrema already are)
+        const uint32_t v01 = pick<S, 0>(w[3]), v23 = pick<S, 2>(w[3]);
+        const uint32_t a01 = m1a, b01 = m2a, a23 = m1b, b23 = m2b;
         // R = max(v - M1, M2 - v) - 1 clamped at 0; thresholds are applied in pass 2
         const uint32_t one = 0x00010001u;
         const uint32_t r01 = __vimax_s16x2_relu(__vsub2(__vsub2(v01, a01), one), __vsub2(__vsub2(b01, v01), one));
