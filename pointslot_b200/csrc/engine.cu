@@ -695,6 +695,8 @@ int pslot_batch_create(pslot_batch **b, int nfeatures, float scale_factor, int n
     Params p{nfeatures, scale_factor, nlevels, ini_th, min_th};
     int rc = c->E.init(p, device, stream);
     if (!rc) rc = c->E.configure(width, height, 2 * max_pairs);
+    if (!rc && c->E.g.kp_cap_total > 16000) // the stereo kernel stages every right key of a pair in shared memory
+        rc = fail(PSLOT_ERR_CAPACITY, "nfeatures too large for the batched stereo matcher (%d keypoint slots > 16000)", c->E.g.kp_cap_total);
     if (rc) { delete c; return rc; }
     c->max_pairs = max_pairs;
     *b = c;

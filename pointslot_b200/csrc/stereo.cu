@@ -37,12 +37,19 @@ struct SadSmem {
     int sad[12];
 };
 
+constexpr int BIN_SHIFT = 4;  // right keypoints are bucketed by 16-row bins of their band
+constexpr int LEFT_PER_CTA = SW * 8;
+
 __global__ void __launch_bounds__(SW * 32)
-k_stereo_match(const __grid_constant__ Geom g, const __grid_constant__ StereoArgs a, int right_cap)
+k_stereo_match(const __grid_constant__ Geom g, const __grid_constant__ StereoArgs a, int right_cap, int list_cap, int nbins)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    RightKey *rk = reinterpret_cast<RightKey *>(smem_raw);
+    RightKey *rk = reinterpret_cast<RightKey *>(smem_raw);                                   // [right_cap]
+    uint16_t *blist = reinterpret_cast<uint16_t *>(smem_raw + sizeof(RightKey) * (size_t)right_cap); // [list_cap]
+    int *bin_start = reinterpret_cast<int *>(blist + list_cap); // [nbins + 1]; list_cap is even
+    int *bin_fill = bin_start + nbins + 1;                                                   // [nbins]
     __shared__ SadSmem sads[SW];
+    __shared__ int s_use_bins;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pair = blockIdx.y;
@@ -51,9 +58,15 @@ k_stereo_match(const __grid_constant__ Geom g, const __grid_constant__ StereoArg
     const pslot_keypoint *kR = a.kps_r + row0;
     const pslot_keypoint *kL = a.kps_l + row0;
 
-    const int iL0 = blockIdx.x * (SW * 4);
+    const int iL0 = blockIdx.x * LEFT_PER_CTA;
     if (iL0 >= nL) return;
 
+    // ---- stage the right keys and bucket them by row bin -------------------------------------------------
+    // The reference's row table vRowIndices[r] lists the right keypoints whose band contains row r (:2152-2169); the
+    // candidates of a left keypoint at row r are a subset of the bin r >> 4, and the band test below restores the
+    // exact set.  The visiting order inside a bin is irrelevant: the argmin is taken over (distance, iR) pairs.
+    for (int i = tid; i <= nbins; i += SW * 32) bin_start[i] = 0;
+    __syncthreads();
     for (int i = tid; i < nR; i += SW * 32) {
         const pslot_keypoint k = kR[i];
         const int oct = min(max(k.octave, 0), g.nlevels - 1);
@@ -64,11 +77,40 @@ k_stereo_match(const __grid_constant__ Geom g, const __grid_constant__ StereoArg
         e.octave = oct;
         e.x = k.x;
         rk[i] = e;
+        const int b0 = min(max((int)e.minr >> BIN_SHIFT, 0), nbins - 1), b1 = min(max((int)e.maxr >> BIN_SHIFT, 0), nbins - 1);
+        for (int b = b0; b <= b1; ++b) atomicAdd(&bin_start[b + 1], 1);
     }
     __syncthreads();
+    if (warp == 0) { // inclusive scan of the bin counts (nbins <= a few hundred)
+        int carry = 0;
+        for (int base = 0; base <= nbins; base += 32) {
+            const int i = base + lane;
+            int v = i <= nbins ? bin_start[i] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            if (i <= nbins) bin_start[i] = v + carry;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+        if (lane == 0) s_use_bins = carry <= list_cap; // very tall bands or no room for the lists: scan every right key
+    }
+    __syncthreads();
+    const bool use_bins = s_use_bins != 0;
+    if (use_bins) {
+        for (int i = tid; i < nbins; i += SW * 32) bin_fill[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < nR; i += SW * 32) {
+            const RightKey e = rk[i];
+            const int b0 = min(max((int)e.minr >> BIN_SHIFT, 0), nbins - 1), b1 = min(max((int)e.maxr >> BIN_SHIFT, 0), nbins - 1);
+            for (int b = b0; b <= b1; ++b) blist[bin_start[b] + atomicAdd(&bin_fill[b], 1)] = (uint16_t)i;
+        }
+        __syncthreads();
+    }
 
     const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < LEFT_PER_CTA / SW; ++q) {
         const int iL = iL0 + q * SW + warp;
         if (iL >= nL) continue; // warp-uniform
         const pslot_keypoint kp = kL[iL];
@@ -82,7 +124,13 @@ k_stereo_match(const __grid_constant__ Geom g, const __grid_constant__ StereoArg
         const uint4 l0 = __ldg(dl), l1 = __ldg(dl + 1);
         unsigned best = ((unsigned)TH_HIGH << 16) | 0xFFFFu;
         if (maxU >= 0) {
-            for (int iR = lane; iR < nR; iR += 32) {
+            int jb = 0, je = nR;
+            if (use_bins) {
+                const int b = min(max(row >> BIN_SHIFT, 0), nbins - 1);
+                jb = bin_start[b]; je = bin_start[b + 1];
+            }
+            for (int j = jb + lane; j < je; j += 32) {
+                const int iR = use_bins ? (int)blist[j] : j;
                 const RightKey e = rk[iR];
                 if (row < e.minr || row > e.maxr) continue;
                 if (e.octave < levelL - 1 || e.octave > levelL + 1) continue;
@@ -91,8 +139,8 @@ k_stereo_match(const __grid_constant__ Geom g, const __grid_constant__ StereoArg
                 const uint4 r0 = __ldg(dr), r1 = __ldg(dr + 1);
                 const int dist = __popc(l0.x ^ r0.x) + __popc(l0.y ^ r0.y) + __popc(l0.z ^ r0.z) + __popc(l0.w ^ r0.w) +
                                  __popc(l1.x ^ r1.x) + __popc(l1.y ^ r1.y) + __popc(l1.z ^ r1.z) + __popc(l1.w ^ r1.w);
-                const unsigned key = ((unsigned)dist << 16) | (unsigned)iR;
-                best = min(best, key); // per lane iR ascends, so equal distances keep the first
+                // first strict minimum in ascending iR (:2219) == minimum of (dist, iR), whatever the visiting order
+                best = min(best, ((unsigned)dist << 16) | (unsigned)iR);
             }
         }
         best = __reduce_min_sync(0xffffffffu, best);
@@ -244,10 +292,15 @@ k_stereo_reject(const __grid_constant__ StereoArgs a)
 
 int launch_stereo(const Geom &g, const StereoArgs &a, int npairs, int max_n_r, cudaStream_t st, cudaEvent_t between)
 {
-    const size_t smem = sizeof(RightKey) * (size_t)max_n_r;
+    const int nbins = ((g.lv[0].h + (1 << BIN_SHIFT) - 1) >> BIN_SHIFT) + 1;
+    const size_t fixed = sizeof(RightKey) * (size_t)max_n_r + sizeof(int) * (2 * (size_t)nbins + 2);
+    // a band of 2 * 2 * scale + 2 rows touches at most 3 bins up to scale 7.5; lists are dropped when they do not fit
+    int list_cap = (3 * max_n_r + 1) & ~1;
+    if (fixed + 2 * (size_t)list_cap > 220 * 1024) list_cap = 0;
+    const size_t smem = fixed + 2 * (size_t)list_cap;
     cudaFuncSetAttribute(k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid((a.K + SW * 4 - 1) / (SW * 4), npairs);
-    k_stereo_match<<<grid, SW * 32, smem, st>>>(g, a, max_n_r);
+    dim3 grid((a.K + LEFT_PER_CTA - 1) / LEFT_PER_CTA, npairs);
+    k_stereo_match<<<grid, SW * 32, smem, st>>>(g, a, max_n_r, list_cap, nbins);
     if (between) cudaEventRecord(between, st);
     k_stereo_reject<<<npairs, 256, 0, st>>>(a);
     return 2;

@@ -135,6 +135,51 @@ def test_noise_image_many_candidates(B, oracle_mod):
     assert k.tobytes() == ok.tobytes() and np.array_equal(d, od)
 
 
+@pytest.mark.parametrize("params", [(7000, 1.2, 8, 12, 5),    # right set doubled to > 12.4 k keys: no room for row-bin lists
+                                    (3000, 1.44, 7, 20, 7)])  # bands up to 2 * 2 * 1.44^6 rows: many bins per key
+def test_stereo_search_fallbacks(params, B, oracle_mod):
+    """The stereo search buckets right keys by 16-row bins in shared memory; both escape hatches of that scheme
+    (lists dropped, lists overflowing) must give the same matches as the oracle's plain row table."""
+    from pointslot_b200.synth import synth_pair
+    rng = np.random.default_rng(11)
+    W, H = (1241, 376) if params[0] > 5000 else (1241, 752)
+    L, R = synth_pair(W, H, 77)
+    if params[0] > 5000:  # add texture everywhere so that the quota is actually reached
+        n = rng.integers(-40, 40, (H, W + 16))
+        L = np.clip(L.astype(int) + n[:, 16:], 0, 255).astype(np.uint8)
+        R = np.clip(R.astype(int) + n[:, 8:W + 8], 0, 255).astype(np.uint8)
+    bf, maxD = 384.38148, B.max_disparity(384.38148, 721.5377)
+    eL, eR = B.OrbExtractor(*params), B.OrbExtractor(*params)
+    oL, oR = oracle_mod.OracleExtractor(*params), oracle_mod.OracleExtractor(*params)
+    kL, dL = eL.extract(L); kR, dR = eR.extract(R)
+    okL, odL = oL.extract(L); okR, odR = oR.extract(R)
+    assert kL.tobytes() == okL.tobytes() and kR.tobytes() == okR.tobytes()
+    if params[0] > 5000:
+        # the matcher takes plain arrays: double the right set (copies shifted by a quarter pixel, same descriptors,
+        # so every Hamming minimum is a tie that the first index must win)
+        k2 = kR.copy(); k2["x"] += 0.25
+        kR = okR = np.concatenate([kR, k2]); dR = odR = np.concatenate([dR, dR])
+        assert len(kR) > 12500
+    ur, dp = B.stereo_match(eL, eR, kL, dL, kR, dR, bf, maxD)
+    our, odp = oracle_mod.stereo_match(oL, oR, okL, odL, okR, odR, bf, maxD)
+    _assert_stereo(ur, dp, our, odp)
+    assert (our > 0).sum() > 50
+    if params[0] <= 5000:
+        # same keypoints relabelled to the two coarsest octaves: every right band now spans 3-4 bins, which overflows the
+        # 3-entries-per-key lists; the matcher takes keypoints as plain arrays, so both sides accept the relabelling
+        # (border keypoints are dropped: at a coarser level their 11x11 SAD window would leave the image, which the
+        # reference does not guard against because real keypoints never get there)
+        def inner(k):
+            return (k["x"] > 100) & (k["x"] < W - 100) & (k["y"] > 64) & (k["y"] < H - 64)
+        mL, mR = inner(kL), inner(kR)
+        kL2, kR2, dL, dR, odL, odR = kL[mL].copy(), kR[mR].copy(), dL[mL], dR[mR], odL[mL], odR[mR]
+        kL2["octave"] = 5 + (np.arange(len(kL2)) & 1); kR2["octave"] = 6
+        ur, dp = B.stereo_match(eL, eR, kL2, dL, kR2, dR, bf, maxD)
+        our, odp = oracle_mod.stereo_match(oL, oR, kL2, odL, kR2, odR, bf, maxD)
+        _assert_stereo(ur, dp, our, odp)
+        assert (our > 0).sum() > 20
+
+
 def test_steering_coefficients_vs_libm(B, oracle_mod):
     """a=(float)cos, b=(float)sin of angle*pi/180 (double trig, rounded): every 509th float in [0,360] + specials.
     (tools/steer_sweep.py runs all 1.14e9 angles; result recorded in profiles/.)"""
