@@ -12,20 +12,21 @@
 //
 // Stages per cell:
 //   0. one TMA box load (cp.async.bulk.tensor.3d, coordinates x, y, slot) brings the cell tile into shared memory;
-//   1. dense, branch-free scoring.  With M1 = min_k max(p_k..p_k+8) and M2 = max_k min(p_k..p_k+8) over the raw ring
-//      pixels, R = max(v - M1, M2 - v) - 1.  Each lane scores 4 adjacent pixels as two 16x2-packed pairs: one PRMT per
-//      ring operand puts the two pixels into the HIGH byte of each 16-bit half (the low byte cannot change which high
-//      byte wins a min/max), and the 9-wide sliding extrema run on the native 3-input VIMNMX3.U16x2 (80 per pair;
+//   A. threshold iniThFAST.  A byte-SWAR rejection test (compass ring pixels 0/8 and 4/12 against the centre, 4
+//      pixels per VABSDIFF4) lists the 4-pixel groups that can hold a corner - a few percent of them on natural
+//      images - and only those get the exact score: with M1 = min_k max(p_k..p_k+8) and M2 = max_k min(p_k..p_k+8)
+//      over the raw ring pixels, R = max(v - M1, M2 - v) - 1.  A lane scores its 4 pixels as two 16x2-packed pairs
+//      (ring bytes extracted on the FMA pipe, IDP.4A + IMAD) on the native 3-input VIMNMX3.U16x2 (80 per pair;
 //      measured on B200: 2- and 3-input integer min/max both issue every 2 cycles per SM sub-partition, so the
-//      3-input form - two comparisons per slot - is the cheapest network);
-//   2. the 4-pixel groups holding some R >= minTh are listed with a ballot sweep, and the strict 3x3 maximum test at
-//      both thresholds runs packed (16x2) on that dense list; the survivors of both thresholds are compacted in raster
-//      order by one packed warp scan (iniTh list straight to global memory, minTh list to shared memory, copied out
-//      only if the iniTh list is empty).
+//      3-input form - two comparisons per slot - is the cheapest network).  The strict 3x3 maximum test runs packed
+//      (16x2) on the same list and the survivors are compacted in raster order by a warp scan, straight to global;
+//   B. only if A found nothing (:812-816): threshold minThFAST, at which the rejection test passes most pixels, so
+//      every group is scored (dense, branch-free), the groups holding some R >= minTh are listed by ballot, and the
+//      same maxima test + compaction follows.
 //
-// Integer-only, hence bit-exact.  Bound: the integer ALU pipe (ncu: sm__throughput ~90 %, math_pipe_throttle +
-// not_selected stalls; DRAM traffic equals the algorithmic bytes); algorithmic global bytes per launch =
-// S * (sum_l P_l + 8 * n_candidates).
+// Integer-only, hence bit-exact.  Bound: the integer ALU pipe (ncu: math_pipe_throttle + not_selected stalls; DRAM
+// traffic equals the algorithmic bytes); algorithmic global bytes per launch = S * (sum_l P_l + 8 * n_candidates)
+// (SURVEY.md 8d).
 #include "pslot_internal.h"
 #include "tma.cuh"
 
@@ -34,33 +35,33 @@ namespace {
 constexpr int FW = 4;        // warps (= cells) per CTA
 // A TMA box must start on a 16-byte boundary of the global row, so the box starts at the aligned x below
 // (cell start - 1); the residual 0..15 byte offset is uniform per warp: a whole-word part folded into the
-// shared-memory word index and a 0..3 byte part S that selects one of four specialisations of the scoring
-// loop, in which every ring byte pair is fetched by ONE PRMT with compile-time selectors.
+// shared-memory word index and a 0..3 byte part S that is removed from the ring rows by funnel shifts.  (Four
+// compile-time specialisations on S save those shifts, but with warps of one SM spread over four copies of the
+// scoring loop the instruction cache thrashes: ncu showed 46 % no_instructions stalls.  One copy it is.)
 
-// w[0..3]: four consecutive shared words of one ring row; the group's first pixel is byte 4 + S of them.
-// Returns a 16x2 value whose HIGH bytes are the pixels at offsets O0 and O0 + 1 from the group's first pixel
-// (low bytes repeat them: a 16-bit min/max is decided by the high byte first, so they are harmless).
-template <int S, int O0>
-__device__ __forceinline__ uint32_t pick(const uint32_t (&w)[4])
+// n[0..2]: twelve bytes of one ring row, already shifted so that the group's first pixel is byte 4.
+// Returns a clean 16x2 value holding the pixels at offsets O0 and O0 + 1 from the group's first pixel.
+template <int O0>
+__device__ __forceinline__ uint32_t pick(const uint32_t (&n)[3])
 {
-    constexpr int i0 = 4 + S + O0, i1 = i0 + 1; // byte indices into the 16-byte row segment
-    static_assert(i0 >= 0 && i1 <= 15, "offset out of the staged segment");
+    constexpr int i0 = 4 + O0, i1 = i0 + 1; // byte indices into the 12-byte row segment
+    static_assert(i0 >= 0 && i1 <= 11, "offset out of the staged segment");
     // Byte extraction on the FMA pipe: IDP.4A with a one-hot byte mask returns that byte zero-extended, and one
-    // IMAD packs the pair as p0 | p1 << 16 (clean 16x2).  The integer ALU pipe - the kernel's bottleneck - is left
-    // to the min/max network; PRMT would cost one ALU slot per operand.
-    const uint32_t p0 = __dp4a(w[i0 >> 2], 1u << (8 * (i0 & 3)), 0u);
-    const uint32_t p1 = __dp4a(w[i1 >> 2], 1u << (8 * (i1 & 3)), 0u);
+    // IMAD packs the pair as p0 | p1 << 16.  The integer ALU pipe - the kernel's bottleneck - is left to the
+    // min/max network; PRMT would cost one ALU slot per operand.
+    const uint32_t p0 = __dp4a(n[i0 >> 2], 1u << (8 * (i0 & 3)), 0u);
+    const uint32_t p1 = __dp4a(n[i1 >> 2], 1u << (8 * (i1 & 3)), 0u);
     return p1 * 65536u + p0;
 }
 
 // ring position k -> (dx, dy) (OpenCV FAST 9-16 pixel order), rows indexed dy + 3
 // k:  0      1      2      3      4      5       6       7       8       9        10       11       12      13      14      15
 //   (0,3)  (1,3)  (2,2)  (3,1)  (3,0)  (3,-1)  (2,-2)  (1,-3)  (0,-3)  (-1,-3)  (-2,-2)  (-3,-1)  (-3,0)  (-3,1)  (-2,2)  (-1,3)
-template <int S, int J>
-__device__ __forceinline__ void ring_pairs(const uint32_t (&w)[7][4], uint32_t (&P)[16])
+template <int J>
+__device__ __forceinline__ void ring_pairs(const uint32_t (&n)[7][3], uint32_t (&P)[16])
 {
     constexpr int o = 2 * J;
-#define PK(k, dx, dy) P[k] = pick<S, o + (dx)>(w[(dy) + 3])
+#define PK(k, dx, dy) P[k] = pick<o + (dx)>(n[(dy) + 3])
     PK(0, 0, 3);   PK(1, 1, 3);   PK(2, 2, 2);    PK(3, 3, 1);
     PK(4, 3, 0);   PK(5, 3, -1);  PK(6, 2, -2);   PK(7, 1, -3);
     PK(8, 0, -3);  PK(9, -1, -3); PK(10, -2, -2); PK(11, -3, -1);
@@ -95,33 +96,77 @@ __device__ __forceinline__ void arc_minmax(const uint32_t (&P)[16], uint32_t &M1
     M2 = m2;
 }
 
-// pass 1 for one alignment S: dense exact scores of every 4-pixel group of the cell
-template <int S>
-__device__ __forceinline__ void score_pass(const uint32_t *tile32, uint32_t *score32, int TSW, int wsh, int lane,
-                                           int ntasks, int gshift, int iw)
+// Rejection test at threshold t for every 4-pixel group of the cell (phase A).  A 9-arc of the 16-pixel ring
+// contains at least one pixel of every opposite pair {k, k + 8}; so a pixel whose ring pixels 0 / 8 (or 4 / 12:
+// the compass points) BOTH lie within t of the centre cannot be a corner at threshold t.  Byte-SWAR on 4 pixels at
+// a time: VABSDIFF4 against the centre quad, then bit 7 of ((d + 127 - t) | d) is set where d > t (a carry from
+// the byte below can only add a false positive, which merely costs an exact score).  The groups with a possible
+// corner are listed in raster order; on KITTI-like images at iniThFAST = 20 that is ~6 % of the groups.
+__device__ __forceinline__ int quick_pass(const uint32_t *tile32, int TSW, int wsh, int S, int lane, int ntasks,
+                                          int gshift, int iw, uint32_t bias, uint16_t *glist)
 {
     const int G1 = (1 << gshift) - 1;
-    for (int t = lane; t < ntasks; t += 32) {
+    // four consecutive pixels starting O bytes from the group's first pixel = bytes 4 + S + O .. of the 16-byte row
+    // segment: word index and PRMT selector per offset, warp-uniform
+    const int a0 = 1, aE = (7 + S) >> 2, aW = (1 + S) >> 2;
+    const uint32_t sel0 = 0x3210u + 0x1111u * (uint32_t)S, selE = 0x3210u + 0x1111u * (uint32_t)((7 + S) & 3),
+                   selW = 0x3210u + 0x1111u * (uint32_t)((1 + S) & 3);
+    int nlist = 0;
+    for (int base = 0; base < ntasks; base += 32) {
+        const int t = base + lane;
+        const int y = t >> gshift, gx = t & G1;
+        bool hit = false;
+        if (t < ntasks && 4 * gx < iw) {
+            const uint32_t *mid = tile32 + (y + 3) * TSW + gx + wsh;
+            const uint32_t *top = mid - 3 * TSW, *bot = mid + 3 * TSW;
+            const uint32_t v = __byte_perm(mid[a0], mid[a0 + 1], sel0);
+            const uint32_t d4 = __vabsdiffu4(__byte_perm(mid[aE], mid[aE + 1], selE), v);
+            const uint32_t d12 = __vabsdiffu4(__byte_perm(mid[aW], mid[aW + 1], selW), v);
+            const uint32_t d0 = __vabsdiffu4(__byte_perm(bot[a0], bot[a0 + 1], sel0), v);
+            const uint32_t d8 = __vabsdiffu4(__byte_perm(top[a0], top[a0 + 1], sel0), v);
+            const uint32_t e0 = (d0 + bias) | d0, e8 = (d8 + bias) | d8, e4 = (d4 + bias) | d4, e12 = (d12 + bias) | d12;
+            uint32_t pass = (e0 | e8) & (e4 | e12) & 0x80808080u;
+            const int rem = iw - 4 * gx;
+            if (rem < 4) pass &= (1u << (8 * rem)) - 1u;
+            hit = pass != 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) glist[nlist + __popc(m & ((1u << lane) - 1u))] = (uint16_t)t;
+        nlist += __popc(m);
+    }
+    return nlist;
+}
+
+// Exact scores of the `count` listed 4-pixel groups (phase A), or of every group of the cell when list == nullptr
+// (phase B, count = ntasks).
+__device__ __forceinline__ void score_pass(const uint32_t *tile32, uint32_t *score32, int TSW, int wsh, int S, int lane,
+                                           const uint16_t *list, int count, int gshift, int iw)
+{
+    const int G1 = (1 << gshift) - 1;
+    const int sh = 8 * S;
+    for (int j = lane; j < count; j += 32) {
+        const int t = list ? (int)list[j] : j;
         const int y = t >> gshift, gx = t & G1;
         if (4 * gx >= iw) continue;
-        // 16-byte segment of each ring row that contains bytes -4..7 around the group's first pixel
+        // 12-byte segment of each ring row holding bytes -4..7 around the group's first pixel
         const uint32_t *base = tile32 + (y + 3) * TSW + gx + wsh;
-        uint32_t w[7][4];
+        uint32_t n[7][3];
 #pragma unroll
         for (int r = 0; r < 7; ++r) {
             const uint32_t *p = base + (r - 3) * TSW;
-            w[r][0] = p[0]; w[r][1] = p[1]; w[r][2] = p[2]; w[r][3] = p[3];
+            const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3];
+            n[r][0] = __funnelshift_r(w0, w1, sh); n[r][1] = __funnelshift_r(w1, w2, sh); n[r][2] = __funnelshift_r(w2, w3, sh);
         }
         uint32_t P[16];
         uint32_t m1a, m2a, m1b, m2b;
-        ring_pairs<S, 0>(w, P);
+        ring_pairs<0>(n, P);
         arc_minmax(P, m1a, m2a);
-        ring_pairs<S, 1>(w, P);
+        ring_pairs<1>(n, P);
         arc_minmax(P, m1b, m2b);
         // the 4 centre pixels as clean (zero-extended) 16x2 pairs (the extrema already are)
-        const uint32_t v01 = pick<S, 0>(w[3]), v23 = pick<S, 2>(w[3]);
+        const uint32_t v01 = pick<0>(n[3]), v23 = pick<2>(n[3]);
         const uint32_t a01 = m1a, b01 = m2a, a23 = m1b, b23 = m2b;
-        // R = max(v - M1, M2 - v) - 1 clamped at 0; thresholds are applied in pass 2
+        // R = max(v - M1, M2 - v) - 1 clamped at 0; the threshold is applied by the maxima test
         const uint32_t one = 0x00010001u;
         const uint32_t r01 = __vimax_s16x2_relu(__vsub2(__vsub2(v01, a01), one), __vsub2(__vsub2(b01, v01), one));
         const uint32_t r23 = __vimax_s16x2_relu(__vsub2(__vsub2(v23, a23), one), __vsub2(__vsub2(b23, v23), one));
@@ -133,7 +178,7 @@ __device__ __forceinline__ void score_pass(const uint32_t *tile32, uint32_t *sco
     }
 }
 
-__global__ void __launch_bounds__(FW * 32)
+__global__ void __launch_bounds__(FW * 32, 6)
 k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet maps,
              int *__restrict__ cell_count, uint32_t *__restrict__ cell_cand, int warp_smem_bytes)
 {
@@ -161,10 +206,11 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
         return;
     }
 
-    // per-warp shared memory: [ TMA tile (box_w x box_h) | score map (same stride, box_h + 1 rows) ]
+    // per-warp shared memory: [ TMA tile (box_w x box_h) | score map (same stride, box_h + 1 rows) | group list ]
     uint8_t *tile = smem + (size_t)warp * warp_smem_bytes;
     const int TS = L.box_w, TSW = TS >> 2;
     uint8_t *score = tile + ((TS * L.box_h + 127) & ~127);
+    uint16_t *glist = reinterpret_cast<uint16_t *>(score + ((TS * (L.box_h + 1) + 127) & ~127)); // <= 16 groups x ih rows
     uint64_t *bar = &bars[warp];
 
     // ---- stage the cell: one TMA box load (x, y, slot) -> dense shared tile, row stride = box width ----
@@ -189,55 +235,59 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
     const int gshift = iw <= 32 ? 3 : 4;
     const int G = 1 << gshift;
     const int ntasks = ih << gshift;
-    // thresholds as packed constants: (t - 1) in both 16-bit halves; SWAR bias for "some byte >= minTh"
-    const uint32_t tmin1 = (uint32_t)(g.min_th - 1) * 0x00010001u, tini1 = (uint32_t)(g.ini_th - 1) * 0x00010001u;
-    const uint32_t ge_bias = g.min_th <= 128 ? (uint32_t)(128 - g.min_th) * 0x01010101u : 0x7F7F7F7Fu;
-
-    // ---- pass 1: dense exact scores (specialised on the warp-uniform byte alignment of the cell) ----
-    {
-        const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
-        uint32_t *score32 = reinterpret_cast<uint32_t *>(score);
-        switch (sh0 & 3) {
-        case 0: score_pass<0>(tile32, score32, TSW, wsh, lane, ntasks, gshift, iw); break;
-        case 1: score_pass<1>(tile32, score32, TSW, wsh, lane, ntasks, gshift, iw); break;
-        case 2: score_pass<2>(tile32, score32, TSW, wsh, lane, ntasks, gshift, iw); break;
-        default: score_pass<3>(tile32, score32, TSW, wsh, lane, ntasks, gshift, iw); break;
-        }
-    }
-    __syncwarp();
-
-    // ---- pass 2: 3x3 strict maxima at both thresholds + raster-ordered compaction of both lists ----
+    const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
+    uint32_t *score32 = reinterpret_cast<uint32_t *>(score);
     uint32_t *out = cell_cand + (size_t)slot * g.cand_per_slot + L.cand_base + (size_t)cell * L.cand_stride;
-    uint32_t *min_list = reinterpret_cast<uint32_t *>(tile); // the raw tile is dead after pass 1
     const int ox = iniX + 3 - PSLOT_MINB, oy = iniY + 3 - PSLOT_MINB; // window-relative (:820-825)
-    // pass 2a: list (raster order) the groups that hold at least one score >= minTh; typically a quarter of
-    // them, so the neighbourhood test below runs on dense warps instead of dragging idle lanes along
-    uint16_t *glist = reinterpret_cast<uint16_t *>(tile + 4 * L.cand_stride); // behind min_list, inside the dead tile
-    int nlist = 0;
-    for (int base = 0; base < ntasks; base += 32) {
-        const int t = base + lane;
-        bool hit = false;
-        if (t < ntasks) {
-            const uint32_t s4 = reinterpret_cast<const uint32_t *>(score)[((t >> gshift) + 3) * TSW + (t & (G - 1)) + 1];
-            hit = (((s4 + ge_bias) | s4) & 0x80808080u) != 0; // SWAR "some byte >= minTh" (false positives are harmless)
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (hit) glist[nlist + __popc(m & ((1u << lane) - 1u))] = (uint16_t)t;
-        nlist += __popc(m);
-    }
-    __syncwarp();
 
-    // pass 2b: strict 3x3 maxima of the listed groups + compaction
-    uint32_t totals = 0; // iniTh count | minTh count << 16
-    for (int base = 0; base < nlist; base += 32) {
-        const int j = base + lane;
-        const int t = j < nlist ? (int)glist[j] : 0;
-        const int y = t >> gshift, gx = t & (G - 1);
-        uint32_t f_ini = 0, f_min = 0, s4 = 0;
-        if (j < nlist) {
-            const uint32_t *sw = reinterpret_cast<const uint32_t *>(score) + (y + 3) * TSW + gx + 1;
-            s4 = sw[0];
-            {
+    // Phase A = cv::FAST(cell, iniThFAST); phase B = cv::FAST(cell, minThFAST), only if A found nothing (:809-816).
+    int n = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+        const int thr = phase == 0 ? g.ini_th : g.min_th;
+        const uint16_t *list = nullptr;
+        int count = ntasks, nlist = 0;
+        if (phase == 0) {
+            // A.1: cheap rejection test on every group; exact scores only where a corner is possible.  Unlisted
+            // groups keep score 0, which is what the maxima test needs: their R is below the threshold.
+            const uint32_t bias = thr <= 127 ? (uint32_t)(127 - thr) * 0x01010101u : 0u;
+            nlist = quick_pass(tile32, TSW, wsh, sh0 & 3, lane, ntasks, gshift, iw, bias, glist);
+            __syncwarp();
+            if (nlist == 0) continue;
+            list = glist;
+            count = nlist;
+        }
+        // exact scores: listed groups in phase A, every group in phase B
+        score_pass(tile32, score32, TSW, wsh, sh0 & 3, lane, list, count, gshift, iw);
+        __syncwarp();
+        if (phase == 1) {
+            // B.1: list (raster order) the groups that hold at least one score >= minTh, so that the neighbourhood
+            // test below runs on dense warps
+            const uint32_t ge_bias = thr <= 128 ? (uint32_t)(128 - thr) * 0x01010101u : 0u;
+            for (int base = 0; base < ntasks; base += 32) {
+                const int t = base + lane;
+                bool hit = false;
+                if (t < ntasks) {
+                    const uint32_t s4 = score32[((t >> gshift) + 3) * TSW + (t & (G - 1)) + 1];
+                    hit = (((s4 + ge_bias) | s4) & 0x80808080u) != 0; // SWAR "some byte >= thr" (false positives are harmless)
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (hit) glist[nlist + __popc(m & ((1u << lane) - 1u))] = (uint16_t)t;
+                nlist += __popc(m);
+            }
+            __syncwarp();
+        }
+
+        // strict 3x3 maxima of the listed groups at this threshold + raster-ordered compaction into the cell's list
+        const uint32_t thr1 = (uint32_t)(thr - 1) * 0x00010001u; // (t - 1) in both 16-bit halves
+        int total = 0;
+        for (int base = 0; base < nlist; base += 32) {
+            const int j = base + lane;
+            const int t = j < nlist ? (int)glist[j] : 0;
+            const int y = t >> gshift, gx = t & (G - 1);
+            uint32_t f = 0, s4 = 0;
+            if (j < nlist) {
+                const uint32_t *sw = score32 + (y + 3) * TSW + gx + 1;
+                s4 = sw[0];
                 // At threshold t the neighbour map is (R >= t ? R : 0) and the pixel needs R >= t, so
                 // "strictly above all 8 neighbours at threshold t" == (R >= t) && (R > max of the 8 raw R).
                 const uint32_t uL = sw[-TSW - 1], uM = sw[-TSW], uR = sw[-TSW + 1];
@@ -261,42 +311,30 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
 #undef EV
 #undef OD
                 // sign bit of each half: (nmax - R) < 0  <=>  R > nmax ;  (t - 1 - R) < 0  <=>  R >= t
-                const uint32_t gte = __vsub2(ne, se), gto = __vsub2(no, so);
-                const uint32_t me = gte & __vsub2(tmin1, se), mo = gto & __vsub2(tmin1, so);
-                const uint32_t ie = gte & __vsub2(tini1, se), io = gto & __vsub2(tini1, so);
+                const uint32_t ke = __vsub2(ne, se) & __vsub2(thr1, se), ko = __vsub2(no, so) & __vsub2(thr1, so);
                 // halves: e = pixels (0, 2), o = pixels (1, 3)  ->  4-bit flags
-                const uint32_t cm = ((me & 0x80008000u) >> 1) | (mo & 0x80008000u);
-                const uint32_t cf = ((ie & 0x80008000u) >> 1) | (io & 0x80008000u);
-                f_min = ((cm >> 14) & 3u) | ((cm >> 28) & 0xCu);
-                f_ini = ((cf >> 14) & 3u) | ((cf >> 28) & 0xCu);
+                const uint32_t c = ((ke & 0x80008000u) >> 1) | (ko & 0x80008000u);
+                f = ((c >> 14) & 3u) | ((c >> 28) & 0xCu);
             }
-        }
-        if (__ballot_sync(0xffffffffu, f_min != 0) == 0) continue; // nothing survives in these 32 groups (warp-uniform)
-        const uint32_t c = (uint32_t)__popc(f_ini) | ((uint32_t)__popc(f_min) << 16);
-        uint32_t incl = c;
+            if (__ballot_sync(0xffffffffu, f != 0) == 0) continue; // nothing survives in these 32 groups (warp-uniform)
+            const int c = __popc(f);
+            int incl = c;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int pos = total + incl - c;
+            const uint32_t vbase = pslot_pack(4 * gx + ox, y + oy, 0);
+            for (uint32_t ff = f; ff; ff &= ff - 1) { // survivors of this group in x order
+                const int i = __ffs((int)ff) - 1;
+                if (pos < L.cand_stride) out[pos] = vbase + ((uint32_t)i << 8) + ((s4 >> (8 * i)) & 0xFFu);
+                ++pos;
+            }
+            total += __shfl_sync(0xffffffffu, incl, 31);
         }
-        const uint32_t excl = totals + incl - c;
-        int pi = (int)(excl & 0xFFFFu), pm = (int)(excl >> 16);
-        const uint32_t vbase = pslot_pack(4 * gx + ox, y + oy, 0);
-        for (uint32_t f = f_min; f; f &= f - 1) { // survivors of this group in x order (f_ini is a subset of f_min)
-            const int i = __ffs((int)f) - 1;
-            const uint32_t v = vbase + ((uint32_t)i << 8) + ((s4 >> (8 * i)) & 0xFFu);
-            if (f_ini & (1u << i)) { if (pi < L.cand_stride) out[pi] = v; ++pi; }
-            if (pm < L.cand_stride) min_list[pm] = v;
-            ++pm;
-        }
-        totals += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    const int n_ini = (int)(totals & 0xFFFFu), n_min = (int)(totals >> 16);
-    int n = n_ini;
-    if (n_ini == 0) { // no corner at iniThFAST: the cell falls back to minThFAST (:812-816)
-        __syncwarp();
-        n = min(n_min, L.cand_stride);
-        for (int i = lane; i < n; i += 32) out[i] = min_list[i];
+        n = total;
+        if (n > 0) break;
     }
     if (lane == 0) *count_out = min(n, L.cand_stride);
 }
@@ -309,7 +347,8 @@ int launch_fast(const Geom &g, const TmapSet &maps, int *cell_count, uint32_t *c
     for (int l = 0; l < g.nlevels; ++l) {
         const int tile = (g.lv[l].box_w * g.lv[l].box_h + 127) & ~127;
         const int score = (g.lv[l].box_w * (g.lv[l].box_h + 1) + 127) & ~127;
-        per_warp = per_warp > tile + score ? per_warp : tile + score;
+        const int list = (2 * 16 * (g.lv[l].box_h - 6) + 127) & ~127;
+        per_warp = per_warp > tile + score + list ? per_warp : tile + score + list;
     }
     const size_t smem = (size_t)per_warp * FW;
     cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
