@@ -111,13 +111,19 @@ __device__ __forceinline__ int quick_pass(const uint32_t *tile32, int TSW, int w
     const int a0 = 1, aE = (7 + S) >> 2, aW = (1 + S) >> 2;
     const uint32_t sel0 = 0x3210u + 0x1111u * (uint32_t)S, selE = 0x3210u + 0x1111u * (uint32_t)((7 + S) & 3),
                    selW = 0x3210u + 0x1111u * (uint32_t)((1 + S) & 3);
+    const int gmax = (iw - 1) >> 2; // last group of a row that holds tested pixels
+    const unsigned lt = (1u << lane) - 1u;
     int nlist = 0;
-    for (int base = 0; base < ntasks; base += 32) {
-        const int t = base + lane;
-        const int y = t >> gshift, gx = t & G1;
-        bool hit = false;
-        if (t < ntasks && 4 * gx < iw) {
-            const uint32_t *mid = tile32 + (y + 3) * TSW + gx + wsh;
+    // two independent groups per lane and iteration, branch-free (clamped addresses, masked result), so that the
+    // loads of one hide the dependent chain of the other
+    for (int base = 0; base < ntasks; base += 64) {
+        bool hit[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int t = base + 32 * u + lane;
+            const int tc = min(t, ntasks - 1);
+            const int y = tc >> gshift, gx = tc & G1, gxc = min(gx, gmax);
+            const uint32_t *mid = tile32 + (y + 3) * TSW + gxc + wsh;
             const uint32_t *top = mid - 3 * TSW, *bot = mid + 3 * TSW;
             const uint32_t v = __byte_perm(mid[a0], mid[a0 + 1], sel0);
             const uint32_t d4 = __vabsdiffu4(__byte_perm(mid[aE], mid[aE + 1], selE), v);
@@ -126,13 +132,15 @@ __device__ __forceinline__ int quick_pass(const uint32_t *tile32, int TSW, int w
             const uint32_t d8 = __vabsdiffu4(__byte_perm(top[a0], top[a0 + 1], sel0), v);
             const uint32_t e0 = (d0 + bias) | d0, e8 = (d8 + bias) | d8, e4 = (d4 + bias) | d4, e12 = (d12 + bias) | d12;
             uint32_t pass = (e0 | e8) & (e4 | e12) & 0x80808080u;
-            const int rem = iw - 4 * gx;
+            const int rem = iw - 4 * gxc; // >= 1
             if (rem < 4) pass &= (1u << (8 * rem)) - 1u;
-            hit = pass != 0;
+            hit[u] = pass != 0 && t < ntasks && gx <= gmax;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (hit) glist[nlist + __popc(m & ((1u << lane) - 1u))] = (uint16_t)t;
-        nlist += __popc(m);
+        const unsigned m0 = __ballot_sync(0xffffffffu, hit[0]), m1 = __ballot_sync(0xffffffffu, hit[1]);
+        const int n0 = __popc(m0);
+        if (hit[0]) glist[nlist + __popc(m0 & lt)] = (uint16_t)(base + lane);
+        if (hit[1]) glist[nlist + n0 + __popc(m1 & lt)] = (uint16_t)(base + 32 + lane);
+        nlist += n0 + __popc(m1);
     }
     return nlist;
 }
@@ -193,7 +201,9 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
     while (l + 1 < g.nlevels && cell >= g.lv[l + 1].cell_base) ++l;
     const LevelGeom &L = g.lv[l];
     cell -= L.cell_base;
-    const int ci = cell / L.n_cols, cj = cell - ci * L.n_cols;
+    // cell / n_cols without the integer-division sequence: (cell + 0.5) / n lies at least 1 / (2 n) away from an
+    // integer, far beyond the 2-ulp error of the approximate division (quotients are below a few hundred)
+    const int ci = (int)__fdividef((float)cell + 0.5f, (float)L.n_cols), cj = cell - ci * L.n_cols;
     int *count_out = cell_count + (size_t)slot * g.cells_per_slot + L.cell_base + cell;
 
     // cell sub-image [ini, max) (:791-806); integers, so the reference's float compares are exact
@@ -317,21 +327,20 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
                 f = ((c >> 14) & 3u) | ((c >> 28) & 0xCu);
             }
             if (__ballot_sync(0xffffffffu, f != 0) == 0) continue; // nothing survives in these 32 groups (warp-uniform)
+            // raster position of this lane's survivors: prefix sum of the per-lane counts (0..4) from three ballots
+            // over the bits of the count - no dependent shuffle chain
             const int c = __popc(f);
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            int pos = total + incl - c;
+            const unsigned b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2),
+                           b2 = __ballot_sync(0xffffffffu, c & 4);
+            const unsigned lt = (1u << lane) - 1u;
+            int pos = total + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
             const uint32_t vbase = pslot_pack(4 * gx + ox, y + oy, 0);
             for (uint32_t ff = f; ff; ff &= ff - 1) { // survivors of this group in x order
                 const int i = __ffs((int)ff) - 1;
                 if (pos < L.cand_stride) out[pos] = vbase + ((uint32_t)i << 8) + ((s4 >> (8 * i)) & 0xFFu);
                 ++pos;
             }
-            total += __shfl_sync(0xffffffffu, incl, 31);
+            total += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
         }
         n = total;
         if (n > 0) break;
