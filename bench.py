@@ -321,6 +321,17 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e, win2 = timed(host=True, collect=not args.no_e2e_stages)
     clocks = sampler.stop([win1, win2]) if rank == 0 else None
 
+    # PCIe reference for the e2e number: the same pinned images uploaded alone on the copy stream (nothing else running)
+    with torch.cuda.stream(copy_stream):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dL.copy_(hL, non_blocking=True); dR.copy_(hR, non_blocking=True)  # warm
+        e0.record()
+        for _ in range(3):
+            dL.copy_(hL, non_blocking=True); dR.copy_(hR, non_blocking=True)
+        e1.record()
+    e1.synchronize()
+    h2d_alone_gbs = 3 * 2 * P * img_bytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
     # sanity: the e2e outputs of the last sub-batch on ctx 0 are real features
     n0 = int(outs[0]["counts"][0])
     assert 0 < n0 <= K, "bench produced no keypoints"
@@ -377,7 +388,7 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": stages[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
                 "launch_pairs": Bsz, "ms_per_launch": stages[dom]["ms_per_launch"],
-                "note": "integer-ALU-bound kernel (ncu: sm__throughput ~90 %, DRAM traffic == algorithmic bytes); durations from a single-stream pass of the same submits inside this run; HBM fraction reported as the contract asks"}
+                "note": "integer-ALU / issue-bound kernel (ncu: issue slots ~66 % busy, DRAM traffic == algorithmic bytes); durations from a single-stream pass of the same submits inside this run; HBM fraction reported as the contract asks"}
 
     # ---- CPU baseline (bounded sample, N=1 only) ---------------------------------------------------
     cpu = None
@@ -402,6 +413,8 @@ def run_ours(args, rank, world, local_rank):
                    "matches_per_pair": stats["matches"] / sp, "synth_seconds": t_gen},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                 "ms_per_step": ms_e2e / args.steps,
+                "pcie": {"h2d_GBps_in_run": h2d / (ms_e2e / args.steps * 1e-3) / 1e9, "h2d_GBps_alone": h2d_alone_gbs,
+                         "note": "per GPU; e2e is bounded by the upload: ms_per_step >= h2d_bytes / h2d_GBps_alone"},
                 "stage_ms_per_submit": {n: float(v) for n, v in zip(B.StereoBatch.STAGES, e2e_stage_ms)}},
         "gpu_launches": launches_per_submit * nsub * args.steps * world,
         "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clocks,

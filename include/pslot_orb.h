@@ -110,6 +110,33 @@ int pslot_stereo_match(pslot_orb *ctx_l, pslot_orb *ctx_r,
 int pslot_hamming256(const void *a, const void *b);
 
 /* ---------------------------------------------------------------------------------------------
+ * Feature grid — void Frame::AssignFeaturesToGrid() with bool Frame::PosInGrid(kp, posX,
+ * posY) (Frame.cc:1636-1655, 2027-2038) and its consumer vector<size_t> Frame::GetFeaturesInArea(x, y, r,
+ * minLevel, maxLevel) (Frame.cc:1808-1861).
+ * mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS] is returned in CSR form: cell = i * rows + j for mGrid[i][j],
+ * cell_start[cols * rows + 1] offsets into `indices`, which lists the keypoint indices of each cell in
+ * push_back (= ascending) order; keypoints outside the grid appear nowhere.
+ * spec: min_x = mnMinX, min_y = mnMinY, inv_w = mfGridElementWidthInv, inv_h = mfGridElementHeightInv
+ * (Frame.cc:184-185), cols / rows = FRAME_GRID_COLS / FRAME_GRID_ROWS (Frame.h:40-41). */
+typedef struct pslot_grid_spec {
+    float min_x, min_y, inv_w, inv_h;
+    int32_t cols, rows;
+} pslot_grid_spec;
+typedef struct pslot_area_query {
+    float x, y, r;
+    int32_t min_level, max_level; /* as GetFeaturesInArea: levels are checked iff min_level > 0 || max_level >= 0 */
+} pslot_area_query;
+/* kps_un = mvKeysUn (n entries, host).  cell_start / indices (host, [cols*rows+1] / [n]) may be NULL to keep the
+ * grid on the device only; *n_in_grid (optional) receives the number of keypoints inside the grid.  The grid and
+ * the keypoints stay on the device for pslot_features_in_area. */
+int pslot_assign_grid(pslot_orb *ctx, const pslot_keypoint *kps_un, int n, const pslot_grid_spec *spec,
+                      int32_t *cell_start, int32_t *indices, int *n_in_grid);
+/* nq area queries against the grid of the last pslot_assign_grid on ctx.  counts[q] = number of features found
+ * (may exceed cap); indices[q * cap + k], k < min(counts[q], cap), in the reference's visiting order. */
+int pslot_features_in_area(pslot_orb *ctx, const pslot_area_query *queries, int nq, int cap, int32_t *counts,
+                           int32_t *indices);
+
+/* ---------------------------------------------------------------------------------------------
  * Throughput API — independent stereo pairs of one geometry, processed `max_pairs` at a time on one
  * GPU stream: both extractions (Frame.cc:161-164) + ComputeStereoMatches (:173) per pair, with no
  * host round trip in between.  This is the data-parallel form of the Frame stereo constructor path
@@ -153,6 +180,10 @@ int pslot_batch_submit(pslot_batch *b, const uint8_t *left, const uint8_t *right
 int pslot_batch_submit_color(pslot_batch *b, const uint8_t *left, const uint8_t *right, ptrdiff_t pitch,
                              ptrdiff_t image_stride, int npairs, int channels, int rgb_order, float bf,
                              float max_d, const pslot_batch_out *out);
+/* AssignFeaturesToGrid for the LEFT keypoints of every pair of the last submit (rectified input: mvKeysUn ==
+ * mvKeys), enqueued on the batch stream.  cell_start [npairs * (cols*rows+1)] / indices [npairs * K] are host
+ * buffers filled asynchronously (valid after pslot_batch_wait); either may be NULL. */
+int pslot_batch_assign_grid(pslot_batch *b, const pslot_grid_spec *spec, int32_t *cell_start, int32_t *indices);
 int pslot_batch_wait(pslot_batch *b);
 /* Number of kernels pslot_batch_submit launches per call (for launch accounting). */
 int pslot_batch_kernel_launches(const pslot_batch *b);

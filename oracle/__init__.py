@@ -78,6 +78,9 @@ def lib():
         L.orc_cvt_gray.restype = None
         L.orc_steer_coeffs.argtypes = [vp, C.c_int, vp, vp]
         L.orc_steer_coeffs.restype = None
+        L.orc_assign_grid.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp]
+        L.orc_features_in_area.argtypes = [vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
+                                           C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, vp]
         L.orc_distribute_octtree.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_int, vp, vp, vp, ip]
         _lib = L
@@ -156,6 +159,28 @@ def distribute_octtree(x, y, resp, min_x, max_x, min_y, max_y, n_features):
     n = lib().orc_distribute_octtree(_ptr(x), _ptr(y), _ptr(resp), len(x), min_x, max_x, min_y, max_y,
                                      n_features, cap, _ptr(ox), _ptr(oy), _ptr(orr), C.byref(tie))
     return ox[:n].copy(), oy[:n].copy(), orr[:n].copy(), bool(tie.value)
+
+
+def assign_grid(kps, min_x, min_y, inv_w, inv_h, cols=64, rows=48):
+    """Frame::AssignFeaturesToGrid (Frame.cc:1636-1655) -> (cell_start [cols*rows+1], indices [n_in_grid]);
+    cell = i * rows + j for mGrid[i][j]."""
+    kps = np.ascontiguousarray(kps, KEYPOINT_DTYPE)
+    cs = np.zeros(cols * rows + 1, np.int32); idx = np.zeros(max(len(kps), 1), np.int32)
+    n = lib().orc_assign_grid(_ptr(kps), len(kps), min_x, min_y, inv_w, inv_h, cols, rows, _ptr(cs), _ptr(idx))
+    if n < 0:
+        raise ValueError("bad grid arguments")
+    return cs, idx[:n].copy()
+
+
+def features_in_area(kps, cell_start, indices, min_x, min_y, inv_w, inv_h, cols, rows, x, y, r, min_level=-1,
+                     max_level=-1):
+    """Frame::GetFeaturesInArea (Frame.cc:1808-1861) -> indices in the reference's visiting order."""
+    kps = np.ascontiguousarray(kps, KEYPOINT_DTYPE)
+    cell_start = np.ascontiguousarray(cell_start, np.int32); indices = np.ascontiguousarray(indices, np.int32)
+    out = np.zeros(max(len(kps), 1), np.int32)
+    n = lib().orc_features_in_area(_ptr(kps), _ptr(cell_start), _ptr(indices), min_x, min_y, inv_w, inv_h, cols, rows,
+                                   x, y, r, min_level, max_level, len(out), _ptr(out))
+    return out[:n].copy()
 
 
 # ---------------------------------------------------------------------------------------------

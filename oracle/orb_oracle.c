@@ -913,3 +913,72 @@ int orc_stereo_match(const orc_extractor *eL, const orc_extractor *eR,
     free(vDistIdx); free(rlist); free(rstart); free(rcount);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Feature grid: Frame::PosInGrid (Frame.cc:2027-2038), Frame::AssignFeaturesToGrid
+ * (Frame.cc:1636-1655) and its consumer Frame::GetFeaturesInArea (Frame.cc:1808-1861).
+ * mGrid[i][j] is returned in CSR form: cell = i * rows + j, cell_start[cols * rows + 1], indices in push_back
+ * order (ascending keypoint index inside a cell).
+ * ------------------------------------------------------------------------------------------------------------ */
+static int pos_in_grid(const orc_keypoint *kp, float min_x, float min_y, float inv_w, float inv_h, int cols, int rows)
+{
+    /* posX = round((kp.pt.x-mnMinX)*mfGridElementWidthInv): float product, C round() on its double promotion */
+    const double rx = round((double)((kp->x - min_x) * inv_w));
+    const double ry = round((double)((kp->y - min_y) * inv_h));
+    /* the reference converts to int before the range test; the float test is the same for every finite value
+     * that fits an int, and rejects what would be undefined behaviour there */
+    if (!(rx >= 0 && rx < cols && ry >= 0 && ry < rows)) return -1;
+    return (int)rx * rows + (int)ry;
+}
+
+int orc_assign_grid(const orc_keypoint *kps, int n, float min_x, float min_y, float inv_w, float inv_h, int cols,
+                    int rows, int *cell_start, int *indices)
+{
+    const int C = cols * rows;
+    if (n < 0 || cols < 1 || rows < 1) return -1;
+    memset(cell_start, 0, sizeof(int) * (size_t)(C + 1));
+    for (int i = 0; i < n; ++i) {
+        const int c = pos_in_grid(&kps[i], min_x, min_y, inv_w, inv_h, cols, rows);
+        if (c >= 0) cell_start[c + 1]++;
+    }
+    for (int c = 0; c < C; ++c) cell_start[c + 1] += cell_start[c];
+    int *fill = (int *)malloc(sizeof(int) * (size_t)C);
+    memcpy(fill, cell_start, sizeof(int) * (size_t)C);
+    for (int i = 0; i < n; ++i) { /* ascending i == push_back order (:1647-1654) */
+        const int c = pos_in_grid(&kps[i], min_x, min_y, inv_w, inv_h, cols, rows);
+        if (c >= 0) indices[fill[c]++] = i;
+    }
+    free(fill);
+    return cell_start[C];
+}
+
+int orc_features_in_area(const orc_keypoint *kps, const int *cell_start, const int *indices, float min_x, float min_y,
+                         float inv_w, float inv_h, int cols, int rows, float x, float y, float r, int min_level,
+                         int max_level, int cap, int *out)
+{
+    int n = 0;
+    const int nMinCellX = (int)fmax(0.0, floor((double)((x - min_x - r) * inv_w)));
+    if (nMinCellX >= cols) return 0;
+    const int nMaxCellX = (int)fmin((double)(cols - 1), ceil((double)((x - min_x + r) * inv_w)));
+    if (nMaxCellX < 0) return 0;
+    const int nMinCellY = (int)fmax(0.0, floor((double)((y - min_y - r) * inv_h)));
+    if (nMinCellY >= rows) return 0;
+    const int nMaxCellY = (int)fmin((double)(rows - 1), ceil((double)((y - min_y + r) * inv_h)));
+    if (nMaxCellY < 0) return 0;
+    const int bCheckLevels = (min_level > 0) || (max_level >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+        for (int iy = nMinCellY; iy <= nMaxCellY; ++iy)
+            for (int j = cell_start[ix * rows + iy]; j < cell_start[ix * rows + iy + 1]; ++j) {
+                const orc_keypoint *k = &kps[indices[j]];
+                if (bCheckLevels) {
+                    if (k->octave < min_level) continue;
+                    if (max_level >= 0 && k->octave > max_level) continue;
+                }
+                const float distx = k->x - x, disty = k->y - y;
+                if (fabsf(distx) < r && fabsf(disty) < r) {
+                    if (n < cap) out[n] = indices[j];
+                    ++n;
+                }
+            }
+    return n;
+}

@@ -90,6 +90,15 @@ int orc_distribute_octtree(const int *x, const int *y, const int *resp, int n,
                            int minX, int maxX, int minY, int maxY, int N,
                            int cap, int *ox, int *oy, int *oresp, int *tie_sensitive);
 
+/* Frame::AssignFeaturesToGrid + PosInGrid (Frame.cc:1636-1655, 2027-2038): mGrid in CSR form, cell = i * rows + j;
+ * returns the number of keypoints that fell inside the grid (-1: bad arguments) */
+int orc_assign_grid(const orc_keypoint *kps, int n, float min_x, float min_y, float inv_w, float inv_h, int cols,
+                    int rows, int *cell_start, int *indices);
+/* Frame::GetFeaturesInArea (Frame.cc:1808-1861) on that CSR grid; returns the number found (may exceed cap) */
+int orc_features_in_area(const orc_keypoint *kps, const int *cell_start, const int *indices, float min_x, float min_y,
+                         float inv_w, float inv_h, int cols, int rows, float x, float y, float r, int min_level,
+                         int max_level, int cap, int *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,7 @@ ABI_SYMBOLS = [
     "pslot_batch_create", "pslot_batch_destroy", "pslot_batch_set_copy_stream", "pslot_batch_max_keypoints", "pslot_batch_stream",
     "pslot_batch_submit", "pslot_batch_submit_color", "pslot_batch_wait", "pslot_batch_kernel_launches", "pslot_batch_device_out",
     "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats",
+    "pslot_assign_grid", "pslot_features_in_area", "pslot_batch_assign_grid",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
 ]
 
@@ -37,6 +38,22 @@ class PslotError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"pslot error {code}: {msg}")
         self.code = code
+
+
+class GridSpec(C.Structure):
+    """pslot_grid_spec: mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv, FRAME_GRID_COLS / ROWS."""
+    _fields_ = [("min_x", C.c_float), ("min_y", C.c_float), ("inv_w", C.c_float), ("inv_h", C.c_float),
+                ("cols", C.c_int32), ("rows", C.c_int32)]
+
+    @classmethod
+    def for_image(cls, width: int, height: int, cols: int = 64, rows: int = 48):
+        """Rectified input (k1 == 0): bounds = the image (Frame.cc:2134-2139), inverse cell sizes as :184-185."""
+        w, h = np.float32(width), np.float32(height)
+        return cls(0.0, 0.0, float(np.float32(cols) / (w - np.float32(0))), float(np.float32(rows) / (h - np.float32(0))),
+                   cols, rows)
+
+
+AREA_QUERY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("r", "<f4"), ("min_level", "<i4"), ("max_level", "<i4")])
 
 
 class BatchOut(C.Structure):
@@ -69,6 +86,9 @@ def lib():
     L.pslot_orb_level.argtypes = [vp, C.c_int, vp, C.c_ssize_t, ip, ip]
     L.pslot_stereo_match.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_float, C.c_float, vp, vp]
     L.pslot_hamming256.argtypes = [vp, vp]
+    L.pslot_assign_grid.argtypes = [vp, vp, C.c_int, C.POINTER(GridSpec), vp, vp, C.POINTER(C.c_int)]
+    L.pslot_features_in_area.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+    L.pslot_batch_assign_grid.argtypes = [vp, C.POINTER(GridSpec), vp, vp]
     L.pslot_batch_create.argtypes = [C.POINTER(vp), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, vp]
     L.pslot_batch_destroy.argtypes = [vp]
@@ -201,6 +221,29 @@ class OrbExtractor:
         return x[: n.value].copy(), y[: n.value].copy(), r[: n.value].copy(), a[: n.value].copy()
 
 
+def assign_grid(ext: OrbExtractor, kps_un, spec: GridSpec):
+    """Frame::AssignFeaturesToGrid (reference src/Frame.cc:1636-1655) -> (cell_start [cols*rows+1], indices
+    [n_in_grid]); mGrid[i][j] = indices[cell_start[i*rows+j] : cell_start[i*rows+j+1]]."""
+    kps_un = np.ascontiguousarray(kps_un, KEYPOINT_DTYPE)
+    n = len(kps_un)
+    cs = np.zeros(spec.cols * spec.rows + 1, np.int32); idx = np.zeros(max(n, 1), np.int32)
+    tot = C.c_int(0)
+    _check(lib().pslot_assign_grid(ext._h, _p(kps_un), n, C.byref(spec), _p(cs), _p(idx), C.byref(tot)))
+    return cs, idx[:tot.value].copy()
+
+
+def features_in_area(ext: OrbExtractor, queries, cap: int):
+    """Frame::GetFeaturesInArea (reference src/Frame.cc:1808-1861) for an array of AREA_QUERY_DTYPE queries against
+    the grid of the last assign_grid on `ext` -> list of index arrays (reference visiting order)."""
+    queries = np.ascontiguousarray(queries, AREA_QUERY_DTYPE)
+    nq = len(queries)
+    counts = np.zeros(max(nq, 1), np.int32); out = np.zeros((max(nq, 1), max(cap, 1)), np.int32)
+    _check(lib().pslot_features_in_area(ext._h, _p(queries), nq, cap, _p(counts), _p(out)))
+    if nq and counts[:nq].max() > cap:
+        raise PslotError(-2, f"area query found {int(counts[:nq].max())} features, cap is {cap}")
+    return [out[q, :counts[q]].copy() for q in range(nq)]
+
+
 def stereo_match(ext_l: OrbExtractor, ext_r: OrbExtractor, kL, dL, kR, dR, bf: float, max_d: float, debug=False):
     """Frame::ComputeStereoMatches (reference src/Frame.cc:2142-2316) -> (mvuRight, mvDepth)."""
     kL = np.ascontiguousarray(kL, KEYPOINT_DTYPE); kR = np.ascontiguousarray(kR, KEYPOINT_DTYPE)
@@ -293,6 +336,13 @@ class StereoBatch:
         assert left.strides[2] == 1 and right.strides == left.strides
         self.submit_ptr(left.ctypes.data, right.ctypes.data, left.strides[1], left.strides[0], left.shape[0], True,
                         bf, max_d, out)
+
+    def assign_grid(self, spec: GridSpec, npairs: int):
+        """Feature grids of the left keypoints of the last submit -> (cell_start [npairs, cells+1], indices [npairs, K]);
+        asynchronous: valid after wait()."""
+        cs = np.zeros((npairs, spec.cols * spec.rows + 1), np.int32); idx = np.zeros((npairs, self.K), np.int32)
+        _check(lib().pslot_batch_assign_grid(self._h, C.byref(spec), _p(cs), _p(idx)))
+        return cs, idx
 
     def wait(self):
         _check(lib().pslot_batch_wait(self._h))

@@ -1,10 +1,12 @@
 // Frame.cc — stereo-construction path of PointSLOT's Frame over the C ABI of libpslot_orb.so
-// (reference src/Frame.cc:144-200, 1658-1664, 2049-2079, 2142-2316).
+// (reference src/Frame.cc:144-200, 1636-1664, 1808-1861, 2027-2038, 2049-2079, 2112-2140, 2142-2316).
 #include "Frame.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <thread>
 
 #include "../../include/pslot_orb.h"
@@ -14,6 +16,8 @@ namespace ORB_SLAM2
 
 bool Frame::mbInitialComputations = true;
 float Frame::cx, Frame::cy, Frame::fx, Frame::fy, Frame::invfx, Frame::invfy;
+float Frame::mnMinX, Frame::mnMinY, Frame::mnMaxX, Frame::mnMaxY;
+float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv;
 
 Frame::Frame()
     : mpORBvocabulary(nullptr), mpORBextractorLeft(nullptr), mpORBextractorRight(nullptr), mTimeStamp(0), mbf(0),
@@ -52,6 +56,9 @@ Frame::Frame(const cv::Mat &imLeft, const cv::Mat &imRight, const double &timeSt
     // :197), i.e. maxD = mbf/mb reads an indeterminate value.  The intended value mb = mbf/fx is set first
     // (DESIGN.md parity rule 2); fx comes from K exactly as :187 does.
     if (mbInitialComputations) {
+        ComputeImageBounds(imLeft);
+        mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (mnMaxX - mnMinX);
+        mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (mnMaxY - mnMinY);
         fx = K.at<float>(0, 0);
         fy = K.at<float>(1, 1);
         cx = K.at<float>(0, 2);
@@ -63,6 +70,8 @@ Frame::Frame(const cv::Mat &imLeft, const cv::Mat &imRight, const double &timeSt
     mb = mbf / fx;
 
     ComputeStereoMatches();
+
+    AssignFeaturesToGrid(); // (:199)
 }
 
 void Frame::ExtractORB(int flag, const cv::Mat &im)
@@ -92,6 +101,115 @@ void Frame::UndistortKeyPoints()
     std::fprintf(stderr, "pslot Frame: distorted keypoints need OpenCV (build with -DPSLOT_USE_OPENCV)\n");
     std::abort();
 #endif
+}
+
+void Frame::ComputeImageBounds(const cv::Mat &imLeft)
+{
+    if (!mDistCoef.empty() && mDistCoef.at<float>(0) != 0.0) {
+#ifdef PSLOT_USE_OPENCV
+        cv::Mat mat(4, 2, CV_32F);
+        mat.at<float>(0, 0) = 0.0; mat.at<float>(0, 1) = 0.0;
+        mat.at<float>(1, 0) = imLeft.cols; mat.at<float>(1, 1) = 0.0;
+        mat.at<float>(2, 0) = 0.0; mat.at<float>(2, 1) = imLeft.rows;
+        mat.at<float>(3, 0) = imLeft.cols; mat.at<float>(3, 1) = imLeft.rows;
+        mat = mat.reshape(2);
+        cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK);
+        mat = mat.reshape(1);
+        mnMinX = std::min(mat.at<float>(0, 0), mat.at<float>(2, 0));
+        mnMaxX = std::max(mat.at<float>(1, 0), mat.at<float>(3, 0));
+        mnMinY = std::min(mat.at<float>(0, 1), mat.at<float>(1, 1));
+        mnMaxY = std::max(mat.at<float>(2, 1), mat.at<float>(3, 1));
+#else
+        std::fprintf(stderr, "pslot Frame: distorted image bounds need OpenCV (build with -DPSLOT_USE_OPENCV)\n");
+        std::abort();
+#endif
+    } else {
+        mnMinX = 0.0f;
+        mnMaxX = imLeft.cols;
+        mnMinY = 0.0f;
+        mnMaxY = imLeft.rows;
+    }
+}
+
+void Frame::AssignFeaturesToGrid()
+{
+    // the device builds mGrid as a CSR table (and keeps it, with mvKeysUn, for GetFeaturesInAreas); the member
+    // vectors are then filled from it in the same order the reference's push_back loop produces (:1647-1654)
+    const pslot_grid_spec spec = {mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv, FRAME_GRID_COLS,
+                                  FRAME_GRID_ROWS};
+    std::vector<int32_t> cellStart(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1), indices(std::max(N, 1));
+    int rc = pslot_assign_grid(mpORBextractorLeft->Handle(), reinterpret_cast<const pslot_keypoint *>(mvKeysUn.data()),
+                               N, &spec, cellStart.data(), indices.data(), nullptr);
+    if (rc != PSLOT_OK) {
+        std::fprintf(stderr, "pslot Frame: pslot_assign_grid failed: %s\n", pslot_last_error());
+        std::abort();
+    }
+    for (unsigned int i = 0; i < FRAME_GRID_COLS; i++)
+        for (unsigned int j = 0; j < FRAME_GRID_ROWS; j++) {
+            const int c = i * FRAME_GRID_ROWS + j;
+            mGrid[i][j].assign(indices.begin() + cellStart[c], indices.begin() + cellStart[c + 1]);
+        }
+}
+
+bool Frame::PosInGrid(const cv::KeyPoint &kp, int &posX, int &posY)
+{
+    posX = round((kp.pt.x - mnMinX) * mfGridElementWidthInv);
+    posY = round((kp.pt.y - mnMinY) * mfGridElementHeightInv);
+    // Keypoint's coordinates are undistorted, which could cause to go out of the image
+    return !(posX < 0 || posX >= FRAME_GRID_COLS || posY < 0 || posY >= FRAME_GRID_ROWS);
+}
+
+std::vector<size_t> Frame::GetFeaturesInArea(const float &x, const float &y, const float &r, const int minLevel,
+                                             const int maxLevel) const
+{
+    // one window: a host walk over mGrid, as in the reference; the batched form below runs on the device
+    std::vector<size_t> vIndices;
+    vIndices.reserve(N);
+    const int nMinCellX = std::max(0, (int)std::floor((x - mnMinX - r) * mfGridElementWidthInv));
+    if (nMinCellX >= FRAME_GRID_COLS) return vIndices;
+    const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)std::ceil((x - mnMinX + r) * mfGridElementWidthInv));
+    if (nMaxCellX < 0) return vIndices;
+    const int nMinCellY = std::max(0, (int)std::floor((y - mnMinY - r) * mfGridElementHeightInv));
+    if (nMinCellY >= FRAME_GRID_ROWS) return vIndices;
+    const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)std::ceil((y - mnMinY + r) * mfGridElementHeightInv));
+    if (nMaxCellY < 0) return vIndices;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
+            for (size_t idx : mGrid[ix][iy]) {
+                const cv::KeyPoint &kpUn = mvKeysUn[idx];
+                if (bCheckLevels) {
+                    if (kpUn.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kpUn.octave > maxLevel) continue;
+                }
+                if (std::fabs(kpUn.pt.x - x) < r && std::fabs(kpUn.pt.y - y) < r) vIndices.push_back(idx);
+            }
+    return vIndices;
+}
+
+std::vector<std::vector<size_t>> Frame::GetFeaturesInAreas(const std::vector<AreaQuery> &queries) const
+{
+    static_assert(sizeof(AreaQuery) == sizeof(pslot_area_query), "AreaQuery must mirror pslot_area_query");
+    const int nq = (int)queries.size();
+    std::vector<std::vector<size_t>> res(nq);
+    if (nq == 0 || N == 0) return res;
+    int cap = 64;
+    std::vector<int32_t> counts(nq), idx;
+    for (;;) {
+        idx.resize((size_t)nq * cap);
+        int rc = pslot_features_in_area(mpORBextractorLeft->Handle(),
+                                        reinterpret_cast<const pslot_area_query *>(queries.data()), nq, cap,
+                                        counts.data(), idx.data());
+        if (rc != PSLOT_OK) {
+            std::fprintf(stderr, "pslot Frame: pslot_features_in_area failed: %s\n", pslot_last_error());
+            std::abort();
+        }
+        const int need = *std::max_element(counts.begin(), counts.end());
+        if (need <= cap) break;
+        cap = need; // a window held more features than the buffer: ask again with room for the largest
+    }
+    for (int q = 0; q < nq; ++q) res[q].assign(idx.begin() + (size_t)q * cap, idx.begin() + (size_t)q * cap + counts[q]);
+    return res;
 }
 
 void Frame::ComputeStereoMatches()

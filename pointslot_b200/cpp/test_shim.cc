@@ -3,7 +3,9 @@
 // usage: test_shim <in.bin> <out.bin>
 //   in : int32 W,H,nfeatures,nlevels,iniTh,minTh; float32 scaleFactor,bf,fx; then W*H left bytes, W*H right bytes
 //   out: int32 N, Nr; N keypoints (28 B), N*32 desc, Nr keypoints, Nr*32 desc, N float uRight, N float depth,
-//        int32 pyramid level-1 w,h + bytes (checks SyncImagePyramid), int32 DescriptorDistance(desc0, desc1)
+//        int32 pyramid level-1 w,h + bytes (checks SyncImagePyramid), int32 DescriptorDistance(desc0, desc1),
+//        mGrid as 64*48 x (int32 size, int32 entries...), then 3 windows x (int32 n, entries) from GetFeaturesInArea
+//        and the same 3 from GetFeaturesInAreas
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -57,6 +59,21 @@ int main(int argc, char **argv)
     for (int r = 0; r < p1.rows; ++r) std::fwrite(p1.ptr(r), 1, p1.cols, o);
     const int dd = N >= 2 ? ORBmatcher::DescriptorDistance(frame.mDescriptors.row(0), frame.mDescriptors.row(1)) : -1;
     std::fwrite(&dd, 4, 1, o);
+    for (int i = 0; i < FRAME_GRID_COLS; ++i)
+        for (int j = 0; j < FRAME_GRID_ROWS; ++j) {
+            const int n = (int)frame.mGrid[i][j].size();
+            std::fwrite(&n, 4, 1, o);
+            for (size_t v : frame.mGrid[i][j]) { const int iv = (int)v; std::fwrite(&iv, 4, 1, o); }
+        }
+    const std::vector<Frame::AreaQuery> qs = {{W * 0.5f, H * 0.5f, 40.f, -1, -1}, {W * 0.25f, H * 0.7f, 25.f, 1, 4}, {5.f, 5.f, 90.f, 0, -1}};
+    std::vector<std::vector<size_t>> res;
+    for (const auto &q : qs) res.push_back(frame.GetFeaturesInArea(q.x, q.y, q.r, q.minLevel, q.maxLevel));
+    for (const auto &r : frame.GetFeaturesInAreas(qs)) res.push_back(r);
+    for (const auto &r : res) {
+        const int n = (int)r.size();
+        std::fwrite(&n, 4, 1, o);
+        for (size_t v : r) { const int iv = (int)v; std::fwrite(&iv, 4, 1, o); }
+    }
     std::fclose(o);
     std::printf("shim ok: N=%d Nr=%d matched=%d mb=%g\n", N, Nr,
                 (int)std::count_if(frame.mvuRight.begin(), frame.mvuRight.end(), [](float v) { return v >= 0; }), frame.mb);

@@ -354,10 +354,19 @@ struct pslot_orb {
     size_t h_stage_bytes = 0;
     uint8_t *d_cstage = nullptr;      // tightly packed colour frame awaiting conversion
     size_t cstage_bytes = 0;
+    // feature grid of the last pslot_assign_grid (kept for pslot_features_in_area)
+    pslot_keypoint *d_gk = nullptr;
+    int *d_gidx = nullptr, *d_gcs = nullptr, *d_qcount = nullptr, *d_qout = nullptr;
+    pslot_area_query *d_q = nullptr;
+    int gk_cap = 0, gcs_cap = 0, q_cap = 0;
+    size_t qout_cap = 0;
+    int grid_n = -1;
+    pslot_grid_spec grid_spec = {};
 
     ~pslot_orb()
     {
         free_stereo();
+        cudaFree(d_gk); cudaFree(d_gidx); cudaFree(d_gcs); cudaFree(d_qcount); cudaFree(d_qout); cudaFree(d_q);
         cudaFree(d_cstage);
         if (h_stage) cudaFreeHost(h_stage);
     }
@@ -377,6 +386,8 @@ struct pslot_batch {
     int launches = 0;
     bool profiling = false, profiled = false;
     cudaEvent_t ev[PSLOT_NUM_STAGES + 1] = {};
+    int *d_gcs = nullptr, *d_gidx = nullptr; // feature grids of the last submit (pslot_batch_assign_grid)
+    int gcs_cells = 0;
     uint8_t *d_stage = nullptr; // tightly packed landing zone for host images (one linear H2D per view)
     uint8_t *d_cstage = nullptr; // same for colour frames
     size_t cstage_bytes = 0;
@@ -394,6 +405,8 @@ struct pslot_batch {
             if (e) cudaEventDestroy(e);
         cudaFree(d_stage);
         cudaFree(d_cstage);
+        cudaFree(d_gcs);
+        cudaFree(d_gidx);
     }
 };
 
@@ -916,6 +929,114 @@ int pslot_batch_stats(pslot_batch *b, int64_t stats[4])
             stats[2] += bd[p * K + i] < 75;
             stats[3] += ur[p * K + i] >= 0.f;
         }
+    return PSLOT_OK;
+}
+
+static int check_grid_spec(const pslot_grid_spec *spec)
+{
+    if (!spec) return fail(PSLOT_ERR_ARG, "spec is null");
+    if (spec->cols < 1 || spec->rows < 1 || (long long)spec->cols * spec->rows > 16384)
+        return fail(PSLOT_ERR_ARG, "grid must have 1..16384 cells");
+    return PSLOT_OK;
+}
+
+int pslot_assign_grid(pslot_orb *ctx, const pslot_keypoint *kps_un, int n, const pslot_grid_spec *spec,
+                      int32_t *cell_start, int32_t *indices, int *n_in_grid)
+{
+    if (!ctx) return fail(PSLOT_ERR_ARG, "ctx is null");
+    if (n < 0 || (n > 0 && !kps_un)) return fail(PSLOT_ERR_ARG, "bad keypoint array");
+    if (int rc = check_grid_spec(spec)) return rc;
+    Engine &E = ctx->E;
+    CU(cudaSetDevice(E.device));
+    const int C = spec->cols * spec->rows;
+    if (n > ctx->gk_cap) {
+        cudaFree(ctx->d_gk); cudaFree(ctx->d_gidx);
+        ctx->d_gk = nullptr; ctx->d_gidx = nullptr; ctx->gk_cap = 0;
+        const int cap = std::max(n, 2048);
+        CU(cudaMalloc(&ctx->d_gk, sizeof(pslot_keypoint) * (size_t)cap));
+        CU(cudaMalloc(&ctx->d_gidx, sizeof(int) * (size_t)cap));
+        ctx->gk_cap = cap;
+    }
+    if (C + 1 > ctx->gcs_cap) {
+        cudaFree(ctx->d_gcs);
+        ctx->d_gcs = nullptr; ctx->gcs_cap = 0;
+        CU(cudaMalloc(&ctx->d_gcs, sizeof(int) * (size_t)(C + 1)));
+        ctx->gcs_cap = C + 1;
+    }
+    cudaStream_t st = E.st;
+    ctx->grid_n = -1;
+    if (n) CU(cudaMemcpyAsync(ctx->d_gk, kps_un, sizeof(pslot_keypoint) * (size_t)n, cudaMemcpyHostToDevice, st));
+    launch_assign_grid(ctx->d_gk, nullptr, n, (size_t)std::max(n, 1), *spec, ctx->d_gcs, ctx->d_gidx, 1, st);
+    CU(cudaGetLastError());
+    int total = 0;
+    CU(cudaMemcpyAsync(&total, ctx->d_gcs + C, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (cell_start) CU(cudaMemcpyAsync(cell_start, ctx->d_gcs, sizeof(int) * (size_t)(C + 1), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (indices && total) CU(cudaMemcpy(indices, ctx->d_gidx, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost));
+    if (n_in_grid) *n_in_grid = total;
+    ctx->grid_n = n;
+    ctx->grid_spec = *spec;
+    return PSLOT_OK;
+}
+
+int pslot_features_in_area(pslot_orb *ctx, const pslot_area_query *queries, int nq, int cap, int32_t *counts,
+                           int32_t *indices)
+{
+    if (!ctx) return fail(PSLOT_ERR_ARG, "ctx is null");
+    if (ctx->grid_n < 0) return fail(PSLOT_ERR_STATE, "pslot_assign_grid has not been called on this context");
+    if (nq < 0 || cap < 0 || (nq > 0 && (!queries || !counts)) || (nq > 0 && cap > 0 && !indices))
+        return fail(PSLOT_ERR_ARG, "bad query arguments");
+    if (nq == 0) return PSLOT_OK;
+    Engine &E = ctx->E;
+    CU(cudaSetDevice(E.device));
+    if (nq > ctx->q_cap) {
+        cudaFree(ctx->d_q); cudaFree(ctx->d_qcount);
+        ctx->d_q = nullptr; ctx->d_qcount = nullptr; ctx->q_cap = 0;
+        const int c = std::max(nq, 1024);
+        CU(cudaMalloc(&ctx->d_q, sizeof(pslot_area_query) * (size_t)c));
+        CU(cudaMalloc(&ctx->d_qcount, sizeof(int) * (size_t)c));
+        ctx->q_cap = c;
+    }
+    const size_t need = (size_t)nq * (size_t)std::max(cap, 1);
+    if (need > ctx->qout_cap) {
+        cudaFree(ctx->d_qout);
+        ctx->d_qout = nullptr; ctx->qout_cap = 0;
+        CU(cudaMalloc(&ctx->d_qout, sizeof(int) * need));
+        ctx->qout_cap = need;
+    }
+    cudaStream_t st = E.st;
+    CU(cudaMemcpyAsync(ctx->d_q, queries, sizeof(pslot_area_query) * (size_t)nq, cudaMemcpyHostToDevice, st));
+    launch_features_in_area(ctx->d_gk, ctx->d_gcs, ctx->d_gidx, ctx->grid_spec, ctx->d_q, nq, cap, ctx->d_qcount,
+                            ctx->d_qout, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(counts, ctx->d_qcount, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    if (cap > 0) CU(cudaMemcpyAsync(indices, ctx->d_qout, sizeof(int) * (size_t)nq * cap, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return PSLOT_OK;
+}
+
+int pslot_batch_assign_grid(pslot_batch *b, const pslot_grid_spec *spec, int32_t *cell_start, int32_t *indices)
+{
+    if (!b) return fail(PSLOT_ERR_ARG, "b is null");
+    if (int rc = check_grid_spec(spec)) return rc;
+    if (b->last_pairs <= 0) return fail(PSLOT_ERR_STATE, "no batch has been submitted");
+    Engine &E = b->E;
+    CU(cudaSetDevice(E.device));
+    const int C = spec->cols * spec->rows, np = b->last_pairs;
+    const size_t K = (size_t)E.g.kp_cap_total;
+    if (!b->d_gidx) CU(cudaMalloc(&b->d_gidx, sizeof(int) * K * (size_t)b->max_pairs));
+    if (C + 1 > b->gcs_cells) {
+        CU(cudaStreamSynchronize(E.st));
+        cudaFree(b->d_gcs);
+        b->d_gcs = nullptr; b->gcs_cells = 0;
+        CU(cudaMalloc(&b->d_gcs, sizeof(int) * (size_t)(C + 1) * (size_t)b->max_pairs));
+        b->gcs_cells = C + 1;
+    }
+    // left images are slots 0..np-1 of the batch: counts and keypoint rows are the first np entries
+    launch_assign_grid(E.d_out_kps, E.d_out_count, 0, K, *spec, b->d_gcs, b->d_gidx, np, E.st);
+    CU(cudaGetLastError());
+    if (cell_start) CU(cudaMemcpyAsync(cell_start, b->d_gcs, sizeof(int) * (size_t)(C + 1) * np, cudaMemcpyDeviceToHost, E.st));
+    if (indices) CU(cudaMemcpyAsync(indices, b->d_gidx, sizeof(int) * K * np, cudaMemcpyDeviceToHost, E.st));
     return PSLOT_OK;
 }
 

@@ -1,0 +1,161 @@
+// grid.cu — the 64 x 48 feature grid of Frame: Frame::PosInGrid (reference
+// src/Frame.cc:2027-2038), Frame::AssignFeaturesToGrid (:1636-1655) and the lookup that consumes it,
+// Frame::GetFeaturesInArea (:1808-1861).
+//
+// mGrid[i][j] (a vector of keypoint indices per cell, filled by push_back in keypoint order) becomes a CSR table
+// on the device: cell = i * rows + j, cell_start[cols * rows + 1], indices[] ascending inside a cell.
+//   k_assign_grid      one CTA per image: shared-memory histogram of the cell of every keypoint, block scan,
+//                      scatter with shared atomics, then each cell's (tiny) list is put in ascending order -
+//                      the only thing the atomics do not fix; the result is deterministic.
+//   k_features_in_area one warp per query: the cell rectangle is walked in the reference's order (ix outer, iy
+//                      inner, list order inside a cell) and the hits are compacted with ballots, so the output
+//                      order equals the reference's vIndices.
+// Float arithmetic as the reference writes it, products and differences kept separate (no FMA).
+// Bound: latency / HBM (28 B read + 4 B written per keypoint); algorithmic bytes = n_k * 32 + 4 * (cols * rows + 1).
+#include "pslot_internal.h"
+
+namespace {
+
+__device__ __forceinline__ int pos_in_grid(const pslot_keypoint &kp, const GridSpec &s)
+{
+    // posX = round((kp.pt.x - mnMinX) * mfGridElementWidthInv) (:2029-2030); C round() of a float value == roundf
+    const float rx = roundf(__fmul_rn(__fsub_rn(kp.x, s.min_x), s.inv_w));
+    const float ry = roundf(__fmul_rn(__fsub_rn(kp.y, s.min_y), s.inv_h));
+    if (!(rx >= 0.0f && rx < (float)s.cols && ry >= 0.0f && ry < (float)s.rows)) return -1; // (:2033)
+    return (int)rx * s.rows + (int)ry;
+}
+
+constexpr int GT = 256;
+
+__global__ void __launch_bounds__(GT)
+k_assign_grid(const pslot_keypoint *__restrict__ kps, const int *__restrict__ counts, int fixed_n, size_t stride,
+              GridSpec s, int *__restrict__ cell_start, int *__restrict__ indices)
+{
+    extern __shared__ int sm[];
+    const int C = s.cols * s.rows;
+    int *start = sm;          // [C + 1]
+    int *fill = sm + C + 1;   // [C]
+    __shared__ int warp_sums[GT / 32];
+
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const pslot_keypoint *k = kps + (size_t)img * stride;
+    const int n = counts ? min(counts[img], (int)stride) : fixed_n;
+    int *cs = cell_start + (size_t)img * (C + 1);
+    int *idx = indices + (size_t)img * stride;
+
+    for (int c = tid; c <= C; c += GT) start[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += GT) {
+        const int c = pos_in_grid(k[i], s);
+        if (c >= 0) atomicAdd(&start[c + 1], 1);
+    }
+    __syncthreads();
+    // inclusive scan of start[1..C] in place: a contiguous chunk per thread, then a scan of the chunk sums
+    const int per = (C + GT - 1) / GT;
+    const int lo = 1 + tid * per, hi = min(lo + per, C + 1);
+    int sum = 0;
+    for (int c = lo; c < hi; ++c) sum += start[c];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    int offset = incl - sum;
+    for (int w = 0; w < warp; ++w) offset += warp_sums[w];
+    for (int c = lo; c < hi; ++c) {
+        offset += start[c];
+        start[c] = offset;
+    }
+    __syncthreads();
+    for (int c = tid; c <= C; c += GT) {
+        cs[c] = start[c];
+        if (c < C) fill[c] = start[c];
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += GT) {
+        const int c = pos_in_grid(k[i], s);
+        if (c >= 0) idx[atomicAdd(&fill[c], 1)] = i;
+    }
+    __syncthreads(); // the block's own global writes are visible to it after the barrier
+    // ascending keypoint index inside each cell == push_back order (:1647-1654); lists are a handful of entries
+    for (int c = tid; c < C; c += GT) {
+        const int a = start[c], b = start[c + 1];
+        for (int i = a + 1; i < b; ++i) {
+            const int v = idx[i];
+            int j = i - 1;
+            while (j >= a && idx[j] > v) { idx[j + 1] = idx[j]; --j; }
+            idx[j + 1] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_features_in_area(const pslot_keypoint *__restrict__ kps, const int *__restrict__ cell_start,
+                   const int *__restrict__ indices, GridSpec s, const pslot_area_query *__restrict__ queries, int nq,
+                   int cap, int *__restrict__ out_count, int *__restrict__ out)
+{
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const pslot_area_query Q = queries[q];
+    const float x = Q.x, y = Q.y, r = Q.r;
+    int n = 0;
+    // (:1813-1827); the float -> int conversions are clamped first (the reference's are undefined out of range)
+    const float big = 1.0e9f;
+    const float fx0 = floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, s.min_x), r), s.inv_w));
+    const float fx1 = ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, s.min_x), r), s.inv_w));
+    const float fy0 = floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, s.min_y), r), s.inv_h));
+    const float fy1 = ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, s.min_y), r), s.inv_h));
+    const int nMinCellX = max(0, (int)fminf(fmaxf(fx0, -big), big));
+    const int nMaxCellX = min(s.cols - 1, (int)fminf(fmaxf(fx1, -big), big));
+    const int nMinCellY = max(0, (int)fminf(fmaxf(fy0, -big), big));
+    const int nMaxCellY = min(s.rows - 1, (int)fminf(fmaxf(fy1, -big), big));
+    const bool ok = nMinCellX < s.cols && nMaxCellX >= 0 && nMinCellY < s.rows && nMaxCellY >= 0 && fx0 == fx0 &&
+                    fx1 == fx1 && fy0 == fy0 && fy1 == fy1;
+    if (ok) {
+        const bool check_levels = Q.min_level > 0 || Q.max_level >= 0;
+        int *o = out + (size_t)q * cap;
+        for (int ix = nMinCellX; ix <= nMaxCellX; ++ix) {
+            // the cells (ix, nMinCellY..nMaxCellY) are adjacent in the CSR table: one contiguous index range
+            const int a = cell_start[ix * s.rows + nMinCellY], b = cell_start[ix * s.rows + nMaxCellY + 1];
+            for (int base = a; base < b; base += 32) {
+                const int j = base + lane;
+                bool hit = false;
+                int id = 0;
+                if (j < b) {
+                    id = indices[j];
+                    const pslot_keypoint kp = kps[id];
+                    hit = !(check_levels && (kp.octave < Q.min_level || (Q.max_level >= 0 && kp.octave > Q.max_level)));
+                    hit = hit && fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                const int p = n + __popc(m & ((1u << lane) - 1u));
+                if (hit && p < cap) o[p] = id;
+                n += __popc(m);
+            }
+        }
+    }
+    if (lane == 0) out_count[q] = n;
+}
+
+} // namespace
+
+size_t grid_smem_bytes(const GridSpec &s) { return sizeof(int) * (2 * (size_t)s.cols * s.rows + 1); }
+
+int launch_assign_grid(const pslot_keypoint *kps, const int *counts, int fixed_n, size_t stride, const GridSpec &s,
+                       int *cell_start, int *indices, int nimages, cudaStream_t st)
+{
+    const size_t smem = grid_smem_bytes(s);
+    cudaFuncSetAttribute(k_assign_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_assign_grid<<<nimages, GT, smem, st>>>(kps, counts, fixed_n, stride, s, cell_start, indices);
+    return 1;
+}
+
+int launch_features_in_area(const pslot_keypoint *kps, const int *cell_start, const int *indices, const GridSpec &s,
+                            const pslot_area_query *queries, int nq, int cap, int *out_count, int *out, cudaStream_t st)
+{
+    k_features_in_area<<<(nq + 7) / 8, 256, 0, st>>>(kps, cell_start, indices, s, queries, nq, cap, out_count, out);
+    return 1;
+}

@@ -89,4 +89,10 @@ int launch_stereo(const Geom &g, const StereoArgs &a, int npairs, int max_n_r, c
 size_t quadtree_smem_bytes(const Geom &g, int *key_cap);
 int launch_gray_ingest(const uint8_t *src, size_t src_image_stride, int channels, int rgb, uint8_t *dst, int w, int h,
                        int dpitch, unsigned long long dstride, int nimages, cudaStream_t st);
+typedef pslot_grid_spec GridSpec;
+size_t grid_smem_bytes(const GridSpec &s);
+int launch_assign_grid(const pslot_keypoint *kps, const int *counts, int fixed_n, size_t stride, const GridSpec &s,
+                       int *cell_start, int *indices, int nimages, cudaStream_t st);
+int launch_features_in_area(const pslot_keypoint *kps, const int *cell_start, const int *indices, const GridSpec &s,
+                            const pslot_area_query *queries, int nq, int cap, int *out_count, int *out, cudaStream_t st);
 void launch_debug_steer(const float *angle_deg, int n, float *a, float *b, cudaStream_t st);

@@ -37,7 +37,15 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle_mod):
     dp = np.frombuffer(raw, np.float32, N, o); o += 4 * N
     pw, ph = struct.unpack_from("<2i", raw, o); o += 8
     p1 = np.frombuffer(raw, np.uint8, pw * ph, o).reshape(ph, pw); o += pw * ph
-    (dd,) = struct.unpack_from("<i", raw, o)
+    (dd,) = struct.unpack_from("<i", raw, o); o += 4
+
+    def read_list():
+        nonlocal o
+        (n,) = struct.unpack_from("<i", raw, o); o += 4
+        v = np.frombuffer(raw, np.int32, n, o); o += 4 * n
+        return v
+    grid = [read_list() for _ in range(64 * 48)]
+    areas = [read_list() for _ in range(6)]
 
     O = oracle_mod
     oL, oR = O.OracleExtractor(*params), O.OracleExtractor(*params)
@@ -50,3 +58,13 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle_mod):
     assert np.allclose(dp, odp, rtol=1e-5, atol=0)
     assert np.array_equal(p1, oL.level(1))  # mvImagePyramid mirror
     assert dd == O.hamming256(odL[0], odL[1])
+    # mGrid (Frame.cc:1636-1655) and GetFeaturesInArea (:1808-1861), host walk and batched device form
+    inv_w, inv_h = float(np.float32(64) / np.float32(W)), float(np.float32(48) / np.float32(H))
+    cs, idx = O.assign_grid(okL, 0.0, 0.0, inv_w, inv_h)
+    for c in range(64 * 48):
+        assert np.array_equal(grid[c], idx[cs[c]:cs[c + 1]])
+    qs = [(W * 0.5, H * 0.5, 40.0, -1, -1), (W * 0.25, H * 0.7, 25.0, 1, 4), (5.0, 5.0, 90.0, 0, -1)]
+    for i, q in enumerate(qs):
+        ref = O.features_in_area(okL, cs, idx, 0.0, 0.0, inv_w, inv_h, 64, 48, *q)
+        assert np.array_equal(areas[i], ref) and np.array_equal(areas[3 + i], ref)
+    assert sum(len(a) for a in areas) > 0
