@@ -33,6 +33,9 @@
 namespace {
 
 constexpr int FW = 4;        // warps (= cells) per CTA
+#ifndef FAST_MIN_BLOCKS
+#define FAST_MIN_BLOCKS 6
+#endif
 // A TMA box must start on a 16-byte boundary of the global row, so the box starts at the aligned x below
 // (cell start - 1); the residual 0..15 byte offset is uniform per warp: a whole-word part folded into the
 // shared-memory word index and a 0..3 byte part S that is removed from the ring rows by funnel shifts.  (Four
@@ -186,7 +189,7 @@ __device__ __forceinline__ void score_pass(const uint32_t *tile32, uint32_t *sco
     }
 }
 
-__global__ void __launch_bounds__(FW * 32, 6)
+__global__ void __launch_bounds__(FW * 32, FAST_MIN_BLOCKS)
 k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet maps,
              int *__restrict__ cell_count, uint32_t *__restrict__ cell_cand, int warp_smem_bytes)
 {

@@ -4,9 +4,9 @@
 //
 // mGrid[i][j] (a vector of keypoint indices per cell, filled by push_back in keypoint order) becomes a CSR table
 // on the device: cell = i * rows + j, cell_start[cols * rows + 1], indices[] ascending inside a cell.
-//   k_assign_grid      one CTA per image: shared-memory histogram of the cell of every keypoint, block scan,
-//                      scatter with shared atomics, then each cell's (tiny) list is put in ascending order -
-//                      the only thing the atomics do not fix; the result is deterministic.
+//   k_assign_grid      one CTA per image: shared-memory histogram of the cell of every keypoint, block scan, then
+//                      a stable scatter (one warp, match.any ranks) that writes each cell's list in ascending
+//                      keypoint order; deterministic.
 //   k_features_in_area one warp per query: the cell rectangle is walked in the reference's order (ix outer, iy
 //                      inner, list order inside a cell) and the hits are compacted with ballots, so the output
 //                      order equals the reference's vIndices.
@@ -29,12 +29,14 @@ constexpr int GT = 256;
 
 __global__ void __launch_bounds__(GT)
 k_assign_grid(const pslot_keypoint *__restrict__ kps, const int *__restrict__ counts, int fixed_n, size_t stride,
-              GridSpec s, int *__restrict__ cell_start, int *__restrict__ indices)
+              GridSpec s, int *__restrict__ cell_start, int *__restrict__ indices, int cache_cap)
 {
     extern __shared__ int sm[];
     const int C = s.cols * s.rows;
     int *start = sm;          // [C + 1]
     int *fill = sm + C + 1;   // [C]
+    // cell of every keypoint (0xFFFF = outside), so that the ordered pass below does not wait on global loads
+    uint16_t *cell_of = reinterpret_cast<uint16_t *>(fill + C); // [cache_cap]; C <= 16384 fits 16 bits
     __shared__ int warp_sums[GT / 32];
 
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -45,9 +47,11 @@ k_assign_grid(const pslot_keypoint *__restrict__ kps, const int *__restrict__ co
 
     for (int c = tid; c <= C; c += GT) start[c] = 0;
     __syncthreads();
+    const bool cached = n <= cache_cap;
     for (int i = tid; i < n; i += GT) {
         const int c = pos_in_grid(k[i], s);
         if (c >= 0) atomicAdd(&start[c + 1], 1);
+        if (cached) cell_of[i] = (uint16_t)c; // -1 -> 0xFFFF
     }
     __syncthreads();
     // inclusive scan of start[1..C] in place: a contiguous chunk per thread, then a scan of the chunk sums
@@ -75,19 +79,28 @@ k_assign_grid(const pslot_keypoint *__restrict__ kps, const int *__restrict__ co
         if (c < C) fill[c] = start[c];
     }
     __syncthreads();
-    for (int i = tid; i < n; i += GT) {
-        const int c = pos_in_grid(k[i], s);
-        if (c >= 0) idx[atomicAdd(&fill[c], 1)] = i;
-    }
-    __syncthreads(); // the block's own global writes are visible to it after the barrier
-    // ascending keypoint index inside each cell == push_back order (:1647-1654); lists are a handful of entries
-    for (int c = tid; c < C; c += GT) {
-        const int a = start[c], b = start[c + 1];
-        for (int i = a + 1; i < b; ++i) {
-            const int v = idx[i];
-            int j = i - 1;
-            while (j >= a && idx[j] > v) { idx[j + 1] = idx[j]; --j; }
-            idx[j + 1] = v;
+    // Stable scatter by ONE warp walking the keypoints in index order, 32 at a time: lanes that share a cell find each
+    // other with match.any, take consecutive slots in lane (= index) order, and the lowest of them advances the cell's
+    // fill pointer.  This reproduces the push_back order (:1647-1654) directly - no atomics, nothing to sort, and no
+    // quadratic behaviour when many keypoints crowd into one cell.
+    if (warp == 0) {
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            int c = -1;
+            if (i < n) {
+                if (cached) { const int v = cell_of[i]; c = v == 0xFFFF ? -1 : v; }
+                else c = pos_in_grid(k[i], s);
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, c);
+            if (c >= 0) {
+                const int leader = __ffs((int)peers) - 1;
+                const int rank = __popc(peers & ((1u << lane) - 1u));
+                const int slot = fill[c] + rank; // every peer reads before the leader writes (warp-synchronous below)
+                __syncwarp(peers);
+                if (lane == leader) fill[c] += __popc(peers);
+                idx[slot] = i;
+            }
+            __syncwarp();
         }
     }
 }
@@ -147,9 +160,14 @@ size_t grid_smem_bytes(const GridSpec &s) { return sizeof(int) * (2 * (size_t)s.
 int launch_assign_grid(const pslot_keypoint *kps, const int *counts, int fixed_n, size_t stride, const GridSpec &s,
                        int *cell_start, int *indices, int nimages, cudaStream_t st)
 {
-    const size_t smem = grid_smem_bytes(s);
+    const size_t tables = grid_smem_bytes(s);
+    // keypoint -> cell cache: room for the largest image of the launch if shared memory allows (else recomputed)
+    const size_t want = counts ? stride : (size_t)fixed_n;
+    const size_t room = (200 * 1024 - tables) / 2;
+    const int cache_cap = (int)(want <= room ? want : 0);
+    const size_t smem = tables + 2 * (size_t)cache_cap + 16;
     cudaFuncSetAttribute(k_assign_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_assign_grid<<<nimages, GT, smem, st>>>(kps, counts, fixed_n, stride, s, cell_start, indices);
+    k_assign_grid<<<nimages, GT, smem, st>>>(kps, counts, fixed_n, stride, s, cell_start, indices, cache_cap);
     return 1;
 }
 

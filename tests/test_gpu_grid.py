@@ -16,7 +16,7 @@ def B():
     return binding
 
 
-@pytest.mark.parametrize("n,seed", [(0, 1), (1, 2), (1500, 3), (9000, 4)])
+@pytest.mark.parametrize("n,seed", [(0, 1), (1, 2), (1500, 3), (9000, 4), (100000, 5)])  # the last exceeds the on-chip cell cache
 def test_assign_grid_random(n, seed, B, oracle_mod):
     W, H = 1241, 376
     e = B.OrbExtractor(1000, 1.2, 8, 20, 7)
