@@ -34,7 +34,7 @@ namespace {
 
 constexpr int FW = 4;        // warps (= cells) per CTA
 #ifndef FAST_MIN_BLOCKS
-#define FAST_MIN_BLOCKS 6
+#define FAST_MIN_BLOCKS 7
 #endif
 // A TMA box must start on a 16-byte boundary of the global row, so the box starts at the aligned x below
 // (cell start - 1); the residual 0..15 byte offset is uniform per warp: a whole-word part folded into the

@@ -7,10 +7,11 @@
 // Integer-only, hence bit-exact.  Levels are chained (each from the previous one, :1120), so a batch
 // needs nlevels-1 dependent launches; each launch covers every slot of the batch.
 //
-// Each CTA produces a 128 x 16 output tile.  The source rectangle it needs (about 156 x 21 bytes at
-// scale 1.2) is staged in shared memory with coalesced 16-byte loads, the 16 row taps are unpacked once
-// into shared memory, and every thread then produces 8 pixels of one column with a branch-free body
-// (one broadcast LDS.128 for the row tap, four byte gathers, four multiply-adds).  A warp covers 32
+// Each CTA produces a 128 x 32 output tile.  The source rectangle it needs (about 156 x 40 bytes at
+// scale 1.2) is staged in shared memory with coalesced 16-byte loads, the 32 row taps are unpacked once
+// into shared memory, and every thread then produces 16 pixels of one column with a branch-free body
+// (one broadcast LDS.128 for the row tap, four byte gathers from two addresses, four multiply-adds, two
+// multiply-highs).  16 rows per thread rather than 8 halves the per-thread set-up per pixel (-12 %).  A warp covers 32
 // consecutive output columns = ~38 consecutive source bytes, so every gather is one conflict-free
 // wavefront.  The finished tile goes back with 16-byte stores.
 //
@@ -20,10 +21,10 @@
 namespace {
 
 constexpr int TW = 128;     // output tile width  (threads.x)
-constexpr int TH = 16;      // output tile height
+constexpr int TH = 32;      // output tile height
 constexpr int TY = 2;       // threads.y; each thread produces TH / TY rows of one column
 constexpr int SRC_W = 208;  // staged source row stride in bytes (13 x 16): 128 * 1.45 + 2 + 15 alignment
-constexpr int SRC_H = 36;   // staged source rows: 16 * 1.45 + 2 and slack
+constexpr int SRC_H = 52;   // staged source rows: 32 * 1.45 + 2 and slack
 constexpr int OUT_S = TW;   // output staging row stride
 
 __global__ void __launch_bounds__(TW *TY)
@@ -56,22 +57,27 @@ k_resize_level(const uint8_t *__restrict__ src, int spitch, unsigned long long s
     }
     if (tid < TH) {
         const ResizeTap t = yt[min(dy0 + tid, dy1)];
-        s_yt[tid] = make_int4(((int)t.s0 - ya) * SRC_W, ((int)t.s1 - ya) * SRC_W, (int)t.c0, (int)t.c1);
+        // row coefficients pre-shifted by 16 so that (c * (h >> 4)) >> 16 is one multiply-high (c <= 2048, h >> 4 < 2^15)
+        s_yt[tid] = make_int4(((int)t.s0 - ya) * SRC_W, ((int)t.s1 - ya) * SRC_W, (int)t.c0 << 16, (int)t.c1 << 16);
     }
     __syncthreads();
 
     {
         const ResizeTap tap = xt[min(dx0 + tx, dx1)];
-        const uint8_t *p0 = s_src + ((int)tap.s0 - xa), *p1 = s_src + ((int)tap.s1 - xa);
-        const int cx0 = tap.c0, cx1 = tap.c1;
+        // the two column taps are adjacent bytes (s1 == s0 + 1) except at the clamped right border (s1 == s0), where
+        // the pair (s0, s0 + 1) with coefficients (c0 + c1, 0) gives the same sum: one address per source row
+        const uint8_t *p0 = s_src + ((int)tap.s0 - xa);
+        const bool adj = tap.s1 != tap.s0;
+        const uint32_t cx0 = adj ? (uint32_t)tap.c0 : (uint32_t)(tap.c0 + tap.c1), cx1 = adj ? (uint32_t)tap.c1 : 0u;
 #pragma unroll
         for (int k = 0; k < TH / TY; ++k) {
             const int r = ty * (TH / TY) + k;
             const int4 t = s_yt[r];
-            const int h0 = (int)p0[t.x] * cx0 + (int)p1[t.x] * cx1;
-            const int h1 = (int)p0[t.y] * cx0 + (int)p1[t.y] * cx1;
+            const uint8_t *a0 = p0 + t.x, *a1 = p0 + t.y;
+            const uint32_t h0 = (uint32_t)a0[0] * cx0 + (uint32_t)a0[1] * cx1;
+            const uint32_t h1 = (uint32_t)a1[0] * cx0 + (uint32_t)a1[1] * cx1;
             // in [0, 255] by construction (coefficients sum to 2048 per axis): no saturation needed
-            const int v = (((t.z * (h0 >> 4)) >> 16) + ((t.w * (h1 >> 4)) >> 16) + 2) >> 2;
+            const uint32_t v = (__umulhi((uint32_t)t.z, h0 >> 4) + __umulhi((uint32_t)t.w, h1 >> 4) + 2u) >> 2;
             s_out[r * OUT_S + tx] = (uint8_t)v;
         }
     }
