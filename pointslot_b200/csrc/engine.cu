@@ -295,12 +295,14 @@ struct Engine {
         off_desc = off_kps + align_up(sizeof(pslot_keypoint) * ns * K, 256);
         out_bytes = off_desc + align_up(32 * ns * K, 256);
         CU(cudaMalloc(&d_out, out_bytes));
+        CU(cudaMemset(d_out, 0, out_bytes)); // result rows are copied out at full capacity; the unused tail reads as zeros
         CU(cudaMemset(d_out, 0, out_bytes));
         d_out_count = (int *)d_out;
         d_out_kps = (pslot_keypoint *)(d_out + off_kps);
         d_out_desc = (uint8_t *)(d_out + off_desc);
         const size_t np = std::max<size_t>(ns / 2, 1);
         CU(cudaMalloc(&d_uright, 4 * np * K)); CU(cudaMalloc(&d_depth, 4 * np * K));
+        CU(cudaMemset(d_uright, 0, 4 * np * K)); CU(cudaMemset(d_depth, 0, 4 * np * K));
         CU(cudaMalloc(&d_best_dist, 4 * np * K)); CU(cudaMalloc(&d_best_idx, 4 * np * K)); CU(cudaMalloc(&d_sad, 4 * np * K));
         W = w; H = h; S = nslots;
         return PSLOT_OK;
@@ -1024,7 +1026,10 @@ int pslot_batch_assign_grid(pslot_batch *b, const pslot_grid_spec *spec, int32_t
     CU(cudaSetDevice(E.device));
     const int C = spec->cols * spec->rows, np = b->last_pairs;
     const size_t K = (size_t)E.g.kp_cap_total;
-    if (!b->d_gidx) CU(cudaMalloc(&b->d_gidx, sizeof(int) * K * (size_t)b->max_pairs));
+    if (!b->d_gidx) {
+        CU(cudaMalloc(&b->d_gidx, sizeof(int) * K * (size_t)b->max_pairs));
+        CU(cudaMemset(b->d_gidx, 0, sizeof(int) * K * (size_t)b->max_pairs));
+    }
     if (C + 1 > b->gcs_cells) {
         CU(cudaStreamSynchronize(E.st));
         cudaFree(b->d_gcs);

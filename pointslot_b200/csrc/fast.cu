@@ -269,7 +269,9 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
             list = glist;
             count = nlist;
         }
-        // exact scores: listed groups in phase A, every group in phase B
+        // exact scores: listed groups in phase A, every group in phase B (whose writes must not overtake the reads of
+        // phase A's maxima test)
+        __syncwarp();
         score_pass(tile32, score32, TSW, wsh, sh0 & 3, lane, list, count, gshift, iw);
         __syncwarp();
         if (phase == 1) {

@@ -72,6 +72,35 @@ k_gray_ingest(const uint8_t *__restrict__ src, size_t src_image_stride, size_t l
     }
 }
 
+// Gray input: plain re-pitch of tightly packed rows into the padded level-0 rows, 16 pixels per thread (five
+// aligned source words re-aligned with funnel shifts, one 16-byte store: destination rows are 128-byte aligned).
+__global__ void __launch_bounds__(128)
+k_gray_repitch(const uint8_t *__restrict__ src, size_t src_image_stride, size_t limit, uint8_t *__restrict__ dst, int w,
+               int h, int dpitch, unsigned long long dstride)
+{
+    // threads are flattened over (row, group of 16 pixels) so that no lane idles on the ragged row end
+    const int groups = (w + 15) >> 4;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= groups * h) return;
+    const int y = idx / groups, x0 = (idx - y * groups) * 16;
+    const size_t off = (size_t)blockIdx.z * src_image_stride + (size_t)y * w + x0;
+    const size_t a = off & ~(size_t)3;
+    const int sh = (int)(off - a) * 8;
+    uint32_t v[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) v[i] = load_word_safe(src, a + 4 * i, limit);
+    uint4 q;
+    q.x = __funnelshift_r(v[0], v[1], sh); q.y = __funnelshift_r(v[1], v[2], sh);
+    q.z = __funnelshift_r(v[2], v[3], sh); q.w = __funnelshift_r(v[3], v[4], sh);
+    uint8_t *o = dst + (size_t)blockIdx.z * dstride + (size_t)y * dpitch + x0;
+    if (x0 + 15 < w) {
+        *reinterpret_cast<uint4 *>(o) = q;
+    } else { // row tail: do not spill the next row's pixels into the padding
+        const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+        for (int i = 0; x0 + i < w; ++i) o[i] = (uint8_t)(qq[i >> 2] >> (8 * (i & 3)));
+    }
+}
+
 } // namespace
 
 int launch_gray_ingest(const uint8_t *src, size_t src_image_stride, int channels, int rgb, uint8_t *dst, int w, int h,
@@ -81,7 +110,8 @@ int launch_gray_ingest(const uint8_t *src, size_t src_image_stride, int channels
     dim3 grid(((w + 3) / 4 + 255) / 256, h, nimages);
     const size_t limit = (size_t)(nimages - 1) * src_image_stride + (size_t)w * h * channels; // end of the last image
     if (channels == 1)
-        k_gray_ingest<1><<<grid, block, 0, st>>>(src, src_image_stride, limit, dst, w, h, dpitch, dstride, rgb);
+        k_gray_repitch<<<dim3((((w + 15) / 16) * h + 127) / 128, 1, nimages), 128, 0, st>>>(src, src_image_stride, limit,
+                                                                                          dst, w, h, dpitch, dstride);
     else if (channels == 3)
         k_gray_ingest<3><<<grid, block, 0, st>>>(src, src_image_stride, limit, dst, w, h, dpitch, dstride, rgb);
     else
