@@ -120,19 +120,18 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
     // which keypoint: global index over the per-level capacity segments
     int idx = blockIdx.x * DW + warp;
     if (idx >= g.lkp_per_slot) return;
-    int l = 0;
-    while (l + 1 < g.nlevels && idx >= g.lv[l + 1].kp_base) ++l;
+    // level of this keypoint slot and the output offset of its level, lane-parallel over the (<= 16) levels: lane k
+    // looks at level k, a ballot / two reductions replace the dependent scans
+    const bool at_or_below = lane < g.nlevels && idx >= g.lv[min(lane, g.nlevels - 1)].kp_base; // kp_base ascending, [0] = 0
+    const int l = __popc(__ballot_sync(0xffffffffu, at_or_below)) - 1;
     const LevelGeom &L = g.lv[l];
     const int i = idx - L.kp_base;
     const int *cnt = lkp_count + (size_t)slot * g.nlevels;
-    int out_base = 0, total = 0;
-    for (int k = 0; k < g.nlevels; ++k) {
-        const int c = cnt[k];
-        if (k < l) out_base += c;
-        total += c;
-    }
+    const int c_lane = lane < g.nlevels ? cnt[lane] : 0;
+    const int out_base = __reduce_add_sync(0xffffffffu, lane < l ? c_lane : 0);
+    const int total = __reduce_add_sync(0xffffffffu, c_lane);
     if (idx == 0 && lane == 0) out_count[slot] = total;
-    if (i >= cnt[l]) return;
+    if (i >= __shfl_sync(0xffffffffu, c_lane, l)) return;
 
     const uint32_t kp = lkp[(size_t)slot * g.lkp_per_slot + idx];
     const int kx = pslot_px(kp), ky = pslot_py(kp), kr = pslot_pr(kp);

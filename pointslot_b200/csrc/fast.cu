@@ -200,8 +200,8 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
     const int slot = blockIdx.y;
     int cell = blockIdx.x * FW + warp;
     if (cell >= g.cells_per_slot) return;
-    int l = 0;
-    while (l + 1 < g.nlevels && cell >= g.lv[l + 1].cell_base) ++l;
+    // level of this cell: lane k looks at level k (cell_base ascending, [0] = 0), one ballot instead of a dependent scan
+    const int l = __popc(__ballot_sync(0xffffffffu, lane < g.nlevels && cell >= g.lv[min(lane, g.nlevels - 1)].cell_base)) - 1;
     const LevelGeom &L = g.lv[l];
     cell -= L.cell_base;
     // cell / n_cols without the integer-division sequence: (cell + 0.5) / n lies at least 1 / (2 n) away from an

@@ -8,7 +8,7 @@ ROOT = Path(__file__).resolve().parents[1]
 G, P = ROOT / "gpurun_out", ROOT / "profiles"
 pre = sys.argv[1] if len(sys.argv) > 1 else "r01"
 KERNELS = {"fast": "k_fast_cells", "describe": "k_describe", "pyramid_level1": "k_resize_level", "quadtree": "k_quadtree",
-           "stereo_match": "k_stereo_match", "ingest": "k_gray_ingest"}
+           "stereo_match": "k_stereo_match", "ingest": "k_gray_repitch"}
 
 shutil.copy(G / "bench.json", P / f"{pre}_bench.json")
 shutil.copy(G / "bench_reference.json", P / f"{pre}_bench_reference.json")
@@ -21,7 +21,7 @@ for name, k in KERNELS.items():
     txt = subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_summary.py"), str(rep), "--source", "25", "--ops"],
                          capture_output=True, text=True).stdout
     short = {"fast": "k_fast", "describe": "k_describe", "pyramid_level1": "k_resize", "quadtree": "k_quadtree",
-             "stereo_match": "k_stereo_match", "ingest": "k_gray_ingest"}[name]
+             "stereo_match": "k_stereo_match", "ingest": "k_gray_repitch"}[name]
     (P / f"{pre}_ncu_{short}.txt").write_text(txt)
     raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
