@@ -137,6 +137,30 @@ int pslot_features_in_area(pslot_orb *ctx, const pslot_area_query *queries, int 
                            int32_t *indices);
 
 /* ---------------------------------------------------------------------------------------------
+ * Local-map projection search — int ORBmatcher::SearchByProjection(Frame &F, const
+ * vector<MapPoint*> &vpMapPoints, const float th) (include/ORBmatcher.h, src/ORBmatcher.cc:68-155), called by
+ * Tracking::SearchLocalPoints (src/Tracking.cc:3354).
+ * The frame side is what pslot_assign_grid left on ctx (mvKeysUn + mGrid) plus the arrays below; a map point is the
+ * set of MapPoint fields the routine reads (include/MapPoint.h:110-120). */
+typedef struct pslot_map_point {
+    float proj_x, proj_y, proj_xr, view_cos; /* mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos */
+    int32_t level;                           /* mnTrackScaleLevel */
+    int32_t flags;                           /* bit 0: mbTrackInView && !isBad()  (searched at all)
+                                                bit 1: Observations() > 0        (its match blocks later points) */
+} pslot_map_point;
+/* mp_desc [n_mp*32] = pMP->GetDescriptor(); frame_desc [n*32] = F.mDescriptors, u_right [n] = F.mvuRight,
+ * occupied [n] (may be NULL) != 0 where F.mvpMapPoints[idx] already holds a point with Observations() > 0;
+ * n must equal the keypoint count of the last pslot_assign_grid; scale_factors [nlevels] = F.mvScaleFactors;
+ * nn_ratio = mfNNratio.  match_of_mp[i] receives the feature index assigned to map point i (the reference's
+ * F.mvpMapPoints[bestIdx] = pMP, to be applied in map-point order) or -1; *nmatches the return value. */
+int pslot_search_by_projection(pslot_orb *ctx, const pslot_map_point *mps, const uint8_t *mp_desc, int n_mp,
+                               const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n,
+                               const float *scale_factors, int nlevels, float th, float nn_ratio,
+                               int32_t *match_of_mp, int *nmatches);
+/* Number of device sweeps the last pslot_search_by_projection needed to reproduce the sequential result (>= 2). */
+int pslot_debug_projection_sweeps(const pslot_orb *ctx);
+
+/* ---------------------------------------------------------------------------------------------
  * Throughput API — independent stereo pairs of one geometry, processed `max_pairs` at a time on one
  * GPU stream: both extractions (Frame.cc:161-164) + ComputeStereoMatches (:173) per pair, with no
  * host round trip in between.  This is the data-parallel form of the Frame stereo constructor path

@@ -81,6 +81,8 @@ def lib():
         L.orc_assign_grid.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp]
         L.orc_features_in_area.argtypes = [vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
                                            C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, vp]
+        L.orc_search_by_projection.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float,
+                                               C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_float, C.c_float, vp]
         L.orc_distribute_octtree.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_int, vp, vp, vp, ip]
         _lib = L
@@ -181,6 +183,25 @@ def features_in_area(kps, cell_start, indices, min_x, min_y, inv_w, inv_h, cols,
     n = lib().orc_features_in_area(_ptr(kps), _ptr(cell_start), _ptr(indices), min_x, min_y, inv_w, inv_h, cols, rows,
                                    x, y, r, min_level, max_level, len(out), _ptr(out))
     return out[:n].copy()
+
+
+MAP_POINT_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"),
+                            ("level", "<i4"), ("flags", "<i4")])
+
+
+def search_by_projection(kps_un, frame_desc, u_right, cell_start, indices, min_x, min_y, inv_w, inv_h, cols, rows,
+                         mps, mp_desc, occupied, scale_factors, th, nn_ratio):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th) (ORBmatcher.cc:68-155) -> (match_of_mp [n_mp], nmatches)."""
+    kps_un = np.ascontiguousarray(kps_un, KEYPOINT_DTYPE); frame_desc = np.ascontiguousarray(frame_desc, np.uint8)
+    u_right = np.ascontiguousarray(u_right, np.float32); mps = np.ascontiguousarray(mps, MAP_POINT_DTYPE)
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8); occupied = np.ascontiguousarray(occupied, np.uint8)
+    cell_start = np.ascontiguousarray(cell_start, np.int32); indices = np.ascontiguousarray(indices, np.int32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    out = np.full(max(len(mps), 1), -1, np.int32)
+    n = lib().orc_search_by_projection(_ptr(kps_un), _ptr(frame_desc), _ptr(u_right), len(kps_un), _ptr(cell_start),
+                                       _ptr(indices), min_x, min_y, inv_w, inv_h, cols, rows, _ptr(mps), _ptr(mp_desc),
+                                       len(mps), _ptr(occupied), _ptr(sf), th, nn_ratio, _ptr(out))
+    return out[:len(mps)].copy(), int(n)
 
 
 # ---------------------------------------------------------------------------------------------

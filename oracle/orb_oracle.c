@@ -982,3 +982,64 @@ int orc_features_in_area(const orc_keypoint *kps, const int *cell_start, const i
             }
     return n;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th)
+ * (ORBmatcher.cc:68-155; RadiusByViewingCos :252-258; TH_HIGH = 100 :58), SURVEY.md 8f row 3 — the local-map
+ * search of Tracking::SearchLocalPoints (Tracking.cc:3354).  The MapPoint / Frame objects are flattened into the
+ * plain fields the routine reads; the loop below is the reference's, statement for statement, including its
+ * order dependence (a feature taken by an earlier map point with observations is skipped by later ones).
+ * ------------------------------------------------------------------------------------------------------------ */
+int orc_search_by_projection(const orc_keypoint *kps_un, const uint8_t *frame_desc, const float *u_right, int n,
+                             const int *cell_start, const int *indices, float min_x, float min_y, float inv_w,
+                             float inv_h, int cols, int rows, const orc_map_point *mps, const uint8_t *mp_desc,
+                             int n_mp, const uint8_t *occupied, const float *scale_factors, float th, float nn_ratio,
+                             int *match_of_mp)
+{
+    int nmatches = 0;
+    const int bFactor = th != 1.0;
+    uint8_t *blocked = (uint8_t *)malloc((size_t)(n > 0 ? n : 1)); /* F.mvpMapPoints[idx] && Observations() > 0 */
+    int *tmp = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; ++i) blocked[i] = occupied ? occupied[i] : 0;
+    for (int iMP = 0; iMP < n_mp; ++iMP) {
+        const orc_map_point *pMP = &mps[iMP];
+        match_of_mp[iMP] = -1;
+        if (!(pMP->flags & 1)) continue; /* !mbTrackInView || isBad() (:76-81) */
+        const int nPredictedLevel = pMP->level;
+        float r = ((double)pMP->view_cos > 0.998) ? 2.5f : 4.0f; /* RadiusByViewingCos (:252-258) */
+        if (bFactor) r *= th;
+        const float rad = r * scale_factors[nPredictedLevel];
+        const int nc = orc_features_in_area(kps_un, cell_start, indices, min_x, min_y, inv_w, inv_h, cols, rows,
+                                            pMP->proj_x, pMP->proj_y, rad, nPredictedLevel - 1, nPredictedLevel, n, tmp);
+        if (nc == 0) continue;
+        const uint8_t *MPdescriptor = mp_desc + (size_t)iMP * 32;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int v = 0; v < nc; ++v) {
+            const int idx = tmp[v];
+            if (blocked[idx]) continue; /* (:111-113) */
+            if (u_right[idx] > 0) {
+                const float er = fabsf(pMP->proj_xr - u_right[idx]);
+                if (er > r * scale_factors[nPredictedLevel]) continue;
+            }
+            const int dist = orc_hamming256(MPdescriptor, frame_desc + (size_t)idx * 32);
+            if (dist < bestDist) {
+                bestDist2 = bestDist;
+                bestDist = dist;
+                bestLevel2 = bestLevel;
+                bestLevel = kps_un[idx].octave;
+                bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = kps_un[idx].octave;
+                bestDist2 = dist;
+            }
+        }
+        if (bestDist <= 100) { /* TH_HIGH */
+            if (bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) continue;
+            match_of_mp[iMP] = bestIdx; /* F.mvpMapPoints[bestIdx] = pMP (:148) */
+            if (pMP->flags & 2) blocked[bestIdx] = 1; /* pMP->Observations() > 0: later map points skip this feature */
+            nmatches++;
+        }
+    }
+    free(blocked); free(tmp);
+    return nmatches;
+}

@@ -99,6 +99,21 @@ int orc_features_in_area(const orc_keypoint *kps, const int *cell_start, const i
                          float inv_w, float inv_h, int cols, int rows, float x, float y, float r, int min_level,
                          int max_level, int cap, int *out);
 
+/* the MapPoint fields ORBmatcher::SearchByProjection reads (MapPoint.h:110-120) */
+typedef struct orc_map_point {
+    float proj_x, proj_y, proj_xr, view_cos; /* mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos */
+    int32_t level;                           /* mnTrackScaleLevel */
+    int32_t flags;                           /* bit 0: mbTrackInView && !isBad(); bit 1: Observations() > 0 */
+} orc_map_point;
+/* ORBmatcher::SearchByProjection(F, vpMapPoints, th) (ORBmatcher.cc:68-155) on the CSR grid of orc_assign_grid;
+ * occupied[idx] != 0 where F.mvpMapPoints[idx] already holds a point with observations; match_of_mp[i] = bestIdx
+ * of map point i or -1; returns nmatches */
+int orc_search_by_projection(const orc_keypoint *kps_un, const uint8_t *frame_desc, const float *u_right, int n,
+                             const int *cell_start, const int *indices, float min_x, float min_y, float inv_w,
+                             float inv_h, int cols, int rows, const orc_map_point *mps, const uint8_t *mp_desc,
+                             int n_mp, const uint8_t *occupied, const float *scale_factors, float th, float nn_ratio,
+                             int *match_of_mp);
+
 #ifdef __cplusplus
 }
 #endif

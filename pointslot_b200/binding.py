@@ -30,6 +30,7 @@ ABI_SYMBOLS = [
     "pslot_batch_submit", "pslot_batch_submit_color", "pslot_batch_wait", "pslot_batch_kernel_launches", "pslot_batch_device_out",
     "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats",
     "pslot_assign_grid", "pslot_features_in_area", "pslot_batch_assign_grid",
+    "pslot_search_by_projection", "pslot_debug_projection_sweeps",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
 ]
 
@@ -53,6 +54,8 @@ class GridSpec(C.Structure):
                    cols, rows)
 
 
+MAP_POINT_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"),
+                            ("level", "<i4"), ("flags", "<i4")])  # pslot_map_point
 AREA_QUERY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("r", "<f4"), ("min_level", "<i4"), ("max_level", "<i4")])
 
 
@@ -89,6 +92,9 @@ def lib():
     L.pslot_assign_grid.argtypes = [vp, vp, C.c_int, C.POINTER(GridSpec), vp, vp, C.POINTER(C.c_int)]
     L.pslot_features_in_area.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
     L.pslot_batch_assign_grid.argtypes = [vp, C.POINTER(GridSpec), vp, vp]
+    L.pslot_search_by_projection.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, C.c_float,
+                                             C.c_float, vp, C.POINTER(C.c_int)]
+    L.pslot_debug_projection_sweeps.argtypes = [vp]
     L.pslot_batch_create.argtypes = [C.POINTER(vp), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, vp]
     L.pslot_batch_destroy.argtypes = [vp]
@@ -242,6 +248,23 @@ def features_in_area(ext: OrbExtractor, queries, cap: int):
     if nq and counts[:nq].max() > cap:
         raise PslotError(-2, f"area query found {int(counts[:nq].max())} features, cap is {cap}")
     return [out[q, :counts[q]].copy() for q in range(nq)]
+
+
+def search_by_projection(ext: OrbExtractor, mps, mp_desc, frame_desc, u_right, occupied, scale_factors, th: float,
+                         nn_ratio: float):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th) (reference src/ORBmatcher.cc:68-155) against the frame whose
+    undistorted keypoints were last passed to assign_grid on `ext` -> (match_of_mp [n_mp] feature index or -1,
+    nmatches, device sweeps)."""
+    mps = np.ascontiguousarray(mps, MAP_POINT_DTYPE); mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+    frame_desc = np.ascontiguousarray(frame_desc, np.uint8); u_right = np.ascontiguousarray(u_right, np.float32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    out = np.full(max(len(mps), 1), -1, np.int32)
+    nm = C.c_int(0)
+    _check(lib().pslot_search_by_projection(ext._h, _p(mps), _p(mp_desc), len(mps), _p(frame_desc), _p(u_right),
+                                            None if occ is None else _p(occ), len(u_right), _p(sf), len(sf), th, nn_ratio,
+                                            _p(out), C.byref(nm)))
+    return out[:len(mps)].copy(), nm.value, lib().pslot_debug_projection_sweeps(ext._h)
 
 
 def stereo_match(ext_l: OrbExtractor, ext_r: OrbExtractor, kL, dL, kR, dR, bf: float, max_d: float, debug=False):

@@ -364,11 +364,16 @@ struct pslot_orb {
     size_t qout_cap = 0;
     int grid_n = -1;
     pslot_grid_spec grid_spec = {};
+    // projection search scratch (pslot_search_by_projection)
+    void *d_proj = nullptr;
+    size_t proj_bytes = 0;
+    int last_sweeps = 0;
 
     ~pslot_orb()
     {
         free_stereo();
         cudaFree(d_gk); cudaFree(d_gidx); cudaFree(d_gcs); cudaFree(d_qcount); cudaFree(d_qout); cudaFree(d_q);
+        cudaFree(d_proj);
         cudaFree(d_cstage);
         if (h_stage) cudaFreeHost(h_stage);
     }
@@ -1016,6 +1021,88 @@ int pslot_features_in_area(pslot_orb *ctx, const pslot_area_query *queries, int 
     CU(cudaStreamSynchronize(st));
     return PSLOT_OK;
 }
+
+int pslot_search_by_projection(pslot_orb *ctx, const pslot_map_point *mps, const uint8_t *mp_desc, int n_mp,
+                               const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n,
+                               const float *scale_factors, int nlevels, float th, float nn_ratio,
+                               int32_t *match_of_mp, int *nmatches)
+{
+    if (!ctx) return fail(PSLOT_ERR_ARG, "ctx is null");
+    if (ctx->grid_n < 0) return fail(PSLOT_ERR_STATE, "pslot_assign_grid has not been called on this context");
+    if (n != ctx->grid_n) return fail(PSLOT_ERR_ARG, "n (%d) differs from the gridded keypoint count (%d)", n, ctx->grid_n);
+    if (n_mp < 0 || (n_mp > 0 && (!mps || !mp_desc || !match_of_mp)) || (n > 0 && (!frame_desc || !u_right)))
+        return fail(PSLOT_ERR_ARG, "null array");
+    if (!scale_factors || nlevels < 1 || nlevels > PSLOT_MAX_LEVELS) return fail(PSLOT_ERR_ARG, "bad scale factor table");
+    if (nmatches) *nmatches = 0;
+    if (n_mp == 0) return PSLOT_OK;
+    for (int i = 0; i < n_mp; ++i)
+        if ((mps[i].flags & 1) && (mps[i].level < 0 || mps[i].level >= nlevels))
+            return fail(PSLOT_ERR_ARG, "map point %d: predicted level %d out of range", i, mps[i].level);
+    if (n == 0) { // no features: nothing can match
+        for (int i = 0; i < n_mp; ++i) match_of_mp[i] = -1;
+        return PSLOT_OK;
+    }
+    Engine &E = ctx->E;
+    CU(cudaSetDevice(E.device));
+    // one scratch block: map points | their descriptors | frame descriptors | uRight | occupied | 2 claim arrays |
+    // 2 match arrays | changed flag
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_mp = take(sizeof(pslot_map_point) * (size_t)n_mp), o_md = take(32 * (size_t)n_mp);
+    const size_t o_fd = take(32 * (size_t)n), o_ur = take(4 * (size_t)n), o_oc = take((size_t)n);
+    const size_t o_c0 = take(4 * (size_t)n), o_c1 = take(4 * (size_t)n);
+    const size_t o_m0 = take(4 * (size_t)n_mp), o_m1 = take(4 * (size_t)n_mp), o_ch = take(4);
+    if (off > ctx->proj_bytes) {
+        cudaFree(ctx->d_proj);
+        ctx->d_proj = nullptr; ctx->proj_bytes = 0;
+        CU(cudaMalloc(&ctx->d_proj, off));
+        ctx->proj_bytes = off;
+    }
+    uint8_t *base = (uint8_t *)ctx->d_proj;
+    cudaStream_t st = E.st;
+    CU(cudaMemcpyAsync(base + o_mp, mps, sizeof(pslot_map_point) * (size_t)n_mp, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_md, mp_desc, 32 * (size_t)n_mp, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_fd, frame_desc, 32 * (size_t)n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_ur, u_right, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (occupied) CU(cudaMemcpyAsync(base + o_oc, occupied, (size_t)n, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemsetAsync(base + o_oc, 0, (size_t)n, st));
+    int *claim[2] = {(int *)(base + o_c0), (int *)(base + o_c1)};
+    int *match[2] = {(int *)(base + o_m0), (int *)(base + o_m1)};
+    CU(cudaMemsetAsync(claim[0], 0x7f, 4 * (size_t)n, st));  // "no map point has claimed this feature"
+    CU(cudaMemsetAsync(match[0], 0xfe, 4 * (size_t)n_mp, st)); // differs from every possible match: the first sweep counts as a change
+    ProjArgs a{};
+    a.kps = ctx->d_gk; a.cell_start = ctx->d_gcs; a.indices = ctx->d_gidx; a.s = ctx->grid_spec;
+    a.mps = (const pslot_map_point *)(base + o_mp); a.mp_desc = base + o_md; a.n_mp = n_mp;
+    a.frame_desc = base + o_fd; a.u_right = (const float *)(base + o_ur); a.occupied = base + o_oc;
+    a.changed = (int *)(base + o_ch);
+    for (int l = 0; l < nlevels; ++l) a.scale_factors[l] = scale_factors[l];
+    a.th = th; a.nn_ratio = nn_ratio;
+    int cur = 0, sweeps = 0;
+    for (;; ++sweeps) {
+        if (sweeps > n_mp + 1) return fail(PSLOT_ERR_STATE, "projection search did not converge"); // cannot happen: see grid.cu
+        a.claim_prev = claim[cur]; a.claim_next = claim[cur ^ 1];
+        a.match_prev = match[cur]; a.match_next = match[cur ^ 1];
+        CU(cudaMemsetAsync(a.claim_next, 0x7f, 4 * (size_t)n, st));
+        CU(cudaMemsetAsync(a.changed, 0, 4, st));
+        launch_search_by_projection(a, st);
+        CU(cudaGetLastError());
+        int changed = 0;
+        CU(cudaMemcpyAsync(&changed, a.changed, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        cur ^= 1;
+        if (!changed) break;
+    }
+    CU(cudaMemcpy(match_of_mp, match[cur], 4 * (size_t)n_mp, cudaMemcpyDeviceToHost));
+    if (nmatches) {
+        int c = 0;
+        for (int i = 0; i < n_mp; ++i) c += match_of_mp[i] >= 0;
+        *nmatches = c;
+    }
+    ctx->last_sweeps = sweeps + 1;
+    return PSLOT_OK;
+}
+
+int pslot_debug_projection_sweeps(const pslot_orb *ctx) { return ctx ? ctx->last_sweeps : fail(PSLOT_ERR_ARG, "ctx is null"); }
 
 int pslot_batch_assign_grid(pslot_batch *b, const pslot_grid_spec *spec, int32_t *cell_start, int32_t *indices)
 {

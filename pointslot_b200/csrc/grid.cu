@@ -11,6 +11,8 @@
 //   k_features_in_area one warp per query: the cell rectangle is walked in the reference's order (ix outer, iy
 //                      inner, list order inside a cell) and the hits are compacted with ballots, so the output
 //                      order equals the reference's vIndices.
+//   k_search_by_projection  ORBmatcher::SearchByProjection (local-map variant) on top of the
+//                      same window walk; see the kernel's comment for how the reference's order dependence is kept.
 // Float arithmetic as the reference writes it, products and differences kept separate (no FMA).
 // Bound: latency / HBM (28 B read + 4 B written per keypoint); algorithmic bytes = n_k * 32 + 4 * (cols * rows + 1).
 #include "pslot_internal.h"
@@ -24,6 +26,25 @@ __device__ __forceinline__ int pos_in_grid(const pslot_keypoint &kp, const GridS
     const float ry = roundf(__fmul_rn(__fsub_rn(kp.y, s.min_y), s.inv_h));
     if (!(rx >= 0.0f && rx < (float)s.cols && ry >= 0.0f && ry < (float)s.rows)) return -1; // (:2033)
     return (int)rx * s.rows + (int)ry;
+}
+
+// cell rectangle of a search window (:1813-1827); the float -> int conversions are clamped first (the reference's are
+// undefined out of range)
+struct AreaCells { int x0, x1, y0, y1; bool ok; };
+__device__ __forceinline__ AreaCells area_cells(const GridSpec &s, float x, float y, float r)
+{
+    const float big = 1.0e9f;
+    const float fx0 = floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, s.min_x), r), s.inv_w));
+    const float fx1 = ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, s.min_x), r), s.inv_w));
+    const float fy0 = floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, s.min_y), r), s.inv_h));
+    const float fy1 = ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, s.min_y), r), s.inv_h));
+    AreaCells A;
+    A.x0 = max(0, (int)fminf(fmaxf(fx0, -big), big));
+    A.x1 = min(s.cols - 1, (int)fminf(fmaxf(fx1, -big), big));
+    A.y0 = max(0, (int)fminf(fmaxf(fy0, -big), big));
+    A.y1 = min(s.rows - 1, (int)fminf(fmaxf(fy1, -big), big));
+    A.ok = A.x0 < s.cols && A.x1 >= 0 && A.y0 < s.rows && A.y1 >= 0 && fx0 == fx0 && fx1 == fx1 && fy0 == fy0 && fy1 == fy1;
+    return A;
 }
 
 constexpr int GT = 256;
@@ -116,18 +137,9 @@ k_features_in_area(const pslot_keypoint *__restrict__ kps, const int *__restrict
     const pslot_area_query Q = queries[q];
     const float x = Q.x, y = Q.y, r = Q.r;
     int n = 0;
-    // (:1813-1827); the float -> int conversions are clamped first (the reference's are undefined out of range)
-    const float big = 1.0e9f;
-    const float fx0 = floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, s.min_x), r), s.inv_w));
-    const float fx1 = ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, s.min_x), r), s.inv_w));
-    const float fy0 = floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, s.min_y), r), s.inv_h));
-    const float fy1 = ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, s.min_y), r), s.inv_h));
-    const int nMinCellX = max(0, (int)fminf(fmaxf(fx0, -big), big));
-    const int nMaxCellX = min(s.cols - 1, (int)fminf(fmaxf(fx1, -big), big));
-    const int nMinCellY = max(0, (int)fminf(fmaxf(fy0, -big), big));
-    const int nMaxCellY = min(s.rows - 1, (int)fminf(fmaxf(fy1, -big), big));
-    const bool ok = nMinCellX < s.cols && nMaxCellX >= 0 && nMinCellY < s.rows && nMaxCellY >= 0 && fx0 == fx0 &&
-                    fx1 == fx1 && fy0 == fy0 && fy1 == fy1;
+    const AreaCells A = area_cells(s, x, y, r);
+    const int nMinCellX = A.x0, nMaxCellX = A.x1, nMinCellY = A.y0, nMaxCellY = A.y1;
+    const bool ok = A.ok;
     if (ok) {
         const bool check_levels = Q.min_level > 0 || Q.max_level >= 0;
         int *o = out + (size_t)q * cap;
@@ -154,7 +166,93 @@ k_features_in_area(const pslot_keypoint *__restrict__ kps, const int *__restrict
     if (lane == 0) out_count[q] = n;
 }
 
+// ORBmatcher::SearchByProjection(F, vpMapPoints, th) (reference src/ORBmatcher.cc:68-155), one warp per map point.
+// The reference loop is order dependent: once a map point with observations has been written into
+// F.mvpMapPoints[bestIdx] (:148), later map points skip that feature (:111-113).  Restated as a fixed point: a sweep
+// computes every map point's match with "feature idx is taken for map point i" <=> occupied[idx] or some map point
+// j < i with observations matched idx in the PREVIOUS sweep (claim_prev[idx] = the smallest such j).  Map point 0 is
+// right after one sweep, map point k after k + 1 at the latest, and a sweep that changes no match is the sequential
+// result; in practice the dependency chains are a few links long.  Inside a map point the candidates are visited
+// in the reference's order (GetFeaturesInArea order), 32 at a time: distances in parallel, then the best / second-best
+// bookkeeping replayed in order, because bestLevel2 depends on the visiting order among equal distances.
+__global__ void __launch_bounds__(256)
+k_search_by_projection(const __grid_constant__ ProjArgs a)
+{
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= a.n_mp) return;
+    const pslot_map_point P = a.mps[i];
+    int match = -1;
+    if (P.flags & 1) { // mbTrackInView && !isBad() (:76-81)
+        const int nPredictedLevel = P.level;
+        float r = ((double)P.view_cos > 0.998) ? 2.5f : 4.0f; // RadiusByViewingCos (:252-258)
+        if (a.th != 1.0f) r = __fmul_rn(r, a.th);
+        const float rad = __fmul_rn(r, a.scale_factors[nPredictedLevel]);
+        const uint4 *md = reinterpret_cast<const uint4 *>(a.mp_desc + (size_t)i * 32);
+        const uint4 m0 = __ldg(md), m1 = __ldg(md + 1);
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        const AreaCells A = area_cells(a.s, P.proj_x, P.proj_y, rad);
+        if (A.ok) {
+            const int minLevel = nPredictedLevel - 1, maxLevel = nPredictedLevel; // maxLevel >= 0: levels are checked
+            for (int ix = A.x0; ix <= A.x1; ++ix) {
+                const int c0 = a.cell_start[ix * a.s.rows + A.y0], c1 = a.cell_start[ix * a.s.rows + A.y1 + 1];
+                for (int base = c0; base < c1; base += 32) {
+                    const int j = base + lane;
+                    bool use = false;
+                    int idx = 0, dist = 0, oct = 0;
+                    if (j < c1) {
+                        idx = a.indices[j];
+                        const pslot_keypoint kp = a.kps[idx];
+                        oct = kp.octave;
+                        // GetFeaturesInArea (:1837-1852)
+                        use = !(oct < minLevel || oct > maxLevel) && fabsf(__fsub_rn(kp.x, P.proj_x)) < rad &&
+                              fabsf(__fsub_rn(kp.y, P.proj_y)) < rad;
+                        // F.mvpMapPoints[idx] with observations (:111-113), as of the previous sweep
+                        use = use && !(a.occupied[idx] || a.claim_prev[idx] < i);
+                        if (use) {
+                            const float ur = a.u_right[idx];
+                            if (ur > 0) use = !(fabsf(__fsub_rn(P.proj_xr, ur)) > rad); // (:115-120)
+                        }
+                        if (use) {
+                            const uint4 *fd = reinterpret_cast<const uint4 *>(a.frame_desc + (size_t)idx * 32);
+                            const uint4 f0 = __ldg(fd), f1 = __ldg(fd + 1);
+                            dist = __popc(m0.x ^ f0.x) + __popc(m0.y ^ f0.y) + __popc(m0.z ^ f0.z) + __popc(m0.w ^ f0.w) +
+                                   __popc(m1.x ^ f1.x) + __popc(m1.y ^ f1.y) + __popc(m1.z ^ f1.z) + __popc(m1.w ^ f1.w);
+                        }
+                    }
+                    // replay (:126-140) over the usable candidates in visiting order
+                    for (unsigned m = __ballot_sync(0xffffffffu, use); m; m &= m - 1) {
+                        const int src = __ffs((int)m) - 1;
+                        const int d = __shfl_sync(0xffffffffu, dist, src), lv = __shfl_sync(0xffffffffu, oct, src);
+                        const int id = __shfl_sync(0xffffffffu, idx, src);
+                        if (d < bestDist) {
+                            bestDist2 = bestDist; bestDist = d;
+                            bestLevel2 = bestLevel; bestLevel = lv;
+                            bestIdx = id;
+                        } else if (d < bestDist2) {
+                            bestLevel2 = lv; bestDist2 = d;
+                        }
+                    }
+                }
+            }
+        }
+        // ratio test against the second best, only if both are in the same scale level (:144-147); TH_HIGH = 100
+        if (bestDist <= 100 && !(bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(a.nn_ratio, (float)bestDist2)))
+            match = bestIdx;
+    }
+    if (lane == 0) {
+        a.match_next[i] = match;
+        if (match != a.match_prev[i]) *a.changed = 1;
+        if (match >= 0 && (P.flags & 2)) atomicMin(&a.claim_next[match], i); // Observations() > 0: blocks later points
+    }
+}
+
 } // namespace
+
+int launch_search_by_projection(const ProjArgs &a, cudaStream_t st)
+{
+    k_search_by_projection<<<(a.n_mp + 7) / 8, 256, 0, st>>>(a);
+    return 1;
+}
 
 size_t grid_smem_bytes(const GridSpec &s) { return sizeof(int) * (2 * (size_t)s.cols * s.rows + 1); }
 

@@ -95,4 +95,23 @@ int launch_assign_grid(const pslot_keypoint *kps, const int *counts, int fixed_n
                        int *cell_start, int *indices, int nimages, cudaStream_t st);
 int launch_features_in_area(const pslot_keypoint *kps, const int *cell_start, const int *indices, const GridSpec &s,
                             const pslot_area_query *queries, int nq, int cap, int *out_count, int *out, cudaStream_t st);
+struct ProjArgs {
+    const pslot_keypoint *kps;      // mvKeysUn of the gridded frame
+    const int *cell_start, *indices;
+    GridSpec s;
+    const pslot_map_point *mps;
+    const uint8_t *mp_desc;
+    int n_mp;
+    const uint8_t *frame_desc;
+    const float *u_right;
+    const uint8_t *occupied;
+    const int *claim_prev;
+    int *claim_next;
+    const int *match_prev;
+    int *match_next;
+    int *changed;
+    float scale_factors[PSLOT_MAX_LEVELS];
+    float th, nn_ratio;
+};
+int launch_search_by_projection(const ProjArgs &a, cudaStream_t st);
 void launch_debug_steer(const float *angle_deg, int n, float *a, float *b, cudaStream_t st);
