@@ -71,6 +71,8 @@ Frame::Frame(const cv::Mat &imLeft, const cv::Mat &imRight, const double &timeSt
 
     ComputeStereoMatches();
 
+    mvpMapPoints = std::vector<MapPoint *>(N, static_cast<MapPoint *>(nullptr)); // (:175)
+
     AssignFeaturesToGrid(); // (:199)
 }
 

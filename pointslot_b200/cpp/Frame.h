@@ -19,6 +19,7 @@ namespace ORB_SLAM2
 #define FRAME_GRID_COLS 64
 
 class ORBVocabulary; // opaque here: the stereo path never touches it
+class MapPoint;      // only pointers are stored
 
 class Frame
 {
@@ -67,6 +68,9 @@ public:
     std::vector<float> mvuRight; // negative value for monocular points
     std::vector<float> mvDepth;
     cv::Mat mDescriptors, mDescriptorsRight;
+
+    // MapPoints associated to keypoints, NULL pointer if no association.
+    std::vector<MapPoint *> mvpMapPoints;
 
     int mnScaleLevels;
     float mfScaleFactor;

@@ -5,7 +5,9 @@
 //   out: int32 N, Nr; N keypoints (28 B), N*32 desc, Nr keypoints, Nr*32 desc, N float uRight, N float depth,
 //        int32 pyramid level-1 w,h + bytes (checks SyncImagePyramid), int32 DescriptorDistance(desc0, desc1),
 //        mGrid as 64*48 x (int32 size, int32 entries...), then 3 windows x (int32 n, entries) from GetFeaturesInArea
-//        and the same 3 from GetFeaturesInAreas
+//        and the same 3 from GetFeaturesInAreas; then int32 nMP, nMP x (4 float + 2 int32 map point record as
+//        pslot_map_point), nMP x 32 descriptor bytes, int32 nmatches of ORBmatcher(0.8).SearchByProjection(frame, mps, 3),
+//        N x int32 map-point index held by frame.mvpMapPoints[idx] afterwards (-1 = none)
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -74,9 +76,45 @@ int main(int argc, char **argv)
         std::fwrite(&n, 4, 1, o);
         for (size_t v : r) { const int iv = (int)v; std::fwrite(&iv, 4, 1, o); }
     }
+    // local-map projection search: map points that re-observe the frame's own features with deterministic noise
+    const int nMP = N + N / 2;
+    std::vector<MapPoint> pool(nMP);
+    std::vector<MapPoint *> vp(nMP);
+    unsigned lcg = 12345u;
+    auto rnd = [&lcg]() { lcg = lcg * 1664525u + 1013904223u; return (lcg >> 8) & 0xFFFF; };
+    for (int i = 0; i < nMP; ++i) {
+        const int src = (int)(rnd() % (unsigned)N);
+        MapPoint &m = pool[i];
+        m.mTrackProjX = frame.mvKeysUn[src].pt.x + ((int)(rnd() % 9) - 4) * 0.5f;
+        m.mTrackProjY = frame.mvKeysUn[src].pt.y + ((int)(rnd() % 9) - 4) * 0.5f;
+        m.mTrackProjXR = frame.mvuRight[src] > 0 ? frame.mvuRight[src] + ((int)(rnd() % 5) - 2) * 0.5f : m.mTrackProjX - 6.f;
+        m.mbTrackInView = rnd() % 10 != 0;
+        m.mbBad = rnd() % 25 == 0;
+        m.nObs = rnd() % 5 == 0 ? 0 : 3;
+        m.mnTrackScaleLevel = std::min(hdr[3] - 1, frame.mvKeysUn[src].octave + (int)(rnd() % 2));
+        m.mTrackViewCos = rnd() % 2 ? 0.9991f : 0.95f;
+        m.mDescriptor = frame.mDescriptors.row(src).clone();
+        for (int b = (int)(rnd() % 40); b > 0; --b) { const unsigned bit = rnd() % 256; m.mDescriptor.ptr<unsigned char>()[bit >> 3] ^= (unsigned char)(1u << (bit & 7)); }
+        vp[i] = &m;
+    }
+    std::fwrite(&nMP, 4, 1, o);
+    for (int i = 0; i < nMP; ++i) {
+        const MapPoint &m = pool[i];
+        const float f4[4] = {m.mTrackProjX, m.mTrackProjY, m.mTrackProjXR, m.mTrackViewCos};
+        const int i2[2] = {m.mnTrackScaleLevel, ((m.mbTrackInView && !m.mbBad) ? 1 : 0) | (m.nObs > 0 ? 2 : 0)};
+        std::fwrite(f4, 4, 4, o); std::fwrite(i2, 4, 2, o);
+    }
+    for (int i = 0; i < nMP; ++i) std::fwrite(pool[i].mDescriptor.ptr<unsigned char>(), 1, 32, o);
+    ORBmatcher matcher(0.8);
+    const int nmatches = matcher.SearchByProjection(frame, vp, 3);
+    std::fwrite(&nmatches, 4, 1, o);
+    for (int idx = 0; idx < N; ++idx) {
+        const int who = frame.mvpMapPoints[idx] ? (int)(frame.mvpMapPoints[idx] - pool.data()) : -1;
+        std::fwrite(&who, 4, 1, o);
+    }
     std::fclose(o);
-    std::printf("shim ok: N=%d Nr=%d matched=%d mb=%g\n", N, Nr,
-                (int)std::count_if(frame.mvuRight.begin(), frame.mvuRight.end(), [](float v) { return v >= 0; }), frame.mb);
+    std::printf("shim ok: N=%d Nr=%d matched=%d mb=%g projection matches=%d\n", N, Nr,
+                (int)std::count_if(frame.mvuRight.begin(), frame.mvuRight.end(), [](float v) { return v >= 0; }), frame.mb, nmatches);
     delete left; delete right;
     return 0;
 }

@@ -1051,7 +1051,7 @@ int pslot_search_by_projection(pslot_orb *ctx, const pslot_map_point *mps, const
     const size_t o_mp = take(sizeof(pslot_map_point) * (size_t)n_mp), o_md = take(32 * (size_t)n_mp);
     const size_t o_fd = take(32 * (size_t)n), o_ur = take(4 * (size_t)n), o_oc = take((size_t)n);
     const size_t o_c0 = take(4 * (size_t)n), o_c1 = take(4 * (size_t)n);
-    const size_t o_m0 = take(4 * (size_t)n_mp), o_m1 = take(4 * (size_t)n_mp), o_ch = take(4);
+    const size_t o_m0 = take(4 * (size_t)n_mp), o_m1 = take(4 * (size_t)n_mp), o_ch = take(64);
     if (off > ctx->proj_bytes) {
         cudaFree(ctx->d_proj);
         ctx->d_proj = nullptr; ctx->proj_bytes = 0;
@@ -1077,20 +1077,30 @@ int pslot_search_by_projection(pslot_orb *ctx, const pslot_map_point *mps, const
     a.changed = (int *)(base + o_ch);
     for (int l = 0; l < nlevels; ++l) a.scale_factors[l] = scale_factors[l];
     a.th = th; a.nn_ratio = nn_ratio;
+    // Sweeps are enqueued four at a time and the host looks at their "changed" flags once per group: a sweep past the
+    // fixed point recomputes the same matches, so overshooting is harmless and saves a round trip per sweep.
+    const int GROUP = 4;
     int cur = 0, sweeps = 0;
-    for (;; ++sweeps) {
-        if (sweeps > n_mp + 1) return fail(PSLOT_ERR_STATE, "projection search did not converge"); // cannot happen: see grid.cu
-        a.claim_prev = claim[cur]; a.claim_next = claim[cur ^ 1];
-        a.match_prev = match[cur]; a.match_next = match[cur ^ 1];
-        CU(cudaMemsetAsync(a.claim_next, 0x7f, 4 * (size_t)n, st));
-        CU(cudaMemsetAsync(a.changed, 0, 4, st));
-        launch_search_by_projection(a, st);
+    for (bool done = false; !done;) {
+        if (sweeps > n_mp + GROUP) return fail(PSLOT_ERR_STATE, "projection search did not converge"); // cannot happen: see grid.cu
+        int *flags = (int *)(base + o_ch);
+        CU(cudaMemsetAsync(flags, 0, 4 * GROUP, st));
+        for (int k = 0; k < GROUP; ++k) {
+            a.claim_prev = claim[cur]; a.claim_next = claim[cur ^ 1];
+            a.match_prev = match[cur]; a.match_next = match[cur ^ 1];
+            a.changed = flags + k;
+            CU(cudaMemsetAsync(a.claim_next, 0x7f, 4 * (size_t)n, st));
+            launch_search_by_projection(a, st);
+            cur ^= 1;
+        }
         CU(cudaGetLastError());
-        int changed = 0;
-        CU(cudaMemcpyAsync(&changed, a.changed, 4, cudaMemcpyDeviceToHost, st));
+        int changed[GROUP];
+        CU(cudaMemcpyAsync(changed, flags, 4 * GROUP, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        cur ^= 1;
-        if (!changed) break;
+        for (int k = 0; k < GROUP; ++k) {
+            ++sweeps;
+            if (!changed[k]) { done = true; break; } // the later sweeps of the group reproduced this one
+        }
     }
     CU(cudaMemcpy(match_of_mp, match[cur], 4 * (size_t)n_mp, cudaMemcpyDeviceToHost));
     if (nmatches) {
@@ -1098,7 +1108,7 @@ int pslot_search_by_projection(pslot_orb *ctx, const pslot_map_point *mps, const
         for (int i = 0; i < n_mp; ++i) c += match_of_mp[i] >= 0;
         *nmatches = c;
     }
-    ctx->last_sweeps = sweeps + 1;
+    ctx->last_sweeps = sweeps;
     return PSLOT_OK;
 }
 

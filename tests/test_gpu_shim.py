@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+O_MP_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"),
+                       ("level", "<i4"), ("flags", "<i4")])
 ROOT = Path(__file__).resolve().parents[1]
 SHIM = ROOT / "pointslot_b200" / "cpp"
 
@@ -46,6 +48,11 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle_mod):
         return v
     grid = [read_list() for _ in range(64 * 48)]
     areas = [read_list() for _ in range(6)]
+    (n_mp,) = struct.unpack_from("<i", raw, o); o += 4
+    mps = np.frombuffer(raw, O_MP_DTYPE, n_mp, o); o += 24 * n_mp
+    md = np.frombuffer(raw, np.uint8, 32 * n_mp, o).reshape(n_mp, 32); o += 32 * n_mp
+    (nmatches,) = struct.unpack_from("<i", raw, o); o += 4
+    holder = np.frombuffer(raw, np.int32, N, o); o += 4 * N
 
     O = oracle_mod
     oL, oR = O.OracleExtractor(*params), O.OracleExtractor(*params)
@@ -68,3 +75,13 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle_mod):
         ref = O.features_in_area(okL, cs, idx, 0.0, 0.0, inv_w, inv_h, 64, 48, *q)
         assert np.array_equal(areas[i], ref) and np.array_equal(areas[3 + i], ref)
     assert sum(len(a) for a in areas) > 0
+    # ORBmatcher::SearchByProjection (ORBmatcher.cc:68-155) through the drop-in class: F.mvpMapPoints afterwards
+    sf = np.array(B.OrbExtractor(*params).tables()["scale"], np.float32)  # = F.mvScaleFactors (ORBextractor.cc:417-424)
+    match, nref = O.search_by_projection(okL, odL, our, cs, idx, 0.0, 0.0, inv_w, inv_h, 64, 48, mps, md,
+                                         np.zeros(N, np.uint8), sf, 3.0, 0.8)
+    expect = np.full(N, -1, np.int32)
+    for i, m in enumerate(match):
+        if m >= 0:
+            expect[m] = i
+    assert nmatches == nref and nref > 50
+    assert np.array_equal(holder, expect)
