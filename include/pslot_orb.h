@@ -157,7 +157,28 @@ int pslot_search_by_projection(pslot_orb *ctx, const pslot_map_point *mps, const
                                const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n,
                                const float *scale_factors, int nlevels, float th, float nn_ratio,
                                int32_t *match_of_mp, int *nmatches);
-/* Number of device sweeps the last pslot_search_by_projection needed to reproduce the sequential result (>= 2). */
+/* int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
+ * (src/ORBmatcher.cc:1613-1756), called by Tracking::TrackWithMotionModel (src/Tracking.cc:3047, 3053).  The caller
+ * keeps the reference's projection lines (:1623-1676: pose algebra on cv::Mat, bounds test, level window) and hands
+ * over one record per LastFrame keypoint that carries a map point; the search, the assignment order dependence
+ * and the rotation-histogram consistency check (:1720-1753, ComputeThreeMaxima :2658-2699) happen here. */
+typedef struct pslot_proj_point {
+    float u, v;      /* projection into the current frame (:1656-1657) */
+    float ur;        /* u - CurrentFrame.mbf * invzc (:1690) */
+    float radius;    /* th * CurrentFrame.mvScaleFactors[nLastOctave] (:1667) */
+    int32_t min_level, max_level; /* the level arguments of the GetFeaturesInArea call taken at :1671-1676
+                                     (forward: nLastOctave, -1; backward: 0, nLastOctave; else nLastOctave-1, nLastOctave+1) */
+    float angle;     /* LastFrame.mvKeysUn[i].angle (:1722) */
+    int32_t flags;   /* bit 0: the point reaches the search (pMP && !mvbOutlier[i] && invzc >= 0 && inside the bounds)
+                        bit 1: pMP->Observations() > 0 */
+} pslot_proj_point;
+/* match_of_pt[i] = bestIdx2 of record i or -1; rejected[i] != 0 where the rotation check removed the match again
+ * (CurrentFrame.mvpMapPoints[match_of_pt[i]] = NULL after all assignments have been applied in order);
+ * *nmatches = the reference's return value.  check_orientation = mbCheckOrientation.  Frame arrays as above. */
+int pslot_search_by_projection_last(pslot_orb *ctx, const pslot_proj_point *pts, const uint8_t *pt_desc, int n_pts,
+                                    const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n,
+                                    int check_orientation, int32_t *match_of_pt, uint8_t *rejected, int *nmatches);
+/* Number of device sweeps the last projection search needed to reproduce the sequential result (>= 2). */
 int pslot_debug_projection_sweeps(const pslot_orb *ctx);
 
 /* ---------------------------------------------------------------------------------------------

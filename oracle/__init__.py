@@ -83,6 +83,8 @@ def lib():
                                            C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, vp]
         L.orc_search_by_projection.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float,
                                                C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_float, C.c_float, vp]
+        L.orc_search_by_projection_last.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float,
+                                                    C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp]
         L.orc_distribute_octtree.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_int, vp, vp, vp, ip]
         _lib = L
@@ -202,6 +204,25 @@ def search_by_projection(kps_un, frame_desc, u_right, cell_start, indices, min_x
                                        _ptr(indices), min_x, min_y, inv_w, inv_h, cols, rows, _ptr(mps), _ptr(mp_desc),
                                        len(mps), _ptr(occupied), _ptr(sf), th, nn_ratio, _ptr(out))
     return out[:len(mps)].copy(), int(n)
+
+
+PROJ_POINT_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("radius", "<f4"), ("min_level", "<i4"),
+                             ("max_level", "<i4"), ("angle", "<f4"), ("flags", "<i4")])
+
+
+def search_by_projection_last(kps_un, frame_desc, u_right, cell_start, indices, min_x, min_y, inv_w, inv_h, cols, rows,
+                              pts, pt_desc, occupied, check_orientation=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) after the projection (ORBmatcher.cc:1671-1756)
+    -> (match_of_pt, rejected, nmatches)."""
+    kps_un = np.ascontiguousarray(kps_un, KEYPOINT_DTYPE); frame_desc = np.ascontiguousarray(frame_desc, np.uint8)
+    u_right = np.ascontiguousarray(u_right, np.float32); pts = np.ascontiguousarray(pts, PROJ_POINT_DTYPE)
+    pt_desc = np.ascontiguousarray(pt_desc, np.uint8); occupied = np.ascontiguousarray(occupied, np.uint8)
+    cell_start = np.ascontiguousarray(cell_start, np.int32); indices = np.ascontiguousarray(indices, np.int32)
+    out = np.full(max(len(pts), 1), -1, np.int32); rej = np.zeros(max(len(pts), 1), np.uint8)
+    n = lib().orc_search_by_projection_last(_ptr(kps_un), _ptr(frame_desc), _ptr(u_right), len(kps_un), _ptr(cell_start),
+                                            _ptr(indices), min_x, min_y, inv_w, inv_h, cols, rows, _ptr(pts), _ptr(pt_desc),
+                                            len(pts), _ptr(occupied), int(check_orientation), _ptr(out), _ptr(rej))
+    return out[:len(pts)].copy(), rej[:len(pts)].copy(), int(n)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1043,3 +1043,81 @@ int orc_search_by_projection(const orc_keypoint *kps_un, const uint8_t *frame_de
     free(blocked); free(tmp);
     return nmatches;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
+ * (ORBmatcher.cc:1613-1756) from the point where each LastFrame map point has been projected: the loop body from the
+ * GetFeaturesInArea call on (:1671-1727), then the rotation consistency step (:1730-1753) with ComputeThreeMaxima
+ * (:2658-2699).  The projection itself (:1623-1667) stays with the caller, who passes its results per point.
+ * ------------------------------------------------------------------------------------------------------------ */
+int orc_search_by_projection_last(const orc_keypoint *kps_un, const uint8_t *frame_desc, const float *u_right, int n,
+                                  const int *cell_start, const int *indices, float min_x, float min_y, float inv_w,
+                                  float inv_h, int cols, int rows, const orc_proj_point *pts, const uint8_t *pt_desc,
+                                  int n_pts, const uint8_t *occupied, int check_orientation, int *match_of_pt,
+                                  uint8_t *rejected)
+{
+    enum { HISTO_LENGTH = 30 };
+    int nmatches = 0;
+    const float factor = HISTO_LENGTH / 360.0f;
+    uint8_t *blocked = (uint8_t *)malloc((size_t)(n > 0 ? n : 1));
+    int *tmp = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    int *hist = (int *)malloc(sizeof(int) * (size_t)HISTO_LENGTH * (size_t)(n_pts > 0 ? n_pts : 1)); /* rotHist[bin][k] */
+    int hsize[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; ++i) hsize[i] = 0;
+    for (int i = 0; i < n; ++i) blocked[i] = occupied ? occupied[i] : 0;
+    for (int i = 0; i < n_pts; ++i) {
+        const orc_proj_point *p = &pts[i];
+        match_of_pt[i] = -1;
+        rejected[i] = 0;
+        if (!(p->flags & 1)) continue; /* no map point, outlier, behind the camera or outside the image (:1640-1662) */
+        const float radius = p->radius;
+        const int nc = orc_features_in_area(kps_un, cell_start, indices, min_x, min_y, inv_w, inv_h, cols, rows, p->u, p->v,
+                                            radius, p->min_level, p->max_level, n, tmp);
+        if (nc == 0) continue;
+        const uint8_t *dMP = pt_desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int v = 0; v < nc; ++v) {
+            const int i2 = tmp[v];
+            if (blocked[i2]) continue; /* (:1684-1686) */
+            if (u_right[i2] > 0) {
+                const float er = fabsf(p->ur - u_right[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = orc_hamming256(dMP, frame_desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= 100) { /* TH_HIGH */
+            match_of_pt[i] = bestIdx2; /* CurrentFrame.mvpMapPoints[bestIdx2] = pMP (:1715) */
+            if (p->flags & 2) blocked[bestIdx2] = 1;
+            nmatches++;
+            if (check_orientation) {
+                float rot = p->angle - kps_un[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)round((double)(rot * factor));
+                if (bin == HISTO_LENGTH) bin = 0;
+                if (bin < 0 || bin >= HISTO_LENGTH) { nmatches = -1; goto done; } /* the reference asserts */
+                hist[(size_t)bin * (size_t)n_pts + (size_t)hsize[bin]++] = i; /* the reference stores bestIdx2; i identifies it */
+            }
+        }
+    }
+    if (check_orientation) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) { /* ComputeThreeMaxima (:2658-2699) */
+            const int s = hsize[i];
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int j = 0; j < hsize[i]; j++) {
+                    rejected[hist[(size_t)i * (size_t)n_pts + (size_t)j]] = 1; /* mvpMapPoints[...] = NULL (:1747) */
+                    nmatches--;
+                }
+    }
+done:
+    free(blocked); free(tmp); free(hist);
+    return nmatches;
+}

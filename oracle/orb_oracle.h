@@ -114,6 +114,21 @@ int orc_search_by_projection(const orc_keypoint *kps_un, const uint8_t *frame_de
                              int n_mp, const uint8_t *occupied, const float *scale_factors, float th, float nn_ratio,
                              int *match_of_mp);
 
+/* one LastFrame map point after the reference's projection lines (ORBmatcher.cc:1640-1676) */
+typedef struct orc_proj_point {
+    float u, v, ur, radius;       /* projection, u - mbf * invzc, th * mvScaleFactors[nLastOctave] */
+    int32_t min_level, max_level; /* level arguments of the GetFeaturesInArea call taken at :1671-1676 */
+    float angle;                  /* LastFrame.mvKeysUn[i].angle */
+    int32_t flags;                /* bit 0: reaches the search; bit 1: Observations() > 0 */
+} orc_proj_point;
+/* the rest of ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1671-1756);
+ * rejected[i] = 1 where the rotation check nulled the match again; returns nmatches (-1: angle out of range) */
+int orc_search_by_projection_last(const orc_keypoint *kps_un, const uint8_t *frame_desc, const float *u_right, int n,
+                                  const int *cell_start, const int *indices, float min_x, float min_y, float inv_w,
+                                  float inv_h, int cols, int rows, const orc_proj_point *pts, const uint8_t *pt_desc,
+                                  int n_pts, const uint8_t *occupied, int check_orientation, int *match_of_pt,
+                                  uint8_t *rejected);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "pslot_batch_submit", "pslot_batch_submit_color", "pslot_batch_wait", "pslot_batch_kernel_launches", "pslot_batch_device_out",
     "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats",
     "pslot_assign_grid", "pslot_features_in_area", "pslot_batch_assign_grid",
-    "pslot_search_by_projection", "pslot_debug_projection_sweeps",
+    "pslot_search_by_projection", "pslot_search_by_projection_last", "pslot_debug_projection_sweeps",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
 ]
 
@@ -56,6 +56,8 @@ class GridSpec(C.Structure):
 
 MAP_POINT_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"),
                             ("level", "<i4"), ("flags", "<i4")])  # pslot_map_point
+PROJ_POINT_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("radius", "<f4"), ("min_level", "<i4"),
+                             ("max_level", "<i4"), ("angle", "<f4"), ("flags", "<i4")])  # pslot_proj_point
 AREA_QUERY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("r", "<f4"), ("min_level", "<i4"), ("max_level", "<i4")])
 
 
@@ -94,6 +96,8 @@ def lib():
     L.pslot_batch_assign_grid.argtypes = [vp, C.POINTER(GridSpec), vp, vp]
     L.pslot_search_by_projection.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, C.c_float,
                                              C.c_float, vp, C.POINTER(C.c_int)]
+    L.pslot_search_by_projection_last.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp,
+                                                  C.POINTER(C.c_int)]
     L.pslot_debug_projection_sweeps.argtypes = [vp]
     L.pslot_batch_create.argtypes = [C.POINTER(vp), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, vp]
@@ -265,6 +269,20 @@ def search_by_projection(ext: OrbExtractor, mps, mp_desc, frame_desc, u_right, o
                                             None if occ is None else _p(occ), len(u_right), _p(sf), len(sf), th, nn_ratio,
                                             _p(out), C.byref(nm)))
     return out[:len(mps)].copy(), nm.value, lib().pslot_debug_projection_sweeps(ext._h)
+
+
+def search_by_projection_last(ext: OrbExtractor, pts, pt_desc, frame_desc, u_right, occupied, check_orientation=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) after the projection (reference
+    src/ORBmatcher.cc:1671-1756) -> (match_of_pt, rejected, nmatches, device sweeps)."""
+    pts = np.ascontiguousarray(pts, PROJ_POINT_DTYPE); pt_desc = np.ascontiguousarray(pt_desc, np.uint8)
+    frame_desc = np.ascontiguousarray(frame_desc, np.uint8); u_right = np.ascontiguousarray(u_right, np.float32)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    out = np.full(max(len(pts), 1), -1, np.int32); rej = np.zeros(max(len(pts), 1), np.uint8)
+    nm = C.c_int(0)
+    _check(lib().pslot_search_by_projection_last(ext._h, _p(pts), _p(pt_desc), len(pts), _p(frame_desc), _p(u_right),
+                                                 None if occ is None else _p(occ), len(u_right), int(check_orientation),
+                                                 _p(out), _p(rej), C.byref(nm)))
+    return out[:len(pts)].copy(), rej[:len(pts)].copy(), nm.value, lib().pslot_debug_projection_sweeps(ext._h)
 
 
 def stereo_match(ext_l: OrbExtractor, ext_r: OrbExtractor, kL, dL, kR, dR, bf: float, max_d: float, debug=False):

@@ -364,6 +364,7 @@ struct pslot_orb {
     size_t qout_cap = 0;
     int grid_n = -1;
     pslot_grid_spec grid_spec = {};
+    std::vector<float> h_gangle; // mvKeysUn[i].angle of the gridded frame (rotation check of the last-frame search)
     // projection search scratch (pslot_search_by_projection)
     void *d_proj = nullptr;
     size_t proj_bytes = 0;
@@ -983,6 +984,8 @@ int pslot_assign_grid(pslot_orb *ctx, const pslot_keypoint *kps_un, int n, const
     if (n_in_grid) *n_in_grid = total;
     ctx->grid_n = n;
     ctx->grid_spec = *spec;
+    ctx->h_gangle.resize((size_t)n);
+    for (int i = 0; i < n; ++i) ctx->h_gangle[i] = kps_un[i].angle;
     return PSLOT_OK;
 }
 
@@ -1022,36 +1025,23 @@ int pslot_features_in_area(pslot_orb *ctx, const pslot_area_query *queries, int 
     return PSLOT_OK;
 }
 
-int pslot_search_by_projection(pslot_orb *ctx, const pslot_map_point *mps, const uint8_t *mp_desc, int n_mp,
-                               const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n,
-                               const float *scale_factors, int nlevels, float th, float nn_ratio,
-                               int32_t *match_of_mp, int *nmatches)
+// Common part of the projection searches: upload the flattened points and frame arrays, run sweeps of
+// k_search_by_projection until a sweep changes no match (see grid.cu), download match_of_pt.
+static int run_projection(pslot_orb *ctx, const std::vector<ProjPoint> &pts, const uint8_t *pt_desc,
+                          const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n, int mode,
+                          float nn_ratio, int32_t *match_of_pt)
 {
-    if (!ctx) return fail(PSLOT_ERR_ARG, "ctx is null");
-    if (ctx->grid_n < 0) return fail(PSLOT_ERR_STATE, "pslot_assign_grid has not been called on this context");
-    if (n != ctx->grid_n) return fail(PSLOT_ERR_ARG, "n (%d) differs from the gridded keypoint count (%d)", n, ctx->grid_n);
-    if (n_mp < 0 || (n_mp > 0 && (!mps || !mp_desc || !match_of_mp)) || (n > 0 && (!frame_desc || !u_right)))
-        return fail(PSLOT_ERR_ARG, "null array");
-    if (!scale_factors || nlevels < 1 || nlevels > PSLOT_MAX_LEVELS) return fail(PSLOT_ERR_ARG, "bad scale factor table");
-    if (nmatches) *nmatches = 0;
-    if (n_mp == 0) return PSLOT_OK;
-    for (int i = 0; i < n_mp; ++i)
-        if ((mps[i].flags & 1) && (mps[i].level < 0 || mps[i].level >= nlevels))
-            return fail(PSLOT_ERR_ARG, "map point %d: predicted level %d out of range", i, mps[i].level);
-    if (n == 0) { // no features: nothing can match
-        for (int i = 0; i < n_mp; ++i) match_of_mp[i] = -1;
-        return PSLOT_OK;
-    }
+    const int n_pts = (int)pts.size();
     Engine &E = ctx->E;
     CU(cudaSetDevice(E.device));
-    // one scratch block: map points | their descriptors | frame descriptors | uRight | occupied | 2 claim arrays |
-    // 2 match arrays | changed flag
+    // one scratch block: points | their descriptors | frame descriptors | uRight | occupied | 2 claim arrays |
+    // 2 match arrays | changed flags
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t o_mp = take(sizeof(pslot_map_point) * (size_t)n_mp), o_md = take(32 * (size_t)n_mp);
+    const size_t o_mp = take(sizeof(ProjPoint) * (size_t)n_pts), o_md = take(32 * (size_t)n_pts);
     const size_t o_fd = take(32 * (size_t)n), o_ur = take(4 * (size_t)n), o_oc = take((size_t)n);
     const size_t o_c0 = take(4 * (size_t)n), o_c1 = take(4 * (size_t)n);
-    const size_t o_m0 = take(4 * (size_t)n_mp), o_m1 = take(4 * (size_t)n_mp), o_ch = take(64);
+    const size_t o_m0 = take(4 * (size_t)n_pts), o_m1 = take(4 * (size_t)n_pts), o_ch = take(64);
     if (off > ctx->proj_bytes) {
         cudaFree(ctx->d_proj);
         ctx->d_proj = nullptr; ctx->proj_bytes = 0;
@@ -1060,8 +1050,8 @@ int pslot_search_by_projection(pslot_orb *ctx, const pslot_map_point *mps, const
     }
     uint8_t *base = (uint8_t *)ctx->d_proj;
     cudaStream_t st = E.st;
-    CU(cudaMemcpyAsync(base + o_mp, mps, sizeof(pslot_map_point) * (size_t)n_mp, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_md, mp_desc, 32 * (size_t)n_mp, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_mp, pts.data(), sizeof(ProjPoint) * (size_t)n_pts, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_md, pt_desc, 32 * (size_t)n_pts, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_fd, frame_desc, 32 * (size_t)n, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_ur, u_right, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
     if (occupied) CU(cudaMemcpyAsync(base + o_oc, occupied, (size_t)n, cudaMemcpyHostToDevice, st));
@@ -1069,20 +1059,18 @@ int pslot_search_by_projection(pslot_orb *ctx, const pslot_map_point *mps, const
     int *claim[2] = {(int *)(base + o_c0), (int *)(base + o_c1)};
     int *match[2] = {(int *)(base + o_m0), (int *)(base + o_m1)};
     CU(cudaMemsetAsync(claim[0], 0x7f, 4 * (size_t)n, st));  // "no map point has claimed this feature"
-    CU(cudaMemsetAsync(match[0], 0xfe, 4 * (size_t)n_mp, st)); // differs from every possible match: the first sweep counts as a change
+    CU(cudaMemsetAsync(match[0], 0xfe, 4 * (size_t)n_pts, st)); // differs from every possible match: the first sweep counts as a change
     ProjArgs a{};
     a.kps = ctx->d_gk; a.cell_start = ctx->d_gcs; a.indices = ctx->d_gidx; a.s = ctx->grid_spec;
-    a.mps = (const pslot_map_point *)(base + o_mp); a.mp_desc = base + o_md; a.n_mp = n_mp;
+    a.pts = (const ProjPoint *)(base + o_mp); a.pt_desc = base + o_md; a.n_pts = n_pts;
     a.frame_desc = base + o_fd; a.u_right = (const float *)(base + o_ur); a.occupied = base + o_oc;
-    a.changed = (int *)(base + o_ch);
-    for (int l = 0; l < nlevels; ++l) a.scale_factors[l] = scale_factors[l];
-    a.th = th; a.nn_ratio = nn_ratio;
+    a.mode = mode; a.nn_ratio = nn_ratio;
     // Sweeps are enqueued four at a time and the host looks at their "changed" flags once per group: a sweep past the
     // fixed point recomputes the same matches, so overshooting is harmless and saves a round trip per sweep.
     const int GROUP = 4;
     int cur = 0, sweeps = 0;
     for (bool done = false; !done;) {
-        if (sweeps > n_mp + GROUP) return fail(PSLOT_ERR_STATE, "projection search did not converge"); // cannot happen: see grid.cu
+        if (sweeps > n_pts + GROUP) return fail(PSLOT_ERR_STATE, "projection search did not converge"); // cannot happen: see grid.cu
         int *flags = (int *)(base + o_ch);
         CU(cudaMemsetAsync(flags, 0, 4 * GROUP, st));
         for (int k = 0; k < GROUP; ++k) {
@@ -1102,13 +1090,113 @@ int pslot_search_by_projection(pslot_orb *ctx, const pslot_map_point *mps, const
             if (!changed[k]) { done = true; break; } // the later sweeps of the group reproduced this one
         }
     }
-    CU(cudaMemcpy(match_of_mp, match[cur], 4 * (size_t)n_mp, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(match_of_pt, match[cur], 4 * (size_t)n_pts, cudaMemcpyDeviceToHost));
+    ctx->last_sweeps = sweeps;
+    return PSLOT_OK;
+}
+
+static int check_projection_frame(pslot_orb *ctx, int n_pts, const void *pts, const void *desc, const void *out,
+                                  const uint8_t *frame_desc, const float *u_right, int n)
+{
+    if (!ctx) return fail(PSLOT_ERR_ARG, "ctx is null");
+    if (ctx->grid_n < 0) return fail(PSLOT_ERR_STATE, "pslot_assign_grid has not been called on this context");
+    if (n != ctx->grid_n) return fail(PSLOT_ERR_ARG, "n (%d) differs from the gridded keypoint count (%d)", n, ctx->grid_n);
+    if (n_pts < 0 || (n_pts > 0 && (!pts || !desc || !out)) || (n > 0 && (!frame_desc || !u_right)))
+        return fail(PSLOT_ERR_ARG, "null array");
+    return PSLOT_OK;
+}
+
+int pslot_search_by_projection(pslot_orb *ctx, const pslot_map_point *mps, const uint8_t *mp_desc, int n_mp,
+                               const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n,
+                               const float *scale_factors, int nlevels, float th, float nn_ratio,
+                               int32_t *match_of_mp, int *nmatches)
+{
+    if (int rc = check_projection_frame(ctx, n_mp, mps, mp_desc, match_of_mp, frame_desc, u_right, n)) return rc;
+    if (!scale_factors || nlevels < 1 || nlevels > PSLOT_MAX_LEVELS) return fail(PSLOT_ERR_ARG, "bad scale factor table");
+    if (nmatches) *nmatches = 0;
+    if (n_mp == 0) return PSLOT_OK;
+    std::vector<ProjPoint> pts((size_t)n_mp);
+    for (int i = 0; i < n_mp; ++i) {
+        const pslot_map_point &m = mps[i];
+        ProjPoint &p = pts[i];
+        p = ProjPoint{};
+        p.flags = m.flags & 3;
+        if (!(m.flags & 1)) continue;
+        if (m.level < 0 || m.level >= nlevels) return fail(PSLOT_ERR_ARG, "map point %d: predicted level %d out of range", i, m.level);
+        // The size of the window depends on the viewing direction (:85-92); float products, one rounding each
+        float r = ((double)m.view_cos > 0.998) ? 2.5f : 4.0f; // RadiusByViewingCos (:252-258)
+        if (th != 1.0f) r *= th;
+        p.x = m.proj_x; p.y = m.proj_y; p.xr = m.proj_xr;
+        p.radius = r * scale_factors[m.level];
+        p.er_limit = p.radius;                           // er > r * F.mvScaleFactors[nPredictedLevel] (:118)
+        p.min_level = m.level - 1; p.max_level = m.level; // (:92)
+    }
+    if (n == 0) { // no features: nothing can match
+        for (int i = 0; i < n_mp; ++i) match_of_mp[i] = -1;
+        return PSLOT_OK;
+    }
+    if (int rc = run_projection(ctx, pts, mp_desc, frame_desc, u_right, occupied, n, 0, nn_ratio, match_of_mp)) return rc;
     if (nmatches) {
         int c = 0;
         for (int i = 0; i < n_mp; ++i) c += match_of_mp[i] >= 0;
         *nmatches = c;
     }
-    ctx->last_sweeps = sweeps;
+    return PSLOT_OK;
+}
+
+int pslot_search_by_projection_last(pslot_orb *ctx, const pslot_proj_point *pts_in, const uint8_t *pt_desc, int n_pts,
+                                    const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n,
+                                    int check_orientation, int32_t *match_of_pt, uint8_t *rejected, int *nmatches)
+{
+    if (int rc = check_projection_frame(ctx, n_pts, pts_in, pt_desc, match_of_pt, frame_desc, u_right, n)) return rc;
+    if (n_pts > 0 && !rejected) return fail(PSLOT_ERR_ARG, "rejected is null");
+    if (nmatches) *nmatches = 0;
+    if (n_pts == 0) return PSLOT_OK;
+    for (int i = 0; i < n_pts; ++i) rejected[i] = 0;
+    if (n == 0) {
+        for (int i = 0; i < n_pts; ++i) match_of_pt[i] = -1;
+        return PSLOT_OK;
+    }
+    std::vector<ProjPoint> pts((size_t)n_pts);
+    for (int i = 0; i < n_pts; ++i) {
+        const pslot_proj_point &q = pts_in[i];
+        ProjPoint &p = pts[i];
+        p = ProjPoint{};
+        p.flags = q.flags & 3;
+        p.x = q.u; p.y = q.v; p.xr = q.ur; p.radius = q.radius; p.er_limit = q.radius; // er > radius (:1692)
+        p.min_level = q.min_level; p.max_level = q.max_level;
+    }
+    if (int rc = run_projection(ctx, pts, pt_desc, frame_desc, u_right, occupied, n, 1, 0.0f, match_of_pt)) return rc;
+    int nm = 0;
+    for (int i = 0; i < n_pts; ++i) nm += match_of_pt[i] >= 0;
+    if (check_orientation) { // rotation consistency (:1720-1753), sequential and tiny: on the host
+        const int HISTO_LENGTH = 30;
+        const float factor = HISTO_LENGTH / 360.0f;
+        std::vector<int> rotHist[HISTO_LENGTH];
+        for (int i = 0; i < n_pts; ++i) {
+            if (match_of_pt[i] < 0) continue;
+            float rot = pts_in[i].angle - ctx->h_gangle[(size_t)match_of_pt[i]];
+            if (rot < 0.0) rot += 360.0f;
+            int bin = (int)round(rot * factor);
+            if (bin == HISTO_LENGTH) bin = 0;
+            if (bin < 0 || bin >= HISTO_LENGTH) return fail(PSLOT_ERR_ARG, "keypoint angle out of [0, 360]"); // the reference asserts
+            rotHist[bin].push_back(i);
+        }
+        // ORBmatcher::ComputeThreeMaxima (:2658-2699)
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            const int sz = (int)rotHist[i].size();
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int j : rotHist[i]) { rejected[j] = 1; --nm; }
+    }
+    if (nmatches) *nmatches = nm;
     return PSLOT_OK;
 }
 

@@ -11,8 +11,9 @@
 //   k_features_in_area one warp per query: the cell rectangle is walked in the reference's order (ix outer, iy
 //                      inner, list order inside a cell) and the hits are compacted with ballots, so the output
 //                      order equals the reference's vIndices.
-//   k_search_by_projection  ORBmatcher::SearchByProjection (local-map variant) on top of the
-//                      same window walk; see the kernel's comment for how the reference's order dependence is kept.
+//   k_search_by_projection  ORBmatcher::SearchByProjection (local-map and last-frame variants)
+//                      on top of the same window walk; see the kernel's comment for how the reference's order
+//                      dependence is kept.
 // Float arithmetic as the reference writes it, products and differences kept separate (no FMA).
 // Bound: latency / HBM (28 B read + 4 B written per keypoint); algorithmic bytes = n_k * 32 + 4 * (cols * rows + 1).
 #include "pslot_internal.h"
@@ -166,33 +167,35 @@ k_features_in_area(const pslot_keypoint *__restrict__ kps, const int *__restrict
     if (lane == 0) out_count[q] = n;
 }
 
-// ORBmatcher::SearchByProjection(F, vpMapPoints, th) (reference src/ORBmatcher.cc:68-155), one warp per map point.
-// The reference loop is order dependent: once a map point with observations has been written into
-// F.mvpMapPoints[bestIdx] (:148), later map points skip that feature (:111-113).  Restated as a fixed point: a sweep
-// computes every map point's match with "feature idx is taken for map point i" <=> occupied[idx] or some map point
-// j < i with observations matched idx in the PREVIOUS sweep (claim_prev[idx] = the smallest such j).  Map point 0 is
-// right after one sweep, map point k after k + 1 at the latest, and a sweep that changes no match is the sequential
-// result; in practice the dependency chains are a few links long.  Inside a map point the candidates are visited
-// in the reference's order (GetFeaturesInArea order), 32 at a time: distances in parallel, then the best / second-best
+// ORBmatcher::SearchByProjection, one warp per projected map point; two variants share the window walk:
+//   mode 0  (F, vpMapPoints, th)                 local map  (reference src/ORBmatcher.cc:68-155): best + second best,
+//                                                ratio test when both lie in the same scale level;
+//   mode 1  (CurrentFrame, LastFrame, th, bMono) last frame (:1613-1756): best only.
+// The per-point window (centre, radius, level range, right-image coordinate and its tolerance) is computed by the
+// caller exactly as the reference computes it; the kernel starts at GetFeaturesInArea.
+// Both reference loops are order dependent: once a map point with observations has been written into
+// F.mvpMapPoints[bestIdx] (:148, :1715), later map points skip that feature (:111-113, :1684-1686).  Restated as a
+// fixed point: a sweep computes every point's match with "feature idx is taken for point i" <=> occupied[idx] or
+// some point j < i with observations matched idx in the PREVIOUS sweep (claim_prev[idx] = the smallest such j).
+// Point 0 is right after one sweep, point k after k + 1 at the latest, and a sweep that changes no match is the
+// sequential result; in practice the dependency chains are a few links long.  Inside a point the candidates are
+// visited in the reference's order (GetFeaturesInArea order), 32 at a time: distances in parallel, then the
 // bookkeeping replayed in order, because bestLevel2 depends on the visiting order among equal distances.
 __global__ void __launch_bounds__(256)
 k_search_by_projection(const __grid_constant__ ProjArgs a)
 {
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (i >= a.n_mp) return;
-    const pslot_map_point P = a.mps[i];
+    if (i >= a.n_pts) return;
+    const ProjPoint P = a.pts[i];
     int match = -1;
-    if (P.flags & 1) { // mbTrackInView && !isBad() (:76-81)
-        const int nPredictedLevel = P.level;
-        float r = ((double)P.view_cos > 0.998) ? 2.5f : 4.0f; // RadiusByViewingCos (:252-258)
-        if (a.th != 1.0f) r = __fmul_rn(r, a.th);
-        const float rad = __fmul_rn(r, a.scale_factors[nPredictedLevel]);
-        const uint4 *md = reinterpret_cast<const uint4 *>(a.mp_desc + (size_t)i * 32);
+    if (P.flags & 1) { // the reference reaches the search for this point
+        const float rad = P.radius;
+        const uint4 *md = reinterpret_cast<const uint4 *>(a.pt_desc + (size_t)i * 32);
         const uint4 m0 = __ldg(md), m1 = __ldg(md + 1);
         int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-        const AreaCells A = area_cells(a.s, P.proj_x, P.proj_y, rad);
+        const AreaCells A = area_cells(a.s, P.x, P.y, rad);
         if (A.ok) {
-            const int minLevel = nPredictedLevel - 1, maxLevel = nPredictedLevel; // maxLevel >= 0: levels are checked
+            const bool check_levels = P.min_level > 0 || P.max_level >= 0; // GetFeaturesInArea (:1829)
             for (int ix = A.x0; ix <= A.x1; ++ix) {
                 const int c0 = a.cell_start[ix * a.s.rows + A.y0], c1 = a.cell_start[ix * a.s.rows + A.y1 + 1];
                 for (int base = c0; base < c1; base += 32) {
@@ -204,13 +207,13 @@ k_search_by_projection(const __grid_constant__ ProjArgs a)
                         const pslot_keypoint kp = a.kps[idx];
                         oct = kp.octave;
                         // GetFeaturesInArea (:1837-1852)
-                        use = !(oct < minLevel || oct > maxLevel) && fabsf(__fsub_rn(kp.x, P.proj_x)) < rad &&
-                              fabsf(__fsub_rn(kp.y, P.proj_y)) < rad;
-                        // F.mvpMapPoints[idx] with observations (:111-113), as of the previous sweep
+                        use = !(check_levels && (oct < P.min_level || (P.max_level >= 0 && oct > P.max_level))) &&
+                              fabsf(__fsub_rn(kp.x, P.x)) < rad && fabsf(__fsub_rn(kp.y, P.y)) < rad;
+                        // F.mvpMapPoints[idx] with observations, as of the previous sweep
                         use = use && !(a.occupied[idx] || a.claim_prev[idx] < i);
                         if (use) {
                             const float ur = a.u_right[idx];
-                            if (ur > 0) use = !(fabsf(__fsub_rn(P.proj_xr, ur)) > rad); // (:115-120)
+                            if (ur > 0) use = !(fabsf(__fsub_rn(P.xr, ur)) > P.er_limit); // (:115-120, :1688-1694)
                         }
                         if (use) {
                             const uint4 *fd = reinterpret_cast<const uint4 *>(a.frame_desc + (size_t)idx * 32);
@@ -219,7 +222,7 @@ k_search_by_projection(const __grid_constant__ ProjArgs a)
                                    __popc(m1.x ^ f1.x) + __popc(m1.y ^ f1.y) + __popc(m1.z ^ f1.z) + __popc(m1.w ^ f1.w);
                         }
                     }
-                    // replay (:126-140) over the usable candidates in visiting order
+                    // replay (:126-140, :1700-1704) over the usable candidates in visiting order
                     for (unsigned m = __ballot_sync(0xffffffffu, use); m; m &= m - 1) {
                         const int src = __ffs((int)m) - 1;
                         const int d = __shfl_sync(0xffffffffu, dist, src), lv = __shfl_sync(0xffffffffu, oct, src);
@@ -235,8 +238,9 @@ k_search_by_projection(const __grid_constant__ ProjArgs a)
                 }
             }
         }
-        // ratio test against the second best, only if both are in the same scale level (:144-147); TH_HIGH = 100
-        if (bestDist <= 100 && !(bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(a.nn_ratio, (float)bestDist2)))
+        // TH_HIGH = 100; local map only: ratio test against the second best if both are in the same level (:144-147)
+        if (bestDist <= 100 &&
+            !(a.mode == 0 && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(a.nn_ratio, (float)bestDist2)))
             match = bestIdx;
     }
     if (lane == 0) {
@@ -250,7 +254,7 @@ k_search_by_projection(const __grid_constant__ ProjArgs a)
 
 int launch_search_by_projection(const ProjArgs &a, cudaStream_t st)
 {
-    k_search_by_projection<<<(a.n_mp + 7) / 8, 256, 0, st>>>(a);
+    k_search_by_projection<<<(a.n_pts + 7) / 8, 256, 0, st>>>(a);
     return 1;
 }
 

@@ -95,13 +95,20 @@ int launch_assign_grid(const pslot_keypoint *kps, const int *counts, int fixed_n
                        int *cell_start, int *indices, int nimages, cudaStream_t st);
 int launch_features_in_area(const pslot_keypoint *kps, const int *cell_start, const int *indices, const GridSpec &s,
                             const pslot_area_query *queries, int nq, int cap, int *out_count, int *out, cudaStream_t st);
+// one projected map point as the search kernel sees it: the window the reference passes to GetFeaturesInArea and the
+// right-image test, already evaluated by the caller
+struct ProjPoint {
+    float x, y, xr, radius, er_limit;
+    int min_level, max_level;
+    int flags; // bit 0: searched; bit 1: Observations() > 0
+};
 struct ProjArgs {
     const pslot_keypoint *kps;      // mvKeysUn of the gridded frame
     const int *cell_start, *indices;
     GridSpec s;
-    const pslot_map_point *mps;
-    const uint8_t *mp_desc;
-    int n_mp;
+    const ProjPoint *pts;
+    const uint8_t *pt_desc;
+    int n_pts;
     const uint8_t *frame_desc;
     const float *u_right;
     const uint8_t *occupied;
@@ -110,8 +117,8 @@ struct ProjArgs {
     const int *match_prev;
     int *match_next;
     int *changed;
-    float scale_factors[PSLOT_MAX_LEVELS];
-    float th, nn_ratio;
+    int mode;       // 0: local map (best + second best, ratio test); 1: last frame (best only)
+    float nn_ratio;
 };
 int launch_search_by_projection(const ProjArgs &a, cudaStream_t st);
 void launch_debug_steer(const float *angle_deg, int n, float *a, float *b, cudaStream_t st);

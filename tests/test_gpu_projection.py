@@ -51,3 +51,23 @@ def test_search_by_projection_edge_cases(B, oracle_mod):
         B.search_by_projection(e, bad, c["md"], c["d"], c["ur"], None, c["sf"], 1.0, 0.8)
     with pytest.raises(B.PslotError):  # frame arrays must describe the gridded keypoints
         B.search_by_projection(e, c["mps"], c["md"], c["d"][:-1], c["ur"][:-1], None, c["sf"], 1.0, 0.8)
+
+
+@pytest.mark.parametrize("seed,mode,ori,n_feat", [(1, "neutral", True, 1200), (2, "forward", True, 1200),
+                                                  (3, "backward", True, 2000), (4, "neutral", False, 600)])
+def test_search_by_projection_last_vs_oracle(seed, mode, ori, n_feat, B, oracle_mod):
+    """Last-frame variant (ORBmatcher.cc:1613-1756): matches, rotation-rejected set and return value."""
+    from test_oracle_projection import make_last_frame_case, run_oracle_last
+    c = make_last_frame_case(oracle_mod, seed, n_feat=n_feat, mode=mode)
+    rm, rrej, rn = run_oracle_last(oracle_mod, c, ori)
+    e = B.OrbExtractor(n_feat, 1.2, 8, 20, 7)
+    B.assign_grid(e, c["k"], B.GridSpec.for_image(c["W"], c["H"]))
+    m, rej, n, sweeps = B.search_by_projection_last(e, c["pts"], c["pd"], c["d"], c["ur"], c["occupied"], ori)
+    assert np.array_equal(m, rm) and np.array_equal(rej, rrej) and n == rn
+    assert 2 <= sweeps <= 64
+    # the local-map search still works on the same context afterwards (shared scratch, different mode)
+    c2 = make_case(oracle_mod, seed, n_feat=n_feat, n_mp=500)
+    B.assign_grid(e, c2["k"], B.GridSpec.for_image(c2["W"], c2["H"]))
+    ref, nref = run_oracle(oracle_mod, c2, 3.0, 0.8)
+    got, n2, _ = B.search_by_projection(e, c2["mps"], c2["md"], c2["d"], c2["ur"], c2["occupied"], c2["sf"], 3.0, 0.8)
+    assert np.array_equal(got, ref) and n2 == nref
