@@ -101,6 +101,9 @@ struct Engine {
     int device = 0;
     cudaStream_t st = nullptr;
     bool own_stream = false;
+    // side stream for the coarse-level quadtree launch, forked from / joined to `st` inside every submit
+    cudaStream_t st_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     int W = 0, H = 0, S = 0; // configured geometry / slot capacity
     Geom g{};
@@ -126,7 +129,14 @@ struct Engine {
     float *d_uright = nullptr, *d_depth = nullptr;
     int *d_best_dist = nullptr, *d_best_idx = nullptr, *d_sad = nullptr;
 
-    ~Engine() { release(); if (own_stream && st) cudaStreamDestroy(st); }
+    ~Engine()
+    {
+        release();
+        if (st_aux) cudaStreamDestroy(st_aux);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (own_stream && st) cudaStreamDestroy(st);
+    }
 
     void release()
     {
@@ -158,6 +168,9 @@ struct Engine {
         CU(cudaSetDevice(dev));
         if (stream) { st = (cudaStream_t)stream; own_stream = false; }
         else { CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); own_stream = true; }
+        CU(cudaStreamCreateWithFlags(&st_aux, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         return PSLOT_OK;
     }
 
@@ -318,7 +331,7 @@ struct Engine {
         n += launch_fast(g, maps, d_cell_count, d_cell_cand, nslots, st);
         if (ev) cudaEventRecord(ev[3], st);
         n += launch_quadtree(g, d_cell_count, d_cell_cand, d_cell_prefix, d_qt_keys, d_qt_nodes, d_lkp, d_lkp_count,
-                             d_err, nslots, st);
+                             d_err, nslots, st, st_aux, ev_fork, ev_join);
         if (ev) cudaEventRecord(ev[4], st);
         n += launch_describe(g, pyr, d_lkp, d_lkp_count, d_out_kps, d_out_desc, d_out_count, nslots, st);
         if (ev) cudaEventRecord(ev[5], st);
@@ -737,8 +750,8 @@ void *pslot_batch_stream(const pslot_batch *b) { return b ? (void *)b->E.st : nu
 int pslot_batch_kernel_launches(const pslot_batch *b)
 {
     if (!b) return fail(PSLOT_ERR_ARG, "b is null");
-    // ingest (re-pitch / colour conversion, one per view when used) + pyramid + FAST + quadtree + describe + 2 stereo
-    return b->launches ? b->launches : b->E.p.nlevels - 1 + 3 + 2 + 2;
+    // ingest (re-pitch / colour conversion, one per view when used) + pyramid + FAST + quadtree (2) + describe + 2 stereo
+    return b->launches ? b->launches : b->E.p.nlevels - 1 + 3 + (b->E.p.nlevels > 2 ? 1 : 0) + 2 + 2;
 }
 
 // Staged uploads go through the shared upload stream when one is set (pslot_batch_set_copy_stream).

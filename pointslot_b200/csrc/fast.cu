@@ -365,7 +365,7 @@ int launch_fast(const Geom &g, const TmapSet &maps, int *cell_count, uint32_t *c
         per_warp = per_warp > tile + score + list ? per_warp : tile + score + list;
     }
     const size_t smem = (size_t)per_warp * FW;
-    cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_dyn_smem(k_fast_cells, smem);
     dim3 grid((g.cells_per_slot + FW - 1) / FW, nslots);
     k_fast_cells<<<grid, FW * 32, smem, st>>>(g, maps, cell_count, cell_cand, per_warp);
     return 1;

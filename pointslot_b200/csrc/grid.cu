@@ -269,7 +269,7 @@ int launch_assign_grid(const pslot_keypoint *kps, const int *counts, int fixed_n
     const size_t room = (200 * 1024 - tables) / 2;
     const int cache_cap = (int)(want <= room ? want : 0);
     const size_t smem = tables + 2 * (size_t)cache_cap + 16;
-    cudaFuncSetAttribute(k_assign_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_dyn_smem(k_assign_grid, smem);
     k_assign_grid<<<nimages, GT, smem, st>>>(kps, counts, fixed_n, stride, s, cell_start, indices, cache_cap);
     return 1;
 }

@@ -15,6 +15,10 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "../../include/pslot_orb.h"
 
 #define PSLOT_MAX_LEVELS 16
@@ -81,7 +85,8 @@ struct TmapSet;
 int launch_fast(const Geom &g, const TmapSet &maps, int *cell_count, uint32_t *cell_cand, int nslots, cudaStream_t st);
 int launch_quadtree(const Geom &g, const int *cell_count, const uint32_t *cell_cand, int *cell_prefix,
                     uint32_t *qt_keys, uint16_t *qt_nodes, uint32_t *lkp, int *lkp_count, int *err_flag,
-                    int nslots, cudaStream_t st);
+                    int nslots, cudaStream_t st, cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr,
+                    cudaEvent_t ev_join = nullptr);
 int launch_describe(const Geom &g, const PyrPtrs &pyr, const uint32_t *lkp, const int *lkp_count,
                     pslot_keypoint *out_kps, uint8_t *out_desc, int *out_count, int nslots, cudaStream_t st);
 int launch_stereo(const Geom &g, const StereoArgs &a, int npairs, int max_n_r, cudaStream_t st,
@@ -89,6 +94,24 @@ int launch_stereo(const Geom &g, const StereoArgs &a, int npairs, int max_n_r, c
 size_t quadtree_smem_bytes(const Geom &g, int *key_cap);
 int launch_gray_ingest(const uint8_t *src, size_t src_image_stride, int channels, int rgb, uint8_t *dst, int w, int h,
                        int dpitch, unsigned long long dstride, int nimages, cudaStream_t st);
+// Opt a kernel in to `bytes` of dynamic shared memory.  The attribute is per function and per device, and contexts with
+// different geometries launch from different host threads (Frame drives its two extractors concurrently), so it is
+// only ever RAISED, under a lock: setting the exact size before each launch would let one thread lower it between
+// another thread's set and launch.
+template <typename K> inline void ensure_dyn_smem(K kernel, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> high;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &h = high[std::make_pair((const void *)kernel, dev)];
+    if (bytes > h) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        h = bytes;
+    }
+}
+
 typedef pslot_grid_spec GridSpec;
 size_t grid_smem_bytes(const GridSpec &s);
 int launch_assign_grid(const pslot_keypoint *kps, const int *counts, int fixed_n, size_t stride, const GridSpec &s,

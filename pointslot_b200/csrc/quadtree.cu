@@ -102,14 +102,14 @@ k_quadtree(const __grid_constant__ Geom g, const int *__restrict__ cell_count,
            const uint32_t *__restrict__ cell_cand, int *__restrict__ cell_prefix,
            uint32_t *__restrict__ g_keys, uint16_t *__restrict__ g_knode,
            uint32_t *__restrict__ lkp, int *__restrict__ lkp_count, int *__restrict__ err_flag,
-           int cap, int key_cap)
+           int cap, int key_cap, int level_base)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int red[QT / 32 + 2];
     __shared__ int s_total;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int l = blockIdx.x, slot = blockIdx.y;
+    const int l = blockIdx.x + level_base, slot = blockIdx.y;
     const LevelGeom &L = g.lv[l];
     const int N = L.quota;
 
@@ -408,30 +408,69 @@ size_t smem_for(int cap, int key_cap)
 
 } // namespace
 
-size_t quadtree_smem_bytes(const Geom &g, int *key_cap)
+// shared memory for the levels [l0, l1): node tables sized for the largest level of the range, key arrays for up to
+// `want_keys` candidates (levels with more spill their key arrays to global scratch), within `budget` bytes per CTA
+static size_t range_smem(const Geom &g, int l0, int l1, int want_keys, size_t budget, int *cap_out, int *key_cap)
 {
-    const int cap = g.max_level_cap;
-    // room for 6144 keys beside the node tables (levels with more candidates spill their key arrays to
-    // global scratch), capped so that at least two CTAs fit per SM
-    const size_t budget = 100 * 1024;
+    int cap = 0;
+    for (int l = l0; l < l1; ++l) cap = cap > g.lv[l].kp_cap ? cap : g.lv[l].kp_cap;
     const size_t fixed = smem_for(cap, 0);
-    int kc = 6144;
+    int kc = want_keys;
     if (fixed + 6 * (size_t)kc > budget) kc = fixed + 6 * 1024 < budget ? (int)((budget - fixed) / 6) : 1024;
     kc = kc & ~7;
+    *cap_out = cap;
     *key_cap = kc;
     return smem_for(cap, kc);
 }
 
+static size_t part_smem(const Geom &g, int part, int *l0, int *l1, int *cap, int *key_cap)
+{
+    const int split = g.nlevels < 2 ? g.nlevels : 2;
+    *l0 = part == 0 ? 0 : split;
+    *l1 = part == 0 ? split : g.nlevels;
+    if (*l1 <= *l0) return 0;
+    // the two finest levels hold over half of the candidates: room for 6144 keys beside the node tables, capped so
+    // that at least two CTAs fit per SM; the coarse levels get small tables
+    return part == 0 ? range_smem(g, *l0, *l1, 6144, 100 * 1024, cap, key_cap)
+                     : range_smem(g, *l0, *l1, 2048, 48 * 1024, cap, key_cap);
+}
+
+// largest dynamic shared-memory request of the two launches (the host refuses configurations beyond the SM's limit)
+size_t quadtree_smem_bytes(const Geom &g, int *key_cap)
+{
+    int l0, l1, cap, kc = 0, kc1 = 0;
+    const size_t a = part_smem(g, 0, &l0, &l1, &cap, &kc), b = part_smem(g, 1, &l0, &l1, &cap, &kc1);
+    *key_cap = kc;
+    return a > b ? a : b;
+}
+
 int launch_quadtree(const Geom &g, const int *cell_count, const uint32_t *cell_cand, int *cell_prefix,
                     uint32_t *qt_keys, uint16_t *qt_nodes, uint32_t *lkp, int *lkp_count, int *err_flag,
-                    int nslots, cudaStream_t st)
+                    int nslots, cudaStream_t st, cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join)
 {
-    int key_cap = 0;
-    const size_t smem = quadtree_smem_bytes(g, &key_cap);
-    // per device and per function: set on every launch (cheap), contexts may live on different devices
-    cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid(g.nlevels, nslots);
-    k_quadtree<<<grid, QT, smem, st>>>(g, cell_count, cell_cand, cell_prefix, qt_keys, qt_nodes, lkp, lkp_count,
-                                       err_flag, g.max_level_cap, key_cap);
-    return 1;
+    // Two launches: the finest levels need big tables (4 CTAs per SM); the coarse levels - most of the CTAs, each a
+    // chain of a dozen barrier-separated steps - run with small tables (twice as many resident CTAs overlap their
+    // barrier waits; ncu: 44 % of the stalls were barrier waits at 4 CTAs per SM) on a side stream, concurrently with
+    // the fine-level launch, whose 2 x nslots long-running CTAs would otherwise leave most of the GPU idle.
+    const bool fork = aux && ev_fork && ev_join && g.nlevels > 2;
+    if (fork) {
+        cudaEventRecord(ev_fork, st);
+        cudaStreamWaitEvent(aux, ev_fork, 0);
+    }
+    int launches = 0;
+    for (int part = 1; part >= 0; --part) { // coarse part first: it goes to the side stream
+        int l0, l1, cap = 0, key_cap = 0;
+        const size_t smem = part_smem(g, part, &l0, &l1, &cap, &key_cap);
+        if (l1 <= l0) continue;
+        ensure_dyn_smem(k_quadtree, smem);
+        dim3 grid(l1 - l0, nslots);
+        k_quadtree<<<grid, QT, smem, part == 1 && fork ? aux : st>>>(g, cell_count, cell_cand, cell_prefix, qt_keys, qt_nodes,
+                                                                    lkp, lkp_count, err_flag, cap, key_cap, l0);
+        ++launches;
+    }
+    if (fork) {
+        cudaEventRecord(ev_join, aux);
+        cudaStreamWaitEvent(st, ev_join, 0);
+    }
+    return launches;
 }

@@ -298,7 +298,7 @@ int launch_stereo(const Geom &g, const StereoArgs &a, int npairs, int max_n_r, c
     int list_cap = (3 * max_n_r + 1) & ~1;
     if (fixed + 2 * (size_t)list_cap > 220 * 1024) list_cap = 0;
     const size_t smem = fixed + 2 * (size_t)list_cap;
-    cudaFuncSetAttribute(k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_dyn_smem(k_stereo_match, smem);
     dim3 grid((a.K + LEFT_PER_CTA - 1) / LEFT_PER_CTA, npairs);
     k_stereo_match<<<grid, SW * 32, smem, st>>>(g, a, max_n_r, list_cap, nbins);
     if (between) cudaEventRecord(between, st);
