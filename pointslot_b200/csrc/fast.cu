@@ -108,42 +108,59 @@ __device__ __forceinline__ void arc_minmax(const uint32_t (&P)[16], uint32_t &M1
 __device__ __forceinline__ int quick_pass(const uint32_t *tile32, int TSW, int wsh, int S, int lane, int ntasks,
                                           int gshift, int iw, uint32_t bias, uint16_t *glist)
 {
-    const int G1 = (1 << gshift) - 1;
-    // four consecutive pixels starting O bytes from the group's first pixel = bytes 4 + S + O .. of the 16-byte row
-    // segment: word index and PRMT selector per offset, warp-uniform
-    const int a0 = 1, aE = (7 + S) >> 2, aW = (1 + S) >> 2;
-    const uint32_t sel0 = 0x3210u + 0x1111u * (uint32_t)S, selE = 0x3210u + 0x1111u * (uint32_t)((7 + S) & 3),
-                   selW = 0x3210u + 0x1111u * (uint32_t)((1 + S) & 3);
+    // A lane tests TWO adjacent groups (8 pixels) of one row: the three rows it needs are fetched as 5 + 3 + 3 words
+    // and re-aligned by the warp-uniform byte offset S with funnel shifts, after which the centre quads are whole
+    // words and the left / right ring quads one more funnel shift each - 11 loads per pair where two separate groups
+    // took 20.
+    const int pshift = gshift - 1, P1 = (1 << pshift) - 1; // pairs per row
+    const int npairs = ntasks >> 1;
     const int gmax = (iw - 1) >> 2; // last group of a row that holds tested pixels
+    const int sh = 8 * S;
     const unsigned lt = (1u << lane) - 1u;
     int nlist = 0;
-    // two independent groups per lane and iteration, branch-free (clamped addresses, masked result), so that the
-    // loads of one hide the dependent chain of the other
-    for (int base = 0; base < ntasks; base += 64) {
-        bool hit[2];
+    for (int base = 0; base < npairs; base += 64) {
+        bool hit[2][2];
+        int tq[2];
+        // two independent pairs per lane and iteration, so that the loads of one hide the dependent chain of the other
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int t = base + 32 * u + lane;
-            const int tc = min(t, ntasks - 1);
-            const int y = tc >> gshift, gx = tc & G1, gxc = min(gx, gmax);
-            const uint32_t *mid = tile32 + (y + 3) * TSW + gxc + wsh;
+        for (int w = 0; w < 2; ++w) {
+            const int p = base + 32 * w + lane;
+            const int pc = min(p, npairs - 1);
+            const int y = pc >> pshift, gx = (pc & P1) << 1;
+            // rows y - 3, y, y + 3 around the pair's first pixel (clamped task, masked result: no divergence)
+            const uint32_t *mid = tile32 + (y + 3) * TSW + gx + wsh;
             const uint32_t *top = mid - 3 * TSW, *bot = mid + 3 * TSW;
-            const uint32_t v = __byte_perm(mid[a0], mid[a0 + 1], sel0);
-            const uint32_t d4 = __vabsdiffu4(__byte_perm(mid[aE], mid[aE + 1], selE), v);
-            const uint32_t d12 = __vabsdiffu4(__byte_perm(mid[aW], mid[aW + 1], selW), v);
-            const uint32_t d0 = __vabsdiffu4(__byte_perm(bot[a0], bot[a0 + 1], sel0), v);
-            const uint32_t d8 = __vabsdiffu4(__byte_perm(top[a0], top[a0 + 1], sel0), v);
-            const uint32_t e0 = (d0 + bias) | d0, e8 = (d8 + bias) | d8, e4 = (d4 + bias) | d4, e12 = (d12 + bias) | d12;
-            uint32_t pass = (e0 | e8) & (e4 | e12) & 0x80808080u;
-            const int rem = iw - 4 * gxc; // >= 1
-            if (rem < 4) pass &= (1u << (8 * rem)) - 1u;
-            hit[u] = pass != 0 && t < ntasks && gx <= gmax;
+            const uint32_t m0 = mid[0], m1 = mid[1], m2 = mid[2], m3 = mid[3], m4 = mid[4];
+            const uint32_t t1 = top[1], t2 = top[2], t3 = top[3], b1 = bot[1], b2 = bot[2], b3 = bot[3];
+            // normalised words: n1 = pixels 0..3, n2 = pixels 4..7 of the pair, n0 / n3 the four pixels before / after
+            const uint32_t n0 = __funnelshift_r(m0, m1, sh), n1 = __funnelshift_r(m1, m2, sh),
+                           n2 = __funnelshift_r(m2, m3, sh), n3 = __funnelshift_r(m3, m4, sh);
+            const uint32_t T0 = __funnelshift_r(t1, t2, sh), T1 = __funnelshift_r(t2, t3, sh);
+            const uint32_t B0 = __funnelshift_r(b1, b2, sh), B1 = __funnelshift_r(b2, b3, sh);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const uint32_t v = u ? n2 : n1;
+                const uint32_t west = u ? __funnelshift_r(n1, n2, 8) : __funnelshift_r(n0, n1, 8);   // pixels -3..0 of the group
+                const uint32_t east = u ? __funnelshift_r(n2, n3, 24) : __funnelshift_r(n1, n2, 24); // pixels 3..6
+                const uint32_t d4 = __vabsdiffu4(east, v), d12 = __vabsdiffu4(west, v);
+                const uint32_t d0 = __vabsdiffu4(u ? B1 : B0, v), d8 = __vabsdiffu4(u ? T1 : T0, v);
+                const uint32_t e0 = (d0 + bias) | d0, e8 = (d8 + bias) | d8, e4 = (d4 + bias) | d4, e12 = (d12 + bias) | d12;
+                uint32_t pass = (e0 | e8) & (e4 | e12) & 0x80808080u;
+                const int rem = iw - 4 * (gx + u); // tested pixels left in this row from the group's first one
+                if (rem < 4) pass &= rem > 0 ? (1u << (8 * rem)) - 1u : 0u;
+                hit[w][u] = pass != 0 && p < npairs && gx + u <= gmax;
+            }
+            tq[w] = (y << gshift) | gx;
         }
-        const unsigned m0 = __ballot_sync(0xffffffffu, hit[0]), m1 = __ballot_sync(0xffffffffu, hit[1]);
-        const int n0 = __popc(m0);
-        if (hit[0]) glist[nlist + __popc(m0 & lt)] = (uint16_t)(base + lane);
-        if (hit[1]) glist[nlist + n0 + __popc(m1 & lt)] = (uint16_t)(base + 32 + lane);
-        nlist += n0 + __popc(m1);
+        // raster order: lane L's two groups are consecutive, before lane L + 1's; the first 32 pairs before the second
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const unsigned q0 = __ballot_sync(0xffffffffu, hit[w][0]), q1 = __ballot_sync(0xffffffffu, hit[w][1]);
+            const int before = nlist + __popc(q0 & lt) + __popc(q1 & lt);
+            if (hit[w][0]) glist[before] = (uint16_t)tq[w];
+            if (hit[w][1]) glist[before + (hit[w][0] ? 1 : 0)] = (uint16_t)(tq[w] + 1);
+            nlist += __popc(q0) + __popc(q1);
+        }
     }
     return nlist;
 }
