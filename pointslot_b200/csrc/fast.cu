@@ -118,12 +118,13 @@ __device__ __forceinline__ int quick_pass(const uint32_t *tile32, int TSW, int w
     const int sh = 8 * S;
     const unsigned lt = (1u << lane) - 1u;
     int nlist = 0;
-    for (int base = 0; base < npairs; base += 64) {
-        bool hit[2][2];
-        int tq[2];
-        // two independent pairs per lane and iteration, so that the loads of one hide the dependent chain of the other
+    constexpr int QP = 2; // pairs in flight per lane (4: slower, the clamped tail costs more than the overlap gains)
+    for (int base = 0; base < npairs; base += 32 * QP) {
+        bool hit[QP][2];
+        int tq[QP];
+        // independent pairs per lane and iteration, so that the loads of one hide the dependent chain of the other
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
+        for (int w = 0; w < QP; ++w) {
             const int p = base + 32 * w + lane;
             const int pc = min(p, npairs - 1);
             const int y = pc >> pshift, gx = (pc & P1) << 1;
@@ -152,9 +153,9 @@ __device__ __forceinline__ int quick_pass(const uint32_t *tile32, int TSW, int w
             }
             tq[w] = (y << gshift) | gx;
         }
-        // raster order: lane L's two groups are consecutive, before lane L + 1's; the first 32 pairs before the second
+        // raster order: lane L's two groups are consecutive, before lane L + 1's; each block of 32 pairs before the next
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
+        for (int w = 0; w < QP; ++w) {
             const unsigned q0 = __ballot_sync(0xffffffffu, hit[w][0]), q1 = __ballot_sync(0xffffffffu, hit[w][1]);
             const int before = nlist + __popc(q0 & lt) + __popc(q1 & lt);
             if (hit[w][0]) glist[before] = (uint16_t)tq[w];
