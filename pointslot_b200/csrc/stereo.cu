@@ -3,11 +3,14 @@
 // k_stereo_match, one warp per LEFT keypoint, CTAs tiled over (chunk of left keypoints, pair):
 //   * the reference's row table vRowIndices (:2152-2169) is replaced by its defining predicate: right
 //     keypoint iR is a candidate of left row r  <=>  floor(yR - 2*s[oct]) <= r <= ceil(yR + 2*s[oct]),
-//     visited in ascending iR — the same set in the same order.  The band limits, octave and x of all
-//     right keypoints of the pair are staged in shared memory once per CTA;
-//   * lanes stride over the right keypoints, gate on band / octave+-1 / uR in [uL-maxD, uL] (:2200-2209)
+//     the same set.  The band limits, octave and x of all right keypoints of the pair are staged in shared
+//     memory once per CTA and bucketed by 16-row bins of their band (count, scan, scatter in shared memory), so
+//     a left keypoint at row r scans only bin r >> 4 and applies the exact predicate; if the lists do not fit
+//     (very many right keys, or bands spanning many bins) it scans every right key instead;
+//   * lanes stride over the candidates, gate on band / octave+-1 / uR in [uL-maxD, uL] (:2200-2209)
 //     and evaluate the 256-bit Hamming distance (ORBmatcher.cc:2704-2720) with __popc over 8 words;
-//     the first strict minimum below TH_HIGH=100 (:2198,2219) is a warp argmin over (dist << 16 | iR);
+//     the first strict minimum below TH_HIGH=100 (:2198,2219) in ascending iR is a warp argmin over
+//     (dist << 16 | iR), whatever order the candidates were visited in;
 //   * if best < thOrbDist=75 (:2228): 11x11 SAD at 11 offsets in the un-blurred pyramid level of the
 //     left keypoint (:2231-2268), first strict minimum, parabola (:2273-2281), disparity/depth
 //     (:2284-2298).  Float steps are single-rounded __f*_rn operations in the reference's order.
