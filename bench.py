@@ -390,6 +390,12 @@ def run_ours(args, rank, world, local_rank):
                 "launch_pairs": Bsz, "ms_per_launch": stages[dom]["ms_per_launch"],
                 "note": "integer-ALU / issue-bound kernel (ncu: issue slots ~66 % busy, DRAM traffic == algorithmic bytes); durations from a single-stream pass of the same submits inside this run; HBM fraction reported as the contract asks"}
 
+    # whole path: compulsory bytes of all stages per pair x pairs/s, against the same HBM peak (per GPU)
+    path_bytes = float(sum(bytes_pair.values()))
+    path_gbs = path_bytes * (value / world) / 1e9
+    roofline["path"] = {"algorithmic_MB_per_pair": path_bytes / 1e6, "achieved_GBps": path_gbs, "frac": path_gbs / peak,
+                        "note": "all kernels of the path at the multi-stream `value` rate, per GPU"}
+
     # ---- CPU baseline (bounded sample, N=1 only) ---------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
