@@ -269,6 +269,13 @@ int pslot_stereo_debug(pslot_orb *ctx_l, int n_l, int32_t *best_dist, int32_t *b
  * float in [0, 360] against libm. */
 int pslot_debug_steer(int device, const float *angle_deg, int n, float *a, float *b);
 
+/* layout checks (plain C: negative array size on mismatch) */
+typedef char pslot_check_keypoint[(sizeof(pslot_keypoint) == 28) ? 1 : -1];
+typedef char pslot_check_grid_spec[(sizeof(pslot_grid_spec) == 24) ? 1 : -1];
+typedef char pslot_check_area_query[(sizeof(pslot_area_query) == 20) ? 1 : -1];
+typedef char pslot_check_map_point[(sizeof(pslot_map_point) == 24) ? 1 : -1];
+typedef char pslot_check_proj_point[(sizeof(pslot_proj_point) == 32) ? 1 : -1];
+
 #ifdef __cplusplus
 }
 #endif

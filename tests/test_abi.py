@@ -61,3 +61,16 @@ def test_product_never_imports_oracle():
         if p.suffix in (".py", ".cu", ".h", ".cc", ".cpp", ".hpp") and p.is_file():
             txt = p.read_text(errors="ignore")
             assert "import oracle" not in txt and "from oracle" not in txt and "orb_oracle" not in txt, p
+
+
+def test_record_layouts_match_the_header():
+    """The numpy / ctypes records the binding passes must have the sizes the C header asserts."""
+    import ctypes as C
+    from pointslot_b200 import binding as B
+    assert B.KEYPOINT_DTYPE.itemsize == 28
+    assert B.MAP_POINT_DTYPE.itemsize == 24
+    assert B.PROJ_POINT_DTYPE.itemsize == 32
+    assert B.AREA_QUERY_DTYPE.itemsize == 20
+    assert C.sizeof(B.GridSpec) == 24
+    import oracle
+    assert oracle.MAP_POINT_DTYPE == B.MAP_POINT_DTYPE and oracle.PROJ_POINT_DTYPE == B.PROJ_POINT_DTYPE
