@@ -164,3 +164,57 @@ def detect_and_compute(image: np.ndarray, mask: np.ndarray | None, nfeatures=100
             descs.append(np.packbits(bits, bitorder="little"))
     out = np.array(kps, KEYPOINT_DTYPE) if kps else np.zeros(0, KEYPOINT_DTYPE)
     return out, (np.array(descs, np.uint8) if descs else np.zeros((0, 32), np.uint8))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The two OpenCV primitives of this path that the ORB-SLAM extractor does not use, restated (and pinned against cv2 by
+# tests/test_oracle_cvorb.py) so that a device version has an arithmetic to follow.
+# ---------------------------------------------------------------------------------------------------------------------
+def resize_linear_exact(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv::resize(..., INTER_LINEAR_EXACT) for CV_8UC1 (resize.cpp, the bit-exact fixed-point path): per axis
+    f = (d + 0.5) * (n_src / n_dst) - 0.5, s = floor(f) clamped to the image, 8-bit coefficient a = round(frac * 256);
+    H = s0 * (256 - ax) + s1 * ax (16 bit), dst = (H0 * (256 - ay) + H1 * ay + 2^15) >> 16."""
+    def taps(n_dst, n_src):
+        scale = n_src / n_dst
+        s0 = np.zeros(n_dst, np.int64); a = np.zeros(n_dst, np.int64)
+        for d in range(n_dst):
+            f = (d + 0.5) * scale - 0.5
+            s = math.floor(f); fr = f - s
+            if s < 0:
+                s, fr = 0, 0.0
+            if s >= n_src - 1:
+                s, fr = n_src - 1, 0.0
+            s0[d] = s; a[d] = int(np.rint(fr * 256))
+        return s0, a
+    sh, sw = src.shape
+    x0, ax = taps(dw, sw); y0, ay = taps(dh, sh)
+    x1, y1 = np.minimum(x0 + 1, sw - 1), np.minimum(y0 + 1, sh - 1)
+    S = src.astype(np.int64)
+    H = S[:, x0] * (256 - ax)[None, :] + S[:, x1] * ax[None, :]
+    V = H[y0, :] * (256 - ay)[:, None] + H[y1, :] * ay[:, None]
+    return ((V + (1 << 15)) >> 16).astype(np.uint8)
+
+
+def blur_float_separable(img: np.ndarray, fma: bool = True) -> np.ndarray:
+    """What cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) computes on a SUBMATRIX (== cv2.sepFilter2D with the
+    float kernel getGaussianKernel(7, 2, CV_32F)): float32 row filter accumulated left to right, float32 column filter
+    accumulated from the centre tap outwards over the symmetric pairs, round-to-nearest-even to 8 bit.  With AVX2/FMA
+    dispatch (this image's CPUs) every multiply-add is FUSED; a CPU without FMA rounds the products separately, i.e.
+    cv::ORB's descriptors are not bit-reproducible across CPU generations."""
+    import cv2
+    k = cv2.getGaussianKernel(7, 2, cv2.CV_32F).ravel().astype(np.float32)
+    f32 = lambda a: a.astype(np.float32)
+
+    def mad(c, x, acc):  # acc + c * x in float32, fused or not
+        if fma:
+            return f32(np.float64(c) * x.astype(np.float64) + acc.astype(np.float64))
+        return f32(acc + f32(np.float32(c) * x))
+    p = cv2.copyMakeBorder(img, 3, 3, 3, 3, cv2.BORDER_REFLECT_101).astype(np.float32)
+    H, W = img.shape
+    row = f32(np.float32(k[0]) * p[:, 0:W])
+    for i in range(1, 7):
+        row = mad(k[i], p[:, i:i + W], row)
+    col = f32(np.float32(k[3]) * row[3:3 + H, :])
+    for i in (1, 2, 3):
+        col = mad(k[3 - i], f32(row[3 - i:3 - i + H, :] + row[3 + i:3 + i + H, :]), col)
+    return np.clip(np.rint(col.astype(np.float64)), 0, 255).astype(np.uint8)

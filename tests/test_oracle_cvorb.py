@@ -33,3 +33,30 @@ def test_cvorb_path_equals_cv2_orb(shape, seed, masked):
         assert np.array_equal(k[name], np.array([r[col] for r in ref], np.float32)), name
     assert np.array_equal(k["octave"], np.array([r[5] for r in ref], np.int32))
     assert np.array_equal(d, rdesc)
+
+
+def test_resize_linear_exact_restated():
+    from oracle import cvorb_path
+    from pointslot_b200.synth import synth_pair
+    L, _ = synth_pair(1242, 375, 3)
+    noise = np.random.default_rng(1).integers(0, 256, (240, 333), dtype=np.uint8)
+    for img, sizes in ((L, ((1035, 313), (863, 260), (620, 187))), (noise, ((278, 200), (231, 167), (100, 70)))):
+        for (dw, dh) in sizes:
+            assert np.array_equal(cvorb_path.resize_linear_exact(img, dw, dh),
+                                  cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT)), (dw, dh)
+
+
+def test_submatrix_gaussian_blur_restated():
+    """The float separable blur cv::ORB applies to its pyramid levels; fused multiply-adds on CPUs with FMA dispatch."""
+    from oracle import cvorb_path
+    kk = cv2.getGaussianKernel(7, 2, cv2.CV_32F)
+    rng = np.random.default_rng(2)
+    ok = {True: True, False: True}
+    for _ in range(3):
+        img = rng.integers(0, 256, (300, 420), dtype=np.uint8)
+        ref = cv2.sepFilter2D(img, cv2.CV_8U, kk, kk, borderType=cv2.BORDER_REFLECT_101)
+        for fma in (True, False):
+            ok[fma] &= bool(np.array_equal(cvorb_path.blur_float_separable(img, fma), ref))
+        # either way it is NOT the fixed-point blur the ORB-SLAM extractor gets on its cloned level
+        assert not np.array_equal(ref, cv2.GaussianBlur(img, (7, 7), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101))
+    assert ok[True] or ok[False], "neither the fused nor the unfused evaluation order reproduces cv2.sepFilter2D"
