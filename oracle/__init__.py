@@ -85,6 +85,8 @@ def lib():
                                                C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_float, C.c_float, vp]
         L.orc_search_by_projection_last.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float,
                                                     C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp]
+        L.orc_cvorb_detect_and_compute.argtypes = [vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_ssize_t, C.c_int, C.c_float,
+                                                   C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, ip]
         L.orc_distribute_octtree.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_int, vp, vp, vp, ip]
         _lib = L
@@ -223,6 +225,28 @@ def search_by_projection_last(kps_un, frame_desc, u_right, cell_start, indices, 
                                             _ptr(indices), min_x, min_y, inv_w, inv_h, cols, rows, _ptr(pts), _ptr(pt_desc),
                                             len(pts), _ptr(occupied), int(check_orientation), _ptr(out), _ptr(rej))
     return out[:len(pts)].copy(), rej[:len(pts)].copy(), int(n)
+
+
+def cvorb_detect_and_compute(img, mask=None, nfeatures=1000, scale_factor=1.2, nlevels=8, edge_threshold=19,
+                             fast_threshold=20):
+    """cv::ORB::create(nfeatures, scale_factor, nlevels, edge_threshold)->detectAndCompute(img, mask) (reference
+    src/Frame.cc:2623-2627) -> (keypoints ordered by (octave, y, x), descriptors)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    cap = nfeatures + 64 * nlevels + 256
+    while True:
+        kps = np.zeros(cap, KEYPOINT_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        rc = lib().orc_cvorb_detect_and_compute(_ptr(img), img.shape[1], img.shape[0], img.strides[0],
+                                                None if m is None else _ptr(m), 0 if m is None else m.strides[0],
+                                                nfeatures, scale_factor, nlevels, edge_threshold, fast_threshold,
+                                                _ptr(kps), _ptr(desc), cap, C.byref(n))
+        if rc == -2:
+            cap *= 4
+            continue
+        if rc:
+            raise ValueError("bad cv::ORB arguments")
+        return kps[:n.value].copy(), desc[:n.value].copy()
 
 
 # ---------------------------------------------------------------------------------------------

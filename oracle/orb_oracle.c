@@ -1121,3 +1121,224 @@ done:
     free(blocked); free(tmp); free(hist);
     return nmatches;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * cv::ORB::create(nfeatures, 1.2f, nlevels, edgeThreshold)->detectAndCompute(image, mask) — the second extractor of
+ * PointSLOT (reference src/Frame.cc:2623-2627).  The algorithm is OpenCV's
+ * (modules/features2d/src/orb.cpp: ORB_Impl::detectAndCompute, computeKeyPoints, HarrisResponses, ICAngles,
+ * computeOrbDescriptors; OpenCV 4.13 semantics); this restatement is pinned against cv2.ORB_create by
+ * tests/test_oracle_cvorb.py, through oracle/cvorb_path.py which established the arithmetic:
+ *   - pyramid: INTER_LINEAR_EXACT, each level from the previous one (8-bit coefficients, (V + 2^15) >> 16);
+ *   - blur: float separable filter with fused multiply-adds (GaussianBlur on a submatrix), not the fixed-point one;
+ *   - steering: cosf / sinf of the float angle (host libm, as OpenCV links it).
+ * Output order: (octave, y, x) — cv::ORB's own order is what std::nth_element leaves and is not part of the contract.
+ * ------------------------------------------------------------------------------------------------------------ */
+static void resize_linear_exact_u8(const uint8_t *src, int sw, int sh, ptrdiff_t sp, uint8_t *dst, int dw, int dh, ptrdiff_t dp)
+{
+    int *x0 = malloc(sizeof(int) * (size_t)dw * 2), *y0 = malloc(sizeof(int) * (size_t)dh * 2);
+    int *ax = x0 + dw, *ay = y0 + dh;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int nd = pass ? dh : dw, ns = pass ? sh : sw;
+        int *s0 = pass ? y0 : x0, *a = pass ? ay : ax;
+        const double scale = (double)ns / (double)nd;
+        for (int d = 0; d < nd; ++d) {
+            double f = (d + 0.5) * scale - 0.5;
+            int s = (int)floor(f);
+            double fr = f - s;
+            if (s < 0) { s = 0; fr = 0.0; }
+            if (s >= ns - 1) { s = ns - 1; fr = 0.0; }
+            s0[d] = s;
+            a[d] = (int)lrint(fr * 256.0);
+        }
+    }
+    int *H0 = malloc(sizeof(int) * (size_t)dw), *H1 = malloc(sizeof(int) * (size_t)dw);
+    for (int y = 0; y < dh; ++y) {
+        const uint8_t *r0 = src + (ptrdiff_t)y0[y] * sp, *r1 = src + (ptrdiff_t)(y0[y] + 1 < sh ? y0[y] + 1 : sh - 1) * sp;
+        for (int x = 0; x < dw; ++x) {
+            const int xa = x0[x], xb = xa + 1 < sw ? xa + 1 : sw - 1;
+            H0[x] = r0[xa] * (256 - ax[x]) + r0[xb] * ax[x];
+            H1[x] = r1[xa] * (256 - ax[x]) + r1[xb] * ax[x];
+            dst[(ptrdiff_t)y * dp + x] = (uint8_t)((H0[x] * (256 - ay[y]) + H1[x] * ay[y] + (1 << 15)) >> 16);
+        }
+    }
+    free(x0); free(y0); free(H0); free(H1);
+}
+
+
+/* float separable Gaussian 7x7 sigma 2 as cv::sepFilter2D evaluates it on CPUs with FMA dispatch: row taps left to
+ * right, column taps from the centre outwards over the symmetric pairs, every multiply-add fused */
+static void blur_float_separable(const uint8_t *src, int w, int h, ptrdiff_t sp, uint8_t *dst)
+{
+    /* getGaussianKernel(7, 2, CV_32F): exp(-x^2 / 8) normalised in double, stored as float */
+    float k[7];
+    {
+        double g[7], sum = 0;
+        for (int i = 0; i < 7; ++i) { const double x = i - 3; g[i] = exp(-0.125 * x * x); sum += g[i]; }
+        for (int i = 0; i < 7; ++i) k[i] = (float)(g[i] / sum);
+    }
+    float *row = malloc(sizeof(float) * (size_t)w * (size_t)(h + 6));
+    for (int y = -3; y < h + 3; ++y) {
+        const uint8_t *r = src + (ptrdiff_t)reflect101(y, h) * sp;
+        float *o = row + (size_t)(y + 3) * (size_t)w;
+        for (int x = 0; x < w; ++x) {
+            float acc = k[0] * (float)r[reflect101(x - 3, w)];
+            for (int i = 1; i < 7; ++i) acc = fmaf(k[i], (float)r[reflect101(x - 3 + i, w)], acc);
+            o[x] = acc;
+        }
+    }
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const float *c = row + (size_t)(y + 3) * (size_t)w + x;
+            float acc = k[3] * c[0];
+            for (int i = 1; i <= 3; ++i) acc = fmaf(k[3 - i], c[-(ptrdiff_t)i * w] + c[(ptrdiff_t)i * w], acc);
+            long v = lrintf(acc);
+            dst[(size_t)y * (size_t)w + x] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+        }
+    free(row);
+}
+
+typedef struct { float x, y, resp; } cvorb_pt;
+static int cvorb_cmp_desc(const void *a, const void *b)
+{
+    const float x = *(const float *)a, y = *(const float *)b;
+    return x > y ? -1 : x < y ? 1 : 0;
+}
+/* KeyPointsFilter::retainBest: keep everything whose response is >= the n-th largest (ties kept); order preserved */
+static int cvorb_retain_best(cvorb_pt *p, int n, int keep)
+{
+    if (keep < 0 || n <= keep) return n;
+    if (keep == 0) return 0;
+    float *r = malloc(sizeof(float) * (size_t)n);
+    for (int i = 0; i < n; ++i) r[i] = p[i].resp;
+    qsort(r, (size_t)n, sizeof(float), cvorb_cmp_desc);
+    const float thr = r[keep - 1];
+    free(r);
+    int m = 0;
+    for (int i = 0; i < n; ++i)
+        if (p[i].resp >= thr) p[m++] = p[i];
+    return m;
+}
+
+int orc_cvorb_detect_and_compute(const uint8_t *img, int w, int h, ptrdiff_t pitch, const uint8_t *mask,
+                                 ptrdiff_t mask_pitch, int nfeatures, float scale_factor_f, int nlevels,
+                                 int edge_threshold, int fast_threshold, orc_keypoint *kps, uint8_t *desc32, int cap,
+                                 int *n_out)
+{
+    if (nlevels < 1 || nlevels > MAX_LEVELS || w <= 0 || h <= 0) return -1;
+    const double scaleFactor = (double)scale_factor_f; /* ORB::create takes a float, the member is a double */
+    const int patchSize = 31, halfPatch = 15;
+    int umax[HALF_PATCH_SIZE + 2];
+    {
+        int v, v0, vmax = (int)floor(halfPatch * sqrt(2.f) / 2 + 1), vmin = (int)ceil(halfPatch * sqrt(2.f) / 2);
+        for (v = 0; v <= vmax; ++v) umax[v] = orc_cv_round(sqrt((double)halfPatch * halfPatch - v * v));
+        for (v = halfPatch, v0 = 0; v >= vmin; --v) {
+            while (umax[v0] == umax[v0 + 1]) ++v0;
+            umax[v] = v0;
+            ++v0;
+        }
+    }
+    /* feature quota per level (computeKeyPoints) */
+    int quota[MAX_LEVELS];
+    {
+        const float factor = (float)(1.0 / scaleFactor);
+        float nd = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+        int sum = 0;
+        for (int l = 0; l < nlevels - 1; ++l) { quota[l] = orc_cv_round(nd); sum += quota[l]; nd *= factor; }
+        quota[nlevels - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
+    }
+    uint8_t *prev = NULL, *prevm = NULL;
+    int pw = 0, ph = 0, n = 0, rc = 0;
+    const float deg2rad = (float)(3.1415926535897932384626433832795 / 180.f);
+    for (int level = 0; level < nlevels && rc == 0; ++level) {
+        const float scale = (float)pow(scaleFactor, (double)level);
+        const int lw = orc_cv_round(w / scale), lh = orc_cv_round(h / scale);
+        if (lw < 2 * edge_threshold + 1 || lh < 2 * edge_threshold + 1) break; /* nothing can pass the border filter */
+        uint8_t *cur = malloc((size_t)lw * (size_t)lh), *curm = mask ? malloc((size_t)lw * (size_t)lh) : NULL;
+        if (level == 0) {
+            for (int y = 0; y < lh; ++y) {
+                memcpy(cur + (size_t)y * lw, img + (ptrdiff_t)y * pitch, (size_t)lw);
+                if (mask) memcpy(curm + (size_t)y * lw, mask + (ptrdiff_t)y * mask_pitch, (size_t)lw);
+            }
+        } else {
+            resize_linear_exact_u8(prev, pw, ph, pw, cur, lw, lh, lw);
+            if (mask) {
+                resize_linear_exact_u8(prevm, pw, ph, pw, curm, lw, lh, lw);
+                for (size_t i = 0; i < (size_t)lw * lh; ++i) curm[i] = curm[i] > 254 ? curm[i] : 0; /* THRESH_TOZERO 254 */
+            }
+        }
+        /* FAST + mask + border filter + retainBest(2 * quota) by the FAST score */
+        int cap_f = 1 << 14, nf;
+        int *fx, *fy, *fr;
+        for (;;) {
+            fx = malloc(sizeof(int) * 3 * (size_t)cap_f); fy = fx + cap_f; fr = fy + cap_f;
+            nf = orc_fast9_16(cur, lw, lh, lw, fast_threshold, cap_f, fx, fy, fr);
+            if (nf <= cap_f) break;
+            free(fx); cap_f = nf;
+        }
+        cvorb_pt *p = malloc(sizeof(cvorb_pt) * (size_t)(nf > 0 ? nf : 1));
+        int m = 0;
+        for (int i = 0; i < nf; ++i) {
+            if (curm && curm[(size_t)fy[i] * lw + fx[i]] == 0) continue; /* runByPixelsMask */
+            if (fx[i] < edge_threshold || fx[i] >= lw - edge_threshold || fy[i] < edge_threshold || fy[i] >= lh - edge_threshold)
+                continue; /* runByImageBorder */
+            p[m].x = (float)fx[i]; p[m].y = (float)fy[i]; p[m].resp = (float)fr[i]; ++m;
+        }
+        free(fx);
+        m = cvorb_retain_best(p, m, 2 * quota[level]);
+        /* HarrisResponses: 7x7 block, k = 0.04, float score in OpenCV's evaluation order */
+        {
+            const int blockSize = 7, r = blockSize / 2;
+            const float harris_k = 0.04f;
+            float scale1 = 1.f / ((1 << 2) * blockSize * 255.f);
+            const float scale_sq_sq = scale1 * scale1 * scale1 * scale1;
+            for (int i = 0; i < m; ++i) {
+                const int x0 = (int)p[i].x, y0 = (int)p[i].y;
+                int a = 0, b = 0, c = 0;
+                for (int dy = -r; dy <= r; ++dy)
+                    for (int dx = -r; dx <= r; ++dx) {
+                        const uint8_t *q = cur + (size_t)(y0 + dy) * lw + (x0 + dx);
+                        const int Ix = (q[1] - q[-1]) * 2 + (q[-lw + 1] - q[-lw - 1]) + (q[lw + 1] - q[lw - 1]);
+                        const int Iy = (q[lw] - q[-lw]) * 2 + (q[lw - 1] - q[-lw - 1]) + (q[lw + 1] - q[-lw + 1]);
+                        a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+                    }
+                p[i].resp = ((float)a * b - (float)c * c - harris_k * ((float)a + b) * ((float)a + b)) * scale_sq_sq;
+            }
+        }
+        m = cvorb_retain_best(p, m, quota[level]);
+        uint8_t *blur = malloc((size_t)lw * (size_t)lh);
+        blur_float_separable(cur, lw, lh, lw, blur);
+        const float inv = 1.f / scale;
+        for (int i = 0; i < m && rc == 0; ++i) { /* p is still in raster order: (y, x) ascending */
+            if (n >= cap) { rc = -2; break; }
+            const int x0 = (int)p[i].x, y0 = (int)p[i].y;
+            orc_keypoint *K = &kps[n];
+            K->angle = ic_angle(cur, lw, x0, y0, umax);
+            K->x = p[i].x * scale; K->y = p[i].y * scale;
+            K->size = patchSize * scale; K->response = p[i].resp; K->octave = level; K->class_id = -1;
+            /* computeOrbDescriptors */
+            const int cy = orc_cv_round(K->y * inv), cx = orc_cv_round(K->x * inv);
+            const float ang = K->angle * deg2rad;
+            const float a = cosf(ang), b = sinf(ang);
+            uint8_t *d = desc32 + (size_t)n * 32;
+            for (int j = 0; j < 32; ++j) {
+                int byte = 0;
+                for (int t = 0; t < 8; ++t) {
+                    const int8_t *pt = k_pattern + (size_t)(j * 8 + t) * 4;
+                    const float ax0 = pt[0] * a - pt[1] * b, ay0 = pt[0] * b + pt[1] * a;
+                    const float ax1 = pt[2] * a - pt[3] * b, ay1 = pt[2] * b + pt[3] * a;
+                    const int t0 = blur[(size_t)(cy + (int)lrintf(ay0)) * lw + (cx + (int)lrintf(ax0))];
+                    const int t1 = blur[(size_t)(cy + (int)lrintf(ay1)) * lw + (cx + (int)lrintf(ax1))];
+                    byte |= (t0 < t1) << t;
+                }
+                d[j] = (uint8_t)byte;
+            }
+            ++n;
+        }
+        free(blur); free(p);
+        free(prev); free(prevm);
+        prev = cur; prevm = curm; pw = lw; ph = lh;
+    }
+    free(prev); free(prevm);
+    *n_out = n;
+    return rc;
+}

@@ -129,6 +129,14 @@ int orc_search_by_projection_last(const orc_keypoint *kps_un, const uint8_t *fra
                                   int n_pts, const uint8_t *occupied, int check_orientation, int *match_of_pt,
                                   uint8_t *rejected);
 
+/* cv::ORB::create(nfeatures, scaleFactor, nlevels, edgeThreshold)->detectAndCompute(image, mask) (reference
+ * src/Frame.cc:2623-2627; OpenCV 4.13 orb.cpp), HARRIS score, patch 31, WTA_K 2; mask may be NULL; output ordered by
+ * (octave, y, x); returns 0, -1 (bad arguments) or -2 (cap too small) */
+int orc_cvorb_detect_and_compute(const uint8_t *img, int w, int h, ptrdiff_t pitch, const uint8_t *mask,
+                                 ptrdiff_t mask_pitch, int nfeatures, float scale_factor, int nlevels,
+                                 int edge_threshold, int fast_threshold, orc_keypoint *kps, uint8_t *desc32, int cap,
+                                 int *n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,3 +60,24 @@ def test_submatrix_gaussian_blur_restated():
         # either way it is NOT the fixed-point blur the ORB-SLAM extractor gets on its cloned level
         assert not np.array_equal(ref, cv2.GaussianBlur(img, (7, 7), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101))
     assert ok[True] or ok[False], "neither the fused nor the unfused evaluation order reproduces cv2.sepFilter2D"
+
+
+@pytest.mark.parametrize("shape,seed,masked", [((375, 1242), 3, False), ((375, 1242), 4, True), ((480, 752), 9, True),
+                                               ((222, 333), 5, False), ((120, 200), 6, False)])
+def test_c_oracle_equals_cv2_orb(shape, seed, masked, oracle_mod):
+    """The C restatement (orc_cvorb_detect_and_compute) against cv2.ORB_create itself."""
+    from pointslot_b200.synth import synth_pair
+    H, W = shape
+    L, _ = synth_pair(W, H, seed)
+    mask = None
+    if masked:
+        mask = np.zeros_like(L)
+        mask[H // 4:3 * H // 4, W // 6:W // 2] = 255
+        mask[H // 8:H // 2, 2 * W // 3:W - 40] = 255
+    ref, rdesc = _cv2_sorted(L, mask)
+    k, d = oracle_mod.cvorb_detect_and_compute(L, mask)
+    assert len(k) == len(ref)
+    for name, col in (("x", 0), ("y", 1), ("size", 2), ("angle", 3), ("response", 4)):
+        assert np.array_equal(k[name], np.array([r[col] for r in ref], np.float32)), name
+    assert np.array_equal(k["octave"], np.array([r[5] for r in ref], np.int32))
+    assert np.array_equal(d, rdesc)
