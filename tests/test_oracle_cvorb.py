@@ -81,3 +81,25 @@ def test_c_oracle_equals_cv2_orb(shape, seed, masked, oracle_mod):
         assert np.array_equal(k[name], np.array([r[col] for r in ref], np.float32)), name
     assert np.array_equal(k["octave"], np.array([r[5] for r in ref], np.int32))
     assert np.array_equal(d, rdesc)
+
+
+def test_c_oracle_equals_cv2_orb_on_varied_content(oracle_mod):
+    """Noise, flat, saturated and checkerboard content at odd sizes: ties in the scores and sparse levels."""
+    rng = np.random.default_rng(7)
+    cases = []
+    for (h, w) in ((97, 131), (150, 150), (241, 322), (64, 500)):
+        cases.append(rng.integers(0, 256, (h, w), dtype=np.uint8))                      # noise: every quota overflows
+        yy, xx = np.mgrid[0:h, 0:w]
+        cases.append((((xx // 9 + yy // 7) & 1) * 200 + 20).astype(np.uint8))           # checkerboard: massive score ties
+        cases.append(np.clip(rng.normal(128, 60, (h, w)), 0, 255).astype(np.uint8) // 64 * 64)  # posterised
+    cases.append(np.full((120, 160), 77, np.uint8))                                     # flat: no keypoints at all
+    for img in cases:
+        ref, rdesc = _cv2_sorted(img, None)
+        k, d = oracle_mod.cvorb_detect_and_compute(img)
+        assert len(k) == len(ref), img.shape
+        if len(ref):
+            got = np.stack([k["x"], k["y"], k["size"], k["angle"], k["response"]], 1)
+            want = np.array([r[:5] for r in ref], np.float32)
+            assert np.array_equal(got, want), img.shape
+            assert np.array_equal(k["octave"], np.array([r[5] for r in ref], np.int32))
+            assert np.array_equal(d, rdesc), img.shape
