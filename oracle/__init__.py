@@ -78,6 +78,8 @@ def lib():
         L.orc_cvt_gray.restype = None
         L.orc_steer_coeffs.argtypes = [vp, C.c_int, vp, vp]
         L.orc_steer_coeffs.restype = None
+        L.orc_glibc_sincosf_n.argtypes = [vp, C.c_int, vp, vp]
+        L.orc_glibc_sincosf_n.restype = None
         L.orc_assign_grid.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp]
         L.orc_features_in_area.argtypes = [vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
                                            C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, vp]
@@ -147,6 +149,24 @@ def steer_coeffs(angle_deg: np.ndarray):
     a = np.empty_like(ang); b = np.empty_like(ang)
     lib().orc_steer_coeffs(_ptr(ang), ang.size, _ptr(a), _ptr(b))
     return a, b
+
+
+def glibc_sincosf(x: np.ndarray):
+    """-> (cosf(x), sinf(x)) by the oracle's restatement of glibc's algorithm (orb_oracle.c: orc_glibc_cosf)."""
+    x = np.ascontiguousarray(x, np.float32)
+    c = np.empty_like(x); s = np.empty_like(x)
+    lib().orc_glibc_sincosf_n(_ptr(x), x.size, _ptr(c), _ptr(s))
+    return c, s
+
+
+def libm_sincosf(x: np.ndarray):
+    """-> (cosf(x), sinf(x)) by the host's libm, the function the reference binary calls (ORBextractor.cc:112-113)."""
+    m = C.CDLL("libm.so.6")
+    m.cosf.restype = C.c_float; m.cosf.argtypes = [C.c_float]
+    m.sinf.restype = C.c_float; m.sinf.argtypes = [C.c_float]
+    x = np.ascontiguousarray(x, np.float32)
+    return (np.array([m.cosf(float(v)) for v in x.ravel()], np.float32).reshape(x.shape),
+            np.array([m.sinf(float(v)) for v in x.ravel()], np.float32).reshape(x.shape))
 
 
 def hamming256(a: np.ndarray, b: np.ndarray) -> int:
@@ -334,6 +354,10 @@ class OracleExtractor:
 
     def tie_sensitive(self, level: int) -> bool:
         return bool(lib().orc_level_tie_sensitive(self._h, level))
+
+    def tie_flags(self, level: int) -> int:
+        """bit 0: retained set depends on the heap-address tie of ORBextractor.cc:684; bit 1: only the order does."""
+        return int(lib().orc_level_tie_sensitive(self._h, level))
 
 
 def stereo_match(eL: OracleExtractor, eR: OracleExtractor, kL, dL, kR, dR, bf: float, maxD: float, debug=False):

@@ -16,6 +16,20 @@ import numpy as np
 EDGE = 19
 HALF = 15
 
+import ctypes as _C  # noqa: E402
+
+_libm = _C.CDLL("libm.so.6")  # the reference binary's own cosf / sinf (glibc)
+_libm.cosf.restype = _C.c_float; _libm.cosf.argtypes = [_C.c_float]
+_libm.sinf.restype = _C.c_float; _libm.sinf.argtypes = [_C.c_float]
+
+
+def _cosf(x: float):
+    return np.float32(_libm.cosf(x))
+
+
+def _sinf(x: float):
+    return np.float32(_libm.sinf(x))
+
 
 def f32(v):
     return np.float32(v)
@@ -200,7 +214,7 @@ class Cv2Extractor:
     def descriptor(self, blurred, x, y, angle):
         factorPI = f32(math.pi / 180.0)
         ang = f32(f32(angle) * factorPI)
-        a = f32(math.cos(float(ang))); b = f32(math.sin(float(ang)))
+        a, b = _cosf(float(ang)), _sinf(float(ang))  # `(float)cos(float)` is std::cos(float) = libm cosf (:112-113)
         d = np.zeros(32, np.uint8)
         for i in range(256):
             x0, y0, x1, y1 = (f32(v) for v in self.pattern[i])

@@ -25,6 +25,8 @@ from pathlib import Path
 
 import numpy as np
 
+from .cv2_path import _cosf, _sinf
+
 F = np.float32
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                            ("octave", "<i4"), ("class_id", "<i4")])
@@ -153,7 +155,7 @@ def detect_and_compute(image: np.ndarray, mask: np.ndarray | None, nfeatures=100
             kps.append((px, py, F(F(patch_size) * s), ang, resp, level, -1))
             cy, cx = _cv_round(F(py * inv)), _cv_round(F(px * inv))
             a_ = F(F(ang) * deg2rad)
-            a, b = F(np.cos(a_)), F(np.sin(a_))
+            a, b = _cosf(float(a_)), _sinf(float(a_))  # libm cosf / sinf, as OpenCV's orb.cpp calls them
 
             def sample(qx, qy):
                 fx = (qx * a).astype(np.float32) - (qy * b).astype(np.float32)

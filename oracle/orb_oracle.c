@@ -435,8 +435,13 @@ int orc_distribute_octtree(const int *x, const int *y, const int *resp, int n,
                     divide_node(P[j].node, x, y, c);
                     push_children(&L, c, &V, &nV, &capV, NULL);
                     qlist_erase(&L, P[j].node);
+                    /* Rule C.1 bookkeeping.  bit 1: two equal-size nodes were both split in this run - under another
+                       allocator they are split in another order, which permutes the list (keypoint order, descriptor
+                       rows, stereo iR ties) without changing the set.  bit 0: the cut of :731 falls inside an
+                       equal-size run - the retained SET depends on the tie rule. */
+                    if (tie_sensitive && j + 1 < nP && P[j + 1].size == P[j].size) *tie_sensitive |= 2;
                     if (L.size >= N) { /* :731 */
-                        if (tie_sensitive && j > 0 && P[j - 1].size == P[j].size) *tie_sensitive = 1;
+                        if (tie_sensitive && j > 0 && P[j - 1].size == P[j].size) *tie_sensitive |= 1;
                         break;
                     }
                 }
@@ -673,13 +678,62 @@ static int compute_keypoints_octtree(orc_extractor *e)
     return 0;
 }
 
-/* steering coefficients (:112-113); rule: cos/sin evaluated in double, rounded to float (DESIGN.md parity rule 3) */
+/* ------------------------------------------------------------------------------------------ */
+/* cosf / sinf exactly as the reference binary gets them.  computeOrbDescriptor writes          */
+/* `(float)cos(angle)` with a float argument under `using namespace std` (ORBextractor.cc:      */
+/* 112-113), which resolves to std::cos(float) = glibc cosf.  glibc >= 2.28 implements          */
+/* sinf/cosf/sincosf with the algorithm of ARM's optimized-routines (sysdeps/ieee754/flt-32/    */
+/* s_sincosf.h): reduce by pi/2 with a 2^24-prescaled multiply, then an even or odd polynomial  */
+/* in double, one final rounding to float.  Restated here (constants = glibc's                  */
+/* __sincosf_table) so the oracle does not depend on the host libm; tests/test_oracle_cv2.py    */
+/* checks it against this image's libm (glibc 2.39), and an exhaustive sweep of all 1.09e9      */
+/* floats in [0, 2 pi] found no differing result for cosf nor sinf, with or without FMA          */
+/* contraction of the double arithmetic (profiles/r02_sincosf_sweep.txt).  Only the ranges the  */
+/* path can reach are covered: |x| < 120.                                                       */
+/* ------------------------------------------------------------------------------------------ */
+static const double SC_HPI_INV = 0x1.45F306DC9C883p+23, SC_HPI = 0x1.921FB54442D18p0;
+static const double SC_C[5] = {0x1p0, -0x1.ffffffd0c621cp-2, 0x1.55553e1068f19p-5, -0x1.6c087e89a359dp-10, 0x1.99343027bf8c3p-16};
+static const double SC_S[3] = {-0x1.555545995a603p-3, 0x1.1107605230bc4p-7, -0x1.994eb3774cf24p-13};
+static inline uint32_t sc_abstop12(float x) { uint32_t u; memcpy(&u, &x, 4); return (u >> 20) & 0x7ff; }
+static inline float sc_poly(double x, double x2, int negcos, int n)
+{
+    if ((n & 1) == 0) { /* sine polynomial */
+        const double x3 = x * x2, s1 = SC_S[1] + x2 * SC_S[2], x7 = x3 * x2, s = x + x3 * SC_S[0];
+        return (float)(s + x7 * s1);
+    }
+    const double g = negcos ? -1.0 : 1.0; /* glibc's second table row: the cosine coefficients negated */
+    const double x4 = x2 * x2, c2 = g * SC_C[3] + x2 * (g * SC_C[4]), c1 = g * SC_C[0] + x2 * (g * SC_C[1]);
+    const double x6 = x4 * x2, c = c1 + x4 * (g * SC_C[2]);
+    return (float)(c + x6 * c2);
+}
+static inline float sc_eval(float y, int cosine)
+{
+    static const double sign[4] = {1.0, -1.0, -1.0, 1.0};
+    double x = y;
+    if (sc_abstop12(y) < sc_abstop12(0x1.921FB6p-1f)) { /* |y| < pi/4 */
+        if (sc_abstop12(y) < sc_abstop12(0x1p-12f)) return cosine ? 1.0f : y;
+        return sc_poly(x, x * x, 0, cosine);
+    }
+    /* reduce_fast: valid for |y| < 120 (angles here are below 2 pi) */
+    const double r = x * SC_HPI_INV;
+    const int n = ((int32_t)r + 0x800000) >> 24;
+    x = x - n * SC_HPI;
+    return sc_poly(x * sign[n & 3], x * x, (n & 2) != 0, cosine ? n ^ 1 : n);
+}
+float orc_glibc_cosf(float x) { return sc_eval(x, 1); }
+float orc_glibc_sinf(float x) { return sc_eval(x, 0); }
+void orc_glibc_sincosf_n(const float *x, int n, float *c, float *s)
+{
+    for (int i = 0; i < n; ++i) { c[i] = sc_eval(x[i], 1); s[i] = sc_eval(x[i], 0); }
+}
+
+/* steering coefficients (:112-113): cosf / sinf of the float angle (DESIGN.md parity rule 3) */
 static inline void steer_coeffs(float kp_angle, float *a, float *b)
 {
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
     float angle = kp_angle * factorPI;
-    *a = (float)cos((double)angle);
-    *b = (float)sin((double)angle);
+    *a = orc_glibc_cosf(angle);
+    *b = orc_glibc_sinf(angle);
 }
 
 void orc_steer_coeffs(const float *angle_deg, int n, float *a, float *b)
@@ -1130,7 +1184,7 @@ done:
  * tests/test_oracle_cvorb.py, through oracle/cvorb_path.py which established the arithmetic:
  *   - pyramid: INTER_LINEAR_EXACT, each level from the previous one (8-bit coefficients, (V + 2^15) >> 16);
  *   - blur: float separable filter with fused multiply-adds (GaussianBlur on a submatrix), not the fixed-point one;
- *   - steering: cosf / sinf of the float angle (host libm, as OpenCV links it).
+ *   - steering: cosf / sinf of the float angle (glibc's algorithm, restated above: orc_glibc_cosf).
  * Output order: (octave, y, x) — cv::ORB's own order is what std::nth_element leaves and is not part of the contract.
  * ------------------------------------------------------------------------------------------------------------ */
 static void resize_linear_exact_u8(const uint8_t *src, int sw, int sh, ptrdiff_t sp, uint8_t *dst, int dw, int dh, ptrdiff_t dp)
@@ -1318,7 +1372,7 @@ int orc_cvorb_detect_and_compute(const uint8_t *img, int w, int h, ptrdiff_t pit
             /* computeOrbDescriptors */
             const int cy = orc_cv_round(K->y * inv), cx = orc_cv_round(K->x * inv);
             const float ang = K->angle * deg2rad;
-            const float a = cosf(ang), b = sinf(ang);
+            const float a = orc_glibc_cosf(ang), b = orc_glibc_sinf(ang);
             uint8_t *d = desc32 + (size_t)n * 32;
             for (int j = 0; j < 32; ++j) {
                 int byte = 0;

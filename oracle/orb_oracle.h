@@ -5,12 +5,15 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs as the checker
  * and the timed CPU baseline.  The shipped library (libpslot_orb.so) never links or calls it.
  *
- * PARITY STATUS: "parity unpinned" by the reference — it ships no tests or golden vectors
- *  and its OpenCV is un-vendored.  The primitives restated here (resize
- * INTER_LINEAR, FAST 9-16 + NMS, GaussianBlur 7x7 s=2, fastAtan2, cvRound) are pinned instead
- * against OpenCV 4.13.0 through cv2 in tests/test_oracle_cv2.py and the fixtures under
- * tests/golden/.  Explicit rules replace the reference's two UB / address-dependent spots
- * (DESIGN.md "Parity rules"): quadtree ties -> later-created node first; maxD explicit.
+ * PARITY STATUS: pinned against the reference's own code compiled in this container (oracle/_ref,
+ * `make -C oracle ref`, tests/test_oracle_reference.py): byte-identical extractor output and bit-equal
+ * stereo results versus the reference binary built with a monotonic allocator; versus the stock-malloc
+ * build the only delta is the heap-address tie of ORBextractor.cc:684 (0.84 % of the keypoint set,
+ * profiles/r02_ref_delta.txt).  The primitives restated here (resize INTER_LINEAR, FAST 9-16 + NMS,
+ * GaussianBlur 7x7 s=2, fastAtan2, cvRound) are pinned against OpenCV 4.13.0 through cv2 in
+ * tests/test_oracle_cv2.py, cosf/sinf against glibc 2.39.  Explicit rules replace the reference's two
+ * UB / address-dependent spots (DESIGN.md "Parity rules"): quadtree ties -> later-created node first;
+ * maxD explicit.
  *
  * Reference files restated (paths under /root/reference):
  *   src/ORBextractor.cc:77-147, 410-853, 1034-1132   include/ORBextractor.h
@@ -57,7 +60,9 @@ const uint8_t *orc_blurred_ptr(const orc_extractor *e, int level); /* NULL if le
 int orc_level_candidates(const orc_extractor *e, int level, int cap, int *x, int *y, int *resp);
 /* keypoints after DistributeOctTree + border offset, level coordinates, list order */
 int orc_level_keypoints(const orc_extractor *e, int level, int cap, int *x, int *y, int *resp, float *angle);
-/* 1 if the fine phase of DistributeOctTree stopped inside a run of equal-size nodes (tie-sensitive) */
+/* Allocator (heap-address) sensitivity of DistributeOctTree's fine phase, ORBextractor.cc:684 (rule C.1):
+ * bit 0: the cut of :731 fell inside a run of equal-size nodes (the retained SET depends on the tie rule);
+ * bit 1: two equal-size nodes were both split in one run (only the list ORDER depends on the tie rule). */
 int orc_level_tie_sensitive(const orc_extractor *e, int level);
 
 /* Frame::ComputeStereoMatches (Frame.cc:2142-2316) on the pyramids held by eL / eR.
@@ -83,6 +88,10 @@ float orc_fast_atan2(float y, float x);
 int orc_cv_round(double v);
 /* cv::cvtColor(RGB/BGR(A) -> GRAY) for 8-bit images as OpenCV 4.13 computes it (called at Tracking.cc:1014-1039) */
 void orc_cvt_gray(const uint8_t *src, int w, int h, ptrdiff_t spitch, int channels, int rgb_order, uint8_t *dst, ptrdiff_t dpitch);
+/* glibc >= 2.28 cosf / sinf (the functions `(float)cos(float)` resolves to in ORBextractor.cc:112-113), |x| < 120 */
+float orc_glibc_cosf(float x);
+float orc_glibc_sinf(float x);
+void orc_glibc_sincosf_n(const float *x, int n, float *c, float *s);
 /* steering coefficients of computeOrbDescriptor (ORBextractor.cc:112-113) for n angles in degrees */
 void orc_steer_coeffs(const float *angle_deg, int n, float *a, float *b);
 /* DistributeOctTree alone (ORBextractor.cc:539-763); in/out arrays of n / cap ints */

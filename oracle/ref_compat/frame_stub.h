@@ -1,0 +1,77 @@
+// frame_stub.h - the smallest Frame / MapPoint / ORBmatcher class shells under which the REFERENCE's own member-function
+// bodies (lifted verbatim at build time by extract_fn.py) compile: each class declares exactly the members those bodies
+// read or write, with the reference's names and types (include/Frame.h:225-316, include/MapPoint.h:110-120,
+// include/ORBmatcher.h:45-130).  No algorithm lives here.  Test infrastructure only.
+#pragma once
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <set>
+#include <vector>
+
+#include "ORBextractor.h" // the reference's own header (-I <reference>/include): mvImagePyramid etc.
+
+#define FRAME_GRID_ROWS 48 // include/Frame.h:40-41
+#define FRAME_GRID_COLS 64
+
+namespace ORB_SLAM2 {
+using namespace std;
+
+class MapPoint {
+public:
+    // tracking fields written by Frame::isInFrustum (include/MapPoint.h:110-116)
+    float mTrackProjX, mTrackProjY, mTrackProjXR;
+    bool mbTrackInView;
+    int mnTrackScaleLevel;
+    float mTrackViewCos;
+    // state behind the accessors
+    bool bad_;
+    int nobs_;
+    cv::Mat desc_, pos_;
+    MapPoint() : mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), mbTrackInView(false), mnTrackScaleLevel(0),
+                 mTrackViewCos(0), bad_(false), nobs_(0) {}
+    bool isBad() { return bad_; }
+    int Observations() { return nobs_; }
+    cv::Mat GetDescriptor() { return desc_.clone(); }
+    cv::Mat GetWorldPos() { return pos_.clone(); }
+};
+
+class Frame {
+public:
+    void ComputeStereoMatches();
+    void AssignFeaturesToGrid();
+    vector<size_t> GetFeaturesInArea(const float &x, const float &y, const float &r, const int minLevel = -1, const int maxLevel = -1) const;
+    bool PosInGrid(const cv::KeyPoint &kp, int &posX, int &posY);
+
+    ORBextractor *mpORBextractorLeft, *mpORBextractorRight;
+    static float fx, fy, cx, cy;
+    float mbf, mb;
+    int N;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
+    std::vector<float> mvuRight, mvDepth;
+    cv::Mat mDescriptors, mDescriptorsRight;
+    std::vector<MapPoint *> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+    static float mfGridElementWidthInv, mfGridElementHeightInv;
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    cv::Mat mTcw;
+    vector<float> mvScaleFactors, mvInvScaleFactors;
+    static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+    Frame() : mpORBextractorLeft(nullptr), mpORBextractorRight(nullptr), mbf(0), mb(0), N(0) {}
+};
+
+class ORBmatcher {
+public:
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+    static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
+    int SearchByProjection(Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th = 3);
+    int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono);
+    static const int TH_LOW, TH_HIGH, TH_HIGH_FORDYNAMIC, RADIUS_FORDYNAMIC, HISTO_LENGTH;
+    float RadiusByViewingCos(const float &viewCos);
+    void ComputeThreeMaxima(std::vector<int> *histo, const int L, int &ind1, int &ind2, int &ind3);
+    float mfNNratio;
+    bool mbCheckOrientation;
+};
+
+} // namespace ORB_SLAM2

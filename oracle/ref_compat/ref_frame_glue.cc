@@ -1,0 +1,182 @@
+// ref_frame_glue.cc - C entry points around the REFERENCE's own Frame::ComputeStereoMatches, AssignFeaturesToGrid,
+// GetFeaturesInArea, PosInGrid (src/Frame.cc) and ORBmatcher::SearchByProjection x2, DescriptorDistance
+// (src/ORBmatcher.cc).  The function bodies are the reference's text, lifted at build time into $(PIECES)/*.inc by
+// extract_fn.py and compiled here inside the class shells of frame_stub.h.  Test infrastructure only.
+#include <cstdint>
+#include <cstring>
+#include <map>
+
+#include "frame_stub.h"
+
+using namespace std;
+
+namespace ORB_SLAM2 {
+float Frame::fx, Frame::fy, Frame::cx, Frame::cy;
+float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv;
+float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+#include "matcher_consts.inc"
+#include "frame_fns.inc"
+#include "matcher_fns.inc"
+} // namespace ORB_SLAM2
+
+using ORB_SLAM2::Frame;
+using ORB_SLAM2::MapPoint;
+using ORB_SLAM2::ORBextractor;
+using ORB_SLAM2::ORBmatcher;
+
+static void set_keys(vector<cv::KeyPoint> &dst, const void *kps, int n)
+{
+    static_assert(sizeof(cv::KeyPoint) == 28, "cv::KeyPoint layout");
+    dst.resize((size_t)n);
+    if (n) memcpy(dst.data(), kps, sizeof(cv::KeyPoint) * (size_t)n);
+}
+static cv::Mat desc_mat(const uint8_t *d, int n)
+{
+    cv::Mat m(n > 0 ? n : 1, 32, CV_8UC1);
+    if (n) memcpy(m.data, d, (size_t)n * 32);
+    return m;
+}
+
+extern "C" {
+
+// Frame::ComputeStereoMatches (Frame.cc:2142-2316) on the pyramids the two reference extractors hold from their last
+// operator().  mb is an explicit argument: the reference reads it before the constructor assigns it (rule C.2).
+int reff_stereo(void *extL, void *extR, const void *kL, int nL, const uint8_t *dL, const void *kR, int nR,
+                const uint8_t *dR, float mbf, float mb, float *uright, float *depth)
+{
+    Frame F;
+    F.mpORBextractorLeft = static_cast<ORBextractor *>(extL);
+    F.mpORBextractorRight = static_cast<ORBextractor *>(extR);
+    F.mvScaleFactors = F.mpORBextractorLeft->GetScaleFactors();
+    F.mvInvScaleFactors = F.mpORBextractorLeft->GetInverseScaleFactors();
+    set_keys(F.mvKeys, kL, nL); set_keys(F.mvKeysRight, kR, nR);
+    F.N = nL; F.mbf = mbf; F.mb = mb;
+    F.mDescriptors = desc_mat(dL, nL); F.mDescriptorsRight = desc_mat(dR, nR);
+    F.ComputeStereoMatches();
+    memcpy(uright, F.mvuRight.data(), sizeof(float) * (size_t)nL);
+    memcpy(depth, F.mvDepth.data(), sizeof(float) * (size_t)nL);
+    return 0;
+}
+
+int reff_hamming256(const uint8_t *a, const uint8_t *b)
+{
+    alignas(4) uint8_t ba[32], bb[32];
+    memcpy(ba, a, 32); memcpy(bb, b, 32);
+    cv::Mat ma(1, 32, CV_8UC1, ba), mb_(1, 32, CV_8UC1, bb);
+    return ORBmatcher::DescriptorDistance(ma, mb_);
+}
+
+// ---- a stub Frame that lives across calls: grid + projection searches --------------------------------------------------
+void *reff_frame_create(const void *kps_un, int n, const uint8_t *desc, const float *uright, const float *scale_factors,
+                        int nlevels, float min_x, float max_x, float min_y, float max_y, float inv_w, float inv_h)
+{
+    Frame *F = new Frame;
+    set_keys(F->mvKeysUn, kps_un, n);
+    F->mvKeys = F->mvKeysUn;
+    F->N = n;
+    F->mDescriptors = desc_mat(desc, n);
+    F->mvuRight.assign(uright, uright + n);
+    F->mvScaleFactors.assign(scale_factors, scale_factors + nlevels);
+    F->mvpMapPoints.assign((size_t)n, nullptr);
+    F->mvbOutlier.assign((size_t)n, false);
+    Frame::mnMinX = min_x; Frame::mnMaxX = max_x; Frame::mnMinY = min_y; Frame::mnMaxY = max_y;
+    Frame::mfGridElementWidthInv = inv_w; Frame::mfGridElementHeightInv = inv_h;
+    F->AssignFeaturesToGrid();
+    return F;
+}
+void reff_frame_destroy(void *h) { delete static_cast<Frame *>(h); }
+
+// mGrid flattened to CSR, cell = i * FRAME_GRID_ROWS + j; returns the number of indices
+int reff_frame_grid(void *h, int *cell_start, int *indices)
+{
+    Frame &F = *static_cast<Frame *>(h);
+    int k = 0;
+    for (int i = 0; i < FRAME_GRID_COLS; ++i)
+        for (int j = 0; j < FRAME_GRID_ROWS; ++j) {
+            cell_start[i * FRAME_GRID_ROWS + j] = k;
+            for (size_t v : F.mGrid[i][j]) indices[k++] = (int)v;
+        }
+    cell_start[FRAME_GRID_COLS * FRAME_GRID_ROWS] = k;
+    return k;
+}
+
+int reff_frame_features_in_area(void *h, float x, float y, float r, int min_level, int max_level, int cap, int *out)
+{
+    Frame &F = *static_cast<Frame *>(h);
+    const vector<size_t> v = F.GetFeaturesInArea(x, y, r, min_level, max_level);
+    for (size_t i = 0; i < v.size() && (int)i < cap; ++i) out[i] = (int)v[i];
+    return (int)v.size();
+}
+
+// the MapPoint fields of oracle/orb_oracle.h:orc_map_point
+struct reff_map_point { float proj_x, proj_y, proj_xr, view_cos; int32_t level, flags; };
+
+// ORBmatcher::SearchByProjection(F, vpMapPoints, th) (ORBmatcher.cc:68-155).  slot_of_feature[idx] = index of the map
+// point F.mvpMapPoints[idx] holds afterwards, -2 for a pre-existing association (occupied), -1 for none.
+int reff_search_by_projection(void *h, const reff_map_point *mps, const uint8_t *mp_desc, int n_mp,
+                              const uint8_t *occupied, float th, float nn_ratio, int *slot_of_feature)
+{
+    Frame &F = *static_cast<Frame *>(h);
+    vector<MapPoint> store((size_t)n_mp);
+    vector<MapPoint *> v((size_t)n_mp);
+    map<MapPoint *, int> index;
+    for (int i = 0; i < n_mp; ++i) {
+        MapPoint &p = store[(size_t)i];
+        p.mTrackProjX = mps[i].proj_x; p.mTrackProjY = mps[i].proj_y; p.mTrackProjXR = mps[i].proj_xr;
+        p.mTrackViewCos = mps[i].view_cos; p.mnTrackScaleLevel = mps[i].level;
+        p.mbTrackInView = (mps[i].flags & 1) != 0; p.bad_ = false; p.nobs_ = (mps[i].flags & 2) ? 1 : 0;
+        p.desc_ = desc_mat(mp_desc + (size_t)i * 32, 1);
+        v[(size_t)i] = &p; index[&p] = i;
+    }
+    MapPoint held; held.nobs_ = 1;
+    for (int i = 0; i < F.N; ++i) F.mvpMapPoints[(size_t)i] = occupied && occupied[i] ? &held : nullptr;
+    ORBmatcher m(nn_ratio, true);
+    const int n = m.SearchByProjection(F, v, th);
+    for (int i = 0; i < F.N; ++i) {
+        MapPoint *p = F.mvpMapPoints[(size_t)i];
+        slot_of_feature[i] = !p ? -1 : p == &held ? -2 : index[p];
+        F.mvpMapPoints[(size_t)i] = nullptr;
+    }
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1613-1756) with identity rotations:
+// CurrentFrame.mTcw = I, LastFrame.mTcw = [I | (0, 0, last_tz)], so x3Dc == x3Dw exactly and tlc.z == last_tz.
+int reff_search_by_projection_last(void *h, const void *last_keys_un, int n_last, const float *world_xyz,
+                                   const uint8_t *last_desc, const uint8_t *last_flags /* bit0 has point, bit1 outlier, bit2 obs>0 */,
+                                   float last_tz, float fx, float fy, float cx, float cy, float mbf, float mb,
+                                   const uint8_t *occupied, float th, int mono, int check_orientation, int *slot_of_feature)
+{
+    Frame &C = *static_cast<Frame *>(h);
+    Frame L;
+    Frame::fx = fx; Frame::fy = fy; Frame::cx = cx; Frame::cy = cy;
+    C.mbf = mbf; C.mb = mb;
+    C.mTcw = cv::Mat::eye(4, 4, CV_32F);
+    L.mTcw = cv::Mat::eye(4, 4, CV_32F); L.mTcw.at<float>(2, 3) = last_tz;
+    set_keys(L.mvKeysUn, last_keys_un, n_last); L.mvKeys = L.mvKeysUn; L.N = n_last;
+    vector<MapPoint> store((size_t)n_last);
+    map<MapPoint *, int> index;
+    L.mvpMapPoints.assign((size_t)n_last, nullptr); L.mvbOutlier.assign((size_t)n_last, false);
+    for (int i = 0; i < n_last; ++i) {
+        MapPoint &p = store[(size_t)i];
+        p.pos_ = cv::Mat(3, 1, CV_32F);
+        for (int k = 0; k < 3; ++k) p.pos_.at<float>(k) = world_xyz[3 * i + k];
+        p.desc_ = desc_mat(last_desc + (size_t)i * 32, 1);
+        p.nobs_ = (last_flags[i] & 4) ? 1 : 0;
+        index[&p] = i;
+        if (last_flags[i] & 1) L.mvpMapPoints[(size_t)i] = &p;
+        L.mvbOutlier[(size_t)i] = (last_flags[i] & 2) != 0;
+    }
+    MapPoint held; held.nobs_ = 1;
+    for (int i = 0; i < C.N; ++i) C.mvpMapPoints[(size_t)i] = occupied && occupied[i] ? &held : nullptr;
+    ORBmatcher m(0.9f, check_orientation != 0);
+    const int n = m.SearchByProjection(C, L, th, mono != 0);
+    for (int i = 0; i < C.N; ++i) {
+        MapPoint *p = C.mvpMapPoints[(size_t)i];
+        slot_of_feature[i] = !p ? -1 : p == &held ? -2 : index[p];
+        C.mvpMapPoints[(size_t)i] = nullptr;
+    }
+    return n;
+}
+
+} // extern "C"

@@ -1,12 +1,15 @@
-// ref_glue.cc — C entry points around the REFERENCE's ORB_SLAM2::ORBextractor and the callback plumbing that serves
-// its OpenCV primitive calls from cv2.  Test infrastructure only; built ONLY by the opt-in recipe `make -C oracle ref`
-// (see oracle/ref_compat/README.md: compiling and running the third-party source needs a maintainer's go-ahead and
-// has NOT been done in round 1).
+// ref_glue.cc — C entry points around the REFERENCE's ORB_SLAM2::ORBextractor and the plumbing that serves its five
+// OpenCV primitive calls.  Two servers: (1) C callbacks into the real OpenCV 4.13 inside cv2 (oracle/ref_path.py) — the
+// parity pin, OpenCV itself in the loop; (2) when no callbacks are installed, the C oracle's restatements of the same
+// primitives (oracle/orb_oracle.c, each pinned bit for bit against cv2 in tests/test_oracle_cv2.py) — native speed, used
+// for the multi-threaded CPU baseline timing and for large parity sweeps.  Test infrastructure only; built by
+// `make -C oracle ref` into oracle/_ref/ (oracle/ref_compat/README.md).
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 
 #include "ORBextractor.h" // the reference's own header (-I <reference>/include)
+#include "../orb_oracle.h"
 
 extern "C" {
 typedef void (*ref_resize_cb)(const uchar *src, int sw, int sh, size_t sstep, uchar *dst, int dw, int dh, size_t dstep, int interp);
@@ -28,18 +31,58 @@ namespace cv {
 void resize(const Mat &src, Mat &dst, Size dsize, double, double, int interpolation)
 {
     dst.create(dsize.height, dsize.width, CV_8UC1); // keeps the caller's view when the size already matches
+    if (!g_resize) {
+        if (interpolation != INTER_LINEAR) std::abort();
+        orc_resize_linear_u8(src.data, src.cols, src.rows, (ptrdiff_t)src.step, dst.data, dst.cols, dst.rows, (ptrdiff_t)dst.step);
+        return;
+    }
     g_resize(src.data, src.cols, src.rows, src.step, dst.data, dst.cols, dst.rows, dst.step, interpolation);
 }
 
 void copyMakeBorder(const Mat &src, Mat &dst, int top, int bottom, int left, int right, int borderType)
 {
     dst.create(src.rows + top + bottom, src.cols + left + right, CV_8UC1);
+    if (!g_border) { // plain data movement: BORDER_REFLECT_101 frame around the source, in place when src views dst
+        if ((borderType & ~BORDER_ISOLATED) != BORDER_REFLECT_101) std::abort();
+        const int w = src.cols, h = src.rows;
+        for (int y = 0; y < h; ++y) {
+            uchar *d = dst.data + (size_t)(y + top) * dst.step + left;
+            if (d != src.data + (size_t)y * src.step) std::memmove(d, src.data + (size_t)y * src.step, (size_t)w);
+            for (int x = 1; x <= left; ++x) d[-x] = d[x < w ? x : w - 1];
+            for (int x = 0; x < right; ++x) d[w + x] = d[w - 2 - x >= 0 ? w - 2 - x : 0];
+        }
+        const size_t rowb = (size_t)(w + left + right);
+        for (int y = 1; y <= top; ++y)
+            std::memcpy(dst.data + (size_t)(top - y) * dst.step, dst.data + (size_t)(top + (y < h ? y : h - 1)) * dst.step, rowb);
+        for (int y = 0; y < bottom; ++y)
+            std::memcpy(dst.data + (size_t)(top + h + y) * dst.step, dst.data + (size_t)(top + (h - 2 - y >= 0 ? h - 2 - y : 0)) * dst.step, rowb);
+        return;
+    }
     g_border(src.data, src.cols, src.rows, src.step, dst.data, dst.step, top, bottom, left, right, borderType);
 }
 
 void FAST(const Mat &image, std::vector<KeyPoint> &keypoints, int threshold, bool nonmaxSuppression)
 {
     keypoints.clear();
+    if (!g_fast) {
+        if (!nonmaxSuppression) std::abort();
+        int cap = 1024;
+        std::vector<int> x, y, r;
+        for (;;) {
+            x.resize(cap); y.resize(cap); r.resize(cap);
+            const int n = orc_fast9_16(image.data, image.cols, image.rows, (ptrdiff_t)image.step, threshold, cap, x.data(), y.data(), r.data());
+            if (n <= cap) {
+                keypoints.resize(n);
+                for (int i = 0; i < n; ++i) {
+                    KeyPoint &k = keypoints[i];
+                    k.pt.x = (float)x[i]; k.pt.y = (float)y[i]; k.size = 7.f; k.angle = -1.f; k.response = (float)r[i];
+                    k.octave = 0; k.class_id = -1;
+                }
+                return;
+            }
+            cap = n;
+        }
+    }
     int cap = 4096;
     std::vector<float> buf;
     for (;;) {
@@ -61,10 +104,16 @@ void FAST(const Mat &image, std::vector<KeyPoint> &keypoints, int threshold, boo
 void GaussianBlur(const Mat &src, Mat &dst, Size ksize, double sigmaX, double sigmaY, int borderType)
 {
     if (dst.data != src.data) dst = src.clone();
+    if (!g_blur) {
+        if (ksize.width != 7 || ksize.height != 7 || sigmaX != 2 || sigmaY != 2 || borderType != BORDER_REFLECT_101) std::abort();
+        Mat tmp = dst.clone();
+        orc_gaussian7x7_s2(tmp.data, tmp.cols, tmp.rows, (ptrdiff_t)tmp.step, dst.data, (ptrdiff_t)dst.step);
+        return;
+    }
     g_blur(dst.data, dst.cols, dst.rows, dst.step, ksize.width, ksize.height, sigmaX, sigmaY, borderType);
 }
 
-float fastAtan2(float y, float x) { return g_atan2(y, x); }
+float fastAtan2(float y, float x) { return g_atan2 ? g_atan2(y, x) : orc_fast_atan2(y, x); }
 
 void KeyPointsFilter::retainBest(std::vector<KeyPoint> &keypoints, int npoints)
 {

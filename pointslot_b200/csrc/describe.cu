@@ -15,8 +15,8 @@
 // BORDER_REFLECT_101 is applied at the true image edge while staging.  No blurred level is ever written
 // to or read from global memory.
 //
-// Float islands follow DESIGN.md parity rule 3: single-rounded __f*_rn ops (no FMA), cos/sin in
-// double then rounded to float, cvRound = round-half-even.
+// Float islands follow DESIGN.md parity rule 3: single-rounded __f*_rn ops (no FMA), cosf/sinf by glibc's own
+// algorithm (glibc_sincosf below), cvRound = round-half-even.
 //
 // Bound: shared memory / integer ALU; algorithmic global bytes per keypoint = 1849 (patch) + 4 (lkp)
 // + 28 + 32 (outputs).
@@ -90,15 +90,46 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
-// a = (float)cos(angle*factorPI), b = (float)sin(...) with the trigonometry in double (parity rule 3)
+// a = cosf(angle*factorPI), b = sinf(...) exactly as the reference binary gets them (parity rule 3): `(float)cos(float)`
+// at ORBextractor.cc:112-113 is glibc's cosf, whose algorithm (glibc >= 2.28, sysdeps/ieee754/flt-32/s_sincosf.h: reduction
+// by pi/2 with a 2^24-prescaled multiply, even / odd polynomial in double, one rounding to float) is restated here with
+// explicit IEEE double operations.  The CPU checker carries the same restatement (orc_glibc_cosf), verified
+// against libm on every float in [0, 2 pi] (profiles/r02_sincosf_sweep.txt); tools/steer_sweep.py checks this device
+// version against it on every float angle in [0, 360].
+__device__ __forceinline__ float glibc_sincos_poly(double x, double x2, bool negcos, int n)
+{
+    if ((n & 1) == 0) {
+        const double x3 = __dmul_rn(x, x2), s1 = __fma_rn(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
+        const double x7 = __dmul_rn(x3, x2), s = __fma_rn(x3, -0x1.555545995a603p-3, x);
+        return __double2float_rn(__fma_rn(x7, s1, s));
+    }
+    const double g = negcos ? -1.0 : 1.0;
+    const double x4 = __dmul_rn(x2, x2);
+    const double c2 = __fma_rn(x2, g * 0x1.99343027bf8c3p-16, g * -0x1.6c087e89a359dp-10);
+    const double c1 = __fma_rn(x2, g * -0x1.ffffffd0c621cp-2, g);
+    const double x6 = __dmul_rn(x4, x2), c = __fma_rn(x4, g * 0x1.55553e1068f19p-5, c1);
+    return __double2float_rn(__fma_rn(x6, c2, c));
+}
+__device__ __forceinline__ float glibc_sincosf(float y, bool cosine)
+{
+    const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ffu;
+    double x = (double)y;
+    if (top < 0x3f4u) {                      // |y| < pi/4: abstop12(0x1.921FB6p-1f)
+        if (top < 0x398u) return cosine ? 1.0f : y; // |y| < 2^-12
+        return glibc_sincos_poly(x, __dmul_rn(x, x), false, cosine ? 1 : 0);
+    }
+    const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+    const int n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = __fma_rn(-(double)n, 0x1.921FB54442D18p0, x);
+    const double sgn = ((n + 1) & 2) ? -1.0 : 1.0; // sign[n & 3] = {1, -1, -1, 1}
+    return glibc_sincos_poly(__dmul_rn(x, sgn), __dmul_rn(x, x), (n & 2) != 0, cosine ? n ^ 1 : n);
+}
 __device__ __forceinline__ void steer_coeffs(float angle_deg, float &a, float &b)
 {
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
     const float ang = __fmul_rn(angle_deg, factorPI);
-    double sd, cd;
-    sincos((double)ang, &sd, &cd);
-    a = (float)cd;
-    b = (float)sd;
+    a = glibc_sincosf(ang, true);
+    b = glibc_sincosf(ang, false);
 }
 
 __global__ void k_debug_steer(const float *__restrict__ angle_deg, int n, float *__restrict__ a, float *__restrict__ b)

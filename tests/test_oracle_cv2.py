@@ -89,3 +89,18 @@ def test_cvt_gray_exhaustive(oracle_mod):
     img4 = np.concatenate([img[:512], np.full((512, 4096, 1), 200, np.uint8)], axis=2)
     assert np.array_equal(oracle_mod.cvt_gray(img4, True), cv2.cvtColor(img4, cv2.COLOR_RGBA2GRAY))
     assert np.array_equal(oracle_mod.cvt_gray(img4, False), cv2.cvtColor(img4, cv2.COLOR_BGRA2GRAY))
+
+
+def test_glibc_sincosf_restatement_equals_libm(oracle_mod):
+    """orc_glibc_cosf / orc_glibc_sinf (the steering trigonometry, ORBextractor.cc:112-113 -> std::cos(float) = glibc cosf)
+    against this host's libm.  The exhaustive sweep over every float in [0, 2 pi] is profiles/r02_sincosf_sweep.txt."""
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(0, 2 * np.pi, 60000), np.deg2rad(np.arange(0, 360, 0.25)),
+                        [0.0, 1e-5, 2.4e-4, 0.7853981, 0.7853982, 0.78539824, 1.5707963, 3.1415927, 4.712389, 6.2831855]]).astype(np.float32)
+    c, s = oracle_mod.glibc_sincosf(x)
+    lc, ls = oracle_mod.libm_sincosf(x)
+    assert c.tobytes() == lc.tobytes() and s.tobytes() == ls.tobytes()
+    # and the angles the path really feeds it: fastAtan2 output (degrees) times the float pi/180
+    ang = rng.uniform(0, 360, 20000).astype(np.float32) * np.float32(np.pi / 180.0)
+    c, s = oracle_mod.glibc_sincosf(ang); lc, ls = oracle_mod.libm_sincosf(ang)
+    assert c.tobytes() == lc.tobytes() and s.tobytes() == ls.tobytes()
