@@ -247,6 +247,11 @@ int pslot_batch_stage_times(pslot_batch *b, float *ms);
  * stats[0] FAST candidates over all images, [1] keypoints over all images, [2] left keypoints that
  * reached the SAD refinement (best Hamming < 75), [3] stereo matches that survived the median test. */
 int pslot_batch_stats(pslot_batch *b, int64_t stats[4]);
+/* Stereo search counters accumulated by the submits made while profiling was enabled, then reset:
+ * out[0] = row-band candidates scanned, i.e. the sum over left keypoints of |vRowIndices[row]| (Frame.cc:2188),
+ * out[1] = descriptor pairs compared (Frame.cc:2217).  With pslot_batch_stats they give the measured c_row and
+ * c-bar of SURVEY.md §8d. */
+int pslot_batch_stereo_counters(pslot_batch *b, int64_t out[2]);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage accessors for the parity tests (not needed by a drop-in caller).

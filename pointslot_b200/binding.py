@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "pslot_orb_extract", "pslot_orb_extract_color", "pslot_orb_level", "pslot_stereo_match", "pslot_hamming256",
     "pslot_batch_create", "pslot_batch_destroy", "pslot_batch_set_copy_stream", "pslot_batch_max_keypoints", "pslot_batch_stream",
     "pslot_batch_submit", "pslot_batch_submit_color", "pslot_batch_wait", "pslot_batch_kernel_launches", "pslot_batch_device_out",
-    "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats",
+    "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats", "pslot_batch_stereo_counters",
     "pslot_assign_grid", "pslot_features_in_area", "pslot_batch_assign_grid",
     "pslot_search_by_projection", "pslot_search_by_projection_last", "pslot_debug_projection_sweeps",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
@@ -117,6 +117,7 @@ def lib():
     L.pslot_batch_set_profiling.argtypes = [vp, C.c_int]
     L.pslot_batch_stage_times.argtypes = [vp, vp]
     L.pslot_batch_stats.argtypes = [vp, vp]
+    L.pslot_batch_stereo_counters.argtypes = [vp, vp]
     L.pslot_orb_debug_candidates.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, ip]
     L.pslot_orb_debug_level_keypoints.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, ip]
     L.pslot_stereo_debug.argtypes = [vp, C.c_int, vp, vp, vp]
@@ -398,6 +399,12 @@ class StereoBatch:
         st = np.zeros(4, np.int64)
         _check(lib().pslot_batch_stats(self._h, _p(st)))
         return dict(zip(("candidates", "keypoints", "sad_evals", "matches"), (int(v) for v in st)))
+
+    def stereo_counters(self) -> dict:
+        """Row-band candidates scanned / descriptors compared by the profiled submits since the last call."""
+        c = np.zeros(2, np.int64)
+        _check(lib().pslot_batch_stereo_counters(self._h, _p(c)))
+        return {"row_candidates": int(c[0]), "hamming_evals": int(c[1])}
 
     def stage_times_ms(self) -> np.ndarray:
         ms = np.zeros(len(self.STAGES), np.float32)

@@ -225,6 +225,10 @@ struct Engine {
                 L.tab_y = (int)taps.size();
                 taps.resize(taps.size() + py);
                 resize_taps(L.h, P.h, taps.data() + L.tab_y, py);
+                // per-level ratios after cvRound can exceed the nominal scale factor (48/33 = 1.4545): check the real taps
+                if (!pyramid_tiles_fit(taps.data() + L.tab_x, L.w, taps.data() + L.tab_y, L.h))
+                    return fail(PSLOT_ERR_SHAPE, "level %d (%dx%d from %dx%d): resize ratio exceeds the pyramid kernel's staging tile", l,
+                                L.w, L.h, P.w, P.h);
             }
         }
         G.cells_per_slot = cells; G.cand_per_slot = cand; G.lkp_per_slot = lkp; G.kp_cap_total = lkp;
@@ -309,7 +313,6 @@ struct Engine {
         out_bytes = off_desc + align_up(32 * ns * K, 256);
         CU(cudaMalloc(&d_out, out_bytes));
         CU(cudaMemset(d_out, 0, out_bytes)); // result rows are copied out at full capacity; the unused tail reads as zeros
-        CU(cudaMemset(d_out, 0, out_bytes));
         d_out_count = (int *)d_out;
         d_out_kps = (pslot_keypoint *)(d_out + off_kps);
         d_out_desc = (uint8_t *)(d_out + off_desc);
@@ -326,7 +329,7 @@ struct Engine {
     {
         int n = 0;
         if (ev) cudaEventRecord(ev[1], st);
-        n += launch_pyramid(g, pyr, d_taps, nslots, st);
+        n += launch_pyramid(g, pyr, d_taps, nslots, d_err, st);
         if (ev) cudaEventRecord(ev[2], st);
         n += launch_fast(g, maps, d_cell_count, d_cell_cand, nslots, st);
         if (ev) cudaEventRecord(ev[3], st);
@@ -345,9 +348,14 @@ struct Engine {
 int check_err_flag(Engine &E)
 {
     CU(cudaStreamSynchronize(E.st));
-    if (*(volatile int *)E.h_err) {
+    const int f = *(volatile int *)E.h_err;
+    if (f) {
         *E.h_err = 0;
-        return fail(PSLOT_ERR_CUDA, "quadtree node table overflow (internal capacity bound violated)");
+        if (f & PSLOT_FLAG_QT_OVERFLOW) return fail(PSLOT_ERR_CUDA, "quadtree node table overflow (internal capacity bound violated)");
+        if (f & PSLOT_FLAG_PYR_TILE) return fail(PSLOT_ERR_SHAPE, "a pyramid resize tile exceeded the staging buffer (level not written)");
+        if (f & PSLOT_FLAG_STEREO_NR) return fail(PSLOT_ERR_CAPACITY, "stereo matcher: more right keypoints than it can stage (results would be truncated)");
+        if (f & PSLOT_FLAG_STEREO_OCTAVE) return fail(PSLOT_ERR_ARG, "stereo matcher: a right keypoint's octave is out of range");
+        return fail(PSLOT_ERR_CUDA, "device error flag 0x%x", f);
     }
     return PSLOT_OK;
 }
@@ -409,6 +417,7 @@ struct pslot_batch {
     cudaEvent_t ev[PSLOT_NUM_STAGES + 1] = {};
     int *d_gcs = nullptr, *d_gidx = nullptr; // feature grids of the last submit (pslot_batch_assign_grid)
     int gcs_cells = 0;
+    unsigned long long *d_counters = nullptr; // stereo work counters, accumulated by profiled submits (pslot_batch_stereo_counters)
     uint8_t *d_stage = nullptr; // tightly packed landing zone for host images (one linear H2D per view)
     uint8_t *d_cstage = nullptr; // same for colour frames
     size_t cstage_bytes = 0;
@@ -426,6 +435,7 @@ struct pslot_batch {
             if (e) cudaEventDestroy(e);
         cudaFree(d_stage);
         cudaFree(d_cstage);
+        cudaFree(d_counters);
         cudaFree(d_gcs);
         cudaFree(d_gidx);
     }
@@ -595,8 +605,15 @@ int pslot_stereo_match(pslot_orb *cl, pslot_orb *cr, const pslot_keypoint *kps_l
     if (L.W != R.W || L.H != R.H || L.p.nlevels != R.p.nlevels || L.device != R.device)
         return fail(PSLOT_ERR_STATE, "left / right extractors differ in geometry or device");
     if (n_r > 16000 || n_l > (1 << 24)) return fail(PSLOT_ERR_ARG, "too many keypoints");
-    for (int i = 0; i < n_l; ++i)
+    for (int i = 0; i < n_l; ++i) {
         if (kps_l[i].octave < 0 || kps_l[i].octave >= L.p.nlevels) return fail(PSLOT_ERR_ARG, "left keypoint %d: octave out of range", i);
+        if (!(fabsf(kps_l[i].x) < 1e6f) || !(fabsf(kps_l[i].y) < 1e6f)) return fail(PSLOT_ERR_ARG, "left keypoint %d: coordinate is not finite", i);
+    }
+    for (int i = 0; i < n_r; ++i) {
+        if (kps_r[i].octave < 0 || kps_r[i].octave >= L.p.nlevels) return fail(PSLOT_ERR_ARG, "right keypoint %d: octave out of range", i);
+        if (!(fabsf(kps_r[i].x) < 1e6f) || !(kps_r[i].y > -30000.f && kps_r[i].y < 30000.f))
+            return fail(PSLOT_ERR_ARG, "right keypoint %d: coordinate is not finite / out of range", i);
+    }
     CU(cudaSetDevice(L.device));
     const int need = std::max(std::max(n_l, n_r), 1);
     if (need > cl->st_cap) {
@@ -626,12 +643,13 @@ int pslot_stereo_match(pslot_orb *cl, pslot_orb *cr, const pslot_keypoint *kps_l
     a.pyr_l = L.pyr; a.pyr_r = R.pyr;
     a.bf = bf; a.max_d = max_d;
     a.u_right = cl->d_ur; a.depth = cl->d_dp; a.best_dist = cl->d_bd; a.best_idx = cl->d_bi; a.sad = cl->d_sd;
+    a.err_flag = L.d_err;
     launch_stereo(L.g, a, 1, std::max(n_r, 1), st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "stereo launch failed: %s", cudaGetErrorString(e));
     CU(cudaMemcpyAsync(u_right, cl->d_ur, 4 * (size_t)n_l, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(depth, cl->d_dp, 4 * (size_t)n_l, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    if (int rc = check_err_flag(L)) return rc; // synchronises the stream
     cl->last_nl = n_l;
     return PSLOT_OK;
 }
@@ -639,6 +657,7 @@ int pslot_stereo_match(pslot_orb *cl, pslot_orb *cr, const pslot_keypoint *kps_l
 int pslot_stereo_debug(pslot_orb *cl, int n_l, int32_t *best_dist, int32_t *best_idx, int32_t *best_sad)
 {
     if (!cl) return fail(PSLOT_ERR_ARG, "ctx is null");
+    if (n_l < 0) return fail(PSLOT_ERR_ARG, "negative count");
     if (n_l > cl->last_nl) return fail(PSLOT_ERR_STATE, "no stereo result of that size");
     CU(cudaSetDevice(cl->E.device));
     if (best_dist) CU(cudaMemcpy(best_dist, cl->d_bd, 4 * (size_t)n_l, cudaMemcpyDeviceToHost));
@@ -852,6 +871,8 @@ static int batch_submit_impl(pslot_batch *b, const uint8_t *left, const uint8_t 
     for (int l = 0; l < E.g.nlevels; ++l) a.pyr_r.lv[l] = E.pyr.lv[l] + (size_t)npairs * E.pyr.slot_stride[l];
     a.bf = bf; a.max_d = max_d;
     a.u_right = E.d_uright; a.depth = E.d_depth; a.best_dist = E.d_best_dist; a.best_idx = E.d_best_idx; a.sad = E.d_sad;
+    a.err_flag = E.d_err;
+    a.counters = b->profiling ? b->d_counters : nullptr;
     rc += launch_stereo(E.g, a, npairs, K, E.st, ev ? ev[6] : nullptr);
     if (ev) cudaEventRecord(ev[7], E.st);
     cudaError_t e = cudaGetLastError();
@@ -909,9 +930,14 @@ int pslot_batch_set_profiling(pslot_batch *b, int enable)
 {
     if (!b) return fail(PSLOT_ERR_ARG, "b is null");
     CU(cudaSetDevice(b->E.device));
-    if (enable)
+    if (enable) {
         for (auto &e : b->ev)
             if (!e) CU(cudaEventCreate(&e));
+        if (!b->d_counters) {
+            CU(cudaMalloc(&b->d_counters, 16));
+            CU(cudaMemset(b->d_counters, 0, 16));
+        }
+    }
     b->profiling = enable != 0;
     b->profiled = false;
     return PSLOT_OK;
@@ -950,6 +976,19 @@ int pslot_batch_stats(pslot_batch *b, int64_t stats[4])
             stats[2] += bd[p * K + i] < 75;
             stats[3] += ur[p * K + i] >= 0.f;
         }
+    return PSLOT_OK;
+}
+
+int pslot_batch_stereo_counters(pslot_batch *b, int64_t out[2])
+{
+    if (!b || !out) return fail(PSLOT_ERR_ARG, "null argument");
+    if (!b->d_counters) return fail(PSLOT_ERR_STATE, "profiling has not been enabled on this context");
+    CU(cudaSetDevice(b->E.device));
+    CU(cudaStreamSynchronize(b->E.st));
+    unsigned long long h[2];
+    CU(cudaMemcpy(h, b->d_counters, 16, cudaMemcpyDeviceToHost));
+    CU(cudaMemset(b->d_counters, 0, 16));
+    out[0] = (int64_t)h[0]; out[1] = (int64_t)h[1];
     return PSLOT_OK;
 }
 

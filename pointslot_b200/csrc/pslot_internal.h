@@ -67,6 +67,14 @@ __host__ __device__ inline int pslot_px(uint32_t p) { return (int)((p >> 8) & 0x
 __host__ __device__ inline int pslot_py(uint32_t p) { return (int)(p >> 20); }
 __host__ __device__ inline int pslot_pr(uint32_t p) { return (int)(p & 0xFFu); }
 
+// bits of the host-mapped error word a kernel can raise (Engine::h_err); decoded by check_err_flag in engine.cu
+enum : int {
+    PSLOT_FLAG_QT_OVERFLOW = 1,   // quadtree node table overflow (internal capacity bound violated)
+    PSLOT_FLAG_STEREO_NR = 2,     // more right keypoints than the stereo kernel staged (would have been truncated)
+    PSLOT_FLAG_STEREO_OCTAVE = 4, // a right keypoint's octave lies outside [0, nlevels)
+    PSLOT_FLAG_PYR_TILE = 8,      // a resize tile's source rectangle exceeds the staging buffer (level left unwritten)
+};
+
 struct StereoArgs {
     // left / right feature sets: per pair p, keypoints at kps + slot*K
     const pslot_keypoint *kps_l, *kps_r;
@@ -77,10 +85,16 @@ struct StereoArgs {
     float bf, max_d;
     float *u_right, *depth;          // [pairs][K]
     int *best_dist, *best_idx, *sad; // [pairs][K]
+    int *err_flag;                   // host-mapped error word (PSLOT_FLAG_*), may be null
+    unsigned long long *counters;    // optional work counters: [0] row-band candidates scanned (sum over left keypoints of
+                                     // |vRowIndices[row]|), [1] descriptors compared; null = not counted
 };
 
 // ---- launchers (each enqueues on `st`; returns the number of kernels launched) -----------------
-int launch_pyramid(const Geom &g, const PyrPtrs &pyr, const ResizeTap *taps, int nslots, cudaStream_t st);
+int launch_pyramid(const Geom &g, const PyrPtrs &pyr, const ResizeTap *taps, int nslots, int *err_flag, cudaStream_t st);
+// true when every 128 x 32 output tile of the level's resize fits the kernel's staging buffer (checked on the host so
+// that the device-side guard can never fire silently)
+bool pyramid_tiles_fit(const ResizeTap *xt, int dw, const ResizeTap *yt, int dh);
 struct TmapSet;
 int launch_fast(const Geom &g, const TmapSet &maps, int *cell_count, uint32_t *cell_cand, int nslots, cudaStream_t st);
 int launch_quadtree(const Geom &g, const int *cell_count, const uint32_t *cell_cand, int *cell_prefix,

@@ -30,7 +30,7 @@ constexpr int OUT_S = TW;   // output staging row stride
 __global__ void __launch_bounds__(TW *TY, 8)
 k_resize_level(const uint8_t *__restrict__ src, int spitch, unsigned long long sstride,
                uint8_t *__restrict__ dst, int dw, int dh, int dpitch, unsigned long long dstride,
-               const ResizeTap *__restrict__ xt, const ResizeTap *__restrict__ yt)
+               const ResizeTap *__restrict__ xt, const ResizeTap *__restrict__ yt, int *__restrict__ err_flag)
 {
     __shared__ __align__(16) uint8_t s_src[SRC_H * SRC_W];
     __shared__ __align__(16) uint8_t s_out[TH * OUT_S];
@@ -45,7 +45,10 @@ k_resize_level(const uint8_t *__restrict__ src, int spitch, unsigned long long s
     const int xa = (int)xt[dx0].s0 & ~15, xb = (int)xt[dx1].s1;
     const int ya = (int)yt[dy0].s0, yb = (int)yt[dy1].s1;
     const int nvec = (xb - xa) / 16 + 1, nrow = yb - ya + 1;
-    if (nvec * 16 > SRC_W || nrow > SRC_H) return; // unsupported ratio (scaleFactor is capped on the host)
+    if (nvec * 16 > SRC_W || nrow > SRC_H) { // cannot happen: make_geom rejects such ratios (pyramid_tiles_fit)
+        if (tid == 0 && err_flag) atomicOr(err_flag, PSLOT_FLAG_PYR_TILE);
+        return;
+    }
     {
         // 16 threads per staged row (nvec <= 13); rows are padded to a multiple of 128 bytes, so a 16-byte read
         // never leaves the row
@@ -108,7 +111,21 @@ k_resize_level(const uint8_t *__restrict__ src, int spitch, unsigned long long s
 
 } // namespace
 
-int launch_pyramid(const Geom &g, const PyrPtrs &pyr, const ResizeTap *taps, int nslots, cudaStream_t st)
+bool pyramid_tiles_fit(const ResizeTap *xt, int dw, const ResizeTap *yt, int dh)
+{
+    for (int dx0 = 0; dx0 < dw; dx0 += TW) {
+        const int dx1 = (dx0 + TW < dw ? dx0 + TW : dw) - 1;
+        const int xa = (int)xt[dx0].s0 & ~15, xb = (int)xt[dx1].s1;
+        if (((xb - xa) / 16 + 1) * 16 > SRC_W) return false;
+    }
+    for (int dy0 = 0; dy0 < dh; dy0 += TH) {
+        const int dy1 = (dy0 + TH < dh ? dy0 + TH : dh) - 1;
+        if ((int)yt[dy1].s1 - (int)yt[dy0].s0 + 1 > SRC_H) return false;
+    }
+    return true;
+}
+
+int launch_pyramid(const Geom &g, const PyrPtrs &pyr, const ResizeTap *taps, int nslots, int *err_flag, cudaStream_t st)
 {
     int launches = 0;
     for (int l = 1; l < g.nlevels; ++l) {
@@ -116,7 +133,7 @@ int launch_pyramid(const Geom &g, const PyrPtrs &pyr, const ResizeTap *taps, int
         dim3 block(TW, TY);
         dim3 grid((D.w + TW - 1) / TW, (D.h + TH - 1) / TH, nslots);
         k_resize_level<<<grid, block, 0, st>>>(pyr.lv[l - 1], S.pitch, pyr.slot_stride[l - 1], pyr.lv[l], D.w, D.h,
-                                               D.pitch, pyr.slot_stride[l], taps + D.tab_x, taps + D.tab_y);
+                                               D.pitch, pyr.slot_stride[l], taps + D.tab_x, taps + D.tab_y, err_flag);
         ++launches;
     }
     return launches;

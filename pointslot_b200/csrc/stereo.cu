@@ -57,6 +57,9 @@ k_stereo_match(const __grid_constant__ Geom g, const __grid_constant__ StereoArg
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pair = blockIdx.y;
     const int nL = a.n_l[pair], nR = min(a.n_r[pair], right_cap);
+    // more right keypoints than were staged, or than the 16-bit iR of the packed argmin can name: an error the host
+    // reports (PSLOT_ERR_CAPACITY), never a silent truncation
+    if ((a.n_r[pair] > right_cap || nR > 0xFFFF) && threadIdx.x == 0 && a.err_flag) atomicOr(a.err_flag, PSLOT_FLAG_STEREO_NR);
     const size_t row0 = (size_t)pair * a.K;
     const pslot_keypoint *kR = a.kps_r + row0;
     const pslot_keypoint *kL = a.kps_l + row0;
@@ -73,6 +76,7 @@ k_stereo_match(const __grid_constant__ Geom g, const __grid_constant__ StereoArg
     for (int i = tid; i < nR; i += SW * 32) {
         const pslot_keypoint k = kR[i];
         const int oct = min(max(k.octave, 0), g.nlevels - 1);
+        if (oct != k.octave && a.err_flag) atomicOr(a.err_flag, PSLOT_FLAG_STEREO_OCTAVE);
         const float r = __fmul_rn(2.0f, g.lv[oct].scale); // (:2162)
         RightKey e;
         e.maxr = (short)(int)ceilf(__fadd_rn(k.y, r));
@@ -113,6 +117,7 @@ k_stereo_match(const __grid_constant__ Geom g, const __grid_constant__ StereoArg
     }
 
     const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+    unsigned n_row = 0, n_cmp = 0; // work counters of this lane (only reported when a.counters is set)
     for (int q = 0; q < LEFT_PER_CTA / SW; ++q) {
         const int iL = iL0 + q * SW + warp;
         if (iL >= nL) continue; // warp-uniform
@@ -136,10 +141,12 @@ k_stereo_match(const __grid_constant__ Geom g, const __grid_constant__ StereoArg
                 const int iR = use_bins ? (int)blist[j] : j;
                 const RightKey e = rk[iR];
                 if (row < e.minr || row > e.maxr) continue;
+                ++n_row;
                 if (e.octave < levelL - 1 || e.octave > levelL + 1) continue;
                 if (!(e.x >= minU && e.x <= maxU)) continue;
                 const uint4 *dr = reinterpret_cast<const uint4 *>(a.desc_r + (row0 + iR) * 32);
                 const uint4 r0 = __ldg(dr), r1 = __ldg(dr + 1);
+                ++n_cmp;
                 const int dist = __popc(l0.x ^ r0.x) + __popc(l0.y ^ r0.y) + __popc(l0.z ^ r0.z) + __popc(l0.w ^ r0.w) +
                                  __popc(l1.x ^ r1.x) + __popc(l1.y ^ r1.y) + __popc(l1.z ^ r1.z) + __popc(l1.w ^ r1.w);
                 // first strict minimum in ascending iR (:2219) == minimum of (dist, iR), whatever the visiting order
@@ -225,6 +232,11 @@ k_stereo_match(const __grid_constant__ Geom g, const __grid_constant__ StereoArg
             a.best_idx[row0 + iL] = bestIdxR;
             a.sad[row0 + iL] = out_sad;
         }
+    }
+    if (a.counters) {
+        n_row = __reduce_add_sync(0xffffffffu, n_row);
+        n_cmp = __reduce_add_sync(0xffffffffu, n_cmp);
+        if (lane == 0) { atomicAdd(a.counters, (unsigned long long)n_row); atomicAdd(a.counters + 1, (unsigned long long)n_cmp); }
     }
 }
 

@@ -236,3 +236,70 @@ def test_object_subset_stereo(B, oracle_mod):
     our, odp = oracle_mod.stereo_match(oL, oR, kL[selL], dL[selL], kR[selR], dR[selR], float(g["bf"]), float(g["maxD"]))
     _assert_stereo(ur, dp, our, odp)
     assert (ur >= 0).sum() > 20
+
+
+def test_stereo_rejects_instead_of_truncating(B, oracle_mod):
+    """Limits of the stereo kernel are errors, never silent clamps: too many right keypoints (the kernel stages them in
+    shared memory and names them with 16 bits), out-of-range octaves on either side, non-finite coordinates."""
+    from pointslot_b200.synth import synth_pair
+    params = (800, 1.2, 8, 20, 7)
+    L, R = synth_pair(640, 360, 9)
+    eL, eR = B.OrbExtractor(*params), B.OrbExtractor(*params)
+    kL, dL = eL.extract(L); kR, dR = eR.extract(R)
+    bf, maxD = 200.0, B.max_disparity(200.0, 500.0)
+    reps = 16001 // len(kR) + 1
+    with pytest.raises(B.PslotError):
+        B.stereo_match(eL, eR, kL, dL, np.tile(kR, reps), np.tile(dR, (reps, 1)), bf, maxD)
+    bad = kR.copy(); bad["octave"][3] = 8
+    with pytest.raises(B.PslotError):
+        B.stereo_match(eL, eR, kL, dL, bad, dR, bf, maxD)
+    bad = kR.copy(); bad["octave"][0] = -1
+    with pytest.raises(B.PslotError):
+        B.stereo_match(eL, eR, kL, dL, bad, dR, bf, maxD)
+    bad = kL.copy(); bad["x"][1] = np.nan
+    with pytest.raises(B.PslotError):
+        B.stereo_match(eL, eR, bad, dL, kR, dR, bf, maxD)
+    bad = kR.copy(); bad["y"][1] = np.inf
+    with pytest.raises(B.PslotError):
+        B.stereo_match(eL, eR, kL, dL, bad, dR, bf, maxD)
+    # the context is still usable afterwards and gives the oracle's answer
+    oL, oR = oracle_mod.OracleExtractor(*params), oracle_mod.OracleExtractor(*params)
+    oL.extract(L); oR.extract(R)
+    ur, dp = B.stereo_match(eL, eR, kL, dL, kR, dR, bf, maxD)
+    our, odp = oracle_mod.stereo_match(oL, oR, kL, dL, kR, dR, bf, maxD)
+    _assert_stereo(ur, dp, our, odp)
+
+
+def test_stereo_work_counters_match_the_row_table(B):
+    """pslot_batch_stereo_counters: c_row = sum of |vRowIndices[row]| over the left keypoints that search, c-bar = the
+    descriptor comparisons (Frame.cc:2188-2217), recomputed here from the returned keypoints."""
+    from pointslot_b200.synth import synth_pair
+    params = (1000, 1.2, 8, 20, 5)
+    W, H, n = 1242, 375, 3
+    Ls, Rs = zip(*[synth_pair(W, H, 40 + i) for i in range(n)])
+    bf, maxD = 384.38148, B.max_disparity(384.38148, 721.5377)
+    sb = B.StereoBatch(params, W, H, n)
+    sb.set_profiling(True)
+    res = sb.run(np.stack(Ls), np.stack(Rs), bf, maxD)
+    got = sb.stereo_counters()
+    sf = np.float32(1.2) ** np.arange(8, dtype=np.float32)
+    sfs = [np.float32(1.0)]
+    for _ in range(7):
+        sfs.append(np.float32(np.float64(sfs[-1]) * np.float64(np.float32(1.2))))
+    sf = np.array(sfs, np.float32)
+    rows = cmps = 0
+    for r in res:
+        kL, kR = r["kL"], r["kR"]
+        rad = np.float32(2.0) * sf[kR["octave"]]
+        maxr = np.ceil(kR["y"] + rad).astype(int); minr = np.floor(kR["y"] - rad).astype(int)
+        for k in kL:
+            row = int(k["y"])
+            band = (minr <= row) & (row <= maxr)
+            if k["x"] < 0:
+                continue
+            rows += int(band.sum())
+            minU = np.float32(k["x"]) - np.float32(maxD)
+            ok = band & (np.abs(kR["octave"] - k["octave"]) <= 1) & (kR["x"] >= minU) & (kR["x"] <= k["x"])
+            cmps += int(ok.sum())
+    assert got["row_candidates"] == rows and got["hamming_evals"] == cmps
+    assert sb.stereo_counters() == {"row_candidates": 0, "hamming_evals": 0}  # reset by the read
