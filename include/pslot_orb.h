@@ -131,6 +131,12 @@ typedef struct pslot_area_query {
  * the keypoints stay on the device for pslot_features_in_area. */
 int pslot_assign_grid(pslot_orb *ctx, const pslot_keypoint *kps_un, int n, const pslot_grid_spec *spec,
                       int32_t *cell_start, int32_t *indices, int *n_in_grid);
+/* Identity of the keypoint set currently gridded on `ctx`: a process-unique non-zero number assigned by every
+ * successful pslot_assign_grid (0 = nothing gridded).  pslot_features_in_area and the projection searches run against
+ * whatever set was gridded LAST on the context; a caller that keeps several frames per extractor (the reference reads
+ * F.mGrid / F.mvKeysUn of the frame it is handed, ORBmatcher.cc:92) stores the token with each frame and re-grids when
+ * it no longer matches - that is what the C++ Frame / ORBmatcher drop-ins do (Frame::EnsureDeviceGrid). */
+uint64_t pslot_grid_token(const pslot_orb *ctx);
 /* nq area queries against the grid of the last pslot_assign_grid on ctx.  counts[q] = number of features found
  * (may exceed cap); indices[q * cap + k], k < min(counts[q], cap), in the reference's visiting order. */
 int pslot_features_in_area(pslot_orb *ctx, const pslot_area_query *queries, int nq, int cap, int32_t *counts,

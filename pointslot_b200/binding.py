@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "pslot_batch_create", "pslot_batch_destroy", "pslot_batch_set_copy_stream", "pslot_batch_max_keypoints", "pslot_batch_stream",
     "pslot_batch_submit", "pslot_batch_submit_color", "pslot_batch_wait", "pslot_batch_kernel_launches", "pslot_batch_device_out",
     "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats", "pslot_batch_stereo_counters",
-    "pslot_assign_grid", "pslot_features_in_area", "pslot_batch_assign_grid",
+    "pslot_assign_grid", "pslot_grid_token", "pslot_features_in_area", "pslot_batch_assign_grid",
     "pslot_search_by_projection", "pslot_search_by_projection_last", "pslot_debug_projection_sweeps",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
 ]
@@ -92,6 +92,8 @@ def lib():
     L.pslot_stereo_match.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_float, C.c_float, vp, vp]
     L.pslot_hamming256.argtypes = [vp, vp]
     L.pslot_assign_grid.argtypes = [vp, vp, C.c_int, C.POINTER(GridSpec), vp, vp, C.POINTER(C.c_int)]
+    L.pslot_grid_token.argtypes = [vp]
+    L.pslot_grid_token.restype = C.c_uint64
     L.pslot_features_in_area.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
     L.pslot_batch_assign_grid.argtypes = [vp, C.POINTER(GridSpec), vp, vp]
     L.pslot_search_by_projection.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, C.c_float,
@@ -241,6 +243,11 @@ def assign_grid(ext: OrbExtractor, kps_un, spec: GridSpec):
     tot = C.c_int(0)
     _check(lib().pslot_assign_grid(ext._h, _p(kps_un), n, C.byref(spec), _p(cs), _p(idx), C.byref(tot)))
     return cs, idx[:tot.value].copy()
+
+
+def grid_token(ext: OrbExtractor) -> int:
+    """Identity of the keypoint set currently gridded on `ext` (0 = none); changes with every assign_grid."""
+    return int(lib().pslot_grid_token(ext._h))
 
 
 def features_in_area(ext: OrbExtractor, queries, cap: int):

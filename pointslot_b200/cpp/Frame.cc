@@ -25,11 +25,10 @@ Frame::Frame()
 {
 }
 
-Frame::Frame(const cv::Mat &imLeft, const cv::Mat &imRight, const double &timeStamp, ORBextractor *extractorLeft,
-             ORBextractor *extractorRight, ORBVocabulary *voc, cv::Mat &K, cv::Mat &distCoef, const float &bf,
-             const float &thDepth)
-    : mpORBvocabulary(voc), mpORBextractorLeft(extractorLeft), mpORBextractorRight(extractorRight),
-      mTimeStamp(timeStamp), mK(K.clone()), mDistCoef(distCoef.clone()), mbf(bf), mb(0), mThDepth(thDepth), N(0)
+Frame::ObjectStageFn Frame::ObjectStageHook = nullptr;
+
+// The path every stereo constructor of the reference runs (:152-199, and the same lines of :203-760).
+void Frame::StereoFrontEnd(const cv::Mat &imLeft, const cv::Mat &imRight, cv::Mat &K, cv::Mat *imColor, int objectMode)
 {
     // Scale Level Info (:152-158)
     mnScaleLevels = mpORBextractorLeft->GetLevels();
@@ -71,10 +70,77 @@ Frame::Frame(const cv::Mat &imLeft, const cv::Mat &imRight, const double &timeSt
 
     ComputeStereoMatches();
 
+    // object modes: detections / masks / AssignFeatures / ExtractObjORB + ComputeObjStereoMatches are PointSLOT's own
+    // code (reference :243-305, 369-404, 469-492, 547-600, 716-740); they run here, where the reference runs them
+    if (objectMode && ObjectStageHook && imColor) {
+        ObjectStageHook(*this, imLeft, imRight, *imColor, objectMode);
+        N = (int)mvKeys.size(); // AssignFeatures may have re-partitioned the keypoints (:308, :407, ...)
+    }
+
     mvpMapPoints = std::vector<MapPoint *>(N, static_cast<MapPoint *>(nullptr)); // (:175)
 
     AssignFeaturesToGrid(); // (:199)
 }
+
+#define PSLOT_FRAME_INIT                                                                                               \
+    mpORBvocabulary(voc), mpORBextractorLeft(extractorLeft), mpORBextractorRight(extractorRight), mTimeStamp(timeStamp), \
+        mK(K.clone()), mDistCoef(distCoef.clone()), mbf(bf), mb(0), mThDepth(thDepth), N(0)
+
+Frame::Frame(const cv::Mat &imLeft, const cv::Mat &imRight, const double &timeStamp, ORBextractor *extractorLeft,
+             ORBextractor *extractorRight, ORBVocabulary *voc, cv::Mat &K, cv::Mat &distCoef, const float &bf,
+             const float &thDepth)
+    : PSLOT_FRAME_INIT
+{
+    StereoFrontEnd(imLeft, imRight, K, nullptr, 0);
+}
+
+// semantic dynamic SLAM (:203)
+Frame::Frame(const cv::Mat &imLeft, const cv::Mat &imRight, cv::Mat &imColor, const double &timeStamp,
+             ORBextractor *extractorLeft, ORBextractor *extractorRight, ORBVocabulary *voc, cv::Mat &K, cv::Mat &distCoef,
+             const float &bf, const float &thDepth, Detector * /*YOLODetector*/)
+    : PSLOT_FRAME_INIT
+{
+    StereoFrontEnd(imLeft, imRight, K, &imColor, 1);
+}
+
+// object tracking + dynamic SLAM (:328)
+Frame::Frame(const cv::Mat &imLeft, const cv::Mat &imRight, cv::Mat &imColor, const double &timeStamp,
+             ORBextractor *extractorLeft, ORBextractor *extractorRight, ORBVocabulary *voc, cv::Mat &K, cv::Mat &distCoef,
+             const float &bf, const float &thDepth, Detector * /*YOLODetector*/, cv::MultiTracker * /*multiTracker*/,
+             std::vector<cv::Ptr<cv::Tracker>> /*vTrackers*/)
+    : PSLOT_FRAME_INIT
+{
+    StereoFrontEnd(imLeft, imRight, K, &imColor, 2);
+}
+
+// object tracking (:428)
+Frame::Frame(const cv::Mat &imLeft, const cv::Mat &imRight, cv::Mat &imColor, const double &timeStamp,
+             ORBextractor *extractorLeft, ORBextractor *extractorRight, ORBVocabulary *voc, cv::Mat &K, cv::Mat &distCoef,
+             const float &bf, const float &thDepth, cv::MultiTracker * /*multiTracker*/,
+             std::vector<cv::Ptr<cv::Tracker>> /*vTrackers*/)
+    : PSLOT_FRAME_INIT
+{
+    StereoFrontEnd(imLeft, imRight, K, &imColor, 2);
+}
+
+// autonomous driving mode: YOLO + DeepSORT, dense object features (:516)
+Frame::Frame(const cv::Mat &imLeft, const cv::Mat &imRight, cv::Mat &imColor, const double &timeStamp,
+             ORBextractor *extractorLeft, ORBextractor *extractorRight, ORBVocabulary *voc, cv::Mat &K, cv::Mat &distCoef,
+             const float &bf, const float &thDepth, Detector * /*YOLODetector*/, DS::DeepSort * /*deepSort*/)
+    : PSLOT_FRAME_INIT
+{
+    StereoFrontEnd(imLeft, imRight, K, &imColor, 3);
+}
+
+// offline "ultimate test" mode (:660)
+Frame::Frame(const cv::Mat &imLeft, const cv::Mat &imRight, cv::Mat &imColor, const double &timeStamp,
+             ORBextractor *extractorLeft, ORBextractor *extractorRight, ORBVocabulary *voc, cv::Mat &K, cv::Mat &distCoef,
+             const float &bf, const float &thDepth, const int &SLOTMode)
+    : PSLOT_FRAME_INIT
+{
+    StereoFrontEnd(imLeft, imRight, K, &imColor, SLOTMode > 0 ? SLOTMode : 4);
+}
+#undef PSLOT_FRAME_INIT
 
 void Frame::ExtractORB(int flag, const cv::Mat &im)
 {
@@ -146,11 +212,25 @@ void Frame::AssignFeaturesToGrid()
         std::fprintf(stderr, "pslot Frame: pslot_assign_grid failed: %s\n", pslot_last_error());
         std::abort();
     }
+    mnGridToken = pslot_grid_token(mpORBextractorLeft->Handle());
     for (unsigned int i = 0; i < FRAME_GRID_COLS; i++)
         for (unsigned int j = 0; j < FRAME_GRID_ROWS; j++) {
             const int c = i * FRAME_GRID_ROWS + j;
             mGrid[i][j].assign(indices.begin() + cellStart[c], indices.begin() + cellStart[c + 1]);
         }
+}
+
+void Frame::EnsureDeviceGrid() const
+{
+    pslot_orb *h = mpORBextractorLeft->Handle();
+    if (mnGridToken != 0 && pslot_grid_token(h) == mnGridToken) return; // the device still holds this frame's set
+    const pslot_grid_spec spec = {mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv, FRAME_GRID_COLS,
+                                  FRAME_GRID_ROWS};
+    if (pslot_assign_grid(h, reinterpret_cast<const pslot_keypoint *>(mvKeysUn.data()), N, &spec, nullptr, nullptr, nullptr) != PSLOT_OK) {
+        std::fprintf(stderr, "pslot Frame: pslot_assign_grid failed: %s\n", pslot_last_error());
+        std::abort();
+    }
+    mnGridToken = pslot_grid_token(h);
 }
 
 bool Frame::PosInGrid(const cv::KeyPoint &kp, int &posX, int &posY)
@@ -195,6 +275,7 @@ std::vector<std::vector<size_t>> Frame::GetFeaturesInAreas(const std::vector<Are
     const int nq = (int)queries.size();
     std::vector<std::vector<size_t>> res(nq);
     if (nq == 0 || N == 0) return res;
+    EnsureDeviceGrid();
     int cap = 64;
     std::vector<int32_t> counts(nq), idx;
     for (;;) {
@@ -214,30 +295,52 @@ std::vector<std::vector<size_t>> Frame::GetFeaturesInAreas(const std::vector<Are
     return res;
 }
 
-void Frame::ComputeStereoMatches()
+void Frame::StereoMatchSets(const std::vector<cv::KeyPoint> &keysL, const cv::Mat &dl, const std::vector<cv::KeyPoint> &keysR,
+                            const cv::Mat &dr, std::vector<float> &uRight, std::vector<float> &depth)
 {
-    mvuRight = std::vector<float>(N, -1.0f);
-    mvDepth = std::vector<float>(N, -1.0f);
-    if (N == 0) return;
+    const int Nl = (int)keysL.size(), Nr = (int)keysR.size();
+    uRight = std::vector<float>(Nl, -1.0f);
+    depth = std::vector<float>(Nl, -1.0f);
+    if (Nl == 0) return;
     const float minZ = mb;
     const float maxD = mbf / minZ; // (:2172-2174)
 
     // cv::Mat descriptor rows are contiguous for matrices made by create(); copy if a caller handed a view
-    const cv::Mat &dl = mDescriptors, &dr = mDescriptorsRight;
     std::vector<unsigned char> bl, br;
     const unsigned char *pl = dl.data, *pr = dr.data;
-    if (dl.step != 32) { bl.resize((size_t)N * 32); for (int i = 0; i < N; ++i) std::memcpy(&bl[(size_t)i * 32], dl.ptr(i), 32); pl = bl.data(); }
-    const int Nr = (int)mvKeysRight.size();
+    if (dl.step != 32) { bl.resize((size_t)Nl * 32); for (int i = 0; i < Nl; ++i) std::memcpy(&bl[(size_t)i * 32], dl.ptr(i), 32); pl = bl.data(); }
     if (Nr && dr.step != 32) { br.resize((size_t)Nr * 32); for (int i = 0; i < Nr; ++i) std::memcpy(&br[(size_t)i * 32], dr.ptr(i), 32); pr = br.data(); }
 
     int rc = pslot_stereo_match(mpORBextractorLeft->Handle(), mpORBextractorRight->Handle(),
-                                reinterpret_cast<const pslot_keypoint *>(mvKeys.data()), N, pl,
-                                reinterpret_cast<const pslot_keypoint *>(mvKeysRight.data()), Nr, pr, mbf, maxD,
-                                mvuRight.data(), mvDepth.data());
+                                reinterpret_cast<const pslot_keypoint *>(keysL.data()), Nl, pl,
+                                reinterpret_cast<const pslot_keypoint *>(keysR.data()), Nr, pr, mbf, maxD, uRight.data(),
+                                depth.data());
     if (rc != PSLOT_OK) {
         std::fprintf(stderr, "pslot Frame: pslot_stereo_match failed: %s\n", pslot_last_error());
         std::abort();
     }
+}
+
+void Frame::ComputeStereoMatches() // (:2142-2316)
+{
+    StereoMatchSets(mvKeys, mDescriptors, mvKeysRight, mDescriptorsRight, mvuRight, mvDepth);
+}
+
+void Frame::ComputeObjStereoMatches() // (:2318-2503): the same routine on the object feature set
+{
+    if (mvTempObjKeys.size() <= 0) return; // (:2320)
+    StereoMatchSets(mvTempObjKeys, mTempObjPointsDescriptors, mvTempObjKeysRight, mTempObjPointsDescriptorsRight,
+                    mvuTempObjKeysRight, mvTempObjDepth);
+}
+
+void Frame::UndistortObjKeyPoints() // (:2080-2110)
+{
+    if (mDistCoef.empty() || mDistCoef.at<float>(0) == 0.0) {
+        mvTempObjKeysUn = mvTempObjKeys;
+        return;
+    }
+    std::fprintf(stderr, "pslot Frame: distorted object keypoints are not supported (all shipped cameras are rectified)\n");
+    std::abort();
 }
 
 } // namespace ORB_SLAM2

@@ -1,9 +1,12 @@
-// Frame.h — the stereo-construction path of PointSLOT's Frame (reference include/Frame.h:65, 94, 134,
-// 232-273, 303-325; src/Frame.cc:144-200, 1636-1664, 1808-1861, 2027-2038, 2049-2079, 2112-2140, 2142-2316) as a
-// drop-in: same constructor signature, same member names, same outputs (mvKeys, mvKeysRight, mvKeysUn,
-// mDescriptors, mDescriptorsRight, mvuRight, mvDepth, mGrid, N, mbf, mb).  Everything else in the reference's Frame
-// (object modes, BoW, pose) consumes these members and is out of scope; in a PointSLOT tree only the member
-// functions below are replaced.
+// Frame.h — the stereo-construction path of PointSLOT's Frame (reference include/Frame.h:65-90, 94, 134, 213-214,
+// 232-273, 303-325; src/Frame.cc:144-200, 203-760, 1636-1664, 1808-1861, 2027-2038, 2049-2110, 2112-2140, 2142-2316,
+// 2318-2503) as a drop-in: same constructor signatures (all six stereo constructors), same member names, same outputs
+// (mvKeys, mvKeysRight, mvKeysUn, mDescriptors, mDescriptorsRight, mvuRight, mvDepth, mGrid, N, mbf, mb, and the
+// object-feature set mvTempObj* of ComputeObjStereoMatches).  Everything else in the reference's Frame (detections,
+// masks, AssignFeatures, BoW, pose) consumes these members and is out of scope: the five object-mode constructors run
+// the hot path exactly like the plain one and then hand over to PointSLOT's own object stage through ObjectStageHook;
+// in a PointSLOT tree only the member functions below are replaced and the constructors stay as they are
+// (INTEGRATION.md §2).
 #ifndef FRAME_H
 #define FRAME_H
 
@@ -20,6 +23,14 @@ namespace ORB_SLAM2
 
 class ORBVocabulary; // opaque here: the stereo path never touches it
 class MapPoint;      // only pointers are stored
+class Detector;      // YOLO wrapper (reference include/YOLOdetector.h); opaque, only passed through
+} // namespace ORB_SLAM2
+namespace DS { class DeepSort; } // reference deepsort/include/deepsort.h; opaque
+#ifndef PSLOT_USE_OPENCV
+namespace cv { class MultiTracker; class Tracker; template <typename T> struct Ptr { T *p = nullptr; }; } // opencv_contrib tracking; opaque
+#endif
+namespace ORB_SLAM2
+{
 
 class Frame
 {
@@ -31,8 +42,43 @@ public:
           ORBextractor *extractorRight, ORBVocabulary *voc, cv::Mat &K, cv::Mat &distCoef, const float &bf,
           const float &thDepth);
 
+    // The five object-mode stereo constructors (reference Frame.h:68-90; Frame.cc:203, 328, 428, 516, 660).  Their hot
+    // path is the plain constructor's - scale info, ExtractORB on two threads, UndistortKeyPoints,
+    // ComputeStereoMatches, statics, mb, AssignFeaturesToGrid - and runs here identically; the object stage in between
+    // (detections, masks, AssignFeatures, ExtractObjORB: out of scope) is PointSLOT's own code, reached through
+    // ObjectStageHook when one is installed.
+    Frame(const cv::Mat &imLeft, const cv::Mat &imRight, cv::Mat &imColor, const double &timeStamp,
+          ORBextractor *extractorLeft, ORBextractor *extractorRight, ORBVocabulary *voc, cv::Mat &K, cv::Mat &distCoef,
+          const float &bf, const float &thDepth, Detector *YOLODetector);
+    Frame(const cv::Mat &imLeft, const cv::Mat &imRight, cv::Mat &imColor, const double &timeStamp,
+          ORBextractor *extractorLeft, ORBextractor *extractorRight, ORBVocabulary *voc, cv::Mat &K, cv::Mat &distCoef,
+          const float &bf, const float &thDepth, Detector *YOLODetector, cv::MultiTracker *multiTracker,
+          std::vector<cv::Ptr<cv::Tracker>> vTrackers);
+    Frame(const cv::Mat &imLeft, const cv::Mat &imRight, cv::Mat &imColor, const double &timeStamp,
+          ORBextractor *extractorLeft, ORBextractor *extractorRight, ORBVocabulary *voc, cv::Mat &K, cv::Mat &distCoef,
+          const float &bf, const float &thDepth, cv::MultiTracker *multiTracker, std::vector<cv::Ptr<cv::Tracker>> vTrackers);
+    Frame(const cv::Mat &imLeft, const cv::Mat &imRight, cv::Mat &imColor, const double &timeStamp,
+          ORBextractor *extractorLeft, ORBextractor *extractorRight, ORBVocabulary *voc, cv::Mat &K, cv::Mat &distCoef,
+          const float &bf, const float &thDepth, Detector *YOLODetector, DS::DeepSort *deepSort);
+    Frame(const cv::Mat &imLeft, const cv::Mat &imRight, cv::Mat &imColor, const double &timeStamp,
+          ORBextractor *extractorLeft, ORBextractor *extractorRight, ORBVocabulary *voc, cv::Mat &K, cv::Mat &distCoef,
+          const float &bf, const float &thDepth, const int &SLOTMode);
+
+    // Where PointSLOT's object stage plugs in (between ComputeStereoMatches and AssignFeaturesToGrid, as in the
+    // reference constructors): called with the frame and the colour image; may fill mvTempObj* and call
+    // ComputeObjStereoMatches().  Null by default.
+    typedef void (*ObjectStageFn)(Frame &frame, const cv::Mat &imLeft, const cv::Mat &imRight, cv::Mat &imColor, int mode);
+    static ObjectStageFn ObjectStageHook;
+
     // Extract ORB on the image. 0 for left image and 1 for right image.
     void ExtractORB(int flag, const cv::Mat &im);
+
+    // Stereo matching of the OBJECT feature set (reference Frame.cc:2318-2503: the same routine as
+    // ComputeStereoMatches on mvTempObjKeys / mvTempObjKeysRight and their descriptors, reading the same two
+    // pyramids); results in mvuTempObjKeysRight / mvTempObjDepth.
+    void ComputeObjStereoMatches();
+    // identity when the images are rectified (reference Frame.cc:2080-2110)
+    void UndistortObjKeyPoints();
 
     // Search a match for each keypoint in the left image to a keypoint in the right image.
     // If there is a match, depth is computed and the right coordinate associated to the left keypoint is stored.
@@ -69,6 +115,11 @@ public:
     std::vector<float> mvDepth;
     cv::Mat mDescriptors, mDescriptorsRight;
 
+    // object feature set of the current detection pass (reference Frame.h:167-173)
+    std::vector<cv::KeyPoint> mvTempObjKeys, mvTempObjKeysRight, mvTempObjKeysUn;
+    std::vector<float> mvuTempObjKeysRight, mvTempObjDepth;
+    cv::Mat mTempObjPointsDescriptors, mTempObjPointsDescriptorsRight;
+
     // MapPoints associated to keypoints, NULL pointer if no association.
     std::vector<MapPoint *> mvpMapPoints;
 
@@ -90,7 +141,18 @@ public:
 
     static bool mbInitialComputations;
 
+    // The device keeps ONE gridded keypoint set per extractor (the last AssignFeaturesToGrid).  The reference reads
+    // F.mGrid / F.mvKeysUn of whichever frame it is handed, so before a device search the frame checks that the set on
+    // the device is still its own (pslot_grid_token) and re-uploads it otherwise - copies of a frame, or an older frame
+    // searched after a newer one was built on the same extractor, behave as in the reference.
+    void EnsureDeviceGrid() const;
+    mutable unsigned long long mnGridToken = 0;
+
 private:
+    // the hot path shared by all six constructors
+    void StereoFrontEnd(const cv::Mat &imLeft, const cv::Mat &imRight, cv::Mat &K, cv::Mat *imColor, int objectMode);
+    void StereoMatchSets(const std::vector<cv::KeyPoint> &keysL, const cv::Mat &descL, const std::vector<cv::KeyPoint> &keysR,
+                         const cv::Mat &descR, std::vector<float> &uRight, std::vector<float> &depth);
     // identity when the images are rectified (k1 == 0, all shipped YAMLs); reference Frame.cc:2049-2079
     void UndistortKeyPoints();
     // Computes image bounds for the undistorted image (reference Frame.cc:2112-2140)

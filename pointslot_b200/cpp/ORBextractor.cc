@@ -26,7 +26,7 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
 
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST,
                            int device, bool keepHostPyramid)
-    : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST),
+    : mvImagePyramid(this), nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST),
       minThFAST(_minThFAST), mpCtx(nullptr), mbKeepHostPyramid(keepHostPyramid)
 {
     if (pslot_orb_create(&mpCtx, nfeatures, _scaleFactor, nlevels, iniThFAST, minThFAST, device) != PSLOT_OK)
@@ -95,17 +95,24 @@ void ORBextractor::Run(const unsigned char *data, int w, int h, long step, int c
         cv::Mat d = _descriptors.getMat();
         for (int i = 0; i < n; ++i) std::memcpy(d.ptr(i), mvDescBuf.data() + (size_t)i * 32, 32);
     }
+    mvImagePyramid.MarkStale(); // the host mirror now lags the device pyramid; refilled on first access
     if (mbKeepHostPyramid) SyncImagePyramid();
+}
+
+void LazyPyramid::Fill()
+{
+    if (mbStale) mpOwner->SyncImagePyramid();
 }
 
 void ORBextractor::SyncImagePyramid()
 {
+    std::vector<cv::Mat> &pyr = mvImagePyramid.mv;
+    mvImagePyramid.mbStale = false;
     for (int l = 0; l < nlevels; ++l) {
         int w = 0, h = 0;
         if (pslot_orb_level(mpCtx, l, nullptr, 0, &w, &h) != PSLOT_OK) die("pslot_orb_level");
-        mvImagePyramid[l].create(h, w, CV_8UC1);
-        if (pslot_orb_level(mpCtx, l, mvImagePyramid[l].data, (ptrdiff_t)mvImagePyramid[l].step, &w, &h) != PSLOT_OK)
-            die("pslot_orb_level");
+        pyr[l].create(h, w, CV_8UC1);
+        if (pslot_orb_level(mpCtx, l, pyr[l].data, (ptrdiff_t)pyr[l].step, &w, &h) != PSLOT_OK) die("pslot_orb_level");
     }
 }
 

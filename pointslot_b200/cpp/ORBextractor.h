@@ -5,11 +5,12 @@
 // compile unchanged.  Every result comes from libpslot_orb.so (include/pslot_orb.h); nothing is computed
 // on the CPU here.
 //
-// Difference a maintainer must know about: the public member `mvImagePyramid`
-// (reference :85) is only filled on request.  The GPU stereo matcher reads the pyramid on the device, so
-// downloading 1.4 MB per image just to mirror the member would be wasted work.  Callers that read the
-// member on the host (Frame::ComputeObjStereoMatches in the reference) either call SyncImagePyramid()
-// first or construct the extractor with keepHostPyramid = true.
+// The public member `mvImagePyramid` (reference :85) keeps its name and its vector-like use
+// (`mvImagePyramid[level].rowRange(...)`, `.size()`, iteration) but fills itself LAZILY: the GPU stereo matcher reads
+// the pyramid on the device, so the 1.4 MB per image are only downloaded when host code first touches the member after
+// an operator() (the reference's Frame::ComputeObjStereoMatches, Frame.cc:2323, 2422-2442, or a viewer).  The levels are
+// borderless (the reference's 19-px replicated frame is never read by any consumer).  Constructing with
+// keepHostPyramid = true downloads eagerly inside operator() instead.
 #ifndef ORBEXTRACTOR_H
 #define ORBEXTRACTOR_H
 
@@ -22,6 +23,33 @@ struct pslot_orb;
 
 namespace ORB_SLAM2
 {
+
+class ORBextractor;
+
+// std::vector<cv::Mat> look-alike that downloads the device pyramid on first host access after each extraction
+class LazyPyramid
+{
+public:
+    typedef std::vector<cv::Mat>::iterator iterator;
+    explicit LazyPyramid(ORBextractor *owner) : mpOwner(owner), mbStale(false) {}
+    cv::Mat &operator[](size_t i) { Fill(); return mv[i]; }
+    cv::Mat &at(size_t i) { Fill(); return mv.at(i); }
+    size_t size() const { return mv.size(); }
+    bool empty() const { return mv.empty(); }
+    void resize(size_t n) { mv.resize(n); }
+    iterator begin() { Fill(); return mv.begin(); }
+    iterator end() { Fill(); return mv.end(); }
+    operator std::vector<cv::Mat> &() { Fill(); return mv; }
+    void MarkStale() { mbStale = true; }
+    bool IsStale() const { return mbStale; }
+
+private:
+    void Fill();
+    friend class ORBextractor;
+    std::vector<cv::Mat> mv;
+    ORBextractor *mpOwner;
+    bool mbStale;
+};
 
 class ORBextractor
 {
@@ -54,9 +82,10 @@ public:
     std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
     std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
-    std::vector<cv::Mat> mvImagePyramid;
+    LazyPyramid mvImagePyramid;
 
-    // Download the pyramid of the last operator() into mvImagePyramid (borderless levels).
+    // Download the pyramid of the last operator() into mvImagePyramid now (borderless levels); host reads of the member
+    // do this by themselves.
     void SyncImagePyramid();
     // The C-ABI context behind this object (used by Frame::ComputeStereoMatches).
     pslot_orb *Handle() const { return mpCtx; }

@@ -46,8 +46,9 @@ int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint *> &vpMa
         for (int i = 0; i < N; ++i) std::memcpy(&fdesc[(size_t)i * 32], F.mDescriptors.ptr(i), 32);
         pd = fdesc.data();
     }
-    // ... run the search on the device, against the grid Frame::AssignFeaturesToGrid left there (the frame must be the
-    // one most recently gridded on its left extractor, which is how Tracking uses mCurrentFrame) ...
+    // ... run the search on the device, against F's own grid: if another frame has been gridded on the extractor since
+    // (or F is a copy), the frame re-uploads its keypoints first (the reference reads F.mGrid / F.mvKeysUn directly) ...
+    F.EnsureDeviceGrid();
     std::vector<int32_t> match(nMP);
     int nmatches = 0;
     int rc = pslot_search_by_projection(F.mpORBextractorLeft->Handle(), mps.data(), mpDesc.data(), nMP, pd,

@@ -7,16 +7,43 @@
 //        mGrid as 64*48 x (int32 size, int32 entries...), then 3 windows x (int32 n, entries) from GetFeaturesInArea
 //        and the same 3 from GetFeaturesInAreas; then int32 nMP, nMP x (4 float + 2 int32 map point record as
 //        pslot_map_point), nMP x 32 descriptor bytes, int32 nmatches of ORBmatcher(0.8).SearchByProjection(frame, mps, 3),
-//        N x int32 map-point index held by frame.mvpMapPoints[idx] afterwards (-1 = none)
+//        N x int32 map-point index held by frame.mvpMapPoints[idx] afterwards (-1 = none);
+//        then the object-mode frame built in between on the same extractors from both images rolled down 7 rows
+//        (SLOTMode constructor + ObjectStageHook): int32 nObjL, nObjR, nObjL float mvuTempObjKeysRight, nObjL float
+//        mvTempObjDepth, int32 N of that frame
+// The second frame is built BEFORE the area / projection queries on the first one, so those queries only pass when the
+// first frame notices that the device grid is no longer its own (Frame::EnsureDeviceGrid).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "Frame.h"
 #include "ORBmatcher.h"
 
 using namespace ORB_SLAM2;
+
+// stands in for PointSLOT's object stage: every third left / second right keypoint becomes an "object feature"
+static void object_stage(Frame &F, const cv::Mat &, const cv::Mat &, cv::Mat &, int)
+{
+    std::vector<int> il, ir;
+    for (int i = 0; i < (int)F.mvKeys.size(); i += 3) il.push_back(i);
+    for (int i = 0; i < (int)F.mvKeysRight.size(); i += 2) ir.push_back(i);
+    F.mvTempObjKeys.clear(); F.mvTempObjKeysRight.clear();
+    F.mTempObjPointsDescriptors.create((int)il.size(), 32, CV_8U);
+    F.mTempObjPointsDescriptorsRight.create((int)ir.size(), 32, CV_8U);
+    for (size_t k = 0; k < il.size(); ++k) {
+        F.mvTempObjKeys.push_back(F.mvKeys[il[k]]);
+        std::memcpy(F.mTempObjPointsDescriptors.ptr((int)k), F.mDescriptors.ptr(il[k]), 32);
+    }
+    for (size_t k = 0; k < ir.size(); ++k) {
+        F.mvTempObjKeysRight.push_back(F.mvKeysRight[ir[k]]);
+        std::memcpy(F.mTempObjPointsDescriptorsRight.ptr((int)k), F.mDescriptorsRight.ptr(ir[k]), 32);
+    }
+    F.UndistortObjKeyPoints();
+    F.ComputeObjStereoMatches();
+}
 
 int main(int argc, char **argv)
 {
@@ -55,8 +82,18 @@ int main(int argc, char **argv)
     for (int i = 0; i < Nr; ++i) std::fwrite(frame.mDescriptorsRight.ptr(i), 1, 32, o);
     std::fwrite(frame.mvuRight.data(), 4, N, o);
     std::fwrite(frame.mvDepth.data(), 4, N, o);
-    left->SyncImagePyramid();
-    const cv::Mat &p1 = left->mvImagePyramid[1];
+    const cv::Mat p1 = left->mvImagePyramid[1]; // no SyncImagePyramid(): the member fills itself on first host access
+
+    // a second frame on the same extractors (object-mode constructor), from the images rolled down by 7 rows
+    std::vector<unsigned char> L2(L.size()), R2(R.size());
+    for (int y = 0; y < H; ++y) {
+        std::memcpy(&L2[(size_t)((y + 7) % H) * W], &L[(size_t)y * W], W);
+        std::memcpy(&R2[(size_t)((y + 7) % H) * W], &R[(size_t)y * W], W);
+    }
+    cv::Mat imL2(H, W, CV_8UC1, L2.data()), imR2(H, W, CV_8UC1, R2.data()), imColor;
+    Frame::ObjectStageHook = object_stage;
+    const int slotMode = 4;
+    Frame other(imL2, imR2, imColor, 0.3, left, right, nullptr, K, dist, bf, thDepth, slotMode);
     std::fwrite(&p1.cols, 4, 1, o); std::fwrite(&p1.rows, 4, 1, o);
     for (int r = 0; r < p1.rows; ++r) std::fwrite(p1.ptr(r), 1, p1.cols, o);
     const int dd = N >= 2 ? ORBmatcher::DescriptorDistance(frame.mDescriptors.row(0), frame.mDescriptors.row(1)) : -1;
@@ -112,6 +149,11 @@ int main(int argc, char **argv)
         const int who = frame.mvpMapPoints[idx] ? (int)(frame.mvpMapPoints[idx] - pool.data()) : -1;
         std::fwrite(&who, 4, 1, o);
     }
+    const int nObjL = (int)other.mvTempObjKeys.size(), nObjR = (int)other.mvTempObjKeysRight.size();
+    std::fwrite(&nObjL, 4, 1, o); std::fwrite(&nObjR, 4, 1, o);
+    std::fwrite(other.mvuTempObjKeysRight.data(), 4, nObjL, o);
+    std::fwrite(other.mvTempObjDepth.data(), 4, nObjL, o);
+    std::fwrite(&other.N, 4, 1, o);
     std::fclose(o);
     std::printf("shim ok: N=%d Nr=%d matched=%d mb=%g projection matches=%d\n", N, Nr,
                 (int)std::count_if(frame.mvuRight.begin(), frame.mvuRight.end(), [](float v) { return v >= 0; }), frame.mb, nmatches);

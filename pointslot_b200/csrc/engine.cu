@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <new>
 #include <vector>
 
@@ -384,6 +385,7 @@ struct pslot_orb {
     int gk_cap = 0, gcs_cap = 0, q_cap = 0;
     size_t qout_cap = 0;
     int grid_n = -1;
+    uint64_t grid_token = 0; // identity of the gridded keypoint set (pslot_grid_token); 0 = none
     pslot_grid_spec grid_spec = {};
     std::vector<float> h_gangle; // mvKeysUn[i].angle of the gridded frame (rotation check of the last-frame search)
     // projection search scratch (pslot_search_by_projection)
@@ -1025,6 +1027,7 @@ int pslot_assign_grid(pslot_orb *ctx, const pslot_keypoint *kps_un, int n, const
     }
     cudaStream_t st = E.st;
     ctx->grid_n = -1;
+    ctx->grid_token = 0;
     if (n) CU(cudaMemcpyAsync(ctx->d_gk, kps_un, sizeof(pslot_keypoint) * (size_t)n, cudaMemcpyHostToDevice, st));
     launch_assign_grid(ctx->d_gk, nullptr, n, (size_t)std::max(n, 1), *spec, ctx->d_gcs, ctx->d_gidx, 1, st);
     CU(cudaGetLastError());
@@ -1034,12 +1037,16 @@ int pslot_assign_grid(pslot_orb *ctx, const pslot_keypoint *kps_un, int n, const
     CU(cudaStreamSynchronize(st));
     if (indices && total) CU(cudaMemcpy(indices, ctx->d_gidx, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost));
     if (n_in_grid) *n_in_grid = total;
+    static std::atomic<uint64_t> generation{0}; // process-wide, so tokens of different contexts never collide either
     ctx->grid_n = n;
+    ctx->grid_token = ++generation;
     ctx->grid_spec = *spec;
     ctx->h_gangle.resize((size_t)n);
     for (int i = 0; i < n; ++i) ctx->h_gangle[i] = kps_un[i].angle;
     return PSLOT_OK;
 }
+
+uint64_t pslot_grid_token(const pslot_orb *ctx) { return ctx ? ctx->grid_token : 0; }
 
 int pslot_features_in_area(pslot_orb *ctx, const pslot_area_query *queries, int nq, int cap, int32_t *counts,
                            int32_t *indices)

@@ -53,6 +53,11 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle_mod):
     md = np.frombuffer(raw, np.uint8, 32 * n_mp, o).reshape(n_mp, 32); o += 32 * n_mp
     (nmatches,) = struct.unpack_from("<i", raw, o); o += 4
     holder = np.frombuffer(raw, np.int32, N, o); o += 4 * N
+    n_obj_l, n_obj_r = struct.unpack_from("<2i", raw, o); o += 8
+    obj_ur = np.frombuffer(raw, np.float32, n_obj_l, o); o += 4 * n_obj_l
+    obj_dp = np.frombuffer(raw, np.float32, n_obj_l, o); o += 4 * n_obj_l
+    (n_other,) = struct.unpack_from("<i", raw, o); o += 4
+    assert o == len(raw)
 
     O = oracle_mod
     oL, oR = O.OracleExtractor(*params), O.OracleExtractor(*params)
@@ -63,7 +68,7 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle_mod):
     assert np.array_equal(dL, odL) and np.array_equal(dR, odR)
     assert np.array_equal(ur >= 0, our >= 0) and np.all(np.abs(ur - our) <= 1e-3)
     assert np.allclose(dp, odp, rtol=1e-5, atol=0)
-    assert np.array_equal(p1, oL.level(1))  # mvImagePyramid mirror
+    assert np.array_equal(p1, oL.level(1))  # mvImagePyramid fills itself on first host access (no explicit sync)
     assert dd == O.hamming256(odL[0], odL[1])
     # mGrid (Frame.cc:1636-1655) and GetFeaturesInArea (:1808-1861), host walk and batched device form
     inv_w, inv_h = float(np.float32(64) / np.float32(W)), float(np.float32(48) / np.float32(H))
@@ -85,3 +90,13 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle_mod):
             expect[m] = i
     assert nmatches == nref and nref > 50
     assert np.array_equal(holder, expect)
+
+    # The object-mode constructor (Frame.h:86-90) built a second frame on the same extractors in between - the area and
+    # projection queries above still saw the FIRST frame's grid (Frame::EnsureDeviceGrid) - and its object stage ran
+    # Frame::ComputeObjStereoMatches (Frame.cc:2318-2503) on a subset of the features: same routine, same answer.
+    L2, R2 = np.roll(L, 7, axis=0), np.roll(R, 7, axis=0)
+    k2L, d2L = oL.extract(L2); k2R, d2R = oR.extract(R2)
+    assert n_other == len(k2L) and n_obj_l == len(k2L[::3]) and n_obj_r == len(k2R[::2])
+    our2, odp2 = O.stereo_match(oL, oR, k2L[::3], d2L[::3], k2R[::2], d2R[::2], bf, maxD)
+    assert np.array_equal(obj_ur >= 0, our2 >= 0) and np.all(np.abs(obj_ur - our2) <= 1e-3)
+    assert np.allclose(obj_dp, odp2, rtol=1e-5, atol=0) and (our2 >= 0).sum() > 10
