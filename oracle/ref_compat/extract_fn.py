@@ -19,6 +19,7 @@ from pathlib import Path
 PIECES = [
     ("frame_fns.inc", "src/Frame.cc", [
         "void Frame::ComputeStereoMatches()",
+        "void Frame::ComputeObjStereoMatches()",
         "void Frame::AssignFeaturesToGrid()",
         "vector<size_t> Frame::GetFeaturesInArea(const float &x, const float  &y, const float  &r, const int minLevel, const int maxLevel) const",
         "bool Frame::PosInGrid(const cv::KeyPoint &kp, int &posX, int &posY)",

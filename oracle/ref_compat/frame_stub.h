@@ -40,6 +40,7 @@ public:
 class Frame {
 public:
     void ComputeStereoMatches();
+    void ComputeObjStereoMatches();
     void AssignFeaturesToGrid();
     vector<size_t> GetFeaturesInArea(const float &x, const float &y, const float &r, const int minLevel = -1, const int maxLevel = -1) const;
     bool PosInGrid(const cv::KeyPoint &kp, int &posX, int &posY);
@@ -51,6 +52,9 @@ public:
     std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
     std::vector<float> mvuRight, mvDepth;
     cv::Mat mDescriptors, mDescriptorsRight;
+    std::vector<cv::KeyPoint> mvTempObjKeys, mvTempObjKeysUn, mvTempObjKeysRight; // include/Frame.h:167-173
+    vector<float> mvTempObjDepth, mvuTempObjKeysRight;
+    cv::Mat mTempObjPointsDescriptors, mTempObjPointsDescriptorsRight;
     std::vector<MapPoint *> mvpMapPoints;
     std::vector<bool> mvbOutlier;
     static float mfGridElementWidthInv, mfGridElementHeightInv;

@@ -58,6 +58,26 @@ int reff_stereo(void *extL, void *extR, const void *kL, int nL, const uint8_t *d
     return 0;
 }
 
+// Frame::ComputeObjStereoMatches (Frame.cc:2318-2503) on an object feature set
+int reff_obj_stereo(void *extL, void *extR, const void *kL, int nL, const uint8_t *dL, const void *kR, int nR,
+                    const uint8_t *dR, float mbf, float mb, float *uright, float *depth)
+{
+    Frame F;
+    F.mpORBextractorLeft = static_cast<ORBextractor *>(extL);
+    F.mpORBextractorRight = static_cast<ORBextractor *>(extR);
+    F.mvScaleFactors = F.mpORBextractorLeft->GetScaleFactors();
+    F.mvInvScaleFactors = F.mpORBextractorLeft->GetInverseScaleFactors();
+    set_keys(F.mvTempObjKeys, kL, nL); set_keys(F.mvTempObjKeysRight, kR, nR);
+    F.mvTempObjKeysUn = F.mvTempObjKeys;
+    F.mbf = mbf; F.mb = mb;
+    F.mTempObjPointsDescriptors = desc_mat(dL, nL); F.mTempObjPointsDescriptorsRight = desc_mat(dR, nR);
+    F.ComputeObjStereoMatches();
+    if ((int)F.mvuTempObjKeysRight.size() != nL) return -1;
+    memcpy(uright, F.mvuTempObjKeysRight.data(), sizeof(float) * (size_t)nL);
+    memcpy(depth, F.mvTempObjDepth.data(), sizeof(float) * (size_t)nL);
+    return 0;
+}
+
 int reff_hamming256(const uint8_t *a, const uint8_t *b)
 {
     alignas(4) uint8_t ba[32], bb[32];

@@ -87,6 +87,7 @@ def _load(variant: str = "stock"):
     lib.ref_extract.argtypes = [vp, vp, i32, i32, C.c_size_t, vp, vp, i32]
     lib.ref_level.argtypes = [vp, i32, vp, C.c_size_t, C.POINTER(i32), C.POINTER(i32)]
     lib.reff_stereo.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, f32, f32, vp, vp]
+    lib.reff_obj_stereo.argtypes = lib.reff_stereo.argtypes
     lib.reff_hamming256.argtypes = [vp, vp]
     lib.reff_frame_create.restype = vp
     lib.reff_frame_create.argtypes = [vp, i32, vp, vp, vp, i32, f32, f32, f32, f32, f32, f32]
@@ -161,6 +162,16 @@ def stereo_match(eL: ReferenceExtractor, eR: ReferenceExtractor, kL, dL, kR, dR,
     dL = np.ascontiguousarray(dL, np.uint8); dR = np.ascontiguousarray(dR, np.uint8)
     ur = np.zeros(max(len(kL), 1), np.float32); dp = np.zeros(max(len(kL), 1), np.float32)
     eL._lib.reff_stereo(eL._h, eR._h, _p(kL), len(kL), _p(dL), _p(kR), len(kR), _p(dR), mbf, mb, _p(ur), _p(dp))
+    return ur[:len(kL)], dp[:len(kL)]
+
+
+def obj_stereo_match(eL: ReferenceExtractor, eR: ReferenceExtractor, kL, dL, kR, dR, mbf: float, mb: float):
+    """Frame::ComputeObjStereoMatches (Frame.cc:2318-2503) on an object feature set -> (uRight, depth)."""
+    kL = np.ascontiguousarray(kL, KEYPOINT_DTYPE); kR = np.ascontiguousarray(kR, KEYPOINT_DTYPE)
+    dL = np.ascontiguousarray(dL, np.uint8); dR = np.ascontiguousarray(dR, np.uint8)
+    ur = np.zeros(max(len(kL), 1), np.float32); dp = np.zeros(max(len(kL), 1), np.float32)
+    rc = eL._lib.reff_obj_stereo(eL._h, eR._h, _p(kL), len(kL), _p(dL), _p(kR), len(kR), _p(dR), mbf, mb, _p(ur), _p(dp))
+    assert rc == 0
     return ur[:len(kL)], dp[:len(kL)]
 
 

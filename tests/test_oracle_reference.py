@@ -174,6 +174,27 @@ def test_reference_stereo_infinite_max_d(oracle_mod):
     assert ur.tobytes() == our.tobytes() and dp.tobytes() == odp.tobytes()
 
 
+def test_oracle_equals_reference_object_stereo(oracle_mod):
+    """Frame::ComputeObjStereoMatches (Frame.cc:2318-2503) is the same routine on the object feature set: the oracle's
+    stereo matcher, fed a subset of the features, gives the reference's answer bit for bit."""
+    ref_path = _ref("mono")
+    from pointslot_b200.synth import synth_pair
+    params = (2000, 1.2, 8, 20, 7)
+    bf, fx = 384.38148, 721.5377
+    L, R = synth_pair(1242, 375, 31)
+    rL = ref_path.ReferenceExtractor(*params, variant="mono", primitives="native")
+    rR = ref_path.ReferenceExtractor(*params, variant="mono", primitives="native")
+    oL, oR = oracle_mod.OracleExtractor(*params), oracle_mod.OracleExtractor(*params)
+    kL, dL = rL.extract(L); kR, dR = rR.extract(R)
+    oL.extract(L); oR.extract(R)
+    box = (kL["x"] > 300) & (kL["x"] < 900); boxr = (kR["x"] > 200) & (kR["x"] < 900)   # features inside an "object" box
+    mb = float(F(bf) / F(fx))
+    ur, dp = ref_path.obj_stereo_match(rL, rR, kL[box], dL[box], kR[boxr], dR[boxr], bf, mb)
+    our, odp = oracle_mod.stereo_match(oL, oR, kL[box], dL[box], kR[boxr], dR[boxr], bf, float(F(bf) / F(mb)))
+    assert (ur >= 0).sum() > 50
+    assert ur.tobytes() == our.tobytes() and dp.tobytes() == odp.tobytes()
+
+
 def test_reference_descriptor_distance(oracle_mod):
     ref_path = _ref("stock")
     rng = np.random.default_rng(5)
