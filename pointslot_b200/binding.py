@@ -23,7 +23,7 @@ KEYPOINT_DTYPE = np.dtype(
 
 # every symbol include/pslot_orb.h declares (tests check the .so exports exactly these)
 ABI_SYMBOLS = [
-    "pslot_last_error", "pslot_abi_version", "pslot_device_count",
+    "pslot_last_error", "pslot_abi_version", "pslot_device_count", "pslot_host_alloc", "pslot_host_free",
     "pslot_orb_create", "pslot_orb_destroy", "pslot_orb_levels", "pslot_orb_tables", "pslot_orb_max_keypoints",
     "pslot_orb_extract", "pslot_orb_extract_color", "pslot_orb_level", "pslot_stereo_match", "pslot_hamming256",
     "pslot_batch_create", "pslot_batch_destroy", "pslot_batch_set_copy_stream", "pslot_batch_max_keypoints", "pslot_batch_stream",
@@ -119,6 +119,8 @@ def lib():
     L.pslot_batch_set_profiling.argtypes = [vp, C.c_int]
     L.pslot_batch_stage_times.argtypes = [vp, vp]
     L.pslot_batch_stats.argtypes = [vp, vp]
+    L.pslot_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]
+    L.pslot_host_free.argtypes = [vp]
     L.pslot_batch_stereo_counters.argtypes = [vp, vp]
     L.pslot_orb_debug_candidates.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, ip]
     L.pslot_orb_debug_level_keypoints.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, ip]
@@ -243,6 +245,27 @@ def assign_grid(ext: OrbExtractor, kps_un, spec: GridSpec):
     tot = C.c_int(0)
     _check(lib().pslot_assign_grid(ext._h, _p(kps_un), n, C.byref(spec), _p(cs), _p(idx), C.byref(tot)))
     return cs, idx[:tot.value].copy()
+
+
+class PinnedBuffer:
+    """Page-locked host memory from pslot_host_alloc, viewed as a numpy array (freed with the object)."""
+
+    def __init__(self, shape, dtype=np.uint8, write_combined: bool = False):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _check(lib().pslot_host_alloc(C.byref(p), self.nbytes, 1 if write_combined else 0))
+        self._p = p
+        self.ptr = p.value or 0
+        buf = (C.c_ubyte * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def close(self):
+        if getattr(self, "_p", None) is not None and self._p.value:
+            self.array = None
+            lib().pslot_host_free(self._p)
+            self._p = None
+
+    __del__ = close
 
 
 def grid_token(ext: OrbExtractor) -> int:

@@ -455,6 +455,22 @@ int pslot_device_count(void)
     return n;
 }
 
+// Page-locked host buffers for the batch API's inputs / outputs (so callers need no CUDA headers of their own).
+int pslot_host_alloc(void **ptr, size_t bytes, int write_combined)
+{
+    if (!ptr) return fail(PSLOT_ERR_ARG, "ptr is null");
+    *ptr = nullptr;
+    if (bytes == 0) return PSLOT_OK;
+    CU(cudaHostAlloc(ptr, bytes, (write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault) | cudaHostAllocPortable));
+    return PSLOT_OK;
+}
+
+int pslot_host_free(void *ptr)
+{
+    if (ptr) CU(cudaFreeHost(ptr));
+    return PSLOT_OK;
+}
+
 int pslot_hamming256(const void *a, const void *b)
 {
     uint64_t x[4], y[4];

@@ -1,0 +1,67 @@
+"""CPU: the host logic of bench.py that needs no GPU - configuration table vs BASELINE.json, pyramid sizes, the algorithmic
+byte formulas of SURVEY.md §8d, the affinity parser, and the reference CPU arm (a few pairs, both kinds)."""
+import json
+from pathlib import Path
+
+import numpy as np
+
+import bench
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_configs_cover_baseline_json():
+    base = json.loads((ROOT / "BASELINE.json").read_text())
+    assert len(base["configs"]) == 5
+    c = bench.CONFIGS
+    assert set(c) == {"kitti1000", "kitti2000", "euroc", "hd1080", "shard8000"}
+    assert c["kitti1000"]["params"] == (1000, 1.2, 8, 20, 5) and (c["kitti1000"]["W"], c["kitti1000"]["H"]) == (1242, 375)
+    assert c["kitti2000"]["params"] == (2000, 1.2, 8, 20, 7)
+    assert (c["euroc"]["W"], c["euroc"]["H"], c["euroc"]["params"][0]) == (752, 480, 1200)
+    assert (c["hd1080"]["W"], c["hd1080"]["H"], c["hd1080"]["params"][0]) == (1920, 1080, 4000)
+    assert c["shard8000"]["total_pairs"] == 8000 and c["shard8000"]["params"] == c["kitti2000"]["params"]
+    assert bench.metric_name(c["kitti1000"]).startswith(base["metric"][:60])
+
+
+def test_level_sizes_match_survey_appendix_b():
+    assert sum(bench.level_sizes(bench.CONFIGS["kitti1000"])) == 1441432
+    assert sum(bench.level_sizes(bench.CONFIGS["euroc"])) == 1117367
+    assert sum(bench.level_sizes(bench.CONFIGS["hd1080"])) == 6419321
+    assert bench.level_sizes(bench.CONFIGS["kitti1000"])[0] == 465750
+
+
+def test_stage_bytes_nominal_values():
+    """SURVEY §8d nominal KITTI counts -> B_img = 9,530,975 and B_st = 2,040,000 (our K4-6 is fused: it is charged its
+    external bytes only, so the describe row is smaller than the survey's unfused K4 + K5 + K6)."""
+    cfg = bench.CONFIGS["kitti2000"]
+    tot = dict(pairs=1, candidates=2 * 10000, keypoints=2 * 2000, sad_evals=600, matches=400, row_candidates=2000 * 58,
+               hamming_evals=2000 * 10)
+    b, counts = bench.stage_bytes_per_pair(cfg, tot)
+    assert counts["row_candidates_per_left_keypoint"] == 58 and counts["hamming_evals_per_left_keypoint"] == 10
+    st = 60 * 4000 + 2000 * (8 * 58 + 32 * 10) + 352 * 600 + 8 * 2000 + 8 * 600
+    assert b["stereo_match"] == st == 2040000
+    SP, P0, PL = 1441432, 465750, 36435
+    assert b["pyramid"] == 2 * ((SP - PL) + (SP - P0)) and b["fast"] == 2 * (SP + 80000)
+    assert b["describe"] == 2 * 2000 * 1913
+
+
+def test_affinity_parser(monkeypatch):
+    class R:
+        stdout = "\t\x1b[4mGPU0\tGPU1\tCPU Affinity\tNUMA Affinity\tGPU NUMA ID\x1b[0m\nGPU0\t X \tNV18\t0-15,64-79\t0\t\tN/A\nGPU1\tNV18\t X \t16-31\t1\t\tN/A\n"
+    monkeypatch.setattr(bench.subprocess, "run", lambda *a, **k: R())
+    assert bench.gpu_cpu_affinity(0) == set(range(0, 16)) | set(range(64, 80))
+    assert bench.gpu_cpu_affinity(1) == set(range(16, 32))
+    assert bench.gpu_cpu_affinity(5) is None
+
+
+def test_cpu_arm_runs_reference_and_port():
+    from pointslot_b200.synth import synth_pair
+    cfg = dict(bench.CONFIGS["kitti1000"]); cfg["W"], cfg["H"] = 640, 360
+    L, R = synth_pair(640, 360, 4)
+    for pref in (True, False):
+        arm = bench.CpuArm(cfg, prefer_reference=pref)
+        assert arm.kind in ("reference", "port") and (pref or arm.kind == "port")
+        fn = arm.make_pair_fn()
+        assert fn(L, R) > 100 and fn(L, R, True) > 100
+        v, done, el = arm.pairs_per_sec([L], [R], 2, 0.5)
+        assert done >= 1 and v > 0

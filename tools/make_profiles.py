@@ -6,7 +6,9 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 G, P = ROOT / "gpurun_out", ROOT / "profiles"
-pre = sys.argv[1] if len(sys.argv) > 1 else "r01"
+pre = sys.argv[1] if len(sys.argv) > 1 else "r02"
+SM_CLOCK_GHZ, SMS = 1.965, 148  # measured (MEASURED_PEAKS.json sm_max_mhz; clocks.sm during the bench)
+SHARED_PEAK_GBPS = SMS * 128 * SM_CLOCK_GHZ  # one 128-byte shared-memory wavefront per SM per clock = 37.2 TB/s
 KERNELS = {"fast": "k_fast_cells", "describe": "k_describe", "pyramid_level1": "k_resize_level", "quadtree": "k_quadtree",
            "stereo_match": "k_stereo_match", "ingest": "k_gray_repitch"}
 
@@ -14,6 +16,10 @@ shutil.copy(G / "bench.json", P / f"{pre}_bench.json")
 shutil.copy(G / "bench_reference.json", P / f"{pre}_bench_reference.json")
 shutil.copy(G / "launches_bench.csv", P / f"{pre}_launches_bench.csv")
 
+ncu_kernels = {"note": "ncu --set full --clock-control none, one launch of each kernel over a 125-pair sub-batch of the bench "
+               "workload (tools/prof.sh); pct = % of peak sustained; shared_GBps = shared-memory wavefronts x 128 B / duration "
+               "against 148 SM x 128 B/clk x 1.965 GHz; bound = the busiest of {dram -> hbm, l1tex/shared -> shared, issue slots -> "
+               "issue}, or latency when none reaches 50 %", "kernels": {}}
 traffic = {"batch": 125, "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full "
            "(tools/prof.sh), sub-batch of 125 pairs = 250 images", "kernels": {}}
 for name, k in KERNELS.items():
@@ -31,9 +37,30 @@ for name, k in KERNELS.items():
     def val(key):
         v, u = float(r[ix[key]].replace(",", "")), units[ix[key]]
         return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+    def pct(key):
+        return float(r[ix[key]].replace(",", "")) if key in ix and r[ix[key]] not in ("", "n/a") else None
+    t_us = val("gpu__time_duration.sum") * {"usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3, "second": 1e6}.get(units[ix["gpu__time_duration.sum"]], 1.0)
+    wf = pct("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum") or 0.0
+    d = {"dram_pct": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+         "l1tex_pct": pct("l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
+         "lts_pct": pct("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+         "issue_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+         "sm_pct": pct("sm__throughput.avg.pct_of_peak_sustained_elapsed"),
+         "occupancy_pct": pct("sm__warps_active.avg.pct_of_peak_sustained_active"),
+         "registers": pct("launch__registers_per_thread"),
+         "duration_us": t_us, "capture_pairs": 125,
+         "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+         "shared_wavefronts": wf, "shared_bank_conflicts": pct("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+         "shared_GBps": wf * 128 / (t_us * 1e-6) / 1e9 if t_us else None, "shared_peak_GBps": SHARED_PEAK_GBPS}
+    d["shared_frac"] = d["shared_GBps"] / SHARED_PEAK_GBPS if d["shared_GBps"] else None
+    cands = {"hbm": d["dram_pct"] or 0, "shared": d["l1tex_pct"] or 0, "issue": d["issue_pct"] or 0}
+    best = max(cands, key=cands.get)
+    d["bound"] = best if cands[best] >= 50 else "latency"
+    ncu_kernels["kernels"][k] = d
     traffic["kernels"][name] = {"dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
                                 "ncu_time": f"{r[ix['gpu__time_duration.sum']]} {units[ix['gpu__time_duration.sum']]}"}
 (P / "dram_traffic.json").write_text(json.dumps(traffic, indent=1))
+(P / "ncu_kernels.json").write_text(json.dumps(ncu_kernels, indent=1))
 
 # kernel shares of the step from the launch list
 rows = list(csv.reader(open(G / "launches_bench.csv")))
