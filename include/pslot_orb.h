@@ -105,9 +105,10 @@ int pslot_stereo_match(pslot_orb *ctx_l, pslot_orb *ctx_r,
                        float bf, float max_d, float *u_right, float *depth);
 
 /* Page-locked (pinned) host memory for the images handed to pslot_batch_submit and for its output arrays: transfers
- * from pageable memory are staged by the driver and run at a fraction of the PCIe rate.  write_combined != 0 asks for
- * write-combined pages (faster for the device to read, slow for the CPU to read back: input buffers only). */
-int pslot_host_alloc(void **ptr, size_t bytes, int write_combined);
+ * from pageable memory are staged by the driver and run at a fraction of the PCIe rate.  mode 0: plain pinned pages;
+ * 1: write-combined pages (slow for the CPU to read back: input buffers only); 2: a transparent-huge-page backed mapping
+ * registered with the driver (fewer translation entries per transfer on virtualised hosts). */
+int pslot_host_alloc(void **ptr, size_t bytes, int mode);
 int pslot_host_free(void *ptr);
 
 /* static int ORBmatcher::DescriptorDistance(const cv::Mat&, const cv::Mat&) (ORBmatcher.cc:2704-2720):

@@ -250,10 +250,13 @@ def assign_grid(ext: OrbExtractor, kps_un, spec: GridSpec):
 class PinnedBuffer:
     """Page-locked host memory from pslot_host_alloc, viewed as a numpy array (freed with the object)."""
 
-    def __init__(self, shape, dtype=np.uint8, write_combined: bool = False):
+    MODES = {"default": 0, "wc": 1, "thp": 2}
+
+    def __init__(self, shape, dtype=np.uint8, write_combined: bool = False, mode: str = ""):
         self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
         p = C.c_void_p()
-        _check(lib().pslot_host_alloc(C.byref(p), self.nbytes, 1 if write_combined else 0))
+        m = self.MODES[mode] if mode else (1 if write_combined else 0)
+        _check(lib().pslot_host_alloc(C.byref(p), self.nbytes, m))
         self._p = p
         self.ptr = p.value or 0
         buf = (C.c_ubyte * self.nbytes).from_address(self.ptr)

@@ -8,6 +8,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <atomic>
@@ -456,18 +457,51 @@ int pslot_device_count(void)
 }
 
 // Page-locked host buffers for the batch API's inputs / outputs (so callers need no CUDA headers of their own).
-int pslot_host_alloc(void **ptr, size_t bytes, int write_combined)
+// mode 0: cudaHostAlloc default; 1: write-combined; 2: anonymous mapping advised to transparent huge pages, touched, then
+// registered with cudaHostRegister (fewer IOMMU / page-table entries per transfer on virtualised hosts).
+static std::mutex g_host_mu;
+static std::map<void *, size_t> g_host_mapped; // mode-2 buffers: base -> mapped length
+
+int pslot_host_alloc(void **ptr, size_t bytes, int mode)
 {
     if (!ptr) return fail(PSLOT_ERR_ARG, "ptr is null");
     *ptr = nullptr;
     if (bytes == 0) return PSLOT_OK;
-    CU(cudaHostAlloc(ptr, bytes, (write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault) | cudaHostAllocPortable));
+    if (mode == 2) {
+        const size_t huge = (size_t)2 << 20, len = align_up(bytes, huge);
+        void *p = mmap(nullptr, len + huge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p == MAP_FAILED) return fail(PSLOT_ERR_ARG, "mmap of %zu bytes failed", len);
+        void *base = (void *)align_up((size_t)p, huge);
+        madvise(base, len, MADV_HUGEPAGE);
+        memset(base, 0, len); // fault the pages in before they are pinned
+        cudaError_t e = cudaHostRegister(base, len, cudaHostRegisterPortable);
+        if (e != cudaSuccess) {
+            munmap(p, len + huge);
+            return fail(PSLOT_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e));
+        }
+        std::lock_guard<std::mutex> lock(g_host_mu);
+        g_host_mapped[base] = len;
+        *ptr = base; // the unaligned head (< 2 MB) stays mapped until process exit: munmap needs the original base
+        return PSLOT_OK;
+    }
+    CU(cudaHostAlloc(ptr, bytes, (mode == 1 ? cudaHostAllocWriteCombined : cudaHostAllocDefault) | cudaHostAllocPortable));
     return PSLOT_OK;
 }
 
 int pslot_host_free(void *ptr)
 {
-    if (ptr) CU(cudaFreeHost(ptr));
+    if (!ptr) return PSLOT_OK;
+    {
+        std::lock_guard<std::mutex> lock(g_host_mu);
+        auto it = g_host_mapped.find(ptr);
+        if (it != g_host_mapped.end()) {
+            cudaHostUnregister(ptr);
+            munmap(ptr, it->second);
+            g_host_mapped.erase(it);
+            return PSLOT_OK;
+        }
+    }
+    CU(cudaFreeHost(ptr));
     return PSLOT_OK;
 }
 

@@ -12,9 +12,10 @@ SHARED_PEAK_GBPS = SMS * 128 * SM_CLOCK_GHZ  # one 128-byte shared-memory wavefr
 KERNELS = {"fast": "k_fast_cells", "describe": "k_describe", "pyramid_level1": "k_resize_level", "quadtree": "k_quadtree",
            "stereo_match": "k_stereo_match", "ingest": "k_gray_repitch"}
 
-shutil.copy(G / "bench.json", P / f"{pre}_bench.json")
-shutil.copy(G / "bench_reference.json", P / f"{pre}_bench_reference.json")
-shutil.copy(G / "launches_bench.csv", P / f"{pre}_launches_bench.csv")
+for src, dst in (("bench.json", f"{pre}_bench.json"), ("bench_reference.json", f"{pre}_bench_reference.json"),
+                 ("launches_bench.csv", f"{pre}_launches_bench.csv")):
+    if (G / src).exists() and "--no-bench" not in sys.argv:
+        shutil.copy(G / src, P / dst)
 
 ncu_kernels = {"note": "ncu --set full --clock-control none, one launch of each kernel over a 125-pair sub-batch of the bench "
                "workload (tools/prof.sh); pct = % of peak sustained; shared_GBps = shared-memory wavefronts x 128 B / duration "
@@ -62,6 +63,8 @@ for name, k in KERNELS.items():
 (P / "dram_traffic.json").write_text(json.dumps(traffic, indent=1))
 (P / "ncu_kernels.json").write_text(json.dumps(ncu_kernels, indent=1))
 
+if not (G / "launches_bench.csv").exists() or "--no-bench" in sys.argv:
+    sys.exit(0)
 # kernel shares of the step from the launch list
 rows = list(csv.reader(open(G / "launches_bench.csv")))
 h = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
