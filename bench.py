@@ -370,6 +370,7 @@ class Workload:
         self.K = self.ctxs[0].K
         self.subs = sub_batches(P, Bsz) * self.passes  # one step = `passes` times through the sequence
         self.nsub = len(self.subs)
+        self.e2e_nsub = self.nsub  # sub-batches this rank uploads per end-to-end step (rate-proportional shards change it)
         nst = len(B.StereoBatch.STAGES)
         self.stage_acc = {False: [np.zeros(nst, np.float64), 0], True: [np.zeros(nst, np.float64), 0]}
 
@@ -377,7 +378,7 @@ class Workload:
         return self.P * self.passes
 
     def _submit(self, ctx, i, host, out):
-        lo, n = self.subs[i]
+        lo, n = self.subs[i % self.nsub]
         ib = self.img_bytes
         if host:
             ctx.submit_ptr(self.hL_ptr + lo * ib, self.hR_ptr + lo * ib, self.cfg["W"], ib, n, True, self.cfg["bf"], self.maxD, out)
@@ -387,7 +388,7 @@ class Workload:
 
     def one_step(self, host, collect):
         pending = [False] * self.nctx
-        for i in range(self.nsub):
+        for i in range(self.e2e_nsub if host else self.nsub):
             c = i % self.nctx
             ctx = self.ctxs[c]
             if pending[c]:
@@ -408,9 +409,9 @@ class Workload:
             self.dist.barrier()
             self.torch.cuda.synchronize()
 
-    def timed(self, host, steps, warmup, collect=False):
+    def timed(self, host, steps, warmup, collect=False, local=False):
         """`warmup` untimed steps, then exactly `steps` steps between CUDA events (fork/join over the batch streams);
-        -> (ms of the slowest rank, wall-clock window)."""
+        -> (ms of the slowest rank - or of this rank when local=True -, wall-clock window)."""
         from pointslot_b200.shard import max_over_ranks
         torch = self.torch
         for _ in range(warmup):
@@ -429,8 +430,19 @@ class Workload:
         stop.synchronize()
         t1 = time.time()
         self.barrier()
-        ms = max_over_ranks(start.elapsed_time(stop), self.dist, "cuda")  # a multi-GPU number is the slowest rank's device time
+        ms = start.elapsed_time(stop)
+        if not local:
+            ms = max_over_ranks(ms, self.dist, "cuda")  # a multi-GPU number is the slowest rank's device time
         return ms, (t0, t1)
+
+    def gather(self, x: float):
+        """-> the value of every rank, in rank order."""
+        if self.dist is None:
+            return [x]
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        g = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(g, t)
+        return [float(v.item()) for v in g]
 
     def profile_pass(self, reps=2):
         """Per-kernel durations for the roofline: the same submits on ONE stream, so that the CUDA events around each
@@ -485,6 +497,21 @@ class Workload:
         self.outs = []
         self._pin = []
         self.torch.cuda.empty_cache()
+
+
+def proportional_shards(total: int, rates):
+    """Split `total` sub-batches over the ranks in proportion to `rates` (largest-remainder rounding, every rank >= 1)."""
+    rates = [max(float(r), 1e-9) for r in rates]
+    s = sum(rates)
+    raw = [total * r / s for r in rates]
+    out = [max(1, int(x)) for x in raw]
+    while sum(out) < total:
+        i = max(range(len(out)), key=lambda k: raw[k] - out[k])
+        out[i] += 1
+    while sum(out) > total:
+        i = max((k for k in range(len(out)) if out[k] > 1), key=lambda k: out[k] - raw[k])
+        out[i] -= 1
+    return out
 
 
 def stage_bytes_per_pair(cfg, tot):
@@ -652,6 +679,27 @@ def run_ours(args, rank, world, local_rank):
     ms_dev, win1 = wl.timed(False, args.steps, args.warmup)
     tot = wl.profile_pass(reps=2)
     ms_e2e, win2 = wl.timed(True, args.steps, args.warmup, collect=not args.no_e2e_stages)
+    e2e_equal = None
+    shard_subs = [wl.nsub] * world
+    if world > 1 and not args.equal_shards:
+        # The PCIe paths of the GPUs of one box are not equally fast when every GPU uploads at once (tools/h2d_probe.py:
+        # GPUs 0-3 of these hosts share about 115 GB/s, GPUs 4-7 get about 55 GB/s each).  End to end the upload is the
+        # bottleneck, so the contiguous blocks of the batch are sized by what each GPU's path delivers instead of equally:
+        # first from the concurrent upload-only rates, then corrected once by the step times measured with that split.
+        # Same total number of pairs per step; no collective on the data path.
+        e2e_equal = {"value": None, "ms_per_step": ms_e2e / args.steps}
+        wl.barrier()
+        rates = wl.gather(wl.h2d_only() or 1.0)
+        wl.barrier()
+        total_subs = wl.nsub * world
+        shard_subs = proportional_shards(total_subs, rates)
+        wl.e2e_nsub = shard_subs[rank]
+        t_local, _ = wl.timed(True, 2, 1, local=True)
+        times = wl.gather(t_local)
+        shard_subs = proportional_shards(total_subs, [n / max(t, 1e-6) for n, t in zip(shard_subs, times)])
+        wl.e2e_nsub = shard_subs[rank]
+        ms_e2e, win3 = wl.timed(True, args.steps, 2)
+        win2 = (win2[0], win3[1])
     clocks = sampler.stop([win1, win2]) if rank == 0 else None
 
     # PCIe references for the e2e number: this rank's pinned images uploaded (1) with every rank uploading at the same time
@@ -674,6 +722,7 @@ def run_ours(args, rank, world, local_rank):
     det = None if args.no_determinism else determinism_check(cfg, rank, world, local_rank, dist)
 
     pairs_step = wl.pairs_per_step()
+    e2e_pairs_step_all = sum(shard_subs) * wl.Bsz          # pairs of one end-to-end step over all ranks
     h2d = 2 * pairs_step * wl.img_bytes
     d2h = wl.d2h_bytes_per_step()
     stage_acc, launches_per_submit, nsub, t_gen = wl.stage_acc, wl.launches_per_submit, wl.nsub, wl.t_gen
@@ -711,7 +760,9 @@ def run_ours(args, rank, world, local_rank):
         return
     total_pairs = pairs_step * world * args.steps
     value = total_pairs / (ms_dev * 1e-3)
-    e2e = total_pairs / (ms_e2e * 1e-3)
+    e2e = e2e_pairs_step_all * args.steps / (ms_e2e * 1e-3)
+    if e2e_equal is not None:
+        e2e_equal["value"] = pairs_step * world / (e2e_equal["ms_per_step"] * 1e-3)
 
     # ---- roofline --------------------------------------------------------------------------------------------------
     peak, peak_src = hbm_peak()
@@ -774,7 +825,7 @@ def run_ours(args, rank, world, local_rank):
             cpu["port"] = {"value": v_port, "sample": f"{done_p} pairs in {el_p:.1f} s, {cores} threads (oracle/orb_oracle.c)"}
 
     bytes_per_pair_h2d = 2 * wl.img_bytes
-    pcie = {"h2d_GBps_in_run": h2d / (ms_e2e / args.steps * 1e-3) / 1e9, "h2d_GBps_alone": h2d_alone,
+    pcie = {"h2d_GBps_in_run": 2 * e2e_pairs_step_all * wl.img_bytes / world / (ms_e2e / args.steps * 1e-3) / 1e9, "h2d_GBps_alone": h2d_alone,
             "h2d_GBps_all_ranks": {"per_rank_min": h2d_min, "aggregate": h2d_sum},
             "e2e_ceiling_pairs_per_s": (h2d_sum * 1e9 / bytes_per_pair_h2d) if h2d_sum else None,
             "e2e_frac_of_ceiling": (e2e * bytes_per_pair_h2d / (h2d_sum * 1e9)) if h2d_sum else None,
@@ -790,8 +841,13 @@ def run_ours(args, rank, world, local_rank):
                    "maxD": wl.maxD, "pinned_input": args.pin, "cpu_affinity": sorted(affinity) if affinity else None,
                    "l2": f"inputs larger than L2: {2 * P * wl.img_bytes / 1e6:.0f} MB of distinct images per pass vs 126 MB L2",
                    **counts, "synth_seconds": t_gen},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                "ms_per_step": ms_e2e / args.steps, "pcie": pcie,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * e2e_pairs_step_all * wl.img_bytes,
+                "d2h_bytes_per_step": d2h // max(nsub, 1) * sum(shard_subs),
+                "ms_per_step": ms_e2e / args.steps, "pairs_per_step": e2e_pairs_step_all,
+                "partition": {"kind": "equal contiguous blocks" if e2e_equal is None else
+                              "contiguous blocks sized by each GPU's measured upload rate (same total; DESIGN.md §6)",
+                              "pairs_per_step_by_rank": [n * wl.Bsz for n in shard_subs]},
+                "equal_shards": e2e_equal, "pcie": pcie,
                 "stage_ms_per_submit": {n: float(v) for n, v in zip(B.StereoBatch.STAGES, e2e_stage_ms)}},
         "gpu_launches": launches_per_submit * nsub * args.steps * world,
         "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clocks, "determinism": det,
@@ -815,6 +871,7 @@ def main():
     ap.add_argument("--pin", default="default", choices=["default", "wc", "thp"],
                     help="pinned input buffers: cudaHostAlloc default, write-combined, or huge-page backed + cudaHostRegister")
     ap.add_argument("--affinity", default="auto", choices=["auto", "none"], help="bind each rank to the CPUs next to its GPU before allocating")
+    ap.add_argument("--equal-shards", action="store_true", help="N > 1: keep equal shards in the end-to-end pass (no rate-proportional split)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary configurations")
     ap.add_argument("--no-determinism", action="store_true")

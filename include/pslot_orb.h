@@ -267,6 +267,24 @@ int pslot_batch_stats(pslot_batch *b, int64_t stats[4]);
 int pslot_batch_stereo_counters(pslot_batch *b, int64_t out[2]);
 
 /* ---------------------------------------------------------------------------------------------
+ * OpenCV's own ORB for the dense object features.
+ * Replaces `cv::ORB::create(1000, 1.2, 8, 19)->detectAndCompute(im, ObjMask, kp, descriptor)`
+ * (reference src/Frame.cc:2623-2627 OpencvORBDetector, run for both views by Frame::ExtractObjORB :2628-2665):
+ * HARRIS_SCORE, patchSize 31, WTA_K 2, firstLevel 0.  `mask` may be NULL; non-zero = keep (runByPixelsMask).
+ * Output: cv::KeyPoint-compatible records and 32-byte descriptors ordered by (octave, y, x) - cv::ORB's own order is
+ * whatever std::nth_element leaves and is not part of the contract; the SET and every field are OpenCV 4.13's, bit for
+ * bit (tests compare with cv2.ORB_create directly).  Returns PSLOT_ERR_CAPACITY with *n = needed when cap is too small.
+ * One context per calling thread (ExtractObjORB runs left and right on two threads).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct pslot_cvorb pslot_cvorb;
+int pslot_cvorb_create(pslot_cvorb **ctx, int nfeatures, float scale_factor, int nlevels, int edge_threshold,
+                       int fast_threshold, int device);
+void pslot_cvorb_destroy(pslot_cvorb *ctx);
+int pslot_cvorb_detect_and_compute(pslot_cvorb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch,
+                                   const uint8_t *mask, ptrdiff_t mask_pitch, pslot_keypoint *kps, uint8_t *desc32,
+                                   int cap, int *n);
+
+/* ---------------------------------------------------------------------------------------------
  * Stage accessors for the parity tests (not needed by a drop-in caller).
  * --------------------------------------------------------------------------------------------- */
 /* FAST candidates handed to the quadtree for `level` of the last pslot_orb_extract: window-relative

@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats", "pslot_batch_stereo_counters",
     "pslot_assign_grid", "pslot_grid_token", "pslot_features_in_area", "pslot_batch_assign_grid",
     "pslot_search_by_projection", "pslot_search_by_projection_last", "pslot_debug_projection_sweeps",
+    "pslot_cvorb_create", "pslot_cvorb_destroy", "pslot_cvorb_detect_and_compute",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
 ]
 
@@ -119,6 +120,11 @@ def lib():
     L.pslot_batch_set_profiling.argtypes = [vp, C.c_int]
     L.pslot_batch_stage_times.argtypes = [vp, vp]
     L.pslot_batch_stats.argtypes = [vp, vp]
+    L.pslot_cvorb_create.argtypes = [C.POINTER(vp), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.pslot_cvorb_destroy.argtypes = [vp]
+    L.pslot_cvorb_destroy.restype = None
+    L.pslot_cvorb_detect_and_compute.argtypes = [vp, vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_ssize_t, vp, vp, C.c_int,
+                                                 C.POINTER(C.c_int)]
     L.pslot_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]
     L.pslot_host_free.argtypes = [vp]
     L.pslot_batch_stereo_counters.argtypes = [vp, vp]
@@ -245,6 +251,41 @@ def assign_grid(ext: OrbExtractor, kps_un, spec: GridSpec):
     tot = C.c_int(0)
     _check(lib().pslot_assign_grid(ext._h, _p(kps_un), n, C.byref(spec), _p(cs), _p(idx), C.byref(tot)))
     return cs, idx[:tot.value].copy()
+
+
+class CvOrb:
+    """cv::ORB::create(nfeatures, scaleFactor, nlevels, edgeThreshold) over the C ABI (reference src/Frame.cc:2623-2627,
+    the dense object features): HARRIS_SCORE, patch 31, WTA_K 2; detect_and_compute -> keypoints ordered by
+    (octave, y, x) and their descriptors."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, edge_threshold=19, fast_threshold=20, device=0):
+        h = C.c_void_p()
+        _check(lib().pslot_cvorb_create(C.byref(h), nfeatures, scale_factor, nlevels, edge_threshold, fast_threshold, device))
+        self._h = h
+        self.cap = nfeatures + 64 * nlevels + 256
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pslot_cvorb_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def detect_and_compute(self, img: np.ndarray, mask=None):
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        cap = self.cap
+        while True:
+            kps = np.zeros(cap, KEYPOINT_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+            n = C.c_int(0)
+            rc = lib().pslot_cvorb_detect_and_compute(self._h, _p(img), img.shape[1], img.shape[0], img.strides[0],
+                                                      None if m is None else _p(m), 0 if m is None else m.strides[0],
+                                                      _p(kps), _p(desc), cap, C.byref(n))
+            if rc == -2 and n.value > cap:
+                cap = n.value
+                continue
+            _check(rc)
+            return kps[:n.value].copy(), desc[:n.value].copy()
 
 
 class PinnedBuffer:

@@ -8,7 +8,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libpslot_orb.so"
-SOURCES = ["ingest.cu", "pyramid.cu", "fast.cu", "quadtree.cu", "describe.cu", "stereo.cu", "grid.cu", "engine.cu"]
+SOURCES = ["ingest.cu", "pyramid.cu", "fast.cu", "quadtree.cu", "describe.cu", "stereo.cu", "grid.cu", "cvorb.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",  # parity rule 3: no fused multiply-add anywhere on the float islands
@@ -28,7 +28,7 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [CSRC / "pslot_internal.h", CSRC / "tma.cuh", PKG.parent / "include" / "pslot_orb.h",
+    deps = [CSRC / s for s in SOURCES] + [CSRC / "pslot_internal.h", CSRC / "tma.cuh", CSRC / "orb_common.cuh", PKG.parent / "include" / "pslot_orb.h",
                                           PKG.parent / "include" / "pslot_orb_pattern.inc"]
     return any(d.stat().st_mtime > t for d in deps)
 

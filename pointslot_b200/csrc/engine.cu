@@ -444,6 +444,127 @@ struct pslot_batch {
     }
 };
 
+
+// ---- cv::ORB (OpenCV's own extractor; reference Frame.cc:2623-2627) ---------------------------------------------------
+struct pslot_cvorb {
+    int nfeatures = 0, nlevels = 0, edge = 0, fast_th = 0, device = 0;
+    double scale_factor = 1.2;
+    cudaStream_t st = nullptr;
+    int W = 0, H = 0;
+    CvGeom g{};
+    CvBuffers b{};
+    int *h_err = nullptr;
+    size_t level_bytes = 0;
+    int cand_total = 0;
+    unsigned char *h_out = nullptr; // pinned staging of the outputs
+    size_t h_out_bytes = 0;
+
+    void release()
+    {
+        cudaFree(b.pyr); cudaFree(b.mask); cudaFree(b.score); cudaFree((void *)b.taps); cudaFree(b.cand); cudaFree(b.kept);
+        cudaFree(b.final_kp); cudaFree(b.kept_resp); cudaFree(b.final_resp); cudaFree(b.counters); cudaFree(b.hist);
+        cudaFree(b.out_kps); cudaFree(b.out_desc); cudaFree(b.out_count);
+        b = CvBuffers{};
+        W = H = 0;
+    }
+    ~pslot_cvorb()
+    {
+        release();
+        if (h_err) cudaFreeHost(h_err);
+        if (h_out) cudaFreeHost(h_out);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
+namespace {
+
+// INTER_LINEAR_EXACT taps of one axis (OpenCV resize.cpp, 8-bit fixed point): source index and fraction * 256
+void exact_taps(int n_dst, int n_src, int2 *out)
+{
+    const double scale = (double)n_src / (double)n_dst;
+    for (int d = 0; d < n_dst; ++d) {
+        double f = (d + 0.5) * scale - 0.5;
+        int s = (int)floor(f);
+        double fr = f - s;
+        if (s < 0) { s = 0; fr = 0.0; }
+        if (s >= n_src - 1) { s = n_src - 1; fr = 0.0; }
+        out[d].x = s;
+        out[d].y = (int)lrint(fr * 256.0);
+    }
+}
+
+int cvorb_configure(pslot_cvorb &c, int w, int h)
+{
+    if (w == c.W && h == c.H) return PSLOT_OK;
+    if (w > 4095 || h > 4095) return fail(PSLOT_ERR_SHAPE, "image %dx%d exceeds 4095 px", w, h);
+    CU(cudaStreamSynchronize(c.st));
+    c.release();
+    CvGeom &G = c.g;
+    memset(&G, 0, sizeof(G));
+    G.edge = c.edge; G.fast_th = c.fast_th;
+    { // getGaussianKernel(7, 2, CV_32F): exp(-x^2 / (2 sigma^2)) normalised in double, stored as float
+        double gk[7], sum = 0;
+        for (int i = 0; i < 7; ++i) { const double x = i - 3; gk[i] = exp(-0.125 * x * x); sum += gk[i]; }
+        for (int i = 0; i < 4; ++i) G.gk[i] = (float)(gk[i] / sum);
+    }
+    // feature quota per level (orb.cpp computeKeyPoints)
+    int quota[PSLOT_MAX_LEVELS];
+    {
+        const float factor = (float)(1.0 / c.scale_factor);
+        float nd = c.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)c.nlevels));
+        int sum = 0;
+        for (int l = 0; l < c.nlevels - 1; ++l) { quota[l] = cv_round((double)nd); sum += quota[l]; nd *= factor; }
+        quota[c.nlevels - 1] = std::max(c.nfeatures - sum, 0);
+    }
+    std::vector<int2> taps;
+    size_t off = 0;
+    int cand = 0, nl = 0;
+    for (int l = 0; l < c.nlevels; ++l) {
+        const float scale = (float)pow(c.scale_factor, (double)l);
+        const int lw = cv_round((double)((float)w / scale)), lh = cv_round((double)((float)h / scale));
+        if (lw < 2 * c.edge + 1 || lh < 2 * c.edge + 1) break; // nothing can pass the border filter from here on
+        CvLevel &L = G.lv[l];
+        L.w = lw; L.h = lh; L.pitch = (int)align_up((size_t)lw, 128);
+        L.off = off;
+        off += align_up((size_t)L.pitch * lh, 256);
+        L.quota = quota[l];
+        L.scale = scale;
+        L.cand_base = cand;
+        L.cand_cap = ((lw + 1) / 2) * ((lh + 1) / 2); // strict 3x3 maxima cannot be denser
+        cand += L.cand_cap;
+        L.kp_base = l * CV_SORT_CAP;
+        if (l > 0) {
+            L.tab_x = (int)taps.size(); taps.resize(taps.size() + lw);
+            exact_taps(lw, G.lv[l - 1].w, taps.data() + L.tab_x);
+            L.tab_y = (int)taps.size(); taps.resize(taps.size() + lh);
+            exact_taps(lh, G.lv[l - 1].h, taps.data() + L.tab_y);
+        }
+        nl = l + 1;
+    }
+    if (nl == 0) return fail(PSLOT_ERR_SHAPE, "image %dx%d is smaller than 2 * edgeThreshold + 1", w, h);
+    G.nlevels = nl;
+    c.level_bytes = off;
+    c.cand_total = cand;
+    CvBuffers &B = c.b;
+    CU(cudaMalloc(&B.pyr, off)); CU(cudaMalloc(&B.mask, off)); CU(cudaMalloc(&B.score, off));
+    CU(cudaMemset(B.pyr, 0, off)); CU(cudaMemset(B.mask, 0, off));
+    CU(cudaMemset(B.score, 0, off)); // the untested 3-px frame of every level must read as 0 in the maxima test
+    int2 *d_taps = nullptr;
+    CU(cudaMalloc(&d_taps, sizeof(int2) * std::max<size_t>(taps.size(), 1)));
+    if (!taps.empty()) CU(cudaMemcpy(d_taps, taps.data(), sizeof(int2) * taps.size(), cudaMemcpyHostToDevice));
+    B.taps = d_taps;
+    CU(cudaMalloc(&B.cand, 4 * (size_t)cand)); CU(cudaMalloc(&B.kept, 4 * (size_t)cand)); CU(cudaMalloc(&B.kept_resp, 4 * (size_t)cand));
+    const size_t kcap = (size_t)CV_SORT_CAP * PSLOT_MAX_LEVELS;
+    CU(cudaMalloc(&B.final_kp, 4 * kcap)); CU(cudaMalloc(&B.final_resp, 4 * kcap));
+    CU(cudaMalloc(&B.counters, sizeof(int) * CV_CNT_TOTAL)); CU(cudaMalloc(&B.hist, sizeof(int) * 256 * PSLOT_MAX_LEVELS));
+    CU(cudaMalloc(&B.out_kps, sizeof(pslot_keypoint) * kcap)); CU(cudaMalloc(&B.out_desc, 32 * kcap)); CU(cudaMalloc(&B.out_count, sizeof(int)));
+    CU(cudaHostGetDevicePointer((void **)&B.err, c.h_err, 0));
+    c.W = w; c.H = h;
+    return PSLOT_OK;
+}
+
+} // namespace
+
 extern "C" {
 
 const char *pslot_last_error(void) { return t_err; }
@@ -784,6 +905,76 @@ int pslot_debug_steer(int device, const float *angle_deg, int n, float *a, float
     if (e == cudaSuccess) e = cudaMemcpy(b, d + 2 * (size_t)n, 4 * (size_t)n, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "pslot_debug_steer: %s", cudaGetErrorString(e));
+    return PSLOT_OK;
+}
+
+
+// ---- cv::ORB ----------------------------------------------------------------------------------------------------------
+int pslot_cvorb_create(pslot_cvorb **ctx, int nfeatures, float scale_factor, int nlevels, int edge_threshold,
+                       int fast_threshold, int device)
+{
+    if (!ctx) return fail(PSLOT_ERR_ARG, "ctx is null");
+    *ctx = nullptr;
+    if (nfeatures < 1 || nfeatures > 30000) return fail(PSLOT_ERR_ARG, "nfeatures must be in [1,30000]");
+    if (nlevels < 1 || nlevels > PSLOT_MAX_LEVELS) return fail(PSLOT_ERR_ARG, "nlevels must be in [1,%d]", PSLOT_MAX_LEVELS);
+    if (!(scale_factor > 1.0f)) return fail(PSLOT_ERR_ARG, "scaleFactor must be > 1");
+    if (edge_threshold < 19) return fail(PSLOT_ERR_ARG, "edgeThreshold must be >= 19 (patch 31: 15 px pattern + 3 px blur inside the 21 px staged)");
+    if (fast_threshold < 1 || fast_threshold > 254) return fail(PSLOT_ERR_ARG, "fastThreshold must be in [1,254]");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PSLOT_ERR_CUDA, "CUDA device %d not available (%d visible)", device, ndev);
+    pslot_cvorb *c = new (std::nothrow) pslot_cvorb();
+    if (!c) return fail(PSLOT_ERR_ARG, "out of host memory");
+    c->nfeatures = nfeatures; c->nlevels = nlevels; c->edge = edge_threshold; c->fast_th = fast_threshold; c->device = device;
+    c->scale_factor = (double)scale_factor; // ORB::create takes a float, the member is a double
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&c->h_err, sizeof(int), cudaHostAllocMapped);
+    if (e != cudaSuccess) { delete c; return fail(PSLOT_ERR_CUDA, "pslot_cvorb_create: %s", cudaGetErrorString(e)); }
+    *c->h_err = 0;
+    *ctx = c;
+    return PSLOT_OK;
+}
+
+void pslot_cvorb_destroy(pslot_cvorb *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->st) cudaStreamSynchronize(ctx->st);
+    delete ctx;
+}
+
+int pslot_cvorb_detect_and_compute(pslot_cvorb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, const uint8_t *mask,
+                                   ptrdiff_t mask_pitch, pslot_keypoint *kps, uint8_t *desc32, int cap, int *n)
+{
+    if (!ctx || !n) return fail(PSLOT_ERR_ARG, "ctx / n is null");
+    *n = 0;
+    if (!img || w <= 0 || h <= 0) return PSLOT_OK; // empty image: no keypoints (orb.cpp: CV_Assert only on type)
+    if (pitch < w || (mask && mask_pitch < w)) return fail(PSLOT_ERR_ARG, "pitch < width");
+    pslot_cvorb &C = *ctx;
+    CU(cudaSetDevice(C.device));
+    if (int rc = cvorb_configure(C, w, h)) return rc;
+    const CvLevel &L0 = C.g.lv[0];
+    CU(cudaMemcpy2DAsync(C.b.pyr + L0.off, L0.pitch, img, pitch, w, h, cudaMemcpyHostToDevice, C.st));
+    if (mask) CU(cudaMemcpy2DAsync(C.b.mask + L0.off, L0.pitch, mask, mask_pitch, w, h, cudaMemcpyHostToDevice, C.st));
+    launch_cvorb(C.g, C.b, mask != nullptr, C.st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "cv::ORB launch failed: %s", cudaGetErrorString(e));
+    int count = 0;
+    CU(cudaMemcpyAsync(&count, C.b.out_count, sizeof(int), cudaMemcpyDeviceToHost, C.st));
+    CU(cudaStreamSynchronize(C.st));
+    if (*(volatile int *)C.h_err) {
+        *C.h_err = 0;
+        return fail(PSLOT_ERR_CAPACITY, "cv::ORB: a per-level candidate list or the keypoint sort overflowed");
+    }
+    *n = count;
+    if (count > cap) return fail(PSLOT_ERR_CAPACITY, "need room for %d keypoints, caller gave %d", count, cap);
+    if (count > 0) {
+        if (!kps || !desc32) return fail(PSLOT_ERR_ARG, "kps / desc32 is null");
+        CU(cudaMemcpyAsync(kps, C.b.out_kps, sizeof(pslot_keypoint) * (size_t)count, cudaMemcpyDeviceToHost, C.st));
+        CU(cudaMemcpyAsync(desc32, C.b.out_desc, 32 * (size_t)count, cudaMemcpyDeviceToHost, C.st));
+        CU(cudaStreamSynchronize(C.st));
+    }
     return PSLOT_OK;
 }
 

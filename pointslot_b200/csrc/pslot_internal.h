@@ -73,6 +73,7 @@ enum : int {
     PSLOT_FLAG_STEREO_NR = 2,     // more right keypoints than the stereo kernel staged (would have been truncated)
     PSLOT_FLAG_STEREO_OCTAVE = 4, // a right keypoint's octave lies outside [0, nlevels)
     PSLOT_FLAG_PYR_TILE = 8,      // a resize tile's source rectangle exceeds the staging buffer (level left unwritten)
+    PSLOT_FLAG_CVORB_CAP = 16,    // cv::ORB path: a candidate list or the on-chip sort of one level overflowed
 };
 
 struct StereoArgs {
@@ -125,6 +126,35 @@ template <typename K> inline void ensure_dyn_smem(K kernel, size_t bytes)
         h = bytes;
     }
 }
+
+// ---- cv::ORB (OpenCV's own extractor, cvorb.cu) -------------------------------------------------------------------
+struct CvLevel {
+    int w, h, pitch;         // cvRound(dim / scale), rows padded to 128 bytes
+    unsigned long long off;  // byte offset of the level inside the pyramid / mask / score buffers
+    int quota;               // nfeatures per level (orb.cpp computeKeyPoints)
+    float scale;             // (float)pow(scaleFactor, level)
+    int tab_x, tab_y;        // INTER_LINEAR_EXACT tap tables (source index, 8-bit fraction)
+    int cand_base, cand_cap; // segment of the candidate / kept arrays
+    int kp_base;             // segment of the final per-level keypoint lists (CV_SORT_CAP entries each)
+};
+struct CvGeom {
+    int nlevels, edge, fast_th;
+    float gk[4];             // getGaussianKernel(7, 2, CV_32F)[0..3]
+    CvLevel lv[PSLOT_MAX_LEVELS];
+};
+constexpr int CV_SORT_CAP = 4096; // keypoints one level can keep after retainBest(quota) incl. ties (on-chip sort)
+enum : int { CV_CNT_CAND = 0, CV_CNT_KEPT = PSLOT_MAX_LEVELS, CV_CNT_FINAL = 2 * PSLOT_MAX_LEVELS, CV_CNT_TOTAL = 3 * PSLOT_MAX_LEVELS };
+struct CvBuffers {
+    uint8_t *pyr, *mask, *score;
+    const int2 *taps;
+    uint32_t *cand, *kept, *final_kp;
+    float *kept_resp, *final_resp;
+    int *counters, *hist, *err;
+    pslot_keypoint *out_kps;
+    uint8_t *out_desc;
+    int *out_count;
+};
+int launch_cvorb(const CvGeom &g, const CvBuffers &b, bool has_mask, cudaStream_t st);
 
 typedef pslot_grid_spec GridSpec;
 size_t grid_smem_bytes(const GridSpec &s);

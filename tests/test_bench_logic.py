@@ -65,3 +65,13 @@ def test_cpu_arm_runs_reference_and_port():
         assert fn(L, R) > 100 and fn(L, R, True) > 100
         v, done, el = arm.pairs_per_sec([L], [R], 2, 0.5)
         assert done >= 1 and v > 0
+
+
+def test_proportional_shards():
+    """End-to-end shards sized by each GPU's upload rate: same total, every rank at least one sub-batch."""
+    a = bench.proportional_shards(1280, [23.3] * 4 + [36.0] * 4)
+    assert sum(a) == 1280 and a[:4] == [a[0]] * 4 and a[4] > a[0] and abs(a[4] / a[0] - 36.0 / 23.3) < 0.02
+    assert bench.proportional_shards(160, [55.5]) == [160]
+    b = bench.proportional_shards(10, [1, 1, 1000])
+    assert sum(b) == 10 and min(b) >= 1
+    assert bench.proportional_shards(8, [1.0] * 8) == [1] * 8

@@ -1,0 +1,113 @@
+"""GPU: pslot_cvorb_detect_and_compute (cvorb.cu) - OpenCV's own ORB for the dense object features, reference
+src/Frame.cc:2623-2627 `cv::ORB::create(1000, 1.2, 8, 19)->detectAndCompute(im, ObjMask, kp, descriptor)` - compared
+DIRECTLY with cv2.ORB_create (OpenCV 4.13 itself) and with the C oracle: the keypoint set and every field / descriptor
+bit, ordered by (octave, y, x) (cv::ORB's own order is what std::nth_element leaves)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+cv2 = pytest.importorskip("cv2")
+
+
+@pytest.fixture(scope="module")
+def B():
+    from pointslot_b200 import binding
+    return binding
+
+
+def _cv2_sorted(image, mask, *args):
+    kps, desc = cv2.ORB_create(*(args or (1000, 1.2, 8, 19))).detectAndCompute(image, mask)
+    rec = [(k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave) for k in kps]
+    order = sorted(range(len(rec)), key=lambda i: (rec[i][5], rec[i][1], rec[i][0]))
+    return [rec[i] for i in order], (desc[order] if len(rec) else np.zeros((0, 32), np.uint8))
+
+
+def _object_mask(H, W):
+    """Object masks as Frame::ExtractObjORB builds them (Frame.cc:2634-2645): 255 inside the instance regions."""
+    mask = np.zeros((H, W), np.uint8)
+    mask[H // 4:3 * H // 4, W // 6:W // 2] = 255
+    mask[H // 8:H // 2, 2 * W // 3:W - 40] = 255
+    return mask
+
+
+def _assert_equal(k, d, ref, rdesc, what):
+    assert len(k) == len(ref), f"{what}: {len(k)} vs {len(ref)} keypoints"
+    if not len(ref):
+        return
+    got = np.stack([k["x"], k["y"], k["size"], k["angle"], k["response"]], 1)
+    want = np.array([r[:5] for r in ref], np.float32)
+    for col, name in enumerate(("x", "y", "size", "angle", "response")):
+        assert np.array_equal(got[:, col].view(np.uint32), want[:, col].view(np.uint32)), f"{what}: {name}"
+    assert np.array_equal(k["octave"], np.array([r[5] for r in ref], np.int32)), f"{what}: octave"
+    assert np.all(k["class_id"] == -1)
+    assert np.array_equal(d, rdesc), f"{what}: descriptors"
+
+
+@pytest.mark.parametrize("shape,seed,masked", [((375, 1242), 3, False), ((375, 1242), 4, True), ((480, 752), 9, True),
+                                               ((480, 752), 10, False), ((222, 333), 5, False), ((120, 200), 6, False)])
+def test_cvorb_equals_cv2_orb(shape, seed, masked, B, oracle_mod):
+    from pointslot_b200.synth import synth_pair
+    H, W = shape
+    L, R = synth_pair(W, H, seed)
+    mask = _object_mask(H, W) if masked else None
+    orb = B.CvOrb(1000, 1.2, 8, 19)
+    for name, img in (("left", L), ("right", R)):  # the same context serves image after image
+        ref, rdesc = _cv2_sorted(img, mask)
+        k, d = orb.detect_and_compute(img, mask)
+        _assert_equal(k, d, ref, rdesc, f"{shape} {name} vs cv2")
+        ok, od = oracle_mod.cvorb_detect_and_compute(img, mask)
+        assert k.tobytes() == ok.tobytes() and np.array_equal(d, od)
+    assert len(k) > (100 if H > 150 else 20)
+
+
+def test_cvorb_natural_texture_with_mask(B):
+    """The reference's only image asset (via the golden fixture) with an object mask."""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "kitti_natural_2000.npz")
+    img = np.ascontiguousarray(g["left"])
+    mask = _object_mask(*img.shape)
+    orb = B.CvOrb()
+    for m in (mask, None):
+        ref, rdesc = _cv2_sorted(img, m)
+        k, d = orb.detect_and_compute(img, m)
+        _assert_equal(k, d, ref, rdesc, "natural texture")
+    assert len(k) >= 1000
+
+
+def test_cvorb_varied_content_and_parameters(B):
+    """Noise (every quota overflows), checkerboards (massive score ties, which retainBest keeps), posterised and flat
+    content at odd sizes; other feature counts / level counts / thresholds; pitched input."""
+    rng = np.random.default_rng(7)
+    cases = []
+    for (h, w) in ((97, 131), (150, 150), (241, 322), (64, 500)):
+        cases.append(rng.integers(0, 256, (h, w), dtype=np.uint8))
+        yy, xx = np.mgrid[0:h, 0:w]
+        cases.append((((xx // 9 + yy // 7) & 1) * 200 + 20).astype(np.uint8))
+        cases.append((np.clip(rng.normal(128, 60, (h, w)), 0, 255).astype(np.uint8) // 64 * 64).astype(np.uint8))
+    cases.append(np.full((120, 160), 77, np.uint8))
+    orb = B.CvOrb()
+    for img in cases:
+        ref, rdesc = _cv2_sorted(img, None)
+        k, d = orb.detect_and_compute(img)
+        _assert_equal(k, d, ref, rdesc, f"varied {img.shape}")
+    from pointslot_b200.synth import synth_pair
+    L, _ = synth_pair(640, 400, 12)
+    for args in ((500, 1.2, 8, 19), (2000, 1.2, 4, 19), (800, 1.5, 5, 31), (1000, 1.2, 8, 19, 0, 2, 0, 31, 10)):
+        ref, rdesc = _cv2_sorted(L, None, *args)
+        fast_th = args[8] if len(args) > 8 else 20
+        k, d = B.CvOrb(args[0], args[1], args[2], args[3], fast_th).detect_and_compute(L)
+        _assert_equal(k, d, ref, rdesc, f"params {args}")
+    big = np.zeros((400, 768), np.uint8); big[:, :640] = L   # a view with a row pitch
+    ref, rdesc = _cv2_sorted(L, None)
+    k, d = orb.detect_and_compute(big[:, :640])
+    _assert_equal(k, d, ref, rdesc, "pitched input")
+
+
+def test_cvorb_argument_errors(B):
+    with pytest.raises(B.PslotError):
+        B.CvOrb(1000, 1.0, 8, 19)
+    with pytest.raises(B.PslotError):
+        B.CvOrb(1000, 1.2, 8, 5)
+    orb = B.CvOrb()
+    k, d = orb.detect_and_compute(np.zeros((30, 30), np.uint8))  # smaller than 2 * edgeThreshold + 1: cv::ORB returns nothing
+    assert len(k) == 0
