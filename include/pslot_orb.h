@@ -284,6 +284,12 @@ int pslot_cvorb_detect_and_compute(pslot_cvorb *ctx, const uint8_t *img, int w, 
                                    const uint8_t *mask, ptrdiff_t mask_pitch, pslot_keypoint *kps, uint8_t *desc32,
                                    int cap, int *n);
 
+/* Stage accessor of the last pslot_cvorb_detect_and_compute, for the parity tests: what = 0 the pyramid level (w*h bytes,
+ * tightly packed), 1 its raw FAST score map (0 where not a corner), 2 the level's candidates after the maxima test, the mask
+ * and the border filter (packed u32 y:12 | x:12 | score:8, unordered), 3 the candidates retainBest(2*quota) kept (same
+ * packing, unordered; their Harris responses go to `aux`).  *w, *h = level size; *n = entries written. */
+int pslot_cvorb_debug(pslot_cvorb *ctx, int what, int level, void *out, float *aux, size_t cap_bytes, int *w, int *h, int *n);
+
 /* ---------------------------------------------------------------------------------------------
  * Stage accessors for the parity tests (not needed by a drop-in caller).
  * --------------------------------------------------------------------------------------------- */

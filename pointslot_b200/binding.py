@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats", "pslot_batch_stereo_counters",
     "pslot_assign_grid", "pslot_grid_token", "pslot_features_in_area", "pslot_batch_assign_grid",
     "pslot_search_by_projection", "pslot_search_by_projection_last", "pslot_debug_projection_sweeps",
-    "pslot_cvorb_create", "pslot_cvorb_destroy", "pslot_cvorb_detect_and_compute",
+    "pslot_cvorb_create", "pslot_cvorb_destroy", "pslot_cvorb_detect_and_compute", "pslot_cvorb_debug",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
 ]
 
@@ -125,6 +125,7 @@ def lib():
     L.pslot_cvorb_destroy.restype = None
     L.pslot_cvorb_detect_and_compute.argtypes = [vp, vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_ssize_t, vp, vp, C.c_int,
                                                  C.POINTER(C.c_int)]
+    L.pslot_cvorb_debug.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.pslot_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]
     L.pslot_host_free.argtypes = [vp]
     L.pslot_batch_stereo_counters.argtypes = [vp, vp]
@@ -286,6 +287,23 @@ class CvOrb:
                 continue
             _check(rc)
             return kps[:n.value].copy(), desc[:n.value].copy()
+
+
+def _cvorb_stage(self, what: int, level: int):
+    """Stage accessor (pslot_cvorb_debug): 0 pyramid level, 1 FAST score map -> (h, w) u8; 2 candidates, 3 kept after
+    retainBest(2 * quota) -> (x, y, score[, harris]) arrays."""
+    cap = 1 << 24
+    buf = np.zeros(cap, np.uint8); aux = np.zeros(cap // 4, np.float32)
+    w, h, n = C.c_int(0), C.c_int(0), C.c_int(0)
+    _check(lib().pslot_cvorb_debug(self._h, what, level, _p(buf), _p(aux), cap, C.byref(w), C.byref(h), C.byref(n)))
+    if what < 2:
+        return buf[:w.value * h.value].reshape(h.value, w.value).copy()
+    c = buf[:4 * n.value].view(np.uint32)
+    x, y, s = ((c >> 8) & 0xFFF).astype(np.int32), (c >> 20).astype(np.int32), (c & 0xFF).astype(np.int32)
+    return (x, y, s) if what == 2 else (x, y, s, aux[:n.value].copy())
+
+
+CvOrb.stage = _cvorb_stage
 
 
 class PinnedBuffer:

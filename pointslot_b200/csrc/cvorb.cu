@@ -68,15 +68,19 @@ k_cv_fast_score(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ py
         d[12] = v - p[-3];        d[13] = v - p[P - 3];     d[14] = v - p[2 * P - 2];  d[15] = v - p[3 * P - 1];
 #pragma unroll
         for (int k = 16; k < 25; ++k) d[k] = d[k - 16];
-        int best = -256;
+        // best = max_k max(min over arc k of (v - p), min over arc k of (p - v)); the second term is -(min_k max over arc k of
+        // (v - p)), kept as a min-of-max until the end.  (Written as max(best, max(mn, -mx)) inside the loop, ptxas 12.9 fuses
+        // the negated operand into VIMNMX3 and loses the sign: the kernel then scored max |v - p| - found by the parity test.)
+        int hi = -256, lo = 256;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             int mn = d[k], mx = d[k];
 #pragma unroll
             for (int j = 1; j < 9; ++j) { mn = min(mn, d[k + j]); mx = max(mx, d[k + j]); }
-            best = max(best, max(mn, -mx)); // min over the arc of (v - p) and of (p - v) = -max(v - p)
+            hi = max(hi, mn);
+            lo = min(lo, mx);
         }
-        const int R = best - 1;
+        const int R = max(hi, -lo) - 1;
         if (R >= t) out = (uint8_t)R;
     }
     score[L.off + (size_t)y * L.pitch + x] = out;

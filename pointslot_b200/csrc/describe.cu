@@ -130,19 +130,35 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // ---- horizontal blur pass: lane owns rows (lane, lane + 22), packed 16x2 --------------------------
+    // ---- horizontal blur pass: lane j owns patch rows 2j and 2j + 1 ------------------------------------
+    // Each row is read as 12 words and re-aligned by the warp-uniform byte offset, so that patch column c is byte c;
+    // blurred column c = sum_i k[i] * byte(c + i) is then 2-3 IDP.4A (u8 x u8 dot products on the FMA pipe) against
+    // the 7 coefficients placed at byte offset c & 3 of a 12-byte window - no byte extraction, no shifts per output.
+    // Sums stay <= 255 * 256 = 65280, so the two rows of a lane pack into one word = one (column, row pair) entry of
+    // the column-major h-pass array: one conflict-free 32-bit store per column.
     if (lane < 22) {
-        const int ra = lane, rb = min(lane + 22, PD - 1);
-        const uint8_t *pa = rawb + ra * RS + shift, *pb = rawb + rb * RS + shift;
-        uint16_t *ha = reinterpret_cast<uint16_t *>(S.hp) + ra, *hb = reinterpret_cast<uint16_t *>(S.hp) + rb;
-        uint32_t q[PD];
+        const int ra = 2 * lane, rb = min(2 * lane + 1, PD - 1);
+        const uint32_t *wa = S.raw + ra * RW, *wb = S.raw + rb * RW;
+        const int sh = 8 * shift;
+        uint32_t A[11], B[11];
+        {
+            uint32_t ta[NW], tb[NW];
 #pragma unroll
-        for (int c = 0; c < PD; ++c) q[c] = (uint32_t)pa[c] | ((uint32_t)pb[c] << 16);
+            for (int k = 0; k < NW; ++k) { ta[k] = wa[k]; tb[k] = wb[k]; }
+#pragma unroll
+            for (int k = 0; k < 11; ++k) { A[k] = __funnelshift_r(ta[k], ta[k + 1], sh); B[k] = __funnelshift_r(tb[k], tb[k + 1], sh); }
+        }
+        uint32_t *hw = S.hp + lane;
 #pragma unroll
         for (int c = 0; c < BD; ++c) {
-            const uint32_t h = 18u * (q[c] + q[c + 6]) + 34u * (q[c + 1] + q[c + 5]) + 48u * (q[c + 2] + q[c + 4]) + 56u * q[c + 3];
-            ha[c * CS] = (uint16_t)(h & 0xFFFFu); // lanes write consecutive rows of one column: conflict-free
-            hb[c * CS] = (uint16_t)(h >> 16);
+            constexpr uint32_t K0[4] = {0x38302212u, 0x30221200u, 0x22120000u, 0x12000000u};
+            constexpr uint32_t K1[4] = {0x00122230u, 0x12223038u, 0x22303830u, 0x30383022u};
+            constexpr uint32_t K2[4] = {0u, 0u, 0x00000012u, 0x00001222u};
+            const int k = c >> 2, s = c & 3;
+            uint32_t ha = __dp4a(A[k], K0[s], 0u), hb = __dp4a(B[k], K0[s], 0u);
+            ha = __dp4a(A[k + 1], K1[s], ha); hb = __dp4a(B[k + 1], K1[s], hb);
+            if (s >= 2) { ha = __dp4a(A[k + 2], K2[s], ha); hb = __dp4a(B[k + 2], K2[s], hb); }
+            hw[c * (CS / 2)] = hb * 65536u + ha;
         }
     }
     __syncwarp();
@@ -150,26 +166,31 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
     // ---- steered BRIEF with the vertical blur pass at the sampled positions (:107-147) ---------------
     float a, b;
     steer_coeffs(angle, a, b);
+    const uint32_t *hp = S.hp;
     auto sample = [&](float px, float py) -> int {
-        const int r = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
-        const int c = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-        // taps = patch rows (r + 18) .. (r + 24) of blurred column c + 18: 7 contiguous u16, fetched as 4 words
-        const int base = (c + BR) * CS + (r + BR);
-        const uint32_t *w = S.hp + (base >> 1);
+        // cvRound (round half to even) by the 1.5 * 2^23 trick: the sum's low mantissa bits are the integer, on the FMA
+        // pipe instead of the quarter-rate conversion unit; the bias folds into the constant below
+        const float MAGIC = 12582912.f;
+        const int rb = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)), MAGIC));
+        const int cb = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)), MAGIC));
+        // taps = patch rows (r + 18) .. (r + 24) of blurred column c + 18: 7 contiguous u16 inside 4 words
+        const int base = cb * CS + rb + (BR * CS + BR - 0x4B400000 * (CS + 1));
+        const uint32_t *w = hp + (base >> 1);
         const int sh = (base & 1) * 16;
-        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
-        const uint32_t t01 = __funnelshift_r(w0, w1, sh), t23 = __funnelshift_r(w1, w2, sh);
-        const uint32_t t45 = __funnelshift_r(w2, w3, sh), t6x = __funnelshift_r(w3, w3, sh);
-        const int v = 18 * (int)((t01 & 0xFFFFu) + (t6x & 0xFFFFu)) + 34 * (int)((t01 >> 16) + (t45 >> 16)) +
-                      48 * (int)((t23 & 0xFFFFu) + (t45 & 0xFFFFu)) + 56 * (int)(t23 >> 16);
-        return (v + 32768) >> 16;
+        // IDP.2A: two 16-bit taps x two 8-bit coefficients per instruction; an odd first row shifts the coefficient pairs
+        // by one tap (upper halves of the constants) instead of shifting the data
+        uint32_t v = __dp2a_lo(w[0], 0x12002212u >> sh, 32768u);  // even: (18, 34)   odd: (0, 18)
+        v = __dp2a_lo(w[1], 0x30223830u >> sh, v);                // even: (48, 56)   odd: (34, 48)
+        v = __dp2a_lo(w[2], 0x30382230u >> sh, v);                // even: (48, 34)   odd: (56, 48)
+        v = __dp2a_lo(w[3], 0x12220012u >> sh, v);                // even: (18, 0)    odd: (34, 18)
+        return (int)(v >> 16);
     };
     int val = 0;
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-        const uint32_t p = __ldg(&g_pat.w[t * 32 + lane]);
-        const int t0 = sample((float)(int8_t)(p & 0xFF), (float)(int8_t)((p >> 8) & 0xFF));
-        const int t1 = sample((float)(int8_t)((p >> 16) & 0xFF), (float)(int8_t)(p >> 24));
+        const float4 p = __ldg(&g_patf.v[t * 32 + lane]);
+        const int t0 = sample(p.x, p.y);
+        const int t1 = sample(p.z, p.w);
         val |= (t0 < t1) << t;
     }
     const size_t o = (size_t)slot * g.kp_cap_total + out_base + i;

@@ -953,6 +953,7 @@ int pslot_cvorb_detect_and_compute(pslot_cvorb *ctx, const uint8_t *img, int w, 
     if (pitch < w || (mask && mask_pitch < w)) return fail(PSLOT_ERR_ARG, "pitch < width");
     pslot_cvorb &C = *ctx;
     CU(cudaSetDevice(C.device));
+    if (w < 2 * C.edge + 1 || h < 2 * C.edge + 1) return PSLOT_OK; // nothing passes runByImageBorder: cv::ORB returns no keypoints
     if (int rc = cvorb_configure(C, w, h)) return rc;
     const CvLevel &L0 = C.g.lv[0];
     CU(cudaMemcpy2DAsync(C.b.pyr + L0.off, L0.pitch, img, pitch, w, h, cudaMemcpyHostToDevice, C.st));
@@ -975,6 +976,33 @@ int pslot_cvorb_detect_and_compute(pslot_cvorb *ctx, const uint8_t *img, int w, 
         CU(cudaMemcpyAsync(desc32, C.b.out_desc, 32 * (size_t)count, cudaMemcpyDeviceToHost, C.st));
         CU(cudaStreamSynchronize(C.st));
     }
+    return PSLOT_OK;
+}
+
+int pslot_cvorb_debug(pslot_cvorb *ctx, int what, int level, void *out, float *aux, size_t cap_bytes, int *w, int *h, int *n)
+{
+    if (!ctx || !out || !w || !h || !n) return fail(PSLOT_ERR_ARG, "null argument");
+    pslot_cvorb &C = *ctx;
+    if (C.W == 0) return fail(PSLOT_ERR_STATE, "no image processed yet");
+    if (level < 0 || level >= C.g.nlevels) return fail(PSLOT_ERR_ARG, "level out of range");
+    CU(cudaSetDevice(C.device));
+    CU(cudaStreamSynchronize(C.st));
+    const CvLevel &L = C.g.lv[level];
+    *w = L.w; *h = L.h; *n = 0;
+    if (what == 0 || what == 1) {
+        if (cap_bytes < (size_t)L.w * L.h) return fail(PSLOT_ERR_CAPACITY, "need %zu bytes", (size_t)L.w * L.h);
+        CU(cudaMemcpy2D(out, L.w, (what ? C.b.score : C.b.pyr) + L.off, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+        *n = L.w * L.h;
+        return PSLOT_OK;
+    }
+    if (what != 2 && what != 3) return fail(PSLOT_ERR_ARG, "what must be 0..3");
+    int counters[CV_CNT_TOTAL];
+    CU(cudaMemcpy(counters, C.b.counters, sizeof(counters), cudaMemcpyDeviceToHost));
+    const int cnt = std::min(counters[(what == 2 ? CV_CNT_CAND : CV_CNT_KEPT) + level], L.cand_cap);
+    if (cap_bytes < 4 * (size_t)cnt) return fail(PSLOT_ERR_CAPACITY, "need %zu bytes", 4 * (size_t)cnt);
+    CU(cudaMemcpy(out, (what == 2 ? C.b.cand : C.b.kept) + L.cand_base, 4 * (size_t)cnt, cudaMemcpyDeviceToHost));
+    if (what == 3 && aux) CU(cudaMemcpy(aux, C.b.kept_resp + L.cand_base, 4 * (size_t)cnt, cudaMemcpyDeviceToHost));
+    *n = cnt;
     return PSLOT_OK;
 }
 

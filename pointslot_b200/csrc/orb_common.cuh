@@ -25,6 +25,23 @@ constexpr PatTable make_pat()
     return t;
 }
 __device__ const PatTable g_pat = make_pat();
+// the same table as floats, [t][lane] = (x0, y0, x1, y1) of test 8*lane + t: one coalesced 16-byte load per lane and
+// test instead of four byte extractions and four int -> float conversions (the conversion unit is quarter rate)
+struct PatTableF { float4 v[256]; };
+constexpr PatTableF make_patf()
+{
+    constexpr int8_t raw[1024] = {
+#include "../../include/pslot_orb_pattern.inc"
+    };
+    PatTableF t{};
+    for (int i = 0; i < 256; ++i) {
+        const int tt = i >> 5, ln = i & 31;
+        const int8_t *p = raw + 4 * (8 * ln + tt);
+        t.v[i].x = (float)p[0]; t.v[i].y = (float)p[1]; t.v[i].z = (float)p[2]; t.v[i].w = (float)p[3];
+    }
+    return t;
+}
+__device__ const PatTableF g_patf = make_patf();
 // umax[v]: half-width of the radius-15 disc at row v (ORBextractor.cc:454-469)
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 

@@ -111,3 +111,32 @@ def test_cvorb_argument_errors(B):
     orb = B.CvOrb()
     k, d = orb.detect_and_compute(np.zeros((30, 30), np.uint8))  # smaller than 2 * edgeThreshold + 1: cv::ORB returns nothing
     assert len(k) == 0
+
+
+def test_cvorb_stages_against_the_oracle(B, oracle_mod):
+    """Stage accessors: every pyramid level equals the INTER_LINEAR_EXACT chain (cv2), and the per-level candidate set
+    (FAST score + whole-level maxima test + border filter) equals the oracle's cv::FAST on that level."""
+    from pointslot_b200.synth import synth_pair
+    L, _ = synth_pair(752, 480, 21)
+    orb = B.CvOrb(1200, 1.2, 8, 19)
+    orb.detect_and_compute(L)
+    prev = L
+    for l in range(8):
+        img = orb.stage(0, l)
+        if l:
+            sc = np.float32(1.2 ** l)
+            w, h = int(np.rint(np.float32(752) / sc)), int(np.rint(np.float32(480) / sc))
+            assert img.shape == (h, w)
+            assert np.array_equal(img, cv2.resize(prev, (w, h), interpolation=cv2.INTER_LINEAR_EXACT)), f"level {l}"
+        prev = img
+        fx, fy, fr = oracle_mod.fast9_16(img, 20)
+        h, w = img.shape
+        keep = (fx >= 19) & (fx < w - 19) & (fy >= 19) & (fy < h - 19)
+        want = set(zip(fx[keep].tolist(), fy[keep].tolist(), fr[keep].tolist()))
+        cx, cy, cs = orb.stage(2, l)
+        assert set(zip(cx.tolist(), cy.tolist(), cs.tolist())) == want and len(cx) == len(want), f"candidates of level {l}"
+        kx, ky, ks, kr = orb.stage(3, l)
+        # retainBest(2 * quota) by the FAST score keeps a score-threshold set, ties included
+        kept = set(zip(kx.tolist(), ky.tolist(), ks.tolist()))
+        assert kept <= want and all(s < ks.min() for (_, _, s) in want - kept)
+        assert np.all(np.isfinite(kr))
