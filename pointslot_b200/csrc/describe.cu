@@ -28,17 +28,20 @@ namespace {
 constexpr int DW = 4;           // warps (keypoints) per CTA
 constexpr int PR = 21;          // raw patch radius
 constexpr int PD = 2 * PR + 1;  // 43
-constexpr int RW = 13;          // raw row stride in words (52 bytes): odd -> conflict-free row-parallel access
+constexpr int RW = 17;          // raw row stride in words (68 bytes = 4 aligned 16-byte chunks + 1): odd -> conflict-free row-parallel access
 constexpr int RS = RW * 4;
-constexpr int NW = 12;          // aligned words fetched per patch row (covers 43 bytes at any alignment)
+constexpr int NW = 12;          // words of a patch row the blur reads (43 bytes at any byte offset inside the first word)
 constexpr int BR = 18;          // blurred support radius
 constexpr int BD = 2 * BR + 1;  // 37
 constexpr int CS = 44;          // h-pass column stride (u16): the h-pass is stored column-major, [blurred column][patch row]
 
 struct WarpSmem {
-    uint32_t raw[PD * RW];  // patch bytes, row stride 52; column c of the patch is byte c + shift
-    uint32_t hp[BD * CS / 2]; // horizontal pass as u16 [blurred column][patch row]: the 7 vertical taps of a sample are contiguous
+    // horizontal pass as u16 [blurred column][patch row]: the 7 vertical taps of a sample are contiguous (+2 words: the dense
+    // vertical pass reads one word past the last column); first, so that every column starts 8-byte aligned
+    uint32_t hp[BD * CS / 2 + 2];
+    uint32_t raw[PD * RW + 1]; // patch bytes, row stride 68; column c of the patch is byte c + shift (+1: size % 16 == 0)
 };
+static_assert(sizeof(WarpSmem) % 16 == 0 && (BD * CS / 2 + 2) % 2 == 0, "8-byte accesses into hp / raw");
 
 __global__ void k_debug_steer(const float *__restrict__ angle_deg, int n, float *__restrict__ a, float *__restrict__ b)
 {
@@ -82,23 +85,29 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
     const int x0 = kx - PR, y0 = ky - PR;
     int shift; // patch column c lives at byte c + shift of its shared row
     if (x0 >= 0 && y0 >= 0 && x0 + PD <= L.w && y0 + PD <= L.h) {
-        // rows are 4-byte aligned in global memory (pitch % 128 == 0): fetch 12 aligned words per row
-        shift = x0 & 3;
-        const uint8_t *src = img + (size_t)y0 * L.pitch + (x0 - shift);
-        // all 17 loads of a lane are issued before the first store (memory-level parallelism)
-        constexpr int NLD = (PD * NW + 31) / 32;
-        uint32_t v[NLD];
+        // rows are 128-byte aligned in global memory: fetch the four aligned 16-byte chunks that cover the 43 bytes at any
+        // alignment (6 wide loads per lane instead of 17 word loads, index arithmetic by shifts only)
+        shift = x0 & 15;
+        const int xa = x0 - shift;
+        const uint8_t *src = img + (size_t)y0 * L.pitch + xa;
+        constexpr int NLD = (PD * 4 + 31) / 32;
+        uint4 v[NLD];
 #pragma unroll
-        for (int k = 0; k < NLD; ++k) {
-            const int e = min(lane + 32 * k, PD * NW - 1);
-            const int r = e / NW, wc = e - r * NW;
-            v[k] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)r * L.pitch) + wc);
+        for (int k = 0; k < NLD; ++k) { // all loads of a lane are issued before the first store (memory-level parallelism)
+            const int e = lane + 32 * k;
+            const int r = min(e >> 2, PD - 1), c = e & 3;
+            // the last chunk may start beyond the row's pitch when the patch ends near the right edge: never needed then
+            const int cc = xa + 16 * c < L.pitch ? c : 0;
+            v[k] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * L.pitch) + cc);
         }
 #pragma unroll
         for (int k = 0; k < NLD; ++k) {
             const int e = lane + 32 * k;
-            const int r = e / NW, wc = e - r * NW;
-            if (e < PD * NW) S.raw[r * RW + wc] = v[k];
+            const int r = e >> 2, c = e & 3;
+            if (r < PD) {
+                uint32_t *d = S.raw + r * RW + 4 * c;
+                d[0] = v[k].x; d[1] = v[k].y; d[2] = v[k].z; d[3] = v[k].w;
+            }
         }
     } else { // within 21 px of the image edge: BORDER_REFLECT_101, byte by byte
         shift = 0;
@@ -111,6 +120,7 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
 
     // ---- IC_Angle: lane r owns disc row v = r - 15 -------------------------------------------------
     int m10 = 0, m01 = 0;
+#ifdef DESC_BYTE_MOMENTS
     if (lane < 31) {
         const int v = lane - PSLOT_HALF_PATCH;
         const int d = c_umax[v < 0 ? -v : v];
@@ -123,6 +133,35 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
         }
         m01 = v * sum;
     }
+#else
+    if (lane < 31) {
+        // The row's 32 bytes u = -16 .. 15 as eight re-aligned words; the disc row |u| <= d is a run of ones in a 32-bit
+        // mask (one bit per byte), spread to byte masks nibble by nibble with a carry-free multiply, so that the two row
+        // sums are IDP.4A dot products with the masked weights (u resp. 1) - no byte loads, no data-dependent loop.
+        const int v = lane - PSLOT_HALF_PATCH;
+        const int d = c_umax[v < 0 ? -v : v];
+        const int off = PR - 16 + shift; // byte offset of u = -16 inside the shared row
+        const uint32_t *w = S.raw + (PR + v) * RW + (off >> 2);
+        const int sh = 8 * (off & 3);
+        const uint32_t bits = ((2u << (2 * d)) - 1u) << (16 - d);
+        uint32_t t[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) t[k] = w[k];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t x = __funnelshift_r(t[k], t[k + 1], sh);
+            const uint32_t ones = (((bits >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u;
+            // u of the word's four bytes: 4k - 16 + {0, 1, 2, 3}, as signed bytes
+            const uint32_t ub = (uint32_t)((4 * k - 16) & 0xFF) * 0x01010101u + 0x03020100u;
+            sum = __dp4a(x, ones, sum);
+            int m;
+            asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(m) : "r"(x), "r"((ones * 0xFFu) & ub), "r"(m10));
+            m10 = m;
+        }
+        m01 = v * (int)sum;
+    }
+#endif
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         m10 += __shfl_xor_sync(0xffffffffu, m10, o);
@@ -138,8 +177,8 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
     // the column-major h-pass array: one conflict-free 32-bit store per column.
     if (lane < 22) {
         const int ra = 2 * lane, rb = min(2 * lane + 1, PD - 1);
-        const uint32_t *wa = S.raw + ra * RW, *wb = S.raw + rb * RW;
-        const int sh = 8 * shift;
+        const uint32_t *wa = S.raw + ra * RW + (shift >> 2), *wb = S.raw + rb * RW + (shift >> 2);
+        const int sh = 8 * (shift & 3);
         uint32_t A[11], B[11];
         {
             uint32_t ta[NW], tb[NW];
@@ -166,15 +205,55 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
     // ---- steered BRIEF with the vertical blur pass at the sampled positions (:107-147) ---------------
     float a, b;
     steer_coeffs(angle, a, b);
+    const float MAGIC = 12582912.f; // 1.5 * 2^23: (x + MAGIC)'s low mantissa bits are cvRound(x) (round half to even), on the
+                                    // FMA pipe instead of the quarter-rate conversion unit; the bias folds into a constant
+#ifndef DESC_GATHER_V
+    // ---- vertical blur pass, dense: the 37 x 37 blurred support as bytes, column-major (stride BS), over the raw patch
+    // (no longer needed).  A unit = 8 consecutive rows of one column: 14 taps rows = 7 words of the column-major h-pass,
+    // 4 IDP.2A per output with compile-time even / odd coefficient pairs; 185 units over the 32 lanes.  The 512 samples
+    // are then single byte loads: the random 4-word gathers of the fused variant cost 4.4 shared-memory wavefronts each
+    // (ncu), which made the shared-memory pipe the kernel's bound.
+    constexpr int BS = 40;
+    {
+        uint8_t *blur = rawb;
+        for (int u = lane; u < BD * 5; u += 32) {
+            const int c = (int)(((unsigned)u * 13108u) >> 16), t = u - 5 * c; // u / 5 for u < 185
+            const uint2 *src = reinterpret_cast<const uint2 *>(S.hp + c * (CS / 2) + 4 * t);
+            const uint2 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
+            const uint32_t w[8] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y};
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = i >> 1;
+                uint32_t v;
+                if ((i & 1) == 0) { // taps start on a word boundary: (18,34) (48,56) (48,34) (18,-)
+                    v = __dp2a_lo(w[k], 0x2212u, 32768u); v = __dp2a_lo(w[k + 1], 0x3830u, v);
+                    v = __dp2a_lo(w[k + 2], 0x2230u, v);  v = __dp2a_lo(w[k + 3], 0x0012u, v);
+                } else {            // one tap later: (-,18) (34,48) (56,48) (34,18)
+                    v = __dp2a_lo(w[k], 0x1200u, 32768u); v = __dp2a_lo(w[k + 1], 0x3022u, v);
+                    v = __dp2a_lo(w[k + 2], 0x3038u, v);  v = __dp2a_lo(w[k + 3], 0x1222u, v);
+                }
+                o[i] = v; // < 2^24: the blurred value is byte 2
+            }
+            uint2 out;
+            out.x = __byte_perm(__byte_perm(o[0], o[1], 0x0062), __byte_perm(o[2], o[3], 0x0062), 0x5410);
+            out.y = __byte_perm(__byte_perm(o[4], o[5], 0x0062), __byte_perm(o[6], o[7], 0x0062), 0x5410);
+            *reinterpret_cast<uint2 *>(blur + c * BS + 8 * t) = out;
+        }
+    }
+    __syncwarp();
+    auto sample = [&](float px, float py) -> int {
+        const int rb = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)), MAGIC));
+        const int cb = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)), MAGIC));
+        return rawb[cb * BS + rb + (int)((uint32_t)(BR * BS + BR) - 0x4B400000u * (uint32_t)(BS + 1))];
+    };
+#else
     const uint32_t *hp = S.hp;
     auto sample = [&](float px, float py) -> int {
-        // cvRound (round half to even) by the 1.5 * 2^23 trick: the sum's low mantissa bits are the integer, on the FMA
-        // pipe instead of the quarter-rate conversion unit; the bias folds into the constant below
-        const float MAGIC = 12582912.f;
         const int rb = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)), MAGIC));
         const int cb = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)), MAGIC));
         // taps = patch rows (r + 18) .. (r + 24) of blurred column c + 18: 7 contiguous u16 inside 4 words
-        const int base = cb * CS + rb + (BR * CS + BR - 0x4B400000 * (CS + 1));
+        const int base = cb * CS + rb + (int)((uint32_t)(BR * CS + BR) - 0x4B400000u * (uint32_t)(CS + 1));
         const uint32_t *w = hp + (base >> 1);
         const int sh = (base & 1) * 16;
         // IDP.2A: two 16-bit taps x two 8-bit coefficients per instruction; an odd first row shifts the coefficient pairs
@@ -185,6 +264,7 @@ k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
         v = __dp2a_lo(w[3], 0x12220012u >> sh, v);                // even: (18, 0)    odd: (34, 18)
         return (int)(v >> 16);
     };
+#endif
     int val = 0;
 #pragma unroll
     for (int t = 0; t < 8; ++t) {

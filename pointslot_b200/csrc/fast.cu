@@ -208,7 +208,7 @@ __device__ __forceinline__ void score_pass(const uint32_t *tile32, uint32_t *sco
 }
 
 __global__ void __launch_bounds__(FW * 32, FAST_MIN_BLOCKS)
-k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet maps,
+k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet maps, const uint4 *__restrict__ cells,
              int *__restrict__ cell_count, uint32_t *__restrict__ cell_cand, int warp_smem_bytes)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -216,48 +216,38 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
-    int cell = blockIdx.x * FW + warp;
+    const int cell = blockIdx.x * FW + warp;
     if (cell >= g.cells_per_slot) return;
-    // level of this cell: lane k looks at level k (cell_base ascending, [0] = 0), one ballot instead of a dependent scan
-    const int l = __popc(__ballot_sync(0xffffffffu, lane < g.nlevels && cell >= g.lv[min(lane, g.nlevels - 1)].cell_base)) - 1;
-    const LevelGeom &L = g.lv[l];
-    cell -= L.cell_base;
-    // cell / n_cols without the integer-division sequence: (cell + 0.5) / n lies at least 1 / (2 n) away from an
-    // integer, far beyond the 2-ulp error of the approximate division (quotients are below a few hundred)
-    const int ci = (int)__fdividef((float)cell + 0.5f, (float)L.n_cols), cj = cell - ci * L.n_cols;
-    int *count_out = cell_count + (size_t)slot * g.cells_per_slot + L.cell_base + cell;
-
-    // cell sub-image [ini, max) (:791-806); integers, so the reference's float compares are exact
-    const int iniY = PSLOT_MINB + ci * L.h_cell, iniX = PSLOT_MINB + cj * L.w_cell;
-    const int maxY = min(iniY + L.h_cell + 6, L.max_by), maxX = min(iniX + L.w_cell + 6, L.max_bx);
-    const int tw = maxX - iniX, th = maxY - iniY;
+    // the cell's record (make_fast_cells): sub-image [ini, ini + (tw, th)) (:791-806), level, TMA box, candidate slots
+    const uint4 rec = __ldg(cells + cell);
+    const int iniX = (int)(rec.x & 0xFFFFu), iniY = (int)(rec.x >> 16);
+    const int tw = (int)(rec.y & 0xFFu), th = (int)((rec.y >> 8) & 0xFFu);
+    const int l = (int)((rec.y >> 16) & 0xFFu), box_h = (int)(rec.y >> 24);
+    const int cand_stride = (int)(rec.w & 0xFFFFu), TS = (int)(rec.w >> 16), TSW = TS >> 2;
     const int iw = tw - 6, ih = th - 6; // pixels cv::FAST actually tests
-    if (iniY >= L.max_by - 3 || iniX >= L.max_bx - 3 || iw <= 0 || ih <= 0) {
-        if (lane == 0) *count_out = 0;
+    if (tw == 0) {
+        if (lane == 0) cell_count[(size_t)slot * g.cells_per_slot + cell] = 0;
         return;
     }
 
-    // per-warp shared memory: [ TMA tile (box_w x box_h) | score map (same stride, box_h + 1 rows) | group list ]
+    // per-warp shared memory: [ TMA tile (box_w x box_h) | score map (same box) | group list ]
     uint8_t *tile = smem + (size_t)warp * warp_smem_bytes;
-    const int TS = L.box_w, TSW = TS >> 2;
-    uint8_t *score = tile + ((TS * L.box_h + 127) & ~127);
-    uint16_t *glist = reinterpret_cast<uint16_t *>(score + ((TS * (L.box_h + 1) + 127) & ~127)); // <= 16 groups x ih rows
+    const int box_bytes = TS * box_h;
+    uint8_t *score = tile + ((box_bytes + 127) & ~127);
+    uint16_t *glist = reinterpret_cast<uint16_t *>(score + ((box_bytes + 127) & ~127)); // <= 16 groups x ih rows
     uint64_t *bar = &bars[warp];
 
-    // ---- stage the cell: one TMA box load (x, y, slot) -> dense shared tile, row stride = box width ----
+    // ---- stage the cell: one TMA box load (x, y, slot) -> dense shared tile, row stride = box width; a second box
+    // far outside the image clears the score map (the TMA unit zero-fills out-of-bounds elements: no store instructions)
     const int xa = (iniX - 1) & ~15;          // 16-byte aligned box origin
     const int sh0 = (iniX - 1) - xa;          // image column iniX-1+b lives at shared byte sh0 + b
     const int wsh = sh0 >> 2;
     if (lane == 0) {
         tma::mbar_init(bar, 1);
         tma::fence_barrier_init();
-        tma::mbar_arrive_expect_tx(bar, (uint32_t)(TS * L.box_h));
+        tma::mbar_arrive_expect_tx(bar, 2u * (uint32_t)box_bytes);
         tma::load_3d(tile, &maps.lv[l], bar, xa, iniY, slot);
-    }
-    {
-        uint4 *s16 = reinterpret_cast<uint4 *>(score);
-        const int n16 = ((th + 1) * TS) >> 4; // TS % 16 == 0
-        for (int i = lane; i < n16; i += 32) s16[i] = make_uint4(0, 0, 0, 0);
+        tma::load_3d(score, &maps.lv[l], bar, xa, 1 << 14, slot);
     }
     __syncwarp();
     tma::mbar_wait(bar, 0);
@@ -268,7 +258,7 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
     const int ntasks = ih << gshift;
     const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
     uint32_t *score32 = reinterpret_cast<uint32_t *>(score);
-    uint32_t *out = cell_cand + (size_t)slot * g.cand_per_slot + L.cand_base + (size_t)cell * L.cand_stride;
+    uint32_t *out = cell_cand + (size_t)slot * g.cand_per_slot + rec.z;
     const int ox = iniX + 3 - PSLOT_MINB, oy = iniY + 3 - PSLOT_MINB; // window-relative (:820-825)
 
     // Phase A = cv::FAST(cell, iniThFAST); phase B = cv::FAST(cell, minThFAST), only if A found nothing (:809-816).
@@ -360,7 +350,7 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
             const uint32_t vbase = pslot_pack(4 * gx + ox, y + oy, 0);
             for (uint32_t ff = f; ff; ff &= ff - 1) { // survivors of this group in x order
                 const int i = __ffs((int)ff) - 1;
-                if (pos < L.cand_stride) out[pos] = vbase + ((uint32_t)i << 8) + ((s4 >> (8 * i)) & 0xFFu);
+                if (pos < cand_stride) out[pos] = vbase + ((uint32_t)i << 8) + ((s4 >> (8 * i)) & 0xFFu);
                 ++pos;
             }
             total += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
@@ -368,23 +358,47 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
         n = total;
         if (n > 0) break;
     }
-    if (lane == 0) *count_out = min(n, L.cand_stride);
+    if (lane == 0) cell_count[(size_t)blockIdx.y * g.cells_per_slot + blockIdx.x * FW + (threadIdx.x >> 5)] = min(n, cand_stride);
 }
 
 } // namespace
 
-int launch_fast(const Geom &g, const TmapSet &maps, int *cell_count, uint32_t *cell_cand, int nslots, cudaStream_t st)
+// host side of the per-cell records: the cell grid of every level (ORBextractor.cc:784-806), integers throughout
+void make_fast_cells(const Geom &g, FastCell *out)
+{
+    for (int l = 0; l < g.nlevels; ++l) {
+        const LevelGeom &L = g.lv[l];
+        for (int ci = 0; ci < L.n_rows; ++ci)
+            for (int cj = 0; cj < L.n_cols; ++cj) {
+                const int cell = ci * L.n_cols + cj;
+                FastCell &c = out[L.cell_base + cell];
+                const int iniY = PSLOT_MINB + ci * L.h_cell, iniX = PSLOT_MINB + cj * L.w_cell;
+                const int maxY = iniY + L.h_cell + 6 < L.max_by ? iniY + L.h_cell + 6 : L.max_by;
+                const int maxX = iniX + L.w_cell + 6 < L.max_bx ? iniX + L.w_cell + 6 : L.max_bx;
+                const int tw = maxX - iniX, th = maxY - iniY;
+                const bool empty = iniY >= L.max_by - 3 || iniX >= L.max_bx - 3 || tw - 6 <= 0 || th - 6 <= 0; // :795-800
+                c.ini_x = (uint16_t)iniX; c.ini_y = (uint16_t)iniY;
+                c.tw = empty ? 0 : (uint8_t)tw; c.th = empty ? 0 : (uint8_t)th;
+                c.level = (uint8_t)l; c.box_h = (uint8_t)L.box_h;
+                c.cand_off = (uint32_t)(L.cand_base + cell * L.cand_stride);
+                c.cand_stride = (uint16_t)L.cand_stride;
+                c.box_w = (uint16_t)L.box_w;
+            }
+    }
+}
+
+int launch_fast(const Geom &g, const TmapSet &maps, const FastCell *cells, int *cell_count, uint32_t *cell_cand, int nslots,
+                cudaStream_t st)
 {
     int per_warp = 0;
     for (int l = 0; l < g.nlevels; ++l) {
         const int tile = (g.lv[l].box_w * g.lv[l].box_h + 127) & ~127;
-        const int score = (g.lv[l].box_w * (g.lv[l].box_h + 1) + 127) & ~127;
         const int list = (2 * 16 * (g.lv[l].box_h - 6) + 127) & ~127;
-        per_warp = per_warp > tile + score + list ? per_warp : tile + score + list;
+        per_warp = per_warp > 2 * tile + list ? per_warp : 2 * tile + list;
     }
     const size_t smem = (size_t)per_warp * FW;
     ensure_dyn_smem(k_fast_cells, smem);
     dim3 grid((g.cells_per_slot + FW - 1) / FW, nslots);
-    k_fast_cells<<<grid, FW * 32, smem, st>>>(g, maps, cell_count, cell_cand, per_warp);
+    k_fast_cells<<<grid, FW * 32, smem, st>>>(g, maps, reinterpret_cast<const uint4 *>(cells), cell_count, cell_cand, per_warp);
     return 1;
 }

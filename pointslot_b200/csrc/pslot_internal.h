@@ -97,7 +97,20 @@ int launch_pyramid(const Geom &g, const PyrPtrs &pyr, const ResizeTap *taps, int
 // that the device-side guard can never fire silently)
 bool pyramid_tiles_fit(const ResizeTap *xt, int dw, const ResizeTap *yt, int dh);
 struct TmapSet;
-int launch_fast(const Geom &g, const TmapSet &maps, int *cell_count, uint32_t *cell_cand, int nslots, cudaStream_t st);
+// One FAST cell of a slot, precomputed on the host (ORBextractor.cc:789-806): everything k_fast_cells needs, in one
+// 16-byte record that a warp fetches with a single load instead of deriving it from the level tables.
+struct FastCell {
+    uint16_t ini_x, ini_y;  // cell sub-image origin (level coordinates)
+    uint8_t tw, th;         // sub-image size incl. the 3-px FAST margin; tw == 0: the cell tests no pixel
+    uint8_t level, box_h;   // pyramid level; rows of the TMA box
+    uint32_t cand_off;      // first candidate slot of the cell inside a slot's candidate array
+    uint16_t cand_stride;   // candidate slots of the cell
+    uint16_t box_w;         // TMA box width = shared-memory row stride (bytes, multiple of 16)
+};
+static_assert(sizeof(FastCell) == 16, "FastCell is loaded as one uint4");
+void make_fast_cells(const Geom &g, FastCell *out); // out[g.cells_per_slot]
+int launch_fast(const Geom &g, const TmapSet &maps, const FastCell *cells, int *cell_count, uint32_t *cell_cand, int nslots,
+                cudaStream_t st);
 int launch_quadtree(const Geom &g, const int *cell_count, const uint32_t *cell_cand, int *cell_prefix,
                     uint32_t *qt_keys, uint16_t *qt_nodes, uint32_t *lkp, int *lkp_count, int *err_flag,
                     int nslots, cudaStream_t st, cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr,
