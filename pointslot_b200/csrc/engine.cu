@@ -111,6 +111,7 @@ struct Engine {
     Geom g{};
     PyrPtrs pyr{};
     TmapSet maps{};
+    PyrMaps pmaps{};
     bool has_pyramid = false;
 
     uint8_t *d_pyr = nullptr;
@@ -244,7 +245,7 @@ struct Engine {
 
     // One (x, y, slot) u8 tensor map per pyramid level; box = the FAST cell tile.  Out-of-image box
     // elements are zero-filled by the TMA unit.
-    int make_tensor_maps(int nslots)
+    int make_tensor_maps(int nslots, const std::vector<ResizeTap> &taps)
     {
         typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -270,6 +271,20 @@ struct Engine {
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(PSLOT_ERR_CUDA, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, (int)r);
+            // the pyramid kernel's views of the same level: destination tile, and source box of the next level's tiles
+            const cuuint32_t obox[3] = {PYR_TILE_W, PYR_TILE_H, 1};
+            r = encode(&pmaps.dst[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pyr.lv[l], dims, strides, obox, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS && l + 1 < g.nlevels) {
+                const LevelGeom &D = g.lv[l + 1];
+                pyramid_src_box(taps.data() + D.tab_x, D.w, taps.data() + D.tab_y, D.h, &pmaps.box_w[l], &pmaps.box_h[l]);
+                const cuuint32_t sbox[3] = {(cuuint32_t)pmaps.box_w[l], (cuuint32_t)pmaps.box_h[l], 1};
+                r = encode(&pmaps.src[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pyr.lv[l], dims, strides, sbox, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            }
+            if (r != CUDA_SUCCESS) return fail(PSLOT_ERR_CUDA, "cuTensorMapEncodeTiled (pyramid) failed for level %d (CUresult %d)", l, (int)r);
         }
         return PSLOT_OK;
     }
@@ -295,7 +310,7 @@ struct Engine {
         CU(cudaMalloc(&d_pyr, off + 256));
         CU(cudaMemset(d_pyr, 0, off + 256)); // row padding is read (never used) by 16-byte loads: keep it defined
         for (int l = 0; l < g.nlevels; ++l) pyr.lv[l] = d_pyr + lvoff[l];
-        rc = make_tensor_maps(nslots);
+        rc = make_tensor_maps(nslots, taps);
         if (rc) return rc;
         CU(cudaMalloc(&d_taps, sizeof(ResizeTap) * std::max<size_t>(taps.size(), 4)));
         if (!taps.empty()) CU(cudaMemcpy(d_taps, taps.data(), sizeof(ResizeTap) * taps.size(), cudaMemcpyHostToDevice));
@@ -338,7 +353,7 @@ struct Engine {
     {
         int n = 0;
         if (ev) cudaEventRecord(ev[1], st);
-        n += launch_pyramid(g, pyr, d_taps, nslots, d_err, st);
+        n += launch_pyramid(g, pyr, pmaps, d_taps, nslots, d_err, st);
         if (ev) cudaEventRecord(ev[2], st);
         n += launch_fast(g, maps, d_fast_cells, d_cell_count, d_cell_cand, nslots, st);
         if (ev) cudaEventRecord(ev[3], st);

@@ -7,133 +7,136 @@
 // Integer-only, hence bit-exact.  Levels are chained (each from the previous one, :1120), so a batch
 // needs nlevels-1 dependent launches; each launch covers every slot of the batch.
 //
-// Each CTA produces a 128 x 32 output tile.  The source rectangle it needs (about 156 x 40 bytes at
-// scale 1.2) is staged in shared memory with coalesced 16-byte loads, the 32 row taps are unpacked once
-// into shared memory, and every thread then produces 2 adjacent columns x 8 rows with a branch-free body: one
-// broadcast LDS.128 for the row tap, two word loads per source row, a PRMT + IDP.2A per row sum, two
-// multiply-highs per pixel.  (History: byte gathers, 4 LDS.U8 per pixel, pinned the shared-memory pipe at 90 %.)  A warp covers 32
-// consecutive output columns = ~38 consecutive source bytes, so every gather is one conflict-free
-// wavefront.  The finished tile goes back with 16-byte stores.
+// Each CTA produces a 128 x 32 output tile.  The source rectangle it needs (about 156 x 40 bytes at scale 1.2) arrives
+// by ONE TMA box load (cp.async.bulk.tensor.3d: no load / store instructions, no staging registers, out-of-image bytes
+// zero-filled), the 32 row taps are unpacked once into shared memory while the box is in flight, and every thread then
+// produces 2 adjacent columns x 8 rows with a branch-free body: one broadcast LDS.128 for the row tap, two word loads per
+// source row, a PRMT + IDP.2A per row sum, two multiply-highs per pixel.  A warp covers 64 consecutive output columns of
+// one row, so every gather is one conflict-free wavefront whatever the box width.  The finished tile goes back with one
+// TMA box store, which clips at the level's right / bottom edge.  (History: byte gathers, 4 LDS.U8 per pixel, pinned the
+// shared-memory pipe at 90 %; staging the source with 16-byte LDG + STS and writing the tile with 16-byte stores cost a
+// fifth of the instructions and two more CTA barriers - ncu: barrier 15 % + long_scoreboard 14 % of the stalls.)
 //
-// Bound: HBM/L2 streaming; algorithmic bytes per launch = S * (P_{l-1} + P_l).
+// Bound: instruction issue above the HBM/L2 stream; algorithmic bytes per launch = S * (P_{l-1} + P_l).
 #include "pslot_internal.h"
+#include "tma.cuh"
 
 namespace {
 
-constexpr int TW = 128;     // output tile width  (threads.x)
-constexpr int TH = 32;      // output tile height
-constexpr int TY = 2;       // threads.y (256 threads per CTA: 64 column pairs x 4 row groups in the compute phase)
-constexpr int SRC_W = 208;  // staged source row stride in bytes (13 x 16): 128 * 1.45 + 2 + 15 alignment
-constexpr int SRC_H = 52;   // staged source rows: 32 * 1.45 + 2 and slack
-constexpr int OUT_S = TW;   // output staging row stride
+constexpr int TW = PYR_TILE_W; // output tile width
+constexpr int TH = PYR_TILE_H; // output tile height
+constexpr int NT = 256;        // threads per CTA: 64 column pairs x 4 row groups
+constexpr int SRC_W = 208;     // largest source box row in bytes (13 x 16): 128 * 1.45 + 2 + 15 alignment
+constexpr int SRC_H = 52;      // largest source box height: 32 * 1.45 + 2 and slack
 
-__global__ void __launch_bounds__(TW *TY, 8)
-k_resize_level(const uint8_t *__restrict__ src, int spitch, unsigned long long sstride,
-               uint8_t *__restrict__ dst, int dw, int dh, int dpitch, unsigned long long dstride,
-               const ResizeTap *__restrict__ xt, const ResizeTap *__restrict__ yt, int *__restrict__ err_flag)
+__global__ void __launch_bounds__(NT, 8)
+k_resize_level(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap dst_map, int box_w, int box_h,
+               int dw, int dh, const ResizeTap *__restrict__ xt, const ResizeTap *__restrict__ yt)
 {
-    __shared__ __align__(16) uint8_t s_src[SRC_H * SRC_W];
-    __shared__ __align__(16) uint8_t s_out[TH * OUT_S];
+    __shared__ __align__(128) uint8_t s_src[SRC_H * SRC_W];
+    __shared__ __align__(128) uint8_t s_out[TH * TW];
     __shared__ int4 s_yt[TH]; // row tap: byte offsets of the two source rows in s_src, c0, c1
+    __shared__ __align__(8) uint64_t bar;
 
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TW + tx;
+    const int tid = threadIdx.x;
     const int dx0 = blockIdx.x * TW, dy0 = blockIdx.y * TH;
     const int dx1 = min(dx0 + TW, dw) - 1, dy1 = min(dy0 + TH, dh) - 1; // last output column / row of the tile
-    const uint8_t *s = src + (size_t)blockIdx.z * sstride;
+    const int slot = blockIdx.z;
 
-    // source rectangle: columns [xa, xb], rows [ya, yb]; xa rounded down to 16 bytes
-    const int xa = (int)xt[dx0].s0 & ~15, xb = (int)xt[dx1].s1;
-    const int ya = (int)yt[dy0].s0, yb = (int)yt[dy1].s1;
-    const int nvec = (xb - xa) / 16 + 1, nrow = yb - ya + 1;
-    if (nvec * 16 > SRC_W || nrow > SRC_H) { // cannot happen: make_geom rejects such ratios (pyramid_tiles_fit)
-        if (tid == 0 && err_flag) atomicOr(err_flag, PSLOT_FLAG_PYR_TILE);
-        return;
-    }
-    {
-        // 16 threads per staged row (nvec <= 13); rows are padded to a multiple of 128 bytes, so a 16-byte read
-        // never leaves the row
-        const int v = tid & 15;
-        if (v < nvec)
-            for (int r = tid >> 4; r < nrow; r += (TW * TY) >> 4)
-                *reinterpret_cast<uint4 *>(s_src + r * SRC_W + v * 16) =
-                    __ldg(reinterpret_cast<const uint4 *>(s + (size_t)(ya + r) * spitch + xa) + v);
+    // source rectangle: columns from xa (rounded down to 16 bytes), rows from ya; pyramid_src_box sized the box so that it
+    // covers the taps of every tile of this level
+    const int xa = (int)xt[dx0].s0 & ~15;
+    const int ya = (int)yt[dy0].s0;
+    if (tid == 0) {
+        tma::mbar_init(&bar, 1);
+        tma::fence_barrier_init();
+        tma::mbar_arrive_expect_tx(&bar, (uint32_t)(box_w * box_h));
+        tma::load_3d(s_src, &src_map, &bar, xa, ya, slot);
     }
     if (tid < TH) {
         const ResizeTap t = yt[min(dy0 + tid, dy1)];
         // row coefficients pre-shifted by 16 so that (c * (h >> 4)) >> 16 is one multiply-high (c <= 2048, h >> 4 < 2^15)
-        s_yt[tid] = make_int4(((int)t.s0 - ya) * SRC_W, ((int)t.s1 - ya) * SRC_W, (int)t.c0 << 16, (int)t.c1 << 16);
+        s_yt[tid] = make_int4(((int)t.s0 - ya) * box_w, ((int)t.s1 - ya) * box_w, (int)t.c0 << 16, (int)t.c1 << 16);
     }
-    __syncthreads();
-
-    {
-        // Each thread produces a PAIR of adjacent columns for TH / 4 rows.  The source bytes of a pair span at most 7
-        // bytes (ratio <= 1.45), i.e. two aligned words of the staged row: two word loads per source row replace four
-        // byte gathers, one PRMT per pixel picks its two tap bytes (selectors are row-invariant), and one IDP.2A
-        // (16-bit coefficients x two bytes) yields the row sum H.  The two column taps are adjacent bytes
-        // (s1 == s0 + 1) except at the clamped right border (s1 == s0), where the pair (s0, s0 + 1) with coefficients
-        // (c0 + c1, 0) gives the same sum.
-        const int cp = tid & 63, rg = tid >> 6; // column pair, row group
-        const ResizeTap ta = xt[min(dx0 + 2 * cp, dx1)], tb = xt[min(dx0 + 2 * cp + 1, dx1)];
-        const int oa = (int)ta.s0 - xa, ob = (int)tb.s0 - xa;
-        const int base = oa & ~3;
-        const uint32_t ja = (uint32_t)(oa - base), jb = (uint32_t)(ob - base); // 0..3 and ja..ja+2
-        const uint32_t sela = ja | ((ja + 1) << 4), selb = jb | ((jb + 1) << 4);
-        const uint32_t ca = ta.s1 != ta.s0 ? ((uint32_t)ta.c0 | ((uint32_t)ta.c1 << 16)) : (uint32_t)(ta.c0 + ta.c1);
-        const uint32_t cb = tb.s1 != tb.s0 ? ((uint32_t)tb.c0 | ((uint32_t)tb.c1 << 16)) : (uint32_t)(tb.c0 + tb.c1);
-        const uint8_t *p0 = s_src + base;
+    // Each thread produces a PAIR of adjacent columns for TH / 4 rows.  The source bytes of a pair span at most 7
+    // bytes (ratio <= 1.45), i.e. two aligned words of the staged row: two word loads per source row replace four
+    // byte gathers, one PRMT per pixel picks its two tap bytes (selectors are row-invariant), and one IDP.2A
+    // (16-bit coefficients x two bytes) yields the row sum H.  The two column taps are adjacent bytes
+    // (s1 == s0 + 1) except at the clamped right border (s1 == s0), where the pair (s0, s0 + 1) with coefficients
+    // (c0 + c1, 0) gives the same sum.
+    const int cp = tid & 63, rg = tid >> 6; // column pair, row group
+    const ResizeTap ta = xt[min(dx0 + 2 * cp, dx1)], tb = xt[min(dx0 + 2 * cp + 1, dx1)];
+    const int oa = (int)ta.s0 - xa, ob = (int)tb.s0 - xa;
+    const int base = oa & ~3;
+    const uint32_t ja = (uint32_t)(oa - base), jb = (uint32_t)(ob - base); // 0..3 and ja..ja+2
+    const uint32_t sela = ja | ((ja + 1) << 4), selb = jb | ((jb + 1) << 4);
+    const uint32_t ca = ta.s1 != ta.s0 ? ((uint32_t)ta.c0 | ((uint32_t)ta.c1 << 16)) : (uint32_t)(ta.c0 + ta.c1);
+    const uint32_t cb = tb.s1 != tb.s0 ? ((uint32_t)tb.c0 | ((uint32_t)tb.c1 << 16)) : (uint32_t)(tb.c0 + tb.c1);
+    const uint8_t *p0 = s_src + base;
+    __syncthreads();          // s_yt and the barrier initialisation are visible
+    tma::mbar_wait(&bar, 0);  // the source box has landed
 #pragma unroll
-        for (int k = 0; k < TH / 4; ++k) {
-            const int r = rg * (TH / 4) + k;
-            const int4 t = s_yt[r];
-            const uint32_t *w0 = reinterpret_cast<const uint32_t *>(p0 + t.x), *w1 = reinterpret_cast<const uint32_t *>(p0 + t.y);
-            const uint32_t u0 = w0[0], u1 = w0[1], l0 = w1[0], l1 = w1[1];
-            // H = c0 * src[s0] + c1 * src[s1] for both source rows and both columns
-            const uint32_t ha0 = __dp2a_lo(ca, __byte_perm(u0, u1, sela), 0u), ha1 = __dp2a_lo(ca, __byte_perm(l0, l1, sela), 0u);
-            const uint32_t hb0 = __dp2a_lo(cb, __byte_perm(u0, u1, selb), 0u), hb1 = __dp2a_lo(cb, __byte_perm(l0, l1, selb), 0u);
-            // in [0, 255] by construction (coefficients sum to 2048 per axis): no saturation needed
-            const uint32_t va = (__umulhi((uint32_t)t.z, ha0 >> 4) + __umulhi((uint32_t)t.w, ha1 >> 4) + 2u) >> 2;
-            const uint32_t vb = (__umulhi((uint32_t)t.z, hb0 >> 4) + __umulhi((uint32_t)t.w, hb1 >> 4) + 2u) >> 2;
-            *reinterpret_cast<uint16_t *>(s_out + r * OUT_S + 2 * cp) = (uint16_t)(va | (vb << 8));
-        }
+    for (int k = 0; k < TH / 4; ++k) {
+        const int r = rg * (TH / 4) + k;
+        const int4 t = s_yt[r];
+        const uint32_t *w0 = reinterpret_cast<const uint32_t *>(p0 + t.x), *w1 = reinterpret_cast<const uint32_t *>(p0 + t.y);
+        const uint32_t u0 = w0[0], u1 = w0[1], l0 = w1[0], l1 = w1[1];
+        // H = c0 * src[s0] + c1 * src[s1] for both source rows and both columns
+        const uint32_t ha0 = __dp2a_lo(ca, __byte_perm(u0, u1, sela), 0u), ha1 = __dp2a_lo(ca, __byte_perm(l0, l1, sela), 0u);
+        const uint32_t hb0 = __dp2a_lo(cb, __byte_perm(u0, u1, selb), 0u), hb1 = __dp2a_lo(cb, __byte_perm(l0, l1, selb), 0u);
+        // in [0, 255] by construction (coefficients sum to 2048 per axis): no saturation needed
+        const uint32_t va = (__umulhi((uint32_t)t.z, ha0 >> 4) + __umulhi((uint32_t)t.w, ha1 >> 4) + 2u) >> 2;
+        const uint32_t vb = (__umulhi((uint32_t)t.z, hb0 >> 4) + __umulhi((uint32_t)t.w, hb1 >> 4) + 2u) >> 2;
+        *reinterpret_cast<uint16_t *>(s_out + r * TW + 2 * cp) = (uint16_t)(va | (vb << 8));
     }
-    __syncthreads();
-
-    // write the tile: 8 x 16-byte stores per row (destination rows are 128-byte aligned and padded)
-    uint8_t *d = dst + (size_t)blockIdx.z * dstride;
-    const int rows = dy1 - dy0 + 1;
-    for (int i = tid; i < rows * (TW / 16); i += TW * TY) {
-        const int r = i >> 3, v = i & 7;
-        if (dx0 + v * 16 <= dx1)
-            *reinterpret_cast<uint4 *>(d + (size_t)(dy0 + r) * dpitch + dx0 + v * 16) =
-                *reinterpret_cast<const uint4 *>(s_out + r * OUT_S + v * 16);
+    tma::fence_proxy_async(); // this thread's tile bytes are visible to the TMA unit ...
+    __syncthreads();          // ... and so are everybody else's
+    if (tid == 0) {
+        tma::store_3d(&dst_map, s_out, dx0, dy0, slot); // clipped at the level's right / bottom edge
+        tma::store_commit();
+        tma::store_wait_read();
     }
 }
 
 } // namespace
 
-bool pyramid_tiles_fit(const ResizeTap *xt, int dw, const ResizeTap *yt, int dh)
+void pyramid_src_box(const ResizeTap *xt, int dw, const ResizeTap *yt, int dh, int *box_w, int *box_h)
 {
+    int bw = 16, bh = 1;
     for (int dx0 = 0; dx0 < dw; dx0 += TW) {
         const int dx1 = (dx0 + TW < dw ? dx0 + TW : dw) - 1;
         const int xa = (int)xt[dx0].s0 & ~15, xb = (int)xt[dx1].s1;
-        if (((xb - xa) / 16 + 1) * 16 > SRC_W) return false;
+        // the compute phase reads two aligned words from the first tap of a column pair: up to byte (s0 & ~3) + 7
+        const int need = (((int)xt[dx1].s0 - xa) & ~3) + 8;
+        const int w = ((xb - xa + 1 > need ? xb - xa + 1 : need) + 15) & ~15;
+        bw = w > bw ? w : bw;
     }
     for (int dy0 = 0; dy0 < dh; dy0 += TH) {
         const int dy1 = (dy0 + TH < dh ? dy0 + TH : dh) - 1;
-        if ((int)yt[dy1].s1 - (int)yt[dy0].s0 + 1 > SRC_H) return false;
+        const int h = (int)yt[dy1].s1 - (int)yt[dy0].s0 + 1;
+        bh = h > bh ? h : bh;
     }
-    return true;
+    *box_w = bw;
+    *box_h = bh;
 }
 
-int launch_pyramid(const Geom &g, const PyrPtrs &pyr, const ResizeTap *taps, int nslots, int *err_flag, cudaStream_t st)
+bool pyramid_tiles_fit(const ResizeTap *xt, int dw, const ResizeTap *yt, int dh)
 {
+    int bw, bh;
+    pyramid_src_box(xt, dw, yt, dh, &bw, &bh);
+    return bw <= SRC_W && bh <= SRC_H;
+}
+
+int launch_pyramid(const Geom &g, const PyrPtrs &pyr, const PyrMaps &maps, const ResizeTap *taps, int nslots, int *err_flag,
+                   cudaStream_t st)
+{
+    (void)pyr; (void)err_flag; // the tile fit is guaranteed on the host (pyramid_tiles_fit): no device-side guard left
     int launches = 0;
     for (int l = 1; l < g.nlevels; ++l) {
-        const LevelGeom &S = g.lv[l - 1], &D = g.lv[l];
-        dim3 block(TW, TY);
+        const LevelGeom &D = g.lv[l];
         dim3 grid((D.w + TW - 1) / TW, (D.h + TH - 1) / TH, nslots);
-        k_resize_level<<<grid, block, 0, st>>>(pyr.lv[l - 1], S.pitch, pyr.slot_stride[l - 1], pyr.lv[l], D.w, D.h,
-                                               D.pitch, pyr.slot_stride[l], taps + D.tab_x, taps + D.tab_y, err_flag);
+        k_resize_level<<<grid, NT, 0, st>>>(maps.src[l - 1], maps.dst[l], maps.box_w[l - 1], maps.box_h[l - 1], D.w, D.h,
+                                            taps + D.tab_x, taps + D.tab_y);
         ++launches;
     }
     return launches;

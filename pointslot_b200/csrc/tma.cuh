@@ -10,6 +10,12 @@
 struct TmapSet {
     CUtensorMap lv[PSLOT_MAX_LEVELS]; // level l as a (x, y, slot) u8 tensor, box = FAST cell tile
 };
+// pyramid: level l as the SOURCE of level l + 1 (box = the source rectangle of one 128 x 32 output tile) and as a
+// DESTINATION (box = one output tile)
+struct PyrMaps {
+    CUtensorMap src[PSLOT_MAX_LEVELS], dst[PSLOT_MAX_LEVELS];
+    int box_w[PSLOT_MAX_LEVELS], box_h[PSLOT_MAX_LEVELS]; // source box of level l (16-byte multiple x rows)
+};
 
 namespace tma {
 
@@ -57,6 +63,19 @@ __device__ __forceinline__ void load_3d(void *smem_dst, const CUtensorMap *map, 
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+
+// 3-D tiled store: dense shared tile -> box of the tensor map at (c0, c1, c2); elements outside the tensor are not written.
+// The generic-proxy writes that filled the tile must be ordered before it with fence_proxy_async().
+__device__ __forceinline__ void store_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the committed bulk stores have finished READING shared memory (the CTA may then exit or reuse the tile)
+__device__ __forceinline__ void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 __device__ __forceinline__ void prefetch_map(const CUtensorMap *map)
 {
