@@ -333,6 +333,51 @@ void Frame::ComputeObjStereoMatches() // (:2318-2503): the same routine on the o
                     mvuTempObjKeysRight, mvTempObjDepth);
 }
 
+void OpencvORBDetector(cv::Mat im, cv::Mat ObjMask, std::vector<cv::KeyPoint> &kp, cv::Mat &descriptor) // (:2623-2627)
+{
+    struct Ctx {
+        pslot_cvorb *h = nullptr;
+        ~Ctx() { pslot_cvorb_destroy(h); }
+    };
+    static thread_local Ctx ctx; // ExtractObjORB calls this from two threads at once: one device context each
+    if (!ctx.h && pslot_cvorb_create(&ctx.h, 1000, 1.2f, 8, 19, 20, 0) != PSLOT_OK) {
+        std::fprintf(stderr, "pslot OpencvORBDetector: %s\n", pslot_last_error());
+        std::abort();
+    }
+    int cap = 1000 + 64 * 8 + 256, n = 0;
+    for (;;) {
+        kp.resize((size_t)cap);
+        descriptor.create(cap, 32, CV_8U);
+        const int rc = pslot_cvorb_detect_and_compute(ctx.h, im.data, im.cols, im.rows, (ptrdiff_t)im.step,
+                                                      ObjMask.empty() ? nullptr : ObjMask.data, (ptrdiff_t)ObjMask.step,
+                                                      reinterpret_cast<pslot_keypoint *>(kp.data()), descriptor.data, cap, &n);
+        if (rc == PSLOT_ERR_CAPACITY && n > cap) { cap = n; continue; }
+        if (rc != PSLOT_OK) {
+            std::fprintf(stderr, "pslot OpencvORBDetector: %s\n", pslot_last_error());
+            std::abort();
+        }
+        break;
+    }
+    kp.resize((size_t)n);
+    cv::Mat d(n, 32, CV_8U);
+    for (int i = 0; i < n; ++i) std::memcpy(d.ptr(i), descriptor.ptr(i), 32);
+    descriptor = d;
+}
+
+void Frame::ExtractObjORB(cv::Mat left, cv::Mat right, cv::Mat LeftObjMask, cv::Mat RightObjMask) // (:2646-2663)
+{
+    std::vector<cv::KeyPoint> keypoints_1, keypoints_2;
+    cv::Mat descriptors_1, descriptors_2;
+    std::thread threadOpencvORBLeft(OpencvORBDetector, left, LeftObjMask, std::ref(keypoints_1), std::ref(descriptors_1));
+    std::thread threadOpencvORBRight(OpencvORBDetector, right, RightObjMask, std::ref(keypoints_2), std::ref(descriptors_2));
+    threadOpencvORBLeft.join();
+    threadOpencvORBRight.join();
+    mvTempObjKeys = keypoints_1;
+    mvTempObjKeysRight = keypoints_2;
+    mTempObjPointsDescriptors = descriptors_1.clone();
+    mTempObjPointsDescriptorsRight = descriptors_2.clone();
+}
+
 void Frame::UndistortObjKeyPoints() // (:2080-2110)
 {
     if (mDistCoef.empty() || mDistCoef.at<float>(0) == 0.0) {

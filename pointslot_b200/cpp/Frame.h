@@ -73,6 +73,12 @@ public:
     // Extract ORB on the image. 0 for left image and 1 for right image.
     void ExtractORB(int flag, const cv::Mat &im);
 
+    // Dense object features (reference Frame.cc:2628-2665): OpenCV's own ORB on both views, restricted to the object
+    // masks, on two threads; fills mvTempObjKeys / mvTempObjKeysRight and their descriptor matrices.  The reference
+    // builds the two masks from mMaskImg / mMaskImgRight (:2633-2645, PointSLOT's own instance-mask members) and
+    // calls this with them.
+    void ExtractObjORB(cv::Mat left, cv::Mat right, cv::Mat LeftObjMask, cv::Mat RightObjMask);
+
     // Stereo matching of the OBJECT feature set (reference Frame.cc:2318-2503: the same routine as
     // ComputeStereoMatches on mvTempObjKeys / mvTempObjKeysRight and their descriptors, reading the same two
     // pyramids); results in mvuTempObjKeysRight / mvTempObjDepth.
@@ -160,6 +166,12 @@ private:
     // Assign keypoints to the grid for speed up feature matching (reference Frame.cc:1636-1655); on the device
     void AssignFeaturesToGrid();
 };
+
+// cv::ORB::create(1000, 1.2, 8, 19)->detectAndCompute(im, ObjMask, kp, descriptor) (reference Frame.cc:2623-2627, same
+// name and signature): runs on the device through pslot_cvorb_detect_and_compute, one context per calling thread.
+// Keypoints come back ordered by (octave, y, x); cv::ORB's own order is unspecified (std::nth_element) and nothing
+// downstream depends on it.
+void OpencvORBDetector(cv::Mat im, cv::Mat ObjMask, std::vector<cv::KeyPoint> &kp, cv::Mat &descriptor);
 
 } // namespace ORB_SLAM2
 

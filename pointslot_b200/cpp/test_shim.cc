@@ -10,7 +10,8 @@
 //        N x int32 map-point index held by frame.mvpMapPoints[idx] afterwards (-1 = none);
 //        then the object-mode frame built in between on the same extractors from both images rolled down 7 rows
 //        (SLOTMode constructor + ObjectStageHook): int32 nObjL, nObjR, nObjL float mvuTempObjKeysRight, nObjL float
-//        mvTempObjDepth, int32 N of that frame
+//        mvTempObjDepth, int32 N of that frame; then Frame::ExtractObjORB on the first frame's images with two-rectangle
+//        object masks: int32 nObjL, nObjR, nObjL keypoints + nObjL*32 desc, nObjR keypoints + nObjR*32 desc
 // The second frame is built BEFORE the area / projection queries on the first one, so those queries only pass when the
 // first frame notices that the device grid is no longer its own (Frame::EnsureDeviceGrid).
 #include <algorithm>
@@ -154,6 +155,22 @@ int main(int argc, char **argv)
     std::fwrite(other.mvuTempObjKeysRight.data(), 4, nObjL, o);
     std::fwrite(other.mvTempObjDepth.data(), 4, nObjL, o);
     std::fwrite(&other.N, 4, 1, o);
+    // dense object features (Frame::ExtractObjORB -> OpencvORBDetector, reference Frame.cc:2623-2665): both views on two
+    // threads, object masks = two rectangles
+    cv::Mat maskL(H, W, CV_8UC1), maskR(H, W, CV_8UC1);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const bool in = (y >= H / 4 && y < 3 * H / 4 && x >= W / 6 && x < W / 2) || (y >= H / 8 && y < H / 2 && x >= 2 * W / 3 && x < W - 40);
+            maskL.ptr(y)[x] = in ? 255 : 0;
+            maskR.ptr(y)[x] = in ? 255 : 0;
+        }
+    frame.ExtractObjORB(imL, imR, maskL, maskR);
+    const int nOL = (int)frame.mvTempObjKeys.size(), nOR = (int)frame.mvTempObjKeysRight.size();
+    std::fwrite(&nOL, 4, 1, o); std::fwrite(&nOR, 4, 1, o);
+    std::fwrite(frame.mvTempObjKeys.data(), sizeof(cv::KeyPoint), nOL, o);
+    for (int i = 0; i < nOL; ++i) std::fwrite(frame.mTempObjPointsDescriptors.ptr(i), 1, 32, o);
+    std::fwrite(frame.mvTempObjKeysRight.data(), sizeof(cv::KeyPoint), nOR, o);
+    for (int i = 0; i < nOR; ++i) std::fwrite(frame.mTempObjPointsDescriptorsRight.ptr(i), 1, 32, o);
     std::fclose(o);
     std::printf("shim ok: N=%d Nr=%d matched=%d mb=%g projection matches=%d\n", N, Nr,
                 (int)std::count_if(frame.mvuRight.begin(), frame.mvuRight.end(), [](float v) { return v >= 0; }), frame.mb, nmatches);

@@ -57,6 +57,11 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle_mod):
     obj_ur = np.frombuffer(raw, np.float32, n_obj_l, o); o += 4 * n_obj_l
     obj_dp = np.frombuffer(raw, np.float32, n_obj_l, o); o += 4 * n_obj_l
     (n_other,) = struct.unpack_from("<i", raw, o); o += 4
+    n_ol, n_or = struct.unpack_from("<2i", raw, o); o += 8
+    okl = np.frombuffer(raw, B.KEYPOINT_DTYPE, n_ol, o); o += 28 * n_ol
+    odl = np.frombuffer(raw, np.uint8, 32 * n_ol, o).reshape(n_ol, 32); o += 32 * n_ol
+    okr = np.frombuffer(raw, B.KEYPOINT_DTYPE, n_or, o); o += 28 * n_or
+    odr = np.frombuffer(raw, np.uint8, 32 * n_or, o).reshape(n_or, 32); o += 32 * n_or
     assert o == len(raw)
 
     O = oracle_mod
@@ -100,3 +105,12 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle_mod):
     our2, odp2 = O.stereo_match(oL, oR, k2L[::3], d2L[::3], k2R[::2], d2R[::2], bf, maxD)
     assert np.array_equal(obj_ur >= 0, our2 >= 0) and np.all(np.abs(obj_ur - our2) <= 1e-3)
     assert np.allclose(obj_dp, odp2, rtol=1e-5, atol=0) and (our2 >= 0).sum() > 10
+
+    # Frame::ExtractObjORB -> OpencvORBDetector (Frame.cc:2623-2665): cv::ORB::create(1000, 1.2, 8, 19) on both views inside
+    # the object masks, through the drop-in function
+    mask = np.zeros((H, W), np.uint8)
+    mask[H // 4:3 * H // 4, W // 6:W // 2] = 255
+    mask[H // 8:H // 2, 2 * W // 3:W - 40] = 255
+    for img, k, d in ((L, okl, odl), (R, okr, odr)):
+        rk, rd = O.cvorb_detect_and_compute(img, mask)
+        assert k.tobytes() == rk.tobytes() and np.array_equal(d, rd) and len(k) > 100
