@@ -20,7 +20,7 @@ for src, dst in (("bench.json", f"{pre}_bench.json"), ("bench_reference.json", f
 ncu_kernels = {"note": "ncu --set full --clock-control none, one launch of each kernel over a 125-pair sub-batch of the bench "
                "workload (tools/prof.sh); pct = % of peak sustained; shared_GBps = shared-memory wavefronts x 128 B / duration "
                "against 148 SM x 128 B/clk x 1.965 GHz; bound = the busiest of {dram -> hbm, l1tex/shared -> shared, issue slots -> "
-               "issue}, or latency when none reaches 50 %", "kernels": {}}
+               "issue, integer ALU pipe -> alu}, or latency when none reaches 50 %", "kernels": {}}
 traffic = {"batch": 125, "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full "
            "(tools/prof.sh), sub-batch of 125 pairs = 250 images", "kernels": {}}
 for name, k in KERNELS.items():
@@ -47,6 +47,9 @@ for name, k in KERNELS.items():
          "lts_pct": pct("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
          "issue_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
          "sm_pct": pct("sm__throughput.avg.pct_of_peak_sustained_elapsed"),
+         "alu_pipe_pct": pct("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+         "fma_pipe_pct": pct("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+         "lsu_data_pipe_pct": pct("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
          "occupancy_pct": pct("sm__warps_active.avg.pct_of_peak_sustained_active"),
          "registers": pct("launch__registers_per_thread"),
          "duration_us": t_us, "capture_pairs": 125,
@@ -54,7 +57,7 @@ for name, k in KERNELS.items():
          "shared_wavefronts": wf, "shared_bank_conflicts": pct("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
          "shared_GBps": wf * 128 / (t_us * 1e-6) / 1e9 if t_us else None, "shared_peak_GBps": SHARED_PEAK_GBPS}
     d["shared_frac"] = d["shared_GBps"] / SHARED_PEAK_GBPS if d["shared_GBps"] else None
-    cands = {"hbm": d["dram_pct"] or 0, "shared": d["l1tex_pct"] or 0, "issue": d["issue_pct"] or 0}
+    cands = {"hbm": d["dram_pct"] or 0, "shared": d["l1tex_pct"] or 0, "issue": d["issue_pct"] or 0, "alu": d["alu_pipe_pct"] or 0}
     best = max(cands, key=cands.get)
     d["bound"] = best if cands[best] >= 50 else "latency"
     ncu_kernels["kernels"][k] = d
