@@ -28,12 +28,15 @@
 namespace {
 
 // ---- pyramid --------------------------------------------------------------------------------------------------------------
-__global__ void k_cv_resize_exact(const uint8_t *__restrict__ src, int sw, int sh, int spitch, uint8_t *__restrict__ dst,
-                                  int dw, int dh, int dpitch, const int2 *__restrict__ xt, const int2 *__restrict__ yt,
-                                  int tozero)
+// blockIdx.z = 0: the image, 1: the object mask (same taps; thresholded)
+__global__ void k_cv_resize_exact(const uint8_t *__restrict__ src_img, const uint8_t *__restrict__ src_mask, int sw, int sh,
+                                  int spitch, uint8_t *__restrict__ dst_img, uint8_t *__restrict__ dst_mask, int dw, int dh,
+                                  int dpitch, const int2 *__restrict__ xt, const int2 *__restrict__ yt)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dw || y >= dh) return;
+    const bool is_mask = blockIdx.z != 0;
+    const uint8_t *src = is_mask ? src_mask : src_img;
     const int2 tx = xt[x], ty = yt[y];
     const int xa = tx.x, xb = min(xa + 1, sw - 1), ax = tx.y;
     const int ya = ty.x, yb = min(ya + 1, sh - 1), ay = ty.y;
@@ -41,8 +44,8 @@ __global__ void k_cv_resize_exact(const uint8_t *__restrict__ src, int sw, int s
     const int H0 = (int)r0[xa] * (256 - ax) + (int)r0[xb] * ax;
     const int H1 = (int)r1[xa] * (256 - ax) + (int)r1[xb] * ax;
     int v = (H0 * (256 - ay) + H1 * ay + (1 << 15)) >> 16;
-    if (tozero) v = v > 254 ? v : 0; // cv::threshold(mask, mask, 254, 0, THRESH_TOZERO)
-    dst[(size_t)y * dpitch + x] = (uint8_t)v;
+    if (is_mask) v = v > 254 ? v : 0; // cv::threshold(mask, mask, 254, 0, THRESH_TOZERO)
+    (is_mask ? dst_mask : dst_img)[(size_t)y * dpitch + x] = (uint8_t)v;
 }
 
 // ---- FAST score map ---------------------------------------------------------------------------------------------------------
@@ -382,15 +385,10 @@ int launch_cvorb(const CvGeom &g, const CvBuffers &b, bool has_mask, cudaStream_
     int n = 0;
     for (int l = 1; l < g.nlevels; ++l) { // each level from the previous one (orb.cpp: resize(prevImg, currImg, INTER_LINEAR_EXACT))
         const CvLevel &S = g.lv[l - 1], &D = g.lv[l];
-        dim3 blk(32, 8), grd((D.w + 31) / 32, (D.h + 7) / 8);
-        k_cv_resize_exact<<<grd, blk, 0, st>>>(b.pyr + S.off, S.w, S.h, S.pitch, b.pyr + D.off, D.w, D.h, D.pitch,
-                                               b.taps + D.tab_x, b.taps + D.tab_y, 0);
+        dim3 blk(32, 8), grd((D.w + 31) / 32, (D.h + 7) / 8, has_mask ? 2 : 1);
+        k_cv_resize_exact<<<grd, blk, 0, st>>>(b.pyr + S.off, b.mask + S.off, S.w, S.h, S.pitch, b.pyr + D.off, b.mask + D.off,
+                                               D.w, D.h, D.pitch, b.taps + D.tab_x, b.taps + D.tab_y);
         ++n;
-        if (has_mask) {
-            k_cv_resize_exact<<<grd, blk, 0, st>>>(b.mask + S.off, S.w, S.h, S.pitch, b.mask + D.off, D.w, D.h, D.pitch,
-                                                   b.taps + D.tab_x, b.taps + D.tab_y, 1);
-            ++n;
-        }
     }
     cudaMemsetAsync(b.counters, 0, sizeof(int) * CV_CNT_TOTAL, st);
     cudaMemsetAsync(b.hist, 0, sizeof(int) * 256 * PSLOT_MAX_LEVELS, st);

@@ -983,20 +983,38 @@ int pslot_cvorb_detect_and_compute(pslot_cvorb *ctx, const uint8_t *img, int w, 
     launch_cvorb(C.g, C.b, mask != nullptr, C.st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "cv::ORB launch failed: %s", cudaGetErrorString(e));
-    int count = 0;
-    CU(cudaMemcpyAsync(&count, C.b.out_count, sizeof(int), cudaMemcpyDeviceToHost, C.st));
+    // one round trip: the count and the (almost always sufficient) first `guess` records travel together into pinned memory
+    const int guess = C.nfeatures + 64;
+    const size_t need = 16 + (size_t)guess * (sizeof(pslot_keypoint) + 32);
+    if (C.h_out_bytes < need) {
+        if (C.h_out) cudaFreeHost(C.h_out);
+        C.h_out = nullptr; C.h_out_bytes = 0;
+        CU(cudaHostAlloc((void **)&C.h_out, need, cudaHostAllocDefault));
+        C.h_out_bytes = need;
+    }
+    pslot_keypoint *hk = reinterpret_cast<pslot_keypoint *>(C.h_out + 16);
+    uint8_t *hd = C.h_out + 16 + (size_t)guess * sizeof(pslot_keypoint);
+    CU(cudaMemcpyAsync(C.h_out, C.b.out_count, sizeof(int), cudaMemcpyDeviceToHost, C.st));
+    CU(cudaMemcpyAsync(hk, C.b.out_kps, sizeof(pslot_keypoint) * (size_t)guess, cudaMemcpyDeviceToHost, C.st));
+    CU(cudaMemcpyAsync(hd, C.b.out_desc, 32 * (size_t)guess, cudaMemcpyDeviceToHost, C.st));
     CU(cudaStreamSynchronize(C.st));
     if (*(volatile int *)C.h_err) {
         *C.h_err = 0;
         return fail(PSLOT_ERR_CAPACITY, "cv::ORB: a per-level candidate list or the keypoint sort overflowed");
     }
+    const int count = *reinterpret_cast<const int *>(C.h_out);
     *n = count;
     if (count > cap) return fail(PSLOT_ERR_CAPACITY, "need room for %d keypoints, caller gave %d", count, cap);
     if (count > 0) {
         if (!kps || !desc32) return fail(PSLOT_ERR_ARG, "kps / desc32 is null");
-        CU(cudaMemcpyAsync(kps, C.b.out_kps, sizeof(pslot_keypoint) * (size_t)count, cudaMemcpyDeviceToHost, C.st));
-        CU(cudaMemcpyAsync(desc32, C.b.out_desc, 32 * (size_t)count, cudaMemcpyDeviceToHost, C.st));
-        CU(cudaStreamSynchronize(C.st));
+        if (count <= guess) {
+            memcpy(kps, hk, sizeof(pslot_keypoint) * (size_t)count);
+            memcpy(desc32, hd, 32 * (size_t)count);
+        } else { // massive response ties kept by retainBest: fetch the full set
+            CU(cudaMemcpyAsync(kps, C.b.out_kps, sizeof(pslot_keypoint) * (size_t)count, cudaMemcpyDeviceToHost, C.st));
+            CU(cudaMemcpyAsync(desc32, C.b.out_desc, 32 * (size_t)count, cudaMemcpyDeviceToHost, C.st));
+            CU(cudaStreamSynchronize(C.st));
+        }
     }
     return PSLOT_OK;
 }
