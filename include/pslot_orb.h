@@ -284,6 +284,35 @@ int pslot_cvorb_detect_and_compute(pslot_cvorb *ctx, const uint8_t *img, int w, 
                                    const uint8_t *mask, ptrdiff_t mask_pitch, pslot_keypoint *kps, uint8_t *desc32,
                                    int cap, int *n);
 
+/* ---------------------------------------------------------------------------------------------
+ * Bag of words (second half).
+ * Replaces `void Frame::ComputeBoW()` (reference src/Frame.cc:2040-2047):
+ *     mpORBvocabulary->transform(Converter::toDescriptorVector(mDescriptors), mBowVec, mFeatVec, 4)
+ * with ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (include/ORBVocabulary.h:30; transform:
+ * Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1132-1201, 1223-1266).
+ *
+ * pslot_vocab_create takes the tree as flat arrays - what loadFromTextFile (:1389-1474) builds from Vocabulary/ORBvoc.txt:
+ * node 0 = root, children of node i = child[child_start[i] .. child_start[i+1]) in file order, a node without children is
+ * a leaf with word_id >= 0 and its weight.  scoring: 0 L1_NORM .. 5 DOT_PRODUCT, weighting: 0 TF_IDF 1 TF 2 IDF 3 BINARY
+ * (BowVector.h:36-57).
+ * pslot_bow_transform: the tree walk on the device, one result pair per descriptor: the leaf reached and the node at
+ * level L - levelsup (desc32 = n x 32 host bytes; or NULL with `ctx` = an extractor whose last pslot_orb_extract left
+ * its n descriptors on the device - they are read there).
+ * pslot_bow_vectors: mBowVec as (word id ascending, value) and mFeatVec as CSR (node id ascending, start, feature
+ * indices in feature order) from those pairs, in DBoW2's own double arithmetic (addWeight accumulation in feature
+ * order, L1 / L2 normalisation in id order) - values are bit-identical to the reference's.  Arrays hold n entries
+ * (fv_start n + 1).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct pslot_vocab pslot_vocab;
+int pslot_vocab_create(pslot_vocab **voc, int n_nodes, int k, int L, int scoring, int weighting, const uint8_t *desc32,
+                       const int32_t *child_start, const int32_t *child, const int32_t *word_id, const double *weight,
+                       int device);
+void pslot_vocab_destroy(pslot_vocab *voc);
+int pslot_bow_transform(pslot_vocab *voc, pslot_orb *ctx, const uint8_t *desc32, int n, int levelsup, int32_t *leaf_node,
+                        int32_t *nid);
+int pslot_bow_vectors(const pslot_vocab *voc, const int32_t *leaf_node, const int32_t *nid, int n, int32_t *bow_id,
+                      double *bow_val, int *n_words, int32_t *fv_node, int32_t *fv_start, int32_t *fv_feat, int *n_fv_nodes);
+
 /* Stage accessor of the last pslot_cvorb_detect_and_compute, for the parity tests: what = 0 the pyramid level (w*h bytes,
  * tightly packed), 1 its raw FAST score map (0 where not a corner), 2 the level's candidates after the maxima test, the mask
  * and the border filter (packed u32 y:12 | x:12 | score:8, unordered), 3 the candidates retainBest(2*quota) kept (same

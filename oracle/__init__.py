@@ -89,6 +89,9 @@ def lib():
                                                     C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp]
         L.orc_cvorb_detect_and_compute.argtypes = [vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_ssize_t, C.c_int, C.c_float,
                                                    C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, ip]
+        L.orc_bow_transform.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+        L.orc_bow_transform.restype = None
+        L.orc_bow_vectors.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, ip]
         L.orc_distribute_octtree.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_int, vp, vp, vp, ip]
         _lib = L
@@ -382,3 +385,44 @@ def stereo_pair(params, imL, imR, bf, maxD):
     kL, dL = eL.extract(imL); kR, dR = eR.extract(imR)
     ur, dp = stereo_match(eL, eR, kL, dL, kR, dR, bf, maxD)
     return kL, dL, kR, dR, ur, dp
+
+
+# ---------------------------------------------------------------------------------------------
+# Frame::ComputeBoW = DBoW2 transform (reference src/Frame.cc:2040-2047, Thirdparty/DBoW2)
+# ---------------------------------------------------------------------------------------------
+class _OrcVocab(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("k", C.c_int32), ("L", C.c_int32), ("scoring", C.c_int32), ("weighting", C.c_int32),
+                ("desc", C.c_void_p), ("child_start", C.c_void_p), ("child", C.c_void_p), ("word_id", C.c_void_p),
+                ("weight", C.c_void_p)]
+
+
+def _orc_vocab(voc):
+    """`voc`: pointslot_b200.vocab.Vocabulary (plain arrays; the container is shared with the product's host side)."""
+    keep = [np.ascontiguousarray(voc.desc, np.uint8), np.ascontiguousarray(voc.child_start, np.int32),
+            np.ascontiguousarray(voc.child, np.int32), np.ascontiguousarray(voc.word_id, np.int32),
+            np.ascontiguousarray(voc.weight, np.float64)]
+    s = _OrcVocab(voc.n_nodes, voc.k, voc.L, voc.scoring, voc.weighting, *(a.ctypes.data for a in keep))
+    return s, keep
+
+
+def bow_transform(voc, desc: np.ndarray, levelsup: int = 4):
+    """-> (leaf node id, node id at level L - levelsup) per descriptor."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    n = len(desc)
+    s, keep = _orc_vocab(voc)
+    leaf = np.zeros(n, np.int32); nid = np.zeros(n, np.int32)
+    lib().orc_bow_transform(C.byref(s), _ptr(desc), n, levelsup, _ptr(leaf), _ptr(nid))
+    return leaf, nid
+
+
+def bow_vectors(voc, leaf: np.ndarray, nid: np.ndarray):
+    """-> (word ids ascending, values) = mBowVec and (node ids ascending, start offsets, feature indices) = mFeatVec."""
+    n = len(leaf)
+    s, keep = _orc_vocab(voc)
+    leaf = np.ascontiguousarray(leaf, np.int32); nid = np.ascontiguousarray(nid, np.int32)
+    m = max(n, 1)
+    bid = np.zeros(m, np.int32); bval = np.zeros(m, np.float64)
+    fn = np.zeros(m, np.int32); fs = np.zeros(m + 1, np.int32); ff = np.zeros(m, np.int32)
+    nf = C.c_int(0)
+    nw = lib().orc_bow_vectors(C.byref(s), _ptr(leaf), _ptr(nid), n, _ptr(bid), _ptr(bval), _ptr(fn), _ptr(fs), _ptr(ff), C.byref(nf))
+    return bid[:nw].copy(), bval[:nw].copy(), fn[:nf.value].copy(), fs[:nf.value + 1].copy(), ff[:fs[nf.value]].copy()

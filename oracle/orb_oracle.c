@@ -1396,3 +1396,104 @@ int orc_cvorb_detect_and_compute(const uint8_t *img, int w, int h, ptrdiff_t pit
     *n_out = n;
     return rc;
 }
+
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Frame::ComputeBoW (reference src/Frame.cc:2040-2047) -> DBoW2 transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h)
+ * ------------------------------------------------------------------------------------------------------------ */
+void orc_bow_transform(const orc_vocab *v, const uint8_t *desc, int n, int levelsup, int32_t *leaf_node, int32_t *nid)
+{
+    const int nid_level = v->L - levelsup; /* :1232 */
+    for (int i = 0; i < n; ++i) {
+        const uint8_t *f = desc + (size_t)i * 32;
+        int final_id = 0, level = 0, at = -1;
+        if (nid_level <= 0) at = 0; /* :1233 */
+        do { /* :1238-1261 */
+            ++level;
+            const int32_t *c = v->child + v->child_start[final_id], nc = v->child_start[final_id + 1] - v->child_start[final_id];
+            final_id = c[0];
+            int best = orc_hamming256(f, v->desc + (size_t)final_id * 32);
+            for (int j = 1; j < nc; ++j) {
+                const int d = orc_hamming256(f, v->desc + (size_t)c[j] * 32);
+                if (d < best) { best = d; final_id = c[j]; }
+            }
+            if (level == nid_level) at = final_id;
+        } while (v->child_start[final_id + 1] > v->child_start[final_id]);
+        leaf_node[i] = final_id;
+        nid[i] = at >= 0 ? at : final_id; /* the reference leaves *nid unset when the leaf lies above nid_level */
+    }
+}
+
+static int cmp_i32(const void *a, const void *b) { const int32_t x = *(const int32_t *)a, y = *(const int32_t *)b; return x < y ? -1 : x > y; }
+
+int orc_bow_vectors(const orc_vocab *v, const int32_t *leaf_node, const int32_t *nid, int n, int32_t *bow_id, double *bow_val,
+                    int32_t *fv_node, int32_t *fv_start, int32_t *fv_feat, int *n_fv_nodes)
+{
+    /* features whose word is not stopped (w > 0), :1163 / :1191 */
+    int m = 0, nf = 0;
+    int32_t *ids = malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1)), *nodes = malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; ++i)
+        if (v->weight[leaf_node[i]] > 0) { ids[m] = v->word_id[leaf_node[i]]; nodes[m] = nid[i]; ++m; }
+    /* std::map keys: the distinct ids in ascending order */
+    int32_t *sorted = malloc(sizeof(int32_t) * (size_t)(m > 0 ? m : 1));
+    memcpy(sorted, ids, sizeof(int32_t) * (size_t)m);
+    qsort(sorted, (size_t)m, sizeof(int32_t), cmp_i32);
+    int nw = 0;
+    for (int i = 0; i < m; ++i)
+        if (i == 0 || sorted[i] != sorted[i - 1]) { bow_id[nw] = sorted[i]; bow_val[nw] = 0.0; ++nw; }
+    /* addWeight accumulates v[id] += w in feature order (TF_IDF, TF :1164); addIfNotExist stores w once (IDF, BINARY :1192) */
+    const int tf = v->weighting == 0 || v->weighting == 1;
+    {
+        uint8_t *seen = calloc((size_t)(nw > 0 ? nw : 1), 1);
+        int j = 0;
+        for (int i = 0; i < n; ++i) {
+            const double w = v->weight[leaf_node[i]];
+            if (!(w > 0)) continue;
+            const int32_t id = ids[j++];
+            int lo = 0, hi = nw - 1;
+            while (lo < hi) { const int mid = (lo + hi) / 2; if (bow_id[mid] < id) lo = mid + 1; else hi = mid; }
+            if (tf) { if (seen[lo]) bow_val[lo] += w; else { bow_val[lo] = w; seen[lo] = 1; } }
+            else if (!seen[lo]) { bow_val[lo] = w; seen[lo] = 1; }
+        }
+        free(seen);
+    }
+    /* mustNormalize (ScoringObject.h): every scoring but DOT_PRODUCT normalises, L2_NORM by L2, the rest by L1 */
+    const int must = v->scoring != 5, l2 = v->scoring == 1;
+    if (tf && nw > 0 && !must) { /* :1169-1175 */
+        const double nd = (double)nw;
+        for (int i = 0; i < nw; ++i) bow_val[i] /= nd;
+    }
+    if (must) { /* BowVector::normalize (BowVector.cpp:62-85): sums in ascending id order */
+        double norm = 0.0;
+        if (!l2) for (int i = 0; i < nw; ++i) norm += fabs(bow_val[i]);
+        else { for (int i = 0; i < nw; ++i) norm += bow_val[i] * bow_val[i]; norm = sqrt(norm); }
+        if (norm > 0.0) for (int i = 0; i < nw; ++i) bow_val[i] /= norm;
+    }
+    /* FeatureVector (FeatureVector.cpp:33-47): node id ascending, feature indices in feature order */
+    memcpy(sorted, nodes, sizeof(int32_t) * (size_t)m);
+    qsort(sorted, (size_t)m, sizeof(int32_t), cmp_i32);
+    for (int i = 0; i < m; ++i)
+        if (i == 0 || sorted[i] != sorted[i - 1]) fv_node[nf++] = sorted[i];
+    for (int i = 0; i <= nf; ++i) fv_start[i] = 0;
+    for (int i = 0; i < m; ++i) {
+        int lo = 0, hi = nf - 1;
+        while (lo < hi) { const int mid = (lo + hi) / 2; if (fv_node[mid] < nodes[i]) lo = mid + 1; else hi = mid; }
+        ++fv_start[lo + 1];
+    }
+    for (int i = 0; i < nf; ++i) fv_start[i + 1] += fv_start[i];
+    {
+        int32_t *fill = calloc((size_t)(nf > 0 ? nf : 1), sizeof(int32_t));
+        int j = 0;
+        for (int i = 0; i < n; ++i) {
+            if (!(v->weight[leaf_node[i]] > 0)) continue;
+            const int32_t node = nodes[j++];
+            int lo = 0, hi = nf - 1;
+            while (lo < hi) { const int mid = (lo + hi) / 2; if (fv_node[mid] < node) lo = mid + 1; else hi = mid; }
+            fv_feat[fv_start[lo] + fill[lo]++] = i;
+        }
+        free(fill);
+    }
+    free(ids); free(nodes); free(sorted);
+    *n_fv_nodes = nf;
+    return nw;
+}

@@ -146,6 +146,30 @@ int orc_cvorb_detect_and_compute(const uint8_t *img, int w, int h, ptrdiff_t pit
                                  int edge_threshold, int fast_threshold, orc_keypoint *kps, uint8_t *desc32, int cap,
                                  int *n_out);
 
+/* Frame::ComputeBoW (reference src/Frame.cc:2040-2047) = ORBVocabulary::transform(descriptors, mBowVec, mFeatVec, 4), i.e.
+ * DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>::transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1132-1201,
+ * 1223-1266; un-vendored algorithm = the vendored copy in the reference tree).  The vocabulary is a flat tree: node 0 is
+ * the root, children of node i are child[child_start[i] .. child_start[i + 1]) in file order, a node without children is
+ * a leaf and carries word_id >= 0 and its weight. */
+typedef struct orc_vocab {
+    int32_t n_nodes, k, L, scoring, weighting; /* scoring: 0 L1 1 L2 2 CHI 3 KL 4 BHATT 5 DOT; weighting: 0 TF_IDF 1 TF 2 IDF 3 BINARY */
+    const uint8_t *desc;        /* [n_nodes][32] */
+    const int32_t *child_start; /* [n_nodes + 1] */
+    const int32_t *child;       /* node ids */
+    const int32_t *word_id;     /* [n_nodes], -1 for inner nodes */
+    const double *weight;       /* [n_nodes] */
+} orc_vocab;
+/* per feature: the leaf reached (TemplatedVocabulary.h:1223-1266: first child with the strictly smallest Hamming distance
+ * at every level) and the node at level L - levelsup on the way (0 when that level is <= 0; the leaf itself when the walk
+ * ends above that level, where the reference leaves *nid unset) */
+void orc_bow_transform(const orc_vocab *v, const uint8_t *desc, int n, int levelsup, int32_t *leaf_node, int32_t *nid);
+/* the two containers of transform(features, v, fv, levelsup) (:1132-1201) from the per-feature results, in the reference's
+ * arithmetic: BowVector = (word id ascending, value) with addWeight / addIfNotExist accumulation in feature order and the
+ * scoring's normalisation; FeatureVector = (node id ascending -> feature indices in feature order) as CSR.
+ * Returns the number of words; *n_fv_nodes = FeatureVector size.  Arrays must hold n entries (fv_start n + 1). */
+int orc_bow_vectors(const orc_vocab *v, const int32_t *leaf_node, const int32_t *nid, int n, int32_t *bow_id, double *bow_val,
+                    int32_t *fv_node, int32_t *fv_start, int32_t *fv_feat, int *n_fv_nodes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,11 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <string>
 #include <vector>
+#include <fstream>   // the real opencv2/core/core.hpp pulls the stream headers in; DBoW2 relies on that
+#include <iostream>
+#include <sstream>
 
 #define CV_8U 0
 #define CV_8UC1 0
@@ -228,6 +232,36 @@ public:
 };
 typedef const _InputArray &InputArray;
 typedef const _OutputArray &OutputArray;
+
+// ---- cv::FileStorage / cv::FileNode: DBoW2's TemplatedVocabulary has virtual save / load members that mention them (the
+// YAML route, Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1500-1716); PointSLOT loads its vocabulary with
+// loadFromTextFile, so these stand-ins only have to compile - a storage never opens
+class FileNode {
+public:
+    enum { NONE = 0, SEQ = 5, MAP = 6 };
+    FileNode operator[](const char *) const { return FileNode(); }
+    FileNode operator[](const std::string &) const { return FileNode(); }
+    FileNode operator[](int) const { return FileNode(); }
+    size_t size() const { return 0; }
+    int type() const { return NONE; }
+    bool empty() const { return true; }
+    operator int() const { return 0; }
+    operator double() const { return 0.0; }
+    operator float() const { return 0.f; }
+    operator std::string() const { return std::string(); }
+};
+class FileStorage {
+public:
+    enum { READ = 0, WRITE = 1 };
+    FileStorage() {}
+    FileStorage(const char *, int) {}
+    FileStorage(const std::string &, int) {}
+    bool isOpened() const { return false; }
+    void release() {}
+    FileNode operator[](const char *) const { return FileNode(); }
+    FileNode operator[](const std::string &) const { return FileNode(); }
+};
+template <typename T> inline FileStorage &operator<<(FileStorage &fs, const T &) { return fs; }
 
 // ---- the primitives: served by ref_glue.cc (cv2 callbacks, or the C oracle's pinned restatements) ---------------------
 void resize(const Mat &src, Mat &dst, Size dsize, double fx, double fy, int interpolation);

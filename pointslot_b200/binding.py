@@ -32,6 +32,7 @@ ABI_SYMBOLS = [
     "pslot_assign_grid", "pslot_grid_token", "pslot_features_in_area", "pslot_batch_assign_grid",
     "pslot_search_by_projection", "pslot_search_by_projection_last", "pslot_debug_projection_sweeps",
     "pslot_cvorb_create", "pslot_cvorb_destroy", "pslot_cvorb_detect_and_compute", "pslot_cvorb_debug",
+    "pslot_vocab_create", "pslot_vocab_destroy", "pslot_bow_transform", "pslot_bow_vectors",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
 ]
 
@@ -126,6 +127,11 @@ def lib():
     L.pslot_cvorb_detect_and_compute.argtypes = [vp, vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_ssize_t, vp, vp, C.c_int,
                                                  C.POINTER(C.c_int)]
     L.pslot_cvorb_debug.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.pslot_vocab_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int]
+    L.pslot_vocab_destroy.argtypes = [vp]
+    L.pslot_vocab_destroy.restype = None
+    L.pslot_bow_transform.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp]
+    L.pslot_bow_vectors.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.POINTER(C.c_int), vp, vp, vp, C.POINTER(C.c_int)]
     L.pslot_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]
     L.pslot_host_free.argtypes = [vp]
     L.pslot_batch_stereo_counters.argtypes = [vp, vp]
@@ -304,6 +310,51 @@ def _cvorb_stage(self, what: int, level: int):
 
 
 CvOrb.stage = _cvorb_stage
+
+
+class OrbVocabulary:
+    """The ORB vocabulary on the device (pslot_vocab_*): `voc` is a pointslot_b200.vocab.Vocabulary (what
+    ORBVocabulary::loadFromTextFile builds).  compute_bow = Frame::ComputeBoW (reference src/Frame.cc:2040-2047)."""
+
+    def __init__(self, voc, device=0):
+        h = C.c_void_p()
+        self._keep = [np.ascontiguousarray(voc.desc, np.uint8), np.ascontiguousarray(voc.child_start, np.int32),
+                      np.ascontiguousarray(voc.child, np.int32), np.ascontiguousarray(voc.word_id, np.int32),
+                      np.ascontiguousarray(voc.weight, np.float64)]
+        _check(lib().pslot_vocab_create(C.byref(h), voc.n_nodes, voc.k, voc.L, voc.scoring, voc.weighting,
+                                        *(_p(a) for a in self._keep), device))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pslot_vocab_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def transform(self, desc=None, levelsup=4, extractor: "OrbExtractor" = None, n=None):
+        """-> (leaf node, node at level L - levelsup) per descriptor; `desc` None = the descriptors the extractor's last
+        extract() left on the device (n of them)."""
+        if desc is not None:
+            desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+            n = len(desc)
+        leaf = np.zeros(max(n, 1), np.int32); nid = np.zeros(max(n, 1), np.int32)
+        _check(lib().pslot_bow_transform(self._h, extractor._h if extractor is not None else None,
+                                         None if desc is None else _p(desc), n, levelsup, _p(leaf), _p(nid)))
+        return leaf[:n], nid[:n]
+
+    def vectors(self, leaf, nid):
+        n = len(leaf)
+        leaf = np.ascontiguousarray(leaf, np.int32); nid = np.ascontiguousarray(nid, np.int32)
+        m = max(n, 1)
+        bid = np.zeros(m, np.int32); bval = np.zeros(m, np.float64)
+        fn = np.zeros(m, np.int32); fs = np.zeros(m + 1, np.int32); ff = np.zeros(m, np.int32)
+        nw, nf = C.c_int(0), C.c_int(0)
+        _check(lib().pslot_bow_vectors(self._h, _p(leaf), _p(nid), n, _p(bid), _p(bval), C.byref(nw), _p(fn), _p(fs), _p(ff), C.byref(nf)))
+        return bid[:nw.value].copy(), bval[:nw.value].copy(), fn[:nf.value].copy(), fs[:nf.value + 1].copy(), ff[:fs[nf.value]].copy()
+
+    def compute_bow(self, desc=None, levelsup=4, extractor=None, n=None):
+        return self.vectors(*self.transform(desc, levelsup, extractor, n))
 
 
 class PinnedBuffer:

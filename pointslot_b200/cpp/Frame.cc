@@ -333,6 +333,17 @@ void Frame::ComputeObjStereoMatches() // (:2318-2503): the same routine on the o
                     mvuTempObjKeysRight, mvTempObjDepth);
 }
 
+void Frame::ComputeBoW() // (:2040-2047)
+{
+    if (mBowVec.empty()) {
+        // Converter::toDescriptorVector(mDescriptors) + transform(vCurrentDesc, mBowVec, mFeatVec, 4): the rows of
+        // mDescriptors are the features, in order
+        std::vector<unsigned char> flat(32 * (size_t)mDescriptors.rows);
+        for (int i = 0; i < mDescriptors.rows; ++i) std::memcpy(&flat[32 * (size_t)i], mDescriptors.ptr(i), 32);
+        mpORBvocabulary->transform(flat.data(), mDescriptors.rows, nullptr, mBowVec, mFeatVec, 4);
+    }
+}
+
 void OpencvORBDetector(cv::Mat im, cv::Mat ObjMask, std::vector<cv::KeyPoint> &kp, cv::Mat &descriptor) // (:2623-2627)
 {
     struct Ctx {

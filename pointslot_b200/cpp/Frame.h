@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "ORBextractor.h"
+#include "ORBVocabulary.h"
 #include "compat/opencv_min.h"
 
 namespace ORB_SLAM2
@@ -21,7 +22,6 @@ namespace ORB_SLAM2
 #define FRAME_GRID_ROWS 48
 #define FRAME_GRID_COLS 64
 
-class ORBVocabulary; // opaque here: the stereo path never touches it
 class MapPoint;      // only pointers are stored
 class Detector;      // YOLO wrapper (reference include/YOLOdetector.h); opaque, only passed through
 } // namespace ORB_SLAM2
@@ -73,6 +73,10 @@ public:
     // Extract ORB on the image. 0 for left image and 1 for right image.
     void ExtractORB(int flag, const cv::Mat &im);
 
+    // Compute Bag of Words representation (reference Frame.h:94 / Frame.cc:2040-2047): mBowVec / mFeatVec of the frame's
+    // descriptors (the tree walk runs on the device, the two containers are filled in DBoW2's own arithmetic).
+    void ComputeBoW();
+
     // Dense object features (reference Frame.cc:2628-2665): OpenCV's own ORB on both views, restricted to the object
     // masks, on two threads; fills mvTempObjKeys / mvTempObjKeysRight and their descriptor matrices.  The reference
     // builds the two masks from mMaskImg / mMaskImgRight (:2633-2645, PointSLOT's own instance-mask members) and
@@ -120,6 +124,10 @@ public:
     std::vector<float> mvuRight; // negative value for monocular points
     std::vector<float> mvDepth;
     cv::Mat mDescriptors, mDescriptorsRight;
+
+    // Bag of Words Vector structures (reference Frame.h:196-197)
+    DBoW2::BowVector mBowVec;
+    DBoW2::FeatureVector mFeatVec;
 
     // object feature set of the current detection pass (reference Frame.h:167-173)
     std::vector<cv::KeyPoint> mvTempObjKeys, mvTempObjKeysRight, mvTempObjKeysUn;

@@ -1,6 +1,6 @@
 // test_shim.cc — exercises the drop-in classes exactly as Tracking::GrabImageStereo does
 // (reference src/Tracking.cc:385-388, 1045): two ORBextractor objects, one Frame per stereo pair.
-// usage: test_shim <in.bin> <out.bin>
+// usage: test_shim <in.bin> <out.bin> [vocabulary.txt]
 //   in : int32 W,H,nfeatures,nlevels,iniTh,minTh; float32 scaleFactor,bf,fx; then W*H left bytes, W*H right bytes
 //   out: int32 N, Nr; N keypoints (28 B), N*32 desc, Nr keypoints, Nr*32 desc, N float uRight, N float depth,
 //        int32 pyramid level-1 w,h + bytes (checks SyncImagePyramid), int32 DescriptorDistance(desc0, desc1),
@@ -11,7 +11,9 @@
 //        then the object-mode frame built in between on the same extractors from both images rolled down 7 rows
 //        (SLOTMode constructor + ObjectStageHook): int32 nObjL, nObjR, nObjL float mvuTempObjKeysRight, nObjL float
 //        mvTempObjDepth, int32 N of that frame; then Frame::ExtractObjORB on the first frame's images with two-rectangle
-//        object masks: int32 nObjL, nObjR, nObjL keypoints + nObjL*32 desc, nObjR keypoints + nObjR*32 desc
+//        object masks: int32 nObjL, nObjR, nObjL keypoints + nObjL*32 desc, nObjR keypoints + nObjR*32 desc; with a third
+//        argument (vocabulary text file) Frame::ComputeBoW: int32 nWords, nFv, nWords x (int32 id, double value),
+//        nFv x (int32 node, int32 count, count x uint32 feature index)
 // The second frame is built BEFORE the area / projection queries on the first one, so those queries only pass when the
 // first frame notices that the device grid is no longer its own (Frame::EnsureDeviceGrid).
 #include <algorithm>
@@ -171,6 +173,23 @@ int main(int argc, char **argv)
     for (int i = 0; i < nOL; ++i) std::fwrite(frame.mTempObjPointsDescriptors.ptr(i), 1, 32, o);
     std::fwrite(frame.mvTempObjKeysRight.data(), sizeof(cv::KeyPoint), nOR, o);
     for (int i = 0; i < nOR; ++i) std::fwrite(frame.mTempObjPointsDescriptorsRight.ptr(i), 1, 32, o);
+    // Frame::ComputeBoW (reference Frame.cc:2040-2047) with the vocabulary file given as the third argument
+    int nWords = -1, nFv = 0;
+    if (argc > 3) {
+        ORBVocabulary voc;
+        if (!voc.loadFromTextFile(argv[3])) return 7;
+        frame.mpORBvocabulary = &voc;
+        frame.ComputeBoW();
+        frame.mpORBvocabulary = nullptr;
+        nWords = (int)frame.mBowVec.size(); nFv = (int)frame.mFeatVec.size();
+        std::fwrite(&nWords, 4, 1, o); std::fwrite(&nFv, 4, 1, o);
+        for (const auto &e : frame.mBowVec) { const int id = (int)e.first; std::fwrite(&id, 4, 1, o); std::fwrite(&e.second, 8, 1, o); }
+        for (const auto &e : frame.mFeatVec) {
+            const int id = (int)e.first, cnt = (int)e.second.size();
+            std::fwrite(&id, 4, 1, o); std::fwrite(&cnt, 4, 1, o);
+            std::fwrite(e.second.data(), 4, cnt, o);
+        }
+    }
     std::fclose(o);
     std::printf("shim ok: N=%d Nr=%d matched=%d mb=%g projection matches=%d\n", N, Nr,
                 (int)std::count_if(frame.mvuRight.begin(), frame.mvuRight.end(), [](float v) { return v >= 0; }), frame.mb, nmatches);

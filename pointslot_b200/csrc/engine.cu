@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <atomic>
 #include <new>
+#include <map>
 #include <vector>
 
 #include "pslot_internal.h"
@@ -494,6 +495,25 @@ struct pslot_cvorb {
         release();
         if (h_err) cudaFreeHost(h_err);
         if (h_out) cudaFreeHost(h_out);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
+// ---- ORB vocabulary (Frame::ComputeBoW; reference Frame.cc:2040-2047, Thirdparty/DBoW2) ------------------------------------
+struct pslot_vocab {
+    int n_nodes = 0, k = 0, L = 0, scoring = 0, weighting = 0, device = 0;
+    std::vector<int32_t> word_id;  // host copies of what pslot_bow_vectors needs
+    std::vector<double> weight;
+    uint8_t *d_desc = nullptr;
+    int *d_child_start = nullptr, *d_child = nullptr;
+    // per-call scratch
+    uint8_t *d_feat = nullptr;
+    int *d_leaf = nullptr, *d_nid = nullptr;
+    int cap = 0;
+    cudaStream_t st = nullptr;
+    ~pslot_vocab()
+    {
+        cudaFree(d_desc); cudaFree(d_child_start); cudaFree(d_child); cudaFree(d_feat); cudaFree(d_leaf); cudaFree(d_nid);
         if (st) cudaStreamDestroy(st);
     }
 };
@@ -1016,6 +1036,144 @@ int pslot_cvorb_detect_and_compute(pslot_cvorb *ctx, const uint8_t *img, int w, 
             CU(cudaStreamSynchronize(C.st));
         }
     }
+    return PSLOT_OK;
+}
+
+// ---- bag of words ------------------------------------------------------------------------------------------------------
+int pslot_vocab_create(pslot_vocab **voc, int n_nodes, int k, int L, int scoring, int weighting, const uint8_t *desc32,
+                       const int32_t *child_start, const int32_t *child, const int32_t *word_id, const double *weight,
+                       int device)
+{
+    if (!voc) return fail(PSLOT_ERR_ARG, "voc is null");
+    *voc = nullptr;
+    if (n_nodes < 2 || !desc32 || !child_start || !child || !word_id || !weight) return fail(PSLOT_ERR_ARG, "empty vocabulary");
+    if (L < 1 || scoring < 0 || scoring > 5 || weighting < 0 || weighting > 3) return fail(PSLOT_ERR_ARG, "bad L / scoring / weighting");
+    // the tree must be walkable: child lists inside the array, every child a later node than its parent (file order), the
+    // root has children, every leaf carries a word
+    if (child_start[0] != 0 || child_start[n_nodes] != n_nodes - 1 || child_start[1] <= 0)
+        return fail(PSLOT_ERR_ARG, "child_start must run from 0 to n_nodes - 1 and the root must have children");
+    for (int i = 0; i < n_nodes; ++i) {
+        if (child_start[i + 1] < child_start[i]) return fail(PSLOT_ERR_ARG, "child_start not ascending at node %d", i);
+        if (child_start[i + 1] - child_start[i] > 65535) return fail(PSLOT_ERR_ARG, "node %d has more than 65535 children", i);
+        for (int c = child_start[i]; c < child_start[i + 1]; ++c)
+            if (child[c] <= i || child[c] >= n_nodes) return fail(PSLOT_ERR_ARG, "child %d of node %d is not a later node", child[c], i);
+        if (child_start[i + 1] == child_start[i] && word_id[i] < 0) return fail(PSLOT_ERR_ARG, "leaf %d has no word id", i);
+    }
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PSLOT_ERR_CUDA, "CUDA device %d not available (%d visible)", device, ndev);
+    pslot_vocab *v = new (std::nothrow) pslot_vocab();
+    if (!v) return fail(PSLOT_ERR_ARG, "out of host memory");
+    v->n_nodes = n_nodes; v->k = k; v->L = L; v->scoring = scoring; v->weighting = weighting; v->device = device;
+    v->word_id.assign(word_id, word_id + n_nodes);
+    v->weight.assign(weight, weight + n_nodes);
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&v->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_desc, 32 * (size_t)n_nodes);
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_child_start, 4 * (size_t)(n_nodes + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_child, 4 * (size_t)n_nodes);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_desc, desc32, 32 * (size_t)n_nodes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_child_start, child_start, 4 * (size_t)(n_nodes + 1), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_child, child, 4 * (size_t)(n_nodes - 1), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete v; return fail(PSLOT_ERR_CUDA, "pslot_vocab_create: %s", cudaGetErrorString(e)); }
+    *voc = v;
+    return PSLOT_OK;
+}
+
+void pslot_vocab_destroy(pslot_vocab *voc)
+{
+    if (!voc) return;
+    cudaSetDevice(voc->device);
+    if (voc->st) cudaStreamSynchronize(voc->st);
+    delete voc;
+}
+
+int pslot_bow_transform(pslot_vocab *voc, pslot_orb *ctx, const uint8_t *desc32, int n, int levelsup, int32_t *leaf_node,
+                        int32_t *nid)
+{
+    if (!voc) return fail(PSLOT_ERR_ARG, "voc is null");
+    if (n < 0 || (n > 0 && (!leaf_node || !nid))) return fail(PSLOT_ERR_ARG, "bad n / null outputs");
+    if (n == 0) return PSLOT_OK;
+    pslot_vocab &V = *voc;
+    CU(cudaSetDevice(V.device));
+    if (n > V.cap) {
+        CU(cudaStreamSynchronize(V.st));
+        cudaFree(V.d_feat); cudaFree(V.d_leaf); cudaFree(V.d_nid);
+        V.d_feat = nullptr; V.d_leaf = V.d_nid = nullptr; V.cap = 0;
+        const int cap = std::max(n, 4096);
+        CU(cudaMalloc(&V.d_feat, 32 * (size_t)cap)); CU(cudaMalloc(&V.d_leaf, 4 * (size_t)cap)); CU(cudaMalloc(&V.d_nid, 4 * (size_t)cap));
+        V.cap = cap;
+    }
+    const uint8_t *feat = V.d_feat;
+    if (desc32) {
+        CU(cudaMemcpyAsync(V.d_feat, desc32, 32 * (size_t)n, cudaMemcpyHostToDevice, V.st));
+    } else {
+        if (!ctx) return fail(PSLOT_ERR_ARG, "desc32 is null and no extractor context given");
+        Engine &E = ctx->E;
+        if (!E.has_pyramid || E.device != V.device) return fail(PSLOT_ERR_STATE, "the extractor holds no features on this device");
+        CU(cudaStreamSynchronize(E.st));
+        if (n > E.g.kp_cap_total) return fail(PSLOT_ERR_ARG, "n exceeds the extractor's keypoint capacity");
+        feat = E.d_out_desc; // the last pslot_orb_extract left its descriptors here (slot 0)
+    }
+    launch_bow_transform(V.d_desc, V.d_child_start, V.d_child, feat, n, V.L - levelsup, V.d_leaf, V.d_nid, V.st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "bow launch failed: %s", cudaGetErrorString(e));
+    CU(cudaMemcpyAsync(leaf_node, V.d_leaf, 4 * (size_t)n, cudaMemcpyDeviceToHost, V.st));
+    CU(cudaMemcpyAsync(nid, V.d_nid, 4 * (size_t)n, cudaMemcpyDeviceToHost, V.st));
+    CU(cudaStreamSynchronize(V.st));
+    return PSLOT_OK;
+}
+
+int pslot_bow_vectors(const pslot_vocab *voc, const int32_t *leaf_node, const int32_t *nid, int n, int32_t *bow_id,
+                      double *bow_val, int *n_words, int32_t *fv_node, int32_t *fv_start, int32_t *fv_feat, int *n_fv_nodes)
+{
+    if (!voc || !n_words || !n_fv_nodes || n < 0) return fail(PSLOT_ERR_ARG, "null argument");
+    *n_words = *n_fv_nodes = 0;
+    if (n > 0 && (!leaf_node || !nid || !bow_id || !bow_val || !fv_node || !fv_start || !fv_feat)) return fail(PSLOT_ERR_ARG, "null array");
+    // DBoW2's order of operations (TemplatedVocabulary.h:1132-1201, BowVector.cpp, FeatureVector.cpp) without its node-based
+    // maps: the non-stopped features are ordered by (key, feature index) - a std::map visits keys ascending, and both
+    // addWeight's running sum and FeatureVector's push_back see a key's features in feature order
+    const bool tf = voc->weighting == 0 || voc->weighting == 1;
+    std::vector<std::pair<uint32_t, int32_t>> by_word, by_node; // (key, feature)
+    by_word.reserve((size_t)n); by_node.reserve((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        const int leaf = leaf_node[i];
+        if (leaf < 0 || leaf >= voc->n_nodes || voc->word_id[leaf] < 0) return fail(PSLOT_ERR_ARG, "leaf_node[%d] = %d is not a word", i, leaf);
+        if (!(voc->weight[leaf] > 0)) continue; // stopped word
+        by_word.emplace_back((uint32_t)voc->word_id[leaf], i);
+        by_node.emplace_back((uint32_t)nid[i], i);
+    }
+    std::sort(by_word.begin(), by_word.end());
+    std::sort(by_node.begin(), by_node.end());
+    int k = 0;
+    for (size_t i = 0; i < by_word.size();) {
+        const uint32_t id = by_word[i].first;
+        const double w = voc->weight[leaf_node[by_word[i].second]];
+        double acc = w; // addWeight: v[id] = w, then += w per further feature; addIfNotExist: w once
+        size_t e = i + 1;
+        for (; e < by_word.size() && by_word[e].first == id; ++e)
+            if (tf) acc += w;
+        bow_id[k] = (int32_t)id; bow_val[k] = acc; ++k;
+        i = e;
+    }
+    const bool must = voc->scoring != 5, l2 = voc->scoring == 1; // ScoringObject.h: DOT_PRODUCT does not normalise, L2_NORM uses L2
+    if (tf && k > 0 && !must) {
+        const double nd = (double)k;
+        for (int i = 0; i < k; ++i) bow_val[i] /= nd;
+    }
+    if (must) {
+        double norm = 0.0;
+        if (!l2) for (int i = 0; i < k; ++i) norm += std::fabs(bow_val[i]);
+        else { for (int i = 0; i < k; ++i) norm += bow_val[i] * bow_val[i]; norm = std::sqrt(norm); }
+        if (norm > 0.0) for (int i = 0; i < k; ++i) bow_val[i] /= norm;
+    }
+    int j = 0, pos = 0;
+    for (size_t i = 0; i < by_node.size(); ++i) {
+        if (i == 0 || by_node[i].first != by_node[i - 1].first) { fv_node[j] = (int32_t)by_node[i].first; fv_start[j] = pos; ++j; }
+        fv_feat[pos++] = by_node[i].second;
+    }
+    if (n > 0) fv_start[j] = pos;
+    *n_words = k; *n_fv_nodes = j;
     return PSLOT_OK;
 }
 

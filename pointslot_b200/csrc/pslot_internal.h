@@ -175,6 +175,9 @@ struct CvBuffers {
 };
 int launch_cvorb(const CvGeom &g, const CvBuffers &b, bool has_mask, cudaStream_t st);
 
+int launch_bow_transform(const uint8_t *node_desc, const int *child_start, const int *child, const uint8_t *feat, int n,
+                         int nid_level, int *leaf_node, int *nid, cudaStream_t st);
+
 typedef pslot_grid_spec GridSpec;
 size_t grid_smem_bytes(const GridSpec &s);
 int launch_assign_grid(const pslot_keypoint *kps, const int *counts, int fixed_n, size_t stride, const GridSpec &s,

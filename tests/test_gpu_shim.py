@@ -27,7 +27,10 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle_mod):
     with open(inp, "wb") as f:
         f.write(struct.pack("<6i3f", W, H, params[0], params[2], params[3], params[4], params[1], bf, fx))
         f.write(L.tobytes()); f.write(R.tobytes())
-    subprocess.check_call([str(SHIM / "test_shim"), str(inp), str(out)])
+    from pointslot_b200.vocab import random_vocabulary
+    voc = random_vocabulary(10, 4, seed=2)
+    voc.to_text(tmp_path / "voc.txt")
+    subprocess.check_call([str(SHIM / "test_shim"), str(inp), str(out), str(tmp_path / "voc.txt")])
     raw = out.read_bytes()
     N, Nr = struct.unpack_from("<2i", raw, 0)
     o = 8
@@ -62,6 +65,12 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle_mod):
     odl = np.frombuffer(raw, np.uint8, 32 * n_ol, o).reshape(n_ol, 32); o += 32 * n_ol
     okr = np.frombuffer(raw, B.KEYPOINT_DTYPE, n_or, o); o += 28 * n_or
     odr = np.frombuffer(raw, np.uint8, 32 * n_or, o).reshape(n_or, 32); o += 32 * n_or
+    n_words, n_fv = struct.unpack_from("<2i", raw, o); o += 8
+    bow = np.frombuffer(raw, np.dtype([("id", "<i4"), ("val", "<f8")]), n_words, o); o += 12 * n_words
+    featvec = []
+    for _ in range(n_fv):
+        node, cnt = struct.unpack_from("<2i", raw, o); o += 8
+        featvec.append((node, np.frombuffer(raw, np.uint32, cnt, o))); o += 4 * cnt
     assert o == len(raw)
 
     O = oracle_mod
@@ -114,3 +123,10 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle_mod):
     for img, k, d in ((L, okl, odl), (R, okr, odr)):
         rk, rd = O.cvorb_detect_and_compute(img, mask)
         assert k.tobytes() == rk.tobytes() and np.array_equal(d, rd) and len(k) > 100
+
+    # Frame::ComputeBoW (Frame.cc:2040-2047) through the drop-in ORBVocabulary (loadFromTextFile + transform)
+    bid, bval, fn, fs, ff = O.bow_vectors(voc, *O.bow_transform(voc, odL, 4))
+    assert np.array_equal(bow["id"], bid) and np.array_equal(bow["val"].view(np.uint64), bval.view(np.uint64)) and n_words > 100
+    assert [f[0] for f in featvec] == fn.tolist()
+    for j, (_, feats) in enumerate(featvec):
+        assert np.array_equal(feats, ff[fs[j]:fs[j + 1]])
