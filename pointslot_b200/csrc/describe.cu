@@ -25,7 +25,13 @@
 
 namespace {
 
-constexpr int DW = 4;           // warps (keypoints) per CTA
+#ifndef DESC_WARPS
+#define DESC_WARPS 4
+#endif
+#ifndef DESC_MIN_BLOCKS
+#define DESC_MIN_BLOCKS (36 / DESC_WARPS)
+#endif
+constexpr int DW = DESC_WARPS;  // warps (keypoints) per CTA
 constexpr int PR = 21;          // raw patch radius
 constexpr int PD = 2 * PR + 1;  // 43
 constexpr int RW = 17;          // raw row stride in words (68 bytes = 4 aligned 16-byte chunks + 1): odd -> conflict-free row-parallel access
@@ -49,7 +55,7 @@ __global__ void k_debug_steer(const float *__restrict__ angle_deg, int n, float 
     if (i < n) steer_coeffs(angle_deg[i], a[i], b[i]);
 }
 
-__global__ void __launch_bounds__(DW * 32, 9) // 56 registers: 9 CTAs per SM measured best (8: 565 us, 9: 552 us, 10: 568 us)
+__global__ void __launch_bounds__(DW * 32, DESC_MIN_BLOCKS) // 56 registers: 9 CTAs per SM measured best (8: 565 us, 9: 552 us, 10: 568 us)
 k_describe(const __grid_constant__ Geom g, const __grid_constant__ PyrPtrs pyr,
            const uint32_t *__restrict__ lkp, const int *__restrict__ lkp_count,
            pslot_keypoint *__restrict__ out_kps, uint8_t *__restrict__ out_desc, int *__restrict__ out_count)

@@ -1,6 +1,6 @@
 // fast.cu — K2: the per-cell FAST loop of ComputeKeyPointsOctTree (reference src/ORBextractor.cc:765-829).
 //
-// One WARP per 30-px cell (4 cells per CTA, no block-level barrier anywhere).  The reference calls
+// One WARP per 30-px cell, one cell per CTA (no block-level barrier anywhere).  The reference calls
 // cv::FAST(cell, iniThFAST, nms=true) and, if that returns nothing, cv::FAST(cell, minThFAST, true) (:809-816).
 // Restated:
 //   raw score R(p) = max over the 16 arcs of 9 ring pixels of min(v - p_k) resp. min(p_k - v), minus 1
@@ -32,9 +32,15 @@
 
 namespace {
 
-constexpr int FW = 4;        // warps (= cells) per CTA
+// One warp per CTA: a cell that needs the minThFAST pass takes ~3.6 x as long as one that does not, and a CTA keeps its
+// shared memory and warp slots until its slowest warp is done - with 4 cells per CTA two thirds of the CTAs held a slow
+// cell and ncu showed 30 % achieved occupancy against 44 % theoretical (827 -> 757 us for 250 images with 1 warp).
+#ifndef FAST_WARPS
+#define FAST_WARPS 1
+#endif
+constexpr int FW = FAST_WARPS; // warps (= cells) per CTA
 #ifndef FAST_MIN_BLOCKS
-#define FAST_MIN_BLOCKS 7
+#define FAST_MIN_BLOCKS (28 / FAST_WARPS)
 #endif
 // A TMA box must start on a 16-byte boundary of the global row, so the box starts at the aligned x below
 // (cell start - 1); the residual 0..15 byte offset is uniform per warp: a whole-word part folded into the
