@@ -484,6 +484,33 @@ class Workload:
         e1.synchronize()
         return reps * 2 * self.P * self.img_bytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
 
+    def h2d_window(self, seconds=0.6):
+        """Upload sub-batch-sized chunks of the pinned images back to back for a fixed wall-clock window, nothing else running
+        on this GPU -> bytes moved.  Started on all ranks behind a barrier, the sum over ranks / window is what the host
+        delivers while EVERY link is busy for the whole window (h2d_only lets a fast rank finish early, after which the
+        slow ranks speed up: the sum of those per-rank rates overstates the concurrent aggregate)."""
+        torch = self.torch
+        if self.hL is None:
+            return None
+        ib, moved = self.img_bytes, 0
+        hL, hR = self.hL.view(-1), self.hR.view(-1)
+        dL, dR = self.dL.view(-1), self.dR.view(-1)
+        with torch.cuda.stream(self.copy_stream):
+            t_end = time.perf_counter() + seconds
+            i, inflight = 0, []
+            while time.perf_counter() < t_end:
+                lo, n = self.subs[i % self.nsub]
+                a, b = lo * ib, (lo + n) * ib
+                dL[a:b].copy_(hL[a:b], non_blocking=True); dR[a:b].copy_(hR[a:b], non_blocking=True)
+                ev = torch.cuda.Event(); ev.record()
+                inflight.append(ev)
+                if len(inflight) > 2:  # two chunks queued behind the running one keep the copy engine busy
+                    inflight.pop(0).synchronize()
+                moved += 2 * n * ib
+                i += 1
+            self.copy_stream.synchronize()
+        return moved
+
     def d2h_bytes_per_step(self):
         o = self.outs[0]
         per = sum(int(np.prod(o[k].shape)) * o[k].dtype.itemsize for k in ("counts", "kps", "desc", "u_right", "depth"))
@@ -685,7 +712,7 @@ def run_ours(args, rank, world, local_rank):
         # The PCIe paths of the GPUs of one box are not equally fast when every GPU uploads at once (tools/h2d_probe.py:
         # GPUs 0-3 of these hosts share about 115 GB/s, GPUs 4-7 get about 55 GB/s each).  End to end the upload is the
         # bottleneck, so the contiguous blocks of the batch are sized by what each GPU's path delivers instead of equally:
-        # first from the concurrent upload-only rates, then corrected once by the step times measured with that split.
+        # first from the concurrent upload-only rates, then corrected by the step times measured with that split.
         # Same total number of pairs per step; no collective on the data path.
         e2e_equal = {"value": None, "ms_per_step": ms_e2e / args.steps}
         wl.barrier()
@@ -694,12 +721,17 @@ def run_ours(args, rank, world, local_rank):
         total_subs = wl.nsub * world
         shard_subs = proportional_shards(total_subs, rates)
         wl.e2e_nsub = shard_subs[rank]
-        t_local, _ = wl.timed(True, 2, 1, local=True)
-        times = wl.gather(t_local)
-        shard_subs = proportional_shards(total_subs, [n / max(t, 1e-6) for n, t in zip(shard_subs, times)])
-        wl.e2e_nsub = shard_subs[rank]
+        # a rank that finishes early leaves its share of the host's bandwidth to the others, so one correction
+        # under-shoots: repeat it a few times (each pass = 2 steps with the current split)
+        for _ in range(3):
+            t_local, _ = wl.timed(True, 2, 1, local=True)
+            times = wl.gather(t_local)
+            shard_subs = proportional_shards(total_subs, [n / max(t, 1e-6) for n, t in zip(shard_subs, times)])
+            wl.e2e_nsub = shard_subs[rank]
         ms_e2e, win3 = wl.timed(True, args.steps, 2)
         win2 = (win2[0], win3[1])
+        t_local, _ = wl.timed(True, 2, 1, local=True)
+        e2e_equal["ms_per_step_by_rank"] = [t / 2 for t in wl.gather(t_local)]
     clocks = sampler.stop([win1, win2]) if rank == 0 else None
 
     # PCIe references for the e2e number: this rank's pinned images uploaded (1) with every rank uploading at the same time
@@ -715,6 +747,16 @@ def run_ours(args, rank, world, local_rank):
         h2d_min, h2d_sum = -float(tmax[1].item()), float(tsum[2].item())
     h2d_alone = wl.h2d_only() if rank == 0 else None
     wl.barrier()
+    # the same ceiling over a COMMON window: every rank uploads for 0.6 s, bytes summed over ranks
+    h2d_win = None
+    if dist is not None and wl.hL is not None:
+        wl.barrier()
+        t0w = time.perf_counter()
+        moved = wl.h2d_window(0.6)
+        dt = time.perf_counter() - t0w
+        wl.barrier()
+        parts = wl.gather(moved / dt / 1e9)
+        h2d_win = {"aggregate_GBps": sum(parts), "GBps_by_rank": parts, "window_s": 0.6}
 
     n0 = int(wl.outs[0]["counts"][0])
     assert 0 < n0 <= wl.K, "bench produced no keypoints"
@@ -827,6 +869,8 @@ def run_ours(args, rank, world, local_rank):
     bytes_per_pair_h2d = 2 * wl.img_bytes
     pcie = {"h2d_GBps_in_run": 2 * e2e_pairs_step_all * wl.img_bytes / world / (ms_e2e / args.steps * 1e-3) / 1e9, "h2d_GBps_alone": h2d_alone,
             "h2d_GBps_all_ranks": {"per_rank_min": h2d_min, "aggregate": h2d_sum},
+            "h2d_GBps_common_window": h2d_win,
+            "e2e_frac_of_common_window_ceiling": (e2e * bytes_per_pair_h2d / (h2d_win["aggregate_GBps"] * 1e9)) if h2d_win else None,
             "e2e_ceiling_pairs_per_s": (h2d_sum * 1e9 / bytes_per_pair_h2d) if h2d_sum else None,
             "e2e_frac_of_ceiling": (e2e * bytes_per_pair_h2d / (h2d_sum * 1e9)) if h2d_sum else None,
             "note": "h2d_GBps_all_ranks: every rank uploads its pinned images at the same time between barriers, no kernels - the "
@@ -846,7 +890,8 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": ms_e2e / args.steps, "pairs_per_step": e2e_pairs_step_all,
                 "partition": {"kind": "equal contiguous blocks" if e2e_equal is None else
                               "contiguous blocks sized by each GPU's measured upload rate (same total; DESIGN.md §6)",
-                              "pairs_per_step_by_rank": [n * wl.Bsz for n in shard_subs]},
+                              "pairs_per_step_by_rank": [n * wl.Bsz for n in shard_subs],
+                              "ms_per_step_by_rank": None if e2e_equal is None else e2e_equal.pop("ms_per_step_by_rank", None)},
                 "equal_shards": e2e_equal, "pcie": pcie,
                 "stage_ms_per_submit": {n: float(v) for n, v in zip(B.StereoBatch.STAGES, e2e_stage_ms)}},
         "gpu_launches": launches_per_submit * nsub * args.steps * world,
