@@ -191,6 +191,19 @@ typedef struct pslot_proj_point {
 int pslot_search_by_projection_last(pslot_orb *ctx, const pslot_proj_point *pts, const uint8_t *pt_desc, int n_pts,
                                     const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n,
                                     int check_orientation, int32_t *match_of_pt, uint8_t *rejected, int *nmatches);
+
+/* Replaces `int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound,
+ * const float th, const int ORBdist)` (reference src/ORBmatcher.cc:2529-2654; relocalisation, called from
+ * Tracking::Relocalization) from the GetFeaturesInArea call on.  The caller keeps the projection lines (:2551-2581) and
+ * passes one pslot_proj_point per pKF->GetMapPointMatches() entry: u, v, radius = th * mvScaleFactors[nPredictedLevel],
+ * min_level / max_level = nPredictedLevel -+ 1, angle = pKF->mvKeysUn[i].angle, flags bit 0 = the point reaches the search
+ * (pMP && !isBad && !sAlreadyFound.count(pMP), inside the image bounds and the distance range); `ur` and flags bit 1 are
+ * ignored.  Differences from the last-frame overload, all the reference's: no stereo test, ANY association blocks a
+ * feature (occupied[idx] = CurrentFrame.mvpMapPoints[idx] != NULL) and so does every match made on the way, acceptance at
+ * bestDist <= orb_dist, rotation bins of 30 degrees (`factor = 1.0f/HISTO_LENGTH`, :2541). */
+int pslot_search_by_projection_kf(pslot_orb *ctx, const pslot_proj_point *pts, const uint8_t *pt_desc, int n_pts,
+                                  const uint8_t *frame_desc, const uint8_t *occupied, int n, int orb_dist,
+                                  int check_orientation, int32_t *match_of_pt, uint8_t *rejected, int *nmatches);
 /* Number of device sweeps the last projection search needed to reproduce the sequential result (>= 2). */
 int pslot_debug_projection_sweeps(const pslot_orb *ctx);
 

@@ -87,6 +87,8 @@ def lib():
                                                C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_float, C.c_float, vp]
         L.orc_search_by_projection_last.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float,
                                                     C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp]
+        L.orc_search_by_projection_kf.argtypes = [vp, vp, C.c_int, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                                                  C.c_int, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
         L.orc_cvorb_detect_and_compute.argtypes = [vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_ssize_t, C.c_int, C.c_float,
                                                    C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, ip]
         L.orc_bow_transform.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
@@ -247,6 +249,21 @@ def search_by_projection_last(kps_un, frame_desc, u_right, cell_start, indices, 
     n = lib().orc_search_by_projection_last(_ptr(kps_un), _ptr(frame_desc), _ptr(u_right), len(kps_un), _ptr(cell_start),
                                             _ptr(indices), min_x, min_y, inv_w, inv_h, cols, rows, _ptr(pts), _ptr(pt_desc),
                                             len(pts), _ptr(occupied), int(check_orientation), _ptr(out), _ptr(rej))
+    return out[:len(pts)].copy(), rej[:len(pts)].copy(), int(n)
+
+
+def search_by_projection_kf(kps_un, frame_desc, cell_start, indices, min_x, min_y, inv_w, inv_h, cols, rows, pts, pt_desc,
+                            occupied, orb_dist, check_orientation=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) after the projection
+    (ORBmatcher.cc:2583-2654) -> (match_of_pt, rejected, nmatches)."""
+    kps_un = np.ascontiguousarray(kps_un, KEYPOINT_DTYPE); frame_desc = np.ascontiguousarray(frame_desc, np.uint8)
+    pts = np.ascontiguousarray(pts, PROJ_POINT_DTYPE)
+    pt_desc = np.ascontiguousarray(pt_desc, np.uint8); occupied = np.ascontiguousarray(occupied, np.uint8)
+    cell_start = np.ascontiguousarray(cell_start, np.int32); indices = np.ascontiguousarray(indices, np.int32)
+    out = np.full(max(len(pts), 1), -1, np.int32); rej = np.zeros(max(len(pts), 1), np.uint8)
+    n = lib().orc_search_by_projection_kf(_ptr(kps_un), _ptr(frame_desc), len(kps_un), _ptr(cell_start), _ptr(indices), min_x,
+                                          min_y, inv_w, inv_h, cols, rows, _ptr(pts), _ptr(pt_desc), len(pts), _ptr(occupied),
+                                          int(orb_dist), int(check_orientation), _ptr(out), _ptr(rej))
     return out[:len(pts)].copy(), rej[:len(pts)].copy(), int(n)
 
 

@@ -1177,6 +1177,81 @@ done:
 }
 
 /* ------------------------------------------------------------------------------------------------------------
+ * ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, const float th,
+ * const int ORBdist) (ORBmatcher.cc:2529-2654, relocalisation) from the point where each key-frame map point has been
+ * projected (:2551-2581 stay with the caller): window search over levels [nPredictedLevel - 1, nPredictedLevel + 1]
+ * (:2583), best unassigned feature (:2593-2609; ANY existing association blocks a feature, and so does every match made
+ * on the way), acceptance at bestDist <= ORBdist (:2611), rotation histogram (:2616-2651).  No stereo check in this
+ * overload.  pts[i]: u, v, radius = th * mvScaleFactors[level], min/max level, angle = pKF->mvKeysUn[i].angle, flags bit
+ * 0 = the point reaches the search (not null / bad / already found, inside the image and the distance range).
+ * ------------------------------------------------------------------------------------------------------------ */
+int orc_search_by_projection_kf(const orc_keypoint *kps_un, const uint8_t *frame_desc, int n, const int *cell_start,
+                                const int *indices, float min_x, float min_y, float inv_w, float inv_h, int cols, int rows,
+                                const orc_proj_point *pts, const uint8_t *pt_desc, int n_pts, const uint8_t *occupied,
+                                int orb_dist, int check_orientation, int *match_of_pt, uint8_t *rejected)
+{
+    enum { HISTO_LENGTH = 30 };
+    int nmatches = 0;
+    const float factor = 1.0f / HISTO_LENGTH; /* :2542 - this overload divides by 30, the last-frame one by 360/30 */
+    uint8_t *blocked = (uint8_t *)malloc((size_t)(n > 0 ? n : 1));
+    int *tmp = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    int *hist = (int *)malloc(sizeof(int) * (size_t)HISTO_LENGTH * (size_t)(n_pts > 0 ? n_pts : 1));
+    int hsize[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; ++i) hsize[i] = 0;
+    for (int i = 0; i < n; ++i) blocked[i] = occupied ? occupied[i] : 0;
+    for (int i = 0; i < n_pts; ++i) {
+        const orc_proj_point *p = &pts[i];
+        match_of_pt[i] = -1;
+        rejected[i] = 0;
+        if (!(p->flags & 1)) continue;
+        const int nc = orc_features_in_area(kps_un, cell_start, indices, min_x, min_y, inv_w, inv_h, cols, rows, p->u, p->v,
+                                            p->radius, p->min_level, p->max_level, n, tmp);
+        if (nc == 0) continue;
+        const uint8_t *dMP = pt_desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int v = 0; v < nc; ++v) {
+            const int i2 = tmp[v];
+            if (blocked[i2]) continue; /* if(CurrentFrame.mvpMapPoints[i2]) continue; (:2596) */
+            const int dist = orc_hamming256(dMP, frame_desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= orb_dist) {
+            match_of_pt[i] = bestIdx2;
+            blocked[bestIdx2] = 1; /* CurrentFrame.mvpMapPoints[bestIdx2] = pMP (:2613) */
+            nmatches++;
+            if (check_orientation) {
+                float rot = p->angle - kps_un[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)round((double)(rot * factor));
+                if (bin == HISTO_LENGTH) bin = 0;
+                if (bin < 0 || bin >= HISTO_LENGTH) { nmatches = -1; goto done; } /* the reference asserts */
+                hist[(size_t)bin * (size_t)n_pts + (size_t)hsize[bin]++] = i;
+            }
+        }
+    }
+    if (check_orientation) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            const int s = hsize[i];
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int j = 0; j < hsize[i]; j++) {
+                    rejected[hist[(size_t)i * (size_t)n_pts + (size_t)j]] = 1;
+                    nmatches--;
+                }
+    }
+done:
+    free(blocked); free(tmp); free(hist);
+    return nmatches;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
  * cv::ORB::create(nfeatures, 1.2f, nlevels, edgeThreshold)->detectAndCompute(image, mask) — the second extractor of
  * PointSLOT (reference src/Frame.cc:2623-2627).  The algorithm is OpenCV's
  * (modules/features2d/src/orb.cpp: ORB_Impl::detectAndCompute, computeKeyPoints, HarrisResponses, ICAngles,

@@ -138,6 +138,14 @@ int orc_search_by_projection_last(const orc_keypoint *kps_un, const uint8_t *fra
                                   int n_pts, const uint8_t *occupied, int check_orientation, int *match_of_pt,
                                   uint8_t *rejected);
 
+/* the rest of ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:2583-2654,
+ * relocalisation): no stereo check, any association blocks a feature, acceptance at orb_dist, rotation bins of 30 degrees;
+ * pts[i].ur is ignored */
+int orc_search_by_projection_kf(const orc_keypoint *kps_un, const uint8_t *frame_desc, int n, const int *cell_start,
+                                const int *indices, float min_x, float min_y, float inv_w, float inv_h, int cols, int rows,
+                                const orc_proj_point *pts, const uint8_t *pt_desc, int n_pts, const uint8_t *occupied,
+                                int orb_dist, int check_orientation, int *match_of_pt, uint8_t *rejected);
+
 /* cv::ORB::create(nfeatures, scaleFactor, nlevels, edgeThreshold)->detectAndCompute(image, mask) (reference
  * src/Frame.cc:2623-2627; OpenCV 4.13 orb.cpp), HARRIS score, patch 31, WTA_K 2; mask may be NULL; output ordered by
  * (octave, y, x); returns 0, -1 (bad arguments) or -2 (cap too small) */

@@ -27,6 +27,7 @@ PIECES = [
     ("matcher_fns.inc", "src/ORBmatcher.cc", [
         "int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th)",
         "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)",
+        "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, const float th , const int ORBdist)",
         "float ORBmatcher::RadiusByViewingCos(const float &viewCos)",
         "void ORBmatcher::ComputeThreeMaxima(vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3)",
         "int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)",

@@ -30,7 +30,13 @@ public:
     int nobs_;
     cv::Mat desc_, pos_;
     MapPoint() : mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), mbTrackInView(false), mnTrackScaleLevel(0),
-                 mTrackViewCos(0), bad_(false), nobs_(0) {}
+                 mTrackViewCos(0), bad_(false), nobs_(0), mind_(0), maxd_(0), level_(0) {}
+    // scale prediction state of the relocalisation search (include/MapPoint.h: GetMin/MaxDistanceInvariance, PredictScale)
+    float mind_, maxd_;
+    int level_;
+    float GetMinDistanceInvariance() { return mind_; }
+    float GetMaxDistanceInvariance() { return maxd_; }
+    template <typename F> int PredictScale(const float &, F *) { return level_; }
     bool isBad() { return bad_; }
     int Observations() { return nobs_; }
     cv::Mat GetDescriptor() { return desc_.clone(); }
@@ -65,12 +71,20 @@ public:
     Frame() : mpORBextractorLeft(nullptr), mpORBextractorRight(nullptr), mbf(0), mb(0), N(0) {}
 };
 
+class KeyFrame { // what ORBmatcher::SearchByProjection(CurrentFrame, pKF, ...) reads (include/KeyFrame.h)
+public:
+    std::vector<MapPoint *> GetMapPointMatches() { return mvp_; }
+    std::vector<cv::KeyPoint> mvKeysUn;
+    std::vector<MapPoint *> mvp_;
+};
+
 class ORBmatcher {
 public:
     ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
     static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
     int SearchByProjection(Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th = 3);
     int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono);
+    int SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const std::set<MapPoint *> &sAlreadyFound, const float th, const int ORBdist);
     static const int TH_LOW, TH_HIGH, TH_HIGH_FORDYNAMIC, RADIUS_FORDYNAMIC, HISTO_LENGTH;
     float RadiusByViewingCos(const float &viewCos);
     void ComputeThreeMaxima(std::vector<int> *histo, const int L, int &ind1, int &ind2, int &ind3);

@@ -214,6 +214,13 @@ inline double norm(const Mat &a, const Mat &b, int normType) // NORM_L1 of a dif
     return s;
 }
 
+inline double norm(const Mat &a) // NORM_L2 of a CV_32F matrix: double accumulator, then the square root
+{
+    double s = 0;
+    for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) s += (double)a.at<float>(r, c) * (double)a.at<float>(r, c);
+    return std::sqrt(s);
+}
+
 // InputArray / OutputArray: the extractor calls empty()/getMat() on inputs and create()/release()/getMat() on the output
 class _InputArray {
 public:

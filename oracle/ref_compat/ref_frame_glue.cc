@@ -20,6 +20,7 @@ float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
 } // namespace ORB_SLAM2
 
 using ORB_SLAM2::Frame;
+using ORB_SLAM2::KeyFrame;
 using ORB_SLAM2::MapPoint;
 using ORB_SLAM2::ORBextractor;
 using ORB_SLAM2::ORBmatcher;
@@ -199,4 +200,44 @@ int reff_search_by_projection_last(void *h, const void *last_keys_un, int n_last
     return n;
 }
 
-} // extern "C"
+// ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:2529-2654) with
+// CurrentFrame.mTcw = I: x3Dc == x3Dw and Ow == 0 exactly, so dist3D = |x3Dw|.  kf_flags: bit 0 the key frame holds a map
+// point at i, bit 1 it is bad, bit 2 it is in sAlreadyFound.
+int reff_search_by_projection_kf(void *h, const void *kf_keys_un, int n_kf, const float *world_xyz, const uint8_t *kf_desc,
+                                 const uint8_t *kf_flags, const int *level, const float *min_dist, const float *max_dist,
+                                 float fx, float fy, float cx, float cy, const uint8_t *occupied, float th, int orb_dist,
+                                 int check_orientation, int *slot_of_feature)
+{
+    Frame &C = *static_cast<Frame *>(h);
+    Frame::fx = fx; Frame::fy = fy; Frame::cx = cx; Frame::cy = cy;
+    C.mTcw = cv::Mat::eye(4, 4, CV_32F);
+    KeyFrame K;
+    set_keys(K.mvKeysUn, kf_keys_un, n_kf);
+    vector<MapPoint> store((size_t)n_kf);
+    map<MapPoint *, int> index;
+    set<MapPoint *> found;
+    K.mvp_.assign((size_t)n_kf, nullptr);
+    for (int i = 0; i < n_kf; ++i) {
+        MapPoint &p = store[(size_t)i];
+        p.pos_ = cv::Mat(3, 1, CV_32F);
+        for (int k = 0; k < 3; ++k) p.pos_.at<float>(k) = world_xyz[3 * i + k];
+        p.desc_ = desc_mat(kf_desc + (size_t)i * 32, 1);
+        p.bad_ = (kf_flags[i] & 2) != 0;
+        p.level_ = level[i]; p.mind_ = min_dist[i]; p.maxd_ = max_dist[i];
+        index[&p] = i;
+        if (kf_flags[i] & 1) K.mvp_[(size_t)i] = &p;
+        if (kf_flags[i] & 4) found.insert(&p);
+    }
+    MapPoint held;
+    for (int i = 0; i < C.N; ++i) C.mvpMapPoints[(size_t)i] = occupied && occupied[i] ? &held : nullptr;
+    ORBmatcher m(0.9f, check_orientation != 0);
+    const int n = m.SearchByProjection(C, &K, found, th, orb_dist);
+    for (int i = 0; i < C.N; ++i) {
+        MapPoint *p = C.mvpMapPoints[(size_t)i];
+        slot_of_feature[i] = !p ? -1 : p == &held ? -2 : index[p];
+        C.mvpMapPoints[(size_t)i] = nullptr;
+    }
+    return n;
+}
+
+} // extern "C\"

@@ -97,6 +97,7 @@ def _load(variant: str = "stock"):
     lib.reff_search_by_projection.argtypes = [vp, vp, vp, i32, vp, f32, f32, vp]
     lib.reff_search_by_projection_last.argtypes = [vp, vp, i32, vp, vp, vp, f32, f32, f32, f32, f32, f32, f32, vp, f32,
                                                    i32, i32, vp]
+    lib.reff_search_by_projection_kf.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, f32, i32, i32, vp]
     _state[variant] = dict(lib=lib, cbs=None, primitives=None)
     return lib
 
@@ -214,6 +215,17 @@ class ReferenceFrame:
         occ = np.ascontiguousarray(occupied, np.uint8)
         slot = np.zeros(max(self.n, 1), np.int32)
         n = self._lib.reff_search_by_projection(self._h, _p(mps), _p(mp_desc), len(mps), _p(occ), th, nn_ratio, _p(slot))
+        return n, slot[:self.n]
+
+    def search_by_projection_kf(self, kf_keys_un, world_xyz, kf_desc, kf_flags, level, min_dist, max_dist, fx, fy, cx, cy,
+                                occupied, th, orb_dist, check_orientation):
+        kk = np.ascontiguousarray(kf_keys_un, KEYPOINT_DTYPE); xyz = np.ascontiguousarray(world_xyz, np.float32)
+        kd = np.ascontiguousarray(kf_desc, np.uint8); kf = np.ascontiguousarray(kf_flags, np.uint8)
+        lv = np.ascontiguousarray(level, np.int32); mn = np.ascontiguousarray(min_dist, np.float32)
+        mx = np.ascontiguousarray(max_dist, np.float32); occ = np.ascontiguousarray(occupied, np.uint8)
+        slot = np.zeros(max(self.n, 1), np.int32)
+        n = self._lib.reff_search_by_projection_kf(self._h, _p(kk), len(kk), _p(xyz), _p(kd), _p(kf), _p(lv), _p(mn), _p(mx),
+                                                   fx, fy, cx, cy, _p(occ), th, int(orb_dist), int(check_orientation), _p(slot))
         return n, slot[:self.n]
 
     def search_by_projection_last(self, last_keys_un, world_xyz, last_desc, last_flags, last_tz, fx, fy, cx, cy, mbf, mb,

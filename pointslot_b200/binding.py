@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "pslot_batch_submit", "pslot_batch_submit_color", "pslot_batch_wait", "pslot_batch_kernel_launches", "pslot_batch_device_out",
     "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats", "pslot_batch_stereo_counters",
     "pslot_assign_grid", "pslot_grid_token", "pslot_features_in_area", "pslot_batch_assign_grid",
-    "pslot_search_by_projection", "pslot_search_by_projection_last", "pslot_debug_projection_sweeps",
+    "pslot_search_by_projection", "pslot_search_by_projection_last", "pslot_search_by_projection_kf", "pslot_debug_projection_sweeps",
     "pslot_cvorb_create", "pslot_cvorb_destroy", "pslot_cvorb_detect_and_compute", "pslot_cvorb_debug",
     "pslot_vocab_create", "pslot_vocab_destroy", "pslot_bow_transform", "pslot_bow_vectors",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
@@ -102,6 +102,7 @@ def lib():
                                              C.c_float, vp, C.POINTER(C.c_int)]
     L.pslot_search_by_projection_last.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp,
                                                   C.POINTER(C.c_int)]
+    L.pslot_search_by_projection_kf.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_int)]
     L.pslot_debug_projection_sweeps.argtypes = [vp]
     L.pslot_batch_create.argtypes = [C.POINTER(vp), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, vp]
@@ -427,6 +428,20 @@ def search_by_projection_last(ext: OrbExtractor, pts, pt_desc, frame_desc, u_rig
                                                  None if occ is None else _p(occ), len(u_right), int(check_orientation),
                                                  _p(out), _p(rej), C.byref(nm)))
     return out[:len(pts)].copy(), rej[:len(pts)].copy(), nm.value, lib().pslot_debug_projection_sweeps(ext._h)
+
+
+def search_by_projection_kf(ext: OrbExtractor, pts, pt_desc, frame_desc, occupied, orb_dist, check_orientation=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) after the projection (reference
+    src/ORBmatcher.cc:2583-2654) -> (match_of_pt, rejected, nmatches)."""
+    pts = np.ascontiguousarray(pts, PROJ_POINT_DTYPE); pt_desc = np.ascontiguousarray(pt_desc, np.uint8)
+    frame_desc = np.ascontiguousarray(frame_desc, np.uint8).reshape(-1, 32)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    out = np.full(max(len(pts), 1), -1, np.int32); rej = np.zeros(max(len(pts), 1), np.uint8)
+    nm = C.c_int(0)
+    _check(lib().pslot_search_by_projection_kf(ext._h, _p(pts), _p(pt_desc), len(pts), _p(frame_desc),
+                                               None if occ is None else _p(occ), len(frame_desc), int(orb_dist),
+                                               int(check_orientation), _p(out), _p(rej), C.byref(nm)))
+    return out[:len(pts)].copy(), rej[:len(pts)].copy(), nm.value
 
 
 def stereo_match(ext_l: OrbExtractor, ext_r: OrbExtractor, kL, dL, kR, dR, bf: float, max_d: float, debug=False):

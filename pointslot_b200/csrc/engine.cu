@@ -1555,7 +1555,7 @@ int pslot_features_in_area(pslot_orb *ctx, const pslot_area_query *queries, int 
 // k_search_by_projection until a sweep changes no match (see grid.cu), download match_of_pt.
 static int run_projection(pslot_orb *ctx, const std::vector<ProjPoint> &pts, const uint8_t *pt_desc,
                           const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n, int mode,
-                          float nn_ratio, int32_t *match_of_pt)
+                          float nn_ratio, int32_t *match_of_pt, int th_dist = 100 /* ORBmatcher::TH_HIGH */)
 {
     const int n_pts = (int)pts.size();
     Engine &E = ctx->E;
@@ -1590,7 +1590,7 @@ static int run_projection(pslot_orb *ctx, const std::vector<ProjPoint> &pts, con
     a.kps = ctx->d_gk; a.cell_start = ctx->d_gcs; a.indices = ctx->d_gidx; a.s = ctx->grid_spec;
     a.pts = (const ProjPoint *)(base + o_mp); a.pt_desc = base + o_md; a.n_pts = n_pts;
     a.frame_desc = base + o_fd; a.u_right = (const float *)(base + o_ur); a.occupied = base + o_oc;
-    a.mode = mode; a.nn_ratio = nn_ratio;
+    a.mode = mode; a.nn_ratio = nn_ratio; a.th_dist = th_dist;
     // Sweeps are enqueued four at a time and the host looks at their "changed" flags once per group: a sweep past the
     // fixed point recomputes the same matches, so overshooting is harmless and saves a round trip per sweep.
     const int GROUP = 4;
@@ -1670,6 +1670,40 @@ int pslot_search_by_projection(pslot_orb *ctx, const pslot_map_point *mps, const
     return PSLOT_OK;
 }
 
+static int rotation_check(pslot_orb *ctx, const pslot_proj_point *pts_in, int n_pts, int check_orientation, float factor,
+                          int32_t *match_of_pt, uint8_t *rejected, int *nmatches);
+
+// ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:2529-2654) after the
+// projection: the last-frame machinery without the stereo test, every association (pre-existing or made on the way)
+// blocking a feature, acceptance at ORBdist, 30-degree rotation bins (`factor = 1.0f/HISTO_LENGTH`, :2542)
+int pslot_search_by_projection_kf(pslot_orb *ctx, const pslot_proj_point *pts_in, const uint8_t *pt_desc, int n_pts,
+                                  const uint8_t *frame_desc, const uint8_t *occupied, int n, int orb_dist,
+                                  int check_orientation, int32_t *match_of_pt, uint8_t *rejected, int *nmatches)
+{
+    std::vector<float> no_stereo((size_t)std::max(n, 1), -1.0f); // mvuRight <= 0 everywhere: the stereo test never applies
+    if (int rc = check_projection_frame(ctx, n_pts, pts_in, pt_desc, match_of_pt, frame_desc, no_stereo.data(), n)) return rc;
+    if (n_pts > 0 && !rejected) return fail(PSLOT_ERR_ARG, "rejected is null");
+    if (orb_dist < 0 || orb_dist > 256) return fail(PSLOT_ERR_ARG, "ORBdist must be in [0, 256]");
+    if (nmatches) *nmatches = 0;
+    if (n_pts == 0) return PSLOT_OK;
+    for (int i = 0; i < n_pts; ++i) rejected[i] = 0;
+    if (n == 0) {
+        for (int i = 0; i < n_pts; ++i) match_of_pt[i] = -1;
+        return PSLOT_OK;
+    }
+    std::vector<ProjPoint> pts((size_t)n_pts);
+    for (int i = 0; i < n_pts; ++i) {
+        const pslot_proj_point &q = pts_in[i];
+        ProjPoint &p = pts[i];
+        p = ProjPoint{};
+        p.flags = (q.flags & 1) | 2; // CurrentFrame.mvpMapPoints[bestIdx2] = pMP blocks the feature whatever pMP observes (:2596)
+        p.x = q.u; p.y = q.v; p.xr = 0.f; p.radius = q.radius; p.er_limit = q.radius;
+        p.min_level = q.min_level; p.max_level = q.max_level;
+    }
+    if (int rc = run_projection(ctx, pts, pt_desc, frame_desc, no_stereo.data(), occupied, n, 1, 0.0f, match_of_pt, orb_dist)) return rc;
+    return rotation_check(ctx, pts_in, n_pts, check_orientation, 1.0f / 30 /* (:2542) */, match_of_pt, rejected, nmatches);
+}
+
 int pslot_search_by_projection_last(pslot_orb *ctx, const pslot_proj_point *pts_in, const uint8_t *pt_desc, int n_pts,
                                     const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n,
                                     int check_orientation, int32_t *match_of_pt, uint8_t *rejected, int *nmatches)
@@ -1693,11 +1727,17 @@ int pslot_search_by_projection_last(pslot_orb *ctx, const pslot_proj_point *pts_
         p.min_level = q.min_level; p.max_level = q.max_level;
     }
     if (int rc = run_projection(ctx, pts, pt_desc, frame_desc, u_right, occupied, n, 1, 0.0f, match_of_pt)) return rc;
+    return rotation_check(ctx, pts_in, n_pts, check_orientation, 30 / 360.0f /* factor (:1633) */, match_of_pt, rejected, nmatches);
+}
+
+// rotation consistency of the best-only searches (:1720-1753, :2616-2651), sequential and tiny: on the host
+static int rotation_check(pslot_orb *ctx, const pslot_proj_point *pts_in, int n_pts, int check_orientation, float factor,
+                          int32_t *match_of_pt, uint8_t *rejected, int *nmatches)
+{
     int nm = 0;
     for (int i = 0; i < n_pts; ++i) nm += match_of_pt[i] >= 0;
-    if (check_orientation) { // rotation consistency (:1720-1753), sequential and tiny: on the host
+    if (check_orientation) {
         const int HISTO_LENGTH = 30;
-        const float factor = HISTO_LENGTH / 360.0f;
         std::vector<int> rotHist[HISTO_LENGTH];
         for (int i = 0; i < n_pts; ++i) {
             if (match_of_pt[i] < 0) continue;

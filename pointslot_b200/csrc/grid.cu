@@ -238,8 +238,8 @@ k_search_by_projection(const __grid_constant__ ProjArgs a)
                 }
             }
         }
-        // TH_HIGH = 100; local map only: ratio test against the second best if both are in the same level (:144-147)
-        if (bestDist <= 100 &&
+        // bestDist <= TH_HIGH (or ORBdist); local map only: ratio test against the second best if both are in the same level (:144-147)
+        if (bestDist <= a.th_dist &&
             !(a.mode == 0 && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(a.nn_ratio, (float)bestDist2)))
             match = bestIdx;
     }

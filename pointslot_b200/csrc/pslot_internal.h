@@ -206,8 +206,9 @@ struct ProjArgs {
     const int *match_prev;
     int *match_next;
     int *changed;
-    int mode;       // 0: local map (best + second best, ratio test); 1: last frame (best only)
+    int mode;       // 0: local map (best + second best, ratio test); 1: last frame / key frame (best only)
     float nn_ratio;
+    int th_dist;    // acceptance: bestDist <= th_dist (TH_HIGH = 100, or the relocalisation search's ORBdist)
 };
 int launch_search_by_projection(const ProjArgs &a, cudaStream_t st);
 void launch_debug_steer(const float *angle_deg, int n, float *a, float *b, cudaStream_t st);

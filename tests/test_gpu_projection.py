@@ -71,3 +71,22 @@ def test_search_by_projection_last_vs_oracle(seed, mode, ori, n_feat, B, oracle_
     ref, nref = run_oracle(oracle_mod, c2, 3.0, 0.8)
     got, n2, _ = B.search_by_projection(e, c2["mps"], c2["md"], c2["d"], c2["ur"], c2["occupied"], c2["sf"], 3.0, 0.8)
     assert np.array_equal(got, ref) and n2 == nref
+
+
+@pytest.mark.parametrize("seed,ori,orb_dist,n_feat", [(1, True, 100, 1200), (2, True, 64, 2000), (3, False, 100, 600), (4, True, 30, 1200)])
+def test_search_by_projection_kf_vs_oracle(seed, ori, orb_dist, n_feat, B, oracle_mod):
+    """Relocalisation overload (ORBmatcher.cc:2529-2654): no stereo test, every association blocks, ORBdist acceptance,
+    30-degree rotation bins; the oracle is pinned to the reference's own function (tests/test_oracle_reference.py)."""
+    from test_oracle_projection import make_last_frame_case, COLS, ROWS
+    c = make_last_frame_case(oracle_mod, seed, n_feat=n_feat, mode="neutral")
+    c["pts"]["angle"] = (c["pts"]["angle"] + np.float32(60.0)) % np.float32(360.0)  # off the first 30-degree bin
+    cs, idx = oracle_mod.assign_grid(c["k"], 0.0, 0.0, c["inv_w"], c["inv_h"])
+    rm, rrej, rn = oracle_mod.search_by_projection_kf(c["k"], c["d"], cs, idx, 0.0, 0.0, c["inv_w"], c["inv_h"], COLS, ROWS,
+                                                      c["pts"], c["pd"], c["occupied"], orb_dist, ori)
+    e = B.OrbExtractor(n_feat, 1.2, 8, 20, 7)
+    B.assign_grid(e, c["k"], B.GridSpec.for_image(c["W"], c["H"]))
+    m, rej, n = B.search_by_projection_kf(e, c["pts"], c["pd"], c["d"], c["occupied"], orb_dist, ori)
+    assert np.array_equal(m, rm) and np.array_equal(rej, rrej) and n == rn
+    assert (m >= 0).sum() > 50
+    taken = m[m >= 0]
+    assert len(set(taken.tolist())) == len(taken) and not c["occupied"][taken].any()  # every feature matched at most once

@@ -320,3 +320,63 @@ def test_oracle_equals_reference_search_by_projection_last(oracle_mod):
         assert rn == nm and nm > 100
         assert np.array_equal(rslot, slot)
         assert (not ori) or rej.sum() > 0
+
+
+def test_oracle_equals_reference_search_by_projection_kf(oracle_mod):
+    """Relocalisation overload, ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist)
+    (ORBmatcher.cc:2529-2654), the reference's own function: with CurrentFrame.mTcw = I the projection lines below
+    reproduce its u, v, dist3D bit for bit; the oracle takes the points after them."""
+    ref_path = _ref("stock")
+    fx, fy, cx, cy = F(721.5377), F(721.5377), F(609.5593), F(172.854)
+    for seed, ori, th, orb_dist in ((1, 1, 10.0, 100), (2, 1, 3.0, 64), (3, 0, 10.0, 100), (4, 1, 15.0, 80)):
+        c = _frame_case(oracle_mod, seed, n_feat=700, n_mp=10)
+        rng = np.random.default_rng(3000 + seed)
+        k, d = c["k"], c["d"]
+        n = len(k)
+        n_pts = n + n // 3
+        src = np.concatenate([np.arange(n), rng.integers(0, n, n_pts - n)]); rng.shuffle(src)
+        z = rng.uniform(3, 40, n_pts).astype(F)
+        u0 = k["x"][src] + rng.normal(0, 3.0, n_pts).astype(F); v0 = k["y"][src] + rng.normal(0, 3.0, n_pts).astype(F)
+        far = rng.random(n_pts) < 0.03
+        u0[far] += F(3000)                                         # outside the image bounds
+        xc = ((u0 - cx) * z / fx).astype(F); yc = ((v0 - cy) * z / fy).astype(F)
+        xyz = np.stack([xc, yc, z], axis=1).astype(F)
+        # ---- the reference's lines :2554-2575 in float32, one rounding per operation
+        invzc = (1.0 / z.astype(np.float64)).astype(F)
+        u = ((fx * xc).astype(F) * invzc).astype(F) + cx
+        v = ((fy * yc).astype(F) * invzc).astype(F) + cy
+        dist3d = np.sqrt((xyz.astype(np.float64) ** 2).sum(1)).astype(F)   # cv::norm(PO): double accumulator, PO = x3Dw - 0
+        in_range = rng.random(n_pts) < 0.93
+        mind = np.where(in_range, dist3d * F(0.5), dist3d * F(2.0)).astype(F)
+        maxd = (dist3d * F(3.0)).astype(F)
+        kf = np.zeros(n_pts, ref_path.KEYPOINT_DTYPE)
+        ang = (k["angle"][src] + F(41.0)) % F(360.0)
+        rnd = rng.random(n_pts) < 0.25
+        ang[rnd] = rng.uniform(0, 360, rnd.sum()).astype(F)
+        kf["angle"] = ang
+        level = np.clip(k["octave"][src] + rng.integers(-1, 2, n_pts), 0, 7).astype(np.int32)   # PredictScale's answer
+        has = rng.random(n_pts) < 0.93; bad = rng.random(n_pts) < 0.05; found = rng.random(n_pts) < 0.1
+        kflags = (has * 1 + bad * 2 + found * 4).astype(np.uint8)
+        from test_oracle_projection import _flip_bits
+        pd = _flip_bits(rng, d[src], rng.integers(0, 70, n_pts))
+        pts = np.zeros(n_pts, oracle_mod.PROJ_POINT_DTYPE)
+        pts["u"], pts["v"] = u, v
+        pts["radius"] = (F(th) * c["sf"][level]).astype(F)
+        pts["min_level"], pts["max_level"] = level - 1, level + 1
+        pts["angle"] = kf["angle"]
+        inb = (u >= 0) & (u <= c["W"]) & (v >= 0) & (v <= c["H"])
+        pts["flags"] = (has & ~bad & ~found & inb & ~(dist3d < mind) & ~(dist3d > maxd)) * 1
+        cs, idx = oracle_mod.assign_grid(k, 0.0, 0.0, c["inv_w"], c["inv_h"])
+        m, rej, nm = oracle_mod.search_by_projection_kf(k, d, cs, idx, 0.0, 0.0, c["inv_w"], c["inv_h"], 64, 48, pts, pd,
+                                                       c["occupied"], orb_dist, bool(ori))
+        fr = _ref_frame(ref_path, c)
+        rn, rslot = fr.search_by_projection_kf(kf, xyz, pd, kflags, level, mind, maxd, fx, fy, cx, cy, c["occupied"], th,
+                                               orb_dist, ori)
+        slot = np.where(c["occupied"].astype(bool), -2, -1).astype(np.int32)
+        for i in np.nonzero(m >= 0)[0]:
+            slot[m[i]] = i
+        for i in np.nonzero(rej)[0]:
+            slot[m[i]] = -1
+        assert rn == nm and nm > 100
+        assert np.array_equal(rslot, slot)
+        assert (not ori) or rej.sum() > 0
