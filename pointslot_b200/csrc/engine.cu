@@ -119,6 +119,7 @@ struct Engine {
     ResizeTap *d_taps = nullptr;
     int *d_cell_count = nullptr, *d_cell_prefix = nullptr;
     FastCell *d_fast_cells = nullptr;
+    int *d_fast_work = nullptr; // work counter of the persistent FAST warps
     uint32_t *d_cell_cand = nullptr, *d_qt_keys = nullptr;
     uint16_t *d_qt_nodes = nullptr;
     uint32_t *d_lkp = nullptr;
@@ -145,12 +146,12 @@ struct Engine {
 
     void release()
     {
-        cudaFree(d_pyr); cudaFree(d_taps); cudaFree(d_cell_count); cudaFree(d_cell_prefix); cudaFree(d_fast_cells);
+        cudaFree(d_pyr); cudaFree(d_taps); cudaFree(d_cell_count); cudaFree(d_cell_prefix); cudaFree(d_fast_cells); cudaFree(d_fast_work);
         cudaFree(d_cell_cand); cudaFree(d_qt_keys); cudaFree(d_qt_nodes); cudaFree(d_lkp);
         cudaFree(d_lkp_count); cudaFree(d_out);
         if (h_err) cudaFreeHost(h_err);
         cudaFree(d_uright); cudaFree(d_depth); cudaFree(d_best_dist); cudaFree(d_best_idx); cudaFree(d_sad);
-        d_pyr = nullptr; d_taps = nullptr; d_cell_count = d_cell_prefix = nullptr; d_fast_cells = nullptr; d_cell_cand = d_qt_keys = nullptr;
+        d_pyr = nullptr; d_taps = nullptr; d_cell_count = d_cell_prefix = nullptr; d_fast_cells = nullptr; d_fast_work = nullptr; d_cell_cand = d_qt_keys = nullptr;
         d_qt_nodes = nullptr; d_lkp = nullptr; d_lkp_count = nullptr; h_err = d_err = nullptr; d_out = nullptr;
         d_uright = d_depth = nullptr; d_best_dist = d_best_idx = d_sad = nullptr;
         W = H = S = 0; has_pyramid = false;
@@ -322,6 +323,7 @@ struct Engine {
             std::vector<FastCell> fc((size_t)g.cells_per_slot);
             make_fast_cells(g, fc.data());
             CU(cudaMalloc(&d_fast_cells, sizeof(FastCell) * fc.size()));
+            CU(cudaMalloc(&d_fast_work, sizeof(int)));
             CU(cudaMemcpy(d_fast_cells, fc.data(), sizeof(FastCell) * fc.size(), cudaMemcpyHostToDevice));
         }
         CU(cudaMalloc(&d_cell_cand, 4 * ns * g.cand_per_slot));
@@ -356,7 +358,7 @@ struct Engine {
         if (ev) cudaEventRecord(ev[1], st);
         n += launch_pyramid(g, pyr, pmaps, d_taps, nslots, d_err, st);
         if (ev) cudaEventRecord(ev[2], st);
-        n += launch_fast(g, maps, d_fast_cells, d_cell_count, d_cell_cand, nslots, st);
+        n += launch_fast(g, maps, d_fast_cells, d_cell_count, d_cell_cand, nslots, d_fast_work, st);
         if (ev) cudaEventRecord(ev[3], st);
         n += launch_quadtree(g, d_cell_count, d_cell_cand, d_cell_prefix, d_qt_keys, d_qt_nodes, d_lkp, d_lkp_count,
                              d_err, nslots, st, st_aux, ev_fork, ev_join);

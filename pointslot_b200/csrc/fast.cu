@@ -27,6 +27,8 @@
 // Integer-only, hence bit-exact.  Bound: the integer ALU pipe (ncu: math_pipe_throttle + not_selected stalls; DRAM
 // traffic equals the algorithmic bytes); algorithmic global bytes per launch = S * (sum_l P_l + 8 * n_candidates)
 // (SURVEY.md 8d).
+#include <algorithm>
+
 #include "pslot_internal.h"
 #include "tma.cuh"
 
@@ -215,48 +217,74 @@ __device__ __forceinline__ void score_pass(const uint32_t *tile32, uint32_t *sco
 
 __global__ void __launch_bounds__(FW * 32, FAST_MIN_BLOCKS)
 k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet maps, const uint4 *__restrict__ cells,
-             int *__restrict__ cell_count, uint32_t *__restrict__ cell_cand, int warp_smem_bytes)
+             int *__restrict__ cell_count, uint32_t *__restrict__ cell_cand, int warp_smem_bytes, int *__restrict__ work_counter,
+             int total_work)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[FW];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = blockIdx.y;
-    const int cell = blockIdx.x * FW + warp;
-    if (cell >= g.cells_per_slot) return;
+    // per-warp shared memory: [ TMA tile (box_w x box_h) | score map (same box) | group list ]
+    uint8_t *tile = smem + (size_t)warp * warp_smem_bytes;
+    uint64_t *bar = &bars[warp];
+    if (lane == 0) {
+        tma::mbar_init(bar, 1);
+        tma::fence_barrier_init();
+    }
+    __syncwarp();
+    // Persistent warps: every warp pulls (slot, cell) work items from a global counter until none are left - a cell that
+    // needs the minThFAST pass takes ~3.6 x as long as one that does not, so a static assignment leaves warp slots idle
+    // behind the slow cells, and a CTA per cell pays the block scheduler's turnaround 120 000 times per launch.  The next
+    // item's id and record are fetched while the current cell is processed.
+    uint32_t parity = 0;
+    int id = 0;
+    if (lane == 0) id = atomicAdd(work_counter, 1);
+    id = __shfl_sync(0xffffffffu, id, 0);
+    uint4 rec = make_uint4(0, 0, 0, 0);
+    int slot = 0, cell = 0;
+    if (id < total_work) {
+        slot = id / g.cells_per_slot; cell = id - slot * g.cells_per_slot;
+        rec = __ldg(cells + cell);
+    }
+    while (id < total_work) {
     // the cell's record (make_fast_cells): sub-image [ini, ini + (tw, th)) (:791-806), level, TMA box, candidate slots
-    const uint4 rec = __ldg(cells + cell);
     const int iniX = (int)(rec.x & 0xFFFFu), iniY = (int)(rec.x >> 16);
     const int tw = (int)(rec.y & 0xFFu), th = (int)((rec.y >> 8) & 0xFFu);
     const int l = (int)((rec.y >> 16) & 0xFFu), box_h = (int)(rec.y >> 24);
     const int cand_stride = (int)(rec.w & 0xFFFFu), TS = (int)(rec.w >> 16), TSW = TS >> 2;
+    const uint32_t cand_off = rec.z;
     const int iw = tw - 6, ih = th - 6; // pixels cv::FAST actually tests
-    if (tw == 0) {
-        if (lane == 0) cell_count[(size_t)slot * g.cells_per_slot + cell] = 0;
-        return;
-    }
-
-    // per-warp shared memory: [ TMA tile (box_w x box_h) | score map (same box) | group list ]
-    uint8_t *tile = smem + (size_t)warp * warp_smem_bytes;
+    const int my_slot = slot, my_cell = cell;
     const int box_bytes = TS * box_h;
     uint8_t *score = tile + ((box_bytes + 127) & ~127);
     uint16_t *glist = reinterpret_cast<uint16_t *>(score + ((box_bytes + 127) & ~127)); // <= 16 groups x ih rows
-    uint64_t *bar = &bars[warp];
 
     // ---- stage the cell: one TMA box load (x, y, slot) -> dense shared tile, row stride = box width; a second box
     // far outside the image clears the score map (the TMA unit zero-fills out-of-bounds elements: no store instructions)
     const int xa = (iniX - 1) & ~15;          // 16-byte aligned box origin
     const int sh0 = (iniX - 1) - xa;          // image column iniX-1+b lives at shared byte sh0 + b
     const int wsh = sh0 >> 2;
-    if (lane == 0) {
-        tma::mbar_init(bar, 1);
-        tma::fence_barrier_init();
+    if (lane == 0 && tw != 0) {
+        tma::fence_proxy_async(); // the previous cell's reads of this shared memory are ordered before the TMA writes
         tma::mbar_arrive_expect_tx(bar, 2u * (uint32_t)box_bytes);
-        tma::load_3d(tile, &maps.lv[l], bar, xa, iniY, slot);
-        tma::load_3d(score, &maps.lv[l], bar, xa, 1 << 14, slot);
+        tma::load_3d(tile, &maps.lv[l], bar, xa, iniY, my_slot);
+        tma::load_3d(score, &maps.lv[l], bar, xa, 1 << 14, my_slot);
     }
-    __syncwarp();
-    tma::mbar_wait(bar, 0);
+    // next work item, in flight while this cell is processed
+    int next_id = 0;
+    if (lane == 0) next_id = atomicAdd(work_counter, 1);
+    next_id = __shfl_sync(0xffffffffu, next_id, 0);
+    id = next_id;
+    if (id < total_work) {
+        slot = id / g.cells_per_slot; cell = id - slot * g.cells_per_slot;
+        rec = __ldg(cells + cell);
+    }
+    if (tw == 0) {
+        if (lane == 0) cell_count[(size_t)my_slot * g.cells_per_slot + my_cell] = 0;
+        continue;
+    }
+    tma::mbar_wait(bar, parity);
+    parity ^= 1u;
 
     // tasks: (interior row y, group of 4 pixels gx); G groups per row, G a power of two
     const int gshift = iw <= 32 ? 3 : 4;
@@ -264,7 +292,7 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
     const int ntasks = ih << gshift;
     const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
     uint32_t *score32 = reinterpret_cast<uint32_t *>(score);
-    uint32_t *out = cell_cand + (size_t)slot * g.cand_per_slot + rec.z;
+    uint32_t *out = cell_cand + (size_t)my_slot * g.cand_per_slot + cand_off;
     const int ox = iniX + 3 - PSLOT_MINB, oy = iniY + 3 - PSLOT_MINB; // window-relative (:820-825)
 
     // Phase A = cv::FAST(cell, iniThFAST); phase B = cv::FAST(cell, minThFAST), only if A found nothing (:809-816).
@@ -364,7 +392,9 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
         n = total;
         if (n > 0) break;
     }
-    if (lane == 0) cell_count[(size_t)blockIdx.y * g.cells_per_slot + blockIdx.x * FW + (threadIdx.x >> 5)] = min(n, cand_stride);
+    if (lane == 0) cell_count[(size_t)my_slot * g.cells_per_slot + my_cell] = min(n, cand_stride);
+    __syncwarp(); // every lane is done with the tile, the score map and the list before the next cell's boxes land
+    } // work loop
 }
 
 } // namespace
@@ -394,7 +424,7 @@ void make_fast_cells(const Geom &g, FastCell *out)
 }
 
 int launch_fast(const Geom &g, const TmapSet &maps, const FastCell *cells, int *cell_count, uint32_t *cell_cand, int nslots,
-                cudaStream_t st)
+                int *work_counter, cudaStream_t st)
 {
     int per_warp = 0;
     for (int l = 0; l < g.nlevels; ++l) {
@@ -404,7 +434,17 @@ int launch_fast(const Geom &g, const TmapSet &maps, const FastCell *cells, int *
     }
     const size_t smem = (size_t)per_warp * FW;
     ensure_dyn_smem(k_fast_cells, smem);
-    dim3 grid((g.cells_per_slot + FW - 1) / FW, nslots);
-    k_fast_cells<<<grid, FW * 32, smem, st>>>(g, maps, reinterpret_cast<const uint4 *>(cells), cell_count, cell_cand, per_warp);
+    static int sms = 0; // same device family everywhere in a process
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int total = nslots * g.cells_per_slot;
+    const int resident = sms * FAST_MIN_BLOCKS * FW; // warps the device holds at once
+    const int ctas = (std::min(total, resident) + FW - 1) / FW;
+    cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+    k_fast_cells<<<ctas, FW * 32, smem, st>>>(g, maps, reinterpret_cast<const uint4 *>(cells), cell_count, cell_cand, per_warp,
+                                              work_counter, total);
     return 1;
 }

@@ -116,7 +116,7 @@ struct FastCell {
 static_assert(sizeof(FastCell) == 16, "FastCell is loaded as one uint4");
 void make_fast_cells(const Geom &g, FastCell *out); // out[g.cells_per_slot]
 int launch_fast(const Geom &g, const TmapSet &maps, const FastCell *cells, int *cell_count, uint32_t *cell_cand, int nslots,
-                cudaStream_t st);
+                int *work_counter, cudaStream_t st);
 int launch_quadtree(const Geom &g, const int *cell_count, const uint32_t *cell_cand, int *cell_prefix,
                     uint32_t *qt_keys, uint16_t *qt_nodes, uint32_t *lkp, int *lkp_count, int *err_flag,
                     int nslots, cudaStream_t st, cudaStream_t aux = nullptr, cudaEvent_t ev_fork = nullptr,
