@@ -7,10 +7,10 @@
 // Integer-only, hence bit-exact.  Levels are chained (each from the previous one, :1120), so a batch
 // needs nlevels-1 dependent launches; each launch covers every slot of the batch.
 //
-// Each CTA produces a 128 x 32 output tile.  The source rectangle it needs (about 156 x 40 bytes at scale 1.2) arrives
+// Each CTA produces a 128 x 64 output tile.  The source rectangle it needs (about 156 x 79 bytes at scale 1.2) arrives
 // by ONE TMA box load (cp.async.bulk.tensor.3d: no load / store instructions, no staging registers, out-of-image bytes
-// zero-filled), the 32 row taps are unpacked once into shared memory while the box is in flight, and every thread then
-// produces 2 adjacent columns x 8 rows with a branch-free body: one broadcast LDS.128 for the row tap, two word loads per
+// zero-filled), the 64 row taps are unpacked once into shared memory while the box is in flight, and every thread then
+// produces 2 adjacent columns x 16 consecutive rows: one broadcast LDS.128 for the row tap, two word loads per
 // source row, a PRMT + IDP.2A per row sum, two multiply-highs per pixel.  A warp covers 64 consecutive output columns of
 // one row, so every gather is one conflict-free wavefront whatever the box width.  The finished tile goes back with one
 // TMA box store, which clips at the level's right / bottom edge.  (History: byte gathers, 4 LDS.U8 per pixel, pinned the
@@ -27,9 +27,9 @@ constexpr int TW = PYR_TILE_W; // output tile width
 constexpr int TH = PYR_TILE_H; // output tile height
 constexpr int NT = 256;        // threads per CTA: 64 column pairs x 4 row groups
 constexpr int SRC_W = 208;     // largest source box row in bytes (13 x 16): 128 * 1.45 + 2 + 15 alignment
-constexpr int SRC_H = 52;      // largest source box height: 32 * 1.45 + 2 and slack
+constexpr int SRC_H = (PYR_TILE_H * 29 + 19) / 20 + 6; // largest source box height: tile height * 1.45 + 2 and slack
 
-__global__ void __launch_bounds__(NT, 8)
+__global__ void __launch_bounds__(NT, PYR_TILE_H == 32 ? 8 : PYR_TILE_H == 64 ? 6 : PYR_TILE_H == 96 ? 4 : 3)
 k_resize_level(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap dst_map, int box_w, int box_h,
                int dw, int dh, const ResizeTap *__restrict__ xt, const ResizeTap *__restrict__ yt)
 {
@@ -75,19 +75,34 @@ k_resize_level(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     const uint8_t *p0 = s_src + base;
     __syncthreads();          // s_yt and the barrier initialisation are visible
     tma::mbar_wait(&bar, 0);  // the source box has landed
+    // A thread's 8 output rows are consecutive, and at scale 1.2 five out of six of them start on the source row the
+    // previous one ended on: that row's sums are kept in registers (the test is uniform across the warp, which works on
+    // one output row at a time), 1.2 instead of 2 source rows per output row.
+    uint32_t pa = 0, pb = 0; // (H >> 4) of the previous output row's second source row, columns a and b
+    int prev_off = -1;
 #pragma unroll
     for (int k = 0; k < TH / 4; ++k) {
         const int r = rg * (TH / 4) + k;
         const int4 t = s_yt[r];
-        const uint32_t *w0 = reinterpret_cast<const uint32_t *>(p0 + t.x), *w1 = reinterpret_cast<const uint32_t *>(p0 + t.y);
-        const uint32_t u0 = w0[0], u1 = w0[1], l0 = w1[0], l1 = w1[1];
-        // H = c0 * src[s0] + c1 * src[s1] for both source rows and both columns
-        const uint32_t ha0 = __dp2a_lo(ca, __byte_perm(u0, u1, sela), 0u), ha1 = __dp2a_lo(ca, __byte_perm(l0, l1, sela), 0u);
-        const uint32_t hb0 = __dp2a_lo(cb, __byte_perm(u0, u1, selb), 0u), hb1 = __dp2a_lo(cb, __byte_perm(l0, l1, selb), 0u);
+        uint32_t a0, b0;
+        if (t.x == prev_off) {
+            a0 = pa; b0 = pb;
+        } else {
+            const uint32_t *w0 = reinterpret_cast<const uint32_t *>(p0 + t.x);
+            const uint32_t u0 = w0[0], u1 = w0[1];
+            // H = c0 * src[s0] + c1 * src[s1]
+            a0 = __dp2a_lo(ca, __byte_perm(u0, u1, sela), 0u) >> 4;
+            b0 = __dp2a_lo(cb, __byte_perm(u0, u1, selb), 0u) >> 4;
+        }
+        const uint32_t *w1 = reinterpret_cast<const uint32_t *>(p0 + t.y);
+        const uint32_t l0 = w1[0], l1 = w1[1];
+        const uint32_t a1 = __dp2a_lo(ca, __byte_perm(l0, l1, sela), 0u) >> 4;
+        const uint32_t b1 = __dp2a_lo(cb, __byte_perm(l0, l1, selb), 0u) >> 4;
         // in [0, 255] by construction (coefficients sum to 2048 per axis): no saturation needed
-        const uint32_t va = (__umulhi((uint32_t)t.z, ha0 >> 4) + __umulhi((uint32_t)t.w, ha1 >> 4) + 2u) >> 2;
-        const uint32_t vb = (__umulhi((uint32_t)t.z, hb0 >> 4) + __umulhi((uint32_t)t.w, hb1 >> 4) + 2u) >> 2;
+        const uint32_t va = (__umulhi((uint32_t)t.z, a0) + __umulhi((uint32_t)t.w, a1) + 2u) >> 2;
+        const uint32_t vb = (__umulhi((uint32_t)t.z, b0) + __umulhi((uint32_t)t.w, b1) + 2u) >> 2;
         *reinterpret_cast<uint16_t *>(s_out + r * TW + 2 * cp) = (uint16_t)(va | (vb << 8));
+        pa = a1; pb = b1; prev_off = t.y;
     }
     tma::fence_proxy_async(); // this thread's tile bytes are visible to the TMA unit ...
     __syncthreads();          // ... and so are everybody else's
