@@ -95,14 +95,14 @@ struct StereoArgs {
 struct PyrMaps;
 int launch_pyramid(const Geom &g, const PyrPtrs &pyr, const PyrMaps &maps, const ResizeTap *taps, int nslots, int *err_flag,
                    cudaStream_t st);
-// source box (bytes x rows) that covers every 128 x 32 output tile of a level's resize; the x origin of a tile's box is
+// source box (bytes x rows) that covers every 128 x 64 output tile of a level's resize; the x origin of a tile's box is
 // rounded down to 16 bytes
 void pyramid_src_box(const ResizeTap *xt, int dw, const ResizeTap *yt, int dh, int *box_w, int *box_h);
 #ifndef PYR_TH
 #define PYR_TH 64
 #endif
 constexpr int PYR_TILE_W = 128, PYR_TILE_H = PYR_TH;
-// true when every 128 x 32 output tile of the level's resize fits the kernel's staging buffer (checked on the host so
+// true when every 128 x 64 output tile of the level's resize fits the kernel's staging buffer (checked on the host so
 // that the device-side guard can never fire silently)
 bool pyramid_tiles_fit(const ResizeTap *xt, int dw, const ResizeTap *yt, int dh);
 struct TmapSet;

@@ -10,7 +10,7 @@
 struct TmapSet {
     CUtensorMap lv[PSLOT_MAX_LEVELS]; // level l as a (x, y, slot) u8 tensor, box = FAST cell tile
 };
-// pyramid: level l as the SOURCE of level l + 1 (box = the source rectangle of one 128 x 32 output tile) and as a
+// pyramid: level l as the SOURCE of level l + 1 (box = the source rectangle of one 128 x 64 output tile) and as a
 // DESTINATION (box = one output tile)
 struct PyrMaps {
     CUtensorMap src[PSLOT_MAX_LEVELS], dst[PSLOT_MAX_LEVELS];
