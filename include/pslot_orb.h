@@ -200,7 +200,12 @@ int pslot_search_by_projection_last(pslot_orb *ctx, const pslot_proj_point *pts,
  * (pMP && !isBad && !sAlreadyFound.count(pMP), inside the image bounds and the distance range); `ur` and flags bit 1 are
  * ignored.  Differences from the last-frame overload, all the reference's: no stereo test, ANY association blocks a
  * feature (occupied[idx] = CurrentFrame.mvpMapPoints[idx] != NULL) and so does every match made on the way, acceptance at
- * bestDist <= orb_dist, rotation bins of 30 degrees (`factor = 1.0f/HISTO_LENGTH`, :2541). */
+ * bestDist <= orb_dist, rotation bins of 30 degrees (`factor = 1.0f/HISTO_LENGTH`, :2541).
+ * The loop-closing overload `SearchByProjection(KeyFrame *pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints,
+ * vector<MapPoint*> &vpMatched, int th)` (:413-527) is the same search on the key frame's gridded keypoints
+ * (KeyFrame::GetFeaturesInArea, src/KeyFrame.cc:665-704, is Frame's lookup without the level arguments) with
+ * min_level / max_level = nPredictedLevel - 1, nPredictedLevel (:499-502), orb_dist = TH_LOW, check_orientation = 0 and
+ * occupied[idx] = vpMatched[idx] != NULL; flags bit 0 = the point passed :438-480. */
 int pslot_search_by_projection_kf(pslot_orb *ctx, const pslot_proj_point *pts, const uint8_t *pt_desc, int n_pts,
                                   const uint8_t *frame_desc, const uint8_t *occupied, int n, int orb_dist,
                                   int check_orientation, int32_t *match_of_pt, uint8_t *rejected, int *nmatches);

@@ -24,10 +24,15 @@ PIECES = [
         "vector<size_t> Frame::GetFeaturesInArea(const float &x, const float  &y, const float  &r, const int minLevel, const int maxLevel) const",
         "bool Frame::PosInGrid(const cv::KeyPoint &kp, int &posX, int &posY)",
     ]),
+    ("keyframe_fns.inc", "src/KeyFrame.cc", [
+        "vector<size_t> KeyFrame::GetFeaturesInArea(const float &x, const float &y, const float &r) const",
+        "bool KeyFrame::IsInImage(const float &x, const float &y) const",
+    ]),
     ("matcher_fns.inc", "src/ORBmatcher.cc", [
         "int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th)",
         "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)",
         "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, const float th , const int ORBdist)",
+        "int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, vector<MapPoint*> &vpMatched, int th)",
         "float ORBmatcher::RadiusByViewingCos(const float &viewCos)",
         "void ORBmatcher::ComputeThreeMaxima(vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3)",
         "int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)",

@@ -41,6 +41,8 @@ public:
     int Observations() { return nobs_; }
     cv::Mat GetDescriptor() { return desc_.clone(); }
     cv::Mat GetWorldPos() { return pos_.clone(); }
+    cv::Mat normal_;
+    cv::Mat GetNormal() { return normal_.clone(); }
 };
 
 class Frame {
@@ -71,11 +73,21 @@ public:
     Frame() : mpORBextractorLeft(nullptr), mpORBextractorRight(nullptr), mbf(0), mb(0), N(0) {}
 };
 
-class KeyFrame { // what ORBmatcher::SearchByProjection(CurrentFrame, pKF, ...) reads (include/KeyFrame.h)
+class KeyFrame { // what the two KeyFrame overloads of ORBmatcher::SearchByProjection read (include/KeyFrame.h)
 public:
     std::vector<MapPoint *> GetMapPointMatches() { return mvp_; }
     std::vector<cv::KeyPoint> mvKeysUn;
     std::vector<MapPoint *> mvp_;
+    // the Sim3 overload (ORBmatcher.cc:413-527): calibration, image bounds, scale factors, the grid and its lookup -
+    // KeyFrame::GetFeaturesInArea / IsInImage are the reference's own bodies (src/KeyFrame.cc:665-709), lifted like the rest
+    float fx, fy, cx, cy;
+    int N, mnGridCols, mnGridRows, mnMinX, mnMinY, mnMaxX, mnMaxY;
+    float mfGridElementWidthInv, mfGridElementHeightInv;
+    std::vector<float> mvScaleFactors;
+    cv::Mat mDescriptors;
+    std::vector<std::vector<std::vector<size_t>>> mGrid;
+    vector<size_t> GetFeaturesInArea(const float &x, const float &y, const float &r) const;
+    bool IsInImage(const float &x, const float &y) const;
 };
 
 class ORBmatcher {
@@ -85,6 +97,7 @@ public:
     int SearchByProjection(Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th = 3);
     int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono);
     int SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const std::set<MapPoint *> &sAlreadyFound, const float th, const int ORBdist);
+    int SearchByProjection(KeyFrame *pKF, cv::Mat Scw, const std::vector<MapPoint *> &vpPoints, std::vector<MapPoint *> &vpMatched, int th);
     static const int TH_LOW, TH_HIGH, TH_HIGH_FORDYNAMIC, RADIUS_FORDYNAMIC, HISTO_LENGTH;
     float RadiusByViewingCos(const float &viewCos);
     void ComputeThreeMaxima(std::vector<int> *histo, const int L, int &ind1, int &ind2, int &ind3);

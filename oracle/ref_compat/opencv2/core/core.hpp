@@ -158,6 +158,12 @@ public:
                 if (type_ == CV_32F) m.at<float>(c, r) = at<float>(r, c); else m.at<uchar>(c, r) = at<uchar>(r, c);
         return m;
     }
+    double dot(const Mat &b) const // cv::Mat::dot on CV_32F: double accumulator
+    {
+        double s = 0;
+        for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) s += (double)at<float>(r, c) * (double)b.at<float>(r, c);
+        return s;
+    }
     uchar *ptr(int r = 0) { return data + (size_t)r * step; }
     const uchar *ptr(int r = 0) const { return data + (size_t)r * step; }
     template <typename T> T *ptr(int r = 0) { return (T *)(data + (size_t)r * step); }
@@ -181,6 +187,12 @@ inline Mat operator*(float s, const Mat &a)
     return m;
 }
 inline Mat operator*(const Mat &a, float s) { return s * a; }
+inline Mat operator/(const Mat &a, float s)
+{
+    Mat m(a.rows, a.cols, CV_32F);
+    for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) m.at<float>(r, c) = a.at<float>(r, c) / s;
+    return m;
+}
 inline Mat operator-(const Mat &a, const Mat &b)
 {
     Mat m(a.rows, a.cols, CV_32F);

@@ -16,6 +16,7 @@ float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv;
 float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
 #include "matcher_consts.inc"
 #include "frame_fns.inc"
+#include "keyframe_fns.inc"
 #include "matcher_fns.inc"
 } // namespace ORB_SLAM2
 
@@ -240,4 +241,51 @@ int reff_search_by_projection_kf(void *h, const void *kf_keys_un, int n_kf, cons
     return n;
 }
 
-} // extern "C\"
+// ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (ORBmatcher.cc:413-527, loop closing): the key frame is
+// built from the stub Frame's keypoints / descriptors / grid (KeyFrame's constructor copies Frame::mGrid, src/KeyFrame.cc).
+// pt_flags bit 1: the point is bad.  pre_matched[idx] = index of the point already held by vpMatched[idx], -2 for some other
+// point, -1 for none; slot_of_feature[idx] = the same encoding afterwards.
+int reff_search_by_projection_sim3(void *h, const float *scw16, const float *world_xyz, const float *normals,
+                                   const uint8_t *pt_desc, const uint8_t *pt_flags, const int *level, const float *min_dist,
+                                   const float *max_dist, int n_pts, float fx, float fy, float cx, float cy,
+                                   const int *pre_matched, int th, int *slot_of_feature)
+{
+    Frame &F = *static_cast<Frame *>(h);
+    KeyFrame K;
+    K.mvKeysUn = F.mvKeysUn; K.N = F.N; K.mDescriptors = F.mDescriptors; K.mvScaleFactors = F.mvScaleFactors;
+    K.fx = fx; K.fy = fy; K.cx = cx; K.cy = cy;
+    K.mnGridCols = FRAME_GRID_COLS; K.mnGridRows = FRAME_GRID_ROWS;
+    K.mnMinX = (int)Frame::mnMinX; K.mnMinY = (int)Frame::mnMinY; K.mnMaxX = (int)Frame::mnMaxX; K.mnMaxY = (int)Frame::mnMaxY;
+    K.mfGridElementWidthInv = Frame::mfGridElementWidthInv; K.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+    K.mGrid.resize(FRAME_GRID_COLS);
+    for (int i = 0; i < FRAME_GRID_COLS; ++i) {
+        K.mGrid[i].resize(FRAME_GRID_ROWS);
+        for (int j = 0; j < FRAME_GRID_ROWS; ++j) K.mGrid[i][j] = F.mGrid[i][j];
+    }
+    cv::Mat Scw(4, 4, CV_32F);
+    for (int i = 0; i < 16; ++i) Scw.at<float>(i / 4, i % 4) = scw16[i];
+    vector<MapPoint> store((size_t)n_pts);
+    vector<MapPoint *> v((size_t)n_pts);
+    map<MapPoint *, int> index;
+    for (int i = 0; i < n_pts; ++i) {
+        MapPoint &p = store[(size_t)i];
+        p.pos_ = cv::Mat(3, 1, CV_32F); p.normal_ = cv::Mat(3, 1, CV_32F);
+        for (int k = 0; k < 3; ++k) { p.pos_.at<float>(k) = world_xyz[3 * i + k]; p.normal_.at<float>(k) = normals[3 * i + k]; }
+        p.desc_ = desc_mat(pt_desc + (size_t)i * 32, 1);
+        p.bad_ = (pt_flags[i] & 2) != 0;
+        p.level_ = level[i]; p.mind_ = min_dist[i]; p.maxd_ = max_dist[i];
+        v[(size_t)i] = &p; index[&p] = i;
+    }
+    MapPoint held;
+    vector<MapPoint *> matched((size_t)F.N, nullptr);
+    for (int i = 0; i < F.N; ++i) matched[(size_t)i] = pre_matched[i] >= 0 ? &store[(size_t)pre_matched[i]] : pre_matched[i] == -2 ? &held : nullptr;
+    ORBmatcher m(0.75f, true);
+    const int n = m.SearchByProjection(&K, Scw, v, matched, th);
+    for (int i = 0; i < F.N; ++i) {
+        MapPoint *p = matched[(size_t)i];
+        slot_of_feature[i] = !p ? -1 : p == &held ? -2 : index[p];
+    }
+    return n;
+}
+
+} // extern "C"

@@ -98,6 +98,7 @@ def _load(variant: str = "stock"):
     lib.reff_search_by_projection_last.argtypes = [vp, vp, i32, vp, vp, vp, f32, f32, f32, f32, f32, f32, f32, vp, f32,
                                                    i32, i32, vp]
     lib.reff_search_by_projection_kf.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, f32, i32, i32, vp]
+    lib.reff_search_by_projection_sim3.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, vp, i32, vp]
     _state[variant] = dict(lib=lib, cbs=None, primitives=None)
     return lib
 
@@ -226,6 +227,18 @@ class ReferenceFrame:
         slot = np.zeros(max(self.n, 1), np.int32)
         n = self._lib.reff_search_by_projection_kf(self._h, _p(kk), len(kk), _p(xyz), _p(kd), _p(kf), _p(lv), _p(mn), _p(mx),
                                                    fx, fy, cx, cy, _p(occ), th, int(orb_dist), int(check_orientation), _p(slot))
+        return n, slot[:self.n]
+
+    def search_by_projection_sim3(self, scw, world_xyz, normals, pt_desc, pt_flags, level, min_dist, max_dist, fx, fy, cx, cy,
+                                  pre_matched, th):
+        S = np.ascontiguousarray(scw, np.float32).reshape(16); xyz = np.ascontiguousarray(world_xyz, np.float32)
+        nr = np.ascontiguousarray(normals, np.float32); pd = np.ascontiguousarray(pt_desc, np.uint8)
+        pf = np.ascontiguousarray(pt_flags, np.uint8); lv = np.ascontiguousarray(level, np.int32)
+        mn = np.ascontiguousarray(min_dist, np.float32); mx = np.ascontiguousarray(max_dist, np.float32)
+        pm = np.ascontiguousarray(pre_matched, np.int32)
+        slot = np.zeros(max(self.n, 1), np.int32)
+        n = self._lib.reff_search_by_projection_sim3(self._h, _p(S), _p(xyz), _p(nr), _p(pd), _p(pf), _p(lv), _p(mn), _p(mx),
+                                                     len(xyz), fx, fy, cx, cy, _p(pm), int(th), _p(slot))
         return n, slot[:self.n]
 
     def search_by_projection_last(self, last_keys_un, world_xyz, last_desc, last_flags, last_tz, fx, fy, cx, cy, mbf, mb,

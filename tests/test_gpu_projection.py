@@ -90,3 +90,18 @@ def test_search_by_projection_kf_vs_oracle(seed, ori, orb_dist, n_feat, B, oracl
     assert (m >= 0).sum() > 50
     taken = m[m >= 0]
     assert len(set(taken.tolist())) == len(taken) and not c["occupied"][taken].any()  # every feature matched at most once
+
+
+def test_search_by_projection_kf_serves_the_sim3_overload(B, oracle_mod):
+    """Loop closing (ORBmatcher.cc:413-527) = the key-frame search with the level window [L - 1, L], TH_LOW = 50, no rotation
+    check, vpMatched as the occupancy (tests/test_oracle_reference.py pins that reading to the reference's own function)."""
+    from test_oracle_projection import make_last_frame_case, COLS, ROWS
+    c = make_last_frame_case(oracle_mod, 7, n_feat=1500, mode="neutral")
+    c["pts"]["max_level"] = c["pts"]["min_level"] + 1
+    cs, idx = oracle_mod.assign_grid(c["k"], 0.0, 0.0, c["inv_w"], c["inv_h"])
+    rm, rrej, rn = oracle_mod.search_by_projection_kf(c["k"], c["d"], cs, idx, 0.0, 0.0, c["inv_w"], c["inv_h"], COLS, ROWS,
+                                                      c["pts"], c["pd"], c["occupied"], 50, False)
+    e = B.OrbExtractor(1500, 1.2, 8, 20, 7)
+    B.assign_grid(e, c["k"], B.GridSpec.for_image(c["W"], c["H"]))
+    m, rej, n = B.search_by_projection_kf(e, c["pts"], c["pd"], c["d"], c["occupied"], 50, False)
+    assert np.array_equal(m, rm) and not rej.any() and n == rn and n > 100

@@ -380,3 +380,71 @@ def test_oracle_equals_reference_search_by_projection_kf(oracle_mod):
         assert rn == nm and nm > 100
         assert np.array_equal(rslot, slot)
         assert (not ori) or rej.sum() > 0
+
+
+def test_oracle_equals_reference_search_by_projection_sim3(oracle_mod):
+    """Loop-closing overload, ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (ORBmatcher.cc:413-527) with
+    KeyFrame::GetFeaturesInArea / IsInImage (KeyFrame.cc:665-709), all the reference's own bodies: after its projection
+    lines it is the key-frame search with the level window [L - 1, L], TH_LOW and no rotation check - which is how
+    pslot_search_by_projection_kf serves it.  Scw = 2 * [I | t]: scw = 2, Rcw = I, tcw = t / 2 exactly."""
+    ref_path = _ref("stock")
+    fx, fy, cx, cy = F(721.5377), F(721.5377), F(609.5593), F(172.854)
+    for seed, th in ((1, 10), (2, 4), (3, 15)):
+        c = _frame_case(oracle_mod, seed, n_feat=700, n_mp=10)
+        rng = np.random.default_rng(4000 + seed)
+        k, d = c["k"], c["d"]
+        n = len(k)
+        n_pts = n + n // 3
+        src = np.concatenate([np.arange(n), rng.integers(0, n, n_pts - n)]); rng.shuffle(src)
+        t2 = np.array([0.8, -0.4, 1.0], F)                          # Scw's translation column
+        tcw = (t2 / F(2.0)).astype(F)
+        z = rng.uniform(3, 40, n_pts).astype(F)
+        z[rng.random(n_pts) < 0.03] *= F(-1)                       # behind the camera
+        u0 = k["x"][src] + rng.normal(0, 3.0, n_pts).astype(F); v0 = k["y"][src] + rng.normal(0, 3.0, n_pts).astype(F)
+        u0[rng.random(n_pts) < 0.03] += F(3000)                    # outside the image
+        pc = np.stack([((u0 - cx) * z / fx), ((v0 - cy) * z / fy), z], axis=1).astype(F)   # intended camera coordinates
+        xyz = (pc - tcw).astype(F)                                  # world coordinates handed to the reference
+        # ---- the reference's lines :445-487 in float32, one rounding per operation
+        p3dc = (xyz + tcw).astype(F)                                # Rcw * p3Dw is exact (Rcw = I), then one float add
+        invz = (F(1.0) / p3dc[:, 2]).astype(F)
+        x = (p3dc[:, 0] * invz).astype(F); y = (p3dc[:, 1] * invz).astype(F)
+        u = ((fx * x).astype(F) + cx).astype(F); v = ((fy * y).astype(F) + cy).astype(F)
+        po = p3dc                                                    # p3Dw - Ow with Ow = -tcw: the same float add
+        dist64 = np.sqrt((po.astype(np.float64) ** 2).sum(1))
+        dist = dist64.astype(F)
+        normals = (po / np.maximum(dist, F(1e-6))[:, None]).astype(F)
+        oblique = rng.random(n_pts) < 0.08
+        normals[oblique] = np.array([1.0, 0.0, 0.0], F)             # viewing angle above 60 degrees for most of these
+        dot = (po.astype(np.float64) * normals.astype(np.float64)).sum(1)
+        in_range = rng.random(n_pts) < 0.93
+        mind = np.where(in_range, dist * F(0.5), dist * F(2.0)).astype(F)
+        maxd = (dist * F(3.0)).astype(F)
+        level = np.clip(k["octave"][src] + rng.integers(0, 2, n_pts), 0, 7).astype(np.int32)
+        bad = rng.random(n_pts) < 0.05
+        pre = np.full(n, -1, np.int32)                              # vpMatched on entry
+        held = rng.random(n) < 0.08
+        pre[held] = -2
+        own = rng.choice(np.nonzero(~held)[0], 30, replace=False)   # 30 features already hold one of the candidate points
+        pre[own] = rng.choice(n_pts, 30, replace=False)
+        already = np.zeros(n_pts, bool); already[pre[own]] = True
+        from test_oracle_projection import _flip_bits
+        pd = _flip_bits(rng, d[src], rng.integers(0, 60, n_pts))
+        pts = np.zeros(n_pts, oracle_mod.PROJ_POINT_DTYPE)
+        pts["u"], pts["v"] = u, v
+        pts["radius"] = (F(th) * c["sf"][level]).astype(F)
+        pts["min_level"], pts["max_level"] = level - 1, level
+        inb = (u >= 0) & (u < c["W"]) & (v >= 0) & (v < c["H"])
+        reach = ~bad & ~already & ~(p3dc[:, 2] < 0) & inb & ~(dist < mind) & ~(dist > maxd) & ~(dot < 0.5 * dist.astype(np.float64))
+        pts["flags"] = reach * 1
+        cs, idx = oracle_mod.assign_grid(k, 0.0, 0.0, c["inv_w"], c["inv_h"])
+        m, rej, nm = oracle_mod.search_by_projection_kf(k, d, cs, idx, 0.0, 0.0, c["inv_w"], c["inv_h"], 64, 48, pts, pd,
+                                                       (pre != -1).astype(np.uint8), 50, False)
+        fr = _ref_frame(ref_path, c)
+        scw = np.array([[2, 0, 0, t2[0]], [0, 2, 0, t2[1]], [0, 0, 2, t2[2]], [0, 0, 0, 1]], F)
+        rn, rslot = fr.search_by_projection_sim3(scw, xyz, normals, pd, (bad * 2).astype(np.uint8), level, mind, maxd, fx, fy,
+                                                 cx, cy, pre, th)
+        slot = pre.copy()
+        for i in np.nonzero(m >= 0)[0]:
+            slot[m[i]] = i
+        assert rn == nm and nm > 60 and not rej.any()
+        assert np.array_equal(rslot, slot)
