@@ -1312,11 +1312,7 @@ static int batch_submit_impl(pslot_batch *b, const uint8_t *left, const uint8_t 
                 upload_end(b);
                 tight = stg;
             }
-            if (((uintptr_t)tight & 3) == 0) {
-                ingest_launches += launch_gray_ingest(tight, (size_t)E.W * E.H, 1, 0, dst, E.W, E.H, L0.pitch, E.pyr.slot_stride[0], npairs, E.st);
-            } else { // unaligned user device pointer: let the copy engine do it
-                CU(cudaMemcpy2DAsync(dst, L0.pitch, tight, E.W, E.W, (size_t)E.H * npairs, cudaMemcpyDeviceToDevice, E.st));
-            }
+            ingest_launches += launch_gray_ingest(tight, (size_t)E.W * E.H, 1, 0, dst, E.W, E.H, L0.pitch, E.pyr.slot_stride[0], npairs, E.st);
         } else if (image_stride == pitch * E.H) {
             CU(cudaMemcpy2DAsync(dst, L0.pitch, views[v], pitch, E.W, (size_t)E.H * npairs, kind, E.st));
         } else {
