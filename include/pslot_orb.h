@@ -170,6 +170,18 @@ int pslot_search_by_projection(pslot_orb *ctx, const pslot_map_point *mps, const
                                const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n,
                                const float *scale_factors, int nlevels, float th, float nn_ratio,
                                int32_t *match_of_mp, int *nmatches);
+
+/* Replaces `int ORBmatcher::SearchByProjection(Frame &F, const size_t &nOrder, const vector<MapObjectPoint*> &vpMapPoints,
+ * const float th)` (reference src/ORBmatcher.cc:157-246): the same search over ONE detected object's feature set.  Grid
+ * that set first - pslot_assign_grid on F.mvObjKeysUn[nOrder] reproduces F.mvObjKeysGrid[nOrder], and
+ * Frame::GetObjectFeaturesInArea (src/Frame.cc:1892-1951) is GetFeaturesInArea on it - then pass
+ * F.mvObjPointsDescriptors[nOrder], F.mvuObjKeysRight[nOrder] and occupied[idx] = (F.mvpMapObjectPoints[nOrder][idx] has
+ * observations) || !F.isInBBox(nOrder, keypoint) (:206-211).  The overload's own constants: a fixed 5 px search window
+ * (:179), levels nPredictedLevel - 1 .. + 1, TH_HIGH_FORDYNAMIC = 130 (:236); the stereo test keeps r * scale (:215). */
+int pslot_search_by_projection_obj(pslot_orb *ctx, const pslot_map_point *mps, const uint8_t *mp_desc, int n_mp,
+                                   const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n,
+                                   const float *scale_factors, int nlevels, float th, float nn_ratio,
+                                   int32_t *match_of_mp, int *nmatches);
 /* int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
  * (src/ORBmatcher.cc:1613-1756), called by Tracking::TrackWithMotionModel (src/Tracking.cc:3047, 3053).  The caller
  * keeps the reference's projection lines (:1623-1676: pose algebra on cv::Mat, bounds test, level window) and hands

@@ -85,6 +85,7 @@ def lib():
                                            C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, vp]
         L.orc_search_by_projection.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float,
                                                C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_float, C.c_float, vp]
+        L.orc_search_by_projection_obj.argtypes = L.orc_search_by_projection.argtypes
         L.orc_search_by_projection_last.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float,
                                                     C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp]
         L.orc_search_by_projection_kf.argtypes = [vp, vp, C.c_int, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
@@ -236,6 +237,26 @@ def search_by_projection(kps_un, frame_desc, u_right, cell_start, indices, min_x
 PROJ_POINT_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("radius", "<f4"), ("min_level", "<i4"),
                              ("max_level", "<i4"), ("angle", "<f4"), ("flags", "<i4")])
 
+
+
+def search_by_projection_obj(kps_un, frame_desc, u_right, cell_start, indices, min_x, min_y, inv_w, inv_h, cols, rows,
+                         mps, mp_desc, occupied, scale_factors, th, nn_ratio):
+    """ORBmatcher::SearchByProjection(F, nOrder, vpMapObjectPoints, th) (ORBmatcher.cc:157-246) on one object's feature set
+    (`occupied` also carries !isInBBox) -> (match_of_mp [n_mp], nmatches)."""
+    kps_un = np.ascontiguousarray(kps_un, KEYPOINT_DTYPE); frame_desc = np.ascontiguousarray(frame_desc, np.uint8)
+    u_right = np.ascontiguousarray(u_right, np.float32); mps = np.ascontiguousarray(mps, MAP_POINT_DTYPE)
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8); occupied = np.ascontiguousarray(occupied, np.uint8)
+    cell_start = np.ascontiguousarray(cell_start, np.int32); indices = np.ascontiguousarray(indices, np.int32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    out = np.full(max(len(mps), 1), -1, np.int32)
+    n = lib().orc_search_by_projection_obj(_ptr(kps_un), _ptr(frame_desc), _ptr(u_right), len(kps_un), _ptr(cell_start),
+                                       _ptr(indices), min_x, min_y, inv_w, inv_h, cols, rows, _ptr(mps), _ptr(mp_desc),
+                                       len(mps), _ptr(occupied), _ptr(sf), th, nn_ratio, _ptr(out))
+    return out[:len(mps)].copy(), int(n)
+
+
+PROJ_POINT_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("radius", "<f4"), ("min_level", "<i4"),
+                             ("max_level", "<i4"), ("angle", "<f4"), ("flags", "<i4")])
 
 def search_by_projection_last(kps_un, frame_desc, u_right, cell_start, indices, min_x, min_y, inv_w, inv_h, cols, rows,
                               pts, pt_desc, occupied, check_orientation=True):

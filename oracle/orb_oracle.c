@@ -1044,11 +1044,11 @@ int orc_features_in_area(const orc_keypoint *kps, const int *cell_start, const i
  * plain fields the routine reads; the loop below is the reference's, statement for statement, including its
  * order dependence (a feature taken by an earlier map point with observations is skipped by later ones).
  * ------------------------------------------------------------------------------------------------------------ */
-int orc_search_by_projection(const orc_keypoint *kps_un, const uint8_t *frame_desc, const float *u_right, int n,
+static int search_by_projection_core(const orc_keypoint *kps_un, const uint8_t *frame_desc, const float *u_right, int n,
                              const int *cell_start, const int *indices, float min_x, float min_y, float inv_w,
                              float inv_h, int cols, int rows, const orc_map_point *mps, const uint8_t *mp_desc,
                              int n_mp, const uint8_t *occupied, const float *scale_factors, float th, float nn_ratio,
-                             int *match_of_mp)
+                             int *match_of_mp, float fixed_window, int level_up, int th_dist)
 {
     int nmatches = 0;
     const int bFactor = th != 1.0;
@@ -1062,9 +1062,10 @@ int orc_search_by_projection(const orc_keypoint *kps_un, const uint8_t *frame_de
         const int nPredictedLevel = pMP->level;
         float r = ((double)pMP->view_cos > 0.998) ? 2.5f : 4.0f; /* RadiusByViewingCos (:252-258) */
         if (bFactor) r *= th;
-        const float rad = r * scale_factors[nPredictedLevel];
+        /* window: r * scale (local map, :92) or the literal 5 px of the object-point overload (:179) */
+        const float rad = fixed_window > 0 ? fixed_window : r * scale_factors[nPredictedLevel];
         const int nc = orc_features_in_area(kps_un, cell_start, indices, min_x, min_y, inv_w, inv_h, cols, rows,
-                                            pMP->proj_x, pMP->proj_y, rad, nPredictedLevel - 1, nPredictedLevel, n, tmp);
+                                            pMP->proj_x, pMP->proj_y, rad, nPredictedLevel - 1, nPredictedLevel + level_up, n, tmp);
         if (nc == 0) continue;
         const uint8_t *MPdescriptor = mp_desc + (size_t)iMP * 32;
         int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
@@ -1087,7 +1088,7 @@ int orc_search_by_projection(const orc_keypoint *kps_un, const uint8_t *frame_de
                 bestDist2 = dist;
             }
         }
-        if (bestDist <= 100) { /* TH_HIGH */
+        if (bestDist <= th_dist) { /* TH_HIGH (:142) or TH_HIGH_FORDYNAMIC (:236) */
             if (bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) continue;
             match_of_mp[iMP] = bestIdx; /* F.mvpMapPoints[bestIdx] = pMP (:148) */
             if (pMP->flags & 2) blocked[bestIdx] = 1; /* pMP->Observations() > 0: later map points skip this feature */
@@ -1096,6 +1097,31 @@ int orc_search_by_projection(const orc_keypoint *kps_un, const uint8_t *frame_de
     }
     free(blocked); free(tmp);
     return nmatches;
+}
+
+int orc_search_by_projection(const orc_keypoint *kps_un, const uint8_t *frame_desc, const float *u_right, int n,
+                             const int *cell_start, const int *indices, float min_x, float min_y, float inv_w,
+                             float inv_h, int cols, int rows, const orc_map_point *mps, const uint8_t *mp_desc,
+                             int n_mp, const uint8_t *occupied, const float *scale_factors, float th, float nn_ratio,
+                             int *match_of_mp)
+{
+    return search_by_projection_core(kps_un, frame_desc, u_right, n, cell_start, indices, min_x, min_y, inv_w, inv_h, cols, rows,
+                                     mps, mp_desc, n_mp, occupied, scale_factors, th, nn_ratio, match_of_mp, 0.f, 0, 100);
+}
+
+/* ORBmatcher::SearchByProjection(Frame &F, const size_t &nOrder, const vector<MapObjectPoint*> &vpMapPoints, const float th)
+ * (ORBmatcher.cc:157-246): the local-map search over ONE detected object's own feature set (mvObjKeysUn[nOrder] gridded
+ * in mvObjKeysGrid[nOrder], Frame::GetObjectFeaturesInArea :1892-1951 = GetFeaturesInArea on that set) with a fixed 5 px
+ * window, levels [L - 1, L + 1], TH_HIGH_FORDYNAMIC = 130; the stereo test still uses r * scale.  The caller folds
+ * !isInBBox(keypoint) (:206, Frame.cc:1796-1806) into `occupied`: it is a per-feature filter. */
+int orc_search_by_projection_obj(const orc_keypoint *kps_un, const uint8_t *frame_desc, const float *u_right, int n,
+                                 const int *cell_start, const int *indices, float min_x, float min_y, float inv_w,
+                                 float inv_h, int cols, int rows, const orc_map_point *mps, const uint8_t *mp_desc,
+                                 int n_mp, const uint8_t *occupied, const float *scale_factors, float th, float nn_ratio,
+                                 int *match_of_mp)
+{
+    return search_by_projection_core(kps_un, frame_desc, u_right, n, cell_start, indices, min_x, min_y, inv_w, inv_h, cols, rows,
+                                     mps, mp_desc, n_mp, occupied, scale_factors, th, nn_ratio, match_of_mp, 5.f, 1, 130);
 }
 
 /* ------------------------------------------------------------------------------------------------------------

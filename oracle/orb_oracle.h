@@ -123,6 +123,14 @@ int orc_search_by_projection(const orc_keypoint *kps_un, const uint8_t *frame_de
                              int n_mp, const uint8_t *occupied, const float *scale_factors, float th, float nn_ratio,
                              int *match_of_mp);
 
+/* the object-point overload (ORBmatcher.cc:157-246) on one detected object's feature set: fixed 5 px window, levels
+ * [L - 1, L + 1], TH_HIGH_FORDYNAMIC; `occupied` also carries !isInBBox(keypoint) */
+int orc_search_by_projection_obj(const orc_keypoint *kps_un, const uint8_t *frame_desc, const float *u_right, int n,
+                                 const int *cell_start, const int *indices, float min_x, float min_y, float inv_w,
+                                 float inv_h, int cols, int rows, const orc_map_point *mps, const uint8_t *mp_desc,
+                                 int n_mp, const uint8_t *occupied, const float *scale_factors, float th, float nn_ratio,
+                                 int *match_of_mp);
+
 /* one LastFrame map point after the reference's projection lines (ORBmatcher.cc:1640-1676) */
 typedef struct orc_proj_point {
     float u, v, ur, radius;       /* projection, u - mbf * invzc, th * mvScaleFactors[nLastOctave] */

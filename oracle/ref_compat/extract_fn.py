@@ -23,6 +23,8 @@ PIECES = [
         "void Frame::AssignFeaturesToGrid()",
         "vector<size_t> Frame::GetFeaturesInArea(const float &x, const float  &y, const float  &r, const int minLevel, const int maxLevel) const",
         "bool Frame::PosInGrid(const cv::KeyPoint &kp, int &posX, int &posY)",
+        "vector<size_t> Frame::GetObjectFeaturesInArea(const int& nDetObjOrder, const size_t& nDetObjFeaNum, const float &x, const float  &y, const float  &r, const int minLevel, const int maxLevel) const",
+        "bool Frame::isInBBox(const size_t &nOrder, const float &u, const float &v)",
     ]),
     ("keyframe_fns.inc", "src/KeyFrame.cc", [
         "vector<size_t> KeyFrame::GetFeaturesInArea(const float &x, const float &y, const float &r) const",
@@ -30,6 +32,7 @@ PIECES = [
     ]),
     ("matcher_fns.inc", "src/ORBmatcher.cc", [
         "int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th)",
+        "int ORBmatcher::SearchByProjection(Frame &F, const size_t &nOrder, const vector<MapObjectPoint*> &vpMapPoints, const float th)",
         "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)",
         "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, const float th , const int ORBdist)",
         "int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, vector<MapPoint*> &vpMatched, int th)",

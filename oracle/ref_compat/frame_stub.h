@@ -45,8 +45,20 @@ public:
     cv::Mat GetNormal() { return normal_.clone(); }
 };
 
+typedef MapPoint MapObjectPoint; // include/MapObjectPoint.h: the members the object overload reads are MapPoint's
+struct DetectionObject { cv::Rect mrectBBox; DetectionObject() : mrectBBox(0, 0, 0, 0) {} }; // include/DetectionObject.h:40
+
 class Frame {
 public:
+    // per detected object (include/Frame.h:151-163, 206, 222): the object overload of SearchByProjection reads these
+    std::vector<DetectionObject *> mvDetectionObjects;
+    std::vector<std::vector<cv::KeyPoint>> mvObjKeysUn;
+    std::vector<std::vector<MapObjectPoint *>> mvpMapObjectPoints;
+    vector<cv::Mat> mvObjPointsDescriptors;
+    std::vector<std::vector<float>> mvuObjKeysRight;
+    vector<vector<vector<std::vector<std::size_t>>>> mvObjKeysGrid;
+    vector<size_t> GetObjectFeaturesInArea(const int &nDetObjOrder, const size_t &nDetObjFeaNum, const float &x, const float &y, const float &r, const int minLevel = -1, const int maxLevel = -1) const;
+    bool isInBBox(const size_t &nOrder, const float &u, const float &v);
     void ComputeStereoMatches();
     void ComputeObjStereoMatches();
     void AssignFeaturesToGrid();
@@ -95,6 +107,7 @@ public:
     ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
     static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
     int SearchByProjection(Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th = 3);
+    int SearchByProjection(Frame &F, const size_t &nOrder, const std::vector<MapObjectPoint *> &vpMapPoints, const float th);
     int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono);
     int SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const std::set<MapPoint *> &sAlreadyFound, const float th, const int ORBdist);
     int SearchByProjection(KeyFrame *pKF, cv::Mat Scw, const std::vector<MapPoint *> &vpPoints, std::vector<MapPoint *> &vpMatched, int th);

@@ -288,4 +288,44 @@ int reff_search_by_projection_sim3(void *h, const float *scw16, const float *wor
     return n;
 }
 
+// ORBmatcher::SearchByProjection(F, nOrder, vpMapObjectPoints, th) (ORBmatcher.cc:157-246): the stub Frame's keypoints,
+// descriptors, uRight and grid become detected object 0's feature set (mvObjKeysGrid[0] = the grid the reference's own
+// AssignFeaturesToGrid built); bbox = (x, y, w, h) of the detection.  Encoding of slot_of_feature as above.
+int reff_search_by_projection_obj(void *h, const reff_map_point *mps, const uint8_t *mp_desc, int n_mp, const uint8_t *occupied,
+                                  const int *bbox, float th, float nn_ratio, int *slot_of_feature)
+{
+    Frame &F = *static_cast<Frame *>(h);
+    ORB_SLAM2::DetectionObject det;
+    det.mrectBBox = cv::Rect(bbox[0], bbox[1], bbox[2], bbox[3]);
+    F.mvDetectionObjects.assign(1, &det);
+    F.mvObjKeysUn.assign(1, F.mvKeysUn);
+    F.mvObjPointsDescriptors.assign(1, F.mDescriptors);
+    F.mvuObjKeysRight.assign(1, F.mvuRight);
+    F.mvObjKeysGrid.assign(1, vector<vector<vector<size_t>>>(FRAME_GRID_COLS, vector<vector<size_t>>(FRAME_GRID_ROWS)));
+    for (int i = 0; i < FRAME_GRID_COLS; ++i)
+        for (int j = 0; j < FRAME_GRID_ROWS; ++j) F.mvObjKeysGrid[0][i][j] = F.mGrid[i][j];
+    vector<MapPoint> store((size_t)n_mp);
+    vector<MapPoint *> v((size_t)n_mp);
+    map<MapPoint *, int> index;
+    for (int i = 0; i < n_mp; ++i) {
+        MapPoint &p = store[(size_t)i];
+        p.mTrackProjX = mps[i].proj_x; p.mTrackProjY = mps[i].proj_y; p.mTrackProjXR = mps[i].proj_xr;
+        p.mTrackViewCos = mps[i].view_cos; p.mnTrackScaleLevel = mps[i].level;
+        p.mbTrackInView = (mps[i].flags & 1) != 0; p.bad_ = false; p.nobs_ = (mps[i].flags & 2) ? 1 : 0;
+        p.desc_ = desc_mat(mp_desc + (size_t)i * 32, 1);
+        v[(size_t)i] = &p; index[&p] = i;
+    }
+    MapPoint held; held.nobs_ = 1;
+    F.mvpMapObjectPoints.assign(1, vector<MapPoint *>((size_t)F.N, nullptr));
+    for (int i = 0; i < F.N; ++i) F.mvpMapObjectPoints[0][(size_t)i] = occupied && occupied[i] ? &held : nullptr;
+    ORBmatcher m(nn_ratio, true);
+    const int n = m.SearchByProjection(F, (size_t)0, v, th);
+    for (int i = 0; i < F.N; ++i) {
+        MapPoint *p = F.mvpMapObjectPoints[0][(size_t)i];
+        slot_of_feature[i] = !p ? -1 : p == &held ? -2 : index[p];
+    }
+    F.mvDetectionObjects.clear();
+    return n;
+}
+
 } // extern "C"

@@ -98,6 +98,7 @@ def _load(variant: str = "stock"):
     lib.reff_search_by_projection_last.argtypes = [vp, vp, i32, vp, vp, vp, f32, f32, f32, f32, f32, f32, f32, vp, f32,
                                                    i32, i32, vp]
     lib.reff_search_by_projection_kf.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, f32, i32, i32, vp]
+    lib.reff_search_by_projection_obj.argtypes = [vp, vp, vp, i32, vp, vp, f32, f32, vp]
     lib.reff_search_by_projection_sim3.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, vp, i32, vp]
     _state[variant] = dict(lib=lib, cbs=None, primitives=None)
     return lib
@@ -227,6 +228,13 @@ class ReferenceFrame:
         slot = np.zeros(max(self.n, 1), np.int32)
         n = self._lib.reff_search_by_projection_kf(self._h, _p(kk), len(kk), _p(xyz), _p(kd), _p(kf), _p(lv), _p(mn), _p(mx),
                                                    fx, fy, cx, cy, _p(occ), th, int(orb_dist), int(check_orientation), _p(slot))
+        return n, slot[:self.n]
+
+    def search_by_projection_obj(self, mps, mp_desc, occupied, bbox, th, nn_ratio):
+        mps = np.ascontiguousarray(mps); mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+        occ = np.ascontiguousarray(occupied, np.uint8); bb = np.ascontiguousarray(bbox, np.int32)
+        slot = np.zeros(max(self.n, 1), np.int32)
+        n = self._lib.reff_search_by_projection_obj(self._h, _p(mps), _p(mp_desc), len(mps), _p(occ), _p(bb), th, nn_ratio, _p(slot))
         return n, slot[:self.n]
 
     def search_by_projection_sim3(self, scw, world_xyz, normals, pt_desc, pt_flags, level, min_dist, max_dist, fx, fy, cx, cy,

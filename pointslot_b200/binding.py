@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "pslot_batch_submit", "pslot_batch_submit_color", "pslot_batch_wait", "pslot_batch_kernel_launches", "pslot_batch_device_out",
     "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats", "pslot_batch_stereo_counters",
     "pslot_assign_grid", "pslot_grid_token", "pslot_features_in_area", "pslot_batch_assign_grid",
-    "pslot_search_by_projection", "pslot_search_by_projection_last", "pslot_search_by_projection_kf", "pslot_debug_projection_sweeps",
+    "pslot_search_by_projection", "pslot_search_by_projection_obj", "pslot_search_by_projection_last", "pslot_search_by_projection_kf", "pslot_debug_projection_sweeps",
     "pslot_cvorb_create", "pslot_cvorb_destroy", "pslot_cvorb_detect_and_compute", "pslot_cvorb_debug",
     "pslot_vocab_create", "pslot_vocab_destroy", "pslot_bow_transform", "pslot_bow_vectors",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
@@ -100,6 +100,7 @@ def lib():
     L.pslot_batch_assign_grid.argtypes = [vp, C.POINTER(GridSpec), vp, vp]
     L.pslot_search_by_projection.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, C.c_float,
                                              C.c_float, vp, C.POINTER(C.c_int)]
+    L.pslot_search_by_projection_obj.argtypes = L.pslot_search_by_projection.argtypes
     L.pslot_search_by_projection_last.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp,
                                                   C.POINTER(C.c_int)]
     L.pslot_search_by_projection_kf.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_int)]
@@ -415,6 +416,23 @@ def search_by_projection(ext: OrbExtractor, mps, mp_desc, frame_desc, u_right, o
                                             _p(out), C.byref(nm)))
     return out[:len(mps)].copy(), nm.value, lib().pslot_debug_projection_sweeps(ext._h)
 
+
+
+def search_by_projection_obj(ext: OrbExtractor, mps, mp_desc, frame_desc, u_right, occupied, scale_factors, th: float,
+                         nn_ratio: float):
+    """ORBmatcher::SearchByProjection(F, nOrder, vpMapObjectPoints, th) (reference src/ORBmatcher.cc:157-246) against the
+    object feature set last passed to assign_grid on `ext` -> (match_of_mp [n_mp] feature index or -1,
+    nmatches, device sweeps)."""
+    mps = np.ascontiguousarray(mps, MAP_POINT_DTYPE); mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+    frame_desc = np.ascontiguousarray(frame_desc, np.uint8); u_right = np.ascontiguousarray(u_right, np.float32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    out = np.full(max(len(mps), 1), -1, np.int32)
+    nm = C.c_int(0)
+    _check(lib().pslot_search_by_projection_obj(ext._h, _p(mps), _p(mp_desc), len(mps), _p(frame_desc), _p(u_right),
+                                            None if occ is None else _p(occ), len(u_right), _p(sf), len(sf), th, nn_ratio,
+                                            _p(out), C.byref(nm)))
+    return out[:len(mps)].copy(), nm.value, lib().pslot_debug_projection_sweeps(ext._h)
 
 def search_by_projection_last(ext: OrbExtractor, pts, pt_desc, frame_desc, u_right, occupied, check_orientation=True):
     """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) after the projection (reference

@@ -1630,10 +1630,35 @@ static int check_projection_frame(pslot_orb *ctx, int n_pts, const void *pts, co
     return PSLOT_OK;
 }
 
+static int search_by_projection_impl(pslot_orb *ctx, const pslot_map_point *mps, const uint8_t *mp_desc, int n_mp,
+                                     const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n,
+                                     const float *scale_factors, int nlevels, float th, float nn_ratio,
+                                     int32_t *match_of_mp, int *nmatches, float fixed_window, int level_up, int th_dist);
+
 int pslot_search_by_projection(pslot_orb *ctx, const pslot_map_point *mps, const uint8_t *mp_desc, int n_mp,
                                const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n,
                                const float *scale_factors, int nlevels, float th, float nn_ratio,
                                int32_t *match_of_mp, int *nmatches)
+{
+    return search_by_projection_impl(ctx, mps, mp_desc, n_mp, frame_desc, u_right, occupied, n, scale_factors, nlevels, th,
+                                     nn_ratio, match_of_mp, nmatches, 0.f, 0, 100 /* TH_HIGH */);
+}
+
+// ORBmatcher::SearchByProjection(F, nOrder, vpMapObjectPoints, th) (ORBmatcher.cc:157-246): the local-map search over one
+// detected object's own gridded feature set, with a fixed 5 px window, levels [L - 1, L + 1] and TH_HIGH_FORDYNAMIC
+int pslot_search_by_projection_obj(pslot_orb *ctx, const pslot_map_point *mps, const uint8_t *mp_desc, int n_mp,
+                                   const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n,
+                                   const float *scale_factors, int nlevels, float th, float nn_ratio,
+                                   int32_t *match_of_mp, int *nmatches)
+{
+    return search_by_projection_impl(ctx, mps, mp_desc, n_mp, frame_desc, u_right, occupied, n, scale_factors, nlevels, th,
+                                     nn_ratio, match_of_mp, nmatches, 5.f, 1, 130 /* TH_HIGH_FORDYNAMIC */);
+}
+
+static int search_by_projection_impl(pslot_orb *ctx, const pslot_map_point *mps, const uint8_t *mp_desc, int n_mp,
+                                     const uint8_t *frame_desc, const float *u_right, const uint8_t *occupied, int n,
+                                     const float *scale_factors, int nlevels, float th, float nn_ratio,
+                                     int32_t *match_of_mp, int *nmatches, float fixed_window, int level_up, int th_dist)
 {
     if (int rc = check_projection_frame(ctx, n_mp, mps, mp_desc, match_of_mp, frame_desc, u_right, n)) return rc;
     if (!scale_factors || nlevels < 1 || nlevels > PSLOT_MAX_LEVELS) return fail(PSLOT_ERR_ARG, "bad scale factor table");
@@ -1651,15 +1676,15 @@ int pslot_search_by_projection(pslot_orb *ctx, const pslot_map_point *mps, const
         float r = ((double)m.view_cos > 0.998) ? 2.5f : 4.0f; // RadiusByViewingCos (:252-258)
         if (th != 1.0f) r *= th;
         p.x = m.proj_x; p.y = m.proj_y; p.xr = m.proj_xr;
-        p.radius = r * scale_factors[m.level];
-        p.er_limit = p.radius;                           // er > r * F.mvScaleFactors[nPredictedLevel] (:118)
-        p.min_level = m.level - 1; p.max_level = m.level; // (:92)
+        p.er_limit = r * scale_factors[m.level];          // er > r * F.mvScaleFactors[nPredictedLevel] (:118, :215)
+        p.radius = fixed_window > 0 ? fixed_window : p.er_limit; // (:92) / the literal 5 px of the object overload (:179)
+        p.min_level = m.level - 1; p.max_level = m.level + level_up; // (:92) / (:179)
     }
     if (n == 0) { // no features: nothing can match
         for (int i = 0; i < n_mp; ++i) match_of_mp[i] = -1;
         return PSLOT_OK;
     }
-    if (int rc = run_projection(ctx, pts, mp_desc, frame_desc, u_right, occupied, n, 0, nn_ratio, match_of_mp)) return rc;
+    if (int rc = run_projection(ctx, pts, mp_desc, frame_desc, u_right, occupied, n, 0, nn_ratio, match_of_mp, th_dist)) return rc;
     if (nmatches) {
         int c = 0;
         for (int i = 0; i < n_mp; ++i) c += match_of_mp[i] >= 0;

@@ -105,3 +105,21 @@ def test_search_by_projection_kf_serves_the_sim3_overload(B, oracle_mod):
     B.assign_grid(e, c["k"], B.GridSpec.for_image(c["W"], c["H"]))
     m, rej, n = B.search_by_projection_kf(e, c["pts"], c["pd"], c["d"], c["occupied"], 50, False)
     assert np.array_equal(m, rm) and not rej.any() and n == rn and n > 100
+
+
+@pytest.mark.parametrize("seed,th,nn", [(1, 1.0, 0.8), (2, 3.0, 0.8), (3, 5.0, 0.6)])
+def test_search_by_projection_obj_vs_oracle(seed, th, nn, B, oracle_mod):
+    """Object-point overload (ORBmatcher.cc:157-246): fixed 5 px window, levels L - 1 .. L + 1, TH_HIGH_FORDYNAMIC, features
+    outside the detection box passed as occupied; oracle pinned to the reference's own functions."""
+    c = make_case(oracle_mod, seed, n_feat=1500, n_mp=1800)
+    k = c["k"]
+    inside = (k["x"] >= c["W"] / 5) & (k["x"] < 4 * c["W"] / 5) & (k["y"] >= c["H"] / 6) & (k["y"] < 5 * c["H"] / 6)
+    occ = (c["occupied"].astype(bool) | ~inside).astype(np.uint8)
+    from test_oracle_projection import COLS, ROWS
+    cs, idx = oracle_mod.assign_grid(k, 0.0, 0.0, c["inv_w"], c["inv_h"])
+    ref, nref = oracle_mod.search_by_projection_obj(k, c["d"], c["ur"], cs, idx, 0.0, 0.0, c["inv_w"], c["inv_h"], COLS, ROWS,
+                                                   c["mps"], c["md"], occ, c["sf"], th, nn)
+    e = B.OrbExtractor(1500, 1.2, 8, 20, 7)
+    B.assign_grid(e, k, B.GridSpec.for_image(c["W"], c["H"]))
+    got, n, _ = B.search_by_projection_obj(e, c["mps"], c["md"], c["d"], c["ur"], occ, c["sf"], th, nn)
+    assert np.array_equal(got, ref) and n == nref and n > 100

@@ -448,3 +448,25 @@ def test_oracle_equals_reference_search_by_projection_sim3(oracle_mod):
             slot[m[i]] = i
         assert rn == nm and nm > 60 and not rej.any()
         assert np.array_equal(rslot, slot)
+
+
+def test_oracle_equals_reference_search_by_projection_obj(oracle_mod):
+    """Object-point overload, ORBmatcher::SearchByProjection(F, nOrder, vpMapObjectPoints, th) (ORBmatcher.cc:157-246) with
+    Frame::GetObjectFeaturesInArea / isInBBox (Frame.cc:1892-1951, 1796-1806), all lifted from the reference: the frame's
+    features stand in for one detected object's feature set; features outside the detection box are passed to the oracle
+    as occupied (the reference tests isInBBox per candidate, :206)."""
+    ref_path = _ref("stock")
+    for seed, th, nn in ((1, 1.0, 0.8), (2, 3.0, 0.8), (3, 5.0, 0.6)):
+        c = _frame_case(oracle_mod, seed, n_feat=800, n_mp=900)
+        k = c["k"]
+        bbox = np.array([c["W"] // 5, c["H"] // 6, 3 * c["W"] // 5, 2 * c["H"] // 3], np.int32)   # x, y, width, height
+        inside = (k["x"] >= bbox[0]) & (k["x"] < bbox[0] + bbox[2]) & (k["y"] >= bbox[1]) & (k["y"] < bbox[1] + bbox[3])
+        cs, idx = oracle_mod.assign_grid(k, 0.0, 0.0, c["inv_w"], c["inv_h"])
+        occ = (c["occupied"].astype(bool) | ~inside).astype(np.uint8)
+        got, n = oracle_mod.search_by_projection_obj(k, c["d"], c["ur"], cs, idx, 0.0, 0.0, c["inv_w"], c["inv_h"], 64, 48,
+                                                    c["mps"], c["md"], occ, c["sf"], th, nn)
+        fr = _ref_frame(ref_path, c)
+        rn, rslot = fr.search_by_projection_obj(c["mps"], c["md"], c["occupied"], bbox, th, nn)
+        assert rn == n and n > 60
+        assert np.array_equal(rslot, _replay_slots(len(k), c["occupied"], got))
+        assert inside[got[got >= 0]].all() and (~inside).sum() > 50
