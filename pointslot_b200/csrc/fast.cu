@@ -215,6 +215,42 @@ __device__ __forceinline__ void score_pass(const uint32_t *tile32, uint32_t *sco
     }
 }
 
+// Phase A with a short list (the usual case: ~6 % of a cell's 256 groups): one lane per PIXEL PAIR instead of per group, so
+// that a list of up to 16 groups fills the warp in one pass of half the length (one extraction + one min/max network per
+// lane).  The second pair of a group is the first pair of the group shifted by two bytes: the shift joins the alignment
+// funnel shift (per-lane amount), the code stays uniform.
+__device__ __forceinline__ void score_pass_pairs(const uint32_t *tile32, uint8_t *score8, int TS, int wsh, int S, int lane,
+                                                 const uint16_t *list, int count, int gshift, int iw)
+{
+    const int TSW = TS >> 2, G1 = (1 << gshift) - 1;
+    for (int j = lane; j < 2 * count; j += 32) {
+        const int t = (int)list[j >> 1], half = j & 1;
+        const int y = t >> gshift, gx = t & G1;
+        const int px = 4 * gx + 2 * half; // first pixel of the pair inside the row of tested pixels
+        if (px >= iw) continue;
+        const int boff = S + 2 * half;    // byte offset of the pair's "pixel 0" from the aligned word
+        const int sh = 8 * (boff & 3);
+        const uint32_t *base = tile32 + (y + 3) * TSW + gx + wsh + (boff >> 2);
+        uint32_t n[7][3];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            const uint32_t *p = base + (r - 3) * TSW;
+            const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3];
+            n[r][0] = __funnelshift_r(w0, w1, sh); n[r][1] = __funnelshift_r(w1, w2, sh); n[r][2] = __funnelshift_r(w2, w3, sh);
+        }
+        uint32_t P[16], m1, m2;
+        ring_pairs<0>(n, P);
+        arc_minmax(P, m1, m2);
+        const uint32_t v01 = pick<0>(n[3]);
+        const uint32_t one = 0x00010001u;
+        const uint32_t r01 = __vimax_s16x2_relu(__vsub2(__vsub2(v01, m1), one), __vsub2(__vsub2(m2, v01), one));
+        uint32_t s2 = __byte_perm(r01, 0u, 0x4420) & 0xFFFFu; // the two scores as adjacent bytes
+        if (px + 1 >= iw) s2 &= 0xFFu;
+        // score map: tested pixel x lives at byte x + 4 of its row
+        *reinterpret_cast<uint16_t *>(score8 + (y + 3) * TS + 4 + px) = (uint16_t)s2;
+    }
+}
+
 __global__ void __launch_bounds__(FW * 32, FAST_MIN_BLOCKS)
 k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet maps, const uint4 *__restrict__ cells,
              int *__restrict__ cell_count, uint32_t *__restrict__ cell_cand, int warp_smem_bytes, int *__restrict__ work_counter,
@@ -314,7 +350,10 @@ k_fast_cells(const __grid_constant__ Geom g, const __grid_constant__ TmapSet map
         // exact scores: listed groups in phase A, every group in phase B (whose writes must not overtake the reads of
         // phase A's maxima test)
         __syncwarp();
-        score_pass(tile32, score32, TSW, wsh, sh0 & 3, lane, list, count, gshift, iw);
+        if (list && (count <= 16 || (count > 32 && count <= 48)))
+            score_pass_pairs(tile32, score, TS, wsh, sh0 & 3, lane, list, count, gshift, iw);
+        else
+            score_pass(tile32, score32, TSW, wsh, sh0 & 3, lane, list, count, gshift, iw);
         __syncwarp();
         if (phase == 1) {
             // B.1: list (raster order) the groups that hold at least one score >= minTh, so that the neighbourhood
