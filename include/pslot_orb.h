@@ -313,6 +313,15 @@ void pslot_cvorb_destroy(pslot_cvorb *ctx);
 int pslot_cvorb_detect_and_compute(pslot_cvorb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch,
                                    const uint8_t *mask, ptrdiff_t mask_pitch, pslot_keypoint *kps, uint8_t *desc32,
                                    int cap, int *n);
+/* Batched form: n_images images of one size through ONE set of launches and one result round trip - the left and the
+ * right view of Frame::ExtractObjORB (reference src/Frame.cc:2648-2651 runs them on two threads), or the object frames
+ * of a whole sequence.  imgs[s] / masks[s] are the s-th image / object mask (`masks` may be NULL, and so may any
+ * masks[s]: that image is searched everywhere); all share w, h and the two pitches.  Results of image s go to
+ * kps[s * cap ..] / desc32[(s * cap) * 32 ..], counts[s] keypoints; each image's result is exactly what the single-image
+ * call returns for it.  PSLOT_ERR_CAPACITY when some counts[s] > cap (counts are filled in: retry with the largest). */
+int pslot_cvorb_detect_and_compute_batch(pslot_cvorb *ctx, int n_images, const uint8_t *const *imgs, int w, int h,
+                                         ptrdiff_t pitch, const uint8_t *const *masks, ptrdiff_t mask_pitch,
+                                         pslot_keypoint *kps, uint8_t *desc32, int cap, int *counts);
 
 /* ---------------------------------------------------------------------------------------------
  * Bag of words (second half).
@@ -343,8 +352,13 @@ int pslot_bow_transform(pslot_vocab *voc, pslot_orb *ctx, const uint8_t *desc32,
 int pslot_bow_vectors(const pslot_vocab *voc, const int32_t *leaf_node, const int32_t *nid, int n, int32_t *bow_id,
                       double *bow_val, int *n_words, int32_t *fv_node, int32_t *fv_start, int32_t *fv_feat, int *n_fv_nodes);
 
-/* Stage accessor of the last pslot_cvorb_detect_and_compute, for the parity tests: what = 0 the pyramid level (w*h bytes,
- * tightly packed), 1 its raw FAST score map (0 where not a corner), 2 the level's candidates after the maxima test, the mask
+/* Host-clock phases of the last (batched) call in ms: [0] uploads enqueued, [1] kernels + downloads enqueued, [2] waiting
+ * for the device, [3] results copied to the caller's arrays. */
+int pslot_cvorb_last_timing(const pslot_cvorb *ctx, double out_ms[4]);
+
+/* Stage accessor of the last pslot_cvorb_detect_and_compute (image 0 of a batch), for the parity tests: what = 0 the pyramid level (w*h bytes,
+ * tightly packed), 1 its raw FAST score map (0 where not a corner, and outside the band [edge-1, dim-edge] that the
+ * border filter and the maxima test can see), 2 the level's candidates after the maxima test, the mask
  * and the border filter (packed u32 y:12 | x:12 | score:8, unordered), 3 the candidates retainBest(2*quota) kept (same
  * packing, unordered; their Harris responses go to `aux`).  *w, *h = level size; *n = entries written. */
 int pslot_cvorb_debug(pslot_cvorb *ctx, int what, int level, void *out, float *aux, size_t cap_bytes, int *w, int *h, int *n);

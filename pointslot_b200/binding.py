@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats", "pslot_batch_stereo_counters",
     "pslot_assign_grid", "pslot_grid_token", "pslot_features_in_area", "pslot_batch_assign_grid",
     "pslot_search_by_projection", "pslot_search_by_projection_obj", "pslot_search_by_projection_last", "pslot_search_by_projection_kf", "pslot_debug_projection_sweeps",
-    "pslot_cvorb_create", "pslot_cvorb_destroy", "pslot_cvorb_detect_and_compute", "pslot_cvorb_debug",
+    "pslot_cvorb_create", "pslot_cvorb_destroy", "pslot_cvorb_detect_and_compute", "pslot_cvorb_detect_and_compute_batch", "pslot_cvorb_last_timing", "pslot_cvorb_debug",
     "pslot_vocab_create", "pslot_vocab_destroy", "pslot_bow_transform", "pslot_bow_vectors",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
 ]
@@ -128,6 +128,9 @@ def lib():
     L.pslot_cvorb_destroy.restype = None
     L.pslot_cvorb_detect_and_compute.argtypes = [vp, vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_ssize_t, vp, vp, C.c_int,
                                                  C.POINTER(C.c_int)]
+    L.pslot_cvorb_detect_and_compute_batch.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_ssize_t, vp, vp,
+                                                       C.c_int, vp]
+    L.pslot_cvorb_last_timing.argtypes = [vp, vp]
     L.pslot_cvorb_debug.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.pslot_vocab_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int]
     L.pslot_vocab_destroy.argtypes = [vp]
@@ -295,6 +298,49 @@ class CvOrb:
                 continue
             _check(rc)
             return kps[:n.value].copy(), desc[:n.value].copy()
+
+
+def _cvorb_batch(self, imgs, masks=None):
+    """pslot_cvorb_detect_and_compute_batch: `imgs` = equally sized u8 images (e.g. the left and right view), `masks` = None
+    or one entry (array or None) per image -> [(keypoints, descriptors)] per image, each exactly the single-image result."""
+    n = len(imgs)
+    if n == 0:
+        return []
+    ims = [np.ascontiguousarray(i, np.uint8) for i in imgs]
+    H, W = ims[0].shape
+    assert all(i.shape == (H, W) for i in ims)
+    ptrs = (C.c_void_p * n)(*[i.ctypes.data for i in ims])
+    ms, mptrs = None, None
+    if masks is not None and any(m is not None for m in masks):
+        ms = [None if m is None else np.ascontiguousarray(m, np.uint8) for m in masks]
+        assert len(ms) == n and all(m is None or m.shape == (H, W) for m in ms)
+        mptrs = (C.c_void_p * n)(*[None if m is None else m.ctypes.data for m in ms])
+    cap = self.cap
+    while True:
+        # the result arrays are kept between calls (fresh pages for every call cost more than the device work of a batch)
+        buf = getattr(self, "_batch_out", None)
+        if buf is None or buf[0].shape[0] < n or buf[0].shape[1] != cap:
+            buf = (np.zeros((n, cap), KEYPOINT_DTYPE), np.zeros((n, cap, 32), np.uint8))
+            self._batch_out = buf
+        kps, desc = buf
+        counts = np.zeros(n, np.int32)
+        rc = lib().pslot_cvorb_detect_and_compute_batch(self._h, n, ptrs, W, H, W, mptrs, W, _p(kps), _p(desc), cap, _p(counts))
+        if rc == -2 and counts.max() > cap:
+            cap = int(counts.max())
+            continue
+        _check(rc)
+        return [(kps[s, :counts[s]].copy(), desc[s, :counts[s]].copy()) for s in range(n)]
+
+
+def _cvorb_timing(self):
+    """Host-clock phases of the last call in ms: uploads enqueued, kernels enqueued, device wait, copy-out."""
+    t = np.zeros(4, np.float64)
+    _check(lib().pslot_cvorb_last_timing(self._h, _p(t)))
+    return t
+
+
+CvOrb.last_timing = _cvorb_timing
+CvOrb.detect_and_compute_batch = _cvorb_batch
 
 
 def _cvorb_stage(self, what: int, level: int):

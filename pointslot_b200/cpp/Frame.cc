@@ -377,12 +377,57 @@ void OpencvORBDetector(cv::Mat im, cv::Mat ObjMask, std::vector<cv::KeyPoint> &k
 
 void Frame::ExtractObjORB(cv::Mat left, cv::Mat right, cv::Mat LeftObjMask, cv::Mat RightObjMask) // (:2646-2663)
 {
+    // The reference runs OpencvORBDetector for the two views on two threads (:2648-2651); here both views go through ONE
+    // batched call (one set of launches, one result round trip).  Views that do not share a size or pitch fall back to
+    // the reference's own two-thread form over the single-image entry point.
     std::vector<cv::KeyPoint> keypoints_1, keypoints_2;
     cv::Mat descriptors_1, descriptors_2;
-    std::thread threadOpencvORBLeft(OpencvORBDetector, left, LeftObjMask, std::ref(keypoints_1), std::ref(descriptors_1));
-    std::thread threadOpencvORBRight(OpencvORBDetector, right, RightObjMask, std::ref(keypoints_2), std::ref(descriptors_2));
-    threadOpencvORBLeft.join();
-    threadOpencvORBRight.join();
+    const bool masks = !LeftObjMask.empty() && !RightObjMask.empty();
+    const bool same = left.cols == right.cols && left.rows == right.rows && left.step == right.step &&
+                      LeftObjMask.empty() == RightObjMask.empty() && (!masks || LeftObjMask.step == RightObjMask.step);
+    if (same) {
+        struct Ctx {
+            pslot_cvorb *h = nullptr;
+            ~Ctx() { pslot_cvorb_destroy(h); }
+        };
+        static thread_local Ctx ctx;
+        if (!ctx.h && pslot_cvorb_create(&ctx.h, 1000, 1.2f, 8, 19, 20, 0) != PSLOT_OK) {
+            std::fprintf(stderr, "pslot ExtractObjORB: %s\n", pslot_last_error());
+            std::abort();
+        }
+        const unsigned char *imgs[2] = {left.data, right.data};
+        const unsigned char *msk[2] = {masks ? LeftObjMask.data : nullptr, masks ? RightObjMask.data : nullptr};
+        int cap = 1000 + 64 * 8 + 256, n[2] = {0, 0};
+        std::vector<pslot_keypoint> k;
+        std::vector<unsigned char> d;
+        for (;;) {
+            k.resize(2 * (size_t)cap);
+            d.resize(2 * (size_t)cap * 32);
+            const int rc = pslot_cvorb_detect_and_compute_batch(ctx.h, 2, imgs, left.cols, left.rows, (ptrdiff_t)left.step,
+                                                                masks ? msk : nullptr, masks ? (ptrdiff_t)LeftObjMask.step : 0,
+                                                                k.data(), d.data(), cap, n);
+            if (rc == PSLOT_ERR_CAPACITY && std::max(n[0], n[1]) > cap) { cap = std::max(n[0], n[1]); continue; }
+            if (rc != PSLOT_OK) {
+                std::fprintf(stderr, "pslot ExtractObjORB: %s\n", pslot_last_error());
+                std::abort();
+            }
+            break;
+        }
+        static_assert(sizeof(cv::KeyPoint) == sizeof(pslot_keypoint), "cv::KeyPoint layout");
+        auto take = [&](int s, std::vector<cv::KeyPoint> &kp, cv::Mat &desc) {
+            kp.resize((size_t)n[s]);
+            if (n[s]) std::memcpy(static_cast<void *>(kp.data()), k.data() + (size_t)s * cap, sizeof(pslot_keypoint) * (size_t)n[s]);
+            desc.create(n[s], 32, CV_8U);
+            for (int i = 0; i < n[s]; ++i) std::memcpy(desc.ptr(i), d.data() + ((size_t)s * cap + i) * 32, 32);
+        };
+        take(0, keypoints_1, descriptors_1);
+        take(1, keypoints_2, descriptors_2);
+    } else {
+        std::thread threadOpencvORBLeft(OpencvORBDetector, left, LeftObjMask, std::ref(keypoints_1), std::ref(descriptors_1));
+        std::thread threadOpencvORBRight(OpencvORBDetector, right, RightObjMask, std::ref(keypoints_2), std::ref(descriptors_2));
+        threadOpencvORBLeft.join();
+        threadOpencvORBRight.join();
+    }
     mvTempObjKeys = keypoints_1;
     mvTempObjKeysRight = keypoints_2;
     mTempObjPointsDescriptors = descriptors_1.clone();

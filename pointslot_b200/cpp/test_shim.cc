@@ -168,6 +168,15 @@ int main(int argc, char **argv)
         }
     frame.ExtractObjORB(imL, imR, maskL, maskR);
     const int nOL = (int)frame.mvTempObjKeys.size(), nOR = (int)frame.mvTempObjKeysRight.size();
+    { // the free function with the reference's name (single-image entry point) gives the batched call's left result
+        std::vector<cv::KeyPoint> kp1;
+        cv::Mat d1;
+        OpencvORBDetector(imL, maskL, kp1, d1);
+        if ((int)kp1.size() != nOL || (nOL && std::memcmp(static_cast<const void *>(kp1.data()), static_cast<const void *>(frame.mvTempObjKeys.data()), sizeof(cv::KeyPoint) * nOL)))
+            return 8;
+        for (int i = 0; i < nOL; ++i)
+            if (std::memcmp(d1.ptr(i), frame.mTempObjPointsDescriptors.ptr(i), 32)) return 8;
+    }
     std::fwrite(&nOL, 4, 1, o); std::fwrite(&nOR, 4, 1, o);
     std::fwrite(frame.mvTempObjKeys.data(), sizeof(cv::KeyPoint), nOL, o);
     for (int i = 0; i < nOL; ++i) std::fwrite(frame.mTempObjPointsDescriptors.ptr(i), 1, 32, o);

@@ -15,10 +15,12 @@
 // Output order: (octave, y, x).  cv::ORB's own order is whatever std::nth_element leaves; the SET and every per-keypoint
 // value are the contract.
 //
-// Kernels (one image per call; every kernel covers all pyramid levels, blockIdx.y/z = level, except the resize chain):
+// Kernels (a call carries S images of one size - "slots", e.g. the left and right view of Frame::ExtractObjORB; every kernel
+// covers all slots and, except the resize chain, all pyramid levels):
 //   k_cv_resize_exact   level l from level l-1 (image and mask)                      HBM stream, tiny
-//   k_cv_fast_score     raw FAST score map of every level (0 where not a corner)     integer ALU
-//   k_cv_nms_collect    strict 3x3 maxima + mask + border -> candidate list + score histogram per level
+//   k_cv_fast_score     raw FAST score map of every level (0 where not a corner): byte-SWAR rejection test per word,
+//                       exact scores of the few survivors on dense warps
+//   k_cv_nms_collect    strict 3x3 maxima + mask + border -> candidate list (one atomic per CTA) + score histogram per level
 //   k_cv_harris         retainBest(2q) threshold from the histogram; Harris response of the survivors
 //   k_cv_select         per level: radix select of the quota-th largest Harris response, ties kept, bitonic sort by (y, x)
 //   k_cv_describe       one warp per keypoint: orientation, float blur of the 43x43 patch, 256 tests
@@ -28,88 +30,172 @@
 namespace {
 
 // ---- pyramid --------------------------------------------------------------------------------------------------------------
-// blockIdx.z = 0: the image, 1: the object mask (same taps; thresholded)
-__global__ void k_cv_resize_exact(const uint8_t *__restrict__ src_img, const uint8_t *__restrict__ src_mask, int sw, int sh,
-                                  int spitch, uint8_t *__restrict__ dst_img, uint8_t *__restrict__ dst_mask, int dw, int dh,
-                                  int dpitch, const int2 *__restrict__ xt, const int2 *__restrict__ yt)
+// thread = 4 adjacent pixels of one output row (one word store; rows are 128-byte aligned and padded, so the word never
+// leaves the row); blockIdx.z = 2 * slot + (0: the image, 1: the object mask (same taps; thresholded)); without masks
+// blockIdx.z = slot
+__global__ void __launch_bounds__(256)
+k_cv_resize_exact(const uint8_t *__restrict__ src_img, const uint8_t *__restrict__ src_mask, int sw, int sh, int spitch,
+                  uint8_t *__restrict__ dst_img, uint8_t *__restrict__ dst_mask, int dw, int dh, int dpitch,
+                  const int2 *__restrict__ xt, const int2 *__restrict__ yt, size_t slot_bytes, int planes)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= dw || y >= dh) return;
-    const bool is_mask = blockIdx.z != 0;
-    const uint8_t *src = is_mask ? src_mask : src_img;
-    const int2 tx = xt[x], ty = yt[y];
-    const int xa = tx.x, xb = min(xa + 1, sw - 1), ax = tx.y;
+    const int x4 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4, y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x4 >= dw || y >= dh) return;
+    const int slot = blockIdx.z / planes;
+    const bool is_mask = blockIdx.z - slot * planes != 0;
+    const uint8_t *src = (is_mask ? src_mask : src_img) + slot * slot_bytes;
+    const int2 ty = yt[y];
     const int ya = ty.x, yb = min(ya + 1, sh - 1), ay = ty.y;
     const uint8_t *r0 = src + (size_t)ya * spitch, *r1 = src + (size_t)yb * spitch;
-    const int H0 = (int)r0[xa] * (256 - ax) + (int)r0[xb] * ax;
-    const int H1 = (int)r1[xa] * (256 - ax) + (int)r1[xb] * ax;
-    int v = (H0 * (256 - ay) + H1 * ay + (1 << 15)) >> 16;
-    if (is_mask) v = v > 254 ? v : 0; // cv::threshold(mask, mask, 254, 0, THRESH_TOZERO)
-    (is_mask ? dst_mask : dst_img)[(size_t)y * dpitch + x] = (uint8_t)v;
+    uint32_t out = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const int2 tx = xt[min(x4 + b, dw - 1)];
+        const int xa = tx.x, xb = min(xa + 1, sw - 1), ax = tx.y;
+        const int H0 = (int)r0[xa] * (256 - ax) + (int)r0[xb] * ax;
+        const int H1 = (int)r1[xa] * (256 - ax) + (int)r1[xb] * ax;
+        int v = (H0 * (256 - ay) + H1 * ay + (1 << 15)) >> 16;
+        if (is_mask) v = v > 254 ? v : 0; // cv::threshold(mask, mask, 254, 0, THRESH_TOZERO)
+        if (x4 + b < dw) out |= (uint32_t)v << (8 * b);
+    }
+    *reinterpret_cast<uint32_t *>((is_mask ? dst_mask : dst_img) + slot * slot_bytes + (size_t)y * dpitch + x4) = out;
 }
 
 // ---- FAST score map ---------------------------------------------------------------------------------------------------------
 // R = max(max_k min_{j=k..k+8} (v - p_j), max_k min_{j=k..k+8} (p_j - v)) - 1; corner at threshold t <=> R >= t
-// (cv::FAST 9-16, cornerScore<16>).  Only pixels >= 3 px inside the level are tested.
+// (cv::FAST 9-16, cornerScore<16>).  cv::FAST tests every pixel >= 3 px inside the level, but the
+// border filter keeps only [edge, dim - edge) and the maxima test looks one pixel further, so only the band
+// [edge - 1, dim - edge] of rows and columns is scored; everything else keeps the 0 the buffer was cleared to.
+//
+// Tile = 128 px x 8 rows, one thread per aligned 4-pixel word.  Pass 1: byte-SWAR rejection test (a 9-arc holds one pixel
+// of every opposite pair, so both compass pairs need a member farther than t from the centre) on the word and its four
+// compass words; the word's scores are cleared and the few pixels that pass go to a shared list.  Pass 2: the listed
+// pixels, one per thread on dense warps, get the exact score.  blockIdx.x numbers the tiles of all levels, blockIdx.y = slot.
+template <bool NMS>
+__device__ __forceinline__ int tile_level(const CvGeom &g, int tile)
+{
+    int l = 0;
+    while (l + 1 < g.nlevels && tile >= (NMS ? g.lv[l + 1].nms_tile_base : g.lv[l + 1].tile_base)) ++l;
+    return l;
+}
+
+__device__ __forceinline__ int fast_score_exact(const uint8_t *p, int P)
+{
+    const int v = p[0];
+    int d[25];
+    d[0] = v - p[3 * P];      d[1] = v - p[3 * P + 1];  d[2] = v - p[2 * P + 2];   d[3] = v - p[P + 3];
+    d[4] = v - p[3];          d[5] = v - p[-P + 3];     d[6] = v - p[-2 * P + 2];  d[7] = v - p[-3 * P + 1];
+    d[8] = v - p[-3 * P];     d[9] = v - p[-3 * P - 1]; d[10] = v - p[-2 * P - 2]; d[11] = v - p[-P - 3];
+    d[12] = v - p[-3];        d[13] = v - p[P - 3];     d[14] = v - p[2 * P - 2];  d[15] = v - p[3 * P - 1];
+#pragma unroll
+    for (int k = 16; k < 25; ++k) d[k] = d[k - 16];
+    // best = max_k max(min over arc k of (v - p), min over arc k of (p - v)); the second term is -(min_k max over arc k of
+    // (v - p)), kept as a min-of-max until the end.  (Written as max(best, max(mn, -mx)) inside the loop, ptxas 12.9 fuses
+    // the negated operand into VIMNMX3 and loses the sign: the kernel then scored max |v - p| - found by the parity test.)
+    int hi = -256, lo = 256;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        int mn = d[k], mx = d[k];
+#pragma unroll
+        for (int j = 1; j < 9; ++j) { mn = min(mn, d[k + j]); mx = max(mx, d[k + j]); }
+        hi = max(hi, mn);
+        lo = min(lo, mx);
+    }
+    return max(hi, -lo) - 1;
+}
+
 __global__ void __launch_bounds__(256)
 k_cv_fast_score(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ pyr, uint8_t *__restrict__ score)
 {
-    const int l = blockIdx.z;
+    __shared__ uint32_t s_list[1024];
+    __shared__ int s_n;
+    const int l = tile_level<false>(g, blockIdx.x);
     const CvLevel &L = g.lv[l];
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31) + 3, y = blockIdx.y * 8 + (threadIdx.x >> 5) + 3;
-    if (x >= L.w - 3 || y >= L.h - 3) return;
-    const uint8_t *p = pyr + L.off + (size_t)y * L.pitch + x;
-    const int P = L.pitch, v = p[0], t = g.fast_th;
-    uint8_t out = 0;
-    // a 9-arc holds one pixel of every opposite pair: both compass pairs must have a member farther than t from v
-    const int d0 = abs((int)p[3 * P] - v), d8 = abs((int)p[-3 * P] - v), d4 = abs((int)p[3] - v), d12 = abs((int)p[-3] - v);
-    if ((d0 > t || d8 > t) && (d4 > t || d12 > t)) {
-        int d[25];
-        d[0] = v - p[3 * P];      d[1] = v - p[3 * P + 1];  d[2] = v - p[2 * P + 2];   d[3] = v - p[P + 3];
-        d[4] = v - p[3];          d[5] = v - p[-P + 3];     d[6] = v - p[-2 * P + 2];  d[7] = v - p[-3 * P + 1];
-        d[8] = v - p[-3 * P];     d[9] = v - p[-3 * P - 1]; d[10] = v - p[-2 * P - 2]; d[11] = v - p[-P - 3];
-        d[12] = v - p[-3];        d[13] = v - p[P - 3];     d[14] = v - p[2 * P - 2];  d[15] = v - p[3 * P - 1];
+    const int tile = blockIdx.x - L.tile_base, ty = tile / L.tiles_x, tx = tile - ty * L.tiles_x;
+    const int gx = tx * 32 + (threadIdx.x & 31), y = ty * 8 + (threadIdx.x >> 5) + g.edge - 1;
+    const int P = L.pitch, PW = P >> 2, t = g.fast_th;
+    const int x_lo = g.edge - 1, x_hi = L.w - g.edge; // scored columns, inclusive
+    pyr += blockIdx.y * g.slot_bytes + L.off;
+    score += blockIdx.y * g.slot_bytes + L.off;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    if (y <= L.h - g.edge && 4 * gx <= x_hi && 4 * gx + 3 >= x_lo) {
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(pyr + (size_t)y * P) + gx;
+        const uint32_t c = row[0], lft = gx > 0 ? row[-1] : 0u, rgt = gx + 1 < PW ? row[1] : 0u;
+        const uint32_t top = row[-3 * PW], bot = row[3 * PW];
+        const uint32_t east = __funnelshift_r(c, rgt, 24), west = __funnelshift_r(lft, c, 8); // pixels x + 3 / x - 3
+        const uint32_t d0 = __vabsdiffu4(bot, c), d8 = __vabsdiffu4(top, c), d4 = __vabsdiffu4(east, c), d12 = __vabsdiffu4(west, c);
+        // bit 7 of ((d + 127 - t) | d) is set where d > t; a carry from the byte below only adds a false positive
+        const uint32_t bias = t <= 127 ? (uint32_t)(127 - t) * 0x01010101u : 0u;
+        const uint32_t e0 = (d0 + bias) | d0, e8 = (d8 + bias) | d8, e4 = (d4 + bias) | d4, e12 = (d12 + bias) | d12;
+        uint32_t pass = (e0 | e8) & (e4 | e12) & 0x80808080u;
 #pragma unroll
-        for (int k = 16; k < 25; ++k) d[k] = d[k - 16];
-        // best = max_k max(min over arc k of (v - p), min over arc k of (p - v)); the second term is -(min_k max over arc k of
-        // (v - p)), kept as a min-of-max until the end.  (Written as max(best, max(mn, -mx)) inside the loop, ptxas 12.9 fuses
-        // the negated operand into VIMNMX3 and loses the sign: the kernel then scored max |v - p| - found by the parity test.)
-        int hi = -256, lo = 256;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            int mn = d[k], mx = d[k];
-#pragma unroll
-            for (int j = 1; j < 9; ++j) { mn = min(mn, d[k + j]); mx = max(mx, d[k + j]); }
-            hi = max(hi, mn);
-            lo = min(lo, mx);
+        for (int b = 0; b < 4; ++b)
+            if (4 * gx + b < x_lo || 4 * gx + b > x_hi) pass &= ~(0x80u << (8 * b));
+        reinterpret_cast<uint32_t *>(score + (size_t)y * P)[gx] = 0u;
+        while (pass) {
+            const int b = (__ffs((int)pass) - 1) >> 3;
+            s_list[atomicAdd(&s_n, 1)] = ((uint32_t)y << 16) | (uint32_t)(4 * gx + b);
+            pass &= pass - 1;
         }
-        const int R = max(hi, -lo) - 1;
-        if (R >= t) out = (uint8_t)R;
     }
-    score[L.off + (size_t)y * L.pitch + x] = out;
+    __syncthreads(); // also orders the cleared words before the score bytes written below
+    const int n = s_n;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const int x = (int)(s_list[i] & 0xFFFFu), yy = (int)(s_list[i] >> 16);
+        const int R = fast_score_exact(pyr + (size_t)yy * P + x, P);
+        if (R >= t) score[(size_t)yy * P + x] = (uint8_t)R;
+    }
 }
 
-// strict 3x3 maxima (pixels outside the tested range hold 0 in the score map), runByPixelsMask, runByImageBorder;
-// survivors go to the level's candidate list (unordered: everything downstream is a set operation until the final sort)
+// strict 3x3 maxima over the whole level, runByPixelsMask, runByImageBorder; survivors go to the level's candidate list
+// (unordered: everything downstream is a set operation until the final sort).  Tile = 128 px x 32 rows: a CTA gathers its
+// survivors in shared memory and reserves its piece of the level's list with ONE atomic (a counter per candidate
+// serialised 20 000 atomics per image on eight addresses: 407 -> see DESIGN.md).
 __global__ void __launch_bounds__(256)
 k_cv_nms_collect(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ score, const uint8_t *__restrict__ mask,
                  uint32_t *__restrict__ cand, int *__restrict__ counters, int *__restrict__ hist, int *__restrict__ err)
 {
-    const int l = blockIdx.z;
+    __shared__ uint32_t s_c[1024]; // strict 3x3 maxima: at most one per 2x2 block of the 128 x 32 tile
+    __shared__ int s_n, s_base;
+    const int l = tile_level<true>(g, blockIdx.x), slot = blockIdx.y;
     const CvLevel &L = g.lv[l];
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31) + 3, y = blockIdx.y * 8 + (threadIdx.x >> 5) + 3;
-    if (x >= L.w - 3 || y >= L.h - 3) return;
+    const int tile = blockIdx.x - L.nms_tile_base, ty = tile / L.tiles_x, tx = tile - ty * L.tiles_x;
+    const int gx = tx * 32 + (threadIdx.x & 31);
     const int P = L.pitch;
-    const uint8_t *s = score + L.off + (size_t)y * P + x;
-    const int c = s[0];
-    if (c == 0) return;
-    if (!(c > s[-1] && c > s[1] && c > s[-P - 1] && c > s[-P] && c > s[-P + 1] && c > s[P - 1] && c > s[P] && c > s[P + 1])) return;
-    if (mask && mask[L.off + (size_t)y * P + x] == 0) return;
-    if (x < g.edge || x >= L.w - g.edge || y < g.edge || y >= L.h - g.edge) return;
-    const int i = atomicAdd(&counters[CV_CNT_CAND + l], 1);
-    if (i >= L.cand_cap) { atomicOr(err, PSLOT_FLAG_CVORB_CAP); return; }
-    cand[L.cand_base + i] = pslot_pack(x, y, c);
-    atomicAdd(&hist[l * 256 + c], 1);
+    score += slot * g.slot_bytes + L.off;
+    if (mask) mask += slot * g.slot_bytes + L.off;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    if (4 * gx + 3 >= g.edge && 4 * gx < L.w - g.edge) {
+        for (int r = threadIdx.x >> 5; r < 32; r += 8) {
+            const int y = ty * 32 + r + g.edge; // candidates live in [edge, h - edge)
+            if (y >= L.h - g.edge) break;
+            uint32_t w = *reinterpret_cast<const uint32_t *>(score + (size_t)y * P + 4 * gx);
+            for (; w; ) {
+                const int b = (__ffs((int)w) - 1) >> 3;
+                w &= ~(0xFFu << (8 * b));
+                const int x = 4 * gx + b;
+                if (x < g.edge || x >= L.w - g.edge) continue;
+                const uint8_t *s = score + (size_t)y * P + x;
+                const int c = s[0];
+                if (!(c > s[-1] && c > s[1] && c > s[-P - 1] && c > s[-P] && c > s[-P + 1] && c > s[P - 1] && c > s[P] && c > s[P + 1])) continue;
+                if (mask && mask[(size_t)y * P + x] == 0) continue;
+                s_c[atomicAdd(&s_n, 1)] = pslot_pack(x, y, c);
+            }
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n == 0) return;
+    if (threadIdx.x == 0) s_base = atomicAdd(&counters[slot * CV_CNT_TOTAL + CV_CNT_CAND + l], n);
+    __syncthreads();
+    const int base = s_base;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        if (base + i >= L.cand_cap) { atomicOr(err, PSLOT_FLAG_CVORB_CAP); continue; }
+        const uint32_t c = s_c[i];
+        cand[(size_t)slot * g.slot_cand + L.cand_base + base + i] = c;
+        atomicAdd(&hist[(slot * PSLOT_MAX_LEVELS + l) * 256 + pslot_pr(c)], 1);
+    }
 }
 
 // ---- retainBest(2 * quota) on the FAST score, then HarrisResponses -----------------------------------------------------------
@@ -118,8 +204,12 @@ k_cv_harris(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ pyr, c
             int *__restrict__ counters, const int *__restrict__ hist, uint32_t *__restrict__ kept, float *__restrict__ kept_resp)
 {
     __shared__ int s_thr;
-    const int l = blockIdx.y;
+    const int l = blockIdx.y, slot = blockIdx.z;
     const CvLevel &L = g.lv[l];
+    pyr += slot * g.slot_bytes;
+    cand += (size_t)slot * g.slot_cand; kept += (size_t)slot * g.slot_cand; kept_resp += (size_t)slot * g.slot_cand;
+    counters += slot * CV_CNT_TOTAL;
+    hist += slot * PSLOT_MAX_LEVELS * 256;
     const int n = min(counters[CV_CNT_CAND + l], L.cand_cap);
     if (threadIdx.x == 0) {
         // KeyPointsFilter::retainBest(keypoints, 2 * quota): keep everything >= the response of the (2 * quota)-th best
@@ -181,11 +271,13 @@ k_cv_select(const __grid_constant__ CvGeom g, const uint32_t *__restrict__ kept,
     __shared__ int s_hist[256];
     __shared__ uint32_t s_prefix;
     __shared__ int s_k, s_n;
-    const int l = blockIdx.x, tid = threadIdx.x;
+    const int l = blockIdx.x, slot = blockIdx.y, tid = threadIdx.x;
     const CvLevel &L = g.lv[l];
+    counters += slot * CV_CNT_TOTAL;
+    final_kp += (size_t)slot * g.slot_kp; final_resp += (size_t)slot * g.slot_kp;
     const int n1 = counters[CV_CNT_KEPT + l];
-    const uint32_t *K = kept + L.cand_base;
-    const float *R = kept_resp + L.cand_base;
+    const uint32_t *K = kept + (size_t)slot * g.slot_cand + L.cand_base;
+    const float *R = kept_resp + (size_t)slot * g.slot_cand + L.cand_base;
     uint32_t thr_key = 0; // keep everything
     if (L.quota == 0) thr_key = 0xFFFFFFFFu;
     if (n1 > L.quota && L.quota > 0) {
@@ -258,7 +350,7 @@ k_cv_select(const __grid_constant__ CvGeom g, const uint32_t *__restrict__ kept,
 constexpr int CW = 4;            // warps (keypoints) per CTA
 constexpr int CPR = 21;          // raw patch radius: 15 (pattern reach after rotation: 18) + 3 (blur)
 constexpr int CPD = 2 * CPR + 1; // 43
-constexpr int CRW = 13, CRS = CRW * 4;
+constexpr int CRW = 17, CRS = CRW * 4; // four 16-byte chunks cover the 43 bytes of a row at any alignment
 constexpr int CBR = 18, CBD = 2 * CBR + 1; // blurred support 37 x 37
 constexpr int CCS = 45;          // float column stride of the horizontal pass, [blurred column][patch row]
 
@@ -274,14 +366,19 @@ k_cv_describe(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ pyr,
 {
     __shared__ __align__(16) CvWarpSmem sm[CW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int l = blockIdx.y;
+    const int l = blockIdx.y, slot = blockIdx.z;
     const CvLevel &L = g.lv[l];
+    counters += slot * CV_CNT_TOTAL;
+    pyr += slot * g.slot_bytes;
+    final_kp += (size_t)slot * g.slot_kp; final_resp += (size_t)slot * g.slot_kp;
+    out_kps += (size_t)slot * g.slot_kp; out_desc += (size_t)slot * g.slot_kp * 32;
     const int c_lane = lane < g.nlevels ? counters[CV_CNT_FINAL + lane] : 0;
     const int out_base = __reduce_add_sync(0xffffffffu, lane < l ? c_lane : 0);
     const int total = __reduce_add_sync(0xffffffffu, c_lane);
-    if (blockIdx.x == 0 && l == 0 && threadIdx.x == 0) *out_count = total;
-    const int i = blockIdx.x * CW + warp;
-    if (i >= __shfl_sync(0xffffffffu, c_lane, l)) return;
+    if (blockIdx.x == 0 && l == 0 && threadIdx.x == 0) out_count[slot] = total;
+    const int n_level = __shfl_sync(0xffffffffu, c_lane, l);
+    const float k0 = g.gk[0], k1 = g.gk[1], k2 = g.gk[2], k3 = g.gk[3]; // k[4..6] mirror k[2..0]
+    for (int i = blockIdx.x * CW + warp; i < n_level; i += gridDim.x * CW) { // warp-uniform
 
     const uint32_t kp = final_kp[L.kp_base + i];
     const int kx = pslot_px(kp), ky = pslot_py(kp);
@@ -289,11 +386,38 @@ k_cv_describe(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ pyr,
     CvWarpSmem &S = sm[warp];
     uint8_t *rawb = reinterpret_cast<uint8_t *>(S.raw);
 
-    // the 43x43 patch around the keypoint, BORDER_REFLECT_101 at the image edge (the blur runs on the whole level)
+    // the 43x43 patch around the keypoint; patch column c lives at byte c + shift of its shared row
     const int x0 = kx - CPR, y0 = ky - CPR;
-    for (int e = lane; e < CPD * CPD; e += 32) {
-        const int r = e / CPD, c = e - r * CPD;
-        rawb[r * CRS + c] = __ldg(img + (size_t)reflect101(y0 + r, L.h) * L.pitch + reflect101(x0 + c, L.w));
+    int shift;
+    if (x0 >= 0 && y0 >= 0 && x0 + CPD <= L.w && y0 + CPD <= L.h) {
+        // rows are 128-byte aligned in global memory: the four aligned 16-byte chunks that cover the 43 bytes
+        shift = x0 & 15;
+        const int xa = x0 - shift;
+        const uint8_t *src = img + (size_t)y0 * L.pitch + xa;
+        constexpr int NLD = (CPD * 4 + 31) / 32;
+        uint4 v[NLD];
+#pragma unroll
+        for (int k = 0; k < NLD; ++k) { // all loads of a lane are issued before the first store
+            const int e = lane + 32 * k;
+            const int r = min(e >> 2, CPD - 1), c = e & 3;
+            const int cc = xa + 16 * c < L.pitch ? c : 0; // a chunk beyond the row's pitch is never needed
+            v[k] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * L.pitch) + cc);
+        }
+#pragma unroll
+        for (int k = 0; k < NLD; ++k) {
+            const int e = lane + 32 * k;
+            const int r = e >> 2, c = e & 3;
+            if (r < CPD) {
+                uint32_t *d = S.raw + r * CRW + 4 * c;
+                d[0] = v[k].x; d[1] = v[k].y; d[2] = v[k].z; d[3] = v[k].w;
+            }
+        }
+    } else { // within 21 px of the image edge (edgeThreshold 19 or 20): BORDER_REFLECT_101, byte by byte (the blur runs on the whole level)
+        shift = 0;
+        for (int e = lane; e < CPD * CPD; e += 32) {
+            const int r = e / CPD, c = e - r * CPD;
+            rawb[r * CRS + c] = __ldg(img + (size_t)reflect101(y0 + r, L.h) * L.pitch + reflect101(x0 + c, L.w));
+        }
     }
     __syncwarp();
 
@@ -302,7 +426,7 @@ k_cv_describe(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ pyr,
     if (lane < 31) {
         const int v = lane - 15;
         const int d = c_umax[v < 0 ? -v : v];
-        const uint8_t *row = rawb + (CPR + v) * CRS + CPR;
+        const uint8_t *row = rawb + (CPR + v) * CRS + CPR + shift;
         int sum = 0;
         for (int u = -d; u <= d; ++u) {
             const int val = row[u];
@@ -318,19 +442,29 @@ k_cv_describe(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ pyr,
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // horizontal float pass of cv::sepFilter2D: taps left to right, fused multiply-adds
-    const float k0 = g.gk[0], k1 = g.gk[1], k2 = g.gk[2], k3 = g.gk[3]; // k[4..6] mirror k[2..0]
-    for (int r = lane; r < CPD; r += 32) {
-        const uint8_t *p = rawb + r * CRS;
-        for (int c = 0; c < CBD; ++c) {
-            float acc = __fmul_rn(k0, (float)p[c]);
-            acc = __fmaf_rn(k1, (float)p[c + 1], acc);
-            acc = __fmaf_rn(k2, (float)p[c + 2], acc);
-            acc = __fmaf_rn(k3, (float)p[c + 3], acc);
-            acc = __fmaf_rn(k2, (float)p[c + 4], acc);
-            acc = __fmaf_rn(k1, (float)p[c + 5], acc);
-            acc = __fmaf_rn(k0, (float)p[c + 6], acc);
-            S.hp[c * CCS + r] = acc;
+    // horizontal float pass of cv::sepFilter2D: taps left to right, fused multiply-adds.  A task is half a patch row (19 or
+    // 18 blurred columns); its bytes are converted once and slide through a 7-register window (one load, one conversion and
+    // seven multiply-adds per output instead of seven of each).
+    for (int task = lane; task < 2 * CPD; task += 32) {
+        const int half = task >= CPD ? 1 : 0, r = task - half * CPD;
+        const int c0 = half * 19, nc = 19 - half;
+        const uint8_t *p = rawb + r * CRS + shift + c0;
+        float *o = S.hp + c0 * CCS + r;
+        float f0 = (float)p[0], f1 = (float)p[1], f2 = (float)p[2], f3 = (float)p[3], f4 = (float)p[4], f5 = (float)p[5];
+#pragma unroll
+        for (int c = 0; c < 19; ++c) {
+            if (c < nc) {
+                const float f6 = (float)p[c + 6];
+                float acc = __fmul_rn(k0, f0);
+                acc = __fmaf_rn(k1, f1, acc);
+                acc = __fmaf_rn(k2, f2, acc);
+                acc = __fmaf_rn(k3, f3, acc);
+                acc = __fmaf_rn(k2, f4, acc);
+                acc = __fmaf_rn(k1, f5, acc);
+                acc = __fmaf_rn(k0, f6, acc);
+                o[c * CCS] = acc;
+                f0 = f1; f1 = f2; f2 = f3; f3 = f4; f4 = f5; f5 = f6;
+            }
         }
     }
     __syncwarp();
@@ -376,29 +510,31 @@ k_cv_describe(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ pyr,
         k.class_id = -1;
         out_kps[o] = k;
     }
+    __syncwarp(); // the next keypoint's patch overwrites this warp's shared memory
+    }
 }
 
 } // namespace
 
-int launch_cvorb(const CvGeom &g, const CvBuffers &b, bool has_mask, cudaStream_t st)
+int launch_cvorb(const CvGeom &g, const CvBuffers &b, int slots, bool has_mask, cudaStream_t st)
 {
     int n = 0;
+    const int planes = has_mask ? 2 : 1;
     for (int l = 1; l < g.nlevels; ++l) { // each level from the previous one (orb.cpp: resize(prevImg, currImg, INTER_LINEAR_EXACT))
         const CvLevel &S = g.lv[l - 1], &D = g.lv[l];
-        dim3 blk(32, 8), grd((D.w + 31) / 32, (D.h + 7) / 8, has_mask ? 2 : 1);
-        k_cv_resize_exact<<<grd, blk, 0, st>>>(b.pyr + S.off, b.mask + S.off, S.w, S.h, S.pitch, b.pyr + D.off, b.mask + D.off,
-                                               D.w, D.h, D.pitch, b.taps + D.tab_x, b.taps + D.tab_y);
+        dim3 grd((D.w + 127) / 128, (D.h + 7) / 8, planes * slots);
+        k_cv_resize_exact<<<grd, 256, 0, st>>>(b.pyr + S.off, b.mask + S.off, S.w, S.h, S.pitch, b.pyr + D.off, b.mask + D.off,
+                                               D.w, D.h, D.pitch, b.taps + D.tab_x, b.taps + D.tab_y, (size_t)g.slot_bytes, planes);
         ++n;
     }
-    cudaMemsetAsync(b.counters, 0, sizeof(int) * CV_CNT_TOTAL, st);
-    cudaMemsetAsync(b.hist, 0, sizeof(int) * 256 * PSLOT_MAX_LEVELS, st);
-    const CvLevel &L0 = g.lv[0];
-    dim3 grd((L0.w - 6 + 31) / 32, (L0.h - 6 + 7) / 8, g.nlevels);
-    k_cv_fast_score<<<grd, 256, 0, st>>>(g, b.pyr, b.score);
-    k_cv_nms_collect<<<grd, 256, 0, st>>>(g, b.score, has_mask ? b.mask : nullptr, b.cand, b.counters, b.hist, b.err);
-    k_cv_harris<<<dim3(32, g.nlevels), 256, 0, st>>>(g, b.pyr, b.cand, b.counters, b.hist, b.kept, b.kept_resp);
-    k_cv_select<<<g.nlevels, 1024, 0, st>>>(g, b.kept, b.kept_resp, b.counters, b.final_kp, b.final_resp, b.err);
-    k_cv_describe<<<dim3((CV_SORT_CAP + CW - 1) / CW, g.nlevels), CW * 32, 0, st>>>(g, b.pyr, b.final_kp, b.final_resp, b.counters,
-                                                                                  b.out_kps, b.out_desc, b.out_count, b.err);
+    cudaMemsetAsync(b.counters, 0, sizeof(int) * CV_CNT_TOTAL * slots, st);
+    cudaMemsetAsync(b.hist, 0, sizeof(int) * 256 * PSLOT_MAX_LEVELS * slots, st);
+    k_cv_fast_score<<<dim3(g.n_tiles, slots), 256, 0, st>>>(g, b.pyr, b.score);
+    k_cv_nms_collect<<<dim3(g.n_nms_tiles, slots), 256, 0, st>>>(g, b.score, has_mask ? b.mask : nullptr, b.cand, b.counters, b.hist,
+                                                                b.err);
+    k_cv_harris<<<dim3(slots > 8 ? 8 : 32, g.nlevels, slots), 256, 0, st>>>(g, b.pyr, b.cand, b.counters, b.hist, b.kept, b.kept_resp);
+    k_cv_select<<<dim3(g.nlevels, slots), 1024, 0, st>>>(g, b.kept, b.kept_resp, b.counters, b.final_kp, b.final_resp, b.err);
+    k_cv_describe<<<dim3(g.describe_blocks, g.nlevels, slots), CW * 32, 0, st>>>(g, b.pyr, b.final_kp, b.final_resp, b.counters,
+                                                                               b.out_kps, b.out_desc, b.out_count, b.err);
     return n + 5;
 }

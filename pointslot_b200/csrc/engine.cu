@@ -11,6 +11,7 @@
 #include <sys/mman.h>
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <new>
 #include <map>
@@ -475,7 +476,7 @@ struct pslot_cvorb {
     int nfeatures = 0, nlevels = 0, edge = 0, fast_th = 0, device = 0;
     double scale_factor = 1.2;
     cudaStream_t st = nullptr;
-    int W = 0, H = 0;
+    int W = 0, H = 0, slots = 0; // geometry and number of image slots the buffers are sized for
     CvGeom g{};
     CvBuffers b{};
     int *h_err = nullptr;
@@ -483,14 +484,18 @@ struct pslot_cvorb {
     int cand_total = 0;
     unsigned char *h_out = nullptr; // pinned staging of the outputs
     size_t h_out_bytes = 0;
+    uint8_t *d_stage = nullptr;     // tightly packed uploads (images, then masks) before the re-pitch kernel
+    size_t stage_view = 0;          // bytes of one of its two halves
+    double t_phase[4] = {0, 0, 0, 0}; // host clock of the last call: uploads enqueued, kernels enqueued, wait, copy-out (ms)
 
     void release()
     {
+        cudaFree(d_stage); d_stage = nullptr;
         cudaFree(b.pyr); cudaFree(b.mask); cudaFree(b.score); cudaFree((void *)b.taps); cudaFree(b.cand); cudaFree(b.kept);
         cudaFree(b.final_kp); cudaFree(b.kept_resp); cudaFree(b.final_resp); cudaFree(b.counters); cudaFree(b.hist);
         cudaFree(b.out_kps); cudaFree(b.out_desc); cudaFree(b.out_count);
         b = CvBuffers{};
-        W = H = 0;
+        W = H = slots = 0;
     }
     ~pslot_cvorb()
     {
@@ -537,10 +542,11 @@ void exact_taps(int n_dst, int n_src, int2 *out)
     }
 }
 
-int cvorb_configure(pslot_cvorb &c, int w, int h)
+int cvorb_configure(pslot_cvorb &c, int w, int h, int slots)
 {
-    if (w == c.W && h == c.H) return PSLOT_OK;
+    if (w == c.W && h == c.H && slots <= c.slots) return PSLOT_OK;
     if (w > 4095 || h > 4095) return fail(PSLOT_ERR_SHAPE, "image %dx%d exceeds 4095 px", w, h);
+    if (w == c.W && h == c.H) slots = std::max(slots, std::min(2 * c.slots, 1024)); // growing batch: amortise the re-allocation
     CU(cudaStreamSynchronize(c.st));
     c.release();
     CvGeom &G = c.g;
@@ -562,7 +568,7 @@ int cvorb_configure(pslot_cvorb &c, int w, int h)
     }
     std::vector<int2> taps;
     size_t off = 0;
-    int cand = 0, nl = 0;
+    int cand = 0, nl = 0, tiles = 0, nms_tiles = 0, max_quota = 1;
     for (int l = 0; l < c.nlevels; ++l) {
         const float scale = (float)pow(c.scale_factor, (double)l);
         const int lw = cv_round((double)((float)w / scale)), lh = cv_round((double)((float)h / scale));
@@ -577,6 +583,14 @@ int cvorb_configure(pslot_cvorb &c, int w, int h)
         L.cand_cap = ((lw + 1) / 2) * ((lh + 1) / 2); // strict 3x3 maxima cannot be denser
         cand += L.cand_cap;
         L.kp_base = l * CV_SORT_CAP;
+        // only scores within one pixel of the border filter's interior can matter: rows / columns [edge - 1, dim - edge]
+        const int band_rows = lh - 2 * c.edge + 2;
+        L.tile_base = tiles;
+        L.nms_tile_base = nms_tiles;
+        L.tiles_x = (lw + 127) / 128;
+        tiles += L.tiles_x * ((band_rows + 7) / 8);
+        nms_tiles += L.tiles_x * ((band_rows + 31) / 32);
+        max_quota = std::max(max_quota, quota[l]);
         if (l > 0) {
             L.tab_x = (int)taps.size(); taps.resize(taps.size() + lw);
             exact_taps(lw, G.lv[l - 1].w, taps.data() + L.tab_x);
@@ -587,9 +601,17 @@ int cvorb_configure(pslot_cvorb &c, int w, int h)
     }
     if (nl == 0) return fail(PSLOT_ERR_SHAPE, "image %dx%d is smaller than 2 * edgeThreshold + 1", w, h);
     G.nlevels = nl;
+    G.slot_bytes = off;
+    G.slot_cand = cand;
+    G.slot_kp = CV_SORT_CAP * nl;
+    G.n_tiles = tiles;
+    G.n_nms_tiles = nms_tiles;
+    G.describe_blocks = std::min(CV_SORT_CAP / 4, (max_quota + 3) / 4);
     c.level_bytes = off;
     c.cand_total = cand;
     CvBuffers &B = c.b;
+    const size_t S = (size_t)slots;
+    off *= S;
     CU(cudaMalloc(&B.pyr, off)); CU(cudaMalloc(&B.mask, off)); CU(cudaMalloc(&B.score, off));
     CU(cudaMemset(B.pyr, 0, off)); CU(cudaMemset(B.mask, 0, off));
     CU(cudaMemset(B.score, 0, off)); // the untested 3-px frame of every level must read as 0 in the maxima test
@@ -597,13 +619,15 @@ int cvorb_configure(pslot_cvorb &c, int w, int h)
     CU(cudaMalloc(&d_taps, sizeof(int2) * std::max<size_t>(taps.size(), 1)));
     if (!taps.empty()) CU(cudaMemcpy(d_taps, taps.data(), sizeof(int2) * taps.size(), cudaMemcpyHostToDevice));
     B.taps = d_taps;
-    CU(cudaMalloc(&B.cand, 4 * (size_t)cand)); CU(cudaMalloc(&B.kept, 4 * (size_t)cand)); CU(cudaMalloc(&B.kept_resp, 4 * (size_t)cand));
-    const size_t kcap = (size_t)CV_SORT_CAP * PSLOT_MAX_LEVELS;
+    CU(cudaMalloc(&B.cand, 4 * S * cand)); CU(cudaMalloc(&B.kept, 4 * S * cand)); CU(cudaMalloc(&B.kept_resp, 4 * S * cand));
+    const size_t kcap = S * (size_t)G.slot_kp;
     CU(cudaMalloc(&B.final_kp, 4 * kcap)); CU(cudaMalloc(&B.final_resp, 4 * kcap));
-    CU(cudaMalloc(&B.counters, sizeof(int) * CV_CNT_TOTAL)); CU(cudaMalloc(&B.hist, sizeof(int) * 256 * PSLOT_MAX_LEVELS));
-    CU(cudaMalloc(&B.out_kps, sizeof(pslot_keypoint) * kcap)); CU(cudaMalloc(&B.out_desc, 32 * kcap)); CU(cudaMalloc(&B.out_count, sizeof(int)));
+    CU(cudaMalloc(&B.counters, sizeof(int) * CV_CNT_TOTAL * S)); CU(cudaMalloc(&B.hist, sizeof(int) * 256 * PSLOT_MAX_LEVELS * S));
+    CU(cudaMalloc(&B.out_kps, sizeof(pslot_keypoint) * kcap)); CU(cudaMalloc(&B.out_desc, 32 * kcap)); CU(cudaMalloc(&B.out_count, sizeof(int) * S));
     CU(cudaHostGetDevicePointer((void **)&B.err, c.h_err, 0));
-    c.W = w; c.H = h;
+    c.stage_view = align_up(S * (size_t)w * h + 16, 256);
+    CU(cudaMalloc(&c.d_stage, 2 * c.stage_view));
+    c.W = w; c.H = h; c.slots = slots;
     return PSLOT_OK;
 }
 
@@ -988,57 +1012,129 @@ void pslot_cvorb_destroy(pslot_cvorb *ctx)
     delete ctx;
 }
 
-int pslot_cvorb_detect_and_compute(pslot_cvorb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, const uint8_t *mask,
-                                   ptrdiff_t mask_pitch, pslot_keypoint *kps, uint8_t *desc32, int cap, int *n)
+int pslot_cvorb_detect_and_compute_batch(pslot_cvorb *ctx, int n_images, const uint8_t *const *imgs, int w, int h, ptrdiff_t pitch,
+                                         const uint8_t *const *masks, ptrdiff_t mask_pitch, pslot_keypoint *kps, uint8_t *desc32,
+                                         int cap, int *counts)
 {
-    if (!ctx || !n) return fail(PSLOT_ERR_ARG, "ctx / n is null");
-    *n = 0;
-    if (!img || w <= 0 || h <= 0) return PSLOT_OK; // empty image: no keypoints (orb.cpp: CV_Assert only on type)
-    if (pitch < w || (mask && mask_pitch < w)) return fail(PSLOT_ERR_ARG, "pitch < width");
+    if (!ctx || !counts) return fail(PSLOT_ERR_ARG, "ctx / counts is null");
+    if (n_images < 0 || n_images > 1024) return fail(PSLOT_ERR_ARG, "n_images must be in [0,1024]");
+    if (cap < 0) return fail(PSLOT_ERR_ARG, "cap < 0");
+    for (int s = 0; s < n_images; ++s) counts[s] = 0;
+    if (n_images == 0 || w <= 0 || h <= 0) return PSLOT_OK; // empty image: no keypoints (orb.cpp: CV_Assert only on type)
+    if (!imgs) return fail(PSLOT_ERR_ARG, "imgs is null");
+    bool any_mask = false;
+    for (int s = 0; s < n_images; ++s) {
+        if (!imgs[s]) return fail(PSLOT_ERR_ARG, "image %d is null", s);
+        any_mask |= masks && masks[s];
+    }
+    if (pitch < w || (any_mask && mask_pitch < w)) return fail(PSLOT_ERR_ARG, "pitch < width");
     pslot_cvorb &C = *ctx;
     CU(cudaSetDevice(C.device));
     if (w < 2 * C.edge + 1 || h < 2 * C.edge + 1) return PSLOT_OK; // nothing passes runByImageBorder: cv::ORB returns no keypoints
-    if (int rc = cvorb_configure(C, w, h)) return rc;
+    if (int rc = cvorb_configure(C, w, h, n_images)) return rc;
     const CvLevel &L0 = C.g.lv[0];
-    CU(cudaMemcpy2DAsync(C.b.pyr + L0.off, L0.pitch, img, pitch, w, h, cudaMemcpyHostToDevice, C.st));
-    if (mask) CU(cudaMemcpy2DAsync(C.b.mask + L0.off, L0.pitch, mask, mask_pitch, w, h, cudaMemcpyHostToDevice, C.st));
-    launch_cvorb(C.g, C.b, mask != nullptr, C.st);
+    const auto t0 = std::chrono::steady_clock::now();
+    if (pitch == w && (!any_mask || mask_pitch == w)) {
+        // tightly packed rows: linear copies at the full PCIe rate into a staging buffer (images that follow each other in
+        // host memory travel as one copy), then one re-pitch launch into the 128-byte aligned level-0 rows of all slots
+        // (a 2-D copy of 1242-byte rows runs far below the link rate)
+        const size_t img_bytes = (size_t)w * h;
+        for (int view = 0; view < (any_mask ? 2 : 1); ++view) {
+            const uint8_t *const *src = view ? masks : imgs;
+            uint8_t *stg = C.d_stage + view * C.stage_view;
+            for (int s = 0; s < n_images;) {
+                if (!src[s]) { // no mask for this image of a masked batch: keep everything
+                    CU(cudaMemsetAsync(stg + s * img_bytes, 255, img_bytes, C.st));
+                    ++s;
+                    continue;
+                }
+                int e = s + 1;
+                while (e < n_images && src[e] == src[e - 1] + img_bytes) ++e;
+                CU(cudaMemcpyAsync(stg + s * img_bytes, src[s], img_bytes * (size_t)(e - s), cudaMemcpyHostToDevice, C.st));
+                s = e;
+            }
+            launch_gray_ingest(stg, img_bytes, 1, 0, (view ? C.b.mask : C.b.pyr) + L0.off, w, h, L0.pitch, C.g.slot_bytes, n_images, C.st);
+        }
+    } else {
+        for (int s = 0; s < n_images; ++s) {
+            const size_t o = s * (size_t)C.g.slot_bytes + L0.off;
+            CU(cudaMemcpy2DAsync(C.b.pyr + o, L0.pitch, imgs[s], pitch, w, h, cudaMemcpyHostToDevice, C.st));
+            if (!any_mask) continue;
+            if (masks[s]) CU(cudaMemcpy2DAsync(C.b.mask + o, L0.pitch, masks[s], mask_pitch, w, h, cudaMemcpyHostToDevice, C.st));
+            else CU(cudaMemset2DAsync(C.b.mask + o, L0.pitch, 255, w, h, C.st)); // no mask for this image of a masked batch: keep all
+        }
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    launch_cvorb(C.g, C.b, n_images, any_mask, C.st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "cv::ORB launch failed: %s", cudaGetErrorString(e));
-    // one round trip: the count and the (almost always sufficient) first `guess` records travel together into pinned memory
-    const int guess = C.nfeatures + 64;
-    const size_t need = 16 + (size_t)guess * (sizeof(pslot_keypoint) + 32);
+    // one round trip: the counts and the (almost always sufficient) first `guess` records of every image travel together
+    // into pinned memory
+    const int guess = std::min(C.nfeatures + 64, C.g.slot_kp);
+    const size_t S = (size_t)n_images, hdr = align_up(sizeof(int) * S, 16);
+    const size_t need = hdr + S * guess * (sizeof(pslot_keypoint) + 32);
     if (C.h_out_bytes < need) {
         if (C.h_out) cudaFreeHost(C.h_out);
         C.h_out = nullptr; C.h_out_bytes = 0;
         CU(cudaHostAlloc((void **)&C.h_out, need, cudaHostAllocDefault));
         C.h_out_bytes = need;
     }
-    pslot_keypoint *hk = reinterpret_cast<pslot_keypoint *>(C.h_out + 16);
-    uint8_t *hd = C.h_out + 16 + (size_t)guess * sizeof(pslot_keypoint);
-    CU(cudaMemcpyAsync(C.h_out, C.b.out_count, sizeof(int), cudaMemcpyDeviceToHost, C.st));
-    CU(cudaMemcpyAsync(hk, C.b.out_kps, sizeof(pslot_keypoint) * (size_t)guess, cudaMemcpyDeviceToHost, C.st));
-    CU(cudaMemcpyAsync(hd, C.b.out_desc, 32 * (size_t)guess, cudaMemcpyDeviceToHost, C.st));
+    pslot_keypoint *hk = reinterpret_cast<pslot_keypoint *>(C.h_out + hdr);
+    uint8_t *hd = C.h_out + hdr + S * guess * sizeof(pslot_keypoint);
+    const int *hc = reinterpret_cast<const int *>(C.h_out);
+    CU(cudaMemcpyAsync(C.h_out, C.b.out_count, sizeof(int) * S, cudaMemcpyDeviceToHost, C.st));
+    CU(cudaMemcpy2DAsync(hk, sizeof(pslot_keypoint) * (size_t)guess, C.b.out_kps, sizeof(pslot_keypoint) * (size_t)C.g.slot_kp,
+                         sizeof(pslot_keypoint) * (size_t)guess, S, cudaMemcpyDeviceToHost, C.st));
+    CU(cudaMemcpy2DAsync(hd, 32 * (size_t)guess, C.b.out_desc, 32 * (size_t)C.g.slot_kp, 32 * (size_t)guess, S,
+                         cudaMemcpyDeviceToHost, C.st));
+    const auto t2 = std::chrono::steady_clock::now();
     CU(cudaStreamSynchronize(C.st));
+    const auto t3 = std::chrono::steady_clock::now();
     if (*(volatile int *)C.h_err) {
         *C.h_err = 0;
         return fail(PSLOT_ERR_CAPACITY, "cv::ORB: a per-level candidate list or the keypoint sort overflowed");
     }
-    const int count = *reinterpret_cast<const int *>(C.h_out);
-    *n = count;
-    if (count > cap) return fail(PSLOT_ERR_CAPACITY, "need room for %d keypoints, caller gave %d", count, cap);
-    if (count > 0) {
-        if (!kps || !desc32) return fail(PSLOT_ERR_ARG, "kps / desc32 is null");
+    int worst = 0;
+    for (int s = 0; s < n_images; ++s) { counts[s] = hc[s]; worst = std::max(worst, hc[s]); }
+    if (worst > cap) return fail(PSLOT_ERR_CAPACITY, "need room for %d keypoints per image, caller gave %d", worst, cap);
+    if (worst > 0 && (!kps || !desc32)) return fail(PSLOT_ERR_ARG, "kps / desc32 is null");
+    bool refetch = false;
+    for (int s = 0; s < n_images; ++s) {
+        const int count = hc[s];
+        if (count == 0) continue;
+        pslot_keypoint *ok = kps + (size_t)s * cap;
+        uint8_t *od = desc32 + (size_t)s * cap * 32;
         if (count <= guess) {
-            memcpy(kps, hk, sizeof(pslot_keypoint) * (size_t)count);
-            memcpy(desc32, hd, 32 * (size_t)count);
+            memcpy(ok, hk + (size_t)s * guess, sizeof(pslot_keypoint) * (size_t)count);
+            memcpy(od, hd + (size_t)s * guess * 32, 32 * (size_t)count);
         } else { // massive response ties kept by retainBest: fetch the full set
-            CU(cudaMemcpyAsync(kps, C.b.out_kps, sizeof(pslot_keypoint) * (size_t)count, cudaMemcpyDeviceToHost, C.st));
-            CU(cudaMemcpyAsync(desc32, C.b.out_desc, 32 * (size_t)count, cudaMemcpyDeviceToHost, C.st));
-            CU(cudaStreamSynchronize(C.st));
+            CU(cudaMemcpyAsync(ok, C.b.out_kps + (size_t)s * C.g.slot_kp, sizeof(pslot_keypoint) * (size_t)count, cudaMemcpyDeviceToHost, C.st));
+            CU(cudaMemcpyAsync(od, C.b.out_desc + (size_t)s * C.g.slot_kp * 32, 32 * (size_t)count, cudaMemcpyDeviceToHost, C.st));
+            refetch = true;
         }
     }
+    if (refetch) CU(cudaStreamSynchronize(C.st));
+    const auto t4 = std::chrono::steady_clock::now();
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    C.t_phase[0] = ms(t0, t1); C.t_phase[1] = ms(t1, t2); C.t_phase[2] = ms(t2, t3); C.t_phase[3] = ms(t3, t4);
     return PSLOT_OK;
+}
+
+int pslot_cvorb_last_timing(const pslot_cvorb *ctx, double out_ms[4])
+{
+    if (!ctx || !out_ms) return fail(PSLOT_ERR_ARG, "null argument");
+    for (int i = 0; i < 4; ++i) out_ms[i] = ctx->t_phase[i];
+    return PSLOT_OK;
+}
+
+int pslot_cvorb_detect_and_compute(pslot_cvorb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, const uint8_t *mask,
+                                   ptrdiff_t mask_pitch, pslot_keypoint *kps, uint8_t *desc32, int cap, int *n)
+{
+    if (!ctx || !n) return fail(PSLOT_ERR_ARG, "ctx / n is null");
+    *n = 0;
+    if (!img || w <= 0 || h <= 0) return PSLOT_OK; // empty image: no keypoints
+    return pslot_cvorb_detect_and_compute_batch(ctx, 1, &img, w, h, pitch, mask ? &mask : nullptr, mask_pitch, kps, desc32,
+                                                cap < 0 ? 0 : cap, n);
 }
 
 // ---- bag of words ------------------------------------------------------------------------------------------------------

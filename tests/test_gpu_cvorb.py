@@ -103,6 +103,51 @@ def test_cvorb_varied_content_and_parameters(B):
     _assert_equal(k, d, ref, rdesc, "pitched input")
 
 
+def test_cvorb_batch_equals_cv2_orb(B):
+    """pslot_cvorb_detect_and_compute_batch (the two views of Frame::ExtractObjORB, Frame.cc:2648-2651, or more frames in one
+    call): every image of the batch equals cv2.ORB_create on that image - with masks, with a mask on some images only,
+    without masks - and the same context then serves other batch sizes and the single-image call."""
+    from pointslot_b200.synth import synth_pair
+    H, W = 375, 1242
+    imgs = []
+    for seed in (31, 32, 33):
+        imgs.extend(synth_pair(W, H, seed))
+    m1 = _object_mask(H, W)
+    m2 = np.zeros((H, W), np.uint8); m2[60:300, 500:1100] = 255
+    orb = B.CvOrb(1000, 1.2, 8, 19)
+    want = {}
+
+    def ref(i, m):
+        key = (i, None if m is None else id(m))
+        if key not in want:
+            want[key] = _cv2_sorted(imgs[i], m)
+        return want[key]
+
+    # left + right with their object masks: the reference's call pattern
+    out = orb.detect_and_compute_batch(imgs[:2], [m1, m2])
+    for i, m in ((0, m1), (1, m2)):
+        _assert_equal(*out[i], *ref(i, m), f"pair, image {i}")
+    # six images, masks on some
+    masks = [m1, None, m2, None, None, m1]
+    out = orb.detect_and_compute_batch(imgs, masks)
+    assert len(out) == 6
+    for i, m in enumerate(masks):
+        _assert_equal(*out[i], *ref(i, m), f"batch of 6, image {i}")
+    # no masks at all, a smaller batch on the same context, then the single-image entry point
+    out = orb.detect_and_compute_batch(imgs[:3])
+    for i in range(3):
+        _assert_equal(*out[i], *ref(i, None), f"batch of 3, image {i}")
+        k, d = orb.detect_and_compute(imgs[i])
+        assert k.tobytes() == out[i][0].tobytes() and np.array_equal(d, out[i][1])
+    assert orb.detect_and_compute_batch([]) == []
+    # another size re-configures the context; noise overflows every quota and keeps response ties
+    rng = np.random.default_rng(5)
+    noise = [rng.integers(0, 256, (150, 210), dtype=np.uint8) for _ in range(4)]
+    out = orb.detect_and_compute_batch(noise)
+    for i in range(4):
+        _assert_equal(*out[i], *_cv2_sorted(noise[i], None), f"noise batch, image {i}")
+
+
 def test_cvorb_argument_errors(B):
     with pytest.raises(B.PslotError):
         B.CvOrb(1000, 1.0, 8, 19)

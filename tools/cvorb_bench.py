@@ -26,6 +26,35 @@ for name, (W, H) in (("kitti 1242x375", (1242, 375)), ("euroc 752x480", (752, 48
             n += len(k)
         dev_ms = (time.perf_counter() - t0) / reps * 1e3
         r = {"device_ms_per_image": dev_ms, "keypoints_per_image": n / reps}
+        # batched entry point (pslot_cvorb_detect_and_compute_batch): the left + right pair of Frame::ExtractObjORB, and
+        # whole-sequence batches; host images in, host results out, wall clock per image
+        for nb in (2, 8, 32, 64):
+            batch = [imgs[i % 8] for i in range(nb)]
+            masks = None if m is None else [m] * nb
+            for _ in range(3):
+                orb.detect_and_compute_batch(batch, masks)
+            rb = max(4, reps // nb)
+            t0 = time.perf_counter()
+            for _ in range(rb):
+                orb.detect_and_compute_batch(batch, masks)
+            r[f"device_ms_per_image_batch{nb}"] = (time.perf_counter() - t0) / (rb * nb) * 1e3
+            r[f"abi_phases_ms_batch{nb}"] = [round(float(v), 4) for v in orb.last_timing()]
+        # the same 64-image batch from page-locked host memory (pslot_host_alloc): the uploads run at link speed
+        pin = B.PinnedBuffer((64, H, W)); pm = B.PinnedBuffer((H, W))
+        for i in range(64):
+            pin.array[i] = imgs[i % 8]
+        pm.array[:] = mask
+        batch = [pin.array[i] for i in range(64)]
+        masks = None if m is None else [pm.array] * 64
+        for _ in range(3):
+            orb.detect_and_compute_batch(batch, masks)
+        t0 = time.perf_counter()
+        for _ in range(max(4, reps // 64)):
+            orb.detect_and_compute_batch(batch, masks)
+        r["device_ms_per_image_batch64_pinned"] = (time.perf_counter() - t0) / (max(4, reps // 64) * 64) * 1e3
+        r["abi_phases_ms_batch64_pinned"] = [round(float(v), 4) for v in orb.last_timing()]
+        del batch, masks
+        pin.close(); pm.close()
         try:
             import cv2
             cv2.setNumThreads(1)
