@@ -70,11 +70,10 @@ k_cv_resize_exact(const uint8_t *__restrict__ src_img, const uint8_t *__restrict
 // of every opposite pair, so both compass pairs need a member farther than t from the centre) on the word and its four
 // compass words; the word's scores are cleared and the few pixels that pass go to a shared list.  Pass 2: the listed
 // pixels, one per thread on dense warps, get the exact score.  blockIdx.x numbers the tiles of all levels, blockIdx.y = slot.
-template <bool NMS>
 __device__ __forceinline__ int tile_level(const CvGeom &g, int tile)
 {
     int l = 0;
-    while (l + 1 < g.nlevels && tile >= (NMS ? g.lv[l + 1].nms_tile_base : g.lv[l + 1].tile_base)) ++l;
+    while (l + 1 < g.nlevels && tile >= g.lv[l + 1].tile_base) ++l;
     return l;
 }
 
@@ -103,39 +102,55 @@ __device__ __forceinline__ int fast_score_exact(const uint8_t *p, int P)
     return max(hi, -lo) - 1;
 }
 
+constexpr int CT_ROWS = 32; // tile = 128 px x 32 rows: a thread owns one word column and the rows warp, warp + 8, ...
+
 __global__ void __launch_bounds__(256)
 k_cv_fast_score(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ pyr, uint8_t *__restrict__ score)
 {
-    __shared__ uint32_t s_list[1024];
+    __shared__ uint32_t s_list[128 * CT_ROWS];
     __shared__ int s_n;
-    const int l = tile_level<false>(g, blockIdx.x);
+    const int l = tile_level(g, blockIdx.x);
     const CvLevel &L = g.lv[l];
     const int tile = blockIdx.x - L.tile_base, ty = tile / L.tiles_x, tx = tile - ty * L.tiles_x;
-    const int gx = tx * 32 + (threadIdx.x & 31), y = ty * 8 + (threadIdx.x >> 5) + g.edge - 1;
+    const int gx = tx * 32 + (threadIdx.x & 31), y0 = ty * CT_ROWS + (threadIdx.x >> 5) + g.edge - 1;
     const int P = L.pitch, PW = P >> 2, t = g.fast_th;
-    const int x_lo = g.edge - 1, x_hi = L.w - g.edge; // scored columns, inclusive
+    const int x_lo = g.edge - 1, x_hi = L.w - g.edge, y_hi = L.h - g.edge; // scored columns / last row, inclusive
     pyr += blockIdx.y * g.slot_bytes + L.off;
     score += blockIdx.y * g.slot_bytes + L.off;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    if (y <= L.h - g.edge && 4 * gx <= x_hi && 4 * gx + 3 >= x_lo) {
-        const uint32_t *row = reinterpret_cast<const uint32_t *>(pyr + (size_t)y * P) + gx;
-        const uint32_t c = row[0], lft = gx > 0 ? row[-1] : 0u, rgt = gx + 1 < PW ? row[1] : 0u;
-        const uint32_t top = row[-3 * PW], bot = row[3 * PW];
-        const uint32_t east = __funnelshift_r(c, rgt, 24), west = __funnelshift_r(lft, c, 8); // pixels x + 3 / x - 3
-        const uint32_t d0 = __vabsdiffu4(bot, c), d8 = __vabsdiffu4(top, c), d4 = __vabsdiffu4(east, c), d12 = __vabsdiffu4(west, c);
-        // bit 7 of ((d + 127 - t) | d) is set where d > t; a carry from the byte below only adds a false positive
-        const uint32_t bias = t <= 127 ? (uint32_t)(127 - t) * 0x01010101u : 0u;
-        const uint32_t e0 = (d0 + bias) | d0, e8 = (d8 + bias) | d8, e4 = (d4 + bias) | d4, e12 = (d12 + bias) | d12;
-        uint32_t pass = (e0 | e8) & (e4 | e12) & 0x80808080u;
+    if (4 * gx <= x_hi && 4 * gx + 3 >= x_lo) {
+        // all 20 words of the thread's four rows are requested before the first one is used
+        uint32_t c[4], lft[4], rgt[4], top[4], bot[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int y = min(y0 + 8 * i, y_hi); // clamped rows repeat the last one; their result is dropped below
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(pyr + (size_t)y * P) + gx;
+            c[i] = row[0]; lft[i] = gx > 0 ? row[-1] : 0u; rgt[i] = gx + 1 < PW ? row[1] : 0u;
+            top[i] = row[-3 * PW]; bot[i] = row[3 * PW];
+        }
+        // columns of this word outside the scored band
+        uint32_t colmask = 0x80808080u;
 #pragma unroll
         for (int b = 0; b < 4; ++b)
-            if (4 * gx + b < x_lo || 4 * gx + b > x_hi) pass &= ~(0x80u << (8 * b));
-        reinterpret_cast<uint32_t *>(score + (size_t)y * P)[gx] = 0u;
-        while (pass) {
-            const int b = (__ffs((int)pass) - 1) >> 3;
-            s_list[atomicAdd(&s_n, 1)] = ((uint32_t)y << 16) | (uint32_t)(4 * gx + b);
-            pass &= pass - 1;
+            if (4 * gx + b < x_lo || 4 * gx + b > x_hi) colmask &= ~(0x80u << (8 * b));
+        // bit 7 of ((d + 127 - t) | d) is set where d > t; a carry from the byte below only adds a false positive
+        const uint32_t bias = t <= 127 ? (uint32_t)(127 - t) * 0x01010101u : 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int y = y0 + 8 * i;
+            if (y > y_hi) break;
+            const uint32_t east = __funnelshift_r(c[i], rgt[i], 24), west = __funnelshift_r(lft[i], c[i], 8); // pixels x + 3 / x - 3
+            const uint32_t d0 = __vabsdiffu4(bot[i], c[i]), d8 = __vabsdiffu4(top[i], c[i]);
+            const uint32_t d4 = __vabsdiffu4(east, c[i]), d12 = __vabsdiffu4(west, c[i]);
+            const uint32_t e0 = (d0 + bias) | d0, e8 = (d8 + bias) | d8, e4 = (d4 + bias) | d4, e12 = (d12 + bias) | d12;
+            uint32_t pass = (e0 | e8) & (e4 | e12) & colmask;
+            reinterpret_cast<uint32_t *>(score + (size_t)y * P)[gx] = 0u;
+            while (pass) {
+                const int b = (__ffs((int)pass) - 1) >> 3;
+                s_list[atomicAdd(&s_n, 1)] = ((uint32_t)y << 16) | (uint32_t)(4 * gx + b);
+                pass &= pass - 1;
+            }
         }
     }
     __syncthreads(); // also orders the cleared words before the score bytes written below
@@ -148,18 +163,18 @@ k_cv_fast_score(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ py
 }
 
 // strict 3x3 maxima over the whole level, runByPixelsMask, runByImageBorder; survivors go to the level's candidate list
-// (unordered: everything downstream is a set operation until the final sort).  Tile = 128 px x 32 rows: a CTA gathers its
-// survivors in shared memory and reserves its piece of the level's list with ONE atomic (a counter per candidate
-// serialised 20 000 atomics per image on eight addresses: 407 -> see DESIGN.md).
+// (unordered: everything downstream is a set operation until the final sort).  Same tiles: a CTA gathers its survivors in
+// shared memory and reserves its piece of the level's list with ONE atomic (a global counter per candidate serialised
+// 20 000 atomics per image on eight addresses: 407 us per 64 images, 117 us like this).
 __global__ void __launch_bounds__(256)
 k_cv_nms_collect(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ score, const uint8_t *__restrict__ mask,
                  uint32_t *__restrict__ cand, int *__restrict__ counters, int *__restrict__ hist, int *__restrict__ err)
 {
-    __shared__ uint32_t s_c[1024]; // strict 3x3 maxima: at most one per 2x2 block of the 128 x 32 tile
+    __shared__ uint32_t s_c[32 * CT_ROWS]; // strict 3x3 maxima: at most one per 2x2 block of the tile
     __shared__ int s_n, s_base;
-    const int l = tile_level<true>(g, blockIdx.x), slot = blockIdx.y;
+    const int l = tile_level(g, blockIdx.x), slot = blockIdx.y;
     const CvLevel &L = g.lv[l];
-    const int tile = blockIdx.x - L.nms_tile_base, ty = tile / L.tiles_x, tx = tile - ty * L.tiles_x;
+    const int tile = blockIdx.x - L.tile_base, ty = tile / L.tiles_x, tx = tile - ty * L.tiles_x;
     const int gx = tx * 32 + (threadIdx.x & 31);
     const int P = L.pitch;
     score += slot * g.slot_bytes + L.off;
@@ -167,11 +182,17 @@ k_cv_nms_collect(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ s
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     if (4 * gx + 3 >= g.edge && 4 * gx < L.w - g.edge) {
-        for (int r = threadIdx.x >> 5; r < 32; r += 8) {
-            const int y = ty * 32 + r + g.edge; // candidates live in [edge, h - edge)
-            if (y >= L.h - g.edge) break;
-            uint32_t w = *reinterpret_cast<const uint32_t *>(score + (size_t)y * P + 4 * gx);
-            for (; w; ) {
+        const int y0 = ty * CT_ROWS + (threadIdx.x >> 5) + g.edge; // candidates live in [edge, h - edge)
+        uint32_t wv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int y = y0 + 8 * i;
+            wv[i] = y < L.h - g.edge ? *reinterpret_cast<const uint32_t *>(score + (size_t)y * P + 4 * gx) : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int y = y0 + 8 * i;
+            for (uint32_t w = wv[i]; w;) {
                 const int b = (__ffs((int)w) - 1) >> 3;
                 w &= ~(0xFFu << (8 * b));
                 const int x = 4 * gx + b;
@@ -198,12 +219,43 @@ k_cv_nms_collect(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ s
     }
 }
 
+// ---- k-th largest over a 256-bin histogram, block-parallel ----------------------------------------------------------------------
+// Threads 0..255 each hold one bin count (threads beyond hold 0; the first 8 warps must all call).  Returns in every thread
+// the highest bin d whose suffix sum S(d) = sum_{b >= d} cnt[b] reaches k (0 when the whole histogram holds fewer than k),
+// and via `above` the number of entries in bins > d.  One suffix scan instead of a serial walk by thread 0 (ncu: 52 % of
+// k_cv_harris' stall samples sat on the barrier behind that walk).
+__device__ __forceinline__ int kth_bin_from_top(int cnt, int k, int *s_part /* >= 10 ints */, int &above)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // inclusive suffix sum inside the warp (towards higher lanes = higher bins)
+    int suf = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += v;
+    }
+    if (tid < 256 && lane == 0) s_part[warp] = suf; // warp total
+    if (tid == 0) { s_part[8] = 0; s_part[9] = 0; }
+    __syncthreads();
+    int higher = 0; // bins of the warps above this one
+    if (tid < 256)
+        for (int w = warp + 1; w < 8; ++w) higher += s_part[w];
+    const int S = suf + higher;     // S(tid)
+    const int S1 = S - cnt;         // S(tid + 1)
+    if (tid < 256 && S >= k && S1 < k) { s_part[8] = tid; s_part[9] = S1; }
+    __syncthreads();
+    const int d = s_part[8];
+    above = s_part[9];
+    __syncthreads(); // s_part may be reused by the caller's next pass
+    return d;
+}
+
 // ---- retainBest(2 * quota) on the FAST score, then HarrisResponses -----------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_cv_harris(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ pyr, const uint32_t *__restrict__ cand,
             int *__restrict__ counters, const int *__restrict__ hist, uint32_t *__restrict__ kept, float *__restrict__ kept_resp)
 {
-    __shared__ int s_thr;
+    __shared__ int s_part[10];
     const int l = blockIdx.y, slot = blockIdx.z;
     const CvLevel &L = g.lv[l];
     pyr += slot * g.slot_bytes;
@@ -211,21 +263,11 @@ k_cv_harris(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ pyr, c
     counters += slot * CV_CNT_TOTAL;
     hist += slot * PSLOT_MAX_LEVELS * 256;
     const int n = min(counters[CV_CNT_CAND + l], L.cand_cap);
-    if (threadIdx.x == 0) {
-        // KeyPointsFilter::retainBest(keypoints, 2 * quota): keep everything >= the response of the (2 * quota)-th best
-        const int keep = 2 * L.quota;
-        int thr = 0;
-        if (n > keep) {
-            int acc = 0;
-            for (int sc = 255; sc >= 0; --sc) {
-                acc += hist[l * 256 + sc];
-                if (acc >= keep) { thr = sc; break; }
-            }
-        }
-        s_thr = keep == 0 ? 256 : thr;
-    }
-    __syncthreads();
-    const int thr = s_thr;
+    // KeyPointsFilter::retainBest(keypoints, 2 * quota): keep everything >= the response of the (2 * quota)-th best
+    const int keep = 2 * L.quota;
+    int above;
+    const int bin = kth_bin_from_top(hist[l * 256 + threadIdx.x], keep, s_part, above);
+    const int thr = keep == 0 ? 256 : n > keep ? bin : 0;
     const float harris_k = 0.04f;
     const float scale1 = 1.f / ((1 << 2) * 7 * 255.f);
     const float scale_sq_sq = __fmul_rn(__fmul_rn(__fmul_rn(scale1, scale1), scale1), scale1);
@@ -270,7 +312,7 @@ k_cv_select(const __grid_constant__ CvGeom g, const uint32_t *__restrict__ kept,
     __shared__ unsigned long long s_e[CV_SORT_CAP];
     __shared__ int s_hist[256];
     __shared__ uint32_t s_prefix;
-    __shared__ int s_k, s_n;
+    __shared__ int s_k, s_n, s_part[10];
     const int l = blockIdx.x, slot = blockIdx.y, tid = threadIdx.x;
     const CvLevel &L = g.lv[l];
     counters += slot * CV_CNT_TOTAL;
@@ -293,13 +335,11 @@ k_cv_select(const __grid_constant__ CvGeom g, const uint32_t *__restrict__ kept,
                 if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255], 1);
             }
             __syncthreads();
+            int above;
+            const int kk = s_k;
+            const int d = kth_bin_from_top(tid < 256 ? s_hist[tid] : 0, kk, s_part, above); // kk <= entries matching the prefix
             if (tid == 0) {
-                int acc = 0, k = s_k, d = 255;
-                for (; d > 0; --d) {
-                    if (acc + s_hist[d] >= k) break;
-                    acc += s_hist[d];
-                }
-                s_k = k - acc;
+                s_k = kk - above;
                 s_prefix = prefix | ((uint32_t)d << shift);
             }
             mask |= 255u << shift;
@@ -530,7 +570,7 @@ int launch_cvorb(const CvGeom &g, const CvBuffers &b, int slots, bool has_mask, 
     cudaMemsetAsync(b.counters, 0, sizeof(int) * CV_CNT_TOTAL * slots, st);
     cudaMemsetAsync(b.hist, 0, sizeof(int) * 256 * PSLOT_MAX_LEVELS * slots, st);
     k_cv_fast_score<<<dim3(g.n_tiles, slots), 256, 0, st>>>(g, b.pyr, b.score);
-    k_cv_nms_collect<<<dim3(g.n_nms_tiles, slots), 256, 0, st>>>(g, b.score, has_mask ? b.mask : nullptr, b.cand, b.counters, b.hist,
+    k_cv_nms_collect<<<dim3(g.n_tiles, slots), 256, 0, st>>>(g, b.score, has_mask ? b.mask : nullptr, b.cand, b.counters, b.hist,
                                                                 b.err);
     k_cv_harris<<<dim3(slots > 8 ? 8 : 32, g.nlevels, slots), 256, 0, st>>>(g, b.pyr, b.cand, b.counters, b.hist, b.kept, b.kept_resp);
     k_cv_select<<<dim3(g.nlevels, slots), 1024, 0, st>>>(g, b.kept, b.kept_resp, b.counters, b.final_kp, b.final_resp, b.err);

@@ -475,7 +475,8 @@ struct pslot_batch {
 struct pslot_cvorb {
     int nfeatures = 0, nlevels = 0, edge = 0, fast_th = 0, device = 0;
     double scale_factor = 1.2;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st_up = nullptr; // kernels + downloads / uploads (a batch is uploaded in chunks that run ahead)
+    cudaEvent_t ev_up[4] = {nullptr, nullptr, nullptr, nullptr};
     int W = 0, H = 0, slots = 0; // geometry and number of image slots the buffers are sized for
     CvGeom g{};
     CvBuffers b{};
@@ -502,6 +503,9 @@ struct pslot_cvorb {
         release();
         if (h_err) cudaFreeHost(h_err);
         if (h_out) cudaFreeHost(h_out);
+        for (cudaEvent_t e : ev_up)
+            if (e) cudaEventDestroy(e);
+        if (st_up) cudaStreamDestroy(st_up);
         if (st) cudaStreamDestroy(st);
     }
 };
@@ -542,11 +546,25 @@ void exact_taps(int n_dst, int n_src, int2 *out)
     }
 }
 
+// the buffers of slots s0.. as a CvBuffers of their own (a chunk of a batch)
+CvBuffers cv_slot_view(const CvGeom &g, const CvBuffers &b, int s0)
+{
+    CvBuffers v = b;
+    const size_t s = (size_t)s0;
+    v.pyr += s * g.slot_bytes; v.mask += s * g.slot_bytes; v.score += s * g.slot_bytes;
+    v.cand += s * g.slot_cand; v.kept += s * g.slot_cand; v.kept_resp += s * g.slot_cand;
+    v.final_kp += s * g.slot_kp; v.final_resp += s * g.slot_kp;
+    v.out_kps += s * g.slot_kp; v.out_desc += s * g.slot_kp * 32; v.out_count += s;
+    v.counters += s * CV_CNT_TOTAL; v.hist += s * 256 * PSLOT_MAX_LEVELS;
+    return v;
+}
+
 int cvorb_configure(pslot_cvorb &c, int w, int h, int slots)
 {
     if (w == c.W && h == c.H && slots <= c.slots) return PSLOT_OK;
     if (w > 4095 || h > 4095) return fail(PSLOT_ERR_SHAPE, "image %dx%d exceeds 4095 px", w, h);
     if (w == c.W && h == c.H) slots = std::max(slots, std::min(2 * c.slots, 1024)); // growing batch: amortise the re-allocation
+    CU(cudaStreamSynchronize(c.st_up));
     CU(cudaStreamSynchronize(c.st));
     c.release();
     CvGeom &G = c.g;
@@ -568,7 +586,7 @@ int cvorb_configure(pslot_cvorb &c, int w, int h, int slots)
     }
     std::vector<int2> taps;
     size_t off = 0;
-    int cand = 0, nl = 0, tiles = 0, nms_tiles = 0, max_quota = 1;
+    int cand = 0, nl = 0, tiles = 0, max_quota = 1;
     for (int l = 0; l < c.nlevels; ++l) {
         const float scale = (float)pow(c.scale_factor, (double)l);
         const int lw = cv_round((double)((float)w / scale)), lh = cv_round((double)((float)h / scale));
@@ -586,10 +604,8 @@ int cvorb_configure(pslot_cvorb &c, int w, int h, int slots)
         // only scores within one pixel of the border filter's interior can matter: rows / columns [edge - 1, dim - edge]
         const int band_rows = lh - 2 * c.edge + 2;
         L.tile_base = tiles;
-        L.nms_tile_base = nms_tiles;
         L.tiles_x = (lw + 127) / 128;
-        tiles += L.tiles_x * ((band_rows + 7) / 8);
-        nms_tiles += L.tiles_x * ((band_rows + 31) / 32);
+        tiles += L.tiles_x * ((band_rows + 31) / 32);
         max_quota = std::max(max_quota, quota[l]);
         if (l > 0) {
             L.tab_x = (int)taps.size(); taps.resize(taps.size() + lw);
@@ -605,7 +621,6 @@ int cvorb_configure(pslot_cvorb &c, int w, int h, int slots)
     G.slot_cand = cand;
     G.slot_kp = CV_SORT_CAP * nl;
     G.n_tiles = tiles;
-    G.n_nms_tiles = nms_tiles;
     G.describe_blocks = std::min(CV_SORT_CAP / 4, (max_quota + 3) / 4);
     c.level_bytes = off;
     c.cand_total = cand;
@@ -997,6 +1012,9 @@ int pslot_cvorb_create(pslot_cvorb **ctx, int nfeatures, float scale_factor, int
     c->scale_factor = (double)scale_factor; // ORB::create takes a float, the member is a double
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->st_up, cudaStreamNonBlocking);
+    for (cudaEvent_t &ev : c->ev_up)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&c->h_err, sizeof(int), cudaHostAllocMapped);
     if (e != cudaSuccess) { delete c; return fail(PSLOT_ERR_CUDA, "pslot_cvorb_create: %s", cudaGetErrorString(e)); }
     *c->h_err = 0;
@@ -1008,6 +1026,7 @@ void pslot_cvorb_destroy(pslot_cvorb *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->st_up) cudaStreamSynchronize(ctx->st_up);
     if (ctx->st) cudaStreamSynchronize(ctx->st);
     delete ctx;
 }
@@ -1034,38 +1053,62 @@ int pslot_cvorb_detect_and_compute_batch(pslot_cvorb *ctx, int n_images, const u
     if (int rc = cvorb_configure(C, w, h, n_images)) return rc;
     const CvLevel &L0 = C.g.lv[0];
     const auto t0 = std::chrono::steady_clock::now();
-    if (pitch == w && (!any_mask || mask_pitch == w)) {
-        // tightly packed rows: linear copies at the full PCIe rate into a staging buffer (images that follow each other in
-        // host memory travel as one copy), then one re-pitch launch into the 128-byte aligned level-0 rows of all slots
-        // (a 2-D copy of 1242-byte rows runs far below the link rate)
-        const size_t img_bytes = (size_t)w * h;
+    // A larger batch travels in up to four chunks: chunk k + 1 is uploaded (second stream) while chunk k is processed.
+    // Page-locked images arrive at link speed (0.55 ms per 64 KITTI frames): two chunks hide half of that at little cost in
+    // smaller launches; pageable images are staged by the driver at a fifth of the rate: four chunks.
+    int nchunks = 1;
+    if (n_images >= 16) {
+        cudaPointerAttributes pa{};
+        const bool pinned = cudaPointerGetAttributes(&pa, imgs[0]) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError(); // an unregistered pointer is not an error here
+        nchunks = pinned ? (n_images >= 32 ? 2 : 1) : 4;
+    }
+    const int chunk = (n_images + nchunks - 1) / nchunks;
+    const bool tight = pitch == w && (!any_mask || mask_pitch == w);
+    const size_t img_bytes = (size_t)w * h;
+    double t_up = 0;
+    for (int c0 = 0, ci = 0; c0 < n_images; c0 += chunk, ++ci) {
+        const int c1 = std::min(c0 + chunk, n_images);
+        const auto u0 = std::chrono::steady_clock::now();
         for (int view = 0; view < (any_mask ? 2 : 1); ++view) {
             const uint8_t *const *src = view ? masks : imgs;
-            uint8_t *stg = C.d_stage + view * C.stage_view;
-            for (int s = 0; s < n_images;) {
-                if (!src[s]) { // no mask for this image of a masked batch: keep everything
-                    CU(cudaMemsetAsync(stg + s * img_bytes, 255, img_bytes, C.st));
-                    ++s;
-                    continue;
+            if (tight) {
+                // tightly packed rows: linear copies at the full PCIe rate into a staging buffer (images that follow each other
+                // in host memory travel as one copy); a re-pitch launch then fills the 128-byte aligned level-0 rows (a 2-D
+                // copy of 1242-byte rows runs far below the link rate)
+                uint8_t *stg = C.d_stage + view * C.stage_view;
+                for (int s = c0; s < c1;) {
+                    if (!src[s]) { // no mask for this image of a masked batch: keep everything
+                        CU(cudaMemsetAsync(stg + s * img_bytes, 255, img_bytes, C.st_up));
+                        ++s;
+                        continue;
+                    }
+                    int e = s + 1;
+                    while (e < c1 && src[e] == src[e - 1] + img_bytes) ++e;
+                    CU(cudaMemcpyAsync(stg + s * img_bytes, src[s], img_bytes * (size_t)(e - s), cudaMemcpyHostToDevice, C.st_up));
+                    s = e;
                 }
-                int e = s + 1;
-                while (e < n_images && src[e] == src[e - 1] + img_bytes) ++e;
-                CU(cudaMemcpyAsync(stg + s * img_bytes, src[s], img_bytes * (size_t)(e - s), cudaMemcpyHostToDevice, C.st));
-                s = e;
+            } else {
+                uint8_t *dst = (view ? C.b.mask : C.b.pyr) + L0.off;
+                const ptrdiff_t sp = view ? mask_pitch : pitch;
+                for (int s = c0; s < c1; ++s) {
+                    uint8_t *d = dst + s * (size_t)C.g.slot_bytes;
+                    if (src[s]) CU(cudaMemcpy2DAsync(d, L0.pitch, src[s], sp, w, h, cudaMemcpyHostToDevice, C.st_up));
+                    else CU(cudaMemset2DAsync(d, L0.pitch, 255, w, h, C.st_up));
+                }
             }
-            launch_gray_ingest(stg, img_bytes, 1, 0, (view ? C.b.mask : C.b.pyr) + L0.off, w, h, L0.pitch, C.g.slot_bytes, n_images, C.st);
         }
-    } else {
-        for (int s = 0; s < n_images; ++s) {
-            const size_t o = s * (size_t)C.g.slot_bytes + L0.off;
-            CU(cudaMemcpy2DAsync(C.b.pyr + o, L0.pitch, imgs[s], pitch, w, h, cudaMemcpyHostToDevice, C.st));
-            if (!any_mask) continue;
-            if (masks[s]) CU(cudaMemcpy2DAsync(C.b.mask + o, L0.pitch, masks[s], mask_pitch, w, h, cudaMemcpyHostToDevice, C.st));
-            else CU(cudaMemset2DAsync(C.b.mask + o, L0.pitch, 255, w, h, C.st)); // no mask for this image of a masked batch: keep all
-        }
+        CU(cudaEventRecord(C.ev_up[ci], C.st_up));
+        CU(cudaStreamWaitEvent(C.st, C.ev_up[ci], 0));
+        t_up += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - u0).count();
+        if (tight)
+            for (int view = 0; view < (any_mask ? 2 : 1); ++view)
+                launch_gray_ingest(C.d_stage + view * C.stage_view + c0 * img_bytes, img_bytes, 1, 0,
+                                   (view ? C.b.mask : C.b.pyr) + c0 * (size_t)C.g.slot_bytes + L0.off, w, h, L0.pitch, C.g.slot_bytes,
+                                   c1 - c0, C.st);
+        launch_cvorb(C.g, cv_slot_view(C.g, C.b, c0), c1 - c0, any_mask, C.st);
     }
-    const auto t1 = std::chrono::steady_clock::now();
-    launch_cvorb(C.g, C.b, n_images, any_mask, C.st);
+    const auto t1 = t0 + std::chrono::duration_cast<std::chrono::steady_clock::duration>(std::chrono::duration<double, std::milli>(t_up));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "cv::ORB launch failed: %s", cudaGetErrorString(e));
     // one round trip: the counts and the (almost always sufficient) first `guess` records of every image travel together

@@ -158,8 +158,7 @@ struct CvLevel {
     int tab_x, tab_y;        // INTER_LINEAR_EXACT tap tables (source index, 8-bit fraction)
     int cand_base, cand_cap; // segment of the candidate / kept arrays
     int kp_base;             // segment of the final per-level keypoint lists (CV_SORT_CAP entries each)
-    int tile_base, tiles_x;  // 128 px x 8 row tiles of the scored band (rows from edge - 1), numbered level after level
-    int nms_tile_base;       // 128 px x 32 row tiles of the same band for the maxima / collect kernel
+    int tile_base, tiles_x;  // 128 px x 32 row tiles of the scored band (rows from edge - 1), numbered level after level
 };
 struct CvGeom {
     int nlevels, edge, fast_th;
@@ -170,7 +169,7 @@ struct CvGeom {
     int slot_cand;                 // cand / kept / kept_resp entries
     int slot_kp;                   // final_kp / final_resp / out_kps / out_desc entries (CV_SORT_CAP per level)
     int describe_blocks;           // grid.x of k_cv_describe (grid-stride over a level's keypoints)
-    int n_tiles, n_nms_tiles;      // sum of the levels' tiles: grid.x of the score / maxima kernels
+    int n_tiles;                   // sum of the levels' tiles: grid.x of the score / maxima kernels
 };
 constexpr int CV_SORT_CAP = 4096; // keypoints one level can keep after retainBest(quota) incl. ties (on-chip sort)
 enum : int { CV_CNT_CAND = 0, CV_CNT_KEPT = PSLOT_MAX_LEVELS, CV_CNT_FINAL = 2 * PSLOT_MAX_LEVELS, CV_CNT_TOTAL = 3 * PSLOT_MAX_LEVELS };
