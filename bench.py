@@ -662,6 +662,48 @@ def single_pair_latency(cfg, local_rank, reps=30):
     return float(np.median(ts) * 1e3)
 
 
+def measure_cvorb(Ls, Rs, W, H, local_rank, seconds=1.0):
+    """SURVEY §8f row 4 (next row): OpenCV's own ORB for the dense object features, reference Frame.cc:2623-2665 - the pair
+    (left + right view with object masks, one batched call: what Frame::ExtractObjORB does per frame) and a 64-image batch,
+    through the C ABI from page-locked host images, wall clock; cv2.ORB_create on one host core beside it when importable."""
+    from pointslot_b200 import binding as B
+    n = min(64, len(Ls))
+    pin = B.PinnedBuffer((n, H, W)); pm = B.PinnedBuffer((H, W))
+    for i in range(n):
+        pin.array[i] = Ls[i] if i % 2 == 0 else Rs[i]
+    pm.array[:] = 0
+    pm.array[H // 4:3 * H // 4, W // 6:W // 2] = 255; pm.array[H // 8:H // 2, 2 * W // 3:W - 40] = 255
+    orb = B.CvOrb(1000, 1.2, 8, 19, device=local_rank)
+    out = {"what": "cv::ORB::create(1000,1.2,8,19)->detectAndCompute(image, objectMask), host images in, host keypoints + descriptors out"}
+    for label, nb in (("pair", 2), ("batch64", n)):
+        batch = [pin.array[i] for i in range(nb)]
+        masks = [pm.array] * nb
+        for _ in range(3):
+            orb.detect_and_compute_batch(batch, masks)
+        reps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds / 2:
+            res = orb.detect_and_compute_batch(batch, masks)
+            reps += 1
+        dt = time.perf_counter() - t0
+        out[label] = {"images": nb, "ms_per_call": dt / reps * 1e3, "images_per_s": nb * reps / dt,
+                      "keypoints_per_image": float(np.mean([len(k) for k, _ in res])),
+                      "abi_phases_ms": [round(float(v), 4) for v in orb.last_timing()]}
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        c = cv2.ORB_create(1000, 1.2, 8, 19)
+        m = np.array(pm.array)
+        t0, reps = time.perf_counter(), 0
+        while time.perf_counter() - t0 < seconds / 2:
+            c.detectAndCompute(np.asarray(Ls[reps % n]), m)
+            reps += 1
+        out["cv2_one_core_images_per_s"] = reps / (time.perf_counter() - t0)
+    except ImportError:
+        pass
+    orb.close(); pin.close(); pm.close()
+    return out
+
+
 def hbm_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -798,6 +840,13 @@ def run_ours(args, rank, world, local_rank):
             if r is not None:
                 extras[name] = r
 
+    next_rows = {}
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            next_rows["cvorb"] = measure_cvorb(Ls, Rs, cfg["W"], cfg["H"], local_rank)
+        except Exception as e:  # a secondary row must not take the headline line down
+            next_rows["cvorb"] = {"error": repr(e)}
+
     if rank != 0:
         return
     total_pairs = pairs_step * world * args.steps
@@ -896,7 +945,7 @@ def run_ours(args, rank, world, local_rank):
                 "stage_ms_per_submit": {n: float(v) for n, v in zip(B.StereoBatch.STAGES, e2e_stage_ms)}},
         "gpu_launches": launches_per_submit * nsub * args.steps * world,
         "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clocks, "determinism": det,
-        "extra_configs": extras,
+        "extra_configs": extras, "next_rows": next_rows,
     }
     print(json.dumps(line), flush=True)
 

@@ -488,9 +488,18 @@ struct pslot_cvorb {
     uint8_t *d_stage = nullptr;     // tightly packed uploads (images, then masks) before the re-pitch kernel
     size_t stage_view = 0;          // bytes of one of its two halves
     double t_phase[4] = {0, 0, 0, 0}; // host clock of the last call: uploads enqueued, kernels enqueued, wait, copy-out (ms)
+    // the kernels + result downloads of an un-chunked call as one CUDA graph per (images, masks, tight input): ~20 launches
+    // become one (the per-frame pair of Frame::ExtractObjORB is latency-bound); dropped whenever a buffer they name moves
+    std::map<int, cudaGraphExec_t> graphs;
+    void drop_graphs()
+    {
+        for (auto &kv : graphs) cudaGraphExecDestroy(kv.second);
+        graphs.clear();
+    }
 
     void release()
     {
+        drop_graphs();
         cudaFree(d_stage); d_stage = nullptr;
         cudaFree(b.pyr); cudaFree(b.mask); cudaFree(b.score); cudaFree((void *)b.taps); cudaFree(b.cand); cudaFree(b.kept);
         cudaFree(b.final_kp); cudaFree(b.kept_resp); cudaFree(b.final_resp); cudaFree(b.counters); cudaFree(b.hist);
@@ -1066,6 +1075,37 @@ int pslot_cvorb_detect_and_compute_batch(pslot_cvorb *ctx, int n_images, const u
     const int chunk = (n_images + nchunks - 1) / nchunks;
     const bool tight = pitch == w && (!any_mask || mask_pitch == w);
     const size_t img_bytes = (size_t)w * h;
+    // one round trip: the counts and the (almost always sufficient) first `guess` records of every image travel together
+    // into pinned memory
+    const int guess = std::min(C.nfeatures + 64, C.g.slot_kp);
+    const size_t S = (size_t)n_images, hdr = align_up(sizeof(int) * S, 16);
+    const size_t need = hdr + S * guess * (sizeof(pslot_keypoint) + 32);
+    if (C.h_out_bytes < need) {
+        C.drop_graphs();
+        if (C.h_out) cudaFreeHost(C.h_out);
+        C.h_out = nullptr; C.h_out_bytes = 0;
+        CU(cudaHostAlloc((void **)&C.h_out, need, cudaHostAllocDefault));
+        C.h_out_bytes = need;
+    }
+    pslot_keypoint *hk = reinterpret_cast<pslot_keypoint *>(C.h_out + hdr);
+    uint8_t *hd = C.h_out + hdr + S * guess * sizeof(pslot_keypoint);
+    const int *hc = reinterpret_cast<const int *>(C.h_out);
+    auto device_work = [&](int c0, int c1) { // re-pitch + the kernels of slots [c0, c1) on the main stream
+        if (tight)
+            for (int view = 0; view < (any_mask ? 2 : 1); ++view)
+                launch_gray_ingest(C.d_stage + view * C.stage_view + c0 * img_bytes, img_bytes, 1, 0,
+                                   (view ? C.b.mask : C.b.pyr) + c0 * (size_t)C.g.slot_bytes + L0.off, w, h, L0.pitch, C.g.slot_bytes,
+                                   c1 - c0, C.st);
+        launch_cvorb(C.g, cv_slot_view(C.g, C.b, c0), c1 - c0, any_mask, C.st);
+    };
+    auto downloads = [&]() -> int {
+        CU(cudaMemcpyAsync(C.h_out, C.b.out_count, sizeof(int) * S, cudaMemcpyDeviceToHost, C.st));
+        CU(cudaMemcpy2DAsync(hk, sizeof(pslot_keypoint) * (size_t)guess, C.b.out_kps, sizeof(pslot_keypoint) * (size_t)C.g.slot_kp,
+                             sizeof(pslot_keypoint) * (size_t)guess, S, cudaMemcpyDeviceToHost, C.st));
+        CU(cudaMemcpy2DAsync(hd, 32 * (size_t)guess, C.b.out_desc, 32 * (size_t)C.g.slot_kp, 32 * (size_t)guess, S,
+                             cudaMemcpyDeviceToHost, C.st));
+        return PSLOT_OK;
+    };
     double t_up = 0;
     for (int c0 = 0, ci = 0; c0 < n_images; c0 += chunk, ++ci) {
         const int c1 = std::min(c0 + chunk, n_images);
@@ -1101,35 +1141,31 @@ int pslot_cvorb_detect_and_compute_batch(pslot_cvorb *ctx, int n_images, const u
         CU(cudaEventRecord(C.ev_up[ci], C.st_up));
         CU(cudaStreamWaitEvent(C.st, C.ev_up[ci], 0));
         t_up += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - u0).count();
-        if (tight)
-            for (int view = 0; view < (any_mask ? 2 : 1); ++view)
-                launch_gray_ingest(C.d_stage + view * C.stage_view + c0 * img_bytes, img_bytes, 1, 0,
-                                   (view ? C.b.mask : C.b.pyr) + c0 * (size_t)C.g.slot_bytes + L0.off, w, h, L0.pitch, C.g.slot_bytes,
-                                   c1 - c0, C.st);
-        launch_cvorb(C.g, cv_slot_view(C.g, C.b, c0), c1 - c0, any_mask, C.st);
+        if (nchunks > 1) device_work(c0, c1);
     }
     const auto t1 = t0 + std::chrono::duration_cast<std::chrono::steady_clock::duration>(std::chrono::duration<double, std::milli>(t_up));
+    if (nchunks > 1) {
+        if (int rc = downloads()) return rc;
+    } else {
+        const int key = n_images * 4 + (any_mask ? 2 : 0) + (tight ? 1 : 0);
+        auto it = C.graphs.find(key);
+        if (it == C.graphs.end()) {
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            CU(cudaStreamBeginCapture(C.st, cudaStreamCaptureModeThreadLocal));
+            device_work(0, n_images);
+            const int rc = downloads();
+            cudaError_t ce = cudaStreamEndCapture(C.st, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return fail(PSLOT_ERR_CUDA, "cv::ORB graph: %s", cudaGetErrorString(ce));
+            it = C.graphs.emplace(key, exec).first;
+        }
+        CU(cudaGraphLaunch(it->second, C.st));
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "cv::ORB launch failed: %s", cudaGetErrorString(e));
-    // one round trip: the counts and the (almost always sufficient) first `guess` records of every image travel together
-    // into pinned memory
-    const int guess = std::min(C.nfeatures + 64, C.g.slot_kp);
-    const size_t S = (size_t)n_images, hdr = align_up(sizeof(int) * S, 16);
-    const size_t need = hdr + S * guess * (sizeof(pslot_keypoint) + 32);
-    if (C.h_out_bytes < need) {
-        if (C.h_out) cudaFreeHost(C.h_out);
-        C.h_out = nullptr; C.h_out_bytes = 0;
-        CU(cudaHostAlloc((void **)&C.h_out, need, cudaHostAllocDefault));
-        C.h_out_bytes = need;
-    }
-    pslot_keypoint *hk = reinterpret_cast<pslot_keypoint *>(C.h_out + hdr);
-    uint8_t *hd = C.h_out + hdr + S * guess * sizeof(pslot_keypoint);
-    const int *hc = reinterpret_cast<const int *>(C.h_out);
-    CU(cudaMemcpyAsync(C.h_out, C.b.out_count, sizeof(int) * S, cudaMemcpyDeviceToHost, C.st));
-    CU(cudaMemcpy2DAsync(hk, sizeof(pslot_keypoint) * (size_t)guess, C.b.out_kps, sizeof(pslot_keypoint) * (size_t)C.g.slot_kp,
-                         sizeof(pslot_keypoint) * (size_t)guess, S, cudaMemcpyDeviceToHost, C.st));
-    CU(cudaMemcpy2DAsync(hd, 32 * (size_t)guess, C.b.out_desc, 32 * (size_t)C.g.slot_kp, 32 * (size_t)guess, S,
-                         cudaMemcpyDeviceToHost, C.st));
     const auto t2 = std::chrono::steady_clock::now();
     CU(cudaStreamSynchronize(C.st));
     const auto t3 = std::chrono::steady_clock::now();
