@@ -662,6 +662,42 @@ def single_pair_latency(cfg, local_rank, reps=30):
     return float(np.median(ts) * 1e3)
 
 
+def object_frame_latency(cfg, local_rank, reps=30):
+    """The device work of the reference's object-mode Frame constructor (SLOT mode 4, Frame.cc:660-757) for ONE stereo pair:
+    ExtractORB left / right on two host threads + ExtractObjORB (cv::ORB on both views inside the object masks, here one
+    batched call) on a third (:706-713), then ComputeStereoMatches and ComputeObjStereoMatches (:720-726) -> ms per frame,
+    host images in, host results out."""
+    from pointslot_b200 import binding as B
+    from pointslot_b200.synth import synth_pair
+    W, H = cfg["W"], cfg["H"]
+    L, R = synth_pair(W, H, 0)
+    mask = np.zeros((H, W), np.uint8)
+    mask[H // 4:3 * H // 4, W // 6:W // 2] = 255; mask[H // 8:H // 2, 2 * W // 3:W - 40] = 255
+    eL, eR = B.OrbExtractor(*cfg["params"], device=local_rank), B.OrbExtractor(*cfg["params"], device=local_rank)
+    orb = B.CvOrb(1000, 1.2, 8, 19, device=local_rank)
+    maxD = max_disparity(cfg)
+
+    def once():
+        box = {}
+        t1 = threading.Thread(target=lambda: box.__setitem__("r", eR.extract(R)))
+        t2 = threading.Thread(target=lambda: box.__setitem__("o", orb.detect_and_compute_batch([L, R], [mask, mask])))
+        t1.start(); t2.start()
+        kL, dL = eL.extract(L)
+        t1.join(); t2.join()
+        kR, dR = box["r"]
+        (okL, odL), (okR, odR) = box["o"]
+        B.stereo_match(eL, eR, kL, dL, kR, dR, cfg["bf"], maxD)
+        B.stereo_match(eL, eR, okL, odL, okR, odR, cfg["bf"], maxD)  # ComputeObjStereoMatches: same routine, object keypoints
+        return len(kL), len(okL)
+    for _ in range(5):
+        n = once()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); once(); ts.append(time.perf_counter() - t0)
+    orb.close()
+    return {"ms_per_frame": float(np.median(ts) * 1e3), "keypoints_left": n[0], "object_keypoints_left": n[1]}
+
+
 def measure_cvorb(Ls, Rs, W, H, local_rank, seconds=1.0):
     """SURVEY §8f row 4 (next row): OpenCV's own ORB for the dense object features, reference Frame.cc:2623-2665 - the pair
     (left + right view with object masks, one batched call: what Frame::ExtractObjORB does per frame) and a 64-image batch,
@@ -844,6 +880,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_extra:
         try:
             next_rows["cvorb"] = measure_cvorb(Ls, Rs, cfg["W"], cfg["H"], local_rank)
+            next_rows["object_mode_frame"] = object_frame_latency(cfg, local_rank)
         except Exception as e:  # a secondary row must not take the headline line down
             next_rows["cvorb"] = {"error": repr(e)}
 
