@@ -251,15 +251,60 @@ __device__ __forceinline__ int kth_bin_from_top(int cnt, int k, int *s_part /* >
 }
 
 // ---- retainBest(2 * quota) on the FAST score, then HarrisResponses -----------------------------------------------------------
+// HarrisResponses of one candidate (orb.cpp: 7x7 block of Sobel-3 gradients, k = 0.04): the 9x9 byte patch is fetched as
+// three aligned words per row (27 loads instead of 392 byte loads) and the Sobel kernels are applied separably, row by row:
+// d = p[x+1] - p[x-1], s = p[x-1] + 2 p[x] + p[x+1];  Ix = d[y-1] + 2 d[y] + d[y+1],  Iy = s[y+1] - s[y-1].  Integer sums,
+// so the order of the additions is free.
+__device__ __forceinline__ float harris_response(const uint8_t *__restrict__ img, int P, int x0, int y0, float scale_sq_sq)
+{
+    const int xs = x0 - 4, o8 = 8 * (xs & 3);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(img + (size_t)(y0 - 4) * P + (xs & ~3));
+    const int PW = P >> 2;
+    int d[3][7], sm[3][7];
+    int a = 0, b = 0, cc = 0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const uint32_t w0 = w[j * PW], w1 = w[j * PW + 1], w2 = w[j * PW + 2];
+        const uint32_t q0 = __funnelshift_r(w0, w1, o8), q1 = __funnelshift_r(w1, w2, o8), q2 = w2 >> o8;
+        int p[9];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { p[k] = (int)((q0 >> (8 * k)) & 0xFFu); p[4 + k] = (int)((q1 >> (8 * k)) & 0xFFu); }
+        p[8] = (int)(q2 & 0xFFu);
+#pragma unroll
+        for (int x = 0; x < 7; ++x) {
+            d[j % 3][x] = p[x + 2] - p[x];
+            sm[j % 3][x] = p[x] + 2 * p[x + 1] + p[x + 2];
+        }
+        if (j >= 2) { // block row j - 1: rows j - 2, j - 1, j are in the ring
+#pragma unroll
+            for (int x = 0; x < 7; ++x) {
+                const int Ix = d[(j - 2) % 3][x] + 2 * d[(j - 1) % 3][x] + d[j % 3][x];
+                const int Iy = sm[j % 3][x] - sm[(j - 2) % 3][x];
+                a += Ix * Ix; b += Iy * Iy; cc += Ix * Iy;
+            }
+        }
+    }
+    const float harris_k = 0.04f;
+    const float fa = (float)a, fb = (float)b, fc = (float)cc;
+    const float tr = __fadd_rn(fa, fb);
+    return __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(harris_k, tr), tr)), scale_sq_sq);
+}
+
+// Per (level, slot): the retainBest(2 * quota) threshold from the level's score histogram, then rounds of 1024 candidates:
+// the ones at or above the threshold (about one in seven) are compacted into a shared list so that the response runs on
+// dense warps, and a round reserves its piece of the kept list with one atomic.
 __global__ void __launch_bounds__(256)
 k_cv_harris(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ pyr, const uint32_t *__restrict__ cand,
             int *__restrict__ counters, const int *__restrict__ hist, uint32_t *__restrict__ kept, float *__restrict__ kept_resp)
 {
     __shared__ int s_part[10];
+    __shared__ uint32_t s_keep[1024];
+    __shared__ int s_nk, s_out;
     const int l = blockIdx.y, slot = blockIdx.z;
     const CvLevel &L = g.lv[l];
-    pyr += slot * g.slot_bytes;
-    cand += (size_t)slot * g.slot_cand; kept += (size_t)slot * g.slot_cand; kept_resp += (size_t)slot * g.slot_cand;
+    pyr += slot * g.slot_bytes + L.off;
+    cand += (size_t)slot * g.slot_cand + L.cand_base;
+    kept += (size_t)slot * g.slot_cand + L.cand_base; kept_resp += (size_t)slot * g.slot_cand + L.cand_base;
     counters += slot * CV_CNT_TOTAL;
     hist += slot * PSLOT_MAX_LEVELS * 256;
     const int n = min(counters[CV_CNT_CAND + l], L.cand_cap);
@@ -268,33 +313,29 @@ k_cv_harris(const __grid_constant__ CvGeom g, const uint8_t *__restrict__ pyr, c
     int above;
     const int bin = kth_bin_from_top(hist[l * 256 + threadIdx.x], keep, s_part, above);
     const int thr = keep == 0 ? 256 : n > keep ? bin : 0;
-    const float harris_k = 0.04f;
     const float scale1 = 1.f / ((1 << 2) * 7 * 255.f);
     const float scale_sq_sq = __fmul_rn(__fmul_rn(__fmul_rn(scale1, scale1), scale1), scale1);
-    const int P = L.pitch;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t c = cand[L.cand_base + i];
-        if (pslot_pr(c) < thr) continue;
-        const int x0 = pslot_px(c), y0 = pslot_py(c);
-        const uint8_t *ctr = pyr + L.off + (size_t)y0 * P + x0;
-        int a = 0, b = 0, cc = 0;
-        for (int dy = -3; dy <= 3; ++dy) {
-            const uint8_t *q = ctr + dy * P;
+    for (int base = blockIdx.x * 1024; base < n; base += gridDim.x * 1024) { // block-uniform
+        if (threadIdx.x == 0) s_nk = 0;
+        __syncthreads();
 #pragma unroll
-            for (int dx = -3; dx <= 3; ++dx) {
-                const uint8_t *r = q + dx;
-                const int Ix = ((int)r[1] - r[-1]) * 2 + ((int)r[-P + 1] - r[-P - 1]) + ((int)r[P + 1] - r[P - 1]);
-                const int Iy = ((int)r[P] - r[-P]) * 2 + ((int)r[P - 1] - r[-P - 1]) + ((int)r[P + 1] - r[-P + 1]);
-                a += Ix * Ix; b += Iy * Iy; cc += Ix * Iy;
+        for (int j = 0; j < 4; ++j) {
+            const int i = base + j * 256 + threadIdx.x;
+            if (i < n) {
+                const uint32_t c = cand[i];
+                if (pslot_pr(c) >= thr) s_keep[atomicAdd(&s_nk, 1)] = c;
             }
         }
-        const float fa = (float)a, fb = (float)b, fc = (float)cc;
-        const float tr = __fadd_rn(fa, fb);
-        const float resp = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(harris_k, tr), tr)),
-                                     scale_sq_sq);
-        const int j = atomicAdd(&counters[CV_CNT_KEPT + l], 1); // <= cand count <= cand_cap: the kept arrays share the capacity
-        kept[L.cand_base + j] = c;
-        kept_resp[L.cand_base + j] = resp;
+        __syncthreads();
+        const int nk = s_nk;
+        if (threadIdx.x == 0 && nk) s_out = atomicAdd(&counters[CV_CNT_KEPT + l], nk); // <= cand count: the kept arrays share the capacity
+        __syncthreads();
+        for (int q = threadIdx.x; q < nk; q += 256) {
+            const uint32_t c = s_keep[q];
+            kept[s_out + q] = c;
+            kept_resp[s_out + q] = harris_response(pyr, L.pitch, pslot_px(c), pslot_py(c), scale_sq_sq);
+        }
+        __syncthreads(); // s_nk / s_out / s_keep are reused by the next round
     }
 }
 

@@ -148,6 +148,20 @@ def test_cvorb_batch_equals_cv2_orb(B):
         _assert_equal(*out[i], *_cv2_sorted(noise[i], None), f"noise batch, image {i}")
 
 
+def test_cvorb_full_hd_pair(B):
+    """BASELINE.json's largest shape (1920x1080, 4000 features) as a left + right batch with object masks."""
+    from pointslot_b200.synth import synth_pair
+    H, W = 1080, 1920
+    L, R = synth_pair(W, H, 41)
+    mask = _object_mask(H, W)
+    orb = B.CvOrb(4000, 1.2, 8, 19)
+    out = orb.detect_and_compute_batch([L, R], [mask, mask])
+    for name, img, (k, d) in (("left", L, out[0]), ("right", R, out[1])):
+        ref, rdesc = _cv2_sorted(img, mask, 4000, 1.2, 8, 19)
+        _assert_equal(k, d, ref, rdesc, f"1080p {name}")
+        assert len(k) >= 3500
+
+
 def test_cvorb_argument_errors(B):
     with pytest.raises(B.PslotError):
         B.CvOrb(1000, 1.0, 8, 19)

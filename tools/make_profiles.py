@@ -13,9 +13,18 @@ KERNELS = {"fast": "k_fast_cells", "describe": "k_describe", "pyramid_level1": "
            "stereo_match": "k_stereo_match", "ingest": "k_gray_repitch"}
 
 for src, dst in (("bench.json", f"{pre}_bench.json"), ("bench_reference.json", f"{pre}_bench_reference.json"),
-                 ("launches_bench.csv", f"{pre}_launches_bench.csv")):
+                 ("launches_bench.csv", f"{pre}_launches_bench.csv"), ("launches_cvorb.csv", f"{pre}_launches_cvorb.csv"),
+                 ("cvorb_bench.json", f"{pre}_cvorb_bench.json")):
     if (G / src).exists() and "--no-bench" not in sys.argv:
         shutil.copy(G / src, P / dst)
+
+# the cv::ORB row's kernels: text summaries only (16 images per launch: a chunk of a 64-image batch)
+for k in ("k_cv_fast_score", "k_cv_nms_collect", "k_cv_harris", "k_cv_describe", "k_cv_resize_exact", "k_cv_select"):
+    rep = G / f"prof_{k}.ncu-rep"
+    if rep.exists():
+        txt = subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_summary.py"), str(rep), "--source", "20", "--ops"],
+                             capture_output=True, text=True).stdout
+        (P / f"{pre}_ncu_{k}.txt").write_text(txt)
 
 ncu_kernels = {"note": "ncu --set full --clock-control none, one launch of each kernel over a 125-pair sub-batch of the bench "
                "workload (tools/prof.sh); pct = % of peak sustained; shared_GBps = shared-memory wavefronts x 128 B / duration "
