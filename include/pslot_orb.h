@@ -352,6 +352,33 @@ int pslot_bow_transform(pslot_vocab *voc, pslot_orb *ctx, const uint8_t *desc32,
 int pslot_bow_vectors(const pslot_vocab *voc, const int32_t *leaf_node, const int32_t *nid, int n, int32_t *bow_id,
                       double *bow_val, int *n_words, int32_t *fv_node, int32_t *fv_start, int32_t *fv_feat, int *n_fv_nodes);
 
+/* ---------------------------------------------------------------------------------------------
+ * Feature partition by the instance mask (the step after the stereo matchers in the object-mode Frame constructors).
+ * Replaces the classification + push_back loops of `void Frame::AssignFeatures(vector<DetectionObject*>&)`
+ * (reference src/Frame.cc:759-977; called :478, :648, :733): feature i is looked up at mMaskImg((int)pt.y, (int)pt.x);
+ * label 0 -> background, 255 -> dropped, L in 1..254 -> the first non-null detection j whose id equals L - 1, with
+ * id = mnObjectID > 255 ? mnObjectID - 255 : mnObjectID (:836-846), else dropped.  The same routine serves the frame's
+ * own ORB features (-> mvKeys / mvOriKeys[j] ...) and the dense cv::ORB object features (-> mvObjKeys[j] ...; pass
+ * `depth` = mvTempObjDepth and `depth_limit` = 2 * mThDepth to get vnEffectiveObjPointDepthNums, :893-896).
+ *   object_ids[j] = vDetectionObjects[j]->mnObjectID, or any negative value for a NULL detection;
+ *   cls[i]        = -1 dropped | 0 background | 1 + j;
+ *   order[]       = feature indices grouped by class (background, detection 0, 1, ...), original order inside a class -
+ *                   exactly the reference's push_back order; class c owns order[class_start[c] .. class_start[c + 1]);
+ *                   class_start has n_objects + 2 entries, the last = number of kept features;
+ *   effective[j]  = features of detection j with 0 < depth < depth_limit (NULL, or `depth` NULL: not computed).
+ * `mask` may be NULL to reuse the mask the previous call uploaded (the two calls of one frame share mMaskImg).
+ * The per-object grids (AssignDetObjFeasToGrid, :1863-1888) are pslot_assign_grid on each object's slice.
+ * pslot_batch_assign_features: the same for the LEFT keypoints of every pair of the last submit, which are still on the
+ * device (masks: one per pair; object_ids: n_objects per pair); cls / order hold K entries per pair (K = the batch's
+ * keypoint capacity), class_start n_objects + 2 per pair; results are valid after pslot_batch_wait.
+ * --------------------------------------------------------------------------------------------- */
+int pslot_assign_features(pslot_orb *ctx, const pslot_keypoint *kps, int n, const uint8_t *mask, int w, int h,
+                          ptrdiff_t mask_pitch, const int32_t *object_ids, int n_objects, const float *depth,
+                          float depth_limit, int32_t *cls, int32_t *order, int32_t *class_start, int32_t *effective);
+int pslot_batch_assign_features(pslot_batch *b, const uint8_t *masks, ptrdiff_t mask_pitch, ptrdiff_t mask_image_stride,
+                                const int32_t *object_ids, int n_objects, int32_t *cls, int32_t *order,
+                                int32_t *class_start);
+
 /* Host-clock phases of the last (batched) call in ms: [0] uploads enqueued, [1] kernels + downloads enqueued, [2] waiting
  * for the device, [3] results copied to the caller's arrays. */
 int pslot_cvorb_last_timing(const pslot_cvorb *ctx, double out_ms[4]);

@@ -80,6 +80,7 @@ def lib():
         L.orc_steer_coeffs.restype = None
         L.orc_glibc_sincosf_n.argtypes = [vp, C.c_int, vp, vp]
         L.orc_glibc_sincosf_n.restype = None
+        L.orc_assign_features.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, C.c_float, vp, vp, vp, vp]
         L.orc_assign_grid.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp]
         L.orc_features_in_area.argtypes = [vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
                                            C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, vp]
@@ -202,6 +203,23 @@ def assign_grid(kps, min_x, min_y, inv_w, inv_h, cols=64, rows=48):
     if n < 0:
         raise ValueError("bad grid arguments")
     return cs, idx[:n].copy()
+
+
+def assign_features(kps, mask, object_ids, depth=None, depth_limit=0.0):
+    """Frame::AssignFeatures (Frame.cc:759-977) -> (cls [n], groups, effective): groups[0] = indices of the background
+    features, groups[1 + j] = those of detection j, each in push_back order."""
+    kps = np.ascontiguousarray(kps, KEYPOINT_DTYPE)
+    mask = np.ascontiguousarray(mask, np.uint8)
+    ids = np.ascontiguousarray(object_ids, np.int32)
+    n, J = len(kps), len(ids)
+    d = None if depth is None else np.ascontiguousarray(depth, np.float32)
+    cls = np.zeros(max(n, 1), np.int32); order = np.zeros(max(n, 1), np.int32)
+    cs = np.zeros(J + 2, np.int32); eff = np.zeros(max(J, 1), np.int32)
+    r = lib().orc_assign_features(_ptr(kps), n, _ptr(mask), mask.shape[1], mask.shape[0], mask.strides[0], _ptr(ids), J,
+                                  None if d is None else _ptr(d), depth_limit, _ptr(cls), _ptr(order), _ptr(cs), _ptr(eff))
+    if r < 0:
+        raise ValueError("bad arguments")
+    return cls[:n], [order[cs[c]:cs[c + 1]].copy() for c in range(J + 1)], (eff[:J] if d is not None else None)
 
 
 def features_in_area(kps, cell_start, indices, min_x, min_y, inv_w, inv_h, cols, rows, x, y, r, min_level=-1,

@@ -1006,6 +1006,44 @@ int orc_assign_grid(const orc_keypoint *kps, int n, float min_x, float min_y, fl
     return cell_start[C];
 }
 
+/* Frame::AssignFeatures (Frame.cc:811-905): the two classification loops (ORB features :813-868, dense object features
+ * :870-903) differ only in what they do with the background class, so one routine returns the class of every feature
+ * and the push_back order per class. */
+int orc_assign_features(const orc_keypoint *kps, int n, const uint8_t *mask, int w, int h, int pitch, const int *object_ids,
+                        int n_objects, const float *depth, float depth_limit, int *cls, int *order, int *class_start,
+                        int *effective)
+{
+    if (n < 0 || n_objects < 0 || w <= 0 || h <= 0 || pitch < w) return -1;
+    memset(class_start, 0, sizeof(int) * (size_t)(n_objects + 2));
+    if (effective) memset(effective, 0, sizeof(int) * (size_t)n_objects);
+    for (int i = 0; i < n; ++i) {
+        const int x = (int)kps[i].x, y = (int)kps[i].y; /* int x = mvKeys[i].pt.x (:816-817) */
+        int c = -1;
+        if (x >= 0 && y >= 0 && x < w && y < h) {
+            const int label = mask[(size_t)y * pitch + x];
+            if (label == 0)
+                c = 0; /* :820-829 */
+            else if (label != 255) { /* :835 */
+                for (int j = 0; j < n_objects; ++j) { /* :837-866: first match wins (break) */
+                    if (object_ids[j] < 0) continue;  /* if (!vDetectionObjects[j]) continue; negative ids match no label either */
+                    const int id = object_ids[j] > 255 ? object_ids[j] - 255 : object_ids[j];
+                    if (id == label - 1) { c = 1 + j; break; }
+                }
+            }
+        }
+        cls[i] = c;
+        if (c >= 0) class_start[c + 1]++;
+        if (c >= 1 && depth && effective && depth[i] > 0 && depth[i] < depth_limit) effective[c - 1]++; /* :893-896 */
+    }
+    for (int c = 0; c <= n_objects; ++c) class_start[c + 1] += class_start[c];
+    int *fill = (int *)malloc(sizeof(int) * (size_t)(n_objects + 1));
+    memcpy(fill, class_start, sizeof(int) * (size_t)(n_objects + 1));
+    for (int i = 0; i < n; ++i)
+        if (cls[i] >= 0) order[fill[cls[i]]++] = i;
+    free(fill);
+    return class_start[n_objects + 1];
+}
+
 int orc_features_in_area(const orc_keypoint *kps, const int *cell_start, const int *indices, float min_x, float min_y,
                          float inv_w, float inv_h, int cols, int rows, float x, float y, float r, int min_level,
                          int max_level, int cap, int *out)

@@ -103,6 +103,14 @@ int orc_distribute_octtree(const int *x, const int *y, const int *resp, int n,
  * returns the number of keypoints that fell inside the grid (-1: bad arguments) */
 int orc_assign_grid(const orc_keypoint *kps, int n, float min_x, float min_y, float inv_w, float inv_h, int cols,
                     int rows, int *cell_start, int *indices);
+/* Frame::AssignFeatures (Frame.cc:759-977), its classification + push_back loops: feature i -> mask((int)pt.y, (int)pt.x);
+ * 0 -> background, 255 -> dropped, L -> the first detection j (object_ids[j] >= 0) with
+ * (object_ids[j] > 255 ? object_ids[j] - 255 : object_ids[j]) == L - 1 (:836-846), else dropped.  cls[i] = -1 | 0 | 1 + j;
+ * order = indices grouped by class in push_back order; class_start[n_objects + 2]; effective[j] (depth != NULL) = features
+ * of detection j with 0 < depth < depth_limit (:893-896).  Returns the number of kept features (-1: bad arguments). */
+int orc_assign_features(const orc_keypoint *kps, int n, const uint8_t *mask, int w, int h, int pitch, const int *object_ids,
+                        int n_objects, const float *depth, float depth_limit, int *cls, int *order, int *class_start,
+                        int *effective);
 /* Frame::GetFeaturesInArea (Frame.cc:1808-1861) on that CSR grid; returns the number found (may exceed cap) */
 int orc_features_in_area(const orc_keypoint *kps, const int *cell_start, const int *indices, float min_x, float min_y,
                          float inv_w, float inv_h, int cols, int rows, float x, float y, float r, int min_level,

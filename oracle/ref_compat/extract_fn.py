@@ -25,6 +25,8 @@ PIECES = [
         "bool Frame::PosInGrid(const cv::KeyPoint &kp, int &posX, int &posY)",
         "vector<size_t> Frame::GetObjectFeaturesInArea(const int& nDetObjOrder, const size_t& nDetObjFeaNum, const float &x, const float  &y, const float  &r, const int minLevel, const int maxLevel) const",
         "bool Frame::isInBBox(const size_t &nOrder, const float &u, const float &v)",
+        "void Frame::AssignFeatures(vector<DetectionObject*> &vDetectionObjects)",
+        "void Frame::AssignDetObjFeasToGrid(const size_t &objOrder, const size_t &objFeaNum)",
     ]),
     ("keyframe_fns.inc", "src/KeyFrame.cc", [
         "vector<size_t> KeyFrame::GetFeaturesInArea(const float &x, const float &y, const float &r) const",

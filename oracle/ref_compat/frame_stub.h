@@ -7,7 +7,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <iostream>
 #include <set>
+#include <sys/types.h> // u_int8_t (Frame::AssignFeatures reads the mask as at<u_int8_t>)
 #include <vector>
 
 #include "ORBextractor.h" // the reference's own header (-I <reference>/include): mvImagePyramid etc.
@@ -46,7 +48,15 @@ public:
 };
 
 typedef MapPoint MapObjectPoint; // include/MapObjectPoint.h: the members the object overload reads are MapPoint's
-struct DetectionObject { cv::Rect mrectBBox; DetectionObject() : mrectBBox(0, 0, 0, 0) {} }; // include/DetectionObject.h:40
+struct DetectionObject { // include/DetectionObject.h:33, 40, 84: what the lifted functions read
+    cv::Rect mrectBBox;
+    int mnObjectID;
+    size_t init_order_n_; // argument of the last InitInFrameMapObjectPointsOrder call
+    DetectionObject() : mrectBBox(0, 0, 0, 0), mnObjectID(0), init_order_n_(0) {}
+    void InitInFrameMapObjectPointsOrder(const size_t &nNum) { init_order_n_ = nNum; }
+};
+class MapObject;
+extern int EnSLOTMode; // include/Parameters.h:75
 
 class Frame {
 public:
@@ -59,6 +69,19 @@ public:
     vector<vector<vector<std::vector<std::size_t>>>> mvObjKeysGrid;
     vector<size_t> GetObjectFeaturesInArea(const int &nDetObjOrder, const size_t &nDetObjFeaNum, const float &x, const float &y, const float &r, const int minLevel = -1, const int maxLevel = -1) const;
     bool isInBBox(const size_t &nOrder, const float &u, const float &v);
+    // Frame::AssignFeatures and what it fills (include/Frame.h:153-190, 201, 209, 252)
+    void AssignFeatures(vector<DetectionObject *> &vDetectionObjects);
+    void AssignDetObjFeasToGrid(const size_t &objOrder, const size_t &objFeaNum);
+    cv::Mat mMaskImg;
+    float mThDepth;
+    size_t mnDetObj;
+    std::vector<std::vector<cv::KeyPoint>> mvObjKeys, mvOriKeys, mvOriKeysUn;
+    std::vector<std::vector<float>> mvObjPointDepth, mvuOriRight, mvOriDepth;
+    vector<cv::Mat> mOriDescriptors;
+    std::vector<MapObject *> mvMapObjects;
+    std::vector<std::vector<bool>> mvbObjKeysOutlier, mvbObjKeysMatchedFlag;
+    vector<size_t> mvnNewConstructedObjOrders, mvTotalTrackedObjOrders;
+    vector<pair<size_t, size_t>> mvInLastFrameTrackedObjOrders;
     void ComputeStereoMatches();
     void ComputeObjStereoMatches();
     void AssignFeaturesToGrid();
@@ -82,7 +105,7 @@ public:
     cv::Mat mTcw;
     vector<float> mvScaleFactors, mvInvScaleFactors;
     static float mnMinX, mnMaxX, mnMinY, mnMaxY;
-    Frame() : mpORBextractorLeft(nullptr), mpORBextractorRight(nullptr), mbf(0), mb(0), N(0) {}
+    Frame() : mThDepth(0), mnDetObj(0), mpORBextractorLeft(nullptr), mpORBextractorRight(nullptr), mbf(0), mb(0), N(0) {}
 };
 
 class KeyFrame { // what the two KeyFrame overloads of ORBmatcher::SearchByProjection read (include/KeyFrame.h)

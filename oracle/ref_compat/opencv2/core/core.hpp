@@ -131,6 +131,17 @@ public:
         return m;
     }
     void copyTo(Mat &dst) const { dst = clone(); }
+    // cv::Mat::push_back(const Mat&): appends the rows of m (Frame::AssignFeatures grows descriptor matrices row by row)
+    void push_back(const Mat &m)
+    {
+        if (m.empty()) return;
+        Mat out;
+        out.create(rows + m.rows, empty() ? m.cols : cols, empty() ? m.type_ : type_);
+        for (int r = 0; r < rows; ++r) std::memcpy(out.data + (size_t)r * out.step, data + (size_t)r * step, (size_t)cols * elemSize());
+        for (int r = 0; r < m.rows; ++r)
+            std::memcpy(out.data + (size_t)(rows + r) * out.step, m.data + (size_t)r * m.step, (size_t)m.cols * m.elemSize());
+        *this = out;
+    }
     // cv::Mat::convertTo without scaling; a type change always lands in a fresh buffer (in-place calls on a view,
     // as in Frame.cc:2240, therefore never touch the viewed image)
     void convertTo(Mat &dst, int rtype) const

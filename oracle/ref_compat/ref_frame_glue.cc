@@ -11,6 +11,7 @@
 using namespace std;
 
 namespace ORB_SLAM2 {
+int EnSLOTMode = 4; // src/Parameters.cc; Frame::AssignFeatures returns early in mode 1 only
 float Frame::fx, Frame::fy, Frame::cx, Frame::cy;
 float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv;
 float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
@@ -326,6 +327,89 @@ int reff_search_by_projection_obj(void *h, const reff_map_point *mps, const uint
     }
     F.mvDetectionObjects.clear();
     return n;
+}
+
+// Frame::AssignFeatures (Frame.cc:759-977) on a stub frame.  Every feature carries its index in KeyPoint::class_id (the
+// function copies whole KeyPoints), so the partitions come back as index lists; that the descriptor rows, mvuRight,
+// mvDepth and mvKeysUn travelled with their keypoints is checked here (return -2 otherwise).  Outputs:
+//   bg_idx / *bg_n                         indices of the frame's ORB features left in mvKeys (the background)
+//   det_of / *n_det                        original index j of every detection kept in mvDetectionObjects
+//   ori_idx, ori_start[n_det + 1]          mvOriKeys[k]: the ORB features inside detection k's mask
+//   obj_idx, obj_start[n_det + 1]          mvObjKeys[k]: the dense object features of detection k
+//   init_n[k]                              argument of InitInFrameMapObjectPointsOrder for detection k
+//   grid_cs[k][64 * 48 + 1], grid_idx      mvObjKeysGrid[k] flattened (AssignDetObjFeasToGrid), indices LOCAL to mvObjKeys[k]
+int reff_assign_features(const void *kps, int n, const uint8_t *desc, const float *uright, const float *depth,
+                         const void *okps, int on, const uint8_t *odesc, const float *ouright, const float *odepth,
+                         const uint8_t *mask, int w, int h, const int *object_ids, int n_objects, float th_depth,
+                         float min_x, float max_x, float min_y, float max_y, float inv_w, float inv_h,
+                         int *bg_idx, int *bg_n, int *det_of, int *n_det, int *ori_idx, int *ori_start, int *obj_idx,
+                         int *obj_start, int *init_n, int *grid_cs, int *grid_idx)
+{
+    Frame F;
+    set_keys(F.mvKeys, kps, n);
+    for (int i = 0; i < n; ++i) F.mvKeys[i].class_id = i;
+    F.mvKeysUn = F.mvKeys;
+    F.N = n;
+    F.mDescriptors = desc_mat(desc, n);
+    F.mvuRight.assign(uright, uright + n);
+    F.mvDepth.assign(depth, depth + n);
+    set_keys(F.mvTempObjKeys, okps, on);
+    for (int i = 0; i < on; ++i) F.mvTempObjKeys[i].class_id = i;
+    F.mvTempObjKeysUn = F.mvTempObjKeys;
+    F.mTempObjPointsDescriptors = desc_mat(odesc, on);
+    F.mvuTempObjKeysRight.assign(ouright, ouright + on);
+    F.mvTempObjDepth.assign(odepth, odepth + on);
+    F.mMaskImg = cv::Mat(h, w, CV_8UC1, const_cast<uint8_t *>(mask));
+    F.mThDepth = th_depth;
+    Frame::mnMinX = min_x; Frame::mnMaxX = max_x; Frame::mnMinY = min_y; Frame::mnMaxY = max_y;
+    Frame::mfGridElementWidthInv = inv_w; Frame::mfGridElementHeightInv = inv_h;
+    vector<ORB_SLAM2::DetectionObject> pool((size_t)n_objects);
+    vector<ORB_SLAM2::DetectionObject *> dets((size_t)n_objects, nullptr);
+    for (int j = 0; j < n_objects; ++j)
+        if (object_ids[j] >= 0) { pool[j].mnObjectID = object_ids[j]; dets[j] = &pool[j]; }
+    F.AssignFeatures(dets);
+
+    auto same_row = [](const cv::Mat &m, int r, const uint8_t *d, int id) { return memcmp(m.ptr(r), d + (size_t)id * 32, 32) == 0; };
+    *bg_n = (int)F.mvKeys.size();
+    if (F.mDescriptors.rows != *bg_n && *bg_n) return -2;
+    for (int r = 0; r < *bg_n; ++r) {
+        const int id = F.mvKeys[r].class_id;
+        bg_idx[r] = id;
+        if (!same_row(F.mDescriptors, r, desc, id) || F.mvuRight[r] != uright[id] || F.mvDepth[r] != depth[id] || F.mvKeysUn[r].class_id != id) return -2;
+    }
+    *n_det = (int)F.mvDetectionObjects.size();
+    if ((size_t)*n_det != F.mnDetObj || F.mvObjKeysGrid.size() != F.mnDetObj) return -2;
+    int ko = 0, kd = 0, kg = 0;
+    for (int k = 0; k < *n_det; ++k) {
+        det_of[k] = (int)(F.mvDetectionObjects[k] - pool.data());
+        init_n[k] = (int)F.mvDetectionObjects[k]->init_order_n_;
+        ori_start[k] = ko;
+        for (size_t r = 0; r < F.mvOriKeys[k].size(); ++r) {
+            const int id = F.mvOriKeys[k][r].class_id;
+            ori_idx[ko++] = id;
+            if (!same_row(F.mOriDescriptors[k], (int)r, desc, id) || F.mvuOriRight[k][r] != uright[id] || F.mvOriDepth[k][r] != depth[id] ||
+                F.mvOriKeysUn[k][r].class_id != id) return -2;
+        }
+        obj_start[k] = kd;
+        for (size_t r = 0; r < F.mvObjKeys[k].size(); ++r) {
+            const int id = F.mvObjKeys[k][r].class_id;
+            obj_idx[kd++] = id;
+            if (!same_row(F.mvObjPointsDescriptors[k], (int)r, odesc, id) || F.mvuObjKeysRight[k][r] != ouright[id] ||
+                F.mvObjPointDepth[k][r] != odepth[id] || F.mvObjKeysUn[k][r].class_id != id) return -2;
+        }
+        if (F.mvpMapObjectPoints[k].size() != F.mvObjKeys[k].size() || F.mvbObjKeysOutlier[k].size() != F.mvObjKeys[k].size()) return -2;
+        int *cs = grid_cs + (size_t)k * (FRAME_GRID_COLS * FRAME_GRID_ROWS + 1);
+        const int g0 = kg;
+        for (int i = 0; i < FRAME_GRID_COLS; ++i)
+            for (int j = 0; j < FRAME_GRID_ROWS; ++j) {
+                cs[i * FRAME_GRID_ROWS + j] = kg - g0;
+                for (size_t v : F.mvObjKeysGrid[k][i][j]) grid_idx[kg++] = (int)v;
+            }
+        cs[FRAME_GRID_COLS * FRAME_GRID_ROWS] = kg - g0;
+    }
+    ori_start[*n_det] = ko;
+    obj_start[*n_det] = kd;
+    return 0;
 }
 
 } // extern "C"

@@ -89,6 +89,8 @@ def _load(variant: str = "stock"):
     lib.reff_stereo.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, f32, f32, vp, vp]
     lib.reff_obj_stereo.argtypes = lib.reff_stereo.argtypes
     lib.reff_hamming256.argtypes = [vp, vp]
+    lib.reff_assign_features.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, vp, i32, f32, f32, f32, f32, f32,
+                                         f32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.reff_frame_create.restype = vp
     lib.reff_frame_create.argtypes = [vp, i32, vp, vp, vp, i32, f32, f32, f32, f32, f32, f32]
     lib.reff_frame_destroy.argtypes = [vp]
@@ -181,6 +183,42 @@ def obj_stereo_match(eL: ReferenceExtractor, eR: ReferenceExtractor, kL, dL, kR,
 def hamming256(a, b, variant="stock") -> int:
     a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
     return int(_load(variant).reff_hamming256(_p(a), _p(b)))
+
+
+def assign_features(kps, desc, u_right, depth, okps, odesc, ou_right, odepth, mask, object_ids, th_depth, min_x, max_x,
+                    min_y, max_y, inv_w, inv_h, variant="stock"):
+    """The reference's own Frame::AssignFeatures (src/Frame.cc:759-977, with AssignDetObjFeasToGrid :1863-1888) on a stub frame
+    holding the given ORB features (kps ...) and dense object features (okps ...) -> dict of index lists:
+    background, det_of (original index of each kept detection), ori[k], obj[k], init_n[k], grid[k] = (cell_start, indices)."""
+    lib = _load(variant)
+    kps = np.ascontiguousarray(kps, KEYPOINT_DTYPE); okps = np.ascontiguousarray(okps, KEYPOINT_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8); odesc = np.ascontiguousarray(odesc, np.uint8)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    u_right, depth, ou_right, odepth = f(u_right), f(depth), f(ou_right), f(odepth)
+    mask = np.ascontiguousarray(mask, np.uint8)
+    ids = np.ascontiguousarray(object_ids, np.int32)
+    n, on, J = len(kps), len(okps), len(ids)
+    i32 = lambda m: np.zeros(max(m, 1), np.int32)
+    bg, det_of, ori, ori_s, obj, obj_s, init_n = i32(n), i32(J), i32(n), i32(J + 1), i32(on), i32(J + 1), i32(J)
+    gcs, gidx = i32(J * (64 * 48 + 1)), i32(on)
+    bg_n, n_det = C.c_int(0), C.c_int(0)
+    rc = lib.reff_assign_features(_p(kps), n, _p(desc), _p(u_right), _p(depth), _p(okps), on, _p(odesc), _p(ou_right), _p(odepth),
+                                  _p(mask), mask.shape[1], mask.shape[0], _p(ids), J, th_depth, min_x, max_x, min_y, max_y,
+                                  inv_w, inv_h, _p(bg), C.byref(bg_n), _p(det_of), C.byref(n_det), _p(ori), _p(ori_s), _p(obj),
+                                  _p(obj_s), _p(init_n), _p(gcs), _p(gidx))
+    if rc:
+        raise RuntimeError(f"reference AssignFeatures moved an attribute away from its keypoint (rc {rc})")
+    nd = n_det.value
+    out = {"background": bg[:bg_n.value].copy(), "det_of": det_of[:nd].copy(), "init_n": init_n[:nd].copy(), "ori": [], "obj": [],
+           "grid": []}
+    g0 = 0
+    for k in range(nd):
+        out["ori"].append(ori[ori_s[k]:ori_s[k + 1]].copy())
+        out["obj"].append(obj[obj_s[k]:obj_s[k + 1]].copy())
+        cs = gcs[k * (64 * 48 + 1):(k + 1) * (64 * 48 + 1)].copy()
+        out["grid"].append((cs, gidx[g0:g0 + cs[-1]].copy()))
+        g0 += cs[-1]
+    return out
 
 
 class ReferenceFrame:

@@ -32,6 +32,7 @@ ABI_SYMBOLS = [
     "pslot_assign_grid", "pslot_grid_token", "pslot_features_in_area", "pslot_batch_assign_grid",
     "pslot_search_by_projection", "pslot_search_by_projection_obj", "pslot_search_by_projection_last", "pslot_search_by_projection_kf", "pslot_debug_projection_sweeps",
     "pslot_cvorb_create", "pslot_cvorb_destroy", "pslot_cvorb_detect_and_compute", "pslot_cvorb_detect_and_compute_batch", "pslot_cvorb_last_timing", "pslot_cvorb_debug",
+    "pslot_assign_features", "pslot_batch_assign_features",
     "pslot_vocab_create", "pslot_vocab_destroy", "pslot_bow_transform", "pslot_bow_vectors",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
 ]
@@ -131,6 +132,8 @@ def lib():
     L.pslot_cvorb_detect_and_compute_batch.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_ssize_t, vp, vp,
                                                        C.c_int, vp]
     L.pslot_cvorb_last_timing.argtypes = [vp, vp]
+    L.pslot_assign_features.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_int, vp, C.c_float, vp, vp, vp, vp]
+    L.pslot_batch_assign_features.argtypes = [vp, vp, C.c_ssize_t, C.c_ssize_t, vp, C.c_int, vp, vp, vp]
     L.pslot_cvorb_debug.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.pslot_vocab_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int]
     L.pslot_vocab_destroy.argtypes = [vp]
@@ -263,6 +266,31 @@ def assign_grid(ext: OrbExtractor, kps_un, spec: GridSpec):
     tot = C.c_int(0)
     _check(lib().pslot_assign_grid(ext._h, _p(kps_un), n, C.byref(spec), _p(cs), _p(idx), C.byref(tot)))
     return cs, idx[:tot.value].copy()
+
+
+def assign_features(ext: OrbExtractor, kps, mask, object_ids, depth=None, depth_limit=0.0):
+    """Frame::AssignFeatures (reference src/Frame.cc:759-977): classify the features by the instance mask and partition them
+    in the reference's push_back order -> (cls [n], groups, effective) with groups[0] = indices of the background features,
+    groups[1 + j] = indices of detection j's features; effective[j] (when `depth` is given) = features of detection j with
+    0 < depth < depth_limit.  `mask` = None reuses the mask of the previous call on `ext`."""
+    kps = np.ascontiguousarray(kps, KEYPOINT_DTYPE)
+    ids = np.ascontiguousarray(object_ids, np.int32)
+    n, J = len(kps), len(ids)
+    m = mask
+    if m is not None and not (m.dtype == np.uint8 and m.ndim == 2 and m.strides[1] == 1):
+        m = np.ascontiguousarray(m, np.uint8)
+    H, W = (getattr(ext, "_mask_shape", (1, 1)) if m is None else m.shape)
+    pitch = W if m is None else m.strides[0]
+    d = None if depth is None else np.ascontiguousarray(depth, np.float32)
+    cls = np.zeros(max(n, 1), np.int32); order = np.zeros(max(n, 1), np.int32)
+    cs = np.zeros(J + 2, np.int32); eff = np.zeros(max(J, 1), np.int32)
+    _check(lib().pslot_assign_features(ext._h, _p(kps), n, None if m is None else _p(m), W, H, pitch, _p(ids), J,
+                                       None if d is None else _p(d), C.c_float(depth_limit), _p(cls), _p(order), _p(cs),
+                                       _p(eff) if d is not None else None))
+    if m is not None:
+        ext._mask_shape = (H, W)
+    groups = [order[cs[c]:cs[c + 1]].copy() for c in range(J + 1)]
+    return cls[:n], groups, (eff[:J] if d is not None else None)
 
 
 class CvOrb:
@@ -607,6 +635,20 @@ class StereoBatch:
         cs = np.zeros((npairs, spec.cols * spec.rows + 1), np.int32); idx = np.zeros((npairs, self.K), np.int32)
         _check(lib().pslot_batch_assign_grid(self._h, C.byref(spec), _p(cs), _p(idx)))
         return cs, idx
+
+    def assign_features(self, masks, object_ids):
+        """Frame::AssignFeatures for the left keypoints of every pair of the last submit (they are still on the device):
+        masks [npairs, H, W] u8, object_ids [npairs, J] -> (cls [npairs, K], order [npairs, K], class_start [npairs, J + 2]);
+        asynchronous: valid after wait()."""
+        masks = np.ascontiguousarray(masks, np.uint8)
+        ids = np.ascontiguousarray(object_ids, np.int32)
+        npairs, J = ids.shape
+        assert masks.shape == (npairs, self.H, self.W)
+        cls = np.zeros((npairs, self.K), np.int32); order = np.zeros((npairs, self.K), np.int32)
+        cs = np.zeros((npairs, J + 2), np.int32)
+        _check(lib().pslot_batch_assign_features(self._h, _p(masks), self.W, self.W * self.H, _p(ids), J, _p(cls), _p(order), _p(cs)))
+        self._keep = (masks, ids)  # the copies run asynchronously
+        return cls, order, cs
 
     def wait(self):
         _check(lib().pslot_batch_wait(self._h))

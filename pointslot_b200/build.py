@@ -8,7 +8,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libpslot_orb.so"
-SOURCES = ["ingest.cu", "pyramid.cu", "fast.cu", "quadtree.cu", "describe.cu", "stereo.cu", "grid.cu", "cvorb.cu", "bow.cu", "engine.cu"]
+SOURCES = ["ingest.cu", "pyramid.cu", "fast.cu", "quadtree.cu", "describe.cu", "stereo.cu", "grid.cu", "partition.cu", "cvorb.cu", "bow.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",  # parity rule 3: no fused multiply-add anywhere on the float islands

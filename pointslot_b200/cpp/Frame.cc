@@ -434,6 +434,102 @@ void Frame::ExtractObjORB(cv::Mat left, cv::Mat right, cv::Mat LeftObjMask, cv::
     mTempObjPointsDescriptorsRight = descriptors_2.clone();
 }
 
+void Frame::AssignDetObjFeasToGrid(const size_t &objOrder, const size_t &objFeaNum) // (:1863-1888)
+{
+    auto &grid = mvObjKeysGrid[objOrder];
+    grid.assign(FRAME_GRID_COLS, std::vector<std::vector<std::size_t>>(FRAME_GRID_ROWS));
+    for (size_t i = 0; i < objFeaNum; i++) {
+        const cv::KeyPoint &kp = mvObjKeysUn[objOrder][i];
+        int nGridPosX, nGridPosY;
+        if (PosInGrid(kp, nGridPosX, nGridPosY)) grid[nGridPosX][nGridPosY].push_back(i);
+    }
+}
+
+void Frame::AssignFeatures(std::vector<DetectionObject *> &vDetectionObjects) // (:759-977)
+{
+    const int nObj = (int)vDetectionObjects.size();
+    if (nObj > 256 || mMaskImg.empty()) {
+        std::fprintf(stderr, "pslot Frame::AssignFeatures: %s\n", mMaskImg.empty() ? "mMaskImg is empty" : "more than 256 detections");
+        std::abort();
+    }
+    std::vector<int32_t> ids((size_t)std::max(nObj, 1), -1);
+    for (int j = 0; j < nObj; ++j)
+        if (vDetectionObjects[j]) ids[j] = vDetectionObjects[j]->mnObjectID; // a null detection matches no label (:839)
+    pslot_orb *ctx = mpORBextractorLeft->Handle();
+    auto partition = [&](const std::vector<cv::KeyPoint> &keys, bool first, const std::vector<float> *depth, std::vector<int32_t> &order,
+                         std::vector<int32_t> &start, std::vector<int32_t> &effective) {
+        const int n = (int)keys.size();
+        std::vector<int32_t> cls((size_t)std::max(n, 1));
+        order.assign((size_t)std::max(n, 1), 0);
+        start.assign((size_t)nObj + 2, 0);
+        effective.assign((size_t)std::max(nObj, 1), 0);
+        const int rc = pslot_assign_features(ctx, reinterpret_cast<const pslot_keypoint *>(keys.data()), n,
+                                             first ? mMaskImg.data : nullptr, mMaskImg.cols, mMaskImg.rows, (ptrdiff_t)mMaskImg.step,
+                                             ids.data(), nObj, depth ? depth->data() : nullptr, 2 * mThDepth, cls.data(), order.data(),
+                                             start.data(), depth ? effective.data() : nullptr);
+        if (rc != PSLOT_OK) {
+            std::fprintf(stderr, "pslot Frame::AssignFeatures: %s\n", pslot_last_error());
+            std::abort();
+        }
+    };
+    std::vector<int32_t> order, start, eff, oorder, ostart, oeff;
+    partition(mvKeys, true, nullptr, order, start, eff);                // the frame's ORB features (:813-868)
+    partition(mvTempObjKeys, false, &mvTempObjDepth, oorder, ostart, oeff); // the dense object features (:870-903), same mask
+
+    auto gather_keys = [](const std::vector<cv::KeyPoint> &src, const int32_t *idx, int n) {
+        std::vector<cv::KeyPoint> out((size_t)n);
+        for (int r = 0; r < n; ++r) out[r] = src[idx[r]];
+        return out;
+    };
+    auto gather_f = [](const std::vector<float> &src, const int32_t *idx, int n) {
+        std::vector<float> out((size_t)n);
+        for (int r = 0; r < n; ++r) out[r] = src[idx[r]];
+        return out;
+    };
+    auto gather_rows = [](const cv::Mat &src, const int32_t *idx, int n) {
+        cv::Mat out;
+        if (n == 0) return out; // push_back never ran: an empty matrix, as in the reference
+        out.create(n, 32, CV_8U);
+        for (int r = 0; r < n; ++r) std::memcpy(out.ptr(r), src.ptr(idx[r]), 32);
+        return out;
+    };
+    mvnEffectiveObjPointDepthNums.clear();
+    for (int j = 0; j < nObj; ++j) { // (:914-948) every non-null detection, in order
+        if (!vDetectionObjects[j]) continue;
+        const int32_t *oi = order.data() + start[j + 1], *di = oorder.data() + ostart[j + 1];
+        const int no = start[j + 2] - start[j + 1], nd = ostart[j + 2] - ostart[j + 1];
+        mvDetectionObjects.push_back(vDetectionObjects[j]);
+        mvObjKeys.push_back(gather_keys(mvTempObjKeys, di, nd));
+        mvObjPointsDescriptors.push_back(gather_rows(mTempObjPointsDescriptors, di, nd));
+        mvObjKeysUn.push_back(gather_keys(mvTempObjKeysUn, di, nd));
+        mvObjPointDepth.push_back(gather_f(mvTempObjDepth, di, nd));
+        mvuObjKeysRight.push_back(gather_f(mvuTempObjKeysRight, di, nd));
+        mvOriKeys.push_back(gather_keys(mvKeys, oi, no));
+        mOriDescriptors.push_back(gather_rows(mDescriptors, oi, no));
+        mvOriKeysUn.push_back(gather_keys(mvKeysUn, oi, no));
+        mvOriDepth.push_back(gather_f(mvDepth, oi, no));
+        mvuOriRight.push_back(gather_f(mvuRight, oi, no));
+        mvnEffectiveObjPointDepthNums.push_back((size_t)oeff[j]);
+        vDetectionObjects[j]->InitInFrameMapObjectPointsOrder((size_t)nd);
+    }
+    // background features (:950-955)
+    const int nb = start[1];
+    std::vector<cv::KeyPoint> keys = gather_keys(mvKeys, order.data(), nb), keysUn = gather_keys(mvKeysUn, order.data(), nb);
+    cv::Mat desc = gather_rows(mDescriptors, order.data(), nb);
+    std::vector<float> depth = gather_f(mvDepth, order.data(), nb), uright = gather_f(mvuRight, order.data(), nb);
+    mvKeys.swap(keys); mvKeysUn.swap(keysUn); mDescriptors = desc; mvDepth.swap(depth); mvuRight.swap(uright);
+    mnDetObj = mvDetectionObjects.size();
+    mvObjKeysGrid.resize(mnDetObj);
+    mvbObjKeysOutlier.resize(mnDetObj);
+    mvbObjKeysMatchedFlag.resize(mnDetObj);
+    for (size_t i = 0; i < mnDetObj; i++) { // (:967-975)
+        const size_t nFeaNum = mvObjKeysUn[i].size();
+        mvbObjKeysOutlier[i] = std::vector<bool>(nFeaNum, false);
+        mvbObjKeysMatchedFlag[i] = std::vector<bool>(nFeaNum, false);
+        AssignDetObjFeasToGrid(i, nFeaNum);
+    }
+}
+
 void Frame::UndistortObjKeyPoints() // (:2080-2110)
 {
     if (mDistCoef.empty() || mDistCoef.at<float>(0) == 0.0) {

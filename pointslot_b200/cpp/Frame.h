@@ -13,6 +13,7 @@
 #include <cstddef>
 #include <vector>
 
+#include "DetectionObject.h"
 #include "ORBextractor.h"
 #include "ORBVocabulary.h"
 #include "compat/opencv_min.h"
@@ -83,6 +84,16 @@ public:
     // calls this with them.
     void ExtractObjORB(cv::Mat left, cv::Mat right, cv::Mat LeftObjMask, cv::Mat RightObjMask);
 
+    // Feature partition by the instance mask (reference Frame.h:209 / Frame.cc:759-977; runs after the two stereo matchers
+    // in the object-mode constructors, :478, :648, :733): the frame's ORB features with mMaskImg == 0 stay in mvKeys /
+    // mDescriptors / mvuRight / mvDepth / mvKeysUn, the others go to their detection's mvOri* lists; the dense object
+    // features (mvTempObj*) go to their detection's mvObj* lists; null detections are dropped from mvDetectionObjects.
+    // The classification and the push_back order of every list come from the device (pslot_assign_features, one call
+    // per feature set, the mask uploaded once); the containers are then filled on the host.
+    void AssignFeatures(std::vector<DetectionObject *> &vDetectionObjects);
+    // mvObjKeysGrid[objOrder] from mvObjKeysUn[objOrder] (reference Frame.cc:1863-1888)
+    void AssignDetObjFeasToGrid(const size_t &objOrder, const size_t &objFeaNum);
+
     // Stereo matching of the OBJECT feature set (reference Frame.cc:2318-2503: the same routine as
     // ComputeStereoMatches on mvTempObjKeys / mvTempObjKeysRight and their descriptors, reading the same two
     // pyramids); results in mvuTempObjKeysRight / mvTempObjDepth.
@@ -133,6 +144,18 @@ public:
     std::vector<cv::KeyPoint> mvTempObjKeys, mvTempObjKeysRight, mvTempObjKeysUn;
     std::vector<float> mvuTempObjKeysRight, mvTempObjDepth;
     cv::Mat mTempObjPointsDescriptors, mTempObjPointsDescriptorsRight;
+
+    // instance mask of the left view (reference Frame.h:190): 0 background, 255 ignored, object id + 1 elsewhere
+    cv::Mat mMaskImg;
+    // per detected object, filled by AssignFeatures (reference Frame.h:151-164, 176-180, 206)
+    std::vector<DetectionObject *> mvDetectionObjects;
+    std::vector<std::vector<cv::KeyPoint>> mvObjKeys, mvObjKeysUn, mvOriKeys, mvOriKeysUn;
+    std::vector<cv::Mat> mvObjPointsDescriptors, mOriDescriptors;
+    std::vector<std::vector<float>> mvObjPointDepth, mvuObjKeysRight, mvuOriRight, mvOriDepth;
+    std::vector<std::vector<bool>> mvbObjKeysOutlier, mvbObjKeysMatchedFlag;
+    std::vector<std::vector<std::vector<std::vector<std::size_t>>>> mvObjKeysGrid;
+    size_t mnDetObj = 0;
+    std::vector<size_t> mvnEffectiveObjPointDepthNums; // vnEffectiveObjPointDepthNums of the reference (a local there, :775)
 
     // MapPoints associated to keypoints, NULL pointer if no association.
     std::vector<MapPoint *> mvpMapPoints;

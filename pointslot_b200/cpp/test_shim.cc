@@ -199,6 +199,55 @@ int main(int argc, char **argv)
             std::fwrite(e.second.data(), 4, cnt, o);
         }
     }
+    // Frame::AssignFeatures (reference Frame.cc:759-977) with the instance mask and detection ids given as the fourth
+    // argument: [int nObj][int ids[nObj] (negative: null detection)][H * W mask bytes].  As in the object-mode constructors
+    // (:725-733) the dense features get their stereo depth first.
+    if (argc > 4) {
+        FILE *mf = std::fopen(argv[4], "rb");
+        int nObj = 0;
+        if (!mf || std::fread(&nObj, 4, 1, mf) != 1 || nObj < 0 || nObj > 256) return 9;
+        std::vector<int> ids((size_t)nObj);
+        std::vector<unsigned char> mbytes((size_t)W * H);
+        if ((nObj && std::fread(ids.data(), 4, nObj, mf) != (size_t)nObj) || std::fread(mbytes.data(), 1, mbytes.size(), mf) != mbytes.size()) return 9;
+        std::fclose(mf);
+        std::vector<DetectionObject> pool((size_t)nObj);
+        std::vector<DetectionObject *> dets((size_t)nObj, nullptr);
+        for (int j = 0; j < nObj; ++j)
+            if (ids[j] >= 0) { pool[j].mnObjectID = ids[j]; dets[j] = &pool[j]; }
+        frame.UndistortObjKeyPoints();
+        frame.ComputeObjStereoMatches();
+        const int nOL2 = (int)frame.mvTempObjKeys.size();
+        std::fwrite(&nOL2, 4, 1, o);
+        std::fwrite(frame.mvuTempObjKeysRight.data(), 4, nOL2, o);
+        std::fwrite(frame.mvTempObjDepth.data(), 4, nOL2, o);
+        frame.mMaskImg = cv::Mat(H, W, CV_8UC1, mbytes.data());
+        frame.AssignFeatures(dets);
+        const int nKept = (int)frame.mnDetObj, nb = (int)frame.mvKeys.size();
+        std::fwrite(&nKept, 4, 1, o); std::fwrite(&nb, 4, 1, o);
+        auto dump_set = [&](const std::vector<cv::KeyPoint> &k, const std::vector<cv::KeyPoint> &kun, const cv::Mat &d,
+                            const std::vector<float> &ur, const std::vector<float> &dp) {
+            const int n = (int)k.size();
+            if ((int)kun.size() != n || (int)ur.size() != n || (int)dp.size() != n || (n ? d.rows : 0) != n) std::exit(10);
+            std::fwrite(k.data(), sizeof(cv::KeyPoint), n, o);
+            std::fwrite(kun.data(), sizeof(cv::KeyPoint), n, o);
+            for (int i = 0; i < n; ++i) std::fwrite(d.ptr(i), 1, 32, o);
+            std::fwrite(ur.data(), 4, n, o);
+            std::fwrite(dp.data(), 4, n, o);
+        };
+        dump_set(frame.mvKeys, frame.mvKeysUn, frame.mDescriptors, frame.mvuRight, frame.mvDepth);
+        for (int k = 0; k < nKept; ++k) {
+            const int id = frame.mvDetectionObjects[k]->mnObjectID, nOri = (int)frame.mvOriKeys[k].size(), nDense = (int)frame.mvObjKeys[k].size();
+            const int eff = (int)frame.mvnEffectiveObjPointDepthNums[k], init = (int)frame.mvDetectionObjects[k]->mnInFrameOrderSize;
+            int gridTotal = 0, gridChecksum = 0;
+            for (int i = 0; i < FRAME_GRID_COLS; ++i)
+                for (int j = 0; j < FRAME_GRID_ROWS; ++j)
+                    for (size_t v : frame.mvObjKeysGrid[k][i][j]) { ++gridTotal; gridChecksum += (int)v * (i * FRAME_GRID_ROWS + j + 1); }
+            const int head[7] = {id, nOri, nDense, eff, init, gridTotal, gridChecksum};
+            std::fwrite(head, 4, 7, o);
+            dump_set(frame.mvOriKeys[k], frame.mvOriKeysUn[k], frame.mOriDescriptors[k], frame.mvuOriRight[k], frame.mvOriDepth[k]);
+            dump_set(frame.mvObjKeys[k], frame.mvObjKeysUn[k], frame.mvObjPointsDescriptors[k], frame.mvuObjKeysRight[k], frame.mvObjPointDepth[k]);
+        }
+    }
     std::fclose(o);
     std::printf("shim ok: N=%d Nr=%d matched=%d mb=%g projection matches=%d\n", N, Nr,
                 (int)std::count_if(frame.mvuRight.begin(), frame.mvuRight.end(), [](float v) { return v >= 0; }), frame.mb, nmatches);

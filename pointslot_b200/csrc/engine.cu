@@ -419,9 +419,16 @@ struct pslot_orb {
     void *d_proj = nullptr;
     size_t proj_bytes = 0;
     int last_sweeps = 0;
+    // pslot_assign_features scratch: one arena (keypoints | depth | ids | cls | order | class_start | effective) + the mask
+    unsigned char *d_part = nullptr;
+    size_t part_bytes = 0;
+    uint8_t *d_pmask = nullptr;
+    size_t pmask_bytes = 0;
+    int pmask_w = 0, pmask_h = 0;
 
     ~pslot_orb()
     {
+        cudaFree(d_part); cudaFree(d_pmask);
         free_stereo();
         cudaFree(d_gk); cudaFree(d_gidx); cudaFree(d_gcs); cudaFree(d_qcount); cudaFree(d_qout); cudaFree(d_q);
         cudaFree(d_proj);
@@ -445,6 +452,8 @@ struct pslot_batch {
     bool profiling = false, profiled = false;
     cudaEvent_t ev[PSLOT_NUM_STAGES + 1] = {};
     int *d_gcs = nullptr, *d_gidx = nullptr; // feature grids of the last submit (pslot_batch_assign_grid)
+    unsigned char *d_part = nullptr;         // pslot_batch_assign_features: masks | ids | cls | order | class_start | effective
+    size_t part_bytes = 0;
     int gcs_cells = 0;
     unsigned long long *d_counters = nullptr; // stereo work counters, accumulated by profiled submits (pslot_batch_stereo_counters)
     uint8_t *d_stage = nullptr; // tightly packed landing zone for host images (one linear H2D per view)
@@ -466,6 +475,7 @@ struct pslot_batch {
         cudaFree(d_cstage);
         cudaFree(d_counters);
         cudaFree(d_gcs);
+        cudaFree(d_part);
         cudaFree(d_gidx);
     }
 };
@@ -1683,6 +1693,120 @@ int pslot_assign_grid(pslot_orb *ctx, const pslot_keypoint *kps_un, int n, const
     ctx->grid_spec = *spec;
     ctx->h_gangle.resize((size_t)n);
     for (int i = 0; i < n; ++i) ctx->h_gangle[i] = kps_un[i].angle;
+    return PSLOT_OK;
+}
+
+// ---- Frame::AssignFeatures ---------------------------------------------------------------------------------------------
+int pslot_assign_features(pslot_orb *ctx, const pslot_keypoint *kps, int n, const uint8_t *mask, int w, int h, ptrdiff_t mask_pitch,
+                          const int32_t *object_ids, int n_objects, const float *depth, float depth_limit, int32_t *cls,
+                          int32_t *order, int32_t *class_start, int32_t *effective)
+{
+    if (!ctx) return fail(PSLOT_ERR_ARG, "ctx is null");
+    if (n < 0 || (n > 0 && (!kps || !cls || !order))) return fail(PSLOT_ERR_ARG, "bad feature arrays");
+    if (n_objects < 0 || n_objects > 256 || (n_objects > 0 && !object_ids)) return fail(PSLOT_ERR_ARG, "n_objects must be in [0,256]");
+    if (!class_start) return fail(PSLOT_ERR_ARG, "class_start is null");
+    if (w <= 0 || h <= 0) return fail(PSLOT_ERR_ARG, "bad mask size");
+    if (mask && mask_pitch < w) return fail(PSLOT_ERR_ARG, "pitch < width");
+    Engine &E = ctx->E;
+    CU(cudaSetDevice(E.device));
+    cudaStream_t st = E.st;
+    if (mask) {
+        const size_t need = (size_t)w * h;
+        if (need > ctx->pmask_bytes) {
+            CU(cudaStreamSynchronize(st));
+            cudaFree(ctx->d_pmask);
+            ctx->d_pmask = nullptr; ctx->pmask_bytes = 0;
+            CU(cudaMalloc(&ctx->d_pmask, need));
+            ctx->pmask_bytes = need;
+        }
+        CU(cudaMemcpy2DAsync(ctx->d_pmask, (size_t)w, mask, (size_t)mask_pitch, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, st));
+        ctx->pmask_w = w; ctx->pmask_h = h;
+    } else if (!ctx->d_pmask || ctx->pmask_w != w || ctx->pmask_h != h) {
+        return fail(PSLOT_ERR_STATE, "mask is null and no mask of this size was uploaded by an earlier call");
+    }
+    // arena layout
+    const size_t N = (size_t)std::max(n, 1), J = (size_t)std::max(n_objects, 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_k = take(sizeof(pslot_keypoint) * N), o_d = take(4 * N), o_id = take(4 * J), o_cls = take(4 * N),
+                 o_ord = take(4 * N), o_cs = take(4 * (J + 2)), o_eff = take(4 * J);
+    if (off > ctx->part_bytes) {
+        CU(cudaStreamSynchronize(st));
+        cudaFree(ctx->d_part);
+        ctx->d_part = nullptr; ctx->part_bytes = 0;
+        const size_t cap = std::max<size_t>(2 * off, 1 << 18);
+        CU(cudaMalloc(&ctx->d_part, cap));
+        ctx->part_bytes = cap;
+    }
+    unsigned char *A = ctx->d_part;
+    if (n) CU(cudaMemcpyAsync(A + o_k, kps, sizeof(pslot_keypoint) * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (n && depth) CU(cudaMemcpyAsync(A + o_d, depth, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (n_objects) CU(cudaMemcpyAsync(A + o_id, object_ids, 4 * (size_t)n_objects, cudaMemcpyHostToDevice, st));
+    PartArgs a{};
+    a.kps = reinterpret_cast<const pslot_keypoint *>(A + o_k); a.counts = nullptr; a.fixed_n = n; a.kp_stride = 0;
+    a.mask = ctx->d_pmask; a.w = w; a.h = h; a.pitch = w; a.mask_stride = 0;
+    a.object_ids = reinterpret_cast<const int *>(A + o_id); a.n_objects = n_objects; a.ids_stride = 0;
+    a.depth = depth ? reinterpret_cast<const float *>(A + o_d) : nullptr; a.depth_stride = 0; a.depth_limit = depth_limit;
+    a.cls = reinterpret_cast<int *>(A + o_cls); a.order = reinterpret_cast<int *>(A + o_ord); a.out_stride = 0;
+    a.class_start = reinterpret_cast<int *>(A + o_cs);
+    a.effective = reinterpret_cast<int *>(A + o_eff);
+    launch_assign_features(a, 1, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(class_start, A + o_cs, 4 * (size_t)(n_objects + 2), cudaMemcpyDeviceToHost, st));
+    if (n) CU(cudaMemcpyAsync(cls, A + o_cls, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (effective && n_objects) CU(cudaMemcpyAsync(effective, A + o_eff, 4 * (size_t)n_objects, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int kept = class_start[n_objects + 1];
+    if (kept > 0) CU(cudaMemcpy(order, A + o_ord, 4 * (size_t)kept, cudaMemcpyDeviceToHost));
+    return PSLOT_OK;
+}
+
+int pslot_batch_assign_features(pslot_batch *b, const uint8_t *masks, ptrdiff_t mask_pitch, ptrdiff_t mask_image_stride,
+                                const int32_t *object_ids, int n_objects, int32_t *cls, int32_t *order, int32_t *class_start)
+{
+    if (!b) return fail(PSLOT_ERR_ARG, "b is null");
+    if (b->last_pairs <= 0) return fail(PSLOT_ERR_STATE, "no batch has been submitted");
+    if (!masks || !cls || !order || !class_start) return fail(PSLOT_ERR_ARG, "null argument");
+    if (n_objects < 0 || n_objects > 256 || (n_objects > 0 && !object_ids)) return fail(PSLOT_ERR_ARG, "n_objects must be in [0,256]");
+    Engine &E = b->E;
+    if (mask_pitch < E.W || mask_image_stride < mask_pitch * E.H) return fail(PSLOT_ERR_ARG, "bad mask pitch / stride");
+    CU(cudaSetDevice(E.device));
+    const int np = b->last_pairs;
+    const size_t K = (size_t)E.g.kp_cap_total, P = (size_t)b->max_pairs, J = (size_t)std::max(n_objects, 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_m = take((size_t)E.W * E.H * P), o_id = take(4 * J * P), o_cls = take(4 * K * P), o_ord = take(4 * K * P),
+                 o_cs = take(4 * (J + 2) * P);
+    if (off > b->part_bytes) {
+        CU(cudaStreamSynchronize(E.st));
+        cudaFree(b->d_part);
+        b->d_part = nullptr; b->part_bytes = 0;
+        CU(cudaMalloc(&b->d_part, off));
+        CU(cudaMemset(b->d_part, 0, off));
+        b->part_bytes = off;
+    }
+    unsigned char *A = b->d_part;
+    if (mask_image_stride == mask_pitch * E.H)
+        CU(cudaMemcpy2DAsync(A + o_m, (size_t)E.W, masks, (size_t)mask_pitch, (size_t)E.W, (size_t)E.H * np, cudaMemcpyHostToDevice, E.st));
+    else // images not back to back: one copy per image
+        for (int i = 0; i < np; ++i)
+            CU(cudaMemcpy2DAsync(A + o_m + (size_t)i * E.W * E.H, (size_t)E.W, masks + (size_t)i * mask_image_stride, (size_t)mask_pitch,
+                                 (size_t)E.W, (size_t)E.H, cudaMemcpyHostToDevice, E.st));
+    if (n_objects) CU(cudaMemcpyAsync(A + o_id, object_ids, 4 * (size_t)n_objects * np, cudaMemcpyHostToDevice, E.st));
+    PartArgs a{};
+    // left images are slots 0..np-1 of the batch: counts and keypoint rows are the first np entries
+    a.kps = E.d_out_kps; a.counts = E.d_out_count; a.fixed_n = 0; a.kp_stride = K;
+    a.mask = A + o_m; a.w = E.W; a.h = E.H; a.pitch = E.W; a.mask_stride = (size_t)E.W * E.H;
+    a.object_ids = reinterpret_cast<const int *>(A + o_id); a.n_objects = n_objects; a.ids_stride = (size_t)n_objects;
+    a.depth = nullptr; a.depth_stride = 0; a.depth_limit = 0.f;
+    a.cls = reinterpret_cast<int *>(A + o_cls); a.order = reinterpret_cast<int *>(A + o_ord); a.out_stride = K;
+    a.class_start = reinterpret_cast<int *>(A + o_cs);
+    a.effective = nullptr;
+    launch_assign_features(a, np, E.st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(class_start, A + o_cs, 4 * (size_t)(n_objects + 2) * np, cudaMemcpyDeviceToHost, E.st));
+    CU(cudaMemcpyAsync(cls, A + o_cls, 4 * K * np, cudaMemcpyDeviceToHost, E.st));
+    CU(cudaMemcpyAsync(order, A + o_ord, 4 * K * np, cudaMemcpyDeviceToHost, E.st));
     return PSLOT_OK;
 }
 

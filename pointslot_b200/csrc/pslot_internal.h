@@ -221,4 +221,15 @@ struct ProjArgs {
     int th_dist;    // acceptance: bestDist <= th_dist (TH_HIGH = 100, or the relocalisation search's ORBdist)
 };
 int launch_search_by_projection(const ProjArgs &a, cudaStream_t st);
+// Frame::AssignFeatures (partition.cu): classify by the instance mask + stable partition, one CTA per image
+struct PartArgs {
+    const pslot_keypoint *kps; const int *counts; int fixed_n; size_t kp_stride; // image i: kps + i * kp_stride, counts[i] or fixed_n features
+    const uint8_t *mask; int w, h, pitch; size_t mask_stride;                   // instance mask (0 background, 255 ignored, id + 1)
+    const int *object_ids; int n_objects; size_t ids_stride;                    // mnObjectID per detection (negative: null); stride 0 = shared
+    const float *depth; size_t depth_stride; float depth_limit;                 // optional: effective[j] counts 0 < depth < limit
+    int *cls, *order; size_t out_stride;
+    int *class_start;                                                           // n_objects + 2 per image
+    int *effective;                                                             // n_objects per image, or null
+};
+int launch_assign_features(const PartArgs &a, int nimages, cudaStream_t st);
 void launch_debug_steer(const float *angle_deg, int n, float *a, float *b, cudaStream_t st);

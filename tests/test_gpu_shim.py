@@ -30,7 +30,18 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle_mod):
     from pointslot_b200.vocab import random_vocabulary
     voc = random_vocabulary(10, 4, seed=2)
     voc.to_text(tmp_path / "voc.txt")
-    subprocess.check_call([str(SHIM / "test_shim"), str(inp), str(out), str(tmp_path / "voc.txt")])
+    # instance mask + detections for Frame::AssignFeatures (Frame.cc:759-977): ids above 255, a null detection, a repeated
+    # id, ids without a region, a region without a detection, ignored (255) areas
+    seg = np.zeros((H, W), np.uint8)
+    for i, lab in enumerate([1, 4, 9, 30, 200, 254, 77]):
+        x0 = 20 + i * 85
+        seg[50 + 6 * i:340 - 5 * i, x0:x0 + 70] = lab
+    seg[:, W - 25:] = 255
+    seg[360:, 200:420] = 255
+    det_ids = np.array([0, 3 + 255, -1, 8, 8, 29, 199, 253, 500, 120], np.int32)
+    with open(tmp_path / "seg.bin", "wb") as f:
+        f.write(struct.pack("<i", len(det_ids))); f.write(det_ids.tobytes()); f.write(seg.tobytes())
+    subprocess.check_call([str(SHIM / "test_shim"), str(inp), str(out), str(tmp_path / "voc.txt"), str(tmp_path / "seg.bin")])
     raw = out.read_bytes()
     N, Nr = struct.unpack_from("<2i", raw, 0)
     o = 8
@@ -71,6 +82,25 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle_mod):
     for _ in range(n_fv):
         node, cnt = struct.unpack_from("<2i", raw, o); o += 8
         featvec.append((node, np.frombuffer(raw, np.uint32, cnt, o))); o += 4 * cnt
+    # ---- Frame::AssignFeatures section
+    (n_ol2,) = struct.unpack_from("<i", raw, o); o += 4
+    f_our = np.frombuffer(raw, np.float32, n_ol2, o); o += 4 * n_ol2
+    f_odp = np.frombuffer(raw, np.float32, n_ol2, o); o += 4 * n_ol2
+    n_kept, n_bg = struct.unpack_from("<2i", raw, o); o += 8
+
+    def read_set(n):
+        nonlocal o
+        k = np.frombuffer(raw, B.KEYPOINT_DTYPE, n, o); o += 28 * n
+        kun = np.frombuffer(raw, B.KEYPOINT_DTYPE, n, o); o += 28 * n
+        d = np.frombuffer(raw, np.uint8, 32 * n, o).reshape(n, 32); o += 32 * n
+        u = np.frombuffer(raw, np.float32, n, o); o += 4 * n
+        z = np.frombuffer(raw, np.float32, n, o); o += 4 * n
+        return k, kun, d, u, z
+    bg_set = read_set(n_bg)
+    det_sets = []
+    for _ in range(n_kept):
+        head = struct.unpack_from("<7i", raw, o); o += 28
+        det_sets.append((head, read_set(head[1]), read_set(head[2])))
     assert o == len(raw)
 
     O = oracle_mod
@@ -123,6 +153,31 @@ def test_cpp_shim_matches_oracle(tmp_path, oracle_mod):
     for img, k, d in ((L, okl, odl), (R, okr, odr)):
         rk, rd = O.cvorb_detect_and_compute(img, mask)
         assert k.tobytes() == rk.tobytes() and np.array_equal(d, rd) and len(k) > 100
+
+    # Frame::AssignFeatures (Frame.cc:759-977) through the drop-in Frame: background set, per-detection ORB and dense sets in
+    # the reference's push_back order, effective-depth counts, per-object grids - against the oracle (pinned to the
+    # reference's own function in tests/test_oracle_reference.py)
+    def same_set(got, k, d, u, z, idx, what):
+        gk, gkun, gd, gu, gz = got
+        assert gk.tobytes() == k[idx].tobytes() and gkun.tobytes() == k[idx].tobytes(), what
+        assert np.array_equal(gd, d[idx]) and np.array_equal(gu, u[idx]) and np.array_equal(gz, z[idx]), what
+    assert n_ol2 == len(okl)
+    oour, oodp = O.stereo_match(oL, oR, okl, odl, okr, odr, bf, maxD)
+    assert np.array_equal(f_our >= 0, oour >= 0) and np.all(np.abs(f_our - oour) <= 1e-3)
+    _, groups, _ = O.assign_features(kL, seg, det_ids)
+    _, ogroups, oeff = O.assign_features(okl, seg, det_ids, depth=f_odp, depth_limit=2 * 35.0)
+    same_set(bg_set, kL, dL, ur, dp, groups[0], "background")
+    kept = [j for j in range(len(det_ids)) if det_ids[j] >= 0]
+    assert n_kept == len(kept) and n_bg > 100
+    for (head, ori, dense), j in zip(det_sets, kept):
+        assert head[0] == det_ids[j] and head[1] == len(groups[1 + j]) and head[2] == len(ogroups[1 + j])
+        same_set(ori, kL, dL, ur, dp, groups[1 + j], f"ORB features of detection {j}")
+        same_set(dense, okl, odl, f_our, f_odp, ogroups[1 + j], f"dense features of detection {j}")
+        assert head[3] == oeff[j] and head[4] == len(ogroups[1 + j])
+        cs, idx = O.assign_grid(okl[ogroups[1 + j]], 0.0, 0.0, np.float32(64) / np.float32(W), np.float32(48) / np.float32(H))
+        cell_of = np.repeat(np.arange(64 * 48), np.diff(cs))
+        assert head[5] == len(idx) and head[6] == int((idx.astype(np.int64) * (cell_of + 1)).sum())
+    assert sum(h[2] for h, _, _ in det_sets) > 300 and sum(h[1] for h, _, _ in det_sets) > 100
 
     # Frame::ComputeBoW (Frame.cc:2040-2047) through the drop-in ORBVocabulary (loadFromTextFile + transform)
     bid, bval, fn, fs, ff = O.bow_vectors(voc, *O.bow_transform(voc, odL, 4))

@@ -10,6 +10,10 @@
 * grid (AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea, Frame.cc:1636-1655, 2027-2038, 1808-1861), projection
   searches (ORBmatcher.cc:68-155, 1613-1756) and DescriptorDistance (:2704-2720): identical results.
 
+* feature partition (Frame::AssignFeatures + AssignDetObjFeasToGrid, Frame.cc:759-977, 1863-1888, lifted verbatim): the
+  background set, every detection's ORB and dense feature lists in push_back order, the effective-depth counts' consumers
+  and the per-object grids.
+
 The libraries travel to the GPU box prebuilt; /root/reference is only needed to (re)build them."""
 import numpy as np
 import pytest
@@ -470,3 +474,59 @@ def test_oracle_equals_reference_search_by_projection_obj(oracle_mod):
         assert rn == n and n > 60
         assert np.array_equal(rslot, _replay_slots(len(k), c["occupied"], got))
         assert inside[got[got >= 0]].all() and (~inside).sum() > 50
+
+
+def _partition_case(oracle_mod, seed, n_orb=1500, n_dense=1000, W=1242, H=375):
+    """Features of a frame + an instance mask (0 background, 255 ignored, id + 1 inside the objects) + detections whose ids
+    exercise every branch of Frame.cc:836-846: ids above 255, a null detection, two detections with the same id (first
+    wins), an id with no mask region, a mask label with no detection."""
+    rng = np.random.default_rng(seed)
+
+    def feats(n):
+        k = np.zeros(n, oracle_mod.KEYPOINT_DTYPE)
+        k["x"] = rng.uniform(0, W - 0.01, n).astype(F); k["y"] = rng.uniform(0, H - 0.01, n).astype(F)
+        k["octave"] = rng.integers(0, 8, n); k["size"] = 31; k["angle"] = rng.uniform(0, 360, n).astype(F)
+        d = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        ur = np.where(rng.random(n) < 0.6, k["x"] - rng.uniform(1, 60, n), -1).astype(F)
+        dp = np.where(ur >= 0, rng.uniform(0.5, 120, n), -1).astype(F)
+        return k, d, ur, dp
+    mask = np.zeros((H, W), np.uint8)
+    labels = [1, 4, 9, 30, 200, 254, 77]  # 77: no detection carries id 76
+    for i, lab in enumerate(labels):
+        x0 = 40 + i * 165
+        mask[60 + 10 * i:300 - 8 * i, x0:x0 + 140] = lab
+    mask[:, W - 30:] = 255
+    mask[320:, 500:800] = 255
+    ids = np.array([0, 3 + 255, -1, 8, 8, 29, 199, 253, 500, 120], np.int32)  # 8 twice; 500 -> 245 and 120: no region; -1 null
+    return feats(n_orb), feats(n_dense), mask, ids
+
+
+def test_oracle_equals_reference_assign_features(oracle_mod):
+    ref_path = _ref("stock")
+    W, H = 1242, 375
+    inv_w, inv_h = F(64) / F(W), F(48) / F(H)
+    for seed in (1, 2, 3):
+        (k, d, ur, dp), (ok, od, our, odp), mask, ids = _partition_case(oracle_mod, seed)
+        if seed == 3:
+            ids = ids[:0]  # no detections at all: everything outside label 0 is dropped
+        th_depth = 35.0
+        r = ref_path.assign_features(k, d, ur, dp, ok, od, our, odp, mask, ids, th_depth, 0.0, float(W), 0.0, float(H),
+                                     float(inv_w), float(inv_h))
+        cls, groups, _ = oracle_mod.assign_features(k, mask, ids)
+        ocls, ogroups, eff = oracle_mod.assign_features(ok, mask, ids, depth=odp, depth_limit=2 * th_depth)
+        assert np.array_equal(r["background"], groups[0])
+        kept = [j for j in range(len(ids)) if ids[j] >= 0]  # the reference keeps every non-null detection, in order
+        assert r["det_of"].tolist() == kept
+        for kk, j in enumerate(kept):
+            assert np.array_equal(r["ori"][kk], groups[1 + j]), f"ORB features of detection {j}"
+            assert np.array_equal(r["obj"][kk], ogroups[1 + j]), f"dense features of detection {j}"
+            assert r["init_n"][kk] == len(ogroups[1 + j])
+            # AssignDetObjFeasToGrid == the grid of the object's own keypoint list
+            cs, idx = oracle_mod.assign_grid(ok[ogroups[1 + j]], 0.0, 0.0, inv_w, inv_h)
+            assert np.array_equal(r["grid"][kk][0], cs) and np.array_equal(r["grid"][kk][1], idx)
+            want_eff = int(((odp[ogroups[1 + j]] > 0) & (odp[ogroups[1 + j]] < 2 * th_depth)).sum())
+            assert eff[j] == want_eff
+        if len(ids):
+            assert len(groups[1 + 4]) == 0 and len(groups[1 + 3]) > 0      # the second detection with id 8 gets nothing
+            assert len(groups[1 + 1]) > 0                                   # mnObjectID 258 -> id 3 -> label 4
+            assert len(groups[1 + 8]) == 0 and len(groups[1 + 9]) == 0 and (cls == -1).sum() > 0
