@@ -638,8 +638,9 @@ def measure_brief(cfg, name, rank, world, local_rank, args, dist, steps, warmup,
 
 
 def single_pair_latency(cfg, local_rank, reps=30):
-    """configs[0] as the reference runs it: ONE pair through the reference-shaped API (two extractor contexts driven from two
-    host threads as Frame.cc:161-164 does, then ComputeStereoMatches), host images in, host results out -> ms per pair."""
+    """configs[0] as the reference runs it: ONE pair through the reference-shaped API (two extractor contexts, both views in
+    flight at once as Frame.cc:161-164 arranges with two threads, then ComputeStereoMatches), host images in, host results out
+    -> ms per pair."""
     from pointslot_b200 import binding as B
     from pointslot_b200.synth import synth_pair
     L, R = synth_pair(cfg["W"], cfg["H"], 0)
@@ -647,12 +648,9 @@ def single_pair_latency(cfg, local_rank, reps=30):
     maxD = max_disparity(cfg)
 
     def once():
-        box = {}
-        th = threading.Thread(target=lambda: box.__setitem__("r", eR.extract(R)))
-        th.start()
-        kL, dL = eL.extract(L)
-        th.join()
-        kR, dR = box["r"]
+        # one host thread keeps both views in flight (pslot_orb_extract_begin / _end), as the drop-in Frame constructor does
+        eL.extract_begin(L); eR.extract_begin(R)
+        kL, dL = eL.extract_end(); kR, dR = eR.extract_end()
         B.stereo_match(eL, eR, kL, dL, kR, dR, cfg["bf"], maxD)
     for _ in range(5):
         once()
@@ -678,14 +676,9 @@ def object_frame_latency(cfg, local_rank, reps=30):
     maxD = max_disparity(cfg)
 
     def once():
-        box = {}
-        t1 = threading.Thread(target=lambda: box.__setitem__("r", eR.extract(R)))
-        t2 = threading.Thread(target=lambda: box.__setitem__("o", orb.detect_and_compute_batch([L, R], [mask, mask])))
-        t1.start(); t2.start()
-        kL, dL = eL.extract(L)
-        t1.join(); t2.join()
-        kR, dR = box["r"]
-        (okL, odL), (okR, odR) = box["o"]
+        eL.extract_begin(L); eR.extract_begin(R)  # in flight while this thread runs the (synchronous) cv::ORB pair
+        (okL, odL), (okR, odR) = orb.detect_and_compute_batch([L, R], [mask, mask])
+        kL, dL = eL.extract_end(); kR, dR = eR.extract_end()
         B.stereo_match(eL, eR, kL, dL, kR, dR, cfg["bf"], maxD)
         B.stereo_match(eL, eR, okL, odL, okR, odR, cfg["bf"], maxD)  # ComputeObjStereoMatches: same routine, object keypoints
         return len(kL), len(okL)

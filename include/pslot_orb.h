@@ -81,6 +81,12 @@ int pslot_orb_extract(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_
  * OpenCV 4.13: Y = (R*9798 + G*19235 + B*3735 + 2^14) >> 15.  channels = 1 is pslot_orb_extract. */
 int pslot_orb_extract_color(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, int channels,
                             int rgb_order, pslot_keypoint *kps, uint8_t *desc32, int cap, int *n);
+/* The same extraction in two halves, so that ONE host thread can have both views in flight (the reference spawns two
+ * threads per frame for that, Frame.cc:161-164): _begin uploads the image and enqueues every kernel and the result
+ * download on the context's stream, _end waits and hands the results over exactly as pslot_orb_extract does.  One
+ * extraction per context at a time; the image may be released once _begin returns. */
+int pslot_orb_extract_begin(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch);
+int pslot_orb_extract_end(pslot_orb *ctx, pslot_keypoint *kps, uint8_t *desc32, int cap, int *n);
 
 /* Backing store of the public member std::vector<cv::Mat> mvImagePyramid (ORBextractor.h:85,
  * filled by ComputePyramid, ORBextractor.cc:1107-1132).  Copies level `level` of the most recent

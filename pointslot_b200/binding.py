@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "pslot_assign_grid", "pslot_grid_token", "pslot_features_in_area", "pslot_batch_assign_grid",
     "pslot_search_by_projection", "pslot_search_by_projection_obj", "pslot_search_by_projection_last", "pslot_search_by_projection_kf", "pslot_debug_projection_sweeps",
     "pslot_cvorb_create", "pslot_cvorb_destroy", "pslot_cvorb_detect_and_compute", "pslot_cvorb_detect_and_compute_batch", "pslot_cvorb_last_timing", "pslot_cvorb_debug",
-    "pslot_assign_features", "pslot_batch_assign_features",
+    "pslot_assign_features", "pslot_batch_assign_features", "pslot_orb_extract_begin", "pslot_orb_extract_end",
     "pslot_vocab_create", "pslot_vocab_destroy", "pslot_bow_transform", "pslot_bow_vectors",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
 ]
@@ -132,6 +132,8 @@ def lib():
     L.pslot_cvorb_detect_and_compute_batch.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_ssize_t, vp, vp,
                                                        C.c_int, vp]
     L.pslot_cvorb_last_timing.argtypes = [vp, vp]
+    L.pslot_orb_extract_begin.argtypes = [vp, vp, C.c_int, C.c_int, C.c_ssize_t]
+    L.pslot_orb_extract_end.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_int)]
     L.pslot_assign_features.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_int, vp, C.c_float, vp, vp, vp, vp]
     L.pslot_batch_assign_features.argtypes = [vp, vp, C.c_ssize_t, C.c_ssize_t, vp, C.c_int, vp, vp, vp]
     L.pslot_cvorb_debug.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -227,6 +229,26 @@ class OrbExtractor:
                 rc = lib().pslot_orb_extract_color(self._h, _p(img), w, h, img.strides[0], channels, 1 if rgb else 0,
                                                    _p(kps), _p(desc), cap, C.byref(n))
             if rc == -2:  # PSLOT_ERR_CAPACITY
+                cap = n.value
+                continue
+            _check(rc)
+            return kps[: n.value].copy(), desc[: n.value].copy()
+        raise PslotError(-2, "capacity retry failed")
+
+    def extract_begin(self, img: np.ndarray):
+        """First half of extract() for a gray image: upload + all kernels + the result download are enqueued; pair with
+        extract_end().  Lets one host thread keep several extractors (the two views) in flight."""
+        assert img.dtype == np.uint8 and img.ndim == 2 and (img.size == 0 or img.strides[1] == 1)
+        h, w = img.shape
+        _check(lib().pslot_orb_extract_begin(self._h, _p(img), w, h, img.strides[0] if img.size else 0))
+
+    def extract_end(self):
+        cap = _check(lib().pslot_orb_max_keypoints(self._h))
+        for _ in range(2):
+            kps = np.zeros(cap, KEYPOINT_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+            n = C.c_int(0)
+            rc = lib().pslot_orb_extract_end(self._h, _p(kps), _p(desc), cap, C.byref(n))
+            if rc == -2:  # PSLOT_ERR_CAPACITY: the results wait in the staging buffer
                 cap = n.value
                 continue
             _check(rc)

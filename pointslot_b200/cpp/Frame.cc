@@ -39,12 +39,14 @@ void Frame::StereoFrontEnd(const cv::Mat &imLeft, const cv::Mat &imRight, cv::Ma
     mvLevelSigma2 = mpORBextractorLeft->GetScaleSigmaSquares();
     mvInvLevelSigma2 = mpORBextractorLeft->GetInverseScaleSigmaSquares();
 
-    // ORB extraction: two host threads drive the two extractor contexts concurrently (:161-164);
-    // each context owns its CUDA stream, so the two images overlap on the device
-    std::thread threadLeft(&Frame::ExtractORB, this, 0, imLeft);
-    std::thread threadRight(&Frame::ExtractORB, this, 1, imRight);
-    threadLeft.join();
-    threadRight.join();
+    // ORB extraction: the reference drives the two extractors from two host threads (:161-164).  Each drop-in extractor
+    // owns a CUDA stream, so ONE thread keeps both views in flight - enqueue left, enqueue right, collect left, collect
+    // right - and the two thread launches per frame go away.  (Frame::ExtractORB is kept for callers that want the
+    // reference's own form.)
+    mpORBextractorLeft->Begin(imLeft);
+    mpORBextractorRight->Begin(imRight);
+    mpORBextractorLeft->End(mvKeys, mDescriptors);
+    mpORBextractorRight->End(mvKeysRight, mDescriptorsRight);
 
     N = (int)mvKeys.size();
     if (mvKeys.empty()) return;

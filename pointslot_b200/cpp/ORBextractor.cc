@@ -69,16 +69,18 @@ void ORBextractor::ExtractFromColor(const cv::Mat &imColor, int channels, bool b
 void ORBextractor::Run(const unsigned char *data, int w, int h, long step, int channels, bool rgb,
                        std::vector<cv::KeyPoint> &_keypoints, cv::OutputArray _descriptors)
 {
+    if (channels == 1) {
+        if (pslot_orb_extract_begin(mpCtx, data, w, h, (ptrdiff_t)step) != PSLOT_OK) die("pslot_orb_extract_begin");
+        End(_keypoints, _descriptors);
+        return;
+    }
     const int cap = pslot_orb_max_keypoints(mpCtx);
     _keypoints.resize(cap);
     mvDescBuf.resize((size_t)cap * 32);
     int n = 0;
-    static_assert(sizeof(cv::KeyPoint) == sizeof(pslot_keypoint), "cv::KeyPoint must be 28 bytes");
     auto call = [&](int capacity) {
         pslot_keypoint *k = reinterpret_cast<pslot_keypoint *>(_keypoints.data());
-        return channels == 1 ? pslot_orb_extract(mpCtx, data, w, h, (ptrdiff_t)step, k, mvDescBuf.data(), capacity, &n)
-                             : pslot_orb_extract_color(mpCtx, data, w, h, (ptrdiff_t)step, channels, rgb ? 1 : 0, k,
-                                                       mvDescBuf.data(), capacity, &n);
+        return pslot_orb_extract_color(mpCtx, data, w, h, (ptrdiff_t)step, channels, rgb ? 1 : 0, k, mvDescBuf.data(), capacity, &n);
     };
     int rc = call(cap);
     if (rc == PSLOT_ERR_CAPACITY) { // the capacity depends on the image aspect ratio; retry with the exact count
@@ -87,6 +89,36 @@ void ORBextractor::Run(const unsigned char *data, int w, int h, long step, int c
         rc = call(n);
     }
     if (rc != PSLOT_OK) die("pslot_orb_extract");
+    Deliver(n, _keypoints, _descriptors);
+}
+
+void ORBextractor::Begin(cv::InputArray _image)
+{
+    cv::Mat image = _image.getMat();
+    if (image.empty()) { // :1046-1047; End() then returns nothing
+        if (pslot_orb_extract_begin(mpCtx, nullptr, 0, 0, 0) != PSLOT_OK) die("pslot_orb_extract_begin");
+        return;
+    }
+    if (pslot_orb_extract_begin(mpCtx, image.data, image.cols, image.rows, (ptrdiff_t)image.step) != PSLOT_OK) die("pslot_orb_extract_begin");
+}
+
+void ORBextractor::End(std::vector<cv::KeyPoint> &_keypoints, cv::OutputArray _descriptors)
+{
+    static_assert(sizeof(cv::KeyPoint) == sizeof(pslot_keypoint), "cv::KeyPoint must be 28 bytes");
+    int cap = pslot_orb_max_keypoints(mpCtx), n = 0, rc = PSLOT_OK;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        _keypoints.resize(cap);
+        mvDescBuf.resize((size_t)cap * 32);
+        rc = pslot_orb_extract_end(mpCtx, reinterpret_cast<pslot_keypoint *>(_keypoints.data()), mvDescBuf.data(), cap, &n);
+        if (rc != PSLOT_ERR_CAPACITY) break; // the capacity depends on the image aspect ratio; retry with the exact count
+        cap = n;
+    }
+    if (rc != PSLOT_OK) die("pslot_orb_extract_end");
+    Deliver(n, _keypoints, _descriptors);
+}
+
+void ORBextractor::Deliver(int n, std::vector<cv::KeyPoint> &_keypoints, cv::OutputArray _descriptors)
+{
     _keypoints.resize(n);
     if (n == 0) {
         _descriptors.release(); // :1065

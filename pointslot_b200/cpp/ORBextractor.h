@@ -75,6 +75,12 @@ public:
     void ExtractFromColor(const cv::Mat &imColor, int channels, bool bRGB, std::vector<cv::KeyPoint> &keypoints,
                           cv::OutputArray descriptors);
 
+    // Extension: operator() in two halves, so that one host thread keeps both views in flight (the reference spawns two
+    // threads per frame for that, Frame.cc:161-164): Begin uploads the image and enqueues the whole extraction on this
+    // extractor's stream, End waits and fills keypoints / descriptors exactly as operator() does.
+    void Begin(cv::InputArray image);
+    void End(std::vector<cv::KeyPoint> &keypoints, cv::OutputArray descriptors);
+
     int inline GetLevels() { return nlevels; }
     float inline GetScaleFactor() { return scaleFactor; }
     std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }
@@ -106,6 +112,7 @@ protected:
 
     void Run(const unsigned char *data, int w, int h, long step, int channels, bool rgb,
              std::vector<cv::KeyPoint> &keypoints, cv::OutputArray descriptors);
+    void Deliver(int n, std::vector<cv::KeyPoint> &keypoints, cv::OutputArray descriptors);
 
     pslot_orb *mpCtx;
     bool mbKeepHostPyramid;

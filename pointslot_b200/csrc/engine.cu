@@ -302,6 +302,7 @@ struct Engine {
         if (rc) return rc;
         CU(cudaStreamSynchronize(st));
         release();
+        ++generation; // every device pointer a captured graph may hold is gone
         g = G;
         size_t off = 0;
         size_t lvoff[PSLOT_MAX_LEVELS];
@@ -353,6 +354,7 @@ struct Engine {
     }
 
     // K1..K6 on slots [0, nslots); level 0 must already be in place.  Returns kernels launched (>0) or <0.
+    int generation = 0; // bumped by every (re)configuration
     int run_extract(int nslots, cudaEvent_t *ev = nullptr)
     {
         int n = 0;
@@ -403,7 +405,12 @@ struct pslot_orb {
     int last_nl = 0;
     unsigned char *h_stage = nullptr; // pinned mirror of E.d_out
     size_t h_stage_bytes = 0;
-    uint8_t *d_cstage = nullptr;      // tightly packed colour frame awaiting conversion
+    // single-frame path: kernels + result download replayed as one CUDA graph (13 launches + 1 copy -> 1 launch); built on
+    // the second frame of a geometry (the first one sets the kernels' attributes), dropped when the engine re-configures
+    cudaGraphExec_t extract_graph = nullptr;
+    int extract_graph_gen = -1, extract_calls_gen = -1, extract_calls = 0;
+    bool extract_pending = false; // pslot_orb_extract_begin ran, pslot_orb_extract_end has not
+    uint8_t *d_cstage = nullptr;      // tightly packed frame (colour, or gray at any pitch-free layout) awaiting conversion / re-pitch
     size_t cstage_bytes = 0;
     // feature grid of the last pslot_assign_grid (kept for pslot_features_in_area)
     pslot_keypoint *d_gk = nullptr;
@@ -428,6 +435,7 @@ struct pslot_orb {
 
     ~pslot_orb()
     {
+        if (extract_graph) cudaGraphExecDestroy(extract_graph);
         cudaFree(d_part); cudaFree(d_pmask);
         free_stereo();
         cudaFree(d_gk); cudaFree(d_gidx); cudaFree(d_gcs); cudaFree(d_qcount); cudaFree(d_qout); cudaFree(d_q);
@@ -789,53 +797,104 @@ int pslot_orb_max_keypoints(const pslot_orb *ctx)
     return ctx->E.W ? ctx->E.g.kp_cap_total : max_keypoints(ctx->E);
 }
 
-static int extract_impl(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, int channels, int rgb,
-                        pslot_keypoint *kps, uint8_t *desc32, int cap, int *n)
+// first half of an extraction: upload + every kernel + the result download are enqueued on the context's stream
+static int extract_enqueue(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, int channels, int rgb)
 {
-    if (!ctx || !n) return fail(PSLOT_ERR_ARG, "ctx / n is null");
-    *n = 0;
-    if (!img || w <= 0 || h <= 0) return PSLOT_OK; // ORBextractor.cc:1046-1047
+    if (!ctx) return fail(PSLOT_ERR_ARG, "ctx is null");
+    ctx->extract_pending = false;
+    if (!img || w <= 0 || h <= 0) return PSLOT_OK; // ORBextractor.cc:1046-1047: no keypoints
     if (channels != 1 && channels != 3 && channels != 4) return fail(PSLOT_ERR_ARG, "channels must be 1, 3 or 4");
     if (pitch < (ptrdiff_t)w * channels) return fail(PSLOT_ERR_ARG, "pitch < width * channels");
     Engine &E = ctx->E;
     CU(cudaSetDevice(E.device));
     int rc = E.configure(w, h, 1);
     if (rc) return rc;
+    if (ctx->extract_graph && (ctx->h_stage_bytes < E.out_bytes || ctx->extract_graph_gen != E.generation)) {
+        cudaGraphExecDestroy(ctx->extract_graph); // it names buffers that are about to move, or already have
+        ctx->extract_graph = nullptr;
+    }
     if (ctx->h_stage_bytes < E.out_bytes) {
         if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
         ctx->h_stage = nullptr;
         CU(cudaHostAlloc((void **)&ctx->h_stage, E.out_bytes, cudaHostAllocDefault));
         ctx->h_stage_bytes = E.out_bytes;
     }
-    if (channels == 1) {
+    if (channels == 1 && pitch != w) {
         CU(cudaMemcpy2DAsync(E.pyr.lv[0], E.g.lv[0].pitch, img, pitch, w, h, cudaMemcpyHostToDevice, E.st));
-    } else { // colour frame: upload once, convert on the device straight into level 0 (Tracking.cc:1014-1039)
+    } else {
+        // tightly packed gray frame: one linear copy + the re-pitch kernel (a 2-D copy of 1242-byte rows runs far below the
+        // link rate); colour frame: upload once, convert on the device straight into level 0 (Tracking.cc:1014-1039)
         const size_t need = (size_t)w * h * channels + 16;
         if (ctx->cstage_bytes < need) {
+            CU(cudaStreamSynchronize(E.st));
             cudaFree(ctx->d_cstage);
             ctx->d_cstage = nullptr; ctx->cstage_bytes = 0;
             CU(cudaMalloc(&ctx->d_cstage, need));
             ctx->cstage_bytes = need;
         }
-        CU(cudaMemcpy2DAsync(ctx->d_cstage, (size_t)w * channels, img, pitch, (size_t)w * channels, h,
-                             cudaMemcpyHostToDevice, E.st));
+        if (pitch == (ptrdiff_t)w * channels)
+            CU(cudaMemcpyAsync(ctx->d_cstage, img, (size_t)w * h * channels, cudaMemcpyHostToDevice, E.st));
+        else
+            CU(cudaMemcpy2DAsync(ctx->d_cstage, (size_t)w * channels, img, pitch, (size_t)w * channels, h, cudaMemcpyHostToDevice, E.st));
         launch_gray_ingest(ctx->d_cstage, (size_t)w * h * channels, channels, rgb, E.pyr.lv[0], w, h, E.g.lv[0].pitch,
                            E.pyr.slot_stride[0], 1, E.st);
     }
-    rc = E.run_extract(1);
-    if (rc < 0) return rc;
-    CU(cudaMemcpyAsync(ctx->h_stage, E.d_out, E.out_bytes, cudaMemcpyDeviceToHost, E.st));
-    rc = check_err_flag(E); // synchronises the stream
-    if (rc) return rc;
+    if (ctx->extract_calls_gen != E.generation) { ctx->extract_calls_gen = E.generation; ctx->extract_calls = 0; }
+    if (!ctx->extract_graph && ctx->extract_calls >= 1) {
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(E.st, cudaStreamCaptureModeThreadLocal));
+        rc = E.run_extract(1);
+        cudaError_t ce = cudaMemcpyAsync(ctx->h_stage, E.d_out, E.out_bytes, cudaMemcpyDeviceToHost, E.st);
+        const cudaError_t ee = cudaStreamEndCapture(E.st, &graph);
+        if (ce == cudaSuccess) ce = ee;
+        if (rc >= 0 && ce == cudaSuccess) ce = cudaGraphInstantiate(&ctx->extract_graph, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc < 0) return rc;
+        if (ce != cudaSuccess) { ctx->extract_graph = nullptr; return fail(PSLOT_ERR_CUDA, "extract graph: %s", cudaGetErrorString(ce)); }
+        ctx->extract_graph_gen = E.generation;
+    }
+    if (ctx->extract_graph) {
+        CU(cudaGraphLaunch(ctx->extract_graph, E.st));
+    } else {
+        rc = E.run_extract(1);
+        if (rc < 0) return rc;
+        CU(cudaMemcpyAsync(ctx->h_stage, E.d_out, E.out_bytes, cudaMemcpyDeviceToHost, E.st));
+    }
+    ++ctx->extract_calls;
+    ctx->extract_pending = true;
+    return PSLOT_OK;
+}
+
+// second half: wait for the stream, hand the results over
+static int extract_finish(pslot_orb *ctx, pslot_keypoint *kps, uint8_t *desc32, int cap, int *n)
+{
+    if (!ctx || !n) return fail(PSLOT_ERR_ARG, "ctx / n is null");
+    *n = 0;
+    if (!ctx->extract_pending) return PSLOT_OK; // empty image
+    Engine &E = ctx->E;
+    CU(cudaSetDevice(E.device));
+    int rc = check_err_flag(E); // synchronises the stream
+    if (rc) { ctx->extract_pending = false; return rc; }
     const int count = *(const int *)ctx->h_stage;
     *n = count;
+    // (the results stay in the staging buffer: the caller may come back with more room)
     if (count > cap) return fail(PSLOT_ERR_CAPACITY, "need room for %d keypoints, caller gave %d", count, cap);
+    ctx->extract_pending = false;
     if (count > 0) {
         if (!kps || !desc32) return fail(PSLOT_ERR_ARG, "kps / desc32 is null");
         memcpy(kps, ctx->h_stage + E.off_kps, sizeof(pslot_keypoint) * (size_t)count);
         memcpy(desc32, ctx->h_stage + E.off_desc, 32 * (size_t)count);
     }
     return PSLOT_OK;
+}
+
+static int extract_impl(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, int channels, int rgb,
+                        pslot_keypoint *kps, uint8_t *desc32, int cap, int *n)
+{
+    if (!ctx || !n) return fail(PSLOT_ERR_ARG, "ctx / n is null");
+    *n = 0;
+    if (int rc = extract_enqueue(ctx, img, w, h, pitch, channels, rgb)) return rc;
+    return extract_finish(ctx, kps, desc32, cap, n);
 }
 
 int pslot_orb_extract(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, pslot_keypoint *kps,
@@ -848,6 +907,16 @@ int pslot_orb_extract_color(pslot_orb *ctx, const uint8_t *img, int w, int h, pt
                             int rgb_order, pslot_keypoint *kps, uint8_t *desc32, int cap, int *n)
 {
     return extract_impl(ctx, img, w, h, pitch, channels, rgb_order, kps, desc32, cap, n);
+}
+
+int pslot_orb_extract_begin(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch)
+{
+    return extract_enqueue(ctx, img, w, h, pitch, 1, 0);
+}
+
+int pslot_orb_extract_end(pslot_orb *ctx, pslot_keypoint *kps, uint8_t *desc32, int cap, int *n)
+{
+    return extract_finish(ctx, kps, desc32, cap, n);
 }
 
 int pslot_orb_level(pslot_orb *ctx, int level, uint8_t *dst, ptrdiff_t pitch, int *w, int *h)

@@ -303,3 +303,29 @@ def test_stereo_work_counters_match_the_row_table(B):
             cmps += int(ok.sum())
     assert got["row_candidates"] == rows and got["hamming_evals"] == cmps
     assert sb.stereo_counters() == {"row_candidates": 0, "hamming_evals": 0}  # reset by the read
+
+
+def test_extract_in_two_halves(oracle_mod):
+    """pslot_orb_extract_begin / _end: both views in flight from one host thread, frame after frame (the second frame of a
+    geometry onwards replays a CUDA graph), other sizes in between, an empty image - always the bytes of the oracle."""
+    from pointslot_b200 import binding as B
+    from pointslot_b200.synth import synth_pair
+    params = (1000, 1.2, 8, 20, 7)
+    eL, eR = B.OrbExtractor(*params), B.OrbExtractor(*params)
+    oe = oracle_mod.OracleExtractor(*params)
+    for W, H, seed in ((640, 360, 1), (640, 360, 2), (640, 360, 3), (403, 301, 4), (640, 360, 5)):
+        L, R = synth_pair(W, H, seed)
+        eL.extract_begin(L); eR.extract_begin(R)
+        kL, dL = eL.extract_end(); kR, dR = eR.extract_end()
+        okL, odL = oe.extract(L); okR, odR = oe.extract(R)
+        assert kL.tobytes() == okL.tobytes() and np.array_equal(dL, odL), (W, H, seed)
+        assert kR.tobytes() == okR.tobytes() and np.array_equal(dR, odR), (W, H, seed)
+        k2, d2 = eL.extract(L)  # the one-call form on the same context
+        assert k2.tobytes() == okL.tobytes() and np.array_equal(d2, odL)
+    big = np.zeros((360, 768), np.uint8); big[:, :640] = L   # a pitched view takes the 2-D upload
+    eL.extract_begin(big[:, :640])
+    k3, d3 = eL.extract_end()
+    assert k3.tobytes() == okL.tobytes() and np.array_equal(d3, odL)
+    eL.extract_begin(np.zeros((0, 0), np.uint8))
+    k0, d0 = eL.extract_end()
+    assert len(k0) == 0 and len(d0) == 0

@@ -23,6 +23,15 @@ def main():
         else:
             kL, dL = eL.extract(L); kR, dR = eR.extract(R)
         return B.stereo_match(eL, eR, kL, dL, kR, dR, bf, maxD)
+    def frame_one_thread():
+        eL.extract_begin(L); eR.extract_begin(R)
+        kL, dL = eL.extract_end(); kR, dR = eR.extract_end()
+        return B.stereo_match(eL, eR, kL, dL, kR, dR, bf, maxD)
+    for _ in range(20): frame_one_thread()
+    ts = []
+    for _ in range(200):
+        t0 = time.perf_counter(); frame_one_thread(); ts.append(time.perf_counter() - t0)
+    print(f"frame latency (one host thread, both views in flight): median {np.median(ts)*1e3:.3f} ms")
     for mode in (True, False):
         for _ in range(20): frame(mode)
         ts = []
@@ -33,5 +42,15 @@ def main():
     t0 = time.perf_counter()
     for _ in range(200): eL.extract(L)
     print(f"single extract: {(time.perf_counter()-t0)/200*1e3:.3f} ms")
+    # the same pair as ONE submit of the batch API (both views + stereo on one stream, one result round trip)
+    sb = B.StereoBatch(params, 1242, 375, 1)
+    out = sb.alloc_out(1, pinned=True)
+    Ls, Rs = np.stack([L, L])[:1].copy(), np.stack([R, R])[:1].copy()
+    for _ in range(20):
+        sb.submit(Ls, Rs, bf, maxD, out); sb.wait()
+    ts = []
+    for _ in range(200):
+        t0 = time.perf_counter(); sb.submit(Ls, Rs, bf, maxD, out); sb.wait(); ts.append(time.perf_counter() - t0)
+    print(f"pair as a 1-pair batch submit: median {np.median(ts)*1e3:.3f} ms")
 if __name__ == "__main__":
     main()
