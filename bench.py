@@ -651,7 +651,8 @@ def single_pair_latency(cfg, local_rank, reps=30):
         # one host thread keeps both views in flight (pslot_orb_extract_begin / _end), as the drop-in Frame constructor does
         eL.extract_begin(L); eR.extract_begin(R)
         kL, dL = eL.extract_end(); kR, dR = eR.extract_end()
-        B.stereo_match(eL, eR, kL, dL, kR, dR, cfg["bf"], maxD)
+        # ... and ComputeStereoMatches runs on the feature sets where they lie (pslot_stereo_match_resident)
+        B.stereo_match_resident(eL, eR, B.extract_token(eL), B.extract_token(eR), cfg["bf"], maxD)
     for _ in range(5):
         once()
     ts = []

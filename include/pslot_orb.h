@@ -87,6 +87,15 @@ int pslot_orb_extract_color(pslot_orb *ctx, const uint8_t *img, int w, int h, pt
  * extraction per context at a time; the image may be released once _begin returns. */
 int pslot_orb_extract_begin(pslot_orb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch);
 int pslot_orb_extract_end(pslot_orb *ctx, pslot_keypoint *kps, uint8_t *desc32, int cap, int *n);
+/* Identity of the feature set the context's last extraction left on the device (0: none); changes with every
+ * extraction.  pslot_stereo_match_resident = pslot_stereo_match on the two sets as they lie on the device - what
+ * Frame::ComputeStereoMatches does in the Frame constructors, right after the two extractions (reference
+ * src/Frame.cc:161-173): nothing is uploaded.  The caller passes the tokens it took after the extractions;
+ * PSLOT_ERR_STATE when either context has moved on (use pslot_stereo_match with the host arrays then).  *n_l = number of
+ * left keypoints = entries written to u_right / depth (PSLOT_ERR_CAPACITY with *n_l = needed when cap is smaller). */
+uint64_t pslot_orb_extract_token(const pslot_orb *ctx);
+int pslot_stereo_match_resident(pslot_orb *ctx_l, pslot_orb *ctx_r, uint64_t token_l, uint64_t token_r, float bf,
+                                float max_d, float *u_right, float *depth, int cap, int *n_l);
 
 /* Backing store of the public member std::vector<cv::Mat> mvImagePyramid (ORBextractor.h:85,
  * filled by ComputePyramid, ORBextractor.cc:1107-1132).  Copies level `level` of the most recent

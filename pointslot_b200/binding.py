@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "pslot_assign_grid", "pslot_grid_token", "pslot_features_in_area", "pslot_batch_assign_grid",
     "pslot_search_by_projection", "pslot_search_by_projection_obj", "pslot_search_by_projection_last", "pslot_search_by_projection_kf", "pslot_debug_projection_sweeps",
     "pslot_cvorb_create", "pslot_cvorb_destroy", "pslot_cvorb_detect_and_compute", "pslot_cvorb_detect_and_compute_batch", "pslot_cvorb_last_timing", "pslot_cvorb_debug",
-    "pslot_assign_features", "pslot_batch_assign_features", "pslot_orb_extract_begin", "pslot_orb_extract_end",
+    "pslot_assign_features", "pslot_batch_assign_features", "pslot_orb_extract_begin", "pslot_orb_extract_end", "pslot_orb_extract_token", "pslot_stereo_match_resident",
     "pslot_vocab_create", "pslot_vocab_destroy", "pslot_bow_transform", "pslot_bow_vectors",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
 ]
@@ -134,6 +134,9 @@ def lib():
     L.pslot_cvorb_last_timing.argtypes = [vp, vp]
     L.pslot_orb_extract_begin.argtypes = [vp, vp, C.c_int, C.c_int, C.c_ssize_t]
     L.pslot_orb_extract_end.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_int)]
+    L.pslot_orb_extract_token.argtypes = [vp]
+    L.pslot_orb_extract_token.restype = C.c_uint64
+    L.pslot_stereo_match_resident.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_float, C.c_float, vp, vp, C.c_int, C.POINTER(C.c_int)]
     L.pslot_assign_features.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_int, vp, C.c_float, vp, vp, vp, vp]
     L.pslot_batch_assign_features.argtypes = [vp, vp, C.c_ssize_t, C.c_ssize_t, vp, C.c_int, vp, vp, vp]
     L.pslot_cvorb_debug.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -572,6 +575,22 @@ def stereo_match(ext_l: OrbExtractor, ext_r: OrbExtractor, kL, dL, kR, dR, bf: f
             _check(lib().pslot_stereo_debug(ext_l._h, nL, _p(bd), _p(bi), _p(bs)))
         return ur[:nL], dp[:nL], bd[:nL], bi[:nL], bs[:nL]
     return ur[:nL], dp[:nL]
+
+
+def extract_token(ext: OrbExtractor) -> int:
+    """Identity of the feature set the last extraction left on the device (0: none)."""
+    return int(lib().pslot_orb_extract_token(ext._h))
+
+
+def stereo_match_resident(ext_l: OrbExtractor, ext_r: OrbExtractor, token_l: int, token_r: int, bf: float, max_d: float):
+    """Frame::ComputeStereoMatches on the two feature sets the extractors' last extractions left on the device (nothing is
+    uploaded) -> (mvuRight, mvDepth); PslotError (state) when either extractor has moved on since the tokens were taken."""
+    cap = _check(lib().pslot_orb_max_keypoints(ext_l._h))
+    ur = np.full(max(cap, 1), -1, np.float32); dp = np.full(max(cap, 1), -1, np.float32)
+    n = C.c_int(0)
+    _check(lib().pslot_stereo_match_resident(ext_l._h, ext_r._h, token_l, token_r, C.c_float(bf), C.c_float(max_d), _p(ur), _p(dp),
+                                             cap, C.byref(n)))
+    return ur[:n.value].copy(), dp[:n.value].copy()
 
 
 class StereoBatch:

@@ -47,6 +47,8 @@ void Frame::StereoFrontEnd(const cv::Mat &imLeft, const cv::Mat &imRight, cv::Ma
     mpORBextractorRight->Begin(imRight);
     mpORBextractorLeft->End(mvKeys, mDescriptors);
     mpORBextractorRight->End(mvKeysRight, mDescriptorsRight);
+    mnExtractTokenLeft = pslot_orb_extract_token(mpORBextractorLeft->Handle());
+    mnExtractTokenRight = pslot_orb_extract_token(mpORBextractorRight->Handle());
 
     N = (int)mvKeys.size();
     if (mvKeys.empty()) return;
@@ -325,6 +327,22 @@ void Frame::StereoMatchSets(const std::vector<cv::KeyPoint> &keysL, const cv::Ma
 
 void Frame::ComputeStereoMatches() // (:2142-2316)
 {
+    // In the constructors this runs right after the two extractions: the feature sets are still on the device, untouched
+    // (the tokens taken after End() say so), and need not travel back up.  Any other caller - or a frame whose extractors
+    // have moved on - takes the general form, which uploads mvKeys / mDescriptors as they are now.
+    const int Nl = (int)mvKeys.size();
+    if (Nl > 0 && mnExtractTokenLeft && mnExtractTokenRight) {
+        mvuRight = std::vector<float>(Nl, -1.0f);
+        mvDepth = std::vector<float>(Nl, -1.0f);
+        int n = 0;
+        const int rc = pslot_stereo_match_resident(mpORBextractorLeft->Handle(), mpORBextractorRight->Handle(), mnExtractTokenLeft,
+                                                   mnExtractTokenRight, mbf, mbf / mb, mvuRight.data(), mvDepth.data(), Nl, &n);
+        if (rc == PSLOT_OK && n == Nl) return;
+        if (rc != PSLOT_ERR_STATE && rc != PSLOT_OK) {
+            std::fprintf(stderr, "pslot Frame: pslot_stereo_match_resident failed: %s\n", pslot_last_error());
+            std::abort();
+        }
+    }
     StereoMatchSets(mvKeys, mDescriptors, mvKeysRight, mDescriptorsRight, mvuRight, mvDepth);
 }
 

@@ -184,6 +184,9 @@ public:
     // searched after a newer one was built on the same extractor, behave as in the reference.
     void EnsureDeviceGrid() const;
     mutable unsigned long long mnGridToken = 0;
+    // identities of the feature sets the two extractions of this frame left on the device (pslot_orb_extract_token): while
+    // they are current, ComputeStereoMatches matches them where they are instead of uploading mvKeys / mDescriptors again
+    unsigned long long mnExtractTokenLeft = 0, mnExtractTokenRight = 0;
 
 private:
     // the hot path shared by all six constructors

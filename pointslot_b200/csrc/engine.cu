@@ -410,6 +410,9 @@ struct pslot_orb {
     cudaGraphExec_t extract_graph = nullptr;
     int extract_graph_gen = -1, extract_calls_gen = -1, extract_calls = 0;
     bool extract_pending = false; // pslot_orb_extract_begin ran, pslot_orb_extract_end has not
+    uint64_t extract_token = 0;   // identity of the feature set the last extraction left on the device (0: none)
+    float *h_stereo = nullptr;    // pinned landing zone of pslot_stereo_match_resident (uRight | depth)
+    size_t h_stereo_cap = 0;
     uint8_t *d_cstage = nullptr;      // tightly packed frame (colour, or gray at any pitch-free layout) awaiting conversion / re-pitch
     size_t cstage_bytes = 0;
     // feature grid of the last pslot_assign_grid (kept for pslot_features_in_area)
@@ -436,6 +439,7 @@ struct pslot_orb {
     ~pslot_orb()
     {
         if (extract_graph) cudaGraphExecDestroy(extract_graph);
+        if (h_stereo) cudaFreeHost(h_stereo);
         cudaFree(d_part); cudaFree(d_pmask);
         free_stereo();
         cudaFree(d_gk); cudaFree(d_gidx); cudaFree(d_gcs); cudaFree(d_qcount); cudaFree(d_qout); cudaFree(d_q);
@@ -802,6 +806,7 @@ static int extract_enqueue(pslot_orb *ctx, const uint8_t *img, int w, int h, ptr
 {
     if (!ctx) return fail(PSLOT_ERR_ARG, "ctx is null");
     ctx->extract_pending = false;
+    ctx->extract_token = 0;
     if (!img || w <= 0 || h <= 0) return PSLOT_OK; // ORBextractor.cc:1046-1047: no keypoints
     if (channels != 1 && channels != 3 && channels != 4) return fail(PSLOT_ERR_ARG, "channels must be 1, 3 or 4");
     if (pitch < (ptrdiff_t)w * channels) return fail(PSLOT_ERR_ARG, "pitch < width * channels");
@@ -862,6 +867,8 @@ static int extract_enqueue(pslot_orb *ctx, const uint8_t *img, int w, int h, ptr
     }
     ++ctx->extract_calls;
     ctx->extract_pending = true;
+    static std::atomic<uint64_t> extract_generation{0}; // process-wide: tokens of different contexts never collide
+    ctx->extract_token = ++extract_generation;
     return PSLOT_OK;
 }
 
@@ -995,6 +1002,67 @@ int pslot_stereo_match(pslot_orb *cl, pslot_orb *cr, const pslot_keypoint *kps_l
     CU(cudaMemcpyAsync(depth, cl->d_dp, 4 * (size_t)n_l, cudaMemcpyDeviceToHost, st));
     if (int rc = check_err_flag(L)) return rc; // synchronises the stream
     cl->last_nl = n_l;
+    return PSLOT_OK;
+}
+
+uint64_t pslot_orb_extract_token(const pslot_orb *ctx) { return ctx ? ctx->extract_token : 0; }
+
+int pslot_stereo_match_resident(pslot_orb *cl, pslot_orb *cr, uint64_t token_l, uint64_t token_r, float bf, float max_d,
+                                float *u_right, float *depth, int cap, int *n_l)
+{
+    if (!cl || !cr || !n_l) return fail(PSLOT_ERR_ARG, "null argument");
+    *n_l = 0;
+    if (!token_l || !token_r || token_l != cl->extract_token || token_r != cr->extract_token || cl->extract_pending || cr->extract_pending)
+        return fail(PSLOT_ERR_STATE, "the feature sets on the device are not the ones the caller means (a later extraction ran, or one is pending)");
+    Engine &L = cl->E, &R = cr->E;
+    if (!L.has_pyramid || !R.has_pyramid) return fail(PSLOT_ERR_STATE, "both extractors must have processed an image");
+    if (L.W != R.W || L.H != R.H || L.p.nlevels != R.p.nlevels || L.device != R.device)
+        return fail(PSLOT_ERR_STATE, "left / right extractors differ in geometry or device");
+    if (R.g.kp_cap_total > 16000) return fail(PSLOT_ERR_CAPACITY, "too many right keypoint slots for the stereo matcher");
+    CU(cudaSetDevice(L.device));
+    const int K = L.g.kp_cap_total;
+    if (K > cl->st_cap) { // result arrays (the feature arrays are the extractors' own)
+        cl->free_stereo();
+        const size_t c = (size_t)K + 256;
+        CU(cudaMalloc(&cl->d_kl, sizeof(pslot_keypoint) * c)); CU(cudaMalloc(&cl->d_kr, sizeof(pslot_keypoint) * c));
+        CU(cudaMalloc(&cl->d_dl, 32 * c)); CU(cudaMalloc(&cl->d_dr, 32 * c));
+        CU(cudaMalloc(&cl->d_n, 8));
+        CU(cudaMalloc(&cl->d_ur, 4 * c)); CU(cudaMalloc(&cl->d_dp, 4 * c));
+        CU(cudaMalloc(&cl->d_bd, 4 * c)); CU(cudaMalloc(&cl->d_bi, 4 * c)); CU(cudaMalloc(&cl->d_sd, 4 * c));
+        cl->st_cap = (int)c;
+    }
+    if ((size_t)K > cl->h_stereo_cap) {
+        if (cl->h_stereo) cudaFreeHost(cl->h_stereo);
+        cl->h_stereo = nullptr; cl->h_stereo_cap = 0;
+        CU(cudaHostAlloc((void **)&cl->h_stereo, sizeof(float) * 2 * (size_t)K + 16, cudaHostAllocDefault));
+        cl->h_stereo_cap = (size_t)K;
+    }
+    cudaStream_t st = L.st;
+    StereoArgs a{};
+    a.kps_l = L.d_out_kps; a.kps_r = R.d_out_kps; a.desc_l = L.d_out_desc; a.desc_r = R.d_out_desc;
+    a.n_l = L.d_out_count; a.n_r = R.d_out_count; // one slot each: the counts of the two extractions
+    a.K = K;
+    a.pyr_l = L.pyr; a.pyr_r = R.pyr;
+    a.bf = bf; a.max_d = max_d;
+    a.u_right = cl->d_ur; a.depth = cl->d_dp; a.best_dist = cl->d_bd; a.best_idx = cl->d_bi; a.sad = cl->d_sd;
+    a.err_flag = L.d_err;
+    launch_stereo(L.g, a, 1, R.g.kp_cap_total, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "stereo launch failed: %s", cudaGetErrorString(e));
+    int *hn = reinterpret_cast<int *>(cl->h_stereo + 2 * (size_t)K);
+    CU(cudaMemcpyAsync(hn, L.d_out_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cl->h_stereo, cl->d_ur, 4 * (size_t)K, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cl->h_stereo + K, cl->d_dp, 4 * (size_t)K, cudaMemcpyDeviceToHost, st));
+    if (int rc = check_err_flag(L)) return rc; // synchronises the stream
+    const int n = *hn;
+    *n_l = n;
+    cl->last_nl = n;
+    if (n > cap) return fail(PSLOT_ERR_CAPACITY, "need room for %d results, caller gave %d", n, cap);
+    if (n > 0) {
+        if (!u_right || !depth) return fail(PSLOT_ERR_ARG, "u_right / depth is null");
+        memcpy(u_right, cl->h_stereo, 4 * (size_t)n);
+        memcpy(depth, cl->h_stereo + K, 4 * (size_t)n);
+    }
     return PSLOT_OK;
 }
 

@@ -329,3 +329,29 @@ def test_extract_in_two_halves(oracle_mod):
     eL.extract_begin(np.zeros((0, 0), np.uint8))
     k0, d0 = eL.extract_end()
     assert len(k0) == 0 and len(d0) == 0
+
+
+def test_stereo_match_on_resident_feature_sets(oracle_mod):
+    """pslot_stereo_match_resident: the matcher on the feature sets the two extractions left on the device equals the general
+    form with the same arrays uploaded (and the oracle); stale tokens are refused."""
+    from pointslot_b200 import binding as B
+    from pointslot_b200.synth import synth_pair
+    params = (1500, 1.2, 8, 20, 7)
+    eL, eR = B.OrbExtractor(*params), B.OrbExtractor(*params)
+    oL, oR = oracle_mod.OracleExtractor(*params), oracle_mod.OracleExtractor(*params)
+    bf, maxD = 386.1448, B.max_disparity(386.1448, 718.856)
+    for seed in (11, 12):
+        L, R = synth_pair(1242, 375, seed)
+        eL.extract_begin(L); eR.extract_begin(R)
+        kL, dL = eL.extract_end(); kR, dR = eR.extract_end()
+        tl, tr = B.extract_token(eL), B.extract_token(eR)
+        assert tl and tr and tl != tr
+        ur, dp = B.stereo_match_resident(eL, eR, tl, tr, bf, maxD)
+        ur2, dp2 = B.stereo_match(eL, eR, kL, dL, kR, dR, bf, maxD)
+        assert len(ur) == len(kL) and np.array_equal(ur.view(np.uint32), ur2.view(np.uint32)) and np.array_equal(dp.view(np.uint32), dp2.view(np.uint32))
+        okL, odL = oL.extract(L); okR, odR = oR.extract(R)
+        our, odp = oracle_mod.stereo_match(oL, oR, okL, odL, okR, odR, bf, maxD)
+        assert np.array_equal(ur >= 0, our >= 0) and np.all(np.abs(ur - our) <= 1e-3) and (ur >= 0).sum() > 50
+    eR.extract(R)  # the right extractor moves on: the old token no longer names what is on the device
+    with pytest.raises(B.PslotError):
+        B.stereo_match_resident(eL, eR, tl, tr, bf, maxD)

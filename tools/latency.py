@@ -32,6 +32,15 @@ def main():
     for _ in range(200):
         t0 = time.perf_counter(); frame_one_thread(); ts.append(time.perf_counter() - t0)
     print(f"frame latency (one host thread, both views in flight): median {np.median(ts)*1e3:.3f} ms")
+    def frame_resident():
+        eL.extract_begin(L); eR.extract_begin(R)
+        kL, dL = eL.extract_end(); kR, dR = eR.extract_end()
+        return B.stereo_match_resident(eL, eR, B.extract_token(eL), B.extract_token(eR), bf, maxD)
+    for _ in range(20): frame_resident()
+    ts = []
+    for _ in range(200):
+        t0 = time.perf_counter(); frame_resident(); ts.append(time.perf_counter() - t0)
+    print(f"frame latency (one host thread, stereo on the resident feature sets): median {np.median(ts)*1e3:.3f} ms")
     for mode in (True, False):
         for _ in range(20): frame(mode)
         ts = []
