@@ -680,7 +680,7 @@ def object_frame_latency(cfg, local_rank, reps=30):
         eL.extract_begin(L); eR.extract_begin(R)  # in flight while this thread runs the (synchronous) cv::ORB pair
         (okL, odL), (okR, odR) = orb.detect_and_compute_batch([L, R], [mask, mask])
         kL, dL = eL.extract_end(); kR, dR = eR.extract_end()
-        B.stereo_match(eL, eR, kL, dL, kR, dR, cfg["bf"], maxD)
+        B.stereo_match_resident(eL, eR, B.extract_token(eL), B.extract_token(eR), cfg["bf"], maxD)
         B.stereo_match(eL, eR, okL, odL, okR, odR, cfg["bf"], maxD)  # ComputeObjStereoMatches: same routine, object keypoints
         return len(kL), len(okL)
     for _ in range(5):

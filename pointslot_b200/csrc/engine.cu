@@ -1307,6 +1307,7 @@ int pslot_cvorb_detect_and_compute_batch(pslot_cvorb *ctx, int n_images, const u
             if (ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
             if (graph) cudaGraphDestroy(graph);
             if (ce != cudaSuccess) return fail(PSLOT_ERR_CUDA, "cv::ORB graph: %s", cudaGetErrorString(ce));
+            if (C.graphs.size() >= 16) C.drop_graphs(); // a caller that keeps changing the batch size: do not hoard executables
             it = C.graphs.emplace(key, exec).first;
         }
         CU(cudaGraphLaunch(it->second, C.st));
