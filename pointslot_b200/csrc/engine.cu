@@ -413,6 +413,8 @@ struct pslot_orb {
     uint64_t extract_token = 0;   // identity of the feature set the last extraction left on the device (0: none)
     float *h_stereo = nullptr;    // pinned landing zone of pslot_stereo_match_resident (uRight | depth)
     size_t h_stereo_cap = 0;
+    unsigned char *h_match = nullptr, *d_match = nullptr; // pslot_stereo_match: counts | kpsL | kpsR | descL | descR (+ results on the host side)
+    size_t h_match_cap = 0;
     uint8_t *d_cstage = nullptr;      // tightly packed frame (colour, or gray at any pitch-free layout) awaiting conversion / re-pitch
     size_t cstage_bytes = 0;
     // feature grid of the last pslot_assign_grid (kept for pslot_features_in_area)
@@ -440,6 +442,8 @@ struct pslot_orb {
     {
         if (extract_graph) cudaGraphExecDestroy(extract_graph);
         if (h_stereo) cudaFreeHost(h_stereo);
+        if (h_match) cudaFreeHost(h_match);
+        cudaFree(d_match);
         cudaFree(d_part); cudaFree(d_pmask);
         free_stereo();
         cudaFree(d_gk); cudaFree(d_gidx); cudaFree(d_gcs); cudaFree(d_qcount); cudaFree(d_qout); cudaFree(d_q);
@@ -979,17 +983,34 @@ int pslot_stereo_match(pslot_orb *cl, pslot_orb *cr, const pslot_keypoint *kps_l
     }
     cudaStream_t st = L.st;
     CU(cudaStreamSynchronize(R.st)); // the right pyramid must be complete (extract is synchronous anyway)
-    const int counts[2] = {n_l, n_r};
-    CU(cudaMemcpyAsync(cl->d_n, counts, 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(cl->d_kl, kps_l, sizeof(pslot_keypoint) * (size_t)n_l, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(cl->d_dl, desc_l, 32 * (size_t)n_l, cudaMemcpyHostToDevice, st));
-    if (n_r) {
-        CU(cudaMemcpyAsync(cl->d_kr, kps_r, sizeof(pslot_keypoint) * (size_t)n_r, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(cl->d_dr, desc_r, 32 * (size_t)n_r, cudaMemcpyHostToDevice, st));
+    // The four feature arrays and the counts gather in one page-locked block and travel as ONE copy (five copies from
+    // pageable memory block the host once each), and the two result arrays come back the same way.
+    const size_t cap = (size_t)cl->st_cap;
+    const size_t o_kl = 256, o_kr = align_up(o_kl + sizeof(pslot_keypoint) * cap, 256), o_dl = align_up(o_kr + sizeof(pslot_keypoint) * cap, 256),
+                 o_dr = align_up(o_dl + 32 * cap, 256), in_bytes = align_up(o_dr + 32 * cap, 256), out_bytes = 8 * cap;
+    if (cl->h_match_cap != cap) {
+        if (cl->h_match) cudaFreeHost(cl->h_match);
+        cudaFree(cl->d_match);
+        cl->h_match = nullptr; cl->d_match = nullptr; cl->h_match_cap = 0;
+        CU(cudaHostAlloc((void **)&cl->h_match, in_bytes + out_bytes, cudaHostAllocDefault));
+        CU(cudaMalloc(&cl->d_match, in_bytes));
+        cl->h_match_cap = cap;
     }
+    unsigned char *hm = cl->h_match, *dm = cl->d_match;
+    const int counts[2] = {n_l, n_r};
+    memcpy(hm, counts, 8);
+    memcpy(hm + o_kl, kps_l, sizeof(pslot_keypoint) * (size_t)n_l);
+    memcpy(hm + o_dl, desc_l, 32 * (size_t)n_l);
+    if (n_r) {
+        memcpy(hm + o_kr, kps_r, sizeof(pslot_keypoint) * (size_t)n_r);
+        memcpy(hm + o_dr, desc_r, 32 * (size_t)n_r);
+    }
+    // (one copy up to the end of what is used: the right descriptors are the last block)
+    CU(cudaMemcpyAsync(dm, hm, n_r ? o_dr + 32 * (size_t)n_r : o_dl + 32 * (size_t)n_l, cudaMemcpyHostToDevice, st));
     StereoArgs a{};
-    a.kps_l = cl->d_kl; a.kps_r = cl->d_kr; a.desc_l = cl->d_dl; a.desc_r = cl->d_dr;
-    a.n_l = cl->d_n; a.n_r = cl->d_n + 1;
+    a.kps_l = reinterpret_cast<const pslot_keypoint *>(dm + o_kl); a.kps_r = reinterpret_cast<const pslot_keypoint *>(dm + o_kr);
+    a.desc_l = dm + o_dl; a.desc_r = dm + o_dr;
+    a.n_l = reinterpret_cast<const int *>(dm); a.n_r = reinterpret_cast<const int *>(dm) + 1;
     a.K = need; // one pair: the row stride is never used, and the grid (sized from K) covers exactly the left set
     a.pyr_l = L.pyr; a.pyr_r = R.pyr;
     a.bf = bf; a.max_d = max_d;
@@ -998,9 +1019,12 @@ int pslot_stereo_match(pslot_orb *cl, pslot_orb *cr, const pslot_keypoint *kps_l
     launch_stereo(L.g, a, 1, std::max(n_r, 1), st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "stereo launch failed: %s", cudaGetErrorString(e));
-    CU(cudaMemcpyAsync(u_right, cl->d_ur, 4 * (size_t)n_l, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(depth, cl->d_dp, 4 * (size_t)n_l, cudaMemcpyDeviceToHost, st));
+    float *ho = reinterpret_cast<float *>(hm + in_bytes);
+    CU(cudaMemcpyAsync(ho, cl->d_ur, 4 * (size_t)n_l, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ho + cap, cl->d_dp, 4 * (size_t)n_l, cudaMemcpyDeviceToHost, st));
     if (int rc = check_err_flag(L)) return rc; // synchronises the stream
+    memcpy(u_right, ho, 4 * (size_t)n_l);
+    memcpy(depth, ho + cap, 4 * (size_t)n_l);
     cl->last_nl = n_l;
     return PSLOT_OK;
 }
