@@ -90,3 +90,42 @@ def test_stereo_matches_oracle(seed, shift, nfeatures, maxd):
     assert np.array_equal(ur >= 0, our >= 0) and np.all(np.abs(ur - our) <= 1e-3)
     assert ur.tobytes() == our.tobytes() and dp.tobytes() == odp.tobytes()  # in practice bit-equal
     eL.close(); eR.close()
+
+
+def test_cross_device_determinism(oracle_mod):
+    """the same pairs give the same bytes on every GPU of the box (bench.py checks it across ranks; this is the
+    in-process form).  Skips on a single-GPU box."""
+    import hashlib
+    from pointslot_b200 import binding as B
+    from pointslot_b200.synth import synth_pair
+    ndev = B.device_count()
+    if ndev < 2:
+        pytest.skip("needs at least two CUDA devices")
+    W, H, P = 640, 360, 6
+    params = (800, 1.2, 8, 20, 7)
+    pairs = [synth_pair(W, H, 90 + s) for s in range(P)]
+    Ls = np.stack([p[0] for p in pairs]); Rs = np.stack([p[1] for p in pairs])
+    digests = []
+    for dev in range(ndev):
+        sb = B.StereoBatch(params, W, H, P, device=dev)
+        res = sb.run(Ls, Rs, 200.0, B.max_disparity(200.0, 500.0))
+        h = hashlib.sha256()
+        for r in res:
+            for key in ("kL", "dL", "kR", "dR", "u_right", "depth"):
+                h.update(np.ascontiguousarray(r[key]).tobytes())
+        digests.append(h.hexdigest())
+        if dev == 0:
+            o = oracle_mod.OracleExtractor(*params)
+            ok, od = o.extract(Ls[0])
+            assert res[0]["kL"].tobytes() == ok.tobytes() and np.array_equal(res[0]["dL"], od)
+        # the single-frame path and the cv::ORB row on that device as well
+        e = B.OrbExtractor(*params, device=dev)
+        k, d = e.extract(Ls[1])
+        assert k.tobytes() == res[1]["kL"].tobytes() and np.array_equal(d, res[1]["dL"])
+        c = B.CvOrb(500, 1.2, 8, 19, device=dev)
+        ck, cd = c.detect_and_compute(Ls[2])
+        if dev == 0:
+            first_cv = (ck.tobytes(), cd.tobytes())
+        else:
+            assert (ck.tobytes(), cd.tobytes()) == first_cv
+    assert len(set(digests)) == 1, digests
