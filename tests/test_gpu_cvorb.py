@@ -148,6 +148,42 @@ def test_cvorb_batch_equals_cv2_orb(B):
         _assert_equal(*out[i], *_cv2_sorted(noise[i], None), f"noise batch, image {i}")
 
 
+def test_cvorb_large_batches_equal_single_calls(B):
+    """Batches of 16 images and more travel in chunks (uploads run ahead on a second stream; four chunks from pageable
+    memory, two from page-locked memory): every image's result must equal the single-image call's, which the tests above
+    tie to cv2.ORB_create.  KITTI-sized frames, masks on some images only."""
+    from pointslot_b200.synth import synth_pair
+    H, W = 375, 1242
+    base = []
+    for seed in (51, 52, 53, 54):
+        base.extend(synth_pair(W, H, seed))
+    mask = _object_mask(H, W)
+    orb = B.CvOrb(1000, 1.2, 8, 19)
+    single = {}
+    for i, img in enumerate(base):
+        for m in (None, mask):
+            single[(i, m is not None)] = orb.detect_and_compute(img, m)
+    for n in (16, 37, 64):
+        imgs = [base[i % 8] for i in range(n)]
+        masks = [mask if (i * 7) % 3 == 0 else None for i in range(n)]
+        for ms in (None, masks):
+            out = orb.detect_and_compute_batch(imgs, ms)
+            assert len(out) == n
+            for i, (k, d) in enumerate(out):
+                sk, sd = single[(i % 8, ms is not None and ms[i] is not None)]
+                assert k.tobytes() == sk.tobytes() and np.array_equal(d, sd), f"batch of {n}, image {i}"
+    # page-locked input: two chunks from 32 images on
+    pin = B.PinnedBuffer((40, H, W))
+    for i in range(40):
+        pin.array[i] = base[i % 8]
+    out = orb.detect_and_compute_batch([pin.array[i] for i in range(40)])
+    for i, (k, d) in enumerate(out):
+        sk, sd = single[(i % 8, False)]
+        assert k.tobytes() == sk.tobytes() and np.array_equal(d, sd), f"pinned batch, image {i}"
+    del out
+    pin.close()
+
+
 def test_cvorb_full_hd_pair(B):
     """BASELINE.json's largest shape (1920x1080, 4000 features) as a left + right batch with object masks."""
     from pointslot_b200.synth import synth_pair
