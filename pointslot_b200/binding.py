@@ -359,14 +359,23 @@ def _cvorb_batch(self, imgs, masks=None):
     n = len(imgs)
     if n == 0:
         return []
-    ims = [np.ascontiguousarray(i, np.uint8) for i in imgs]
+    def rows(a):  # a view with contiguous rows travels as it is (its pitch is passed on), anything else is copied
+        a = np.asarray(a)
+        return a if a.dtype == np.uint8 and a.ndim == 2 and a.strides[1] == 1 and a.strides[0] >= a.shape[1] else np.ascontiguousarray(a, np.uint8)
+    ims = [rows(i) for i in imgs]
     H, W = ims[0].shape
     assert all(i.shape == (H, W) for i in ims)
+    if len({i.strides[0] for i in ims}) > 1:
+        ims = [np.ascontiguousarray(i) for i in ims]
+    pitch = ims[0].strides[0]
     ptrs = (C.c_void_p * n)(*[i.ctypes.data for i in ims])
-    ms, mptrs = None, None
+    ms, mptrs, mpitch = None, None, W
     if masks is not None and any(m is not None for m in masks):
-        ms = [None if m is None else np.ascontiguousarray(m, np.uint8) for m in masks]
+        ms = [None if m is None else rows(m) for m in masks]
         assert len(ms) == n and all(m is None or m.shape == (H, W) for m in ms)
+        if len({m.strides[0] for m in ms if m is not None}) > 1:
+            ms = [None if m is None else np.ascontiguousarray(m) for m in ms]
+        mpitch = next(m.strides[0] for m in ms if m is not None)
         mptrs = (C.c_void_p * n)(*[None if m is None else m.ctypes.data for m in ms])
     cap = self.cap
     while True:
@@ -377,7 +386,7 @@ def _cvorb_batch(self, imgs, masks=None):
             self._batch_out = buf
         kps, desc = buf
         counts = np.zeros(n, np.int32)
-        rc = lib().pslot_cvorb_detect_and_compute_batch(self._h, n, ptrs, W, H, W, mptrs, W, _p(kps), _p(desc), cap, _p(counts))
+        rc = lib().pslot_cvorb_detect_and_compute_batch(self._h, n, ptrs, W, H, pitch, mptrs, mpitch, _p(kps), _p(desc), cap, _p(counts))
         if rc == -2 and counts.max() > cap:
             cap = int(counts.max())
             continue

@@ -172,6 +172,16 @@ def test_cvorb_large_batches_equal_single_calls(B):
             for i, (k, d) in enumerate(out):
                 sk, sd = single[(i % 8, ms is not None and ms[i] is not None)]
                 assert k.tobytes() == sk.tobytes() and np.array_equal(d, sd), f"batch of {n}, image {i}"
+    # views with a row pitch (cv::Mat ROIs): the 2-D upload path, un-chunked and chunked
+    wide = np.zeros((20, H, 1280), np.uint8); wmask = np.zeros((H, 1300), np.uint8)
+    for i in range(20):
+        wide[i, :, :W] = base[i % 8]
+    wmask[:, :W] = mask
+    for n in (3, 20):
+        out = orb.detect_and_compute_batch([wide[i, :, :W] for i in range(n)], [wmask[:, :W] if i % 2 else None for i in range(n)])
+        for i, (k, d) in enumerate(out):
+            sk, sd = single[(i % 8, i % 2 == 1)]
+            assert k.tobytes() == sk.tobytes() and np.array_equal(d, sd), f"pitched batch of {n}, image {i}"
     # page-locked input: two chunks from 32 images on
     pin = B.PinnedBuffer((40, H, W))
     for i in range(40):
