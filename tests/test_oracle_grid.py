@@ -105,3 +105,36 @@ def test_features_in_area_matches_literal(oracle_mod):
         lv = [(-1, -1), (0, -1), (2, -1), (-1, 3), (1, 4), (5, 2)][int(rng.integers(0, 6))]
         got = oracle_mod.features_in_area(k, cs, idx, 0.0, 0.0, inv_w, inv_h, COLS, ROWS, x, y, r, *lv)
         assert list(got) == literal_area(k, grid, 0.0, 0.0, inv_w, inv_h, x, y, r, *lv)
+
+
+def test_assign_features_against_a_numpy_model(oracle_mod):
+    """orc_assign_features (Frame::AssignFeatures, Frame.cc:759-977) against a few lines of numpy on random label images:
+    label 0 -> background, 255 -> dropped, L -> first detection j with (id_j > 255 ? id_j - 255 : id_j) == L - 1; every class in
+    ascending feature order.  (tests/test_oracle_reference.py pins the same routine to the reference's own function.)"""
+    rng = np.random.default_rng(17)
+    for trial in range(20):
+        H, W = int(rng.integers(40, 200)), int(rng.integers(40, 300))
+        n, J = int(rng.integers(0, 600)), int(rng.integers(0, 60))
+        mask = rng.choice(np.array([0, 0, 0, 255, 1, 2, 3, 7, 100, 254], np.uint8), size=(H, W))
+        k = np.zeros(n, oracle_mod.KEYPOINT_DTYPE)
+        k["x"] = rng.uniform(0, W - 0.001, n).astype(np.float32); k["y"] = rng.uniform(0, H - 0.001, n).astype(np.float32)
+        ids = rng.choice(np.array([-1, 0, 1, 2, 6, 99, 253, 255 + 2, 255 + 6, 400], np.int32), size=J)
+        depth = rng.uniform(-5, 100, n).astype(np.float32)
+        cls, groups, eff = oracle_mod.assign_features(k, mask, ids, depth=depth, depth_limit=50.0)
+        lab = mask[k["y"].astype(np.int32), k["x"].astype(np.int32)].astype(np.int32) if n else np.zeros(0, np.int32)
+        eff_id = np.where(ids > 255, ids - 255, ids)
+        want = np.full(n, -1, np.int32)
+        for i in range(n):
+            if lab[i] == 0:
+                want[i] = 0
+            elif lab[i] != 255:
+                hit = np.nonzero((ids >= 0) & (eff_id == lab[i] - 1))[0]
+                if len(hit):
+                    want[i] = 1 + hit[0]
+        assert np.array_equal(cls, want)
+        assert len(groups) == J + 1
+        for c in range(J + 1):
+            assert np.array_equal(groups[c], np.nonzero(want == c)[0])
+        for j in range(J):
+            sel = want == 1 + j
+            assert eff[j] == int(((depth[sel] > 0) & (depth[sel] < 50.0)).sum())
