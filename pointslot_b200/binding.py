@@ -353,9 +353,10 @@ class CvOrb:
             return kps[:n.value].copy(), desc[:n.value].copy()
 
 
-def _cvorb_batch(self, imgs, masks=None):
+def _cvorb_batch(self, imgs, masks=None, copy=True):
     """pslot_cvorb_detect_and_compute_batch: `imgs` = equally sized u8 images (e.g. the left and right view), `masks` = None
-    or one entry (array or None) per image -> [(keypoints, descriptors)] per image, each exactly the single-image result."""
+    or one entry (array or None) per image -> [(keypoints, descriptors)] per image, each exactly the single-image result.
+    copy=False returns views into the context's result arrays, valid until the next call (no per-image copies)."""
     n = len(imgs)
     if n == 0:
         return []
@@ -391,6 +392,8 @@ def _cvorb_batch(self, imgs, masks=None):
             cap = int(counts.max())
             continue
         _check(rc)
+        if not copy:
+            return [(kps[s, :counts[s]], desc[s, :counts[s]]) for s in range(n)]
         return [(kps[s, :counts[s]].copy(), desc[s, :counts[s]].copy()) for s in range(n)]
 
 
