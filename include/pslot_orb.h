@@ -337,6 +337,14 @@ int pslot_cvorb_detect_and_compute(pslot_cvorb *ctx, const uint8_t *img, int w, 
 int pslot_cvorb_detect_and_compute_batch(pslot_cvorb *ctx, int n_images, const uint8_t *const *imgs, int w, int h,
                                          ptrdiff_t pitch, const uint8_t *const *masks, ptrdiff_t mask_pitch,
                                          pslot_keypoint *kps, uint8_t *desc32, int cap, int *counts);
+/* The same on images that are ALREADY on the device: images first_image .. first_image + n_images - 1 of the last
+ * pslot_batch_submit on `b` (0 .. npairs-1 = the left views, npairs .. 2*npairs-1 = the right views), read from level 0
+ * of the batch's pyramids - in object mode (Frame.cc:706-713) both extractors look at the same two images, so they need
+ * not cross PCIe twice; only the masks (at most) are uploaded.  Call after pslot_batch_wait and before the next submit
+ * on `b`.  Results as pslot_cvorb_detect_and_compute_batch. */
+int pslot_cvorb_detect_and_compute_resident(pslot_cvorb *ctx, pslot_batch *b, int first_image, int n_images,
+                                            const uint8_t *const *masks, ptrdiff_t mask_pitch, pslot_keypoint *kps,
+                                            uint8_t *desc32, int cap, int *counts);
 
 /* ---------------------------------------------------------------------------------------------
  * Bag of words (second half).

@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats", "pslot_batch_stereo_counters",
     "pslot_assign_grid", "pslot_grid_token", "pslot_features_in_area", "pslot_batch_assign_grid",
     "pslot_search_by_projection", "pslot_search_by_projection_obj", "pslot_search_by_projection_last", "pslot_search_by_projection_kf", "pslot_debug_projection_sweeps",
-    "pslot_cvorb_create", "pslot_cvorb_destroy", "pslot_cvorb_detect_and_compute", "pslot_cvorb_detect_and_compute_batch", "pslot_cvorb_last_timing", "pslot_cvorb_debug",
+    "pslot_cvorb_create", "pslot_cvorb_destroy", "pslot_cvorb_detect_and_compute", "pslot_cvorb_detect_and_compute_batch", "pslot_cvorb_detect_and_compute_resident", "pslot_cvorb_last_timing", "pslot_cvorb_debug",
     "pslot_assign_features", "pslot_batch_assign_features", "pslot_orb_extract_begin", "pslot_orb_extract_end", "pslot_orb_extract_token", "pslot_stereo_match_resident",
     "pslot_vocab_create", "pslot_vocab_destroy", "pslot_bow_transform", "pslot_bow_vectors",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
@@ -131,6 +131,7 @@ def lib():
                                                  C.POINTER(C.c_int)]
     L.pslot_cvorb_detect_and_compute_batch.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_ssize_t, vp, vp,
                                                        C.c_int, vp]
+    L.pslot_cvorb_detect_and_compute_resident.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_ssize_t, vp, vp, C.c_int, vp]
     L.pslot_cvorb_last_timing.argtypes = [vp, vp]
     L.pslot_orb_extract_begin.argtypes = [vp, vp, C.c_int, C.c_int, C.c_ssize_t]
     L.pslot_orb_extract_end.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_int)]
@@ -395,6 +396,38 @@ def _cvorb_batch(self, imgs, masks=None, copy=True):
         if not copy:
             return [(kps[s, :counts[s]], desc[s, :counts[s]]) for s in range(n)]
         return [(kps[s, :counts[s]].copy(), desc[s, :counts[s]].copy()) for s in range(n)]
+
+
+def _cvorb_resident(self, batch, first_image, n_images, masks=None, copy=True):
+    """pslot_cvorb_detect_and_compute_resident: cv::ORB on images first_image .. of the last submit of `batch` (a StereoBatch;
+    left views first, then right views), read where they lie on the device; `masks` as in detect_and_compute_batch."""
+    n = n_images
+    H, W = batch.H, batch.W
+    ms, mptrs, mpitch = None, None, W
+    if masks is not None and any(m is not None for m in masks):
+        ms = [None if m is None else np.ascontiguousarray(m, np.uint8) for m in masks]
+        assert len(ms) == n and all(m is None or m.shape == (H, W) for m in ms)
+        mptrs = (C.c_void_p * n)(*[None if m is None else m.ctypes.data for m in ms])
+    cap = self.cap
+    while True:
+        buf = getattr(self, "_batch_out", None)
+        if buf is None or buf[0].shape[0] < n or buf[0].shape[1] != cap:
+            buf = (np.zeros((n, cap), KEYPOINT_DTYPE), np.zeros((n, cap, 32), np.uint8))
+            self._batch_out = buf
+        kps, desc = buf
+        counts = np.zeros(max(n, 1), np.int32)
+        rc = lib().pslot_cvorb_detect_and_compute_resident(self._h, batch._h, first_image, n, mptrs, mpitch, _p(kps), _p(desc), cap,
+                                                           _p(counts))
+        if rc == -2 and counts.max() > cap:
+            cap = int(counts.max())
+            continue
+        _check(rc)
+        if not copy:
+            return [(kps[s, :counts[s]], desc[s, :counts[s]]) for s in range(n)]
+        return [(kps[s, :counts[s]].copy(), desc[s, :counts[s]].copy()) for s in range(n)]
+
+
+CvOrb.detect_and_compute_resident = _cvorb_resident
 
 
 def _cvorb_timing(self):

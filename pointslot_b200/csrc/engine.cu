@@ -1211,22 +1211,25 @@ void pslot_cvorb_destroy(pslot_cvorb *ctx)
     delete ctx;
 }
 
-int pslot_cvorb_detect_and_compute_batch(pslot_cvorb *ctx, int n_images, const uint8_t *const *imgs, int w, int h, ptrdiff_t pitch,
-                                         const uint8_t *const *masks, ptrdiff_t mask_pitch, pslot_keypoint *kps, uint8_t *desc32,
-                                         int cap, int *counts)
+// The images come from the host (imgs) or - dev_src != NULL - are already on the device as padded level-0 images with the
+// extractor's row pitch (align_up(w, 128), the same as here), dev_stride bytes apart.
+static int cvorb_batch_impl(pslot_cvorb *ctx, int n_images, const uint8_t *const *imgs, const uint8_t *dev_src, size_t dev_stride,
+                            int w, int h, ptrdiff_t pitch, const uint8_t *const *masks, ptrdiff_t mask_pitch, pslot_keypoint *kps,
+                            uint8_t *desc32, int cap, int *counts)
 {
     if (!ctx || !counts) return fail(PSLOT_ERR_ARG, "ctx / counts is null");
     if (n_images < 0 || n_images > 1024) return fail(PSLOT_ERR_ARG, "n_images must be in [0,1024]");
     if (cap < 0) return fail(PSLOT_ERR_ARG, "cap < 0");
     for (int s = 0; s < n_images; ++s) counts[s] = 0;
     if (n_images == 0 || w <= 0 || h <= 0) return PSLOT_OK; // empty image: no keypoints (orb.cpp: CV_Assert only on type)
-    if (!imgs) return fail(PSLOT_ERR_ARG, "imgs is null");
+    const bool img_dev = dev_src != nullptr;
+    if (!img_dev && !imgs) return fail(PSLOT_ERR_ARG, "imgs is null");
     bool any_mask = false;
     for (int s = 0; s < n_images; ++s) {
-        if (!imgs[s]) return fail(PSLOT_ERR_ARG, "image %d is null", s);
+        if (!img_dev && !imgs[s]) return fail(PSLOT_ERR_ARG, "image %d is null", s);
         any_mask |= masks && masks[s];
     }
-    if (pitch < w || (any_mask && mask_pitch < w)) return fail(PSLOT_ERR_ARG, "pitch < width");
+    if ((!img_dev && pitch < w) || (any_mask && mask_pitch < w)) return fail(PSLOT_ERR_ARG, "pitch < width");
     pslot_cvorb &C = *ctx;
     CU(cudaSetDevice(C.device));
     if (w < 2 * C.edge + 1 || h < 2 * C.edge + 1) return PSLOT_OK; // nothing passes runByImageBorder: cv::ORB returns no keypoints
@@ -1237,14 +1240,16 @@ int pslot_cvorb_detect_and_compute_batch(pslot_cvorb *ctx, int n_images, const u
     // Page-locked images arrive at link speed (0.55 ms per 64 KITTI frames): two chunks hide half of that at little cost in
     // smaller launches; pageable images are staged by the driver at a fifth of the rate: four chunks.
     int nchunks = 1;
-    if (n_images >= 16) {
+    if (img_dev) {
+        nchunks = any_mask && n_images >= 32 ? 2 : 1; // only the masks travel
+    } else if (n_images >= 16) {
         cudaPointerAttributes pa{};
         const bool pinned = cudaPointerGetAttributes(&pa, imgs[0]) == cudaSuccess && pa.type == cudaMemoryTypeHost;
         cudaGetLastError(); // an unregistered pointer is not an error here
         nchunks = pinned ? (n_images >= 32 ? 2 : 1) : 4;
     }
     const int chunk = (n_images + nchunks - 1) / nchunks;
-    const bool tight = pitch == w && (!any_mask || mask_pitch == w);
+    const bool tight = (img_dev || pitch == w) && (!any_mask || mask_pitch == w);
     const size_t img_bytes = (size_t)w * h;
     // one round trip: the counts and the (almost always sufficient) first `guess` records of every image travel together
     // into pinned memory
@@ -1263,7 +1268,7 @@ int pslot_cvorb_detect_and_compute_batch(pslot_cvorb *ctx, int n_images, const u
     const int *hc = reinterpret_cast<const int *>(C.h_out);
     auto device_work = [&](int c0, int c1) { // re-pitch + the kernels of slots [c0, c1) on the main stream
         if (tight)
-            for (int view = 0; view < (any_mask ? 2 : 1); ++view)
+            for (int view = img_dev ? 1 : 0; view < (any_mask ? 2 : 1); ++view)
                 launch_gray_ingest(C.d_stage + view * C.stage_view + c0 * img_bytes, img_bytes, 1, 0,
                                    (view ? C.b.mask : C.b.pyr) + c0 * (size_t)C.g.slot_bytes + L0.off, w, h, L0.pitch, C.g.slot_bytes,
                                    c1 - c0, C.st);
@@ -1281,7 +1286,10 @@ int pslot_cvorb_detect_and_compute_batch(pslot_cvorb *ctx, int n_images, const u
     for (int c0 = 0, ci = 0; c0 < n_images; c0 += chunk, ++ci) {
         const int c1 = std::min(c0 + chunk, n_images);
         const auto u0 = std::chrono::steady_clock::now();
-        for (int view = 0; view < (any_mask ? 2 : 1); ++view) {
+        if (img_dev) // level-0 images as they lie in the extractor's pyramid: one device-to-device copy, image = "row"
+            CU(cudaMemcpy2DAsync(C.b.pyr + c0 * (size_t)C.g.slot_bytes + L0.off, (size_t)C.g.slot_bytes, dev_src + c0 * dev_stride, dev_stride,
+                                 (size_t)L0.pitch * h, (size_t)(c1 - c0), cudaMemcpyDeviceToDevice, C.st_up));
+        for (int view = img_dev ? 1 : 0; view < (any_mask ? 2 : 1); ++view) {
             const uint8_t *const *src = view ? masks : imgs;
             if (tight) {
                 // tightly packed rows: linear copies at the full PCIe rate into a staging buffer (images that follow each other
@@ -1318,7 +1326,7 @@ int pslot_cvorb_detect_and_compute_batch(pslot_cvorb *ctx, int n_images, const u
     if (nchunks > 1) {
         if (int rc = downloads()) return rc;
     } else {
-        const int key = n_images * 4 + (any_mask ? 2 : 0) + (tight ? 1 : 0);
+        const int key = n_images * 8 + (img_dev ? 4 : 0) + (any_mask ? 2 : 0) + (tight ? 1 : 0);
         auto it = C.graphs.find(key);
         if (it == C.graphs.end()) {
             cudaGraph_t graph = nullptr;
@@ -1376,6 +1384,30 @@ int pslot_cvorb_last_timing(const pslot_cvorb *ctx, double out_ms[4])
     if (!ctx || !out_ms) return fail(PSLOT_ERR_ARG, "null argument");
     for (int i = 0; i < 4; ++i) out_ms[i] = ctx->t_phase[i];
     return PSLOT_OK;
+}
+
+int pslot_cvorb_detect_and_compute_batch(pslot_cvorb *ctx, int n_images, const uint8_t *const *imgs, int w, int h, ptrdiff_t pitch,
+                                         const uint8_t *const *masks, ptrdiff_t mask_pitch, pslot_keypoint *kps, uint8_t *desc32,
+                                         int cap, int *counts)
+{
+    return cvorb_batch_impl(ctx, n_images, imgs, nullptr, 0, w, h, pitch, masks, mask_pitch, kps, desc32, cap, counts);
+}
+
+int pslot_cvorb_detect_and_compute_resident(pslot_cvorb *ctx, pslot_batch *b, int first_image, int n_images,
+                                            const uint8_t *const *masks, ptrdiff_t mask_pitch, pslot_keypoint *kps,
+                                            uint8_t *desc32, int cap, int *counts)
+{
+    if (!ctx || !b) return fail(PSLOT_ERR_ARG, "ctx / b is null");
+    if (b->last_pairs <= 0) return fail(PSLOT_ERR_STATE, "no batch has been submitted");
+    if (first_image < 0 || n_images < 0 || first_image + n_images > 2 * b->last_pairs)
+        return fail(PSLOT_ERR_ARG, "images [%d, %d) are not among the %d images of the last submit", first_image, first_image + n_images,
+                    2 * b->last_pairs);
+    Engine &E = b->E;
+    if (E.device != ctx->device) return fail(PSLOT_ERR_STATE, "the batch lives on another device");
+    CU(cudaSetDevice(E.device));
+    CU(cudaStreamSynchronize(E.st)); // the pyramids of the last submit are complete (a no-op after pslot_batch_wait)
+    return cvorb_batch_impl(ctx, n_images, nullptr, E.pyr.lv[0] + (size_t)first_image * E.pyr.slot_stride[0], (size_t)E.pyr.slot_stride[0],
+                            E.W, E.H, E.W, masks, mask_pitch, kps, desc32, cap, counts);
 }
 
 int pslot_cvorb_detect_and_compute(pslot_cvorb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, const uint8_t *mask,

@@ -194,6 +194,39 @@ def test_cvorb_large_batches_equal_single_calls(B):
     pin.close()
 
 
+def test_cvorb_on_the_images_of_a_batch(B):
+    """pslot_cvorb_detect_and_compute_resident: cv::ORB on the images a StereoBatch still holds on the device (level 0 of its
+    pyramids) - left views, right views, with masks, a sub-range, 40 images (two chunks) - equals the calls fed from the host."""
+    from pointslot_b200.synth import synth_pair
+    W, H, P = 1242, 375, 20
+    pairs = [synth_pair(W, H, 70 + s) for s in range(4)]
+    Ls = np.stack([pairs[i % 4][0] for i in range(P)]); Rs = np.stack([pairs[i % 4][1] for i in range(P)])
+    sb = B.StereoBatch((1000, 1.2, 8, 20, 7), W, H, P)
+    sb.run(Ls, Rs, 386.1448, B.max_disparity(386.1448, 718.856))
+    mask = _object_mask(H, W)
+    orb = B.CvOrb(1000, 1.2, 8, 19)
+    want = {}
+    for i in range(4):
+        for view, img in enumerate(pairs[i]):
+            for m in (None, mask):
+                want[(i, view, m is not None)] = orb.detect_and_compute(img, m)
+    out = orb.detect_and_compute_resident(sb, 0, 2 * P)                       # all 40 images, no masks
+    for s, (k, d) in enumerate(out):
+        wk, wd = want[(s % P % 4, s // P, False)]
+        assert k.tobytes() == wk.tobytes() and np.array_equal(d, wd), f"image {s}"
+    masks = [mask if s % 3 else None for s in range(2 * P)]
+    out = orb.detect_and_compute_resident(sb, 0, 2 * P, masks)                # masks on two thirds of them
+    for s, (k, d) in enumerate(out):
+        wk, wd = want[(s % P % 4, s // P, masks[s] is not None)]
+        assert k.tobytes() == wk.tobytes() and np.array_equal(d, wd), f"masked image {s}"
+    out = orb.detect_and_compute_resident(sb, P + 3, 2, [mask, mask])         # the right views of pairs 3 and 4
+    for j, (k, d) in enumerate(out):
+        wk, wd = want[((3 + j) % 4, 1, True)]
+        assert k.tobytes() == wk.tobytes() and np.array_equal(d, wd)
+    with pytest.raises(B.PslotError):
+        orb.detect_and_compute_resident(sb, 2 * P - 1, 2)
+
+
 def test_cvorb_full_hd_pair(B):
     """BASELINE.json's largest shape (1920x1080, 4000 features) as a left + right batch with object masks."""
     from pointslot_b200.synth import synth_pair
