@@ -345,6 +345,13 @@ int pslot_cvorb_detect_and_compute_batch(pslot_cvorb *ctx, int n_images, const u
 int pslot_cvorb_detect_and_compute_resident(pslot_cvorb *ctx, pslot_batch *b, int first_image, int n_images,
                                             const uint8_t *const *masks, ptrdiff_t mask_pitch, pslot_keypoint *kps,
                                             uint8_t *desc32, int cap, int *counts);
+/* Frame::ComputeObjStereoMatches (reference src/Frame.cc:2318-2503) for every pair of the batch at once: the stereo
+ * matcher on the cv::ORB features that pslot_cvorb_detect_and_compute_resident(ctx, b, 0, 2 * npairs, ...) just left on
+ * the device (left views = images 0 .. npairs-1, right views = npairs .. 2*npairs-1), reading the pyramids of `b`'s last
+ * submit.  u_right / depth: npairs rows of `cap` floats; row p holds one entry per left cv::ORB keypoint of pair p, in the
+ * order the resident call returned them.  PSLOT_ERR_STATE unless the context holds exactly those features. */
+int pslot_cvorb_stereo_match_resident(pslot_cvorb *ctx, pslot_batch *b, float bf, float max_d, float *u_right, float *depth,
+                                      int cap);
 
 /* ---------------------------------------------------------------------------------------------
  * Bag of words (second half).

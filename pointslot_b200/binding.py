@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "pslot_batch_set_profiling", "pslot_batch_stage_times", "pslot_batch_stats", "pslot_batch_stereo_counters",
     "pslot_assign_grid", "pslot_grid_token", "pslot_features_in_area", "pslot_batch_assign_grid",
     "pslot_search_by_projection", "pslot_search_by_projection_obj", "pslot_search_by_projection_last", "pslot_search_by_projection_kf", "pslot_debug_projection_sweeps",
-    "pslot_cvorb_create", "pslot_cvorb_destroy", "pslot_cvorb_detect_and_compute", "pslot_cvorb_detect_and_compute_batch", "pslot_cvorb_detect_and_compute_resident", "pslot_cvorb_last_timing", "pslot_cvorb_debug",
+    "pslot_cvorb_create", "pslot_cvorb_destroy", "pslot_cvorb_detect_and_compute", "pslot_cvorb_detect_and_compute_batch", "pslot_cvorb_detect_and_compute_resident", "pslot_cvorb_stereo_match_resident", "pslot_cvorb_last_timing", "pslot_cvorb_debug",
     "pslot_assign_features", "pslot_batch_assign_features", "pslot_orb_extract_begin", "pslot_orb_extract_end", "pslot_orb_extract_token", "pslot_stereo_match_resident",
     "pslot_vocab_create", "pslot_vocab_destroy", "pslot_bow_transform", "pslot_bow_vectors",
     "pslot_orb_debug_candidates", "pslot_orb_debug_level_keypoints", "pslot_stereo_debug", "pslot_debug_steer",
@@ -132,6 +132,7 @@ def lib():
     L.pslot_cvorb_detect_and_compute_batch.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_ssize_t, vp, C.c_ssize_t, vp, vp,
                                                        C.c_int, vp]
     L.pslot_cvorb_detect_and_compute_resident.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_ssize_t, vp, vp, C.c_int, vp]
+    L.pslot_cvorb_stereo_match_resident.argtypes = [vp, vp, C.c_float, C.c_float, vp, vp, C.c_int]
     L.pslot_cvorb_last_timing.argtypes = [vp, vp]
     L.pslot_orb_extract_begin.argtypes = [vp, vp, C.c_int, C.c_int, C.c_ssize_t]
     L.pslot_orb_extract_end.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_int)]
@@ -428,6 +429,17 @@ def _cvorb_resident(self, batch, first_image, n_images, masks=None, copy=True):
 
 
 CvOrb.detect_and_compute_resident = _cvorb_resident
+
+
+def _cvorb_stereo_resident(self, batch, npairs, bf, max_d):
+    """pslot_cvorb_stereo_match_resident: ComputeObjStereoMatches for every pair of `batch` on the cv::ORB features the last
+    detect_and_compute_resident(batch, 0, 2 * npairs) left on the device -> (u_right [npairs, cap], depth [npairs, cap])."""
+    ur = np.full((npairs, self.cap), -1, np.float32); dp = np.full((npairs, self.cap), -1, np.float32)
+    _check(lib().pslot_cvorb_stereo_match_resident(self._h, batch._h, C.c_float(bf), C.c_float(max_d), _p(ur), _p(dp), self.cap))
+    return ur, dp
+
+
+CvOrb.stereo_match_resident = _cvorb_stereo_resident
 
 
 def _cvorb_timing(self):

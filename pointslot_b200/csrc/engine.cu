@@ -464,6 +464,7 @@ struct pslot_batch {
     Engine E;
     int max_pairs = 0;
     int last_pairs = 0;
+    unsigned long long submits = 0; // identity of what the pyramids hold
     int launches = 0;
     bool profiling = false, profiled = false;
     cudaEvent_t ev[PSLOT_NUM_STAGES + 1] = {};
@@ -516,6 +517,12 @@ struct pslot_cvorb {
     double t_phase[4] = {0, 0, 0, 0}; // host clock of the last call: uploads enqueued, kernels enqueued, wait, copy-out (ms)
     // the kernels + result downloads of an un-chunked call as one CUDA graph per (images, masks, tight input): ~20 launches
     // become one (the per-frame pair of Frame::ExtractObjORB is latency-bound); dropped whenever a buffer they name moves
+    // what the slots hold after pslot_cvorb_detect_and_compute_resident (for pslot_cvorb_stereo_match_resident)
+    const pslot_batch *res_batch = nullptr;
+    unsigned long long res_submits = 0;
+    int res_first = 0, res_n = 0;
+    unsigned char *d_stereo = nullptr; // uRight | depth | best_dist | best_idx | sad, [pairs][slot_kp] each
+    size_t stereo_bytes = 0;
     std::map<int, cudaGraphExec_t> graphs;
     void drop_graphs()
     {
@@ -538,6 +545,7 @@ struct pslot_cvorb {
         release();
         if (h_err) cudaFreeHost(h_err);
         if (h_out) cudaFreeHost(h_out);
+        cudaFree(d_stereo);
         for (cudaEvent_t e : ev_up)
             if (e) cudaEventDestroy(e);
         if (st_up) cudaStreamDestroy(st_up);
@@ -1223,6 +1231,7 @@ static int cvorb_batch_impl(pslot_cvorb *ctx, int n_images, const uint8_t *const
     for (int s = 0; s < n_images; ++s) counts[s] = 0;
     if (n_images == 0 || w <= 0 || h <= 0) return PSLOT_OK; // empty image: no keypoints (orb.cpp: CV_Assert only on type)
     const bool img_dev = dev_src != nullptr;
+    ctx->res_batch = nullptr; // set again by the resident entry point when this call succeeds
     if (!img_dev && !imgs) return fail(PSLOT_ERR_ARG, "imgs is null");
     bool any_mask = false;
     for (int s = 0; s < n_images; ++s) {
@@ -1406,8 +1415,66 @@ int pslot_cvorb_detect_and_compute_resident(pslot_cvorb *ctx, pslot_batch *b, in
     if (E.device != ctx->device) return fail(PSLOT_ERR_STATE, "the batch lives on another device");
     CU(cudaSetDevice(E.device));
     CU(cudaStreamSynchronize(E.st)); // the pyramids of the last submit are complete (a no-op after pslot_batch_wait)
-    return cvorb_batch_impl(ctx, n_images, nullptr, E.pyr.lv[0] + (size_t)first_image * E.pyr.slot_stride[0], (size_t)E.pyr.slot_stride[0],
-                            E.W, E.H, E.W, masks, mask_pitch, kps, desc32, cap, counts);
+    const int rc = cvorb_batch_impl(ctx, n_images, nullptr, E.pyr.lv[0] + (size_t)first_image * E.pyr.slot_stride[0],
+                                    (size_t)E.pyr.slot_stride[0], E.W, E.H, E.W, masks, mask_pitch, kps, desc32, cap, counts);
+    if (rc == PSLOT_OK || rc == PSLOT_ERR_CAPACITY) { // the device holds the complete result either way
+        ctx->res_batch = b; ctx->res_submits = b->submits; ctx->res_first = first_image; ctx->res_n = n_images;
+    }
+    return rc;
+}
+
+int pslot_cvorb_stereo_match_resident(pslot_cvorb *ctx, pslot_batch *b, float bf, float max_d, float *u_right, float *depth, int cap)
+{
+    if (!ctx || !b || !u_right || !depth) return fail(PSLOT_ERR_ARG, "null argument");
+    pslot_cvorb &C = *ctx;
+    Engine &E = b->E;
+    const int np = b->last_pairs;
+    if (C.res_batch != b || C.res_submits != b->submits || C.res_first != 0 || C.res_n != 2 * np || np <= 0)
+        return fail(PSLOT_ERR_STATE, "the context does not hold the cv::ORB features of all %d images of this batch's last submit", 2 * np);
+    if (C.nlevels > E.p.nlevels) return fail(PSLOT_ERR_ARG, "cv::ORB has more levels (%d) than the batch's pyramids (%d)", C.nlevels, E.p.nlevels);
+    if (cap < 1) return fail(PSLOT_ERR_ARG, "cap < 1");
+    CU(cudaSetDevice(C.device));
+    const int K = C.g.slot_kp;
+    const int *hc = reinterpret_cast<const int *>(C.h_out); // counts of the resident call, still in the staging block
+    int max_l = 0, max_r = 1;
+    for (int p = 0; p < np; ++p) { max_l = std::max(max_l, hc[p]); max_r = std::max(max_r, hc[np + p]); }
+    if (max_r > 16000) return fail(PSLOT_ERR_CAPACITY, "too many right keypoints for the stereo matcher (%d > 16000)", max_r);
+    if (max_l > cap) return fail(PSLOT_ERR_CAPACITY, "need room for %d results per pair, caller gave %d", max_l, cap);
+    const size_t plane = 4 * (size_t)np * K;
+    if (5 * plane > C.stereo_bytes) {
+        CU(cudaStreamSynchronize(C.st));
+        cudaFree(C.d_stereo);
+        C.d_stereo = nullptr; C.stereo_bytes = 0;
+        CU(cudaMalloc(&C.d_stereo, 5 * plane));
+        C.stereo_bytes = 5 * plane;
+    }
+    StereoArgs a{};
+    a.kps_l = C.b.out_kps; a.kps_r = C.b.out_kps + (size_t)np * K;
+    a.desc_l = C.b.out_desc; a.desc_r = C.b.out_desc + (size_t)np * K * 32;
+    a.n_l = C.b.out_count; a.n_r = C.b.out_count + np;
+    a.K = K;
+    a.pyr_l = E.pyr; a.pyr_r = E.pyr; // pair p: slot p of the left views, slot npairs + p of the right views
+    for (int l = 0; l < E.g.nlevels; ++l) a.pyr_r.lv[l] = E.pyr.lv[l] + (size_t)np * E.pyr.slot_stride[l];
+    a.bf = bf; a.max_d = max_d;
+    a.u_right = reinterpret_cast<float *>(C.d_stereo); a.depth = reinterpret_cast<float *>(C.d_stereo + plane);
+    a.best_dist = reinterpret_cast<int *>(C.d_stereo + 2 * plane); a.best_idx = reinterpret_cast<int *>(C.d_stereo + 3 * plane);
+    a.sad = reinterpret_cast<int *>(C.d_stereo + 4 * plane);
+    a.err_flag = C.b.err;
+    a.counters = nullptr;
+    CU(cudaStreamSynchronize(E.st)); // the batch's pyramids are complete and idle
+    launch_stereo(E.g, a, np, (max_r + 63) & ~63, C.st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "stereo launch failed: %s", cudaGetErrorString(e));
+    const size_t wbytes = 4 * (size_t)std::min(cap, K);
+    CU(cudaMemcpy2DAsync(u_right, 4 * (size_t)cap, a.u_right, 4 * (size_t)K, wbytes, (size_t)np, cudaMemcpyDeviceToHost, C.st));
+    CU(cudaMemcpy2DAsync(depth, 4 * (size_t)cap, a.depth, 4 * (size_t)K, wbytes, (size_t)np, cudaMemcpyDeviceToHost, C.st));
+    CU(cudaStreamSynchronize(C.st));
+    if (*(volatile int *)C.h_err) {
+        const int f = *C.h_err;
+        *C.h_err = 0;
+        return fail(PSLOT_ERR_CUDA, "stereo matcher on the cv::ORB features: device error flag 0x%x", f);
+    }
+    return PSLOT_OK;
 }
 
 int pslot_cvorb_detect_and_compute(pslot_cvorb *ctx, const uint8_t *img, int w, int h, ptrdiff_t pitch, const uint8_t *mask,
@@ -1725,6 +1792,7 @@ static int batch_submit_impl(pslot_batch *b, const uint8_t *left, const uint8_t 
     if (e != cudaSuccess) return fail(PSLOT_ERR_CUDA, "stereo launch failed: %s", cudaGetErrorString(e));
     b->launches = rc;
     b->last_pairs = npairs;
+    ++b->submits;
     if (out) {
         const size_t ni = 2 * (size_t)npairs;
         if (out->counts) CU(cudaMemcpyAsync(out->counts, E.d_out_count, 4 * ni, cudaMemcpyDeviceToHost, E.st));

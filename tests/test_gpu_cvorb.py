@@ -214,6 +214,17 @@ def test_cvorb_on_the_images_of_a_batch(B):
     for s, (k, d) in enumerate(out):
         wk, wd = want[(s % P % 4, s // P, False)]
         assert k.tobytes() == wk.tobytes() and np.array_equal(d, wd), f"image {s}"
+    # ComputeObjStereoMatches for all 20 pairs at once on those resident features == the per-pair call with the same arrays
+    bf, maxD = 386.1448, B.max_disparity(386.1448, 718.856)
+    ur, dp = orb.stereo_match_resident(sb, P, bf, maxD)
+    eL, eR = B.OrbExtractor(1000, 1.2, 8, 20, 7), B.OrbExtractor(1000, 1.2, 8, 20, 7)
+    for p_ in (0, 1, 2, 3, 19):
+        eL.extract(Ls[p_]); eR.extract(Rs[p_])
+        (kl, dl), (kr, dr) = out[p_], out[P + p_]
+        wu, wd = B.stereo_match(eL, eR, kl, dl, kr, dr, bf, maxD)
+        n_ = len(kl)
+        assert np.array_equal(ur[p_, :n_].view(np.uint32), wu.view(np.uint32)) and np.array_equal(dp[p_, :n_].view(np.uint32), wd.view(np.uint32)), p_
+        assert (wu >= 0).sum() > 30
     masks = [mask if s % 3 else None for s in range(2 * P)]
     out = orb.detect_and_compute_resident(sb, 0, 2 * P, masks)                # masks on two thirds of them
     for s, (k, d) in enumerate(out):
@@ -223,6 +234,8 @@ def test_cvorb_on_the_images_of_a_batch(B):
     for j, (k, d) in enumerate(out):
         wk, wd = want[((3 + j) % 4, 1, True)]
         assert k.tobytes() == wk.tobytes() and np.array_equal(d, wd)
+    with pytest.raises(B.PslotError):
+        orb.stereo_match_resident(sb, P, bf, maxD)   # the context now holds a sub-range, not the whole batch
     with pytest.raises(B.PslotError):
         orb.detect_and_compute_resident(sb, 2 * P - 1, 2)
 
