@@ -113,11 +113,16 @@ def detect_and_compute(image: np.ndarray, mask: np.ndarray | None, nfeatures=100
     border = max(edge_threshold, max(desc_patch, HARRIS_BLOCK_SIZE // 2)) + 1
     # pyramid (ORB_Impl::detectAndCompute): level sizes from the layer scale, each level resized from the previous one
     scales, levels, masks = [], [], []
+    if mask is not None:  # cv::ORB looks at the mask as zero / non-zero: any non-zero value acts as 255 on every level
+        mask = np.where(mask != 0, 255, 0).astype(np.uint8)
     prev, prev_m = image, mask
     for level in range(nlevels):
         s = F(math.pow(sf, float(level)))
         scales.append(s)
-        size = (_cv_round(image.shape[1] / s), _cv_round(image.shape[0] / s))
+        # written `cvRound(image.cols / scale)` in orb.cpp, but OpenCV 4.13's build evaluates both divisions as products with
+        # one float reciprocal (465 / 1.2f -> 387, 465 * (1 / 1.2f) -> 388): found by tools/cvorb_fuzz.py
+        inv_s = F(F(1.0) / s)
+        size = (_cv_round(F(F(image.shape[1]) * inv_s)), _cv_round(F(F(image.shape[0]) * inv_s)))
         cur, cur_m = image, mask
         if level:
             cur = cv2.resize(prev, size, interpolation=cv2.INTER_LINEAR_EXACT)

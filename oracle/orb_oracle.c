@@ -1418,6 +1418,9 @@ int orc_cvorb_detect_and_compute(const uint8_t *img, int w, int h, ptrdiff_t pit
                                  int *n_out)
 {
     if (nlevels < 1 || nlevels > MAX_LEVELS || w <= 0 || h <= 0) return -1;
+    /* the same ranges as pslot_cvorb_create.  edgeThreshold < 19: the steered pattern (radius 18.4) leaves the level and
+     * cv::ORB samples the unblurred reflected frame of its pyramid buffer there, which this restatement does not model */
+    if (nfeatures < 1 || !(scale_factor_f > 1.0f) || edge_threshold < 19 || fast_threshold < 1 || fast_threshold > 254) return -1;
     const double scaleFactor = (double)scale_factor_f; /* ORB::create takes a float, the member is a double */
     const int patchSize = 31, halfPatch = 15;
     int umax[HALF_PATCH_SIZE + 2];
@@ -1444,13 +1447,17 @@ int orc_cvorb_detect_and_compute(const uint8_t *img, int w, int h, ptrdiff_t pit
     const float deg2rad = (float)(3.1415926535897932384626433832795 / 180.f);
     for (int level = 0; level < nlevels && rc == 0; ++level) {
         const float scale = (float)pow(scaleFactor, (double)level);
-        const int lw = orc_cv_round(w / scale), lh = orc_cv_round(h / scale);
+        /* `cvRound(image.cols / scale)` in orb.cpp; OpenCV 4.13's build evaluates the two divisions as products with one float
+         * reciprocal (465 / 1.2f -> 387, 465 * (1 / 1.2f) -> 388; pinned by tools/cvorb_fuzz.py against cv2) */
+        const float inv_scale = 1.0f / scale;
+        const int lw = orc_cv_round((float)w * inv_scale), lh = orc_cv_round((float)h * inv_scale);
         if (lw < 2 * edge_threshold + 1 || lh < 2 * edge_threshold + 1) break; /* nothing can pass the border filter */
         uint8_t *cur = malloc((size_t)lw * (size_t)lh), *curm = mask ? malloc((size_t)lw * (size_t)lh) : NULL;
         if (level == 0) {
             for (int y = 0; y < lh; ++y) {
                 memcpy(cur + (size_t)y * lw, img + (ptrdiff_t)y * pitch, (size_t)lw);
-                if (mask) memcpy(curm + (size_t)y * lw, mask + (ptrdiff_t)y * mask_pitch, (size_t)lw);
+                if (mask) /* cv::ORB looks at the mask as zero / non-zero: any non-zero value acts as 255 on every level */
+                    for (int x = 0; x < lw; ++x) curm[(size_t)y * lw + x] = mask[(ptrdiff_t)y * mask_pitch + x] ? 255 : 0;
             }
         } else {
             resize_linear_exact_u8(prev, pw, ph, pw, cur, lw, lh, lw);

@@ -51,8 +51,12 @@ k_cv_resize_exact(const uint8_t *__restrict__ src_img, const uint8_t *__restrict
     for (int b = 0; b < 4; ++b) {
         const int2 tx = xt[min(x4 + b, dw - 1)];
         const int xa = tx.x, xb = min(xa + 1, sw - 1), ax = tx.y;
-        const int H0 = (int)r0[xa] * (256 - ax) + (int)r0[xb] * ax;
-        const int H1 = (int)r1[xa] * (256 - ax) + (int)r1[xb] * ax;
+        int p00 = r0[xa], p01 = r0[xb], p10 = r1[xa], p11 = r1[xb];
+        if (is_mask) { // cv::ORB looks at a mask as zero / non-zero; levels >= 1 hold 0 / 255 already (the threshold below)
+            p00 = p00 ? 255 : 0; p01 = p01 ? 255 : 0; p10 = p10 ? 255 : 0; p11 = p11 ? 255 : 0;
+        }
+        const int H0 = p00 * (256 - ax) + p01 * ax;
+        const int H1 = p10 * (256 - ax) + p11 * ax;
         int v = (H0 * (256 - ay) + H1 * ay + (1 << 15)) >> 16;
         if (is_mask) v = v > 254 ? v : 0; // cv::threshold(mask, mask, 254, 0, THRESH_TOZERO)
         if (x4 + b < dw) out |= (uint32_t)v << (8 * b);

@@ -275,8 +275,8 @@ def test_cvorb_stages_against_the_oracle(B, oracle_mod):
     for l in range(8):
         img = orb.stage(0, l)
         if l:
-            sc = np.float32(1.2 ** l)
-            w, h = int(np.rint(np.float32(752) / sc)), int(np.rint(np.float32(480) / sc))
+            inv = np.float32(1) / np.float32(np.float64(np.float32(1.2)) ** l)  # one float reciprocal, as OpenCV 4.13's build
+            w, h = int(np.rint(np.float32(752) * inv)), int(np.rint(np.float32(480) * inv))
             assert img.shape == (h, w)
             assert np.array_equal(img, cv2.resize(prev, (w, h), interpolation=cv2.INTER_LINEAR_EXACT)), f"level {l}"
         prev = img
@@ -291,3 +291,73 @@ def test_cvorb_stages_against_the_oracle(B, oracle_mod):
         kept = set(zip(kx.tolist(), ky.tolist(), ks.tolist()))
         assert kept <= want and all(s < ks.min() for (_, _, s) in want - kept)
         assert np.all(np.isfinite(kr))
+
+
+@pytest.mark.parametrize("shape", [(465, 750), (585, 1123), (312, 561)])
+def test_cvorb_level_sizes_round_like_opencv(shape, B, oracle_mod):
+    """A dimension with dim / 1.2 = x.5 (465 * (1 / 1.2f) rounds to 388, 465 / 1.2f to 387): OpenCV 4.13 multiplies by one
+    float reciprocal, and every level from there on is a different image.  Found by tools/cvorb_fuzz.py."""
+    from pointslot_b200.synth import synth_pair
+    H, W = shape
+    img = synth_pair(W, H, 17)[0]
+    mask = _object_mask(H, W)
+    orb = B.CvOrb(1000, 1.2, 8, 19)
+    for m in (None, mask):
+        ref, rdesc = _cv2_sorted(img, m)
+        k, d = orb.detect_and_compute(img, m)
+        _assert_equal(k, d, ref, rdesc, f"{shape} mask={m is not None} vs cv2")
+        ok, od = oracle_mod.cvorb_detect_and_compute(img, m)
+        assert k.tobytes() == ok.tobytes() and np.array_equal(d, od)
+
+
+def test_cvorb_mask_is_zero_or_nonzero(B):
+    """cv::ORB looks at its mask as zero / non-zero: regions filled with 1 or 100 keep their keypoints on every level."""
+    from pointslot_b200.synth import synth_pair
+    img = synth_pair(871, 409, 7)[0]
+    m = np.zeros_like(img)
+    m[50:300, 100:500] = 255
+    m[100:380, 450:800] = 100
+    m[20:90, 600:860] = 1
+    ref, rdesc = _cv2_sorted(img, m)
+    orb = B.CvOrb(1000, 1.2, 8, 19)
+    k, d = orb.detect_and_compute(img, m)
+    _assert_equal(k, d, ref, rdesc, "mask values 255 / 100 / 1 vs cv2")
+    (k2, d2), (k3, d3) = orb.detect_and_compute_batch([img, img], [m, None])   # the batched path reads the same mask plane
+    assert k2.tobytes() == k.tobytes() and np.array_equal(d2, d)
+    ref3, rdesc3 = _cv2_sorted(img, None)
+    _assert_equal(k3, d3, ref3, rdesc3, "unmasked image of the same batch vs cv2")
+
+
+def test_cvorb_randomised_against_cv2(B):
+    """Cases drawn by tools/cvorb_fuzz.py (random shapes, parameters, content classes, object masks with arbitrary non-zero
+    values): the device against cv2.ORB_create itself."""
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("cvorb_fuzz", Path(__file__).resolve().parents[1] / "tools" / "cvorb_fuzz.py")
+    fz = importlib.util.module_from_spec(spec); spec.loader.exec_module(fz)
+    rng = np.random.default_rng(99)
+    done = n = 0
+    while done < 16:
+        n += 1
+        W, H, p = fz.draw_case(rng)
+        if n % 2:
+            p = (1000, 1.2, 8, 19, 20)
+        kind = fz.CONTENT[n % len(fz.CONTENT)]
+        if kind == "checker" or p[0] > 2000:
+            continue  # thousands of exactly tied responses on one level exceed the on-chip sort (PSLOT_ERR_CAPACITY, by design)
+        img = fz.make_image(kind, W, H, rng, 990000 + n)
+        mask = fz.make_mask(W, H, rng, True) if n % 3 else None
+        try:
+            orb = B.CvOrb(*p)
+        except B.PslotError:
+            continue  # edgeThreshold < 19
+        rec, octv, rdesc = fz.cv2_sorted(img, mask, p)
+        k, d = orb.detect_and_compute(img, mask)
+        what = f"{W}x{H} {p} mask={mask is not None}"
+        assert len(k) == len(rec), f"{what}: {len(k)} vs {len(rec)} keypoints"
+        if len(rec):
+            got = np.stack([k["x"], k["y"], k["size"], k["angle"], k["response"]], 1)
+            assert np.array_equal(got.view(np.uint32), rec.view(np.uint32)), what
+            assert np.array_equal(k["octave"], octv) and np.array_equal(d, rdesc), what
+        orb.close()
+        done += 1

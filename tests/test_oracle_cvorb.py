@@ -103,3 +103,66 @@ def test_c_oracle_equals_cv2_orb_on_varied_content(oracle_mod):
             assert np.array_equal(got, want), img.shape
             assert np.array_equal(k["octave"], np.array([r[5] for r in ref], np.int32))
             assert np.array_equal(d, rdesc), img.shape
+
+
+def _equal_to_cv2(k, d, ref, rdesc, what):
+    assert len(k) == len(ref), f"{what}: {len(k)} vs {len(ref)} keypoints"
+    if len(ref):
+        got = np.stack([k["x"], k["y"], k["size"], k["angle"], k["response"]], 1)
+        assert np.array_equal(got, np.array([r[:5] for r in ref], np.float32)), what
+        assert np.array_equal(k["octave"], np.array([r[5] for r in ref], np.int32)), what
+        assert np.array_equal(d, rdesc), what
+
+
+@pytest.mark.parametrize("shape", [(465, 750), (585, 1123), (832, 609), (312, 561), (390, 513)])
+def test_level_sizes_round_like_opencv(shape, oracle_mod):
+    """A dimension with dim / 1.2 = x.5: orb.cpp writes cvRound(cols / scale), OpenCV 4.13's build multiplies by one float
+    reciprocal instead (465 / 1.2f = 387.49997 -> 387, 465 * (1 / 1.2f) = 387.5 -> 388), and every level from there on is a
+    different image.  Found by tools/cvorb_fuzz.py; both restatements follow the library."""
+    from oracle import cvorb_path
+    from pointslot_b200.synth import synth_pair
+    H, W = shape
+    img = synth_pair(W, H, 17)[0]
+    ref, rdesc = _cv2_sorted(img, None)
+    _equal_to_cv2(*oracle_mod.cvorb_detect_and_compute(img), ref, rdesc, f"C oracle {shape}")
+    if shape == (465, 750):
+        _equal_to_cv2(*cvorb_path.detect_and_compute(img, None), ref, rdesc, f"python path {shape}")
+
+
+def test_mask_is_zero_or_nonzero(oracle_mod):
+    """cv::ORB looks at its mask as zero / non-zero: a region filled with 1, 100 or 254 keeps its keypoints on EVERY level
+    (not only on level 0, as resizing the raw mask and thresholding at 254 would give).  The reference itself only builds
+    0 / 255 masks (Frame.cc:2637-2646)."""
+    from oracle import cvorb_path
+    from pointslot_b200.synth import synth_pair
+    img = synth_pair(871, 409, 7)[0]
+    m = np.zeros_like(img)
+    m[50:300, 100:500] = 255
+    m[100:380, 450:800] = 100
+    m[20:90, 600:860] = 1
+    ref, rdesc = _cv2_sorted(img, m)
+    ref255, _ = _cv2_sorted(img, np.where(m != 0, 255, 0).astype(np.uint8))
+    assert ref == ref255 and len(ref) > 500
+    _equal_to_cv2(*oracle_mod.cvorb_detect_and_compute(img, m), ref, rdesc, "C oracle")
+    _equal_to_cv2(*cvorb_path.detect_and_compute(img, m), ref, rdesc, "python path")
+
+
+def test_c_oracle_equals_cv2_orb_randomised(oracle_mod):
+    """A bounded run of tools/cvorb_fuzz.py (random shapes, parameters, content classes, object masks with arbitrary
+    non-zero values); the long sweeps are in profiles/r02_cvorb_fuzz.txt."""
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("cvorb_fuzz", Path(__file__).resolve().parents[1] / "tools" / "cvorb_fuzz.py")
+    fz = importlib.util.module_from_spec(spec); spec.loader.exec_module(fz)
+    for flags in ({"ref"}, {"anymask"}):
+        s = fz.run(25, 1234, flags)
+        assert s["cases"] == 25 and s["mismatches"] == 0 and s["keypoints"] > 3000, s
+
+
+def test_c_oracle_refuses_what_the_abi_refuses(oracle_mod):
+    """edgeThreshold < 19 lets the steered pattern (radius 18.4) leave the level; neither the device nor the restatement
+    models the unblurred frame cv::ORB samples there, so both refuse (pslot_cvorb_create: PSLOT_ERR_ARG)."""
+    img = np.zeros((200, 300), np.uint8)
+    for bad in (dict(edge_threshold=18), dict(scale_factor=1.0), dict(fast_threshold=0), dict(nfeatures=0)):
+        with pytest.raises(ValueError):
+            oracle_mod.cvorb_detect_and_compute(img, None, **bad)
