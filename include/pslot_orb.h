@@ -315,7 +315,8 @@ int pslot_batch_stereo_counters(pslot_batch *b, int64_t out[2]);
  * OpenCV's own ORB for the dense object features.
  * Replaces `cv::ORB::create(1000, 1.2, 8, 19)->detectAndCompute(im, ObjMask, kp, descriptor)`
  * (reference src/Frame.cc:2623-2627 OpencvORBDetector, run for both views by Frame::ExtractObjORB :2628-2665):
- * HARRIS_SCORE, patchSize 31, WTA_K 2, firstLevel 0.  `mask` may be NULL; non-zero = keep (runByPixelsMask).
+ * HARRIS_SCORE, patchSize 31, WTA_K 2, firstLevel 0.  `mask` may be NULL; non-zero = keep, on every pyramid level (cv::ORB
+ * reads its mask as zero / non-zero; the reference builds 0 / 255 masks, Frame.cc:2637-2646).  edge_threshold >= 19.
  * Output: cv::KeyPoint-compatible records and 32-byte descriptors ordered by (octave, y, x) - cv::ORB's own order is
  * whatever std::nth_element leaves and is not part of the contract; the SET and every field are OpenCV 4.13's, bit for
  * bit (tests compare with cv2.ORB_create directly).  Returns PSLOT_ERR_CAPACITY with *n = needed when cap is too small.
