@@ -261,69 +261,131 @@ def test_oracle_equals_reference_search_by_projection(oracle_mod):
         assert np.array_equal(rslot, _replay_slots(len(c["k"]), c["occupied"], got))
 
 
+def _check_projection_last(oracle_mod, ref_path, seed, tz, mono, ori, th):
+    """One comparison of oracle_equals_reference_search_by_projection_last (the body of the test below; tools/ref_fuzz_frame.py calls it with random arguments)."""
+    fx, fy, cx, cy, mbf = F(721.5377), F(721.5377), F(609.5593), F(172.854), F(384.38148)
+    mb = F(mbf / fx)
+    c = _frame_case(oracle_mod, seed, n_feat=700, n_mp=10)
+    rng = np.random.default_rng(2000 + seed)
+    k, d, ur = c["k"], c["d"], c["ur"]
+    n = len(k)
+    n_pts = n + n // 3
+    src = np.concatenate([np.arange(n), rng.integers(0, n, n_pts - n)]); rng.shuffle(src)
+    z = rng.uniform(3, 40, n_pts).astype(F)
+    z[rng.random(n_pts) < 0.03] *= F(-1)                       # behind the camera -> invzc < 0
+    u0 = k["x"][src] + rng.normal(0, 3.0, n_pts).astype(F); v0 = k["y"][src] + rng.normal(0, 3.0, n_pts).astype(F)
+    far = rng.random(n_pts) < 0.03
+    u0[far] += F(3000)                                         # outside the image bounds
+    xc = ((u0 - cx) * z / fx).astype(F); yc = ((v0 - cy) * z / fy).astype(F)
+    xyz = np.stack([xc, yc, z], axis=1).astype(F)
+    # ---- the reference's projection lines in float32, one rounding per operation (no FMA: -ffp-contract=off)
+    invzc = (1.0 / z.astype(np.float64)).astype(F)
+    u = ((fx * xc).astype(F) * invzc).astype(F) + cx
+    v = ((fy * yc).astype(F) * invzc).astype(F) + cy
+    last = np.zeros(n_pts, ref_path.KEYPOINT_DTYPE)
+    last["octave"] = k["octave"][src]
+    ang = (k["angle"][src] + F(11.0)) % F(360.0)
+    rnd = rng.random(n_pts) < 0.25
+    ang[rnd] = rng.uniform(0, 360, rnd.sum()).astype(F)
+    last["angle"] = ang
+    has = rng.random(n_pts) < 0.93; outl = rng.random(n_pts) < 0.05; obs = rng.random(n_pts) < 0.85
+    lflags = (has * 1 + outl * 2 + obs * 4).astype(np.uint8)
+    from test_oracle_projection import _flip_bits
+    pd = _flip_bits(rng, d[src], rng.integers(0, 50, n_pts))
+    # ---- what the oracle takes: the points after the projection lines
+    pts = np.zeros(n_pts, oracle_mod.PROJ_POINT_DTYPE)
+    pts["u"], pts["v"] = u, v
+    pts["ur"] = u - (mbf * invzc).astype(F)
+    octv = last["octave"]
+    pts["radius"] = (F(th) * c["sf"][octv]).astype(F)
+    forward = (not mono) and F(tz) > mb; backward = (not mono) and -F(tz) > mb
+    if forward:
+        pts["min_level"], pts["max_level"] = octv, -1
+    elif backward:
+        pts["min_level"], pts["max_level"] = 0, octv
+    else:
+        pts["min_level"], pts["max_level"] = octv - 1, octv + 1
+    pts["angle"] = last["angle"]
+    inb = (u >= 0) & (u <= c["W"]) & (v >= 0) & (v <= c["H"])
+    reach = has & ~outl & ~(invzc < 0) & inb
+    pts["flags"] = reach * 1 + obs * 2
+    cs, idx = oracle_mod.assign_grid(k, 0.0, 0.0, c["inv_w"], c["inv_h"])
+    m, rej, nm = oracle_mod.search_by_projection_last(k, d, ur, cs, idx, 0.0, 0.0, c["inv_w"], c["inv_h"], 64, 48, pts,
+                                                     pd, c["occupied"], bool(ori))
+    fr = _ref_frame(ref_path, c)
+    rn, rslot = fr.search_by_projection_last(last, xyz, pd, lflags, tz, fx, fy, cx, cy, mbf, mb, c["occupied"], th,
+                                             mono, ori)
+    slot = _replay_slots(n, c["occupied"], m)
+    for i in np.nonzero(rej)[0]:
+        slot[m[i]] = -1
+    assert rn == nm
+    assert np.array_equal(rslot, slot)
+    return int(nm), int(rej.sum())
+
+
 def test_oracle_equals_reference_search_by_projection_last(oracle_mod):
     """The reference projects LastFrame's map points itself (ORBmatcher.cc:1640-1676); with identity rotations the camera
     coordinates equal the world coordinates exactly, so the float32 lines below reproduce its u, v, invzc bit for bit."""
     ref_path = _ref("stock")
-    fx, fy, cx, cy, mbf = F(721.5377), F(721.5377), F(609.5593), F(172.854), F(384.38148)
-    mb = F(mbf / fx)
     for seed, tz, mono, ori, th in ((1, 0.0, 0, 1, 7.0), (2, 2.0, 0, 1, 15.0), (3, -2.0, 0, 1, 7.0), (4, 2.0, 1, 0, 15.0)):
-        c = _frame_case(oracle_mod, seed, n_feat=700, n_mp=10)
-        rng = np.random.default_rng(2000 + seed)
-        k, d, ur = c["k"], c["d"], c["ur"]
-        n = len(k)
-        n_pts = n + n // 3
-        src = np.concatenate([np.arange(n), rng.integers(0, n, n_pts - n)]); rng.shuffle(src)
-        z = rng.uniform(3, 40, n_pts).astype(F)
-        z[rng.random(n_pts) < 0.03] *= F(-1)                       # behind the camera -> invzc < 0
-        u0 = k["x"][src] + rng.normal(0, 3.0, n_pts).astype(F); v0 = k["y"][src] + rng.normal(0, 3.0, n_pts).astype(F)
-        far = rng.random(n_pts) < 0.03
-        u0[far] += F(3000)                                         # outside the image bounds
-        xc = ((u0 - cx) * z / fx).astype(F); yc = ((v0 - cy) * z / fy).astype(F)
-        xyz = np.stack([xc, yc, z], axis=1).astype(F)
-        # ---- the reference's projection lines in float32, one rounding per operation (no FMA: -ffp-contract=off)
-        invzc = (1.0 / z.astype(np.float64)).astype(F)
-        u = ((fx * xc).astype(F) * invzc).astype(F) + cx
-        v = ((fy * yc).astype(F) * invzc).astype(F) + cy
-        last = np.zeros(n_pts, ref_path.KEYPOINT_DTYPE)
-        last["octave"] = k["octave"][src]
-        ang = (k["angle"][src] + F(11.0)) % F(360.0)
-        rnd = rng.random(n_pts) < 0.25
-        ang[rnd] = rng.uniform(0, 360, rnd.sum()).astype(F)
-        last["angle"] = ang
-        has = rng.random(n_pts) < 0.93; outl = rng.random(n_pts) < 0.05; obs = rng.random(n_pts) < 0.85
-        lflags = (has * 1 + outl * 2 + obs * 4).astype(np.uint8)
-        from test_oracle_projection import _flip_bits
-        pd = _flip_bits(rng, d[src], rng.integers(0, 50, n_pts))
-        # ---- what the oracle takes: the points after the projection lines
-        pts = np.zeros(n_pts, oracle_mod.PROJ_POINT_DTYPE)
-        pts["u"], pts["v"] = u, v
-        pts["ur"] = u - (mbf * invzc).astype(F)
-        octv = last["octave"]
-        pts["radius"] = (F(th) * c["sf"][octv]).astype(F)
-        forward = (not mono) and F(tz) > mb; backward = (not mono) and -F(tz) > mb
-        if forward:
-            pts["min_level"], pts["max_level"] = octv, -1
-        elif backward:
-            pts["min_level"], pts["max_level"] = 0, octv
-        else:
-            pts["min_level"], pts["max_level"] = octv - 1, octv + 1
-        pts["angle"] = last["angle"]
-        inb = (u >= 0) & (u <= c["W"]) & (v >= 0) & (v <= c["H"])
-        reach = has & ~outl & ~(invzc < 0) & inb
-        pts["flags"] = reach * 1 + obs * 2
-        cs, idx = oracle_mod.assign_grid(k, 0.0, 0.0, c["inv_w"], c["inv_h"])
-        m, rej, nm = oracle_mod.search_by_projection_last(k, d, ur, cs, idx, 0.0, 0.0, c["inv_w"], c["inv_h"], 64, 48, pts,
-                                                         pd, c["occupied"], bool(ori))
-        fr = _ref_frame(ref_path, c)
-        rn, rslot = fr.search_by_projection_last(last, xyz, pd, lflags, tz, fx, fy, cx, cy, mbf, mb, c["occupied"], th,
-                                                 mono, ori)
-        slot = _replay_slots(n, c["occupied"], m)
-        for i in np.nonzero(rej)[0]:
-            slot[m[i]] = -1
-        assert rn == nm and nm > 100
-        assert np.array_equal(rslot, slot)
-        assert (not ori) or rej.sum() > 0
+        nm, nrej = _check_projection_last(oracle_mod, ref_path, seed, tz, mono, ori, th)
+        assert nm > 100 and ((not ori) or nrej > 0)
+
+
+def _check_projection_kf(oracle_mod, ref_path, seed, ori, th, orb_dist):
+    """One comparison of oracle_equals_reference_search_by_projection_kf (the body of the test below; tools/ref_fuzz_frame.py calls it with random arguments)."""
+    fx, fy, cx, cy = F(721.5377), F(721.5377), F(609.5593), F(172.854)
+    c = _frame_case(oracle_mod, seed, n_feat=700, n_mp=10)
+    rng = np.random.default_rng(3000 + seed)
+    k, d = c["k"], c["d"]
+    n = len(k)
+    n_pts = n + n // 3
+    src = np.concatenate([np.arange(n), rng.integers(0, n, n_pts - n)]); rng.shuffle(src)
+    z = rng.uniform(3, 40, n_pts).astype(F)
+    u0 = k["x"][src] + rng.normal(0, 3.0, n_pts).astype(F); v0 = k["y"][src] + rng.normal(0, 3.0, n_pts).astype(F)
+    far = rng.random(n_pts) < 0.03
+    u0[far] += F(3000)                                         # outside the image bounds
+    xc = ((u0 - cx) * z / fx).astype(F); yc = ((v0 - cy) * z / fy).astype(F)
+    xyz = np.stack([xc, yc, z], axis=1).astype(F)
+    # ---- the reference's lines :2554-2575 in float32, one rounding per operation
+    invzc = (1.0 / z.astype(np.float64)).astype(F)
+    u = ((fx * xc).astype(F) * invzc).astype(F) + cx
+    v = ((fy * yc).astype(F) * invzc).astype(F) + cy
+    dist3d = np.sqrt((xyz.astype(np.float64) ** 2).sum(1)).astype(F)   # cv::norm(PO): double accumulator, PO = x3Dw - 0
+    in_range = rng.random(n_pts) < 0.93
+    mind = np.where(in_range, dist3d * F(0.5), dist3d * F(2.0)).astype(F)
+    maxd = (dist3d * F(3.0)).astype(F)
+    kf = np.zeros(n_pts, ref_path.KEYPOINT_DTYPE)
+    ang = (k["angle"][src] + F(41.0)) % F(360.0)
+    rnd = rng.random(n_pts) < 0.25
+    ang[rnd] = rng.uniform(0, 360, rnd.sum()).astype(F)
+    kf["angle"] = ang
+    level = np.clip(k["octave"][src] + rng.integers(-1, 2, n_pts), 0, 7).astype(np.int32)   # PredictScale's answer
+    has = rng.random(n_pts) < 0.93; bad = rng.random(n_pts) < 0.05; found = rng.random(n_pts) < 0.1
+    kflags = (has * 1 + bad * 2 + found * 4).astype(np.uint8)
+    from test_oracle_projection import _flip_bits
+    pd = _flip_bits(rng, d[src], rng.integers(0, 70, n_pts))
+    pts = np.zeros(n_pts, oracle_mod.PROJ_POINT_DTYPE)
+    pts["u"], pts["v"] = u, v
+    pts["radius"] = (F(th) * c["sf"][level]).astype(F)
+    pts["min_level"], pts["max_level"] = level - 1, level + 1
+    pts["angle"] = kf["angle"]
+    inb = (u >= 0) & (u <= c["W"]) & (v >= 0) & (v <= c["H"])
+    pts["flags"] = (has & ~bad & ~found & inb & ~(dist3d < mind) & ~(dist3d > maxd)) * 1
+    cs, idx = oracle_mod.assign_grid(k, 0.0, 0.0, c["inv_w"], c["inv_h"])
+    m, rej, nm = oracle_mod.search_by_projection_kf(k, d, cs, idx, 0.0, 0.0, c["inv_w"], c["inv_h"], 64, 48, pts, pd,
+                                                   c["occupied"], orb_dist, bool(ori))
+    fr = _ref_frame(ref_path, c)
+    rn, rslot = fr.search_by_projection_kf(kf, xyz, pd, kflags, level, mind, maxd, fx, fy, cx, cy, c["occupied"], th,
+                                           orb_dist, ori)
+    slot = np.where(c["occupied"].astype(bool), -2, -1).astype(np.int32)
+    for i in np.nonzero(m >= 0)[0]:
+        slot[m[i]] = i
+    for i in np.nonzero(rej)[0]:
+        slot[m[i]] = -1
+    assert rn == nm
+    assert np.array_equal(rslot, slot)
+    return int(nm), int(rej.sum())
 
 
 def test_oracle_equals_reference_search_by_projection_kf(oracle_mod):
@@ -331,59 +393,73 @@ def test_oracle_equals_reference_search_by_projection_kf(oracle_mod):
     (ORBmatcher.cc:2529-2654), the reference's own function: with CurrentFrame.mTcw = I the projection lines below
     reproduce its u, v, dist3D bit for bit; the oracle takes the points after them."""
     ref_path = _ref("stock")
-    fx, fy, cx, cy = F(721.5377), F(721.5377), F(609.5593), F(172.854)
     for seed, ori, th, orb_dist in ((1, 1, 10.0, 100), (2, 1, 3.0, 64), (3, 0, 10.0, 100), (4, 1, 15.0, 80)):
-        c = _frame_case(oracle_mod, seed, n_feat=700, n_mp=10)
-        rng = np.random.default_rng(3000 + seed)
-        k, d = c["k"], c["d"]
-        n = len(k)
-        n_pts = n + n // 3
-        src = np.concatenate([np.arange(n), rng.integers(0, n, n_pts - n)]); rng.shuffle(src)
-        z = rng.uniform(3, 40, n_pts).astype(F)
-        u0 = k["x"][src] + rng.normal(0, 3.0, n_pts).astype(F); v0 = k["y"][src] + rng.normal(0, 3.0, n_pts).astype(F)
-        far = rng.random(n_pts) < 0.03
-        u0[far] += F(3000)                                         # outside the image bounds
-        xc = ((u0 - cx) * z / fx).astype(F); yc = ((v0 - cy) * z / fy).astype(F)
-        xyz = np.stack([xc, yc, z], axis=1).astype(F)
-        # ---- the reference's lines :2554-2575 in float32, one rounding per operation
-        invzc = (1.0 / z.astype(np.float64)).astype(F)
-        u = ((fx * xc).astype(F) * invzc).astype(F) + cx
-        v = ((fy * yc).astype(F) * invzc).astype(F) + cy
-        dist3d = np.sqrt((xyz.astype(np.float64) ** 2).sum(1)).astype(F)   # cv::norm(PO): double accumulator, PO = x3Dw - 0
-        in_range = rng.random(n_pts) < 0.93
-        mind = np.where(in_range, dist3d * F(0.5), dist3d * F(2.0)).astype(F)
-        maxd = (dist3d * F(3.0)).astype(F)
-        kf = np.zeros(n_pts, ref_path.KEYPOINT_DTYPE)
-        ang = (k["angle"][src] + F(41.0)) % F(360.0)
-        rnd = rng.random(n_pts) < 0.25
-        ang[rnd] = rng.uniform(0, 360, rnd.sum()).astype(F)
-        kf["angle"] = ang
-        level = np.clip(k["octave"][src] + rng.integers(-1, 2, n_pts), 0, 7).astype(np.int32)   # PredictScale's answer
-        has = rng.random(n_pts) < 0.93; bad = rng.random(n_pts) < 0.05; found = rng.random(n_pts) < 0.1
-        kflags = (has * 1 + bad * 2 + found * 4).astype(np.uint8)
-        from test_oracle_projection import _flip_bits
-        pd = _flip_bits(rng, d[src], rng.integers(0, 70, n_pts))
-        pts = np.zeros(n_pts, oracle_mod.PROJ_POINT_DTYPE)
-        pts["u"], pts["v"] = u, v
-        pts["radius"] = (F(th) * c["sf"][level]).astype(F)
-        pts["min_level"], pts["max_level"] = level - 1, level + 1
-        pts["angle"] = kf["angle"]
-        inb = (u >= 0) & (u <= c["W"]) & (v >= 0) & (v <= c["H"])
-        pts["flags"] = (has & ~bad & ~found & inb & ~(dist3d < mind) & ~(dist3d > maxd)) * 1
-        cs, idx = oracle_mod.assign_grid(k, 0.0, 0.0, c["inv_w"], c["inv_h"])
-        m, rej, nm = oracle_mod.search_by_projection_kf(k, d, cs, idx, 0.0, 0.0, c["inv_w"], c["inv_h"], 64, 48, pts, pd,
-                                                       c["occupied"], orb_dist, bool(ori))
-        fr = _ref_frame(ref_path, c)
-        rn, rslot = fr.search_by_projection_kf(kf, xyz, pd, kflags, level, mind, maxd, fx, fy, cx, cy, c["occupied"], th,
-                                               orb_dist, ori)
-        slot = np.where(c["occupied"].astype(bool), -2, -1).astype(np.int32)
-        for i in np.nonzero(m >= 0)[0]:
-            slot[m[i]] = i
-        for i in np.nonzero(rej)[0]:
-            slot[m[i]] = -1
-        assert rn == nm and nm > 100
-        assert np.array_equal(rslot, slot)
-        assert (not ori) or rej.sum() > 0
+        nm, nrej = _check_projection_kf(oracle_mod, ref_path, seed, ori, th, orb_dist)
+        assert nm > 100 and ((not ori) or nrej > 0)
+
+
+def _check_projection_sim3(oracle_mod, ref_path, seed, th):
+    """One comparison of oracle_equals_reference_search_by_projection_sim3 (the body of the test below; tools/ref_fuzz_frame.py calls it with random arguments)."""
+    fx, fy, cx, cy = F(721.5377), F(721.5377), F(609.5593), F(172.854)
+    c = _frame_case(oracle_mod, seed, n_feat=700, n_mp=10)
+    rng = np.random.default_rng(4000 + seed)
+    k, d = c["k"], c["d"]
+    n = len(k)
+    n_pts = n + n // 3
+    src = np.concatenate([np.arange(n), rng.integers(0, n, n_pts - n)]); rng.shuffle(src)
+    t2 = np.array([0.8, -0.4, 1.0], F)                          # Scw's translation column
+    tcw = (t2 / F(2.0)).astype(F)
+    z = rng.uniform(3, 40, n_pts).astype(F)
+    z[rng.random(n_pts) < 0.03] *= F(-1)                       # behind the camera
+    u0 = k["x"][src] + rng.normal(0, 3.0, n_pts).astype(F); v0 = k["y"][src] + rng.normal(0, 3.0, n_pts).astype(F)
+    u0[rng.random(n_pts) < 0.03] += F(3000)                    # outside the image
+    pc = np.stack([((u0 - cx) * z / fx), ((v0 - cy) * z / fy), z], axis=1).astype(F)   # intended camera coordinates
+    xyz = (pc - tcw).astype(F)                                  # world coordinates handed to the reference
+    # ---- the reference's lines :445-487 in float32, one rounding per operation
+    p3dc = (xyz + tcw).astype(F)                                # Rcw * p3Dw is exact (Rcw = I), then one float add
+    invz = (F(1.0) / p3dc[:, 2]).astype(F)
+    x = (p3dc[:, 0] * invz).astype(F); y = (p3dc[:, 1] * invz).astype(F)
+    u = ((fx * x).astype(F) + cx).astype(F); v = ((fy * y).astype(F) + cy).astype(F)
+    po = p3dc                                                    # p3Dw - Ow with Ow = -tcw: the same float add
+    dist64 = np.sqrt((po.astype(np.float64) ** 2).sum(1))
+    dist = dist64.astype(F)
+    normals = (po / np.maximum(dist, F(1e-6))[:, None]).astype(F)
+    oblique = rng.random(n_pts) < 0.08
+    normals[oblique] = np.array([1.0, 0.0, 0.0], F)             # viewing angle above 60 degrees for most of these
+    dot = (po.astype(np.float64) * normals.astype(np.float64)).sum(1)
+    in_range = rng.random(n_pts) < 0.93
+    mind = np.where(in_range, dist * F(0.5), dist * F(2.0)).astype(F)
+    maxd = (dist * F(3.0)).astype(F)
+    level = np.clip(k["octave"][src] + rng.integers(0, 2, n_pts), 0, 7).astype(np.int32)
+    bad = rng.random(n_pts) < 0.05
+    pre = np.full(n, -1, np.int32)                              # vpMatched on entry
+    held = rng.random(n) < 0.08
+    pre[held] = -2
+    own = rng.choice(np.nonzero(~held)[0], 30, replace=False)   # 30 features already hold one of the candidate points
+    pre[own] = rng.choice(n_pts, 30, replace=False)
+    already = np.zeros(n_pts, bool); already[pre[own]] = True
+    from test_oracle_projection import _flip_bits
+    pd = _flip_bits(rng, d[src], rng.integers(0, 60, n_pts))
+    pts = np.zeros(n_pts, oracle_mod.PROJ_POINT_DTYPE)
+    pts["u"], pts["v"] = u, v
+    pts["radius"] = (F(th) * c["sf"][level]).astype(F)
+    pts["min_level"], pts["max_level"] = level - 1, level
+    inb = (u >= 0) & (u < c["W"]) & (v >= 0) & (v < c["H"])
+    reach = ~bad & ~already & ~(p3dc[:, 2] < 0) & inb & ~(dist < mind) & ~(dist > maxd) & ~(dot < 0.5 * dist.astype(np.float64))
+    pts["flags"] = reach * 1
+    cs, idx = oracle_mod.assign_grid(k, 0.0, 0.0, c["inv_w"], c["inv_h"])
+    m, rej, nm = oracle_mod.search_by_projection_kf(k, d, cs, idx, 0.0, 0.0, c["inv_w"], c["inv_h"], 64, 48, pts, pd,
+                                                   (pre != -1).astype(np.uint8), 50, False)
+    fr = _ref_frame(ref_path, c)
+    scw = np.array([[2, 0, 0, t2[0]], [0, 2, 0, t2[1]], [0, 0, 2, t2[2]], [0, 0, 0, 1]], F)
+    rn, rslot = fr.search_by_projection_sim3(scw, xyz, normals, pd, (bad * 2).astype(np.uint8), level, mind, maxd, fx, fy,
+                                             cx, cy, pre, th)
+    slot = pre.copy()
+    for i in np.nonzero(m >= 0)[0]:
+        slot[m[i]] = i
+    assert rn == nm and not rej.any()
+    assert np.array_equal(rslot, slot)
+    return int(nm)
 
 
 def test_oracle_equals_reference_search_by_projection_sim3(oracle_mod):
@@ -392,66 +468,26 @@ def test_oracle_equals_reference_search_by_projection_sim3(oracle_mod):
     lines it is the key-frame search with the level window [L - 1, L], TH_LOW and no rotation check - which is how
     pslot_search_by_projection_kf serves it.  Scw = 2 * [I | t]: scw = 2, Rcw = I, tcw = t / 2 exactly."""
     ref_path = _ref("stock")
-    fx, fy, cx, cy = F(721.5377), F(721.5377), F(609.5593), F(172.854)
     for seed, th in ((1, 10), (2, 4), (3, 15)):
-        c = _frame_case(oracle_mod, seed, n_feat=700, n_mp=10)
-        rng = np.random.default_rng(4000 + seed)
-        k, d = c["k"], c["d"]
-        n = len(k)
-        n_pts = n + n // 3
-        src = np.concatenate([np.arange(n), rng.integers(0, n, n_pts - n)]); rng.shuffle(src)
-        t2 = np.array([0.8, -0.4, 1.0], F)                          # Scw's translation column
-        tcw = (t2 / F(2.0)).astype(F)
-        z = rng.uniform(3, 40, n_pts).astype(F)
-        z[rng.random(n_pts) < 0.03] *= F(-1)                       # behind the camera
-        u0 = k["x"][src] + rng.normal(0, 3.0, n_pts).astype(F); v0 = k["y"][src] + rng.normal(0, 3.0, n_pts).astype(F)
-        u0[rng.random(n_pts) < 0.03] += F(3000)                    # outside the image
-        pc = np.stack([((u0 - cx) * z / fx), ((v0 - cy) * z / fy), z], axis=1).astype(F)   # intended camera coordinates
-        xyz = (pc - tcw).astype(F)                                  # world coordinates handed to the reference
-        # ---- the reference's lines :445-487 in float32, one rounding per operation
-        p3dc = (xyz + tcw).astype(F)                                # Rcw * p3Dw is exact (Rcw = I), then one float add
-        invz = (F(1.0) / p3dc[:, 2]).astype(F)
-        x = (p3dc[:, 0] * invz).astype(F); y = (p3dc[:, 1] * invz).astype(F)
-        u = ((fx * x).astype(F) + cx).astype(F); v = ((fy * y).astype(F) + cy).astype(F)
-        po = p3dc                                                    # p3Dw - Ow with Ow = -tcw: the same float add
-        dist64 = np.sqrt((po.astype(np.float64) ** 2).sum(1))
-        dist = dist64.astype(F)
-        normals = (po / np.maximum(dist, F(1e-6))[:, None]).astype(F)
-        oblique = rng.random(n_pts) < 0.08
-        normals[oblique] = np.array([1.0, 0.0, 0.0], F)             # viewing angle above 60 degrees for most of these
-        dot = (po.astype(np.float64) * normals.astype(np.float64)).sum(1)
-        in_range = rng.random(n_pts) < 0.93
-        mind = np.where(in_range, dist * F(0.5), dist * F(2.0)).astype(F)
-        maxd = (dist * F(3.0)).astype(F)
-        level = np.clip(k["octave"][src] + rng.integers(0, 2, n_pts), 0, 7).astype(np.int32)
-        bad = rng.random(n_pts) < 0.05
-        pre = np.full(n, -1, np.int32)                              # vpMatched on entry
-        held = rng.random(n) < 0.08
-        pre[held] = -2
-        own = rng.choice(np.nonzero(~held)[0], 30, replace=False)   # 30 features already hold one of the candidate points
-        pre[own] = rng.choice(n_pts, 30, replace=False)
-        already = np.zeros(n_pts, bool); already[pre[own]] = True
-        from test_oracle_projection import _flip_bits
-        pd = _flip_bits(rng, d[src], rng.integers(0, 60, n_pts))
-        pts = np.zeros(n_pts, oracle_mod.PROJ_POINT_DTYPE)
-        pts["u"], pts["v"] = u, v
-        pts["radius"] = (F(th) * c["sf"][level]).astype(F)
-        pts["min_level"], pts["max_level"] = level - 1, level
-        inb = (u >= 0) & (u < c["W"]) & (v >= 0) & (v < c["H"])
-        reach = ~bad & ~already & ~(p3dc[:, 2] < 0) & inb & ~(dist < mind) & ~(dist > maxd) & ~(dot < 0.5 * dist.astype(np.float64))
-        pts["flags"] = reach * 1
-        cs, idx = oracle_mod.assign_grid(k, 0.0, 0.0, c["inv_w"], c["inv_h"])
-        m, rej, nm = oracle_mod.search_by_projection_kf(k, d, cs, idx, 0.0, 0.0, c["inv_w"], c["inv_h"], 64, 48, pts, pd,
-                                                       (pre != -1).astype(np.uint8), 50, False)
-        fr = _ref_frame(ref_path, c)
-        scw = np.array([[2, 0, 0, t2[0]], [0, 2, 0, t2[1]], [0, 0, 2, t2[2]], [0, 0, 0, 1]], F)
-        rn, rslot = fr.search_by_projection_sim3(scw, xyz, normals, pd, (bad * 2).astype(np.uint8), level, mind, maxd, fx, fy,
-                                                 cx, cy, pre, th)
-        slot = pre.copy()
-        for i in np.nonzero(m >= 0)[0]:
-            slot[m[i]] = i
-        assert rn == nm and nm > 60 and not rej.any()
-        assert np.array_equal(rslot, slot)
+        assert _check_projection_sim3(oracle_mod, ref_path, seed, th) > 60
+
+
+def _check_projection_obj(oracle_mod, ref_path, seed, th, nn):
+    """One comparison of oracle_equals_reference_search_by_projection_obj (the body of the test below; tools/ref_fuzz_frame.py calls it with random arguments)."""
+    c = _frame_case(oracle_mod, seed, n_feat=800, n_mp=900)
+    k = c["k"]
+    bbox = np.array([c["W"] // 5, c["H"] // 6, 3 * c["W"] // 5, 2 * c["H"] // 3], np.int32)   # x, y, width, height
+    inside = (k["x"] >= bbox[0]) & (k["x"] < bbox[0] + bbox[2]) & (k["y"] >= bbox[1]) & (k["y"] < bbox[1] + bbox[3])
+    cs, idx = oracle_mod.assign_grid(k, 0.0, 0.0, c["inv_w"], c["inv_h"])
+    occ = (c["occupied"].astype(bool) | ~inside).astype(np.uint8)
+    got, n = oracle_mod.search_by_projection_obj(k, c["d"], c["ur"], cs, idx, 0.0, 0.0, c["inv_w"], c["inv_h"], 64, 48,
+                                                c["mps"], c["md"], occ, c["sf"], th, nn)
+    fr = _ref_frame(ref_path, c)
+    rn, rslot = fr.search_by_projection_obj(c["mps"], c["md"], c["occupied"], bbox, th, nn)
+    assert rn == n
+    assert np.array_equal(rslot, _replay_slots(len(k), c["occupied"], got))
+    assert inside[got[got >= 0]].all()
+    return int(n), int((~inside).sum())
 
 
 def test_oracle_equals_reference_search_by_projection_obj(oracle_mod):
@@ -461,19 +497,8 @@ def test_oracle_equals_reference_search_by_projection_obj(oracle_mod):
     as occupied (the reference tests isInBBox per candidate, :206)."""
     ref_path = _ref("stock")
     for seed, th, nn in ((1, 1.0, 0.8), (2, 3.0, 0.8), (3, 5.0, 0.6)):
-        c = _frame_case(oracle_mod, seed, n_feat=800, n_mp=900)
-        k = c["k"]
-        bbox = np.array([c["W"] // 5, c["H"] // 6, 3 * c["W"] // 5, 2 * c["H"] // 3], np.int32)   # x, y, width, height
-        inside = (k["x"] >= bbox[0]) & (k["x"] < bbox[0] + bbox[2]) & (k["y"] >= bbox[1]) & (k["y"] < bbox[1] + bbox[3])
-        cs, idx = oracle_mod.assign_grid(k, 0.0, 0.0, c["inv_w"], c["inv_h"])
-        occ = (c["occupied"].astype(bool) | ~inside).astype(np.uint8)
-        got, n = oracle_mod.search_by_projection_obj(k, c["d"], c["ur"], cs, idx, 0.0, 0.0, c["inv_w"], c["inv_h"], 64, 48,
-                                                    c["mps"], c["md"], occ, c["sf"], th, nn)
-        fr = _ref_frame(ref_path, c)
-        rn, rslot = fr.search_by_projection_obj(c["mps"], c["md"], c["occupied"], bbox, th, nn)
-        assert rn == n and n > 60
-        assert np.array_equal(rslot, _replay_slots(len(k), c["occupied"], got))
-        assert inside[got[got >= 0]].all() and (~inside).sum() > 50
+        n, outside = _check_projection_obj(oracle_mod, ref_path, seed, th, nn)
+        assert n > 60 and outside > 50
 
 
 def _partition_case(oracle_mod, seed, n_orb=1500, n_dense=1000, W=1242, H=375):

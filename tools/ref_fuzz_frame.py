@@ -1,7 +1,7 @@
 """Randomised parity sweep of the oracle's "next rows" against the reference's own functions lifted verbatim into
 oracle/_ref/libref_orb.so: Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea
-(src/Frame.cc:1636-1655, 2027-2038, 1808-1861), ORBmatcher::SearchByProjection(F, vpMapPoints, th) (src/ORBmatcher.cc:68-155)
-and Frame::AssignFeatures (src/Frame.cc:759-977).  CPU only; test infrastructure.
+(src/Frame.cc:1636-1655, 2027-2038, 1808-1861), the five ORBmatcher::SearchByProjection overloads (src/ORBmatcher.cc:68-155,
+157-246, 413-527, 1613-1756, 2529-2654) and Frame::AssignFeatures (src/Frame.cc:759-977).  CPU only; test infrastructure.
 
 Every case draws a seed, feature / map-point counts, grid origin offsets, search radii, level windows, nnratio, and - for the
 partition - a random label image and detection list; the frame scenario builder is the one of tests/ (make_case).
@@ -34,7 +34,7 @@ def main():
     O.build()
     rng = np.random.default_rng(seed0)
     t0 = time.time()
-    n_grid = n_area = n_proj = n_match = n_part = n_part_feat = bad = 0
+    n_grid = n_area = n_proj = n_match = n_part = n_part_feat = n_other = n_other_match = bad = 0
     for case in range(cases):
         seed = int(rng.integers(0, 1 << 30))
         n_feat = int(rng.choice([200, 500, 800, 1200, 2000]))
@@ -69,6 +69,20 @@ def main():
         n_proj += 1; n_match += int(n)
         if rn != n or not np.array_equal(rslot, TR._replay_slots(len(c["k"]), c["occupied"], got)):
             bad += 1; print(f"MISMATCH case {case} (seed {seed}): search_by_projection th={th} nn={nn}: {n} vs {rn}", flush=True)
+        # ---- the other SearchByProjection overloads (check functions of tests/test_oracle_reference.py, random arguments)
+        sd = seed % 1000000
+        for name, fn, args in (
+                ("last-frame", TR._check_projection_last, (sd, float(rng.choice([0.0, 2.0, -2.0, 0.3, -0.3])), int(rng.random() < 0.3),
+                                                           int(rng.random() < 0.7), float(rng.choice([7.0, 15.0, 3.0, 30.0])))),
+                ("relocalisation", TR._check_projection_kf, (sd, int(rng.random() < 0.7), float(rng.choice([3.0, 10.0, 15.0, 25.0])),
+                                                               int(rng.choice([50, 64, 80, 100])))),
+                ("loop-closing", TR._check_projection_sim3, (sd, int(rng.choice([3, 4, 10, 15, 25])))),
+                ("object-point", TR._check_projection_obj, (sd, float(rng.choice([1.0, 3.0, 5.0])), float(rng.choice([0.6, 0.8, 0.9]))))):
+            try:
+                r = fn(O, RP, *args)
+                n_other += 1; n_other_match += int(r[0] if isinstance(r, tuple) else r)
+            except AssertionError as e:
+                bad += 1; print(f"MISMATCH case {case}: {name} SearchByProjection{args}: {e}", flush=True)
         # ---- Frame::AssignFeatures
         if case % 3 == 0:
             ok, nf = partition_case(seed % 100000, rng)
@@ -76,7 +90,8 @@ def main():
             if not ok:
                 bad += 1; print(f"MISMATCH case {case} (seed {seed}): assign_features", flush=True)
     print(f"oracle vs the reference's lifted functions, randomised: {cases} frames (seed {seed0}): {n_grid} grids, {n_area} area lookups, "
-          f"{n_proj} local-map projection searches with {n_match} matches, {n_part} feature partitions over {n_part_feat} features, "
+          f"{n_proj} local-map projection searches with {n_match} matches, {n_other} searches of the four other SearchByProjection overloads "
+          f"with {n_other_match} matches, {n_part} feature partitions over {n_part_feat} features, "
           f"{bad} mismatches, {time.time() - t0:.0f} s")
     sys.exit(1 if bad else 0)
 
