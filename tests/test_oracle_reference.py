@@ -555,3 +555,29 @@ def test_oracle_equals_reference_assign_features(oracle_mod):
             assert len(groups[1 + 4]) == 0 and len(groups[1 + 3]) > 0      # the second detection with id 8 gets nothing
             assert len(groups[1 + 1]) > 0                                   # mnObjectID 258 -> id 3 -> label 4
             assert len(groups[1 + 8]) == 0 and len(groups[1 + 9]) == 0 and (cls == -1).sum() > 0
+
+
+# ---- bounded runs of the randomised sweeps (the long ones are in profiles/r02_ref_fuzz*.txt) ------------------------------
+def _tool(name):
+    import importlib.util
+    import sys
+    from pathlib import Path
+    tools = Path(__file__).resolve().parents[1] / "tools"
+    if str(tools) not in sys.path:
+        sys.path.insert(0, str(tools))
+    spec = importlib.util.spec_from_file_location(name, tools / f"{name}.py")
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    return mod
+
+
+def test_randomised_extractor_and_stereo_against_reference(oracle_mod):
+    """tools/ref_fuzz.py: random shapes, extractor parameters, calibrations and content classes, oracle vs the reference binary
+    byte for byte; the oracle refuses exactly the shapes on which the reference's arithmetic is undefined."""
+    _ref("mono")
+    fz = _tool("ref_fuzz")
+    s = fz.run(16, 4242)
+    assert s["cases"] == 16 and s["mismatches"] == 0 and s["keypoints"] > 5000 and s["stereo_pairs"] >= 10, s
+    # the independent predicate of "the reference is undefined here" on shapes whose answer is known
+    assert not fz.reference_undefined(1242, 375, (1000, 1.2, 8, 20, 5))
+    assert fz.reference_undefined(200, 200, (1000, 1.2, 8, 20, 5))       # level 7 is 56x56: no 30-px cell fits
+    assert fz.reference_undefined(100, 400, (500, 1.2, 1, 20, 7))        # portrait 68x368 window: round(68 / 368) = 0 roots
