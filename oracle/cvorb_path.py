@@ -119,8 +119,9 @@ def detect_and_compute(image: np.ndarray, mask: np.ndarray | None, nfeatures=100
     for level in range(nlevels):
         s = F(math.pow(sf, float(level)))
         scales.append(s)
-        # written `cvRound(image.cols / scale)` in orb.cpp, but OpenCV 4.13's build evaluates both divisions as products with
-        # one float reciprocal (465 / 1.2f -> 387, 465 * (1 / 1.2f) -> 388): found by tools/cvorb_fuzz.py
+        # level size = cvRound(dim * (1.f / scale)): one float reciprocal, then a float product - what OpenCV 4.13 (cv2) is
+        # observed to compute; a float division differs where dim / scale lands on x.5 (465 / 1.2f -> 387,
+        # 465 * (1 / 1.2f) -> 388): found by tools/cvorb_fuzz.py
         inv_s = F(F(1.0) / s)
         size = (_cv_round(F(F(image.shape[1]) * inv_s)), _cv_round(F(F(image.shape[0]) * inv_s)))
         cur, cur_m = image, mask

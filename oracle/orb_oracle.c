@@ -1447,8 +1447,9 @@ int orc_cvorb_detect_and_compute(const uint8_t *img, int w, int h, ptrdiff_t pit
     const float deg2rad = (float)(3.1415926535897932384626433832795 / 180.f);
     for (int level = 0; level < nlevels && rc == 0; ++level) {
         const float scale = (float)pow(scaleFactor, (double)level);
-        /* `cvRound(image.cols / scale)` in orb.cpp; OpenCV 4.13's build evaluates the two divisions as products with one float
-         * reciprocal (465 / 1.2f -> 387, 465 * (1 / 1.2f) -> 388; pinned by tools/cvorb_fuzz.py against cv2) */
+        /* level size = cvRound(dim * (1.f / scale)): one float reciprocal, then a float product - what OpenCV 4.13 (cv2) is
+         * observed to compute; a float division differs where dim / scale lands on x.5 (465 / 1.2f -> 387,
+         * 465 * (1 / 1.2f) -> 388).  Pinned against cv2.ORB_create by tools/cvorb_fuzz.py */
         const float inv_scale = 1.0f / scale;
         const int lw = orc_cv_round((float)w * inv_scale), lh = orc_cv_round((float)h * inv_scale);
         if (lw < 2 * edge_threshold + 1 || lh < 2 * edge_threshold + 1) break; /* nothing can pass the border filter */

@@ -632,8 +632,9 @@ int cvorb_configure(pslot_cvorb &c, int w, int h, int slots)
     int cand = 0, nl = 0, tiles = 0, max_quota = 1;
     for (int l = 0; l < c.nlevels; ++l) {
         const float scale = (float)pow(c.scale_factor, (double)l);
-        // `cvRound(image.cols / scale)` in orb.cpp; OpenCV 4.13's build evaluates the two divisions as products with one float
-        // reciprocal (465 / 1.2f -> 387, 465 * (1 / 1.2f) -> 388); pinned against cv2 by tools/cvorb_fuzz.py
+        // level size = cvRound(dim * (1.f / scale)): one float reciprocal, then a float product - what OpenCV 4.13 (cv2) is observed
+        // to compute; a float division differs where dim / scale lands on x.5 (465 / 1.2f -> 387, 465 * (1 / 1.2f) -> 388).
+        // Pinned against cv2.ORB_create by tools/cvorb_fuzz.py
         const float inv_scale = 1.0f / scale;
         const int lw = cv_round((double)((float)w * inv_scale)), lh = cv_round((double)((float)h * inv_scale));
         if (lw < 2 * c.edge + 1 || lh < 2 * c.edge + 1) break; // nothing can pass the border filter from here on

@@ -275,7 +275,7 @@ def test_cvorb_stages_against_the_oracle(B, oracle_mod):
     for l in range(8):
         img = orb.stage(0, l)
         if l:
-            inv = np.float32(1) / np.float32(np.float64(np.float32(1.2)) ** l)  # one float reciprocal, as OpenCV 4.13's build
+            inv = np.float32(1) / np.float32(np.float64(np.float32(1.2)) ** l)  # one float reciprocal, as OpenCV 4.13 is observed to do
             w, h = int(np.rint(np.float32(752) * inv)), int(np.rint(np.float32(480) * inv))
             assert img.shape == (h, w)
             assert np.array_equal(img, cv2.resize(prev, (w, h), interpolation=cv2.INTER_LINEAR_EXACT)), f"level {l}"
@@ -295,7 +295,7 @@ def test_cvorb_stages_against_the_oracle(B, oracle_mod):
 
 @pytest.mark.parametrize("shape", [(465, 750), (585, 1123), (312, 561)])
 def test_cvorb_level_sizes_round_like_opencv(shape, B, oracle_mod):
-    """A dimension with dim / 1.2 = x.5 (465 * (1 / 1.2f) rounds to 388, 465 / 1.2f to 387): OpenCV 4.13 multiplies by one
+    """A dimension with dim / 1.2 = x.5 (465 * (1 / 1.2f) rounds to 388, 465 / 1.2f to 387): OpenCV 4.13 is observed to multiply by one
     float reciprocal, and every level from there on is a different image.  Found by tools/cvorb_fuzz.py."""
     from pointslot_b200.synth import synth_pair
     H, W = shape

@@ -116,8 +116,8 @@ def _equal_to_cv2(k, d, ref, rdesc, what):
 
 @pytest.mark.parametrize("shape", [(465, 750), (585, 1123), (832, 609), (312, 561), (390, 513)])
 def test_level_sizes_round_like_opencv(shape, oracle_mod):
-    """A dimension with dim / 1.2 = x.5: orb.cpp writes cvRound(cols / scale), OpenCV 4.13's build multiplies by one float
-    reciprocal instead (465 / 1.2f = 387.49997 -> 387, 465 * (1 / 1.2f) = 387.5 -> 388), and every level from there on is a
+    """A dimension with dim / 1.2 = x.5: OpenCV 4.13 is observed to multiply by one float reciprocal, cvRound(dim * (1.f / scale)),
+    not to divide (465 / 1.2f = 387.49997 -> 387, 465 * (1 / 1.2f) = 387.5 -> 388), and every level from there on is a
     different image.  Found by tools/cvorb_fuzz.py; both restatements follow the library."""
     from oracle import cvorb_path
     from pointslot_b200.synth import synth_pair
