@@ -7,7 +7,8 @@ keypoints, descriptors, mvuRight and mvDepth byte for byte.  Shapes the referenc
 30-px cell per axis, or zero quadtree roots: it divides by zero, ORBextractor.cc:784-787 / :543-545) are the ones the oracle
 rejects; they are counted, and the reference is not called on them.
 
-    python tools/ref_fuzz.py [cases=200] [seed=0] > profiles/r02_ref_fuzz.txt
+    python tools/ref_fuzz.py [cases=200] [seed=0] [--cv2] > profiles/r02_ref_fuzz.txt
+(--cv2: OpenCV 4.13 itself, through cv2, serves the five primitives to the reference's glue instead of the oracle's restatements)
 """
 import sys
 import time
@@ -26,6 +27,11 @@ F = np.float32
 VERBOSE = "-v" in sys.argv
 if VERBOSE:
     sys.argv.remove("-v")
+# who serves resize / copyMakeBorder / FAST / GaussianBlur / fastAtan2 to the reference's glue: the oracle's restatements
+# ("native", fast) or OpenCV 4.13 itself through cv2 ("cv2": the complete check - glue AND primitives against the library)
+PRIMITIVES = "cv2" if "--cv2" in sys.argv else "native"
+if "--cv2" in sys.argv:
+    sys.argv.remove("--cv2")
 CONTENT = ["synth", "noise", "smooth_noise", "checker", "posterised", "low_contrast", "saturated", "flat", "shifted_noise"]
 
 
@@ -102,7 +108,8 @@ def reference_undefined(W, H, params):
     return False
 
 
-def run(cases, seed0):
+def run(cases, seed0, primitives=None):
+    primitives = primitives or PRIMITIVES
     rng = np.random.default_rng(seed0)
     stats = dict(cases=0, rejected=0, images=0, keypoints=0, stereo_pairs=0, matches=0, mismatches=0, by_content={})
     t0 = time.time()
@@ -129,8 +136,8 @@ def run(cases, seed0):
             stats["mismatches"] += 1
             print(f"UNDER-REJECTION draw {n}: {W}x{H} {params}: the oracle accepted a shape the reference is undefined on", flush=True)
             continue
-        rL = RP.ReferenceExtractor(*params, variant="mono", primitives="native")
-        rR = RP.ReferenceExtractor(*params, variant="mono", primitives="native")
+        rL = RP.ReferenceExtractor(*params, variant="mono", primitives=primitives)
+        rR = RP.ReferenceExtractor(*params, variant="mono", primitives=primitives)
         kL, dL = rL.extract(L)
         kR, dR = rR.extract(R)
         bad = []
@@ -175,7 +182,7 @@ def main():
     # processes (chunk i uses seed seed0 + i), a few of them side by side.
     import multiprocessing as mp
     from concurrent.futures import ProcessPoolExecutor
-    chunks = [(min(CHUNK, cases - c0), seed0 + i) for i, c0 in enumerate(range(0, cases, CHUNK))]
+    chunks = [(min(CHUNK, cases - c0), seed0 + i, PRIMITIVES) for i, c0 in enumerate(range(0, cases, CHUNK))]
     t0 = time.time()
     if len(chunks) == 1:
         parts = [run(*chunks[0])]
@@ -191,7 +198,7 @@ def main():
             c = s["by_content"].setdefault(k, [0, 0, 0])
             for i in range(3):
                 c[i] += v[i]
-    print(f"oracle vs reference binary (mono build), randomised: {s['cases']} cases ({s['images']} images, seeds {seed0}..{seed0 + len(chunks) - 1}), "
+    print(f"oracle vs reference binary (mono build, primitives served by {'OpenCV 4.13 / cv2' if PRIMITIVES == 'cv2' else 'the restatements'}), randomised: {s['cases']} cases ({s['images']} images, seeds {seed0}..{seed0 + len(chunks) - 1}), "
           f"{s['rejected']} draws rejected by both (the reference's arithmetic is undefined there), {s['keypoints']} keypoints, "
           f"{s['stereo_pairs']} stereo calls with {s['matches']} matches, {s['mismatches']} mismatching cases, {time.time() - t0:.0f} s")
     print("content class: cases / keypoints / stereo matches")
