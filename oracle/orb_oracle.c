@@ -5,6 +5,12 @@
  * must round once per operation (DESIGN.md parity rule 3, "no FMA").
  *
  * Each function cites the reference lines it restates (paths under /root/reference).
+ *
+ * PINNED: against the reference's own code compiled in place into oracle/_ref (src/ORBextractor.cc unmodified, the
+ * Frame / ORBmatcher hot-path functions and the vendored DBoW2 lifted verbatim; tests/test_oracle_reference.py, test_oracle_bow.py),
+ * against OpenCV 4.13 itself through cv2 for the primitives and for cv::ORB (tests/test_oracle_cv2.py, test_oracle_cvorb.py), and by
+ * randomised sweeps of both (tools/ref_fuzz.py, ref_fuzz_frame.py, cvorb_fuzz.py; results in profiles/r02_*fuzz*.txt).
+ * Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may load it; nothing under pointslot_b200/ does.
  */
 #include "orb_oracle.h"
 
