@@ -415,7 +415,7 @@ class OracleExtractor:
         return bool(lib().orc_level_tie_sensitive(self._h, level))
 
     def tie_flags(self, level: int) -> int:
-        """bit 0: retained set depends on the heap-address tie of ORBextractor.cc:684; bit 1: only the order does."""
+        """bit 0: the retained set depends on the heap-address tie of ORBextractor.cc:684; bit 1: the order does (orb_oracle.h)."""
         return int(lib().orc_level_tie_sensitive(self._h, level))
 
 

@@ -441,13 +441,18 @@ int orc_distribute_octtree(const int *x, const int *y, const int *resp, int n,
                     divide_node(P[j].node, x, y, c);
                     push_children(&L, c, &V, &nV, &capV, NULL);
                     qlist_erase(&L, P[j].node);
-                    /* Rule C.1 bookkeeping.  bit 1: two equal-size nodes were both split in this run - under another
-                       allocator they are split in another order, which permutes the list (keypoint order, descriptor
-                       rows, stereo iR ties) without changing the set.  bit 0: the cut of :731 falls inside an
-                       equal-size run - the retained SET depends on the tie rule. */
-                    if (tie_sensitive && j + 1 < nP && P[j + 1].size == P[j].size) *tie_sensitive |= 2;
+                    /* Rule C.1 bookkeeping.  bit 1: two equal-size nodes are split in this run - under another allocator
+                       they are split in another order, which permutes the list (keypoint order, descriptor rows, stereo iR
+                       ties) without changing the set.  bit 0: the cut of :731 comes at a node that belongs to a run of
+                       equal-size nodes - the retained SET depends on the tie rule: either equal-size nodes stay unsplit
+                       behind the cut, or (cut at the end of the run) another order inside the run reaches N earlier,
+                       because a split adds 0 to 3 nodes.  A cut at a node of unique size is safe: every larger run was
+                       split completely and would be in any order.  Checked against the stock-allocator build of the
+                       reference: a level with flags == 0 is byte-identical, one without bit 0 holds the same set. */
+                    const int next_equal = j + 1 < nP && P[j + 1].size == P[j].size;
+                    if (tie_sensitive && next_equal && L.size < N) *tie_sensitive |= 2;
                     if (L.size >= N) { /* :731 */
-                        if (tie_sensitive && j > 0 && P[j - 1].size == P[j].size) *tie_sensitive |= 1;
+                        if (tie_sensitive && (next_equal || (j > 0 && P[j - 1].size == P[j].size))) *tie_sensitive |= 1;
                         break;
                     }
                 }

@@ -61,8 +61,9 @@ int orc_level_candidates(const orc_extractor *e, int level, int cap, int *x, int
 /* keypoints after DistributeOctTree + border offset, level coordinates, list order */
 int orc_level_keypoints(const orc_extractor *e, int level, int cap, int *x, int *y, int *resp, float *angle);
 /* Allocator (heap-address) sensitivity of DistributeOctTree's fine phase, ORBextractor.cc:684 (rule C.1):
- * bit 0: the cut of :731 fell inside a run of equal-size nodes (the retained SET depends on the tie rule);
- * bit 1: two equal-size nodes were both split in one run (only the list ORDER depends on the tie rule). */
+ * bit 0: the cut of :731 came at a node that belongs to a run of equal-size nodes (the retained SET depends on the tie rule);
+ * bit 1: two equal-size nodes were both split in one run (the list ORDER depends on the tie rule).
+ * Sound against the stock-allocator build of the reference: no bit 0 -> same set, no flag -> byte-identical level. */
 int orc_level_tie_sensitive(const orc_extractor *e, int level);
 
 /* Frame::ComputeStereoMatches (Frame.cc:2142-2316) on the pyramids held by eL / eR.

@@ -136,6 +136,43 @@ def test_stock_reference_differs_only_by_heap_address_tie(oracle_mod):
     assert st["ref_only"] <= 0.03 * st["ref_kps"] and st["oracle_only"] <= 0.03 * st["oracle_kps"]
 
 
+def test_tie_flags_are_sound(oracle_mod):
+    """What the oracle's per-level tie flags promise about the reference as anyone builds it (stock allocator): a level without
+    bit 0 holds the same keypoint SET, a level with no flag at all is byte-identical (keypoints and descriptor rows)."""
+    ref_path = _ref("stock")
+    import sys
+    from pathlib import Path
+    from pointslot_b200.synth import synth_pair
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "tools"))
+    import ref_fuzz as RF
+    cases = [((1000, 1.2, 8, 20, 5), list(synth_pair(1242, 375, s))) for s in range(400, 406)]
+    rng = np.random.default_rng(77)
+    n = 0
+    while len(cases) < 46:
+        n += 1
+        W, H, params, _, _ = RF.draw_case(rng)
+        if not RF.reference_undefined(W, H, params):
+            cases.append((params, list(RF.make_pair(RF.CONTENT[n % len(RF.CONTENT)], W, H, rng, n))))
+    clean = same_set = flagged_set = 0
+    for params, imgs in cases:
+        r = ref_path.ReferenceExtractor(*params, variant="stock", primitives="native")
+        o = oracle_mod.OracleExtractor(*params)
+        for img in imgs:
+            rk, rd = r.extract(img); ok, od = o.extract(img)
+            for l in range(params[2]):
+                f = o.tie_flags(l)
+                ra, oa = rk["octave"] == l, ok["octave"] == l
+                if f == 0:
+                    clean += 1
+                    assert rk[ra].tobytes() == ok[oa].tobytes() and np.array_equal(rd[ra], od[oa]), (params, l)
+                if not f & 1:
+                    same_set += 1
+                    assert set(zip(rk[ra]["x"].tolist(), rk[ra]["y"].tolist())) == set(zip(ok[oa]["x"].tolist(), ok[oa]["y"].tolist())), (params, l)
+                else:
+                    flagged_set += 1
+    assert clean > 100 and same_set > 150 and flagged_set > 100   # the three classes all occur
+
+
 # ---- Frame::ComputeStereoMatches ----------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape,params,seed,bf,fx", [((375, 1242), (2000, 1.2, 8, 20, 7), 0, 384.38148, 721.5377),
                                                        ((375, 1242), (1000, 1.2, 8, 20, 5), 11, 384.38148, 721.5377),

@@ -35,7 +35,7 @@ for name, (W, H), params, n in (("kitti 1242x375 (1000,1.2,8,20,5)", (1242, 375)
     print(f"   shared (same octave,x,y)        {st['common']}  = {100.0 * st['common'] / st['ref_kps']:.2f} % of the reference's")
     print(f"   only in reference / only oracle {st['ref_only']} / {st['oracle_only']}  = {100.0 * st['ref_only'] / st['ref_kps']:.2f} % / {100.0 * st['oracle_only'] / st['oracle_kps']:.2f} %")
     print(f"   shared keypoints whose angle/response/size/descriptor differ: {st['common_mismatch']}")
-    print(f"   oracle tie flags: order-sensitive levels {order}/{st['levels']}, cut inside an equal-size run {cut}/{st['levels']}")
+    print(f"   oracle tie flags: order-sensitive levels {order}/{st['levels']}, cut at a node of an equal-size run (set-sensitive) {cut}/{st['levels']}")
 
 # ---- FMA contraction (rule 3): the reference's own CMake flags (-O3 -march=native, GCC default -ffp-contract=fast) let the
 # compiler fuse x*b + y*a (ORBextractor.cc:119-120) and uL - scale*(...) (Frame.cc:2284-2286); the oracle is strict IEEE.
