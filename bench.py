@@ -285,7 +285,10 @@ def run_reference(args, rank):
         "impl": "reference", "metric": metric_name(cfg), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "pairs_per_step": sample, "host_threads": cores,
+        # the GPU arm's workload (the static keys of its `config`, same names and values); what this arm ran of it is `sample`
+        "config": {"workload": cfg["workload"], "name": args.config, "image": f"{cfg['W']}x{cfg['H']}", "params": list(cfg["params"]),
+                   "bf": cfg["bf"], "maxD": max_disparity(cfg)},
+        "sample": {"pairs_per_step": sample, "host_threads": cores,
                    "note": "bounded sample of the GPU arm's workload: same images, same extractor parameters, fewer pairs per step"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": arm.kind, "sample": desc},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
