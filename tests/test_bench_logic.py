@@ -75,3 +75,23 @@ def test_proportional_shards():
     b = bench.proportional_shards(10, [1, 1, 1000])
     assert sum(b) == 10 and min(b) >= 1
     assert bench.proportional_shards(8, [1.0] * 8) == [1] * 8
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's CPU arm): one JSON line with the GPU arm's metric / unit / static config keys,
+    "impl": "reference", a cpu_baseline describing the run and an e2e object without copies."""
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    cfg = bench.CONFIGS["kitti1000"]
+    assert line["impl"] == "reference" and line["metric"] == bench.metric_name(cfg) and line["unit"] == bench.UNIT
+    assert line["higher_is_better"] is True and line["steps"] == 1 and line["warmup"] == 0 and line["value"] > 0
+    assert line["config"]["workload"] == cfg["workload"] and line["config"]["params"] == list(cfg["params"])
+    assert line["config"]["maxD"] == bench.max_disparity(cfg)
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["value"] == line["value"]
+    assert line["cpu_baseline"]["cores"] >= 1 and line["sample"]["pairs_per_step"] >= 64
+    assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
