@@ -74,3 +74,47 @@ def test_record_layouts_match_the_header():
     assert C.sizeof(B.GridSpec) == 24
     import oracle
     assert oracle.MAP_POINT_DTYPE == B.MAP_POINT_DTYPE and oracle.PROJ_POINT_DTYPE == B.PROJ_POINT_DTYPE
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The boundary is a C ABI: include/pslot_orb.h compiles as strict C11 (no C++ in the signatures), a C program links against
+    libpslot_orb.so and calls the entry points that need no GPU; a compute call without a device returns an error code and a
+    message, never a result."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    from pointslot_b200 import build
+    lib = build.build()
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "pslot_orb.h"
+int main(void)
+{
+    unsigned char a[32], b[32];
+    memset(a, 0, 32); memset(b, 0xff, 32);
+    if (pslot_hamming256(a, b) != 256 || pslot_hamming256(a, a) != 0) return 2;
+    if (sizeof(pslot_keypoint) != 28) return 3;
+    printf("abi %d\n", pslot_abi_version());
+    pslot_orb *ctx = NULL;
+    int rc = pslot_orb_create(&ctx, 1000, 1.2f, 8, 20, 5, 0);
+    if (rc == PSLOT_OK) { pslot_orb_destroy(ctx); printf("device present\n"); return 0; }
+    if (ctx != NULL) return 4;
+    const char *msg = pslot_last_error();
+    if (!msg || !msg[0]) return 5;
+    printf("no device: rc=%d (%s)\n", rc, msg);
+    /* bad arguments are refused before anything else */
+    if (pslot_orb_create(NULL, 1000, 1.2f, 8, 20, 5, 0) != PSLOT_ERR_ARG) return 6;
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    cmd = ["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", str(ROOT / "include"), str(src), "-o", str(exe),
+           str(lib), f"-Wl,-rpath,{lib.parent}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "abi " in r.stdout
